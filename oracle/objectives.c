@@ -1,0 +1,107 @@
+/*
+ * oracle/objectives.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * The three synthetic objectives of SURVEY.md 8(d) as reference-ABI callbacks
+ * (f90:33-38).  Only the quartic exists in the reference (test/test.f90:630-663:
+ * f = sum x**4, f' = 4 x**3, evaluated as gfortran expands integer powers:
+ * x**4 = (x*x)*(x*x), x**3 = (x*x)*x).  Extended Rosenbrock and the diagonal
+ * quadratic are defined here; the CUDA objective kernels use the same operation
+ * order without FMA so that gradients agree bit for bit given the same x.
+ *
+ * Build with -ffp-contract=off.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdint.h>
+
+static int g_kind = ORC_OBJ_QUARTIC;
+static long long g_offset = 0, g_nglobal = 0;
+static double T0[256], T1[256], T2[256];
+static int g_tables = 0;
+
+static void build_tables(void) {
+    for (int k = 0; k < 256; k++) {
+        T0[k] = pow(10.0, 6.0 * (double)k / 16777216.0);
+        T1[k] = pow(10.0, 6.0 * (double)k / 65536.0);
+        T2[k] = pow(10.0, 6.0 * (double)k / 256.0);
+    }
+    g_tables = 1;
+}
+
+/* d_i = 10^(6 q / 2^24), q = floor(i 2^24 / (n-1)): log-uniform in [1, 1e6], built from
+ * three table factors with exact IEEE multiplies so host and device agree bitwise. */
+double orc_diag_coeff(long long i, long long n_global) {
+    if (!g_tables) build_tables();
+    if (n_global <= 1) return 1.0;
+    uint64_t q = ((uint64_t)i << 24) / (uint64_t)(n_global - 1);
+    if (q >> 24) return 1.0e6;
+    return T2[(q >> 16) & 255] * T1[(q >> 8) & 255] * T0[q & 255];
+}
+
+void orc_obj_select(int kind, long long offset, long long n_global) {
+    g_kind = kind; g_offset = offset; g_nglobal = n_global;
+}
+
+static double splitmix_u(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+void orc_obj_start(int start_kind, unsigned long long seed, double *x, long long offset, long long n,
+                   long long n_global) {
+    (void)n_global;
+    for (long long k = 0; k < n; k++) {
+        const long long i = offset + k;
+        const double u = splitmix_u((uint64_t)i + seed);
+        switch (start_kind) {
+        case ORC_START_QUARTIC_U: x[k] = u; break;
+        case ORC_START_ROSEN_STD: x[k] = (i & 1) ? 1.0 : -1.2; break;
+        case ORC_START_ROSEN_PERT: x[k] = ((i & 1) ? 1.0 : -1.2) + 0.1 * (u - 0.5); break;
+        default: x[k] = 0.0; break;
+        }
+    }
+}
+
+static int eval(double *fx, double *g, const double *x, int n) {
+    double f = 0.0;
+    if (g_kind == ORC_OBJ_QUARTIC) {
+        for (int i = 0; i < n; i++) {
+            const double x2 = x[i] * x[i];
+            if (fx) f = f + x2 * x2;
+            if (g) g[i] = 4.0 * (x2 * x[i]);
+        }
+    } else if (g_kind == ORC_OBJ_ROSENBROCK) {
+        /* pairs (2j, 2j+1) in GLOBAL indexing; shards start on even offsets */
+        int i = 0;
+        for (; i + 1 < n; i += 2) {
+            const double a = x[i], b = x[i + 1];
+            const double t1 = b - a * a, t2 = 1.0 - a;
+            if (fx) f = f + ((100.0 * t1) * t1 + t2 * t2);
+            if (g) { g[i] = (-400.0 * a) * t1 - 2.0 * t2; g[i + 1] = 200.0 * t1; }
+        }
+        if (i < n) { /* unpaired last element of an odd-length problem */
+            const double t2 = 1.0 - x[i];
+            if (fx) f = f + t2 * t2;
+            if (g) g[i] = -2.0 * t2;
+        }
+    } else {
+        for (int i = 0; i < n; i++) {
+            const double d = orc_diag_coeff(g_offset + i, g_nglobal);
+            const double t = x[i] - 1.0;
+            if (fx) f = f + ((0.5 * d) * t) * t;
+            if (g) g[i] = d * t;
+        }
+    }
+    if (fx) *fx = f;
+    return 0;
+}
+
+void orc_obj_f(double *fx, const double *x, const int *dim) { eval(fx, 0, x, *dim); }
+void orc_obj_fd(double *fdx, const double *x, const int *dim) { eval(0, fdx, x, *dim); }
+int orc_obj_f_fd(double *fx, double *fdx, const double *x, const int *dim) {
+    return eval(fx, fdx, x, *dim);
+}

@@ -1,0 +1,108 @@
+/*
+ * oracle/oracle.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C, strict IEEE: -O2 -ffp-contract=off, sequential sums)
+ * of the reference's large-dimension unconstrained-optimizer path in
+ * /root/reference/source/NonlinearOptimization.f90:
+ *     ConjugateGradient        f90:193-394
+ *     LBFGS                    f90:398-625
+ *     Wolfe / Wolfe_fdwithf    f90:1286-1459
+ *     StrongWolfe / _fdwithf   f90:1462-1698
+ *     ConjugateGradient_basic  f90:2249-2346
+ *
+ * PARITY UNPINNED: the reference cannot be compiled here (no Fortran compiler,
+ * no MKL: SURVEY.md F1/F2) and its tests hold no golden vectors for this path
+ * (F8).  This restatement is pinned only by (i) an independent NumPy
+ * transcription (oracle/oracle_np.py) that must agree with it, (ii) closed-form
+ * minimisers and scipy, (iii) structural checks.  See DESIGN.md.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.  The product (libflgpu.so) never does.
+ *
+ * Calling convention mirrors gfortran's for the reference routines: every
+ * argument by reference, an absent OPTIONAL is a NULL pointer, LOGICAL is a
+ * 4-byte int (non-zero = true), CHARACTER(*) is char* + trailing hidden length.
+ */
+#ifndef FLGPU_ORACLE_H
+#define FLGPU_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* user callbacks, f90:33-38; C shapes as cpp/NonlinearOptimization.hpp:281-284 */
+typedef void (*orc_f_t)(double *fx, const double *x, const int *dim);
+typedef void (*orc_fd_t)(double *fdx, const double *x, const int *dim);
+typedef int (*orc_ffd_t)(double *fx, double *fdx, const double *x, const int *dim);
+
+/* Called after every line search of an outer iteration (iteration 0 = the
+ * steepest-descent step of LBFGS / first CG step).  p = direction searched along,
+ * x, g = point and gradient accepted, a = accepted step, phid0 = phi'(0). */
+typedef void (*orc_trace_t)(void *user, int iter, int dim, const double *p, const double *x,
+                            const double *g, double a, double fx, double phid0, long trials);
+
+typedef struct {
+    long n_f, n_fd, n_ffd;  /* callback invocations */
+    long n_trials;          /* x = x0 + a*p formations */
+    long n_linesearch;      /* line searches run */
+    long n_iter;            /* outer iterations completed (accepted steps) */
+    long n_quirk_f9;        /* times StrongWolfe fell through f90:1511-1512 */
+    int status;             /* 0 converged(g), 1 step converged, 2 max iteration, 3 initial g small */
+} orc_stats_t;
+
+void orc_set_trace(orc_trace_t cb, void *user);
+/* 0 = sequential double (reference semantics), 1 = long double accumulate,
+ * 2 = pairwise double.  Modes 1/2 exist only to bound summation noise. */
+void orc_set_sum_mode(int mode);
+void orc_get_stats(orc_stats_t *out);
+
+/* f90:398-625 */
+void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim, const int *Memory, orc_ffd_t f_fd,
+               const int *Strong, const int *Warning, const int *MaxIteration, const double *Precision,
+               const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
+               const double *Increment);
+/* f90:193-394 */
+void orc_conjugategradient(orc_f_t f, orc_fd_t fd, double *x, const int *dim, const char *Method,
+                           orc_ffd_t f_fd, const int *Strong, const int *Warning,
+                           const int *MaxIteration, const double *Precision,
+                           const double *MinStepLength, const double *WolfeConst1,
+                           const double *WolfeConst2, const double *Increment, int len_Method);
+/* f90:2249-2346 (all arguments mandatory, no clamps) */
+void orc_conjugategradient_basic(orc_f_t f, orc_fd_t fd, double *x, const int *dim, const char *Method,
+                                 const int *Strong, const int *Warning, const int *MaxIteration,
+                                 const double *Precision, const double *MinStepLength,
+                                 const double *WolfeConst1, const double *WolfeConst2,
+                                 const double *Increment, int len_Method);
+
+/* line searchers, f90:1286,1373,1462,1582 (exported like the reference's module procedures) */
+void orc_wolfe(const double *c1, const double *c2, orc_f_t f, orc_fd_t fd, double *x, double *a,
+               const double *p, double *fx, const double *phid0, double *fdx, const int *dim,
+               const double *Increment);
+void orc_wolfe_fdwithf(const double *c1, const double *c2, orc_f_t f, orc_fd_t fd, orc_ffd_t f_fd,
+                       double *x, double *a, const double *p, double *fx, const double *phid0,
+                       double *fdx, const int *dim, const double *Increment);
+void orc_strongwolfe(const double *c1, const double *c2, orc_f_t f, orc_fd_t fd, double *x, double *a,
+                     const double *p, double *fx, const double *phid0, double *fdx, const int *dim,
+                     const double *Increment);
+void orc_strongwolfe_fdwithf(const double *c1, const double *c2, orc_f_t f, orc_fd_t fd,
+                             orc_ffd_t f_fd, double *x, double *a, const double *p, double *fx,
+                             const double *phid0, double *fdx, const int *dim,
+                             const double *Increment);
+
+/* ---- synthetic objectives (oracle/objectives.c), SURVEY.md 8(d) ---- */
+enum { ORC_OBJ_QUARTIC = 0, ORC_OBJ_ROSENBROCK = 1, ORC_OBJ_DIAGQUAD = 2 };
+enum { ORC_START_QUARTIC_U = 0, ORC_START_ROSEN_STD = 1, ORC_START_ROSEN_PERT = 2, ORC_START_ZERO = 3 };
+/* Select the objective the three callbacks below evaluate.  offset/n_global let a
+ * row shard be evaluated (index-dependent objectives). */
+void orc_obj_select(int kind, long long offset, long long n_global);
+void orc_obj_f(double *fx, const double *x, const int *dim);
+void orc_obj_fd(double *fdx, const double *x, const int *dim);
+int orc_obj_f_fd(double *fx, double *fdx, const double *x, const int *dim);
+void orc_obj_start(int start_kind, unsigned long long seed, double *x, long long offset, long long n,
+                   long long n_global);
+double orc_diag_coeff(long long i, long long n_global);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

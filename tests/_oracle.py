@@ -1,0 +1,178 @@
+"""ctypes loader for oracle/liboracle.so (TEST INFRASTRUCTURE: the checker, never the product).
+
+Builds the library on demand with oracle/Makefile.  Used by tests/, by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs only.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
+
+OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD = 0, 1, 2
+START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO = 0, 1, 2, 3
+
+F_T = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int))
+FD_T = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int))
+FFD_T = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                    C.POINTER(C.c_int))
+TRACE_T = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                      C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double, C.c_long)
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_f", C.c_long), ("n_fd", C.c_long), ("n_ffd", C.c_long), ("n_trials", C.c_long),
+                ("n_linesearch", C.c_long), ("n_iter", C.c_long), ("n_quirk_f9", C.c_long),
+                ("status", C.c_int)]
+
+
+def build(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("oracle.c", "objectives.c", "oracle.h", "Makefile")]
+    stale = (not os.path.exists(LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", ORACLE_DIR, "-B", "liboracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_diag_coeff.restype = C.c_double
+        _lib.orc_diag_coeff.argtypes = [C.c_longlong, C.c_longlong]
+        _lib.orc_obj_select.argtypes = [C.c_int, C.c_longlong, C.c_longlong]
+        _lib.orc_obj_start.argtypes = [C.c_int, C.c_ulonglong, C.c_void_p, C.c_longlong, C.c_longlong,
+                                       C.c_longlong]
+        _lib.orc_set_trace.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.orc_set_sum_mode.argtypes = [C.c_int]
+    return _lib
+
+
+def _opt(ctype, v):
+    return None if v is None else C.byref(ctype(v))
+
+
+def start_vector(start_kind, n, seed=0, offset=0, n_global=None):
+    x = np.empty(n, dtype=np.float64)
+    lib().orc_obj_start(start_kind, seed, x.ctypes.data, offset, n, n if n_global is None else n_global)
+    return x
+
+
+def builtin_callbacks(kind, offset=0, n_global=0):
+    L = lib()
+    L.orc_obj_select(kind, offset, n_global)
+    return (C.cast(L.orc_obj_f, C.c_void_p), C.cast(L.orc_obj_fd, C.c_void_p),
+            C.cast(L.orc_obj_f_fd, C.c_void_p))
+
+
+class Trace:
+    """Collects (iter, p, x, g, a, f, phid0, trials) after every line search."""
+
+    def __init__(self, keep_vectors=True, max_vec_iters=10**9):
+        self.rows = []
+        self.p, self.x, self.g = [], [], []
+        self.keep = keep_vectors
+        self.max_vec_iters = max_vec_iters
+        self._cb = TRACE_T(self._on)
+
+    def _on(self, user, it, dim, p, x, g, a, fx, phid0, trials):
+        self.rows.append((it, a, fx, phid0, trials))
+        if self.keep and it < self.max_vec_iters:
+            self.p.append(np.ctypeslib.as_array(p, (dim,)).copy())
+            self.x.append(np.ctypeslib.as_array(x, (dim,)).copy())
+            self.g.append(np.ctypeslib.as_array(g, (dim,)).copy())
+
+    def install(self):
+        lib().orc_set_trace(C.cast(self._cb, C.c_void_p), None)
+
+    @staticmethod
+    def uninstall():
+        lib().orc_set_trace(None, None)
+
+
+def stats():
+    s = Stats()
+    lib().orc_get_stats(C.byref(s))
+    return s
+
+
+def lbfgs(cbs, x, Memory=None, use_ffd=False, Strong=None, Warning=None, MaxIteration=None,
+          Precision=None, MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None,
+          trace=None, sum_mode=0):
+    """orc_lbfgs with the reference's optional-argument semantics (None = absent)."""
+    L = lib()
+    f, fd, ffd = cbs
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = C.c_int(x.size)
+    L.orc_set_sum_mode(sum_mode)
+    if trace is not None:
+        trace.install()
+    try:
+        L.orc_lbfgs(f, fd, x.ctypes.data_as(C.c_void_p), C.byref(n), _opt(C.c_int, Memory),
+                    ffd if use_ffd else None, _opt(C.c_int, None if Strong is None else int(Strong)),
+                    _opt(C.c_int, None if Warning is None else int(Warning)),
+                    _opt(C.c_int, MaxIteration), _opt(C.c_double, Precision),
+                    _opt(C.c_double, MinStepLength), _opt(C.c_double, WolfeConst1),
+                    _opt(C.c_double, WolfeConst2), _opt(C.c_double, Increment))
+    finally:
+        Trace.uninstall()
+        L.orc_set_sum_mode(0)
+    return x, stats()
+
+
+def cg(cbs, x, Method=None, use_ffd=False, Strong=None, Warning=None, MaxIteration=None,
+       Precision=None, MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None,
+       trace=None, sum_mode=0):
+    L = lib()
+    f, fd, ffd = cbs
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = C.c_int(x.size)
+    m = None if Method is None else Method.encode()
+    L.orc_set_sum_mode(sum_mode)
+    if trace is not None:
+        trace.install()
+    try:
+        L.orc_conjugategradient(f, fd, x.ctypes.data_as(C.c_void_p), C.byref(n), m,
+                                ffd if use_ffd else None,
+                                _opt(C.c_int, None if Strong is None else int(Strong)),
+                                _opt(C.c_int, None if Warning is None else int(Warning)),
+                                _opt(C.c_int, MaxIteration), _opt(C.c_double, Precision),
+                                _opt(C.c_double, MinStepLength), _opt(C.c_double, WolfeConst1),
+                                _opt(C.c_double, WolfeConst2), _opt(C.c_double, Increment),
+                                C.c_int(0 if m is None else len(m)))
+    finally:
+        Trace.uninstall()
+        L.orc_set_sum_mode(0)
+    return x, stats()
+
+
+def cg_basic(cbs, x, Method="DY", Strong=True, Warning=True, MaxIteration=1000, Precision=1e-15,
+             MinStepLength=1e-15, WolfeConst1=1e-4, WolfeConst2=0.45, Increment=1.05, trace=None):
+    L = lib()
+    f, fd, _ = cbs
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = C.c_int(x.size)
+    m = Method.encode()
+    if trace is not None:
+        trace.install()
+    try:
+        L.orc_conjugategradient_basic(f, fd, x.ctypes.data_as(C.c_void_p), C.byref(n), m,
+                                      C.byref(C.c_int(-1 if Strong else 0)),
+                                      C.byref(C.c_int(-1 if Warning else 0)),
+                                      C.byref(C.c_int(MaxIteration)), C.byref(C.c_double(Precision)),
+                                      C.byref(C.c_double(MinStepLength)),
+                                      C.byref(C.c_double(WolfeConst1)), C.byref(C.c_double(WolfeConst2)),
+                                      C.byref(C.c_double(Increment)), C.c_int(len(m)))
+    finally:
+        Trace.uninstall()
+    return x, stats()
