@@ -1,0 +1,74 @@
+"""ctypes mirror of include/flgpu.h (structs, callback types, constants)."""
+import ctypes as C
+
+# enums
+CG_DY, CG_PR = 0, 1
+SPACE_HOST, SPACE_DEVICE = 0, 1
+CONVERGED, STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER = 0, 1, 2, 3, 4
+OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD = 0, 1, 2
+START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO = 0, 1, 2, 3
+
+
+class EvalCtx(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("stream", C.c_void_p), ("offset", C.c_int64),
+                ("n_global", C.c_int64), ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int)]
+
+
+F_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_void_p, C.c_void_p, C.c_int64)
+FD_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_void_p, C.c_void_p, C.c_int64)
+F_FD_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+# reference callback ABI (f90:33-38)
+REF_F_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int))
+REF_FD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
+REF_F_FD_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
+
+
+class Problem(C.Structure):
+    _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p)]
+
+
+class IterInfo(C.Structure):
+    _fields_ = [("iteration", C.c_int64), ("n_local", C.c_int64), ("step", C.c_double),
+                ("f", C.c_double), ("phid0", C.c_double), ("trials", C.c_int64),
+                ("p_dev", C.c_void_p), ("x_dev", C.c_void_p), ("g_dev", C.c_void_p),
+                ("stream", C.c_void_p)]
+
+
+OBSERVER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(IterInfo))
+
+
+class Options(C.Structure):
+    _fields_ = [("memory", C.c_int), ("method", C.c_int), ("strong", C.c_int), ("warning", C.c_int),
+                ("max_iteration", C.c_int), ("precision", C.c_double), ("min_step_length", C.c_double),
+                ("wolfe_c1", C.c_double), ("wolfe_c2", C.c_double), ("increment", C.c_double),
+                ("no_clamp", C.c_int), ("stream", C.c_void_p), ("comm", C.c_void_p),
+                ("offset", C.c_int64), ("n_global", C.c_int64), ("observer", C.c_void_p),
+                ("observer_user", C.c_void_p), ("time_kernels", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("status", C.c_int), ("n_f", C.c_int64), ("n_fd", C.c_int64),
+                ("n_f_fd", C.c_int64), ("n_trials", C.c_int64), ("n_f_only_trials", C.c_int64),
+                ("n_linesearch", C.c_int64), ("gpu_launches", C.c_int64), ("host_syncs", C.c_int64),
+                ("f", C.c_double), ("gnorm2", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def apply_options(o, **kw):
+    """Set Options fields from reference-style keyword names (None = leave default)."""
+    names = {"Memory": "memory", "Method": "method", "Strong": "strong", "Warning": "warning",
+             "MaxIteration": "max_iteration", "Precision": "precision", "MinStepLength": "min_step_length",
+             "WolfeConst1": "wolfe_c1", "WolfeConst2": "wolfe_c2", "Increment": "increment"}
+    for k, v in kw.items():
+        if v is None:
+            continue
+        field = names.get(k, k)
+        if field == "method" and isinstance(v, str):
+            v = {"DY": CG_DY, "PR": CG_PR}[v]
+        if field in ("strong", "warning"):
+            v = int(bool(v))
+        setattr(o, field, v)
+    return o

@@ -1,0 +1,301 @@
+// api.cu -- the C-ABI of libflgpu.so (include/flgpu.h): flgpu_* entry points and the reference's
+// own compiled symbol names (__nonlinearoptimization_MOD_* / nonlinearoptimization_mp_*_).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "backend_cuda.cuh"
+#include "driver.hpp"
+
+using namespace flgpu;
+
+namespace {
+
+struct ThreadState {
+    void *stream = nullptr;
+    int device = -1;
+    flgpu_stats last{};
+    std::vector<KernelTime> times;
+    flgpu_observer_fn observer = nullptr;
+    void *observer_user = nullptr;
+};
+thread_local ThreadState tls;
+
+std::atomic<int> g_x_space{-1}, g_cb_space{-1};
+
+int space_from_env(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    if (!v) return dflt;
+    if (!std::strcmp(v, "host") || !std::strcmp(v, "HOST")) return FLGPU_SPACE_HOST;
+    if (!std::strcmp(v, "device") || !std::strcmp(v, "DEVICE")) return FLGPU_SPACE_DEVICE;
+    return dflt;
+}
+int x_space_now() {
+    int v = g_x_space.load();
+    return v >= 0 ? v : space_from_env("FLGPU_X_SPACE", FLGPU_SPACE_HOST);
+}
+int cb_space_now() {
+    int v = g_cb_space.load();
+    return v >= 0 ? v : space_from_env("FLGPU_CALLBACK_SPACE", FLGPU_SPACE_DEVICE);
+}
+
+int run(bool cg, const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n, int x_space,
+        flgpu_stats *stats) {
+    require_device();
+    if (!prob || !prob->f || !prob->fd) fatal("flgpu: f and fd callbacks are required (f90:40)");
+    if (n < 0) fatal("flgpu: negative dimension");
+    CudaBackend B(*prob, n, *opt);
+    Params P = params_from_options(*opt, cg, prob->f_fd != nullptr);
+    ThreadState saved = tls;
+    tls.stream = B.stream_handle();
+    FLGPU_CUDA_CHECK(cudaGetDevice(&tls.device));
+    flgpu_stats st;
+    if (cg) run_cg(B, P, x, x_space, &st);
+    else run_lbfgs(B, P, x, x_space, &st);
+    B.resolve_times();
+    tls.stream = saved.stream;
+    tls.device = saved.device;
+    tls.last = st;
+    tls.times = B.times;
+    if (stats) *stats = st;
+    return 0;
+}
+
+// ---- adapter: reference-ABI callbacks (f90:33-38) behind the 64-bit device-callback interface
+struct RefAdapter {
+    flgpu_ref_f_fn f;
+    flgpu_ref_fd_fn fd;
+    flgpu_ref_f_fd_fn f_fd;
+    int cb_space;
+    double *xh = nullptr, *gh = nullptr;  // pinned staging (callback space HOST)
+};
+void to_host(const RefAdapter *A, const double *x_dev, int64_t n, cudaStream_t s) {
+    FLGPU_CUDA_CHECK(cudaMemcpyAsync(A->xh, x_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+void ad_f(const flgpu_eval_ctx *c, double *f_dev, const double *x, int64_t n) {
+    const RefAdapter *A = (const RefAdapter *)c->user;
+    cudaStream_t s = (cudaStream_t)c->stream;
+    int dim = (int)n;
+    double fx = 0.0;
+    if (A->cb_space == FLGPU_SPACE_HOST) { to_host(A, x, n, s); A->f(&fx, A->xh, &dim); }
+    else A->f(&fx, x, &dim);
+    k::set_scalar_kernel<<<1, 1, 0, s>>>(f_dev, fx);
+}
+void ad_fd(const flgpu_eval_ctx *c, double *g, const double *x, int64_t n) {
+    const RefAdapter *A = (const RefAdapter *)c->user;
+    cudaStream_t s = (cudaStream_t)c->stream;
+    int dim = (int)n;
+    if (A->cb_space == FLGPU_SPACE_HOST) {
+        to_host(A, x, n, s);
+        A->fd(A->gh, A->xh, &dim);
+        FLGPU_CUDA_CHECK(cudaMemcpyAsync(g, A->gh, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+        A->fd(g, x, &dim);
+    }
+}
+void ad_ffd(const flgpu_eval_ctx *c, double *f_dev, double *g, const double *x, int64_t n) {
+    const RefAdapter *A = (const RefAdapter *)c->user;
+    cudaStream_t s = (cudaStream_t)c->stream;
+    int dim = (int)n;
+    double fx = 0.0;
+    if (A->cb_space == FLGPU_SPACE_HOST) {
+        to_host(A, x, n, s);
+        (void)A->f_fd(&fx, A->gh, A->xh, &dim);
+        FLGPU_CUDA_CHECK(cudaMemcpyAsync(g, A->gh, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    } else {
+        (void)A->f_fd(&fx, g, x, &dim);
+    }
+    k::set_scalar_kernel<<<1, 1, 0, s>>>(f_dev, fx);
+}
+
+void run_ref(bool cg, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
+             flgpu_options &o) {
+    require_device();
+    RefAdapter A;
+    A.f = f; A.fd = fd; A.f_fd = f_fd; A.cb_space = cb_space_now();
+    if (A.cb_space == FLGPU_SPACE_HOST) {
+        FLGPU_CUDA_CHECK(cudaMallocHost((void **)&A.xh, sizeof(double) * (size_t)(dim > 0 ? dim : 1)));
+        FLGPU_CUDA_CHECK(cudaMallocHost((void **)&A.gh, sizeof(double) * (size_t)(dim > 0 ? dim : 1)));
+    }
+    flgpu_problem prob;
+    prob.f = ad_f; prob.fd = ad_fd; prob.f_fd = f_fd ? ad_ffd : nullptr; prob.user = &A;
+    o.observer = tls.observer;
+    o.observer_user = tls.observer_user;
+    run(cg, &prob, &o, x, dim, x_space_now(), nullptr);
+    if (A.xh) cudaFreeHost(A.xh);
+    if (A.gh) cudaFreeHost(A.gh);
+}
+
+// Fortran OPTIONAL -> options (NULL = absent keeps the default, f90:417-434 / 212-229)
+void fill_optional(flgpu_options &o, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
+                   const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+                   const double *WolfeConst2, const double *Increment) {
+    if (Strong) o.strong = *Strong != 0;
+    if (Warning) o.warning = *Warning != 0;
+    if (MaxIteration) o.max_iteration = *MaxIteration;
+    if (Precision) o.precision = *Precision;
+    if (MinStepLength) o.min_step_length = *MinStepLength;
+    if (WolfeConst1) o.wolfe_c1 = *WolfeConst1;
+    if (WolfeConst2) o.wolfe_c2 = *WolfeConst2;
+    if (Increment) o.increment = *Increment;
+}
+
+// character(*) Method compared as 'DY' / 'PR' (f90:207,214,240,311,345; f90:2273-2297)
+int parse_method(const char *Method, int len, bool whole_string) {
+    char t[2] = {' ', ' '};
+    if (Method) { if (len > 0) t[0] = Method[0]; if (len > 1) t[1] = Method[1]; }
+    bool tail_blank = true;
+    if (whole_string && Method) for (int j = 2; j < len; j++) if (Method[j] != ' ') tail_blank = false;
+    if (t[0] == 'D' && t[1] == 'Y' && tail_blank) return FLGPU_CG_DY;
+    if (t[0] == 'P' && t[1] == 'R' && tail_blank) return FLGPU_CG_PR;
+    std::string name(Method ? Method : "", Method ? (size_t)(len > 0 ? len : 0) : 0);
+    std::printf(" Program abort: unsupported conjugate gradient method %s\n", name.c_str());
+    std::fflush(stdout);
+    std::exit(1);  // the reference executes `stop` (f90:345)
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *flgpu_version(void) { return "flgpu 0.1 (sm_100a, fp64)"; }
+
+void flgpu_options_default(flgpu_options *o, int for_cg) {
+    std::memset(o, 0, sizeof *o);
+    o->memory = 10;
+    o->method = FLGPU_CG_DY;
+    o->strong = 1;
+    o->warning = 1;
+    o->max_iteration = 1000;
+    o->precision = 1e-15;
+    o->min_step_length = 1e-15;
+    o->wolfe_c1 = 1e-4;
+    o->wolfe_c2 = for_cg ? 0.45 : 0.9;
+    o->increment = 1.05;
+}
+
+int flgpu_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local, int x_space,
+                flgpu_stats *stats) {
+    return run(false, prob, opt, x, n_local, x_space, stats);
+}
+int flgpu_conjugate_gradient(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local,
+                             int x_space, flgpu_stats *stats) {
+    return run(true, prob, opt, x, n_local, x_space, stats);
+}
+
+void flgpu_set_x_space(int space) { g_x_space.store(space); }
+void flgpu_set_callback_space(int space) { g_cb_space.store(space); }
+void *flgpu_current_stream(void) { return tls.stream; }
+int flgpu_current_device(void) { return tls.device; }
+void flgpu_last_stats(flgpu_stats *out) { *out = tls.last; }
+void flgpu_set_observer(flgpu_observer_fn fn, void *user) { tls.observer = fn; tls.observer_user = user; }
+
+int flgpu_kernel_times(const char **names, double *ms, int64_t *launches, double *bytes, int cap) {
+    int n = 0;
+    for (auto &kt : tls.times) {
+        if (n >= cap) break;
+        names[n] = kt.name.c_str();
+        ms[n] = kt.ms;
+        launches[n] = kt.launches;
+        bytes[n] = kt.bytes;
+        n++;
+    }
+    return n;
+}
+
+void *flgpu_malloc(size_t bytes) {
+    require_device();
+    void *p = nullptr;
+    FLGPU_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1));
+    return p;
+}
+void flgpu_free(void *dev_ptr) { if (dev_ptr) cudaFree(dev_ptr); }
+int flgpu_memcpy(void *dst, const void *src, size_t bytes, int dst_space, int src_space, void *stream) {
+    require_device();
+    cudaMemcpyKind kind = dst_space == FLGPU_SPACE_DEVICE
+                              ? (src_space == FLGPU_SPACE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                              : (src_space == FLGPU_SPACE_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    FLGPU_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, kind, (cudaStream_t)stream));
+    FLGPU_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+int flgpu_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+// ---------------------------------------------------------------- Fortran ABI
+void __nonlinearoptimization_MOD_lbfgs(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
+                                       const int *Memory, flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+                                       const int32_t *Warning, const int *MaxIteration, const double *Precision,
+                                       const double *MinStepLength, const double *WolfeConst1,
+                                       const double *WolfeConst2, const double *Increment) {
+    flgpu_options o;
+    flgpu_options_default(&o, 0);
+    if (Memory) o.memory = *Memory;
+    fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
+    run_ref(false, f, fd, f_fd, x, *dim, o);
+}
+
+void __nonlinearoptimization_MOD_conjugategradient(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
+                                                   const char *Method, flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+                                                   const int32_t *Warning, const int *MaxIteration,
+                                                   const double *Precision, const double *MinStepLength,
+                                                   const double *WolfeConst1, const double *WolfeConst2,
+                                                   const double *Increment, int len_Method) {
+    flgpu_options o;
+    flgpu_options_default(&o, 1);
+    if (Method) o.method = parse_method(Method, len_Method, false);
+    fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
+    run_ref(true, f, fd, f_fd, x, *dim, o);
+}
+
+void __nonlinearoptimization_MOD_conjugategradient_basic(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x,
+                                                         const int *dim, const char *Method, const int32_t *Strong,
+                                                         const int32_t *Warning, const int *MaxIteration,
+                                                         const double *Precision, const double *MinStepLength,
+                                                         const double *WolfeConst1, const double *WolfeConst2,
+                                                         const double *Increment, int len_Method) {
+    flgpu_options o;
+    flgpu_options_default(&o, 1);
+    o.method = parse_method(Method, len_Method, true);
+    o.no_clamp = 1;  // f90:2265-2278: tunables used as given
+    fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
+    run_ref(true, f, fd, nullptr, x, *dim, o);
+}
+
+void nonlinearoptimization_mp_lbfgs_(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
+                                     const int *Memory, flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+                                     const int32_t *Warning, const int *MaxIteration, const double *Precision,
+                                     const double *MinStepLength, const double *WolfeConst1,
+                                     const double *WolfeConst2, const double *Increment) {
+    __nonlinearoptimization_MOD_lbfgs(f, fd, x, dim, Memory, f_fd, Strong, Warning, MaxIteration, Precision,
+                                      MinStepLength, WolfeConst1, WolfeConst2, Increment);
+}
+void nonlinearoptimization_mp_conjugategradient_(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
+                                                 const char *Method, flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+                                                 const int32_t *Warning, const int *MaxIteration,
+                                                 const double *Precision, const double *MinStepLength,
+                                                 const double *WolfeConst1, const double *WolfeConst2,
+                                                 const double *Increment, int len_Method) {
+    __nonlinearoptimization_MOD_conjugategradient(f, fd, x, dim, Method, f_fd, Strong, Warning, MaxIteration,
+                                                  Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment,
+                                                  len_Method);
+}
+void nonlinearoptimization_mp_conjugategradient_basic_(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x,
+                                                       const int *dim, const char *Method, const int32_t *Strong,
+                                                       const int32_t *Warning, const int *MaxIteration,
+                                                       const double *Precision, const double *MinStepLength,
+                                                       const double *WolfeConst1, const double *WolfeConst2,
+                                                       const double *Increment, int len_Method) {
+    __nonlinearoptimization_MOD_conjugategradient_basic(f, fd, x, dim, Method, Strong, Warning, MaxIteration,
+                                                        Precision, MinStepLength, WolfeConst1, WolfeConst2,
+                                                        Increment, len_Method);
+}
+
+}  // extern "C"

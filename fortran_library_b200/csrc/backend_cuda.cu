@@ -1,0 +1,391 @@
+// backend_cuda.cu -- CudaBackend: memory, launch geometry, stream ordering, NCCL exchange.
+#include "backend_cuda.cuh"
+
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace flgpu {
+
+void cuda_fail(const char *what, cudaError_t e, const char *file, int line) {
+    std::fprintf(stderr, "flgpu: CUDA failure %s (%s) at %s:%d -- no CPU fallback exists, aborting\n",
+                 cudaGetErrorString(e), what, file, line);
+    std::abort();
+}
+void fatal(const char *msg) {
+    std::fprintf(stderr, "flgpu: %s\n", msg);
+    std::abort();
+}
+int require_device() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        std::fprintf(stderr,
+                     "flgpu: no usable CUDA device (%s). This library is CUDA-only (sm_100a); there is no "
+                     "CPU fallback.\n",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        std::abort();
+    }
+    int dev = 0;
+    FLGPU_CUDA_CHECK(cudaGetDevice(&dev));
+    return dev;
+}
+
+// --------------------------------------------------------------------------- NCCL via dlopen
+namespace {
+struct UniqueId { char internal[128]; };
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi &nccl() {
+    static NcclApi api;
+    if (!api.handle) {
+        api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.handle) fatal("multi-GPU run requested but libnccl.so.2 cannot be loaded");
+        api.GetUniqueId = (int (*)(UniqueId *))dlsym(api.handle, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void **, int, UniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+        api.CommDestroy = (int (*)(void *))dlsym(api.handle, "ncclCommDestroy");
+        api.GetErrorString = (const char *(*)(int))dlsym(api.handle, "ncclGetErrorString");
+        if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy)
+            fatal("libnccl.so.2 lacks a required symbol");
+    }
+    return api;
+}
+void nccl_check(int rc, const char *what) {
+    if (rc != 0) {
+        std::fprintf(stderr, "flgpu: NCCL failure in %s: %s -- aborting\n", what,
+                     nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+        std::abort();
+    }
+}
+}  // namespace
+
+void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s) {
+    nccl_check(nccl().AllGather(send, recv, count, /*ncclFloat64*/ 8, c->nccl_comm, s), "ncclAllGather");
+}
+
+}  // namespace flgpu
+
+extern "C" int flgpu_comm_unique_id(void *id128) {
+    flgpu::require_device();
+    flgpu::UniqueId id;
+    flgpu::nccl_check(flgpu::nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(id128, &id, 128);
+    return 0;
+}
+extern "C" flgpu_comm *flgpu_comm_create(const void *id128, int rank, int nranks) {
+    flgpu::require_device();
+    flgpu_comm *c = new flgpu_comm;
+    c->rank = rank;
+    c->nranks = nranks;
+    flgpu::UniqueId id;
+    std::memcpy(&id, id128, 128);
+    flgpu::nccl_check(flgpu::nccl().CommInitRank(&c->nccl_comm, nranks, id, rank), "ncclCommInitRank");
+    return c;
+}
+extern "C" void flgpu_comm_destroy(flgpu_comm *c) {
+    if (!c) return;
+    if (c->nccl_comm) flgpu::nccl().CommDestroy(c->nccl_comm);
+    delete c;
+}
+
+namespace flgpu {
+
+// --------------------------------------------------------------------------- CudaBackend
+CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgpu_options &opt)
+    : prob(prob_) {
+    device = require_device();
+    n = n_local;
+    comm = opt.comm;
+    timing = opt.time_kernels != 0;
+    cudaDeviceProp props;
+    FLGPU_CUDA_CHECK(cudaGetDeviceProperties(&props, device));
+    num_sms = props.multiProcessorCount;
+    if (props.major < 10)
+        std::fprintf(stderr, "flgpu: warning: device %s is sm_%d%d; kernels are built for sm_100a only\n",
+                     props.name, props.major, props.minor);
+    if (opt.stream) {
+        stream = (cudaStream_t)opt.stream;
+    } else {
+        FLGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        own_stream = true;
+    }
+    ld = (n + 31) / 32 * 32;  // 256-byte aligned columns
+    if (ld == 0) ld = 32;
+    ctx.user = prob.user;
+    ctx.stream = (void *)stream;
+    ctx.offset = opt.offset;
+    ctx.n_global = opt.n_global ? opt.n_global : n_local;
+    ctx.rank = comm ? comm->rank : 0;
+    ctx.nranks = comm ? comm->nranks : 1;
+    ctx.device = device;
+    const int G = ctx.nranks;
+    const size_t nres = NSLOTS + nd_of(k::kMaxMem);
+    auto dalloc = [&](size_t bytes) {
+        void *p = nullptr;
+        FLGPU_CUDA_CHECK(cudaMalloc(&p, bytes));
+        FLGPU_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream));
+        owned.push_back(p);
+        return p;
+    };
+    R = (double *)dalloc(nres * sizeof(double));
+    Rall = (double *)dalloc(nres * sizeof(double) * G);
+    Rglob = (double *)dalloc(NSLOTS * sizeof(double));
+    work.partials = (double *)dalloc((size_t)k::kMaxGrid * nd_of(k::kMaxMem) * sizeof(double));
+    work.ticket = (unsigned int *)dalloc(64);
+    FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, NSLOTS * sizeof(double)));
+}
+
+CudaBackend::~CudaBackend() {
+    cudaStreamSynchronize(stream);
+    for (void *p : owned) cudaFree(p);
+    if (host_pinned) cudaFreeHost(host_pinned);
+    for (auto &pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto e : event_pool) cudaEventDestroy(e);
+    if (own_stream) cudaStreamDestroy(stream);
+}
+
+double *CudaBackend::vec_alloc() {
+    void *p = nullptr;
+    FLGPU_CUDA_CHECK(cudaMalloc(&p, (size_t)ld * sizeof(double)));
+    FLGPU_CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)ld * sizeof(double), stream));
+    owned.push_back(p);
+    return (double *)p;
+}
+
+void CudaBackend::lbfgs_alloc(int m) {
+    if (m > k::kMaxMem) {
+        std::fprintf(stderr, "flgpu: LBFGS Memory=%d exceeds the supported maximum %d\n", m, k::kMaxMem);
+        std::abort();
+    }
+    mem = m;
+    auto dalloc = [&](size_t bytes) {
+        void *p = nullptr;
+        FLGPU_CUDA_CHECK(cudaMalloc(&p, bytes));
+        owned.push_back(p);
+        return p;
+    };
+    // ring buffers: column-major (ld, m) like the reference's s(dim,0:mem), y(dim,0:mem) (f90:435)
+    S = (double *)dalloc((size_t)ld * m * sizeof(double));
+    Y = (double *)dalloc((size_t)ld * m * sizeof(double));
+    SY = (double *)dalloc((size_t)m * m * sizeof(double));
+    YY = (double *)dalloc((size_t)m * m * sizeof(double));
+    C = (double *)dalloc((size_t)nc_of(m) * sizeof(double));
+    FLGPU_CUDA_CHECK(cudaMemsetAsync(SY, 0, (size_t)m * m * sizeof(double), stream));
+    FLGPU_CUDA_CHECK(cudaMemsetAsync(YY, 0, (size_t)m * m * sizeof(double), stream));
+    FLGPU_CUDA_CHECK(cudaMemsetAsync(C, 0, (size_t)nc_of(m) * sizeof(double), stream));
+}
+
+void CudaBackend::upload(double *dst, const double *user_x, int x_space) {
+    FLGPU_CUDA_CHECK(cudaMemcpyAsync(dst, user_x, (size_t)n * sizeof(double),
+                                     x_space == FLGPU_SPACE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                     stream));
+    FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+void CudaBackend::download(double *user_x, const double *src, int x_space) {
+    FLGPU_CUDA_CHECK(cudaMemcpyAsync(user_x, src, (size_t)n * sizeof(double),
+                                     x_space == FLGPU_SPACE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                     stream));
+    FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+    resolve_times();
+}
+
+// ---- launch geometry: a multiple of the SM count, bounded by the work and the partial buffers
+int CudaBackend::grid_for(int64_t units, int tpb, int blocks_per_sm) const {
+    int64_t need = (units + tpb - 1) / tpb;
+    if (need < 1) need = 1;
+    int64_t g = (int64_t)num_sms * blocks_per_sm;
+    if (g > k::kMaxGrid) g = k::kMaxGrid;
+    if (need < g) g = need;
+    return (int)g;
+}
+
+// ---- timing
+cudaEvent_t CudaBackend::get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    FLGPU_CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+}
+int CudaBackend::time_index(const char *name) {
+    for (size_t i = 0; i < times.size(); i++) if (times[i].name == name) return (int)i;
+    KernelTime kt; kt.name = name; times.push_back(kt);
+    return (int)times.size() - 1;
+}
+int CudaBackend::time_begin(const char *name, double bytes) {
+    if (!timing) return -1;
+    const int idx = time_index(name);
+    times[idx].launches++;
+    times[idx].bytes += bytes;
+    Pending pe; pe.idx = idx; pe.a = get_event(); pe.b = get_event();
+    FLGPU_CUDA_CHECK(cudaEventRecord(pe.a, stream));
+    pending.push_back(pe);
+    return (int)pending.size() - 1;
+}
+void CudaBackend::time_end(int token) {
+    if (token < 0) return;
+    FLGPU_CUDA_CHECK(cudaEventRecord(pending[token].b, stream));
+}
+void CudaBackend::resolve_times() {
+    if (pending.empty()) return;
+    for (auto &pe : pending) {
+        float ms = 0.f;
+        FLGPU_CUDA_CHECK(cudaEventSynchronize(pe.b));
+        FLGPU_CUDA_CHECK(cudaEventElapsedTime(&ms, pe.a, pe.b));
+        times[pe.idx].ms += ms;
+        event_pool.push_back(pe.a); event_pool.push_back(pe.b);
+    }
+    pending.clear();
+}
+
+// ---- callbacks
+void CudaBackend::eval_f(const double *x) {
+    const int t = time_begin("callback:f", 8.0 * n);
+    prob.f(&ctx, R + SL_F, x, n);
+    time_end(t);
+}
+void CudaBackend::eval_g(const double *x, double *g) {
+    const int t = time_begin("callback:fd", 16.0 * n);
+    prob.fd(&ctx, g, x, n);
+    time_end(t);
+}
+void CudaBackend::eval_fg(const double *x, double *g) {
+    const int t = time_begin("callback:f_fd", 16.0 * n);
+    prob.f_fd(&ctx, R + SL_F, g, x, n);
+    time_end(t);
+}
+
+// ---- primitives
+void CudaBackend::trial_x(double *x, const double *x0, const double *p, double a) {
+    const int t = time_begin("trial_x", 24.0 * n);
+    k::trial_kernel<<<grid_for(n / 8 + 1, k::kThreads, 8), k::kThreads, 0, stream>>>(x, x0, p, a, n);
+    time_end(t);
+    launches++;
+}
+void CudaBackend::dot(const double *a, const double *b, int slot) {
+    const int t = time_begin("dot", 16.0 * n);
+    k::dot_kernel<<<grid_for(n / 8 + 1, k::kThreads, 8), k::kThreads, 0, stream>>>(a, b, n, work, R, slot);
+    time_end(t);
+    launches++;
+}
+void CudaBackend::neg(double *p, const double *g) {
+    const int t = time_begin("neg", 16.0 * n);
+    k::neg_kernel<<<grid_for(n / 2 + 1, k::kThreads, 8), k::kThreads, 0, stream>>>(p, g, n);
+    time_end(t);
+    launches++;
+}
+
+// ---- L-BFGS
+namespace {
+template <int MT, int NG>
+void launch_k1(const k::K1Args &a, int grid, cudaStream_t s) {
+    k::k1_update_dots_kernel<MT, NG><<<grid, k::kThreads, 0, s>>>(a);
+}
+}  // namespace
+
+void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const double *g1,
+                                    const double *g0, int new_slot, int k_after) {
+    const int nother = k_after - 1;
+    const int t = time_begin("k1_update_dots", 8.0 * n * (2.0 * nother + 6.0));
+    k::K1Args a;
+    a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.S = S; a.Y = Y; a.ld = ld; a.n = n;
+    a.m = mem; a.new_slot = new_slot; a.k_after = k_after; a.w = work; a.R = R;
+    int age = 1;
+    bool first = true;
+    // one pass covers NG*MT older columns; more than 64 older columns never occurs (kMaxMem)
+    do {
+        a.age_base = age;
+        a.write_new = first ? 1 : 0;
+        const int rem = nother - (age - 1);
+        int cover;
+        if (rem <= 2)       { cover = 2;  launch_k1<2, 1>(a, grid_for(n / 2 + 1, 256, 2), stream); }
+        else if (rem <= 4)  { cover = 4;  launch_k1<4, 1>(a, grid_for(n / 2 + 1, 256, 2), stream); }
+        else if (rem <= 5)  { cover = 5;  launch_k1<5, 1>(a, grid_for(n / 2 + 1, 256, 2), stream); }
+        else if (rem <= 8)  { cover = 8;  launch_k1<4, 2>(a, grid_for(n / 2 + 1, 128, 2), stream); }
+        else if (rem <= 10) { cover = 10; launch_k1<5, 2>(a, grid_for(n / 2 + 1, 128, 2), stream); }
+        else if (rem <= 16) { cover = 16; launch_k1<4, 4>(a, grid_for(n / 2 + 1, 64, 2), stream); }
+        else if (rem <= 20) { cover = 20; launch_k1<5, 4>(a, grid_for(n / 2 + 1, 64, 2), stream); }
+        else if (rem <= 32) { cover = 32; launch_k1<8, 4>(a, grid_for(n / 2 + 1, 64, 2), stream); }
+        else                { cover = 64; launch_k1<8, 8>(a, grid_for(n / 2 + 1, 32, 2), stream); }
+        launches++;
+        age += cover;
+        first = false;
+    } while (age - 1 < nother);
+    time_end(t);
+}
+
+void CudaBackend::lbfgs_solve(int kk, int recent) {
+    const int nd = nd_of(mem);
+    const int G = ctx.nranks;
+    const double *Dall = R + NSLOTS;
+    if (G > 1) {
+        nccl_allgather_f64(comm, R + NSLOTS, Rall, (size_t)nd, stream);
+        Dall = Rall;
+    }
+    const int t = time_begin("k2_solve", 0.0);
+    const size_t smem = (size_t)(nd + 2 * mem * mem) * sizeof(double);
+    if (smem > 48 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k2_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            attr_set = true;
+        }
+    }
+    k::k2_solve_kernel<<<1, 32, smem, stream>>>(mem, kk, recent, Dall, G, SY, YY, C);
+    time_end(t);
+    launches++;
+}
+
+void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int kk,
+                                  int recent) {
+    const int t = time_begin("k3_direction", 8.0 * n * (2.0 * kk + 4.0));
+    k::K3Args a;
+    a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n;
+    a.m = mem; a.k = kk; a.recent = recent; a.w = work; a.R = R;
+    k::k3_direction_kernel<<<grid_for(n / 2 + 1, k::kThreads, 4), k::kThreads, 0, stream>>>(a);
+    time_end(t);
+    launches++;
+}
+
+// ---- CG
+void CudaBackend::cg_dots(const double *g1, const double *g0, const double *p) {
+    const int t = time_begin("cg_dots", 24.0 * n);
+    k::cg_dots_kernel<<<grid_for(n / 4 + 1, k::kThreads, 6), k::kThreads, 0, stream>>>(g1, g0, p, n, work, R);
+    time_end(t);
+    launches++;
+}
+void CudaBackend::cg_update(double *p, const double *g1, double beta) {
+    const int t = time_begin("cg_update", 24.0 * n);
+    k::cg_update_kernel<<<grid_for(n / 4 + 1, k::kThreads, 6), k::kThreads, 0, stream>>>(p, g1, beta, n, work, R);
+    time_end(t);
+    launches++;
+}
+
+// ---- host <- device: one 128-byte copy and one stream synchronisation
+void CudaBackend::fetch(double *host_slots) {
+    const double *src = R;
+    if (ctx.nranks > 1) {
+        nccl_allgather_f64(comm, R, Rall, (size_t)NSLOTS, stream);
+        k::combine_kernel<<<1, 32, 0, stream>>>(Rall, ctx.nranks, NSLOTS, Rglob);
+        launches++;
+        src = Rglob;
+    }
+    FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned, src, NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) cuda_fail("kernel launch", e, __FILE__, __LINE__);
+    std::memcpy(host_slots, host_pinned, NSLOTS * sizeof(double));
+    syncs++;
+    if (timing && pending.size() > 4096) resolve_times();
+}
+
+}  // namespace flgpu

@@ -1,0 +1,97 @@
+// backend_cuda.cuh -- the product's only Backend: hand-written sm_100a kernels on one CUDA stream.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/flgpu.h"
+#include "backend.hpp"
+#include "kernels.cuh"
+
+#define FLGPU_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) ::flgpu::cuda_fail(#expr, e__, __FILE__, __LINE__);                \
+    } while (0)
+
+struct flgpu_comm {
+    void *nccl_comm = nullptr;  // ncclComm_t
+    int rank = 0, nranks = 1;
+};
+
+namespace flgpu {
+
+[[noreturn]] void cuda_fail(const char *what, cudaError_t e, const char *file, int line);
+[[noreturn]] void fatal(const char *msg);
+// Aborts with a message unless a CUDA device is usable (the library has no CPU path).
+int require_device();
+
+// ---- NCCL (resolved with dlopen so single-GPU use has no NCCL dependency)
+void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s);
+
+// ---- per-kernel CUDA-event timing (flgpu_options.time_kernels)
+struct KernelTime {
+    std::string name;
+    double ms = 0.0;
+    int64_t launches = 0;
+    double bytes = 0.0;  // algorithmic bytes credited
+};
+
+class CudaBackend : public Backend {
+public:
+    CudaBackend(const flgpu_problem &prob, int64_t n_local, const flgpu_options &opt);
+    ~CudaBackend() override;
+
+    double *vec_alloc() override;
+    void lbfgs_alloc(int mem) override;
+    void upload(double *dst, const double *user_x, int x_space) override;
+    void download(double *user_x, const double *src, int x_space) override;
+    void eval_f(const double *x) override;
+    void eval_g(const double *x, double *g) override;
+    void eval_fg(const double *x, double *g) override;
+    void trial_x(double *x, const double *x0, const double *p, double a) override;
+    void dot(const double *a, const double *b, int slot) override;
+    void neg(double *p, const double *g) override;
+    void lbfgs_update_dots(const double *x1, const double *x0, const double *g1, const double *g0,
+                           int new_slot, int k_after) override;
+    void lbfgs_solve(int k, int recent) override;
+    void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
+                         int recent) override;
+    void cg_dots(const double *g1, const double *g0, const double *p) override;
+    void cg_update(double *p, const double *g1, double beta) override;
+    void fetch(double *host_slots) override;
+    void *stream_handle() override { return (void *)stream; }
+
+    // accessors for the history API / tests
+    double *S = nullptr, *Y = nullptr, *SY = nullptr, *YY = nullptr, *C = nullptr;
+    int mem = 0;
+    int64_t ld = 0;
+    double *R = nullptr;          // [NSLOTS + nd] device results
+    cudaStream_t stream = nullptr;
+    std::vector<KernelTime> times;
+    void resolve_times();
+
+private:
+    flgpu_problem prob;
+    flgpu_eval_ctx ctx;
+    flgpu_comm *comm = nullptr;
+    bool own_stream = false;
+    int device = 0, num_sms = 148;
+    std::vector<void *> owned;
+    k::Work work{};
+    double *Rall = nullptr;       // [G][NSLOTS + nd] all-gathered results
+    double *Rglob = nullptr;      // [NSLOTS] combined slots
+    double *host_pinned = nullptr;
+    bool timing = false;
+    struct Pending { int idx; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
+    int grid_for(int64_t units, int threads_per_block, int blocks_per_sm) const;
+    int time_begin(const char *name, double bytes);
+    void time_end(int token);
+    cudaEvent_t get_event();
+    int time_index(const char *name);
+};
+
+}  // namespace flgpu

@@ -1,0 +1,441 @@
+// driver.cpp -- host control flow of the hot path: LBFGS (f90:398-625), ConjugateGradient
+// (f90:193-394, 2249-2346) and the Wolfe / Strong-Wolfe line searchers (f90:1286-1698), written
+// against the asynchronous vector operations of backend.hpp.  "f90:" = the reference's
+// source/NonlinearOptimization.f90.
+//
+// What differs from the reference, by design:
+//  * vectors never leave the device: x0/x and f'old/f'new are pairs of buffers that swap roles
+//    when a step is accepted, so `x0=x` (f90:1480), `xold=x; fdold=fdnew` (f90:587) cost nothing;
+//  * every host decision is taken from scalars delivered by Backend::fetch(), one
+//    synchronisation per line-search trial;
+//  * LBFGS: Before()/After() (f90:586-624) become one stream-ordered chain K1 -> K2 -> K3 ->
+//    first trial evaluation that is enqueued speculatively right after a step is accepted;
+//    the convergence tests of After() are applied to the scalars that chain returns.
+// Every branch, comparison, default and exit test follows the reference statement by statement.
+#include "driver.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <utility>
+
+namespace flgpu {
+
+Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
+    Params P;
+    P.mem = o.memory > 1 ? o.memory : 1;                                    // f90:419
+    P.method = o.method;
+    P.strong = o.strong != 0;
+    P.warn = o.warning != 0;
+    P.maxit = o.max_iteration;
+    P.tol = o.precision * o.precision;                                      // f90:427
+    P.minstep = o.min_step_length * o.min_step_length;                      // f90:429
+    if (o.no_clamp) {                                                       // f90:2265-2278
+        P.c1 = o.wolfe_c1;
+        P.c2 = o.wolfe_c2;
+    } else {
+        P.c1 = std::fmax(1e-15, o.wolfe_c1);                                // f90:431
+        P.c2 = std::fmin(1.0 - 1e-15, std::fmax(P.c1 + 1e-15, o.wolfe_c2)); // f90:433
+    }
+    P.incr = std::fmax(1.0 + 1e-15, o.increment);                           // f90:1478
+    P.has_f_fd = has_f_fd;
+    P.observer = o.observer;
+    P.observer_user = o.observer_user;
+    (void)for_cg;
+    return P;
+}
+
+namespace {
+
+// One line search along p from x0 (device buffers); trial points go to xt, trial gradients to gt.
+struct Search {
+    Backend &B;
+    flgpu_stats &st;
+    const double *x0;
+    double *xt, *gt;
+    const double *p;
+    double c1, c2abs, fx0, phid0, incr;
+    bool fdwithf;
+    double a;              // Fortran `a`
+    int64_t trials = 0;
+    // the first trial may already have been formed/evaluated by the caller's chain:
+    // 0 nothing, 2 x formed and f known, 3 x formed, f, f' and f'.p known
+    int pre = 0;
+    double pre_f = 0.0, pre_gp = 0.0;
+
+    Search(Backend &b, flgpu_stats &s) : B(b), st(s) {}
+
+    // ---- Fortran `fx`, filled lazily from the device
+    double fx_ = 0.0;
+    bool f_pending = false;
+    double slots[NSLOTS];
+    void sync() {
+        B.fetch(slots);
+        st.host_syncs++;
+        if (f_pending) { fx_ = slots[SL_F]; f_pending = false; }
+    }
+    double fx() { if (f_pending) sync(); return fx_; }
+    void set_fx(double v) { f_pending = false; fx_ = v; }
+
+    void form(double step) { B.trial_x(xt, x0, p, step); trials++; st.n_trials++; }  // x=x0+a*p
+    void call_f() { B.eval_f(xt); st.n_f++; f_pending = true; }
+    void call_fd() { B.eval_g(xt, gt); st.n_fd++; }
+    void call_ffd() { B.eval_fg(xt, gt); st.n_f_fd++; f_pending = true; }
+    void both() { if (fdwithf) call_ffd(); else { call_f(); call_fd(); } }
+    double slope() { B.dot(gt, p, SL_GP); sync(); return slots[SL_GP]; }             // dot_product(fdx,p)
+    bool armijo_violated() { return fx() > fx0 + c1 * a * phid0; }
+    static bool collapsed(double low, double up) {
+        return std::fabs(up - low) < 1e-15 ||
+               std::fabs(up - low) / std::fmax(std::fabs(low), std::fabs(up)) < 1e-15;
+    }
+
+    // ---------------- Wolfe / Wolfe_fdwithf, f90:1286-1459 (quadratic zoom f90:1347-1370)
+    void wolfe_zoom(double &low, double &up, double &flow, double &fup, double &phidlow) {
+        double phidlow_m_a = phidlow * a;
+        for (;;) {
+            a = phidlow_m_a * a / 2.0 / (flow + phidlow_m_a - fup);
+            if (!(a > low && a < up)) a = (low + up) / 2.0;
+            form(a); call_f();
+            if (armijo_violated()) {
+                up = a;
+                if (up - low < 1e-15 || (up - low) / std::fmax(std::fabs(low), std::fabs(up)) < 1e-15) {
+                    call_fd(); return;
+                }
+                fup = fx();
+            } else {
+                call_fd();
+                const double phidnew = slope();
+                if (phidnew > c2abs) return;
+                low = a;
+                if (up - low < 1e-15 || (up - low) / std::fmax(std::fabs(low), std::fabs(up)) < 1e-15) return;
+                flow = fx(); phidlow = phidnew; phidlow_m_a = phidlow * a;
+            }
+        }
+    }
+    void wolfe() {
+        double aold, fold, atemp, ftemp, phidx;
+        if (pre == 0) { form(a); call_f(); } else { trials++; set_fx(pre_f); }       // f90:1306
+        if (!armijo_violated()) {
+            for (;;) {
+                aold = a; fold = fx();
+                a = aold * incr; form(a); call_f();
+                if (armijo_violated()) {
+                    form(aold);                                                      // f90:1312
+                    call_fd();
+                    phidx = slope();
+                    if (phidx > c2abs) {
+                        a = aold; set_fx(fold);
+                    } else {
+                        atemp = a; ftemp = fx();
+                        wolfe_zoom(aold, atemp, fold, ftemp, phidx);
+                    }
+                    return;
+                }
+            }
+        } else {
+            for (;;) {
+                aold = a; fold = fx();
+                a = aold / incr; form(a); call_f();
+                if (!armijo_violated()) {
+                    call_fd();
+                    phidx = slope();
+                    if (phidx < c2abs) {
+                        atemp = a; ftemp = fx();
+                        wolfe_zoom(atemp, aold, ftemp, fold, phidx);
+                    }
+                    return;
+                }
+                if (a < 1e-15) { call_fd(); return; }
+            }
+        }
+    }
+
+    // ---------------- StrongWolfe / StrongWolfe_fdwithf, f90:1462-1698 (cubic zoom f90:1557-1579)
+    // The six zoom arguments alias the caller's locals exactly as the Fortran by-reference dummies do.
+    void strong_zoom(double &low, double &up, double &flow, double &fup, double &phidlow, double &phidup) {
+        for (;;) {
+            double d1 = phidlow + phidup - 3.0 * (flow - fup) / (low - up);
+            double d2 = up - low;
+            if (d2 > 0.0) d2 = std::sqrt(d1 * d1 - phidlow * phidup);
+            else d2 = -std::sqrt(d1 * d1 - phidlow * phidup);
+            a = up - (up - low) * (phidup + d2 - d1) / (phidup - phidlow + 2.0 * d2);
+            if (!(a > std::fmin(low, up) && a < std::fmax(low, up))) a = (low + up) / 2.0;
+            form(a); both();
+            const double phidnew = slope();
+            if (armijo_violated() || fx() >= flow) {
+                up = a; fup = fx(); phidup = phidnew;
+            } else {
+                if (std::fabs(phidnew) <= c2abs) return;
+                if (phidnew * (up - low) >= 0.0) { up = low; fup = flow; phidup = phidlow; }
+                low = a; flow = fx(); phidlow = phidnew;
+            }
+            if (collapsed(low, up)) return;
+        }
+    }
+    void strongwolfe() {
+        double aold = 0, fold = 0, atemp, ftemp, phidnew, phidold = 0;
+        if (pre == 0) {                                                  // f90:1482 / 1604
+            form(a);
+            if (fdwithf) call_ffd(); else call_f();
+        } else {
+            trials++; set_fx(pre_f);
+        }
+        if (!armijo_violated()) {
+            if (!fdwithf) call_fd();
+            phidnew = (pre == 3) ? pre_gp : slope();
+            if (phidnew > 0.0) {
+                if (std::fabs(phidnew) <= c2abs) return;
+                for (;;) {                                               // f90:1488-1497
+                    aold = a; fold = fx(); phidold = phidnew;
+                    a = aold / incr; form(a); both(); phidnew = slope();
+                    if (fx() >= fold || phidnew <= 0.0) {
+                        atemp = a; ftemp = fx();
+                        strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
+                        return;
+                    }
+                    if (a < 1e-15) return;
+                }
+            } else {
+                for (;;) {                                               // f90:1499-1515
+                    aold = a; fold = fx(); phidold = phidnew;
+                    a = aold * incr; form(a); both(); phidnew = slope();
+                    if (armijo_violated() || fx() >= fold) {
+                        atemp = a; ftemp = fx();
+                        strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
+                        return;
+                    }
+                    if (phidnew > 0.0) {
+                        if (std::fabs(phidnew) <= c2abs) return;
+                        atemp = a; ftemp = fx();
+                        strong_zoom(atemp, aold, ftemp, fold, phidnew, phidold);
+                        if (fdwithf) return;                             // f90:1632
+                        set_fx(fx0);                                     // f90:1512 (no return there)
+                    }
+                }
+            }
+        } else {                                                         // f90:1517-1546
+            for (;;) {
+                aold = a; fold = fx();
+                a = aold / incr; form(a); call_f();
+                st.n_f_only_trials++;
+                if (!armijo_violated()) {
+                    call_fd();
+                    phidnew = slope();
+                    if (std::fabs(phidnew) <= c2abs) return;
+                    if (phidnew < 0.0) {
+                        form(aold); call_fd(); phidold = slope();        // f90:1526
+                        atemp = a; ftemp = fx();
+                        strong_zoom(atemp, aold, ftemp, fold, phidnew, phidold);
+                        return;
+                    } else {
+                        for (;;) {
+                            aold = a; fold = fx(); phidold = phidnew;
+                            a = aold / incr; form(a); both(); phidnew = slope();
+                            if (fx() >= fold || phidnew <= 0.0) {
+                                atemp = a; ftemp = fx();
+                                strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
+                                return;
+                            }
+                            if (a < 1e-15) return;
+                        }
+                    }
+                }
+                if (a < 1e-15) { call_fd(); return; }
+            }
+        }
+    }
+};
+
+// Runs one line search; on return xt/gt hold the accepted point and gradient.
+struct SearchResult { double a, fx; int64_t trials; };
+
+SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool strong, bool fdwithf,
+                         const double *x0, double *xt, double *gt, const double *p, double a,
+                         double fx0, double phid0, int pre, double pre_f, double pre_gp) {
+    Search S(B, st);
+    S.x0 = x0; S.xt = xt; S.gt = gt; S.p = p;
+    S.c1 = P.c1; S.c2abs = P.c2 * std::fabs(phid0); S.fx0 = fx0; S.phid0 = phid0; S.incr = P.incr;
+    S.fdwithf = fdwithf; S.a = a; S.fx_ = fx0;
+    S.pre = pre; S.pre_f = pre_f; S.pre_gp = pre_gp;
+    st.n_linesearch++;
+    if (strong) S.strongwolfe(); else S.wolfe();
+    SearchResult r;
+    r.fx = S.fx();
+    r.a = S.a;
+    r.trials = S.trials;
+    return r;
+}
+
+bool observe(const Params &P, Backend &B, int64_t it, double a, double f, double phid0, int64_t trials,
+             const double *p, const double *x, const double *g) {
+    if (!P.observer) return false;
+    flgpu_iter_info info;
+    info.iteration = it; info.n_local = B.n; info.step = a; info.f = f; info.phid0 = phid0;
+    info.trials = trials; info.p_dev = p; info.x_dev = x; info.g_dev = g; info.stream = B.stream_handle();
+    return P.observer(P.observer_user, &info) != 0;
+}
+
+void step_warning(const char *who, double gg) {
+    std::printf(" %s warning: step length has converged, but gradient norm has not met accuracy goal\n", who);
+    std::printf(" Euclidean norm of gradient = %.17g\n", std::sqrt(gg));
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------- LBFGS
+void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *stp) {
+    flgpu_stats &st = *stp;
+    std::memset(&st, 0, sizeof st);
+    double slots[NSLOTS];
+    double *xc = B.vec_alloc(), *xo = B.vec_alloc();   // current (accepted) x / the other buffer
+    double *gc = B.vec_alloc(), *go = B.vec_alloc();   // f' at xc / the other buffer
+    double *p = B.vec_alloc();
+    const int mem = P.mem;
+    B.lbfgs_alloc(mem);
+    B.upload(xc, x_user, x_space);
+
+    // f90:436-445
+    if (P.has_f_fd) { B.eval_fg(xc, gc); st.n_f_fd++; }
+    else { B.eval_f(xc); st.n_f++; B.eval_g(xc, gc); st.n_fd++; }
+    B.dot(gc, gc, SL_GG);
+    B.fetch(slots); st.host_syncs++;
+    double fnew = slots[SL_F];
+    double gg = slots[SL_GG];
+    st.f = fnew; st.gnorm2 = gg;
+    if (gg < P.tol) { st.status = FLGPU_INITIAL_CONVERGED; goto finish; }    // f90:443 (-phidnew<tol)
+    {
+        B.neg(p, gc);                                                        // p=-fdnew
+        double phid0 = -gg;
+        double a = (fnew == 0.0) ? 1.0 : std::fabs(fnew) / std::sqrt(gg);    // f90:444-445
+        double pp = gg;                                                      // dot_product(p,p), p=-f'
+        int recent = -1, k = 0;
+        int64_t it = 0;                                                      // accepted steps so far
+        const int64_t total = 1 + (int64_t)(mem - 1) + (int64_t)P.maxit;     // f90:448,472,511
+        int pre = 0; double pre_f = 0, pre_gp = 0;
+        for (;;) {
+            // which searcher this outer iteration uses: never _fdwithf before the main loop (f90:448-498)
+            const bool in_main = it >= mem;
+            const bool fdwithf = in_main && P.has_f_fd;
+            SearchResult r = line_search(B, st, P, P.strong, fdwithf && P.strong, xc, xo, go, p, a, fnew,
+                                         phid0, pre, pre_f, pre_gp);
+            std::swap(xc, xo); std::swap(gc, go);       // accepted point becomes current; xo/go = xold/fdold
+            a = r.a; fnew = r.fx;
+            st.iterations = ++it;
+            st.f = fnew;
+            const bool stop = observe(P, B, it - 1, a, fnew, phid0, r.trials, p, xc, gc);
+            // ---- After() f90:609-624 fused with the next Before() f90:586-608
+            const bool last = (it >= total) || stop;
+            int new_slot, k_after;
+            if (it <= mem) { new_slot = recent + 1; k_after = k + 1; }       // f90:470,508 (append)
+            else { new_slot = (recent + 1) % mem; k_after = mem; }           // f90:622 (overwrite oldest)
+            const bool next_fdwithf = (it >= mem) && P.has_f_fd && P.strong;
+            if (last) {
+                B.dot(gc, gc, SL_GG);
+            } else {
+                B.lbfgs_update_dots(xc, xo, gc, go, new_slot, k_after);      // K1
+                B.lbfgs_solve(k_after, new_slot);                            // K2
+                B.lbfgs_direction(p, xo, gc, xc, k_after, new_slot);         // K3: new p, first trial (a=1)
+                st.n_trials++;
+                if (next_fdwithf) { B.eval_fg(xo, go); st.n_f_fd++; B.dot(go, p, SL_GP); }
+                else { B.eval_f(xo); st.n_f++; }
+            }
+            B.fetch(slots); st.host_syncs++;
+            gg = slots[SL_GG];
+            st.gnorm2 = gg;
+            if (gg < P.tol) { st.status = FLGPU_CONVERGED; break; }          // f90:611-614
+            if (pp * a * a < P.minstep) {                                    // f90:615-621
+                if (P.warn) step_warning(it <= mem ? "BFGS" : "L-BFGS", gg);
+                st.status = FLGPU_STEP_CONVERGED; break;
+            }
+            if (stop) { st.status = FLGPU_STOPPED_BY_OBSERVER; break; }
+            if (last) {                                                      // f90:580-583
+                st.status = FLGPU_MAX_ITERATION;
+                if (P.warn) {
+                    std::printf(" Failed L-BFGS: max iteration exceeded!\n");
+                    std::printf(" Euclidean norm of gradient = %.17g\n", std::sqrt(gg));
+                }
+                break;
+            }
+            recent = new_slot; k = k_after;
+            phid0 = slots[SL_GP0];                                           // f90:607
+            pp = slots[SL_PP];
+            a = 1.0;
+            pre = next_fdwithf ? 3 : 2;
+            pre_f = slots[SL_F];
+            pre_gp = slots[SL_GP];
+        }
+    }
+finish:
+    B.download(x_user, xc, x_space);
+    st.gpu_launches = B.launches;
+}
+
+// --------------------------------------------------------------------------- ConjugateGradient
+void run_cg(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *stp) {
+    flgpu_stats &st = *stp;
+    std::memset(&st, 0, sizeof st);
+    double slots[NSLOTS];
+    double *xc = B.vec_alloc(), *xo = B.vec_alloc();
+    double *gc = B.vec_alloc(), *go = B.vec_alloc();
+    double *p = B.vec_alloc();
+    B.upload(xc, x_user, x_space);
+    const bool is_pr = P.method == FLGPU_CG_PR;
+    const bool strong = is_pr ? true : P.strong;                             // f90:311-344
+    const char *who = is_pr ? "Polak-Ribiere+ conjugate gradient" : "Dai-Yuan conjugate gradient";
+
+    if (P.has_f_fd) { B.eval_fg(xc, gc); st.n_f_fd++; }                      // f90:230-234
+    else { B.eval_f(xc); st.n_f++; B.eval_g(xc, gc); st.n_fd++; }
+    B.dot(gc, gc, SL_GG);
+    B.fetch(slots); st.host_syncs++;
+    double fnew = slots[SL_F];
+    double gg = slots[SL_GG];
+    st.f = fnew; st.gnorm2 = gg;
+    if (gg < P.tol) { st.status = FLGPU_INITIAL_CONVERGED; goto finish; }    // f90:237
+    {
+        B.neg(p, gc);
+        double phidnew = -gg;                                                // f90:236
+        double a = (fnew == 0.0) ? 1.0 : std::fabs(fnew) / std::sqrt(gg);
+        st.status = FLGPU_MAX_ITERATION;
+        int64_t it = 0;
+        for (int iIteration = 1; iIteration <= P.maxit; iIteration++) {
+            const double phidold = phidnew;                                  // fdold=fdnew by buffer swap
+            SearchResult r = line_search(B, st, P, strong, P.has_f_fd && strong, xc, xo, go, p, a, fnew,
+                                         phidnew, 0, 0.0, 0.0);
+            std::swap(xc, xo); std::swap(gc, go);
+            a = r.a; fnew = r.fx;
+            st.iterations = ++it;
+            st.f = fnew;
+            const bool stop = observe(P, B, it - 1, a, fnew, phidold, r.trials, p, xc, gc);
+            // DY() f90:352-372 / PR() f90:373-393
+            B.cg_dots(gc, go, p);
+            B.fetch(slots); st.host_syncs++;
+            gg = slots[SL_GG];
+            st.gnorm2 = gg;
+            if (gg < P.tol) { st.status = FLGPU_CONVERGED; break; }
+            if (slots[SL_PP] * a * a < P.minstep) {
+                if (P.warn) step_warning(who, gg);
+                st.status = FLGPU_STEP_CONVERGED; break;
+            }
+            if (stop) { st.status = FLGPU_STOPPED_BY_OBSERVER; break; }
+            const double beta = is_pr ? slots[SL_GDG] / slots[SL_G0G0]       // f90:387
+                                      : gg / slots[SL_DGP];                  // f90:366
+            B.cg_update(p, gc, beta);
+            B.fetch(slots); st.host_syncs++;
+            phidnew = slots[SL_GP0];
+            if (phidnew > 0.0) {                                             // f90:368-370
+                B.neg(p, gc);
+                phidnew = -gg;
+            }
+            a = a * phidold / phidnew;                                       // f90:371
+        }
+        if (st.status == FLGPU_MAX_ITERATION && P.warn) {                    // f90:347-350
+            std::printf(" Failed conjugate gradient: max iteration exceeded!\n");
+            std::printf(" Euclidean norm of gradient = %.17g\n", std::sqrt(gg));
+        }
+    }
+finish:
+    B.download(x_user, xc, x_space);
+    st.gpu_launches = B.launches;
+}
+
+}  // namespace flgpu

@@ -1,0 +1,28 @@
+// driver.hpp -- host control flow of LBFGS / ConjugateGradient and their line searchers.
+#pragma once
+#include "../../include/flgpu.h"
+#include "backend.hpp"
+
+namespace flgpu {
+
+struct Params {
+    int mem = 10;        // f90:419-420
+    int method = FLGPU_CG_DY;
+    bool strong = true;  // f90:421-422
+    bool warn = true;    // f90:423-424
+    int maxit = 1000;    // f90:425-426
+    double tol = 1e-30;  // Precision^2, f90:427-428
+    double minstep = 1e-30;
+    double c1 = 1e-4, c2 = 0.9, incr = 1.05;
+    bool has_f_fd = false;
+    flgpu_observer_fn observer = nullptr;
+    void *observer_user = nullptr;
+};
+
+// Applies the reference defaults and fail-safe clamps (f90:417-434, 212-229, 1478-1479).
+Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd);
+
+void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *st);
+void run_cg(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *st);
+
+}  // namespace flgpu

@@ -1,0 +1,234 @@
+/*
+ * flgpu.h -- C-ABI of libflgpu.so: the B200 (sm_100a, fp64 CUDA) implementation of
+ * Fortran-Library's large-dimension unconstrained-optimizer hot path.
+ *
+ * Reference interfaces replaced ("f90:" = source/NonlinearOptimization.f90,
+ * "hpp:" = cpp/NonlinearOptimization.hpp of YifanShenSZ/Fortran-Library):
+ *   LBFGS                   f90:398-400   (no hpp declaration exists; added by analogy)
+ *   ConjugateGradient       f90:193-195   hpp:310-324 (gnu) / hpp:42-56 (intel)
+ *   ConjugateGradient_basic f90:2249-2251 hpp:292-306 (gnu) / hpp:24-38 (intel)
+ *   Strong-Wolfe / Wolfe line searchers f90:1286,1373,1462,1582 (internal to the above)
+ *   callbacks f, fd, f_fd   f90:33-38     hpp:281-284
+ *
+ * Two layers are exported:
+ *   1. the reference's own compiled symbol names (section "Fortran ABI"), same argument
+ *      order, by-reference passing, NULL = absent OPTIONAL, 4-byte LOGICAL, trailing
+ *      hidden CHARACTER length -- a binary drop-in for libFL.so on this path;
+ *   2. flgpu_* entry points with 64-bit dimensions, device-resident x, an explicit
+ *      stream and a row-shard communicator for multi-GPU runs.
+ *
+ * No torch types, no C++ types.  There is no CPU fallback: every entry point aborts
+ * with a message if no CUDA device is usable.
+ */
+#ifndef FLGPU_H
+#define FLGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ callbacks */
+
+/* Reference callback ABI (f90:33-38, hpp:281-284).  Under the Fortran-ABI entry points
+ * x and fdx are DEVICE pointers by default (flgpu_set_callback_space); fx is a host
+ * scalar that must be valid when the callback returns.  Work must be enqueued on
+ * flgpu_current_stream(). */
+typedef void (*flgpu_ref_f_fn)(double *fx, const double *x, const int *dim);
+typedef void (*flgpu_ref_fd_fn)(double *fdx, const double *x, const int *dim);
+typedef int (*flgpu_ref_f_fd_fn)(double *fx, double *fdx, const double *x, const int *dim);
+
+/* Context handed to the 64-bit device callbacks. */
+typedef struct flgpu_eval_ctx {
+    void *user;       /* flgpu_problem.user */
+    void *stream;     /* cudaStream_t the callback must enqueue on */
+    int64_t offset;   /* global index of local row 0 (row-sharded runs) */
+    int64_t n_global; /* global dimension */
+    int rank, nranks; /* position in the communicator (0,1 when single GPU) */
+    int device;       /* CUDA device ordinal */
+} flgpu_eval_ctx;
+
+/* Device callbacks: enqueue kernels on ctx->stream, do NOT synchronise.
+ * f_dev is a device scalar receiving this rank's partial sum of f (plain store). */
+typedef void (*flgpu_f_fn)(const flgpu_eval_ctx *ctx, double *f_dev, const double *x_dev, int64_t n_local);
+typedef void (*flgpu_fd_fn)(const flgpu_eval_ctx *ctx, double *g_dev, const double *x_dev, int64_t n_local);
+typedef void (*flgpu_f_fd_fn)(const flgpu_eval_ctx *ctx, double *f_dev, double *g_dev, const double *x_dev,
+                              int64_t n_local);
+
+typedef struct flgpu_problem {
+    flgpu_f_fn f;       /* required */
+    flgpu_fd_fn fd;     /* required */
+    flgpu_f_fd_fn f_fd; /* optional (NULL = absent, f90:42-43) */
+    void *user;
+} flgpu_problem;
+
+/* ------------------------------------------------------------------ options / results */
+
+enum { FLGPU_CG_DY = 0, FLGPU_CG_PR = 1 };
+enum { FLGPU_SPACE_HOST = 0, FLGPU_SPACE_DEVICE = 1 };
+/* flgpu_stats.status */
+enum {
+    FLGPU_CONVERGED = 0,        /* |f'|^2 < Precision^2 (f90:612) */
+    FLGPU_STEP_CONVERGED = 1,   /* |p|^2 a^2 < MinStepLength^2 (f90:615) */
+    FLGPU_MAX_ITERATION = 2,    /* f90:580 */
+    FLGPU_INITIAL_CONVERGED = 3,/* f90:443 */
+    FLGPU_STOPPED_BY_OBSERVER = 4
+};
+
+typedef struct flgpu_comm flgpu_comm; /* row-shard communicator (NCCL) */
+
+/* Per outer iteration, called on the host after the line search accepted a step.
+ * Device pointers stay valid until the observer returns.  Return non-zero to stop. */
+typedef struct flgpu_iter_info {
+    int64_t iteration;  /* 0-based count of accepted steps, including LBFGS' pre-iterations */
+    int64_t n_local;
+    double step;        /* accepted a */
+    double f;           /* f at the accepted point */
+    double phid0;       /* phi'(0) of this search */
+    int64_t trials;     /* x0 + a p formations in this search */
+    const double *p_dev, *x_dev, *g_dev;
+    void *stream;
+} flgpu_iter_info;
+typedef int (*flgpu_observer_fn)(void *user, const flgpu_iter_info *info);
+
+/* Tunables: names, defaults and fail-safe clamps of f90:417-434 (LBFGS), f90:212-229
+ * (CG) and f90:1478-1479 (Increment).  Fill with flgpu_options_default(). */
+typedef struct flgpu_options {
+    int memory;             /* LBFGS Memory, default 10, clamped max(1,.) */
+    int method;             /* CG: FLGPU_CG_DY (default) / FLGPU_CG_PR */
+    int strong;             /* default 1 */
+    int warning;            /* default 1 */
+    int max_iteration;      /* default 1000 */
+    double precision;       /* default 1e-15 (compared squared) */
+    double min_step_length; /* default 1e-15 (compared squared) */
+    double wolfe_c1;        /* default 1e-4 */
+    double wolfe_c2;        /* default 0.9 (LBFGS) / 0.45 (CG) */
+    double increment;       /* default 1.05 */
+    int no_clamp;           /* 1 = ConjugateGradient_basic semantics: c1/c2 used as given (f90:2278) */
+    /* execution */
+    void *stream;           /* cudaStream_t; NULL = library-owned non-blocking stream */
+    flgpu_comm *comm;       /* NULL = single GPU */
+    int64_t offset;         /* global index of local row 0 (with comm) */
+    int64_t n_global;       /* global dimension (0 = n_local) */
+    flgpu_observer_fn observer;
+    void *observer_user;
+    int time_kernels;       /* 1 = bracket every library kernel with CUDA events (flgpu_kernel_times) */
+} flgpu_options;
+
+typedef struct flgpu_stats {
+    int64_t iterations;   /* accepted steps */
+    int status;
+    int64_t n_f, n_fd, n_f_fd;      /* callback invocations */
+    int64_t n_trials, n_f_only_trials, n_linesearch;
+    int64_t gpu_launches;           /* library kernels launched (callback kernels not counted) */
+    int64_t host_syncs;
+    double f;             /* final objective */
+    double gnorm2;        /* final |f'|^2 */
+} flgpu_stats;
+
+void flgpu_options_default(flgpu_options *o, int for_cg);
+
+/* x: n_local doubles, host (x_space = FLGPU_SPACE_HOST) or device memory; in: initial
+ * guess, out: minimiser (f90:52).  Returns 0, or aborts on CUDA/NCCL failure (the
+ * reference has no error channel either). */
+int flgpu_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local,
+                int x_space, flgpu_stats *stats);
+int flgpu_conjugate_gradient(const flgpu_problem *prob, const flgpu_options *opt, double *x,
+                             int64_t n_local, int x_space, flgpu_stats *stats);
+
+/* ------------------------------------------------------------------ multi-GPU (row shards) */
+/* One process per GPU.  Rank 0 obtains a 128-byte id, the caller distributes it
+ * (MPI / torch.distributed / file), every rank creates the communicator. */
+int flgpu_comm_unique_id(void *id128);
+flgpu_comm *flgpu_comm_create(const void *id128, int rank, int nranks);
+void flgpu_comm_destroy(flgpu_comm *c);
+
+/* ------------------------------------------------------------------ Fortran ABI (drop-in symbols) */
+/* Where x and the callbacks' vectors live for the entry points below.  Defaults:
+ * x in HOST memory (as in the reference), callbacks receive DEVICE pointers.  With
+ * callback space HOST the library stages x/f' through pinned host buffers so that
+ * unmodified host callbacks (e.g. the reference's test/test.cpp) keep working.
+ * Environment overrides: FLGPU_X_SPACE, FLGPU_CALLBACK_SPACE = host|device. */
+void flgpu_set_x_space(int space);
+void flgpu_set_callback_space(int space);
+/* Stream / shard of the optimizer call currently executing on this thread. */
+void *flgpu_current_stream(void);
+int flgpu_current_device(void);
+/* Statistics of the last Fortran-ABI call on this thread. */
+void flgpu_last_stats(flgpu_stats *out);
+/* Observer applied to Fortran-ABI calls on this thread (NULL to clear). */
+void flgpu_set_observer(flgpu_observer_fn fn, void *user);
+
+/* gfortran names (hpp:278-393 "#elif __GNUC__") */
+void __nonlinearoptimization_MOD_lbfgs(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const int *Memory,
+    flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
+    const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+    const double *WolfeConst2, const double *Increment);
+void __nonlinearoptimization_MOD_conjugategradient(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const char *Method,
+    flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
+    const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+    const double *WolfeConst2, const double *Increment, int len_Method);
+void __nonlinearoptimization_MOD_conjugategradient_basic(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const char *Method,
+    const int32_t *Strong, const int32_t *Warning, const int *MaxIteration, const double *Precision,
+    const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
+    const double *Increment, int len_Method);
+/* ifort names (hpp:9-276 "#ifdef __INTEL_COMPILER") */
+void nonlinearoptimization_mp_lbfgs_(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const int *Memory,
+    flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
+    const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+    const double *WolfeConst2, const double *Increment);
+void nonlinearoptimization_mp_conjugategradient_(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const char *Method,
+    flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
+    const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+    const double *WolfeConst2, const double *Increment, int len_Method);
+void nonlinearoptimization_mp_conjugategradient_basic_(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const char *Method,
+    const int32_t *Strong, const int32_t *Warning, const int *MaxIteration, const double *Precision,
+    const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
+    const double *Increment, int len_Method);
+
+/* ------------------------------------------------------------------ built-in objectives (CUDA) */
+/* The synthetic objectives of the benchmark configs (BASELINE.json), as CUDA kernels. */
+enum { FLGPU_OBJ_QUARTIC = 0, FLGPU_OBJ_ROSENBROCK = 1, FLGPU_OBJ_DIAGQUAD = 2 };
+enum { FLGPU_START_QUARTIC_U = 0, FLGPU_START_ROSEN_STD = 1, FLGPU_START_ROSEN_PERT = 2, FLGPU_START_ZERO = 3 };
+/* 64-bit device-callback form */
+int flgpu_builtin_problem(int kind, flgpu_problem *out);
+/* reference-ABI form (device pointers in, host fx out; use with the Fortran-ABI symbols) */
+int flgpu_builtin_ref_callbacks(int kind, flgpu_ref_f_fn *f, flgpu_ref_fd_fn *fd, flgpu_ref_f_fd_fn *f_fd);
+/* x_dev[k] = start(offset + k), k < n_local; enqueued on stream */
+int flgpu_fill_start(int start_kind, uint64_t seed, double *x_dev, int64_t offset, int64_t n_local,
+                     int64_t n_global, void *stream);
+
+/* ------------------------------------------------------------------ vector primitives (a8) */
+/* Deterministic device primitives the optimizers are built from; exported for tests and
+ * for users writing device callbacks.  All enqueue on `stream`; *_dev outputs are device
+ * scalars.  Replaces the dot_product / array-expression sites of f90:591-606,1482,1485. */
+int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *out_dev, void *stream);
+int flgpu_vec_trial(double *x_dev, const double *x0_dev, const double *p_dev, double a, int64_t n,
+                    void *stream); /* x = x0 + a*p, multiply then add (no FMA), f90:1482 */
+
+/* ------------------------------------------------------------------ device memory helpers */
+/* Thin wrappers (cudaMalloc / cudaFree / cudaMemcpyAsync + stream sync) so that C, Fortran
+ * (iso_c_binding) and ctypes callers need no CUDA runtime binding of their own. */
+void *flgpu_malloc(size_t bytes);
+void flgpu_free(void *dev_ptr);
+int flgpu_memcpy(void *dst, const void *src, size_t bytes, int dst_space, int src_space, void *stream);
+int flgpu_device_count(void); /* 0 when no CUDA device is usable; never aborts */
+
+/* ------------------------------------------------------------------ introspection */
+const char *flgpu_version(void);
+/* Per-kernel accumulated CUDA-event time of the last call run with time_kernels=1.
+ * names/ms/launches/bytes: arrays of capacity cap; returns the number of kernels. */
+int flgpu_kernel_times(const char **names, double *ms, int64_t *launches, double *bytes, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLGPU_H */

@@ -29,12 +29,14 @@ static void build_tables(void) {
     g_tables = 1;
 }
 
-/* d_i = 10^(6 q / 2^24), q = floor(i 2^24 / (n-1)): log-uniform in [1, 1e6], built from
+/* d_i = 10^(6 q / 2^24), q = trunc(i * (2^24/(n-1))) evaluated in IEEE double (one divide, one
+ * multiply, one truncation: identical on host and device): log-uniform in [1, 1e6], built from
  * three table factors with exact IEEE multiplies so host and device agree bitwise. */
 double orc_diag_coeff(long long i, long long n_global) {
     if (!g_tables) build_tables();
     if (n_global <= 1) return 1.0;
-    uint64_t q = ((uint64_t)i << 24) / (uint64_t)(n_global - 1);
+    const double scale = 16777216.0 / (double)(n_global - 1);
+    uint64_t q = (uint64_t)((double)i * scale);
     if (q >> 24) return 1.0e6;
     return T2[(q >> 16) & 255] * T1[(q >> 8) & 255] * T0[q & 255];
 }

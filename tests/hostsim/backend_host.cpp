@@ -1,0 +1,230 @@
+// tests/hostsim/backend_host.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A host-memory implementation of fortran_library_b200/csrc/backend.hpp, so that the host
+// control flow in driver.cpp (the same translation unit the product links) can be checked against
+// the oracle on a machine without a GPU, including the world_size>1 row-shard combination
+// over a caller-supplied all-gather (gloo in the tests).  Built into
+// tests/hostsim/libflgpu_hostsim.so; libflgpu.so never links or loads it and has no CPU path.
+//
+// Element-wise arithmetic matches the CUDA kernels (separate multiply and add roundings);
+// reductions are blocked sums, so results agree with the GPU up to summation order only.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../fortran_library_b200/csrc/backend.hpp"
+#include "../../fortran_library_b200/csrc/driver.hpp"
+#include "../../fortran_library_b200/csrc/lbfgs_gram.hpp"
+#include "../../oracle/oracle.h"
+
+namespace {
+
+typedef void (*allgather_fn)(void *user, const double *local, double *all, int count);
+allgather_fn g_allgather = nullptr;
+void *g_allgather_user = nullptr;
+int g_rank = 0, g_nranks = 1;
+
+const long BLK = 1024;
+
+template <class F>
+double blocked_sum(long n, F term) {
+    double total = 0.0;
+    for (long b = 0; b < n; b += BLK) {
+        double s = 0.0;
+        const long e = b + BLK < n ? b + BLK : n;
+        for (long i = b; i < e; i++) s += term(i);
+        total += s;
+    }
+    return total;
+}
+
+class HostBackend : public flgpu::Backend {
+public:
+    flgpu_problem prob;
+    flgpu_eval_ctx ctx;
+    std::vector<double *> owned;
+    double slots[flgpu::NSLOTS];
+    int mem = 0;
+    double *S = nullptr, *Y = nullptr;
+    std::vector<double> SY, YY, D, C, w1, w2, w3;
+
+    HostBackend(const flgpu_problem &p, int64_t n_, int64_t offset, int64_t n_global) : prob(p) {
+        n = n_;
+        std::memset(slots, 0, sizeof slots);
+        ctx.user = p.user; ctx.stream = nullptr; ctx.offset = offset;
+        ctx.n_global = n_global ? n_global : n_; ctx.rank = g_rank; ctx.nranks = g_nranks; ctx.device = -1;
+    }
+    ~HostBackend() override { for (double *v : owned) std::free(v); }
+
+    double *vec_alloc() override {
+        double *v = (double *)std::calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+        owned.push_back(v);
+        return v;
+    }
+    void lbfgs_alloc(int m) override {
+        mem = m;
+        S = (double *)std::calloc((size_t)(n > 0 ? n : 1) * m, sizeof(double));
+        Y = (double *)std::calloc((size_t)(n > 0 ? n : 1) * m, sizeof(double));
+        owned.push_back(S); owned.push_back(Y);
+        SY.assign((size_t)m * m, 0.0); YY.assign((size_t)m * m, 0.0);
+        D.assign(flgpu::nd_of(m), 0.0); C.assign(flgpu::nc_of(m), 0.0);
+        w1.assign(m, 0.0); w2.assign(m, 0.0); w3.assign(m, 0.0);
+    }
+    void upload(double *dst, const double *user_x, int) override { std::memcpy(dst, user_x, sizeof(double) * n); }
+    void download(double *user_x, const double *src, int) override { std::memcpy(user_x, src, sizeof(double) * n); }
+
+    void eval_f(const double *x) override { prob.f(&ctx, &slots[flgpu::SL_F], x, n); }
+    void eval_g(const double *x, double *g) override { prob.fd(&ctx, g, x, n); }
+    void eval_fg(const double *x, double *g) override { prob.f_fd(&ctx, &slots[flgpu::SL_F], g, x, n); }
+
+    void trial_x(double *x, const double *x0, const double *p, double a) override {
+        launches++;
+        for (long i = 0; i < n; i++) x[i] = x0[i] + a * p[i];
+    }
+    void dot(const double *a, const double *b, int slot) override {
+        launches++;
+        slots[slot] = blocked_sum(n, [&](long i) { return a[i] * b[i]; });
+    }
+    void neg(double *p, const double *g) override {
+        launches++;
+        for (long i = 0; i < n; i++) p[i] = -g[i];
+    }
+
+    void lbfgs_update_dots(const double *x1, const double *x0, const double *g1, const double *g0,
+                           int new_slot, int k_after) override {
+        launches++;
+        const int m = mem;
+        double *sn = S + (long)new_slot * n, *yn = Y + (long)new_slot * n;
+        for (long i = 0; i < n; i++) { sn[i] = x1[i] - x0[i]; yn[i] = g1[i] - g0[i]; }
+        for (int t = 0; t < k_after; t++) {
+            const int j = flgpu::slot_of_age(new_slot, t, m);
+            const double *sj = S + (long)j * n, *yj = Y + (long)j * n;
+            D[flgpu::d_A(m, j)] = blocked_sum(n, [&](long i) { return sj[i] * g1[i]; });
+            D[flgpu::d_B(m, j)] = blocked_sum(n, [&](long i) { return yj[i] * g1[i]; });
+            D[flgpu::d_SYN(m, j)] = blocked_sum(n, [&](long i) { return sj[i] * yn[i]; });
+            D[flgpu::d_YYN(m, j)] = blocked_sum(n, [&](long i) { return yj[i] * yn[i]; });
+        }
+        D[flgpu::d_GG(m)] = blocked_sum(n, [&](long i) { return g1[i] * g1[i]; });
+        slots[flgpu::SL_GG] = D[flgpu::d_GG(m)];
+    }
+    void lbfgs_solve(int k, int recent) override {
+        launches++;
+        std::vector<double> G(D);
+        combine(G.data(), (int)G.size());
+        flgpu::lbfgs_gram_solve(mem, k, recent, G.data(), SY.data(), YY.data(), C.data(), w1.data(),
+                                w2.data(), w3.data());
+    }
+    void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
+                         int recent) override {
+        launches++;
+        const int m = mem;
+        const double gamma = C[0];
+        for (long i = 0; i < n; i++) {
+            double q = g1[i];
+            for (int t = 0; t < k; t++) {
+                const int j = flgpu::slot_of_age(recent, t, m);
+                q = q - C[1 + j] * Y[(long)j * n + i];
+            }
+            double r = gamma * q;
+            for (int t = k - 1; t >= 0; t--) {
+                const int j = flgpu::slot_of_age(recent, t, m);
+                r = r + C[1 + m + j] * S[(long)j * n + i];
+            }
+            p[i] = -r;
+            xt[i] = x1[i] + p[i];
+        }
+        slots[flgpu::SL_GP0] = blocked_sum(n, [&](long i) { return g1[i] * p[i]; });
+        slots[flgpu::SL_PP] = blocked_sum(n, [&](long i) { return p[i] * p[i]; });
+    }
+
+    void cg_dots(const double *g1, const double *g0, const double *p) override {
+        launches++;
+        slots[flgpu::SL_GG] = blocked_sum(n, [&](long i) { return g1[i] * g1[i]; });
+        slots[flgpu::SL_PP] = blocked_sum(n, [&](long i) { return p[i] * p[i]; });
+        slots[flgpu::SL_DGP] = blocked_sum(n, [&](long i) { return (g1[i] - g0[i]) * p[i]; });
+        slots[flgpu::SL_GDG] = blocked_sum(n, [&](long i) { return g1[i] * (g1[i] - g0[i]); });
+        slots[flgpu::SL_G0G0] = blocked_sum(n, [&](long i) { return g0[i] * g0[i]; });
+    }
+    void cg_update(double *p, const double *g1, double beta) override {
+        launches++;
+        for (long i = 0; i < n; i++) p[i] = -g1[i] + beta * p[i];
+        slots[flgpu::SL_GP0] = blocked_sum(n, [&](long i) { return g1[i] * p[i]; });
+    }
+
+    // sum over ranks in rank order (bitwise identical on every rank)
+    void combine(double *v, int count) {
+        if (g_nranks <= 1 || !g_allgather) return;
+        std::vector<double> all((size_t)count * g_nranks);
+        g_allgather(g_allgather_user, v, all.data(), count);
+        for (int i = 0; i < count; i++) {
+            double s = 0.0;
+            for (int r = 0; r < g_nranks; r++) s += all[(size_t)r * count + i];
+            v[i] = s;
+        }
+    }
+    void fetch(double *host) override {
+        syncs++;
+        std::memcpy(host, slots, sizeof slots);
+        combine(host, flgpu::NSLOTS);
+    }
+};
+
+// ---- objective adapters over oracle/objectives.c (host pointers)
+void obj_f(const flgpu_eval_ctx *c, double *f, const double *x, int64_t n) {
+    int d = (int)n;
+    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
+    orc_obj_f(f, x, &d);
+}
+void obj_fd(const flgpu_eval_ctx *c, double *g, const double *x, int64_t n) {
+    int d = (int)n;
+    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
+    orc_obj_fd(g, x, &d);
+}
+void obj_ffd(const flgpu_eval_ctx *c, double *f, double *g, const double *x, int64_t n) {
+    int d = (int)n;
+    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
+    orc_obj_f_fd(f, g, x, &d);
+}
+
+}  // namespace
+
+extern "C" {
+
+void flgpu_hostsim_set_comm(allgather_fn fn, void *user, int rank, int nranks) {
+    g_allgather = fn; g_allgather_user = user; g_rank = rank; g_nranks = nranks;
+}
+
+void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
+    out->f = obj_f; out->fd = obj_fd; out->f_fd = obj_ffd; out->user = (void *)(intptr_t)kind;
+}
+
+void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {
+    std::memset(o, 0, sizeof *o);
+    o->memory = 10; o->method = FLGPU_CG_DY; o->strong = 1; o->warning = 1; o->max_iteration = 1000;
+    o->precision = 1e-15; o->min_step_length = 1e-15; o->wolfe_c1 = 1e-4;
+    o->wolfe_c2 = for_cg ? 0.45 : 0.9; o->increment = 1.05;
+}
+
+int flgpu_hostsim_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n,
+                        flgpu_stats *stats) {
+    HostBackend B(*prob, n, opt->offset, opt->n_global);
+    flgpu::Params P = flgpu::params_from_options(*opt, false, prob->f_fd != nullptr);
+    flgpu_stats st;
+    flgpu::run_lbfgs(B, P, x, 0, &st);
+    if (stats) *stats = st;
+    return 0;
+}
+
+int flgpu_hostsim_cg(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n,
+                     flgpu_stats *stats) {
+    HostBackend B(*prob, n, opt->offset, opt->n_global);
+    flgpu::Params P = flgpu::params_from_options(*opt, true, prob->f_fd != nullptr);
+    flgpu_stats st;
+    flgpu::run_cg(B, P, x, 0, &st);
+    if (stats) *stats = st;
+    return 0;
+}
+
+}  // extern "C"
