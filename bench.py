@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on its headline config (BASELINE.json):
+L-BFGS (m = 10) outer iterations per second on extended Rosenbrock at n = 2^28, fp64, row-sharded over
+--gpus N B200s (strong scaling: the global n is fixed), plus the HBM roofline of the dominant kernel.
+
+A "step" is one main-loop L-BFGS iteration = Before + line search + After of the reference
+(NonlinearOptimization.f90:514-518), i.e. one accepted step: K1 (ring update + all dots) -> K2 -> K3
+(direction + first trial) -> Strong-Wolfe trials (x0 + a p, f_fd callback, f'.p).  Iteration 0 and the
+m-1 pre-iterations (f90:442-510) always run first and are never timed.
+
+  python bench.py [--gpus N --steps K --warmup W]         our arm (one JSON line on rank 0)
+  python bench.py --impl reference [...]                   the reference's CPU algorithm (oracle port)
+
+Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
+Inputs are 2 GiB per vector (>> 126 MB L2), so no L2 flush is needed between iterations.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+LOG2_N = 28
+MEM = 10
+SEED = 7
+METRIC = "lbfgs_iterations_per_sec"
+UNIT = "it/s"
+
+
+def workload(n, mem):
+    return (f"LBFGS m={mem} extended Rosenbrock n=2^{n.bit_length() - 1} fp64, start R1 = (-1.2,1)+0.1(u-0.5) "
+            f"seed {SEED}, f_fd CUDA callback, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle = checker, timed)
+def cpu_lbfgs(n_sample, mem, warmup, steps, n_target):
+    """Times the oracle (C restatement of the reference, strict IEEE, sequential sums, ONE thread -- the
+    reference has no threading on this path) on a bounded sample of the same workload and
+    scales the iteration rate linearly in n (a streaming workload)."""
+    import _oracle as O
+    marks = {}
+
+    class T(O.Trace):
+        def _on(self, user, it, dim, p, x, g, a, fx, phid0, trials):
+            marks[it] = (time.perf_counter(), trials)
+
+    x0 = O.start_vector(O.START_ROSEN_PERT, n_sample, seed=SEED)
+    tr = T(keep_vectors=False)
+    x, st = O.lbfgs(O.builtin_callbacks(O.OBJ_ROSENBROCK, 0, n_sample), x0, Memory=mem, use_ffd=True, Warning=False,
+                    MaxIteration=warmup + steps, trace=tr)
+    first, last = mem + warmup - 1, mem + warmup + steps - 1
+    if last not in marks:                      # converged early (never at these sizes)
+        last = max(marks)
+    dt = marks[last][0] - marks[first][0]
+    its = last - first
+    trials = sum(marks[i][1] for i in range(first + 1, last + 1))
+    rate_sample = its / dt
+    return {"value": rate_sample * n_sample / n_target, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": (f"oracle/liboracle.so (gcc -O2 -ffp-contract=off, 1 thread) on n=2^{n_sample.bit_length() - 1}: "
+                       f"{its} main-loop iterations, {trials} trials, {dt:.2f} s = {rate_sample:.3f} it/s; scaled by "
+                       f"n_sample/n (streaming)"),
+            "sample_it_per_s": rate_sample, "sample_trials_per_iteration": trials / max(its, 1)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = 1 << args.log2n
+    n_sample = 1 << min(args.log2n, args.cpu_log2n)
+    t0 = time.time()
+    cb = cpu_lbfgs(n_sample, args.mem, args.warmup, args.steps, n)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload(n, args.mem), "timing": "host perf_counter around oracle iterations"},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import fortran_library_b200 as fl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    fl.require_gpu()
+    dist = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+        def bcast(data):
+            t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                t.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().numpy().tobytes())
+        comm = fl.comm_create(rank, world, bcast)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    n = 1 << args.log2n
+    mem, W, K = args.mem, args.warmup, args.steps
+    lo = (n * rank // world) // 2 * 2            # even boundaries: Rosenbrock pairs never straddle shards
+    hi = n if rank == world - 1 else (n * (rank + 1) // world) // 2 * 2
+    n_local = hi - lo
+    prob = fl.builtin_problem(fl.OBJ_ROSENBROCK)
+    first, last = mem + W - 1, mem + W + K - 1   # observer indices bracketing exactly K main-loop iterations
+
+    def timed_run(time_kernels):
+        x = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_local, seed=SEED, offset=lo, n_global=n)
+        ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+        mark = {}
+
+        def on_iter(i):
+            if i.iteration == first or i.iteration == last:
+                s = torch.cuda.ExternalStream(i.stream)
+                if i.iteration == first:
+                    barrier()
+                    mark["t0"] = time.time()
+                    mark["c0"] = (i.gpu_launches, i.callbacks, i.total_trials)
+                    if time_kernels:
+                        fl.lib().flgpu_reset_kernel_times()
+                    ev[0].record(s)
+                else:
+                    ev[1].record(s)
+                    barrier()
+                    mark["t1"] = time.time()
+                    mark["c1"] = (i.gpu_launches, i.callbacks, i.total_trials)
+                    return True
+            return False
+        ob = fl.Observer(on_iteration=on_iter)
+        st = fl.LBFGS(prob, x, Memory=mem, Warning=False, MaxIteration=W + K, observer=ob, comm=comm, offset=lo,
+                      n_global=n, time_kernels=time_kernels)
+        if "t1" not in mark:
+            raise SystemExit(f"bench.py: optimizer stopped after {st.iterations} iterations (status {st.status}) "
+                             f"before {last + 1}; lower --steps")
+        ms = ev[0].elapsed_time(ev[1])
+        x.free()
+        return ms, mark, st, fl.kernel_times() if time_kernels else None
+
+    # ---- pass 1: the metric (device-resident inputs, no per-kernel events)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, mark, st, _ = timed_run(False)
+    clocks = sampler.stop(mark["t0"], mark["t1"]) if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    launches = (mark["c1"][0] - mark["c0"][0]) + (mark["c1"][1] - mark["c0"][1])   # library kernels + objective kernels
+    trials = mark["c1"][2] - mark["c0"][2]
+
+    # ---- pass 2: per-kernel CUDA-event times over the same timed region -> roofline of the dominant kernel
+    ms2, mark2, st2, kt = timed_run(True)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    kernels = {}
+    for name, v in kt.items():
+        if v["ms"] > 0 and v["bytes"] > 0:
+            kernels[name] = {"launches": v["launches"], "ms": round(v["ms"], 3), "avg_ms": v["ms"] / v["launches"],
+                             "GBps": v["bytes"] / v["ms"] / 1e6, "frac": v["bytes"] / v["ms"] / 1e6 / peak}
+    own = {k: v for k, v in kernels.items() if not k.startswith("callback:")}
+    top = max(own, key=lambda k: own[k]["ms"])
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = prof.get(top, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    total_bytes = sum(v["bytes"] for v in kt.values())
+    total_kernel_ms = sum(v["ms"] for v in kt.values())
+    roofline = {"bound": "hbm", "kernel": top, "achieved": own[top]["GBps"], "peak": peak, "unit": "GB/s",
+                "frac": own[top]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": kt[top]["bytes"] / kt[top]["launches"],
+                "share_of_step": kt[top]["ms"] / total_kernel_ms,
+                "whole_step": {"algorithmic_GB": total_bytes / 1e9, "kernel_ms": total_kernel_ms,
+                               "GBps": total_bytes / total_kernel_ms / 1e6, "frac": total_bytes / total_kernel_ms / 1e6 / peak,
+                               "note": "all kernels of the K timed iterations (pass 2)"},
+                "kernels": kernels}
+
+    # ---- e2e: the reference-facing call with HOST buffers (pinned), H2D/D2H and work-space allocation inside
+    Ke = args.e2e_steps
+    xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
+    x0 = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_local, seed=SEED, offset=lo, n_global=n)
+    fl.lib().flgpu_memcpy(xh.data_ptr(), x0.ptr, n_local * 8, fl.SPACE_HOST, fl.SPACE_DEVICE, None)
+    x0.free()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    te = time.time()
+    if world == 1:
+        L = fl.lib()
+        f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
+        L.flgpu_builtin_ref_callbacks(fl.OBJ_ROSENBROCK, C.byref(f), C.byref(fd), C.byref(ffd))
+        L.__getattr__("__nonlinearoptimization_MOD_lbfgs")(
+            f, fd, C.c_void_p(xh.data_ptr()), C.byref(C.c_int(n_local)), C.byref(C.c_int(mem)), ffd, None,
+            C.byref(C.c_int32(0)), C.byref(C.c_int(Ke)), None, None, None, None, None)
+        ste = fl.capi.Stats()
+        L.flgpu_last_stats(C.byref(ste))
+        e2e_call = "__nonlinearoptimization_MOD_lbfgs (host x, device-pointer callbacks)"
+    else:
+        ste = fl.LBFGS(prob, xh, Memory=mem, Warning=False, MaxIteration=Ke, comm=comm, offset=lo, n_global=n)
+        e2e_call = "flgpu_lbfgs (host x shard, NCCL communicator)"
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    te = time.time() - te
+    t = torch.tensor([max(e2e_ms, te * 1e3)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e = {"value": ste.iterations / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n / ste.iterations,
+           "d2h_bytes_per_step": 8 * n / ste.iterations, "iterations": ste.iterations, "ms": e2e_ms, "call": e2e_call,
+           "note": "one optimizer call incl. H2D of x, work-space allocation, iteration 0 + m-1 pre-iterations + "
+                   f"{Ke} main iterations, D2H of x; bytes/step = 8n/iterations (x crosses PCIe once per call)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_lbfgs(1 << min(args.log2n, args.cpu_log2n), mem, min(W, 3), min(K, 10), n)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload(n, mem), "n_global": n, "rows_per_gpu": n_local,
+                           "parallelism": f"row-shard x{world}" if world > 1 else "1 GPU",
+                           "l2": "inputs (2 GiB/vector) exceed L2; no flush needed",
+                           "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if comm is not None:
+        fl.lib().flgpu_comm_destroy(comm)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2n", type=int, default=LOG2_N, help="override the global dimension (debugging only)")
+    ap.add_argument("--mem", type=int, default=MEM)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-log2n", type=int, default=21, help="size of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 0 or args.steps < 1:
+        raise SystemExit("need --steps >= 1 and --warmup >= 0")
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

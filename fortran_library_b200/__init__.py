@@ -225,6 +225,46 @@ def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIte
                      WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp)))
 
 
+class History:
+    """The two-loop recursion as a standalone operator (flgpu_history_*; reference LBFGS::Before /
+    After, f90:586-624).  push()/direction() take host arrays or DeviceVectors; direction() returns
+    host copies of p and of the first trial point x1 + p together with f'.p and p.p."""
+
+    def __init__(self, n, memory, stream=None, comm=None):
+        require_gpu()
+        L = lib()
+        L.flgpu_history_create.restype = C.c_void_p
+        L.flgpu_history_create.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+        L.flgpu_history_push.argtypes = [C.c_void_p] * 5
+        L.flgpu_history_direction.argtypes = [C.c_void_p] * 7
+        L.flgpu_history_destroy.argtypes = [C.c_void_p]
+        self.n = int(n)
+        self.h = L.flgpu_history_create(self.n, int(memory), stream, comm)
+        self._p, self._xt = DeviceVector(self.n), DeviceVector(self.n)
+
+    @staticmethod
+    def _dev(v):
+        return v if isinstance(v, DeviceVector) else DeviceVector.from_numpy(v)
+
+    def push(self, x1, x0, g1, g0):
+        vs = [self._dev(v) for v in (x1, x0, g1, g0)]
+        lib().flgpu_history_push(self.h, *[v.ptr for v in vs])
+        lib().flgpu_memcpy(None, None, 0, SPACE_DEVICE, SPACE_DEVICE, None)
+        return vs
+
+    def direction(self, g1, x1):
+        g1, x1 = self._dev(g1), self._dev(x1)
+        gp, pp = C.c_double(), C.c_double()
+        lib().flgpu_history_direction(self.h, g1.ptr, x1.ptr, self._p.ptr, self._xt.ptr, C.addressof(gp),
+                                      C.addressof(pp))
+        return self._p.numpy(), self._xt.numpy(), gp.value, pp.value
+
+    def close(self):
+        if self.h:
+            lib().flgpu_history_destroy(self.h)
+            self.h = None
+
+
 def kernel_times():
     """Per-kernel CUDA-event totals of the last call made with time_kernels=True."""
     cap = 64

@@ -32,7 +32,8 @@ class IterInfo(C.Structure):
     _fields_ = [("iteration", C.c_int64), ("n_local", C.c_int64), ("step", C.c_double),
                 ("f", C.c_double), ("phid0", C.c_double), ("trials", C.c_int64),
                 ("p_dev", C.c_void_p), ("x_dev", C.c_void_p), ("g_dev", C.c_void_p),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("gpu_launches", C.c_int64), ("callbacks", C.c_int64),
+                ("total_trials", C.c_int64)]
 
 
 OBSERVER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(IterInfo))

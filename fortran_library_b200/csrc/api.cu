@@ -21,6 +21,7 @@ struct ThreadState {
     std::vector<KernelTime> times;
     flgpu_observer_fn observer = nullptr;
     void *observer_user = nullptr;
+    CudaBackend *backend = nullptr;   // the call currently executing on this thread
 };
 thread_local ThreadState tls;
 
@@ -51,6 +52,7 @@ int run(bool cg, const flgpu_problem *prob, const flgpu_options *opt, double *x,
     Params P = params_from_options(*opt, cg, prob->f_fd != nullptr);
     ThreadState saved = tls;
     tls.stream = B.stream_handle();
+    tls.backend = &B;
     FLGPU_CUDA_CHECK(cudaGetDevice(&tls.device));
     flgpu_stats st;
     if (cg) run_cg(B, P, x, x_space, &st);
@@ -58,6 +60,7 @@ int run(bool cg, const flgpu_problem *prob, const flgpu_options *opt, double *x,
     B.resolve_times();
     tls.stream = saved.stream;
     tls.device = saved.device;
+    tls.backend = saved.backend;
     tls.last = st;
     tls.times = B.times;
     if (stats) *stats = st;
@@ -194,6 +197,12 @@ int flgpu_current_device(void) { return tls.device; }
 void flgpu_last_stats(flgpu_stats *out) { *out = tls.last; }
 void flgpu_set_observer(flgpu_observer_fn fn, void *user) { tls.observer = fn; tls.observer_user = user; }
 
+void flgpu_reset_kernel_times(void) {
+    if (!tls.backend) return;
+    tls.backend->resolve_times();
+    for (auto &kt : tls.backend->times) { kt.ms = 0.0; kt.launches = 0; kt.bytes = 0.0; }
+}
+
 int flgpu_kernel_times(const char **names, double *ms, int64_t *launches, double *bytes, int cap) {
     int n = 0;
     for (auto &kt : tls.times) {
@@ -299,3 +308,38 @@ void nonlinearoptimization_mp_conjugategradient_basic_(flgpu_ref_f_fn f, flgpu_r
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- two-loop recursion as an operator
+struct flgpu_history {
+    CudaBackend *B;
+    History *H;
+};
+
+extern "C" flgpu_history *flgpu_history_create(int64_t n_local, int memory, void *stream, flgpu_comm *comm) {
+    require_device();
+    flgpu_problem none{};
+    flgpu_options o;
+    flgpu_options_default(&o, 0);
+    o.stream = stream;
+    o.comm = comm;
+    flgpu_history *h = new flgpu_history;
+    h->B = new CudaBackend(none, n_local, o);
+    h->H = new History(*h->B, memory);
+    return h;
+}
+extern "C" int flgpu_history_push(flgpu_history *h, const double *x1_dev, const double *x0_dev, const double *g1_dev,
+                                  const double *g0_dev) {
+    h->H->push(x1_dev, x0_dev, g1_dev, g0_dev);
+    return 0;
+}
+extern "C" int flgpu_history_direction(flgpu_history *h, const double *g1_dev, const double *x1_dev, double *p_dev,
+                                       double *xt_dev, double *gp, double *pp) {
+    h->H->direction(g1_dev, x1_dev, p_dev, xt_dev, gp, pp);
+    return 0;
+}
+extern "C" void flgpu_history_destroy(flgpu_history *h) {
+    if (!h) return;
+    delete h->H;
+    delete h->B;
+    delete h;
+}

@@ -266,12 +266,13 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     return r;
 }
 
-bool observe(const Params &P, Backend &B, int64_t it, double a, double f, double phid0, int64_t trials,
-             const double *p, const double *x, const double *g) {
+bool observe(const Params &P, Backend &B, const flgpu_stats &st, int64_t it, double a, double f, double phid0,
+             int64_t trials, const double *p, const double *x, const double *g) {
     if (!P.observer) return false;
     flgpu_iter_info info;
     info.iteration = it; info.n_local = B.n; info.step = a; info.f = f; info.phid0 = phid0;
     info.trials = trials; info.p_dev = p; info.x_dev = x; info.g_dev = g; info.stream = B.stream_handle();
+    info.gpu_launches = B.launches; info.callbacks = st.n_f + st.n_fd + st.n_f_fd; info.total_trials = st.n_trials;
     return P.observer(P.observer_user, &info) != 0;
 }
 
@@ -322,7 +323,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             a = r.a; fnew = r.fx;
             st.iterations = ++it;
             st.f = fnew;
-            const bool stop = observe(P, B, it - 1, a, fnew, phid0, r.trials, p, xc, gc);
+            const bool stop = observe(P, B, st, it - 1, a, fnew, phid0, r.trials, p, xc, gc);
             // ---- After() f90:609-624 fused with the next Before() f90:586-608
             const bool last = (it >= total) || stop;
             int new_slot, k_after;
@@ -405,7 +406,7 @@ void run_cg(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stat
             a = r.a; fnew = r.fx;
             st.iterations = ++it;
             st.f = fnew;
-            const bool stop = observe(P, B, it - 1, a, fnew, phidold, r.trials, p, xc, gc);
+            const bool stop = observe(P, B, st, it - 1, a, fnew, phidold, r.trials, p, xc, gc);
             // DY() f90:352-372 / PR() f90:373-393
             B.cg_dots(gc, go, p);
             B.fetch(slots); st.host_syncs++;
@@ -436,6 +437,28 @@ void run_cg(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stat
 finish:
     B.download(x_user, xc, x_space);
     st.gpu_launches = B.launches;
+}
+
+}  // namespace flgpu
+
+namespace flgpu {
+
+void History::push(const double *x1, const double *x0, const double *g1, const double *g0) {
+    int new_slot, k_after;
+    if (k_ < mem_) { new_slot = recent_ + 1; k_after = k_ + 1; }   // f90:470,508
+    else { new_slot = (recent_ + 1) % mem_; k_after = mem_; }      // f90:622
+    B.lbfgs_update_dots(x1, x0, g1, g0, new_slot, k_after);
+    B.lbfgs_solve(k_after, new_slot);
+    recent_ = new_slot;
+    k_ = k_after;
+}
+
+void History::direction(const double *g1, const double *x1, double *p, double *xt, double *gp, double *pp) {
+    double slots[NSLOTS];
+    B.lbfgs_direction(p, xt, g1, x1, k_, recent_);
+    B.fetch(slots);
+    if (gp) *gp = slots[SL_GP0];
+    if (pp) *pp = slots[SL_PP];
 }
 
 }  // namespace flgpu

@@ -26,3 +26,23 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
 void run_cg(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *st);
 
 }  // namespace flgpu
+
+namespace flgpu {
+
+// The two-loop recursion as a standalone operator (reference: LBFGS::Before f90:586-608 and the
+// ring-buffer update of After f90:622-623) over the same K1/K2/K3 the optimizer uses.
+class History {
+public:
+    History(Backend &b, int mem) : B(b), mem_(mem > 1 ? mem : 1) { B.lbfgs_alloc(mem_); }
+    // append (or overwrite the oldest) pair s = x1-x0, y = g1-g0; refresh the coefficients for g1
+    void push(const double *x1, const double *x0, const double *g1, const double *g0);
+    // p = -H g1, xt = x1 + p; returns g1.p and p.p
+    void direction(const double *g1, const double *x1, double *p, double *xt, double *gp, double *pp);
+    int count() const { return k_; }
+
+private:
+    Backend &B;
+    int mem_, k_ = 0, recent_ = -1;
+};
+
+}  // namespace flgpu

@@ -90,6 +90,9 @@ typedef struct flgpu_iter_info {
     int64_t trials;     /* x0 + a p formations in this search */
     const double *p_dev, *x_dev, *g_dev;
     void *stream;
+    int64_t gpu_launches; /* library kernels enqueued so far in this call */
+    int64_t callbacks;    /* f + fd + f_fd invocations so far in this call */
+    int64_t total_trials; /* trial points formed so far in this call */
 } flgpu_iter_info;
 typedef int (*flgpu_observer_fn)(void *user, const flgpu_iter_info *info);
 
@@ -214,6 +217,19 @@ int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *o
 int flgpu_vec_trial(double *x_dev, const double *x0_dev, const double *p_dev, double a, int64_t n,
                     void *stream); /* x = x0 + a*p, multiply then add (no FMA), f90:1482 */
 
+/* ------------------------------------------------------------------ two-loop recursion as an operator */
+/* LBFGS::Before (f90:586-608) + the ring-buffer update of After (f90:622-623) on their own, over the
+ * same kernels the optimizer uses: push() appends (or overwrites the oldest of `memory`) the pair
+ * s = x1-x0, y = g1-g0 and prepares the coefficients for g1; direction() forms p = -H g1 and
+ * xt = x1 + p and returns g1.p and p.p.  g1 must be the vector given to the last push(). */
+typedef struct flgpu_history flgpu_history;
+flgpu_history *flgpu_history_create(int64_t n_local, int memory, void *stream, flgpu_comm *comm);
+int flgpu_history_push(flgpu_history *h, const double *x1_dev, const double *x0_dev, const double *g1_dev,
+                       const double *g0_dev);
+int flgpu_history_direction(flgpu_history *h, const double *g1_dev, const double *x1_dev, double *p_dev,
+                            double *xt_dev, double *gp, double *pp);
+void flgpu_history_destroy(flgpu_history *h);
+
 /* ------------------------------------------------------------------ device memory helpers */
 /* Thin wrappers (cudaMalloc / cudaFree / cudaMemcpyAsync + stream sync) so that C, Fortran
  * (iso_c_binding) and ctypes callers need no CUDA runtime binding of their own. */
@@ -227,6 +243,8 @@ const char *flgpu_version(void);
 /* Per-kernel accumulated CUDA-event time of the last call run with time_kernels=1.
  * names/ms/launches/bytes: arrays of capacity cap; returns the number of kernels. */
 int flgpu_kernel_times(const char **names, double *ms, int64_t *launches, double *bytes, int cap);
+/* From inside an observer: zero the accumulators of the call in progress (to time a window). */
+void flgpu_reset_kernel_times(void);
 
 #ifdef __cplusplus
 }

@@ -77,5 +77,34 @@ def cg(kind, x, **kw):
     return _run("flgpu_hostsim_cg", True, kind, x, **kw)
 
 
+class History:
+    """flgpu_hostsim_history_*: the two-loop recursion as an operator (host pointers)."""
+
+    def __init__(self, n, memory):
+        L = lib()
+        L.flgpu_hostsim_history_create.restype = C.c_void_p
+        L.flgpu_hostsim_history_create.argtypes = [C.c_int64, C.c_int]
+        L.flgpu_hostsim_history_push.argtypes = [C.c_void_p] * 5
+        L.flgpu_hostsim_history_direction.argtypes = [C.c_void_p] * 7
+        L.flgpu_hostsim_history_destroy.argtypes = [C.c_void_p]
+        self.n, self.h = n, L.flgpu_hostsim_history_create(n, memory)
+
+    def push(self, x1, x0, g1, g0):
+        self._keep = [np.ascontiguousarray(v, dtype=np.float64) for v in (x1, x0, g1, g0)]
+        lib().flgpu_hostsim_history_push(self.h, *[v.ctypes.data for v in self._keep])
+
+    def direction(self, g1, x1):
+        g1 = np.ascontiguousarray(g1, dtype=np.float64)
+        x1 = np.ascontiguousarray(x1, dtype=np.float64)
+        p, xt = np.empty(self.n), np.empty(self.n)
+        gp, pp = C.c_double(), C.c_double()
+        lib().flgpu_hostsim_history_direction(self.h, g1.ctypes.data, x1.ctypes.data, p.ctypes.data, xt.ctypes.data,
+                                              C.addressof(gp), C.addressof(pp))
+        return p, xt, gp.value, pp.value
+
+    def close(self):
+        lib().flgpu_hostsim_history_destroy(self.h)
+
+
 def set_comm(fn, rank, nranks):
     lib().flgpu_hostsim_set_comm(fn, None, rank, nranks)

@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, HERE, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import _oracle
+    _oracle.lib()
+    return _oracle
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    import _hostsim
+    _hostsim.lib()
+    return _hostsim

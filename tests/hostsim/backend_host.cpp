@@ -228,3 +228,33 @@ int flgpu_hostsim_cg(const flgpu_problem *prob, const flgpu_options *opt, double
 }
 
 }  // extern "C"
+
+// ---- two-loop recursion as an operator (mirror of flgpu_history_* in libflgpu.so)
+struct hostsim_history {
+    HostBackend *B;
+    flgpu::History *H;
+};
+extern "C" {
+hostsim_history *flgpu_hostsim_history_create(int64_t n, int memory) {
+    flgpu_problem none{};
+    hostsim_history *h = new hostsim_history;
+    h->B = new HostBackend(none, n, 0, n);
+    h->H = new flgpu::History(*h->B, memory);
+    return h;
+}
+int flgpu_hostsim_history_push(hostsim_history *h, const double *x1, const double *x0, const double *g1,
+                               const double *g0) {
+    h->H->push(x1, x0, g1, g0);
+    return 0;
+}
+int flgpu_hostsim_history_direction(hostsim_history *h, const double *g1, const double *x1, double *p, double *xt,
+                                    double *gp, double *pp) {
+    h->H->direction(g1, x1, p, xt, gp, pp);
+    return 0;
+}
+void flgpu_hostsim_history_destroy(hostsim_history *h) {
+    delete h->H;
+    delete h->B;
+    delete h;
+}
+}

@@ -1,0 +1,356 @@
+"""GPU parity tests (pytest -m gpu, on the B200 box).  Everything goes through the C-ABI of libflgpu.so
+(ctypes); the oracle (oracle/liboracle.so) is only the checker.  Nothing here reads /root/reference.
+
+Tolerances (BASELINE.json north_star, and DESIGN.md "parity" for why they are applied this way):
+  * integer/index work and element-wise results: bit-exact;
+  * one-step search directions on the oracle's own history: 1e-12 relative;
+  * whole trajectories: within the reference's own summation-order noise (x64) or 1e-12;
+  * minimisers 1e-8 relative, iteration counts 2 % where the oracle itself is that stable.
+"""
+import ctypes as C
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import _cases
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fl():
+    import fortran_library_b200 as fl
+    fl.require_gpu()          # fails loudly: there is no fallback to test instead
+    return fl
+
+
+def _problem(fl, name, use_ffd=True):
+    p = fl.builtin_problem(_cases.OBJECTIVES[name][0])
+    if not use_ffd:
+        p.f_fd = None
+    return p
+
+
+def _dev_start(fl, name, n):
+    kind, st, seed = _cases.OBJECTIVES[name]
+    return fl.DeviceVector.start(st, n, seed=seed)
+
+
+# ----------------------------------------------------------------------------- building blocks
+@pytest.mark.parametrize("name", sorted(_cases.OBJECTIVES))
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 1000, 4097])
+def test_start_vectors_bit_exact(fl, name, n):
+    assert np.array_equal(_dev_start(fl, name, n).numpy(), _cases.start(name, n))
+
+
+@pytest.mark.parametrize("name", ["quartic", "rosenR1", "diag"])
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537])
+def test_objective_kernels_vs_oracle(fl, name, n):
+    """K6: f' bit-exact (same operation order, no FMA), f to summation-order accuracy."""
+    kind = _cases.OBJECTIVES[name][0]
+    rng = np.random.default_rng(n)
+    x = _cases.start(name, n) + 0.01 * rng.standard_normal(n)
+    fo, go = C.c_double(), np.empty(n)
+    O.lib().orc_obj_select(kind, 0, n)
+    O.lib().orc_obj_f_fd(C.byref(fo), go.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)))
+    prob = fl.builtin_problem(kind)
+    xd, gd, fd_ = fl.DeviceVector.from_numpy(x), fl.DeviceVector(n), fl.DeviceVector(2)
+    ctx = fl.capi.EvalCtx(None, None, 0, n, 0, 1, 0)
+    for which in ("f_fd", "f", "fd"):
+        fl.lib().flgpu_memcpy(gd.ptr, np.zeros(n).ctypes.data, n * 8, 1, 0, None)
+        if which == "f_fd":
+            C.cast(prob.f_fd, fl.capi.F_FD_FN)(C.byref(ctx), fd_.ptr, gd.ptr, xd.ptr, n)
+        elif which == "f":
+            C.cast(prob.f, fl.capi.F_FN)(C.byref(ctx), fd_.ptr, xd.ptr, n)
+        else:
+            C.cast(prob.fd, fl.capi.FD_FN)(C.byref(ctx), gd.ptr, xd.ptr, n)
+        if which != "f":
+            assert np.array_equal(gd.numpy(), go), f"{which}: gradient differs"
+        if which != "fd":
+            assert abs(fd_.numpy()[0] - fo.value) <= 1e-13 * abs(fo.value) + 1e-300
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100003, 1 << 20])
+def test_vector_primitives(fl, n):
+    rng = np.random.default_rng(n)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    ad, bd, out = fl.DeviceVector.from_numpy(a), fl.DeviceVector.from_numpy(b), fl.DeviceVector(1)
+    fl.lib().flgpu_vec_dot(ad.ptr, bd.ptr, n, out.ptr, None)
+    exact = math.fsum(a * b)
+    bound = 4e-16 * float(np.sum(np.abs(a * b))) + 1e-300
+    assert abs(out.numpy()[0] - exact) <= bound
+    xd = fl.DeviceVector(n)
+    fl.lib().flgpu_vec_trial(xd.ptr, ad.ptr, bd.ptr, 0.37, n, None)
+    assert np.array_equal(xd.numpy(), a + 0.37 * b)          # multiply then add, no FMA (f90:1482)
+    # determinism: same bits on repetition
+    fl.lib().flgpu_vec_dot(ad.ptr, bd.ptr, n, out.ptr, None)
+    first = out.numpy()[0]
+    for _ in range(3):
+        fl.lib().flgpu_vec_dot(ad.ptr, bd.ptr, n, out.ptr, None)
+        assert out.numpy()[0] == first
+
+
+# ----------------------------------------------------------------------------- parity: strict tier
+@pytest.mark.parametrize("name,mem", [("rosenR1", 10), ("rosenR1", 3), ("quartic", 10), ("diag", 30), ("rosenR0", 5),
+                                      ("quartic", 1), ("rosenR1", 17)])
+def test_one_step_direction_parity_1e12(fl, name, mem):
+    """K1+K2+K3 on the oracle's own history reproduce its next direction to 1e-12 (20 iterations)."""
+    _cases.check_one_step(fl.History, name, mem, n=10_000)
+
+
+@pytest.mark.parametrize("mem", [1, 2, 5, 10, 30, 33, 64])
+def test_two_loop_operator_all_kernel_shapes(fl, mem):
+    """Every (columns-per-group, groups) instantiation of K1 and the two-slot-per-lane path of K2
+    against the extended-precision two-loop on random (well-conditioned) pairs."""
+    n = 5003
+    rng = np.random.default_rng(mem)
+    d = np.exp(rng.uniform(0, 2, n))                     # SPD diagonal Hessian: y = d * s keeps s.y > 0
+    h = fl.History(n, mem)
+    x0, pairs = rng.standard_normal(n), []
+    g0 = d * x0
+    for k in range(mem + 3):
+        x1 = x0 + 0.1 * rng.standard_normal(n)
+        g1 = d * x1
+        h.push(x1, x0, g1, g0)
+        pairs = (pairs + [(x1 - x0, g1 - g0)])[-mem:]
+        p, xt, gp, pp = h.direction(g1, x1)
+        exact = _cases.two_loop_extended(pairs, g1)
+        assert _cases.rel(p, exact) < 1e-12, (mem, k)
+        assert np.array_equal(xt, x1 + p)
+        x0, g0 = x1, g1
+    h.close()
+
+
+# ----------------------------------------------------------------------------- parity: trajectories
+@pytest.mark.parametrize("name,kw", [
+    ("rosenR0", dict(Memory=10)), ("rosenR1", dict(Memory=10)), ("rosenR1", dict(Memory=5)),
+    ("quartic", dict(Memory=10)), ("diag", dict(Memory=30, MaxIteration=40)),
+    ("rosenR1", dict(Memory=1, MaxIteration=30)), ("rosenR1", dict(Memory=10, Strong=False, MaxIteration=30)),
+    ("rosenR1", dict(Memory=10, use_ffd=False)),
+])
+def test_lbfgs_trajectory_within_oracle_envelope(fl, name, kw):
+    n = 10_000                                             # BASELINE.json configs[0]
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.lbfgs(cbs, x, use_ffd=use, **k), **kw)
+    ob = fl.Observer(keep_vectors=True, max_vec_iters=20)
+    x = _dev_start(fl, name, n)
+    st = fl.LBFGS(_problem(fl, name, use), x, observer=ob, Warning=False, **kw)
+    _cases.check_envelope(traces, ob.p, f"lbfgs {name} {kw}")
+    assert np.array_equal(ob.p[0], traces[0].p[0])         # steepest-descent step: bit-exact direction
+    assert st.gpu_launches > 0
+
+
+@pytest.mark.parametrize("method", ["DY", "PR"])
+@pytest.mark.parametrize("name,kw", [("quartic", dict()), ("rosenR1", dict(MaxIteration=60)),
+                                     ("diag", dict(MaxIteration=60)), ("quartic", dict(Strong=False, MaxIteration=60)),
+                                     ("quartic", dict(use_ffd=False))])
+def test_cg_trajectory_within_oracle_envelope(fl, method, name, kw):
+    n = 10_000
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.cg(cbs, x, Method=method, use_ffd=use, **k), **kw)
+    ob = fl.Observer(keep_vectors=True, max_vec_iters=20)
+    x = _dev_start(fl, name, n)
+    fl.ConjugateGradient(_problem(fl, name, use), x, Method=method, observer=ob, Warning=False, **kw)
+    _cases.check_envelope(traces, ob.p, f"cg {method} {name} {kw}")
+
+
+def test_minimisers_and_iteration_counts(fl):
+    n = 10_000
+    for name in ("rosenR0", "rosenR1"):
+        kind = _cases.OBJECTIVES[name][0]
+        x0 = _cases.start(name, n)
+        runs = [O.lbfgs(O.builtin_callbacks(kind, 0, n), x0.copy(), use_ffd=True, Warning=False, sum_mode=m)
+                for m in (0, 1, 2)]
+        x = _dev_start(fl, name, n)
+        st = fl.LBFGS(_problem(fl, name), x, Warning=False)
+        assert _cases.rel(x.numpy(), runs[0][0]) < 1e-8          # minimiser, relative 1e-8
+        its = [r[1].n_iter for r in runs]
+        spread = (max(its) - min(its)) / min(its)
+        assert abs(st.iterations - its[0]) / its[0] <= max(0.02, 1.5 * spread)
+        assert st.status == runs[0][1].status
+    # CG on the quartic (config 3): x* = 0, scale by |x0| (SURVEY.md 7 "x*=0 objectives")
+    x0 = _cases.start("quartic", n)
+    for M in ("DY", "PR"):
+        xr, sr = O.cg(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Method=M, use_ffd=True, Warning=False)
+        x = _dev_start(fl, "quartic", n)
+        st = fl.ConjugateGradient(_problem(fl, "quartic"), x, Method=M, Warning=False)
+        assert np.linalg.norm(x.numpy() - xr) / np.linalg.norm(x0) < 1e-5
+        assert abs(st.iterations - sr.n_iter) <= max(2, 0.05 * sr.n_iter)
+
+
+# ----------------------------------------------------------------------------- Fortran ABI (drop-in)
+def _ref_call_cg(fl, cf, cfd, cffd, x, method, use, maxit):
+    L = fl.lib()
+    keep = (fl.capi.REF_F_FN(cf), fl.capi.REF_FD_FN(cfd), fl.capi.REF_F_FD_FN(cffd))
+    dim = C.c_int(x.size)
+    m = method.encode()
+    L.flgpu_set_callback_space(fl.SPACE_HOST)
+    try:
+        L.__getattr__("__nonlinearoptimization_MOD_conjugategradient")(
+            keep[0], keep[1], x.ctypes.data_as(C.c_void_p), C.byref(dim), m, keep[2] if use else None,
+            None, C.byref(C.c_int32(0)), C.byref(C.c_int(maxit)), None, None, None, None, None, C.c_int(len(m)))
+    finally:
+        L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+    st = fl.capi.Stats()
+    L.flgpu_last_stats(C.byref(st))
+    return st
+
+
+@pytest.mark.parametrize("case", sorted(_cases.TORTURE_1D))
+@pytest.mark.parametrize("method", ["DY", "PR"])
+def test_fortran_abi_torture_1d_bitwise(fl, case, method):
+    """The reference's own symbol (__nonlinearoptimization_MOD_conjugategradient), absent optionals as
+    NULL, host callbacks staged through pinned memory.  dim = 1 has no summation order, so every trial
+    point and the result must equal the oracle's bit for bit -- through every Strong-Wolfe branch."""
+    x0, (f, g) = _cases.TORTURE_1D[case]
+    for use in (False, True):
+        if use and case in _cases.TORTURE_NO_FFD:
+            continue
+        fa = _cases.Fuse(f, g)
+        cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
+        keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+        xa, s = O.cg(tuple(C.cast(k, C.c_void_p) for k in keep), np.array([x0]), Method=method, use_ffd=use,
+                     Warning=False, MaxIteration=30)
+        fb = _cases.Fuse(f, g)
+        cf2, cfd2, cffd2 = _cases.make_ref_callbacks(fb.f, fb.g, fb.fg)
+        x = np.array([x0])
+        st = _ref_call_cg(fl, cf2, cfd2, cffd2, x, method, use, 30)
+        assert fa.xs == fb.xs, "different trial points"
+        assert np.array_equal(x, xa, equal_nan=True)
+        assert st.iterations == s.n_iter and st.status == s.status
+
+
+def test_fortran_abi_device_callbacks_lbfgs(fl):
+    """__nonlinearoptimization_MOD_lbfgs with the built-in CUDA objective in reference-ABI form: host x
+    in/out, device pointers in the callbacks (the default spaces)."""
+    n = 10_000
+    L = fl.lib()
+    f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
+    L.flgpu_builtin_ref_callbacks(fl.OBJ_ROSENBROCK, C.byref(f), C.byref(fd), C.byref(ffd))
+    x = _cases.start("rosenR0", n)
+    xr, sr = O.lbfgs(O.builtin_callbacks(O.OBJ_ROSENBROCK, 0, n), x.copy(), use_ffd=True, Warning=False)
+    L.__getattr__("__nonlinearoptimization_MOD_lbfgs")(
+        f, fd, x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)), C.byref(C.c_int(10)), ffd, None,
+        C.byref(C.c_int32(0)), None, None, None, None, None, None)
+    st = fl.capi.Stats()
+    L.flgpu_last_stats(C.byref(st))
+    assert st.iterations == sr.n_iter and _cases.rel(x, xr) < 1e-8
+    # ifort spelling of the same entry point
+    x2 = _cases.start("rosenR0", n)
+    L.nonlinearoptimization_mp_lbfgs_(f, fd, x2.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)), None, ffd, None,
+                                      C.byref(C.c_int32(0)), None, None, None, None, None, None)
+    assert np.array_equal(x2, x)
+
+
+def test_cpp_dropin_program_runs(fl, tmp_path):
+    """tests/link/cpp_dropin.cpp = the reference's test.cpp optimizer section with host callbacks."""
+    exe = tmp_path / "cpp_dropin"
+    libdir = os.path.join(ROOT, "fortran_library_b200")
+    subprocess.run(["g++", "-std=c++11", os.path.join(ROOT, "tests", "link", "cpp_dropin.cpp"), "-o", str(exe),
+                    "-L" + libdir, "-lflgpu", "-Wl,-rpath," + libdir], check=True)
+    env = dict(os.environ, FLGPU_CALLBACK_SPACE="host")
+    r = subprocess.run([str(exe)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ----------------------------------------------------------------------------- edge cases
+def test_edge_cases(fl):
+    for fn in (fl.LBFGS, fl.ConjugateGradient):                 # start at the minimiser (f90:443 / 237)
+        x = fl.DeviceVector.from_numpy(np.ones(10))
+        st = fn(_problem(fl, "rosenR0"), x, Warning=False)
+        assert st.status == fl.INITIAL_CONVERGED and st.iterations == 0 and np.array_equal(x.numpy(), np.ones(10))
+    for n in (1, 2, 3, 7, 33, 1001):                            # tiny, odd, not a multiple of the vector width
+        x0 = _cases.start("quartic", n)
+        xr, sr = O.lbfgs(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Memory=4, Warning=False, MaxIteration=5)
+        x = fl.DeviceVector.from_numpy(x0)
+        st = fl.LBFGS(_problem(fl, "quartic", False), x, Memory=4, Warning=False, MaxIteration=5)
+        assert st.iterations == sr.n_iter and _cases.rel(x.numpy(), xr) < 1e-6, n
+    # host x (numpy, updated in place) equals device x
+    n = 4097
+    xh = _cases.start("rosenR1", n)
+    fl.LBFGS(_problem(fl, "rosenR1"), xh, Warning=False, MaxIteration=20)
+    xd = _dev_start(fl, "rosenR1", n)
+    fl.LBFGS(_problem(fl, "rosenR1"), xd, Warning=False, MaxIteration=20)
+    assert np.array_equal(xh, xd.numpy())                       # deterministic: bitwise repeatable
+    # MaxIteration = 0 runs the steepest-descent step and the Memory-1 pre-iterations only (f90:448-510)
+    x = _dev_start(fl, "rosenR1", 100)
+    st = fl.LBFGS(_problem(fl, "rosenR1"), x, Memory=4, Warning=False, MaxIteration=0)
+    assert st.iterations == 4 and st.status == fl.MAX_ITERATION and st.n_f_fd == 1
+
+
+def test_memory_above_limit_aborts_with_message(fl):
+    code = ("import sys; sys.path.insert(0, %r)\nimport fortran_library_b200 as fl\n"
+            "x = fl.DeviceVector.start(fl.START_ROSEN_PERT, 100, seed=7)\n"
+            "fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=65, Warning=False)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "exceeds the supported maximum" in r.stderr
+
+
+# ----------------------------------------------------------------------------- full size (BASELINE configs[1], [2])
+def test_full_size_properties(fl):
+    """n = 2^28: size-independent properties.  (a) exact dots of exactly representable data;
+    (b) x0 + 0*p == x0; (c) every accepted L-BFGS step satisfies the strong Wolfe conditions it was
+    searched for and f decreases monotonically; (d) two runs give identical bits."""
+    n = 1 << 28
+    L = fl.lib()
+    ones = fl.DeviceVector.start(fl.START_ROSEN_STD, n)          # (-1.2, 1, -1.2, 1, ...)
+    out = fl.DeviceVector(1)
+    L.flgpu_vec_dot(ones.ptr, ones.ptr, n, out.ptr, None)
+    assert abs(out.numpy()[0] - (n // 2) * (1.44 + 1.0)) <= 1e-9 * n
+    xz, z = fl.DeviceVector(n), fl.DeviceVector(n)
+    L.flgpu_memcpy(z.ptr, ones.ptr, n * 8, 1, 1, None)
+    L.flgpu_vec_trial(xz.ptr, ones.ptr, z.ptr, 0.0, n, None)
+    L.flgpu_vec_dot(xz.ptr, ones.ptr, n, out.ptr, None)
+    first = out.numpy()[0]
+    L.flgpu_vec_dot(ones.ptr, ones.ptr, n, out.ptr, None)
+    assert out.numpy()[0] == first
+    for v in (ones, xz, z):
+        v.free()
+
+    results = []
+    for rep in range(2):
+        rows = []
+
+        def on_iter(i, rows=rows):
+            gp = fl.DeviceVector(1)
+            L.flgpu_vec_dot(i.g_dev, i.p_dev, n, gp.ptr, i.stream)
+            L.flgpu_memcpy(None, None, 0, 1, 1, i.stream)
+            rows.append((i.f, i.step, i.phid0, gp.numpy()[0]))
+            return False
+        x = fl.DeviceVector.start(fl.START_ROSEN_PERT, n, seed=7)
+        ob = fl.Observer(on_iteration=on_iter)
+        st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=10, Warning=False, MaxIteration=6, observer=ob)
+        assert st.iterations == 16
+        L.flgpu_vec_dot(x.ptr, x.ptr, n, out.ptr, None)
+        results.append((out.numpy()[0], st.f, st.n_trials, [r[:3] for r in rows]))
+        f_prev = None
+        for k, (f, a, phid0, gp) in enumerate(rows):
+            assert phid0 < 0.0
+            if f_prev is not None:
+                assert f <= f_prev + 1e-4 * a * phid0 + 1e-9 * abs(f_prev), k     # sufficient decrease, c1 = 1e-4
+                assert abs(gp) <= 0.9 * abs(phid0) * (1 + 1e-9), k                # curvature, c2 = 0.9
+            f_prev = f
+        x.free()
+    assert results[0] == results[1], "two identical runs must give identical bits"
+
+
+def test_full_size_cg_quartic(fl):
+    """BASELINE configs[2]: CG DY and PR+ on the separable quartic, n = 2^28: monotone decrease and the
+    closed-form symmetry of the problem (f = sum x^4 decreases; x stays in [0,1))."""
+    n = 1 << 28
+    for M in ("DY", "PR"):
+        x = fl.DeviceVector.start(fl.START_QUARTIC_U, n, seed=12345)
+        ob = fl.Observer()
+        st = fl.ConjugateGradient(fl.builtin_problem(fl.OBJ_QUARTIC), x, Method=M, Warning=False, MaxIteration=5,
+                                  observer=ob)
+        fs = [r[2] for r in ob.rows]
+        assert st.iterations == 5 and all(b < a for a, b in zip(fs, fs[1:]))
+        x.free()
