@@ -17,6 +17,35 @@
 
 static int g_kind = ORC_OBJ_QUARTIC;
 static long long g_offset = 0, g_nglobal = 0;
+static int g_fsum_mode = 0;
+
+/* Summation order of the objective value, to bound its share of the summation-order noise:
+ * 0 = sequential double (what the reference's own test callback does, test.f90:630-640),
+ * 1 = long double, 2 = pairwise (binary-counter cascade).  Gradients do not depend on it. */
+void orc_obj_set_sum_mode(int mode) { g_fsum_mode = mode; }
+
+typedef struct {
+    int mode, top;
+    unsigned long count;
+    double s;
+    long double sl;
+    double stack[64];
+} facc_t;
+static void facc_init(facc_t *A) { A->mode = g_fsum_mode; A->top = 0; A->count = 0; A->s = 0.0; A->sl = 0.0L; }
+static void facc_add(facc_t *A, double v) {
+    if (A->mode == 0) { A->s = A->s + v; return; }
+    if (A->mode == 1) { A->sl += (long double)v; return; }
+    unsigned long c = ++A->count;
+    while ((c & 1ul) == 0) { v = A->stack[--A->top] + v; c >>= 1; }
+    A->stack[A->top++] = v;
+}
+static double facc_value(facc_t *A) {
+    if (A->mode == 0) return A->s;
+    if (A->mode == 1) return (double)A->sl;
+    double s = 0.0;
+    while (A->top > 0) s = A->stack[--A->top] + s;
+    return s;
+}
 static double T0[256], T1[256], T2[256];
 static int g_tables = 0;
 
@@ -69,11 +98,12 @@ void orc_obj_start(int start_kind, unsigned long long seed, double *x, long long
 }
 
 static int eval(double *fx, double *g, const double *x, int n) {
-    double f = 0.0;
+    facc_t f;
+    facc_init(&f);
     if (g_kind == ORC_OBJ_QUARTIC) {
         for (int i = 0; i < n; i++) {
             const double x2 = x[i] * x[i];
-            if (fx) f = f + x2 * x2;
+            if (fx) facc_add(&f, x2 * x2);
             if (g) g[i] = 4.0 * (x2 * x[i]);
         }
     } else if (g_kind == ORC_OBJ_ROSENBROCK) {
@@ -82,23 +112,23 @@ static int eval(double *fx, double *g, const double *x, int n) {
         for (; i + 1 < n; i += 2) {
             const double a = x[i], b = x[i + 1];
             const double t1 = b - a * a, t2 = 1.0 - a;
-            if (fx) f = f + ((100.0 * t1) * t1 + t2 * t2);
+            if (fx) facc_add(&f, (100.0 * t1) * t1 + t2 * t2);
             if (g) { g[i] = (-400.0 * a) * t1 - 2.0 * t2; g[i + 1] = 200.0 * t1; }
         }
         if (i < n) { /* unpaired last element of an odd-length problem */
             const double t2 = 1.0 - x[i];
-            if (fx) f = f + t2 * t2;
+            if (fx) facc_add(&f, t2 * t2);
             if (g) g[i] = -2.0 * t2;
         }
     } else {
         for (int i = 0; i < n; i++) {
             const double d = orc_diag_coeff(g_offset + i, g_nglobal);
             const double t = x[i] - 1.0;
-            if (fx) f = f + ((0.5 * d) * t) * t;
+            if (fx) facc_add(&f, ((0.5 * d) * t) * t);
             if (g) g[i] = d * t;
         }
     }
-    if (fx) *fx = f;
+    if (fx) *fx = facc_value(&f);
     return 0;
 }
 

@@ -25,7 +25,7 @@ static int g_sum_mode = 0;
 static orc_stats_t g_st;
 
 void orc_set_trace(orc_trace_t cb, void *user) { g_trace = cb; g_trace_user = user; }
-void orc_set_sum_mode(int mode) { g_sum_mode = mode; }
+void orc_set_sum_mode(int mode) { g_sum_mode = mode; orc_obj_set_sum_mode(mode); }
 void orc_get_stats(orc_stats_t *out) { *out = g_st; }
 
 /* ------------------------------------------------------------------ primitives (a8) */

@@ -95,6 +95,9 @@ enum { ORC_START_QUARTIC_U = 0, ORC_START_ROSEN_STD = 1, ORC_START_ROSEN_PERT = 
 /* Select the objective the three callbacks below evaluate.  offset/n_global let a
  * row shard be evaluated (index-dependent objectives). */
 void orc_obj_select(int kind, long long offset, long long n_global);
+/* summation order of the objective VALUE (0 sequential = reference test callback, 1 long double,
+ * 2 pairwise); orc_set_sum_mode() sets it too, so the noise envelope covers every reduction. */
+void orc_obj_set_sum_mode(int mode);
 void orc_obj_f(double *fx, const double *x, const int *dim);
 void orc_obj_fd(double *fdx, const double *x, const int *dim);
 int orc_obj_f_fd(double *fx, double *fdx, const double *x, const int *dim);

@@ -172,9 +172,13 @@ public:
 };
 
 // ---- objective adapters over oracle/objectives.c (host pointers)
+// The simulator sums f pairwise (a GPU callback cannot sum sequentially either), so CPU tests see the
+// same kind of objective-value noise the CUDA objective kernels produce.
+int g_obj_sum_mode = 2;
 void obj_f(const flgpu_eval_ctx *c, double *f, const double *x, int64_t n) {
     int d = (int)n;
     orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
+    orc_obj_set_sum_mode(g_obj_sum_mode);
     orc_obj_f(f, x, &d);
 }
 void obj_fd(const flgpu_eval_ctx *c, double *g, const double *x, int64_t n) {
@@ -185,6 +189,7 @@ void obj_fd(const flgpu_eval_ctx *c, double *g, const double *x, int64_t n) {
 void obj_ffd(const flgpu_eval_ctx *c, double *f, double *g, const double *x, int64_t n) {
     int d = (int)n;
     orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
+    orc_obj_set_sum_mode(g_obj_sum_mode);
     orc_obj_f_fd(f, g, x, &d);
 }
 
@@ -195,6 +200,8 @@ extern "C" {
 void flgpu_hostsim_set_comm(allgather_fn fn, void *user, int rank, int nranks) {
     g_allgather = fn; g_allgather_user = user; g_rank = rank; g_nranks = nranks;
 }
+
+void flgpu_hostsim_set_obj_sum_mode(int mode) { g_obj_sum_mode = mode; }
 
 void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->f = obj_f; out->fd = obj_fd; out->f_fd = obj_ffd; out->user = (void *)(intptr_t)kind;
