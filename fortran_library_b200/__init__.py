@@ -122,14 +122,17 @@ def builtin_problem(kind):
     return p
 
 
-def make_problem(f, fd, f_fd=None, user=None):
+def make_problem(f, fd, f_fd=None, user=None, fused=None):
     """Wrap Python callables (ctx, f_dev, x_dev, n) / (ctx, g_dev, x_dev, n) / (ctx, f_dev, g_dev, x_dev, n)
-    as device callbacks.  The returned object keeps the ctypes thunks alive."""
+    [/ fused: (ctx, flags, f_dev, gp_dev, x_out, g_out, x0_dev, p_dev, a, n)] as device callbacks.
+    The returned object keeps the ctypes thunks alive."""
     p = capi.Problem()
-    keep = [capi.F_FN(f), capi.FD_FN(fd), capi.F_FD_FN(f_fd) if f_fd is not None else None]
+    keep = [capi.F_FN(f), capi.FD_FN(fd), capi.F_FD_FN(f_fd) if f_fd is not None else None,
+            capi.FUSED_FN(fused) if fused is not None else None]
     p.f = C.cast(keep[0], C.c_void_p)
     p.fd = C.cast(keep[1], C.c_void_p)
     p.f_fd = C.cast(keep[2], C.c_void_p) if keep[2] is not None else None
+    p.fused = C.cast(keep[3], C.c_void_p) if keep[3] is not None else None
     p.user = user
     p._keep = keep
     return p
@@ -169,6 +172,7 @@ def default_options(for_cg=False):
 def _run(fn, for_cg, problem, x, n, x_space, observer, stream, comm, offset, n_global, time_kernels, kw):
     require_gpu()
     o = default_options(for_cg)
+    o.no_fused = int(not kw.pop("fused", True))
     capi.apply_options(o, **kw)
     o.stream = stream
     o.comm = comm
@@ -199,10 +203,11 @@ def _resolve_x(x):
 
 def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
           MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None,
-          comm=None, offset=0, n_global=0, time_kernels=False):
+          comm=None, offset=0, n_global=0, time_kernels=False, fused=True):
     """Limited-memory BFGS (reference: LBFGS, NonlinearOptimization.f90:398-625).  x is updated in
     place with the minimiser; returns the run statistics.  `problem.f_fd` present selects the
-    _fdwithf line searcher exactly as the reference's optional f_fd does."""
+    _fdwithf line searcher exactly as the reference's optional f_fd does.  fused=False ignores
+    `problem.fused` (trial points are then materialised and the plain callbacks called)."""
     ptr, n, space = _resolve_x(x)
     return _run(lib().flgpu_lbfgs, False, problem, ptr, n, space, observer, stream, comm, offset, n_global,
                 time_kernels, dict(Memory=Memory, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
@@ -212,7 +217,7 @@ def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None,
 
 def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
                       MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None,
-                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False):
+                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True):
     """Nonlinear conjugate gradient, Method 'DY' (default) or 'PR' (reference: ConjugateGradient,
     f90:193-394; no_clamp=True gives ConjugateGradient_basic, f90:2249-2346)."""
     if Method is not None and Method not in ("DY", "PR", CG_DY, CG_PR):
@@ -222,7 +227,7 @@ def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIte
                 n_global, time_kernels,
                 dict(Method=Method, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                      Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                     WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp)))
+                     WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp), fused=fused))
 
 
 class History:

@@ -24,8 +24,15 @@ REF_FD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
 REF_F_FD_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.POINTER(C.c_int))
 
 
+# fused line-search evaluation (flgpu_fused_fn)
+WANT_F, WANT_GP, WRITE_X, WRITE_G = 1, 2, 4, 8
+FUSED_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                       C.c_void_p, C.c_void_p, C.c_double, C.c_int64)
+
+
 class Problem(C.Structure):
-    _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p)]
+    _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p),
+                ("fused", C.c_void_p)]
 
 
 class IterInfo(C.Structure):
@@ -45,7 +52,7 @@ class Options(C.Structure):
                 ("wolfe_c1", C.c_double), ("wolfe_c2", C.c_double), ("increment", C.c_double),
                 ("no_clamp", C.c_int), ("stream", C.c_void_p), ("comm", C.c_void_p),
                 ("offset", C.c_int64), ("n_global", C.c_int64), ("observer", C.c_void_p),
-                ("observer_user", C.c_void_p), ("time_kernels", C.c_int)]
+                ("observer_user", C.c_void_p), ("time_kernels", C.c_int), ("no_fused", C.c_int)]
 
 
 class Stats(C.Structure):

@@ -1,6 +1,8 @@
 // api.cu -- the C-ABI of libflgpu.so (include/flgpu.h): flgpu_* entry points and the reference's
 // own compiled symbol names (__nonlinearoptimization_MOD_* / nonlinearoptimization_mp_*_).
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -12,7 +14,16 @@
 
 using namespace flgpu;
 
+namespace flgpu {
+flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f);   // objectives.cu
+}
+
 namespace {
+
+// flgpu_register_fused: reference-ABI objective -> fused line-search evaluation
+struct FusedEntry { flgpu_fused_fn fn; void *user; };
+std::mutex g_fused_mu;
+std::map<flgpu_ref_f_fn, FusedEntry> g_fused;
 
 struct ThreadState {
     void *stream = nullptr;
@@ -74,7 +85,16 @@ struct RefAdapter {
     flgpu_ref_f_fd_fn f_fd;
     int cb_space;
     double *xh = nullptr, *gh = nullptr;  // pinned staging (callback space HOST)
+    flgpu_fused_fn fused = nullptr;       // registered with flgpu_register_fused for this f
+    void *fused_user = nullptr;
 };
+void ad_fused(const flgpu_eval_ctx *c, int flags, double *f_dev, double *gp_dev, double *x_out, double *g_out,
+              const double *x0, const double *p, double a, int64_t n) {
+    const RefAdapter *A = (const RefAdapter *)c->user;
+    flgpu_eval_ctx inner = *c;
+    inner.user = A->fused_user;
+    A->fused(&inner, flags, f_dev, gp_dev, x_out, g_out, x0, p, a, n);
+}
 void to_host(const RefAdapter *A, const double *x_dev, int64_t n, cudaStream_t s) {
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(A->xh, x_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -126,8 +146,20 @@ void run_ref(bool cg, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_
     }
     flgpu_problem prob;
     prob.f = ad_f; prob.fd = ad_fd; prob.f_fd = f_fd ? ad_ffd : nullptr; prob.user = &A;
+    prob.fused = nullptr;
+    if (A.cb_space == FLGPU_SPACE_DEVICE) {
+        {
+            std::lock_guard<std::mutex> lock(g_fused_mu);
+            auto it = g_fused.find(f);
+            if (it != g_fused.end()) { A.fused = it->second.fn; A.fused_user = it->second.user; }
+        }
+        if (!A.fused) A.fused = builtin_fused_for(f);
+        if (A.fused) prob.fused = ad_fused;
+    }
     o.observer = tls.observer;
     o.observer_user = tls.observer_user;
+    const char *nf = std::getenv("FLGPU_NO_FUSED");
+    if (nf && nf[0] && nf[0] != '0') o.no_fused = 1;
     run(cg, &prob, &o, x, dim, x_space_now(), nullptr);
     if (A.xh) cudaFreeHost(A.xh);
     if (A.gh) cudaFreeHost(A.gh);
@@ -196,6 +228,11 @@ void *flgpu_current_stream(void) { return tls.stream; }
 int flgpu_current_device(void) { return tls.device; }
 void flgpu_last_stats(flgpu_stats *out) { *out = tls.last; }
 void flgpu_set_observer(flgpu_observer_fn fn, void *user) { tls.observer = fn; tls.observer_user = user; }
+void flgpu_register_fused(flgpu_ref_f_fn f, flgpu_fused_fn fused, void *user) {
+    std::lock_guard<std::mutex> lock(g_fused_mu);
+    if (fused) g_fused[f] = FusedEntry{fused, user};
+    else g_fused.erase(f);
+}
 
 void flgpu_reset_kernel_times(void) {
     if (!tls.backend) return;

@@ -45,6 +45,12 @@ public:
     virtual void eval_g(const double *x, double *g) = 0;
     virtual void eval_fg(const double *x, double *g) = 0;
 
+    // ---- fused line-search evaluation (flgpu_fused_fn): x = x0 + a*p formed inside the objective kernel;
+    // f -> SL_F, f'(x).p -> SL_GP, x / f' stored only when asked (flags = FLGPU_WANT_* | FLGPU_WRITE_*)
+    virtual bool fused_available() const { return false; }
+    virtual void fused_eval(int /*flags*/, double /*a*/, const double * /*x0*/, const double * /*p*/,
+                            double * /*x_out*/, double * /*g_out*/) {}
+
     // ---- primitives
     virtual void trial_x(double *x, const double *x0, const double *p, double a) = 0;  // x = x0 + a*p
     virtual void dot(const double *a, const double *b, int slot) = 0;
@@ -57,7 +63,8 @@ public:
                                    const double *g0, int new_slot, int k_after) = 0;
     // K2: two-loop recursion carried out on the (2k+1)-dimensional Gram representation.
     virtual void lbfgs_solve(int k, int recent) = 0;
-    // K3: p = -H g1 from the coefficients of K2, xt = x1 + p, g1.p -> SL_GP0, p.p -> SL_PP.
+    // K3: p = -H g1 from the coefficients of K2, xt = x1 + p (skipped when xt is null), g1.p -> SL_GP0,
+    //     p.p -> SL_PP.
     virtual void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
                                  int recent) = 0;
 

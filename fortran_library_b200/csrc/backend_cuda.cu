@@ -264,6 +264,15 @@ void CudaBackend::eval_fg(const double *x, double *g) {
     time_end(t);
 }
 
+void CudaBackend::fused_eval(int flags, double a, const double *x0, const double *p, double *x_out,
+                             double *g_out) {
+    const char *name = (flags & (FLGPU_WRITE_X | FLGPU_WRITE_G)) ? "callback:fused_store" : "callback:fused_probe";
+    const double words = 2.0 + ((flags & FLGPU_WRITE_X) ? 1.0 : 0.0) + ((flags & FLGPU_WRITE_G) ? 1.0 : 0.0);
+    const int t = time_begin(name, 8.0 * n * words);
+    prob.fused(&ctx, flags, R + SL_F, R + SL_GP, x_out, g_out, x0, p, a, n);
+    time_end(t);
+}
+
 // ---- primitives
 void CudaBackend::trial_x(double *x, const double *x0, const double *p, double a) {
     const int t = time_begin("trial_x", 24.0 * n);
@@ -347,7 +356,7 @@ void CudaBackend::lbfgs_solve(int kk, int recent) {
 
 void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int kk,
                                   int recent) {
-    const int t = time_begin("k3_direction", 8.0 * n * (2.0 * kk + 4.0));
+    const int t = time_begin("k3_direction", 8.0 * n * (2.0 * kk + (xt ? 4.0 : 2.0)));
     k::K3Args a;
     a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n;
     a.m = mem; a.k = kk; a.recent = recent; a.w = work; a.R = R;

@@ -50,6 +50,8 @@ public:
     void eval_f(const double *x) override;
     void eval_g(const double *x, double *g) override;
     void eval_fg(const double *x, double *g) override;
+    bool fused_available() const override { return prob.fused != nullptr; }
+    void fused_eval(int flags, double a, const double *x0, const double *p, double *x_out, double *g_out) override;
     void trial_x(double *x, const double *x0, const double *p, double a) override;
     void dot(const double *a, const double *b, int slot) override;
     void neg(double *p, const double *g) override;

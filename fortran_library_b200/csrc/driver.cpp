@@ -39,6 +39,7 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
     }
     P.incr = std::fmax(1.0 + 1e-15, o.increment);                           // f90:1478
     P.has_f_fd = has_f_fd;
+    P.fused = !o.no_fused;
     P.observer = o.observer;
     P.observer_user = o.observer_user;
     (void)for_cg;
@@ -77,12 +78,53 @@ struct Search {
     double fx() { if (f_pending) sync(); return fx_; }
     void set_fx(double v) { f_pending = false; fx_ = v; }
 
-    void form(double step) { B.trial_x(xt, x0, p, step); trials++; st.n_trials++; }  // x=x0+a*p
-    void call_f() { B.eval_f(xt); st.n_f++; f_pending = true; }
-    void call_fd() { B.eval_g(xt, gt); st.n_fd++; }
-    void call_ffd() { B.eval_fg(xt, gt); st.n_f_fd++; f_pending = true; }
+    // Fused mode (flgpu_fused_fn): a trial point exists only as its step a_x until the search returns;
+    // each callback of the reference becomes one probe kernel that forms x0+a_x*p on the fly, and
+    // finish() stores the point and gradient the reference would have left in x / fdx.
+    bool fused = false;
+    double a_x = 0.0, a_g = 0.0;   // step of the last point formed / of the last gradient evaluated
+    bool have_x = false, have_g = false;
+
+    void form(double step) {                                                         // x=x0+a*p
+        if (fused) { a_x = step; have_x = true; }
+        else B.trial_x(xt, x0, p, step);
+        trials++; st.n_trials++;
+    }
+    void call_f() {
+        if (fused) B.fused_eval(FLGPU_WANT_F, a_x, x0, p, nullptr, nullptr); else B.eval_f(xt);
+        st.n_f++; f_pending = true;
+    }
+    void call_fd() {
+        if (fused) { B.fused_eval(FLGPU_WANT_GP, a_x, x0, p, nullptr, nullptr); a_g = a_x; have_g = true; }
+        else B.eval_g(xt, gt);
+        st.n_fd++;
+    }
+    void call_ffd() {
+        if (fused) { B.fused_eval(FLGPU_WANT_F | FLGPU_WANT_GP, a_x, x0, p, nullptr, nullptr); a_g = a_x; have_g = true; }
+        else B.eval_fg(xt, gt);
+        st.n_f_fd++; f_pending = true;
+    }
     void both() { if (fdwithf) call_ffd(); else { call_f(); call_fd(); } }
-    double slope() { B.dot(gt, p, SL_GP); sync(); return slots[SL_GP]; }             // dot_product(fdx,p)
+    double slope() {                                                                 // dot_product(fdx,p)
+        if (!fused) B.dot(gt, p, SL_GP);       // fused: f'.p was reduced by the probe that evaluated f'
+        sync();
+        return slots[SL_GP];
+    }
+    // the caller's chain already formed the first trial point (and evaluated it)
+    void adopt_pre() {
+        trials++; set_fx(pre_f);
+        a_x = a; have_x = true;
+        if (pre == 3) { a_g = a; have_g = true; }
+    }
+    void finish() {
+        if (!fused) return;
+        if (have_x && have_g && a_x == a_g) {
+            B.fused_eval(FLGPU_WRITE_X | FLGPU_WRITE_G, a_x, x0, p, xt, gt);
+        } else {                               // never taken by the reference's searchers; kept for fidelity
+            if (have_x) B.trial_x(xt, x0, p, a_x);
+            if (have_g) B.fused_eval(FLGPU_WRITE_G, a_g, x0, p, nullptr, gt);
+        }
+    }
     bool armijo_violated() { return fx() > fx0 + c1 * a * phid0; }
     static bool collapsed(double low, double up) {
         return std::fabs(up - low) < 1e-15 ||
@@ -114,7 +156,7 @@ struct Search {
     }
     void wolfe() {
         double aold, fold, atemp, ftemp, phidx;
-        if (pre == 0) { form(a); call_f(); } else { trials++; set_fx(pre_f); }       // f90:1306
+        if (pre == 0) { form(a); call_f(); } else { adopt_pre(); }                   // f90:1306
         if (!armijo_violated()) {
             for (;;) {
                 aold = a; fold = fx();
@@ -178,7 +220,7 @@ struct Search {
             form(a);
             if (fdwithf) call_ffd(); else call_f();
         } else {
-            trials++; set_fx(pre_f);
+            adopt_pre();
         }
         if (!armijo_violated()) {
             if (!fdwithf) call_fd();
@@ -257,8 +299,10 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     S.c1 = P.c1; S.c2abs = P.c2 * std::fabs(phid0); S.fx0 = fx0; S.phid0 = phid0; S.incr = P.incr;
     S.fdwithf = fdwithf; S.a = a; S.fx_ = fx0;
     S.pre = pre; S.pre_f = pre_f; S.pre_gp = pre_gp;
+    S.fused = P.fused && B.fused_available();
     st.n_linesearch++;
     if (strong) S.strongwolfe(); else S.wolfe();
+    S.finish();
     SearchResult r;
     r.fx = S.fx();
     r.a = S.a;
@@ -292,6 +336,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
     double *gc = B.vec_alloc(), *go = B.vec_alloc();   // f' at xc / the other buffer
     double *p = B.vec_alloc();
     const int mem = P.mem;
+    const bool fused = P.fused && B.fused_available();
     B.lbfgs_alloc(mem);
     B.upload(xc, x_user, x_space);
 
@@ -335,10 +380,17 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             } else {
                 B.lbfgs_update_dots(xc, xo, gc, go, new_slot, k_after);      // K1
                 B.lbfgs_solve(k_after, new_slot);                            // K2
-                B.lbfgs_direction(p, xo, gc, xc, k_after, new_slot);         // K3: new p, first trial (a=1)
-                st.n_trials++;
-                if (next_fdwithf) { B.eval_fg(xo, go); st.n_f_fd++; B.dot(go, p, SL_GP); }
-                else { B.eval_f(xo); st.n_f++; }
+                if (fused) {                                                 // K3: new p; first trial (a=1) probed
+                    B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);
+                    st.n_trials++;
+                    if (next_fdwithf) { B.fused_eval(FLGPU_WANT_F | FLGPU_WANT_GP, 1.0, xc, p, nullptr, nullptr); st.n_f_fd++; }
+                    else { B.fused_eval(FLGPU_WANT_F, 1.0, xc, p, nullptr, nullptr); st.n_f++; }
+                } else {
+                    B.lbfgs_direction(p, xo, gc, xc, k_after, new_slot);     // K3: new p, first trial point (a=1)
+                    st.n_trials++;
+                    if (next_fdwithf) { B.eval_fg(xo, go); st.n_f_fd++; B.dot(go, p, SL_GP); }
+                    else { B.eval_f(xo); st.n_f++; }
+                }
             }
             B.fetch(slots); st.host_syncs++;
             gg = slots[SL_GG];

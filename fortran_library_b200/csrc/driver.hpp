@@ -15,6 +15,7 @@ struct Params {
     double minstep = 1e-30;
     double c1 = 1e-4, c2 = 0.9, incr = 1.05;
     bool has_f_fd = false;
+    bool fused = true;   // use flgpu_problem.fused when the problem supplies it
     flgpu_observer_fn observer = nullptr;
     void *observer_user = nullptr;
 };

@@ -80,6 +80,40 @@ __device__ __forceinline__ void reduce_finish(double (&acc)[NACC], const int (&d
     if (threadIdx.x == 0) *w.ticket = 0u;
 }
 
+// Same reduction with one output pointer per accumulator (objective kernels: f and f'.p go to
+// caller-supplied device scalars).
+template <int NACC>
+__device__ __forceinline__ void reduce_finish_to(double (&acc)[NACC], double *(&out)[NACC], Work w) {
+    __shared__ double sh[NACC][kThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) sh[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
+        w.partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(w.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < NACC) {
+        double s = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&w.partials[(size_t)b * NACC + warp]);
+        s = warp_sum(s);
+        if (lane == 0) *out[warp] = s;
+    }
+    if (threadIdx.x == 0) *w.ticket = 0u;
+}
+
 // ------------------------------------------------------------------ K4a: x = x0 + a*p (f90:1482)
 static __global__ void __launch_bounds__(kThreads) trial_kernel(double *__restrict__ x, const double *__restrict__ x0,
                                                          const double *__restrict__ p, double a, int64_t n) {
@@ -474,7 +508,9 @@ static __global__ void __launch_bounds__(kThreads) k3_direction_kernel(K3Args a)
     const int64_t nu = a.n >> 1;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
-        const double2 g = ld2(a.g1, u), x = ld2(a.x1, u);
+        const double2 g = ld2(a.g1, u);
+        double2 x = make_double2(0.0, 0.0);
+        if (a.xt) x = ld2(a.x1, u);
         double2 q = g;
 #pragma unroll 4
         for (int t = 0; t < k; t++) {
@@ -493,7 +529,7 @@ static __global__ void __launch_bounds__(kThreads) k3_direction_kernel(K3Args a)
         }
         const double2 pv = make_double2(-r.x, -r.y);
         st2(a.p, u, pv);
-        st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
+        if (a.xt) st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
         acc[0] = fma(g.y, pv.y, fma(g.x, pv.x, acc[0]));
         acc[1] = fma(pv.y, pv.y, fma(pv.x, pv.x, acc[1]));
     }
@@ -506,7 +542,7 @@ static __global__ void __launch_bounds__(kThreads) k3_direction_kernel(K3Args a)
         for (int t = k - 1; t >= 0; t--) r = __dadd_rn(r, __dmul_rn(coef_s[t], a.S[(size_t)order[t] * a.ld + i]));
         const double pv = -r;
         a.p[i] = pv;
-        a.xt[i] = a.x1[i] + pv;
+        if (a.xt) a.xt[i] = a.x1[i] + pv;
         acc[0] = fma(g, pv, acc[0]);
         acc[1] = fma(pv, pv, acc[1]);
     }

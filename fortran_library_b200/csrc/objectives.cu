@@ -57,16 +57,25 @@ __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, 
 __device__ __forceinline__ double sub(double a, double b) { return __dadd_rn(a, -b); }
 
 struct ObjArgs {
-    const double *x;
+    const double *x;    // the point (unfused) or x0 (fused: the point is x0 + a*p)
+    const double *p;    // fused only
+    double a;           // fused only
+    double *x_out;      // fused + FLGPU_WRITE_X
     double *g;          // may be null (f only)
     double *f_out;      // device scalar, may be null (f' only)
+    double *gp_out;     // device scalar (FLGPU_WANT_GP)
     int64_t n, offset, n_global;
     double scale;       // diag quad: 2^24/(n_global-1)
     const double *tables;
     Work w;
 };
 
-template <int KIND, bool WANT_F, bool WANT_G>
+// One kernel serves the plain callbacks (f, fd, f_fd) and the fused line-search evaluation
+// (flgpu_fused_fn).  FUSED: the point is formed as x0 + a*p (multiply, then add: f90:1482) instead of
+// being loaded; WANT_GP: f'(x).p is reduced alongside f; WRITE_X / WRITE_G: store the point / gradient.
+// The thread-to-element mapping and the accumulation order of f do not depend on the flags, so f has
+// the same bits on the fused and the unfused path.
+template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
 __global__ void __launch_bounds__(kThreads) objective_kernel(ObjArgs a) {
     __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
     if (KIND == FLGPU_OBJ_DIAGQUAD) {
@@ -79,34 +88,50 @@ __global__ void __launch_bounds__(kThreads) objective_kernel(ObjArgs a) {
         if (q >> 24) return 1.0e6;
         return mul(mul(tab[512 + ((q >> 16) & 255)], tab[256 + ((q >> 8) & 255)]), tab[q & 255]);
     };
-    double fsum = 0.0;
+    constexpr bool NEED_G = WANT_GP || WRITE_G;
+    double fsum = 0.0, gpsum = 0.0;
+    const double step = a.a;
     const int64_t nu = a.n >> 1;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
-        const double2 x = ld2(a.x, u);
-        double2 g;
+        double2 x = ld2(a.x, u), pv = make_double2(0.0, 0.0);
+        if (FUSED) {
+            pv = ld2(a.p, u);
+            x.x = add(x.x, mul(step, pv.x));
+            x.y = add(x.y, mul(step, pv.y));
+            if (WRITE_X) st2(a.x_out, u, x);
+        }
+        double2 g = make_double2(0.0, 0.0);
         if (KIND == FLGPU_OBJ_QUARTIC) {
             const double x2 = mul(x.x, x.x), y2 = mul(x.y, x.y);
             if (WANT_F) { fsum += mul(x2, x2); fsum += mul(y2, y2); }
-            g.x = mul(4.0, mul(x2, x.x)); g.y = mul(4.0, mul(y2, x.y));
+            if (NEED_G) { g.x = mul(4.0, mul(x2, x.x)); g.y = mul(4.0, mul(y2, x.y)); }
         } else if (KIND == FLGPU_OBJ_ROSENBROCK) {
             const double t1 = sub(x.y, mul(x.x, x.x)), t2 = sub(1.0, x.x);
             if (WANT_F) fsum += add(mul(mul(100.0, t1), t1), mul(t2, t2));
-            g.x = sub(mul(mul(-400.0, x.x), t1), mul(2.0, t2));
-            g.y = mul(200.0, t1);
+            if (NEED_G) {
+                g.x = sub(mul(mul(-400.0, x.x), t1), mul(2.0, t2));
+                g.y = mul(200.0, t1);
+            }
         } else {
             const int64_t i = a.offset + 2 * u;
             const double d0 = coeff(i), d1 = coeff(i + 1);
             const double t0 = sub(x.x, 1.0), t1 = sub(x.y, 1.0);
             if (WANT_F) { fsum += mul(mul(mul(0.5, d0), t0), t0); fsum += mul(mul(mul(0.5, d1), t1), t1); }
-            g.x = mul(d0, t0); g.y = mul(d1, t1);
+            if (NEED_G) { g.x = mul(d0, t0); g.y = mul(d1, t1); }
         }
-        if (WANT_G) st2(a.g, u, g);
+        if (WRITE_G) st2(a.g, u, g);
+        if (WANT_GP) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
     }
     if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = a.n - 1;
-        const double x = a.x[i];
-        double g;
+        double x = a.x[i], pv = 0.0;
+        if (FUSED) {
+            pv = a.p[i];
+            x = add(x, mul(step, pv));
+            if (WRITE_X) a.x_out[i] = x;
+        }
+        double g = 0.0;
         if (KIND == FLGPU_OBJ_QUARTIC) {
             const double x2 = mul(x, x);
             if (WANT_F) fsum += mul(x2, x2);
@@ -120,12 +145,21 @@ __global__ void __launch_bounds__(kThreads) objective_kernel(ObjArgs a) {
             if (WANT_F) fsum += mul(mul(mul(0.5, d), t), t);
             g = mul(d, t);
         }
-        if (WANT_G) a.g[i] = g;
+        if (WRITE_G) a.g[i] = g;
+        if (WANT_GP) gpsum = fma(g, pv, gpsum);
     }
-    if (WANT_F) {
+    if (WANT_F && WANT_GP) {
+        double acc[2] = {fsum, gpsum};
+        double *out[2] = {a.f_out, a.gp_out};
+        reduce_finish_to<2>(acc, out, a.w);
+    } else if (WANT_F) {
         double acc[1] = {fsum};
-        const int d[1] = {0};
-        reduce_finish<1>(acc, d, a.w, a.f_out);
+        double *out[1] = {a.f_out};
+        reduce_finish_to<1>(acc, out, a.w);
+    } else if (WANT_GP) {
+        double acc[1] = {gpsum};
+        double *out[1] = {a.gp_out};
+        reduce_finish_to<1>(acc, out, a.w);
     }
 }
 
@@ -171,19 +205,37 @@ static int obj_grid(int64_t n) {
     return (int)(need < g ? (need < 1 ? 1 : need) : g);
 }
 
-void launch_objective(int kind, double *f_dev, double *g_dev, const double *x_dev, int64_t n, int64_t offset,
+// flags = FLGPU_WANT_* | FLGPU_WRITE_*; fused: x_dev is x0 and the point is x0 + a*p
+void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp_dev, double *x_out, double *g_dev,
+                      const double *x_dev, const double *p_dev, double step, int64_t n, int64_t offset,
                       int64_t n_global, cudaStream_t s) {
     Scratch &sc = scratch_for(s);
     k::ObjArgs a;
-    a.x = x_dev; a.g = g_dev; a.f_out = f_dev; a.n = n; a.offset = offset; a.n_global = n_global;
+    a.x = x_dev; a.p = p_dev; a.a = step; a.x_out = x_out; a.g = g_dev; a.f_out = f_dev; a.gp_out = gp_dev;
+    a.n = n; a.offset = offset; a.n_global = n_global;
     a.scale = n_global > 1 ? 16777216.0 / (double)(n_global - 1) : 0.0;
     a.tables = sc.tables; a.w = sc.work;
     const int grid = obj_grid(n);
-#define FLGPU_OBJ_LAUNCH(KIND)                                                                              \
-    do {                                                                                                    \
-        if (f_dev && g_dev) k::objective_kernel<KIND, true, true><<<grid, k::kThreads, 0, s>>>(a);          \
-        else if (f_dev) k::objective_kernel<KIND, true, false><<<grid, k::kThreads, 0, s>>>(a);             \
-        else k::objective_kernel<KIND, false, true><<<grid, k::kThreads, 0, s>>>(a);                        \
+#define FLGPU_OBJ_CASE(KIND, FU, F, GP, WX, WG)                                                                 \
+    k::objective_kernel<KIND, FU, F, GP, WX, WG><<<grid, k::kThreads, 0, s>>>(a)
+#define FLGPU_OBJ_LAUNCH(KIND)                                                                                  \
+    do {                                                                                                        \
+        if (!fused) {                                                                                           \
+            if (flags == (FLGPU_WANT_F | FLGPU_WRITE_G)) FLGPU_OBJ_CASE(KIND, false, true, false, false, true); \
+            else if (flags == FLGPU_WANT_F) FLGPU_OBJ_CASE(KIND, false, true, false, false, false);             \
+            else if (flags == FLGPU_WRITE_G) FLGPU_OBJ_CASE(KIND, false, false, false, false, true);            \
+            else fatal("built-in objective: unsupported evaluation request");                                   \
+        } else {                                                                                                \
+            if (flags == (FLGPU_WANT_F | FLGPU_WANT_GP)) FLGPU_OBJ_CASE(KIND, true, true, true, false, false);  \
+            else if (flags == FLGPU_WANT_F) FLGPU_OBJ_CASE(KIND, true, true, false, false, false);              \
+            else if (flags == FLGPU_WANT_GP) FLGPU_OBJ_CASE(KIND, true, false, true, false, false);             \
+            else if (flags == (FLGPU_WRITE_X | FLGPU_WRITE_G)) FLGPU_OBJ_CASE(KIND, true, false, false, true, true); \
+            else if (flags == FLGPU_WRITE_G) FLGPU_OBJ_CASE(KIND, true, false, false, false, true);             \
+            else if (flags == FLGPU_WRITE_X) FLGPU_OBJ_CASE(KIND, true, false, false, true, false);             \
+            else if (flags == (FLGPU_WANT_F | FLGPU_WANT_GP | FLGPU_WRITE_X | FLGPU_WRITE_G))                   \
+                FLGPU_OBJ_CASE(KIND, true, true, true, true, true);                                             \
+            else fatal("built-in objective: unsupported fused evaluation request");                             \
+        }                                                                                                       \
     } while (0)
     switch (kind) {
     case FLGPU_OBJ_QUARTIC: FLGPU_OBJ_LAUNCH(FLGPU_OBJ_QUARTIC); break;
@@ -192,27 +244,38 @@ void launch_objective(int kind, double *f_dev, double *g_dev, const double *x_de
     default: fatal("unknown built-in objective");
     }
 #undef FLGPU_OBJ_LAUNCH
+#undef FLGPU_OBJ_CASE
 }
 
 // 64-bit device-callback flavour
 template <int KIND>
 static void dev_f(const flgpu_eval_ctx *c, double *f, const double *x, int64_t n) {
-    launch_objective(KIND, f, nullptr, x, n, c->offset, c->n_global, (cudaStream_t)c->stream);
+    launch_objective(KIND, false, FLGPU_WANT_F, f, nullptr, nullptr, nullptr, x, nullptr, 0.0, n, c->offset,
+                     c->n_global, (cudaStream_t)c->stream);
 }
 template <int KIND>
 static void dev_fd(const flgpu_eval_ctx *c, double *g, const double *x, int64_t n) {
-    launch_objective(KIND, nullptr, g, x, n, c->offset, c->n_global, (cudaStream_t)c->stream);
+    launch_objective(KIND, false, FLGPU_WRITE_G, nullptr, nullptr, nullptr, g, x, nullptr, 0.0, n, c->offset,
+                     c->n_global, (cudaStream_t)c->stream);
 }
 template <int KIND>
 static void dev_ffd(const flgpu_eval_ctx *c, double *f, double *g, const double *x, int64_t n) {
-    launch_objective(KIND, f, g, x, n, c->offset, c->n_global, (cudaStream_t)c->stream);
+    launch_objective(KIND, false, FLGPU_WANT_F | FLGPU_WRITE_G, f, nullptr, nullptr, g, x, nullptr, 0.0, n,
+                     c->offset, c->n_global, (cudaStream_t)c->stream);
+}
+template <int KIND>
+static void dev_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp, double *x_out, double *g_out,
+                      const double *x0, const double *p, double a, int64_t n) {
+    launch_objective(KIND, true, flags, f, gp, x_out, g_out, x0, p, a, n, c->offset, c->n_global,
+                     (cudaStream_t)c->stream);
 }
 
 // reference-ABI flavour: device x / f' pointers, host f, runs on the current call's stream
 static double ref_eval(int kind, bool want_f, double *g, const double *x, int dim) {
     cudaStream_t s = (cudaStream_t)flgpu_current_stream();
     Scratch &sc = scratch_for(s);
-    launch_objective(kind, want_f ? sc.scalar : nullptr, g, x, dim, 0, dim, s);
+    launch_objective(kind, false, (want_f ? FLGPU_WANT_F : 0) | (g ? FLGPU_WRITE_G : 0), want_f ? sc.scalar : nullptr,
+                     nullptr, nullptr, g, x, nullptr, 0.0, dim, 0, dim, s);
     if (!want_f) return 0.0;
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(sc.host_scalar, sc.scalar, sizeof(double), cudaMemcpyDeviceToHost, s));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -235,12 +298,22 @@ using namespace flgpu;
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {
-    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; return 0;
-    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; return 0;
-    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; return 0;
+    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; return 0;
+    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; return 0;
+    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; return 0;
     }
     return 1;
 }
+
+// fused evaluation registered for the built-in reference-ABI callbacks (flgpu_register_fused)
+namespace flgpu {
+flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f) {
+    if (f == ref_f<0>) return dev_fused<0>;
+    if (f == ref_f<1>) return dev_fused<1>;
+    if (f == ref_f<2>) return dev_fused<2>;
+    return nullptr;
+}
+}  // namespace flgpu
 
 extern "C" int flgpu_builtin_ref_callbacks(int kind, flgpu_ref_f_fn *f, flgpu_ref_fd_fn *fd, flgpu_ref_f_fd_fn *f_fd) {
     switch (kind) {

@@ -57,11 +57,30 @@ typedef void (*flgpu_fd_fn)(const flgpu_eval_ctx *ctx, double *g_dev, const doub
 typedef void (*flgpu_f_fd_fn)(const flgpu_eval_ctx *ctx, double *f_dev, double *g_dev, const double *x_dev,
                               int64_t n_local);
 
+/* Optional FUSED line-search evaluation (an extension; the reference has no counterpart).
+ * Every line-search trial of the reference is `x=x0+a*p; call f / fd / f_fd; dot_product(fdx,p)`
+ * (f90:1482-1485, 1490, 1501, 1567): 7n doubles of traffic through opaque callbacks.  An objective
+ * whose kernel can form the trial point itself (element-local or block-local objectives) may supply
+ * this callback instead; the library then never materialises rejected trial points:
+ *     x  = x0 + a*p          element-wise, multiply THEN add (two roundings, as the reference)
+ *     FLGPU_WANT_F   : *f_dev  = this rank's partial sum of f(x)
+ *     FLGPU_WANT_GP  : *gp_dev = this rank's partial sum of f'(x).p
+ *     FLGPU_WRITE_X  : x_out[i] = x[i]          (accepted point only)
+ *     FLGPU_WRITE_G  : g_out[i] = f'(x)[i]      (accepted point only)
+ * Enqueue on ctx->stream, do not synchronise.  Which of f / f' are requested follows the
+ * reference's own call sequence (f-only probes in branch D f90:1518-1520, f_fd elsewhere), so
+ * evaluation counts and every host decision are the same as on the unfused path. */
+enum { FLGPU_WANT_F = 1, FLGPU_WANT_GP = 2, FLGPU_WRITE_X = 4, FLGPU_WRITE_G = 8 };
+typedef void (*flgpu_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *f_dev, double *gp_dev,
+                               double *x_out, double *g_out, const double *x0_dev, const double *p_dev,
+                               double a, int64_t n_local);
+
 typedef struct flgpu_problem {
     flgpu_f_fn f;       /* required */
     flgpu_fd_fn fd;     /* required */
     flgpu_f_fd_fn f_fd; /* optional (NULL = absent, f90:42-43) */
     void *user;
+    flgpu_fused_fn fused; /* optional (NULL = trial points are materialised and f / fd / f_fd are called) */
 } flgpu_problem;
 
 /* ------------------------------------------------------------------ options / results */
@@ -118,6 +137,7 @@ typedef struct flgpu_options {
     flgpu_observer_fn observer;
     void *observer_user;
     int time_kernels;       /* 1 = bracket every library kernel with CUDA events (flgpu_kernel_times) */
+    int no_fused;           /* 1 = ignore flgpu_problem.fused (always materialise trial points) */
 } flgpu_options;
 
 typedef struct flgpu_stats {
@@ -163,6 +183,10 @@ int flgpu_current_device(void);
 void flgpu_last_stats(flgpu_stats *out);
 /* Observer applied to Fortran-ABI calls on this thread (NULL to clear). */
 void flgpu_set_observer(flgpu_observer_fn fn, void *user);
+/* Associates a fused line-search evaluation (see flgpu_fused_fn) with a reference-ABI objective:
+ * a later Fortran-ABI call whose `f` argument equals `f` uses it.  fused = NULL removes the entry.
+ * `user` is handed to the fused callback as ctx->user.  The built-in objectives are pre-registered. */
+void flgpu_register_fused(flgpu_ref_f_fn f, flgpu_fused_fn fused, void *user);
 
 /* gfortran names (hpp:278-393 "#elif __GNUC__") */
 void __nonlinearoptimization_MOD_lbfgs(

@@ -59,6 +59,7 @@ def _run(fn_name, for_cg, kind, x, observer=None, use_ffd=True, offset=0, n_glob
         prob.f_fd = None
     o = capi.Options()
     L.flgpu_hostsim_options_default(C.byref(o), int(for_cg))
+    o.no_fused = int(not kw.pop("fused", True))
     capi.apply_options(o, **kw)
     o.offset, o.n_global = offset, n_global
     if observer is not None:

@@ -79,6 +79,10 @@ public:
     void eval_g(const double *x, double *g) override { prob.fd(&ctx, g, x, n); }
     void eval_fg(const double *x, double *g) override { prob.f_fd(&ctx, &slots[flgpu::SL_F], g, x, n); }
 
+    bool fused_available() const override { return prob.fused != nullptr; }
+    void fused_eval(int flags, double a, const double *x0, const double *p, double *x_out, double *g_out) override {
+        prob.fused(&ctx, flags, &slots[flgpu::SL_F], &slots[flgpu::SL_GP], x_out, g_out, x0, p, a, n);
+    }
     void trial_x(double *x, const double *x0, const double *p, double a) override {
         launches++;
         for (long i = 0; i < n; i++) x[i] = x0[i] + a * p[i];
@@ -117,7 +121,7 @@ public:
                                 w2.data(), w3.data());
     }
     void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
-                         int recent) override {
+                         int recent) override {  // xt may be null (fused line search)
         launches++;
         const int m = mem;
         const double gamma = C[0];
@@ -133,7 +137,7 @@ public:
                 r = r + C[1 + m + j] * S[(long)j * n + i];
             }
             p[i] = -r;
-            xt[i] = x1[i] + p[i];
+            if (xt) xt[i] = x1[i] + p[i];
         }
         slots[flgpu::SL_GP0] = blocked_sum(n, [&](long i) { return g1[i] * p[i]; });
         slots[flgpu::SL_PP] = blocked_sum(n, [&](long i) { return p[i] * p[i]; });
@@ -193,6 +197,22 @@ void obj_ffd(const flgpu_eval_ctx *c, double *f, double *g, const double *x, int
     orc_obj_f_fd(f, g, x, &d);
 }
 
+// fused evaluation (flgpu_fused_fn) on host memory: the point is formed element-wise, multiply then add
+void obj_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp, double *x_out, double *g_out,
+               const double *x0, const double *p, double a, int64_t n) {
+    std::vector<double> x((size_t)(n > 0 ? n : 1)), g((size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; i++) x[i] = x0[i] + a * p[i];
+    int d = (int)n;
+    double fv = 0.0;
+    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
+    orc_obj_set_sum_mode(g_obj_sum_mode);
+    orc_obj_f_fd(&fv, g.data(), x.data(), &d);
+    if (flags & FLGPU_WANT_F) *f = fv;
+    if (flags & FLGPU_WANT_GP) *gp = blocked_sum(n, [&](long i) { return g[i] * p[i]; });
+    if (flags & FLGPU_WRITE_X) std::memcpy(x_out, x.data(), sizeof(double) * n);
+    if (flags & FLGPU_WRITE_G) std::memcpy(g_out, g.data(), sizeof(double) * n);
+}
+
 }  // namespace
 
 extern "C" {
@@ -205,6 +225,7 @@ void flgpu_hostsim_set_obj_sum_mode(int mode) { g_obj_sum_mode = mode; }
 
 void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->f = obj_f; out->fd = obj_fd; out->f_fd = obj_ffd; out->user = (void *)(intptr_t)kind;
+    out->fused = obj_fused;
 }
 
 void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {

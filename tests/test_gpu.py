@@ -76,6 +76,42 @@ def test_objective_kernels_vs_oracle(fl, name, n):
             assert abs(fd_.numpy()[0] - fo.value) <= 1e-13 * abs(fo.value) + 1e-300
 
 
+@pytest.mark.parametrize("name", ["quartic", "rosenR1", "diag"])
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537])
+def test_fused_evaluation_vs_plain_callbacks(fl, name, n):
+    """flgpu_fused_fn of the built-in objectives: the point it forms equals flgpu_vec_trial bit for bit,
+    f and f' equal the plain callbacks' bit for bit (same mapping, same order), f'.p to dot accuracy."""
+    kind = _cases.OBJECTIVES[name][0]
+    rng = np.random.default_rng(n + 17)
+    x0 = _cases.start(name, n) + 0.01 * rng.standard_normal(n)
+    p = rng.standard_normal(n)
+    a = 0.3712345
+    prob = fl.builtin_problem(kind)
+    fused = C.cast(prob.fused, fl.capi.FUSED_FN)
+    x0d, pd = fl.DeviceVector.from_numpy(x0), fl.DeviceVector.from_numpy(p)
+    xd, gd, xo, go, sc = (fl.DeviceVector(n), fl.DeviceVector(n), fl.DeviceVector(n), fl.DeviceVector(n),
+                          fl.DeviceVector(4))
+    ctx = fl.capi.EvalCtx(None, None, 0, n, 0, 1, 0)
+    fl.lib().flgpu_vec_trial(xd.ptr, x0d.ptr, pd.ptr, a, n, None)
+    C.cast(prob.f_fd, fl.capi.F_FD_FN)(C.byref(ctx), sc.ptr, gd.ptr, xd.ptr, n)
+    f_plain, x_plain, g_plain = sc.numpy()[0], xd.numpy(), gd.numpy()
+    W = fl.capi
+    for flags in (W.WANT_F | W.WANT_GP, W.WANT_F, W.WANT_GP, W.WRITE_X | W.WRITE_G, W.WRITE_G, W.WRITE_X,
+                  W.WANT_F | W.WANT_GP | W.WRITE_X | W.WRITE_G):
+        fl.lib().flgpu_memcpy(sc.ptr, np.full(4, np.nan).ctypes.data, 32, 1, 0, None)
+        fused(C.byref(ctx), flags, sc.ptr, sc.ptr + 8, xo.ptr, go.ptr, x0d.ptr, pd.ptr, a, n)
+        out = sc.numpy()
+        if flags & W.WANT_F:
+            assert out[0] == f_plain
+        if flags & W.WANT_GP:
+            exact = math.fsum(g_plain * p)
+            assert abs(out[1] - exact) <= 4e-16 * float(np.sum(np.abs(g_plain * p))) + 1e-300
+        if flags & W.WRITE_X:
+            assert np.array_equal(xo.numpy(), x_plain)
+        if flags & W.WRITE_G:
+            assert np.array_equal(go.numpy(), g_plain)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100003, 1 << 20])
 def test_vector_primitives(fl, n):
     rng = np.random.default_rng(n)
@@ -134,11 +170,13 @@ def test_two_loop_operator_all_kernel_shapes(fl, mem):
     ("rosenR1", dict(Memory=1, MaxIteration=30)), ("rosenR1", dict(Memory=10, Strong=False, MaxIteration=30)),
     ("rosenR1", dict(Memory=10, use_ffd=False)),
 ])
-def test_lbfgs_trajectory_within_oracle_envelope(fl, name, kw):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
+def test_lbfgs_trajectory_within_oracle_envelope(fl, name, kw, fused):
     n = 10_000                                             # BASELINE.json configs[0]
-    kw = dict(kw)
+    kw = dict(kw, fused=fused)
     use = kw.pop("use_ffd", True)
-    traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.lbfgs(cbs, x, use_ffd=use, **k), **kw)
+    okw = {k: v for k, v in kw.items() if k != "fused"}
+    traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.lbfgs(cbs, x, use_ffd=use, **k), **okw)
     ob = fl.Observer(keep_vectors=True, max_vec_iters=20)
     x = _dev_start(fl, name, n)
     st = fl.LBFGS(_problem(fl, name, use), x, observer=ob, Warning=False, **kw)
@@ -151,11 +189,13 @@ def test_lbfgs_trajectory_within_oracle_envelope(fl, name, kw):
 @pytest.mark.parametrize("name,kw", [("quartic", dict()), ("rosenR1", dict(MaxIteration=60)),
                                      ("diag", dict(MaxIteration=60)), ("quartic", dict(Strong=False, MaxIteration=60)),
                                      ("quartic", dict(use_ffd=False))])
-def test_cg_trajectory_within_oracle_envelope(fl, method, name, kw):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
+def test_cg_trajectory_within_oracle_envelope(fl, method, name, kw, fused):
     n = 10_000
     kw = dict(kw)
     use = kw.pop("use_ffd", True)
     traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.cg(cbs, x, Method=method, use_ffd=use, **k), **kw)
+    kw["fused"] = fused
     ob = fl.Observer(keep_vectors=True, max_vec_iters=20)
     x = _dev_start(fl, name, n)
     fl.ConjugateGradient(_problem(fl, name, use), x, Method=method, observer=ob, Warning=False, **kw)
@@ -169,13 +209,14 @@ def test_minimisers_and_iteration_counts(fl):
         x0 = _cases.start(name, n)
         runs = [O.lbfgs(O.builtin_callbacks(kind, 0, n), x0.copy(), use_ffd=True, Warning=False, sum_mode=m)
                 for m in (0, 1, 2)]
-        x = _dev_start(fl, name, n)
-        st = fl.LBFGS(_problem(fl, name), x, Warning=False)
-        assert _cases.rel(x.numpy(), runs[0][0]) < 1e-8          # minimiser, relative 1e-8
         its = [r[1].n_iter for r in runs]
         spread = (max(its) - min(its)) / min(its)
-        assert abs(st.iterations - its[0]) / its[0] <= max(0.02, 1.5 * spread)
-        assert st.status == runs[0][1].status
+        for fused in (True, False):
+            x = _dev_start(fl, name, n)
+            st = fl.LBFGS(_problem(fl, name), x, Warning=False, fused=fused)
+            assert _cases.rel(x.numpy(), runs[0][0]) < 1e-8          # minimiser, relative 1e-8
+            assert abs(st.iterations - its[0]) / its[0] <= max(0.02, 1.5 * spread)
+            assert st.status == runs[0][1].status
     # CG on the quartic (config 3): x* = 0, scale by |x0| (SURVEY.md 7 "x*=0 objectives")
     x0 = _cases.start("quartic", n)
     for M in ("DY", "PR"):

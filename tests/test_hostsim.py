@@ -84,6 +84,34 @@ def test_minimisers_and_iteration_counts():
         assert st.status == runs[0][1].status
 
 
+@pytest.mark.parametrize("lbfgs,name,kw", [
+    (True, "rosenR1", dict(Memory=10)), (True, "rosenR1", dict(Memory=3, use_ffd=False)),
+    (True, "quartic", dict(Memory=5, Strong=False)), (True, "diag", dict(Memory=7, MaxIteration=60)),
+    (False, "quartic", dict(Method="DY")), (False, "quartic", dict(Method="PR", use_ffd=False)),
+    (False, "rosenR1", dict(Method="DY", Strong=False, MaxIteration=80)),
+])
+def test_fused_line_search_is_the_same_algorithm(lbfgs, name, kw):
+    """flgpu_fused_fn changes where trial points live, not what is computed: with the host simulator
+    (identical reductions on both paths) the fused and the unfused run must agree bit for bit in every
+    direction, step, iterate and evaluation count."""
+    n = 3001
+    kind = _cases.OBJECTIVES[name][0]
+    run = H.lbfgs if lbfgs else H.cg
+    out = []
+    for fused in (True, False):
+        ob = H.Observer(max_vec_iters=10**9)
+        x, st = run(kind, _cases.start(name, n), observer=ob, Warning=False, n_global=n, fused=fused, **kw)
+        out.append((x, st, ob))
+    (xa, sa, oa), (xb, sb, ob_) = out
+    assert np.array_equal(xa, xb)
+    assert oa.rows == ob_.rows
+    assert all(np.array_equal(u, v) for u, v in zip(oa.p, ob_.p))
+    assert all(np.array_equal(u, v) for u, v in zip(oa.x, ob_.x))
+    assert all(np.array_equal(u, v) for u, v in zip(oa.g, ob_.g))
+    for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
+        assert getattr(sa, k) == getattr(sb, k), k
+
+
 def _py_problem(fuse):
     """flgpu_problem over Python scalar functions (host pointers: this is the host simulator)."""
     def f(ctx, fp, xp, n):
