@@ -212,7 +212,7 @@ def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None,
     return _run(lib().flgpu_lbfgs, False, problem, ptr, n, space, observer, stream, comm, offset, n_global,
                 time_kernels, dict(Memory=Memory, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                                    Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                                   WolfeConst2=WolfeConst2, Increment=Increment))
+                                   WolfeConst2=WolfeConst2, Increment=Increment, fused=fused))
 
 
 def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,

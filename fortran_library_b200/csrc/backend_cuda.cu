@@ -360,7 +360,7 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
     k::K3Args a;
     a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n;
     a.m = mem; a.k = kk; a.recent = recent; a.w = work; a.R = R;
-    k::k3_direction_kernel<<<grid_for(n / 2 + 1, k::kThreads, 4), k::kThreads, 0, stream>>>(a);
+    k::k3_direction_kernel<8><<<grid_for(n / 2 + 1, k::kThreads, 2), k::kThreads, 0, stream>>>(a);
     time_end(t);
     launches++;
 }

@@ -44,6 +44,14 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// butterfly over aligned segments of SEG lanes (SEG = 32: the whole warp)
+template <int SEG>
+__device__ __forceinline__ double seg_sum(double v) {
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 // Block-level reduction of NACC per-thread accumulators followed by the grid-level finish.
 // dest[i] = index into R receiving accumulator i.  All kThreads threads must call this.
 template <int NACC>
@@ -251,11 +259,18 @@ struct K1Args {
     double *R;          // dots land at R[kResSlots + d_*]
 };
 
+// Thread layout: every warp is cut into NG segments of SEG = 32/NG lanes; segment ty is column group
+// ty, and the lanes of all segments of a warp address the SAME SEG consecutive double2 elements.  The loads
+// of x1, x0, g1, g0 that every group needs are therefore issued with identical addresses inside one warp
+// instruction and coalesce into a single request (no re-read of those four vectors per group), while
+// each group's column loads stay contiguous runs of SEG*16 bytes.
 template <int MT, int NG>
 static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args a) {
-    constexpr int TX = kThreads / NG;
-    constexpr int NW = TX / 32;                      // warps per column group
-    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    constexpr int SEG = 32 / NG;                     // lanes per column group inside a warp
+    constexpr int TX = kThreads / NG;                // double2 elements per block and loop trip
+    constexpr int NW = kThreads / 32;                // every warp contributes to every group
+    const int ty = (threadIdx.x & 31) / SEG;
+    const int tx = (threadIdx.x >> 5) * SEG + (threadIdx.x & 31) % SEG;
     const int m = a.m;
     const double *cs[MT], *cy[MT];
     bool valid[MT];
@@ -302,7 +317,7 @@ static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args 
                 acc[c][3] = fma(y[c].y, yn.y, fma(y[c].x, yn.x, acc[c][3]));
             }
     }
-    if ((a.n & 1) && blockIdx.x == 0 && tx == 0) {   // odd tail element
+    if ((a.n & 1) && blockIdx.x == 0 && tx == 0) {   // odd tail element (one thread per column group)
         const int64_t i = a.n - 1;
         const double x1 = a.x1[i], x0 = a.x0[i], g1 = a.g1[i], g0 = a.g0[i];
         const double sn = x1 - x0, yn = g1 - g0;
@@ -324,18 +339,19 @@ static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args 
     const int nd = nd_of(m);
     __shared__ double sh[NG][4 * MT + 5][NW];
     __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, wg = tx >> 5;
+    const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
+    const bool seg_head = (lane % SEG) == 0;
 #pragma unroll
     for (int c = 0; c < MT; c++)
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            const double v = warp_sum(acc[c][q]);
-            if (lane == 0) sh[ty][4 * c + q][wg] = v;
+            const double v = seg_sum<SEG>(acc[c][q]);
+            if (seg_head) sh[ty][4 * c + q][wg] = v;
         }
 #pragma unroll
     for (int q = 0; q < 5; q++) {
-        const double v = warp_sum(ex[q]);
-        if (lane == 0) sh[ty][4 * MT + q][wg] = v;
+        const double v = seg_sum<SEG>(ex[q]);
+        if (seg_head) sh[ty][4 * MT + q][wg] = v;
     }
     __syncthreads();
     double *part = a.w.partials + (size_t)blockIdx.x * nd;
@@ -490,44 +506,64 @@ struct K3Args {
     double *R;
 };
 
-static __global__ void __launch_bounds__(kThreads) k3_direction_kernel(K3Args a) {
-    __shared__ double coef_y[kMaxMem], coef_s[kMaxMem];
-    __shared__ int order[kMaxMem];
+// The 2k column operations are one list in the reference's order -- y_newest..y_oldest (q -= alpha y),
+// the gamma scaling, s_oldest..s_newest (r += e s) -- walked in chunks of CH columns with two register
+// buffers: the loads of chunk c+1 are in flight while chunk c is applied, for any k with a fixed
+// register budget.  -(alpha*y) == (-alpha)*y exactly, so both phases are v = v + coef*col.
+template <int CH>
+static __global__ void __launch_bounds__(kThreads, 2) k3_direction_kernel(K3Args a) {
+    __shared__ double coef[2 * kMaxMem];
+    __shared__ const double *col[2 * kMaxMem];
     __shared__ double s_gamma;
     const int m = a.m, k = a.k;
     for (int t = threadIdx.x; t < k; t += kThreads) {
         const int j = slot_of_age(a.recent, t, m);
-        order[t] = j;
-        coef_y[t] = a.C[1 + j];
-        coef_s[t] = a.C[1 + m + j];
+        coef[t] = -a.C[1 + j];                       // op t        : y of age t
+        col[t] = a.Y + (size_t)j * a.ld;
+        coef[2 * k - 1 - t] = a.C[1 + m + j];        // op 2k-1-t   : s of age t
+        col[2 * k - 1 - t] = a.S + (size_t)j * a.ld;
     }
     if (threadIdx.x == 0) s_gamma = a.C[0];
     __syncthreads();
     const double gamma = s_gamma;
+    const int nops = 2 * k;
+    const int nchunks = (nops + CH - 1) / CH;
     double acc[2] = {0.0, 0.0};
     const int64_t nu = a.n >> 1;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
-        const double2 g = ld2(a.g1, u);
+        double2 bufA[CH], bufB[CH];
+        auto load = [&](double2 (&b)[CH], int c) {
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                const int o = c * CH + i;
+                if (o < nops) b[i] = ld2(col[o], u);
+            }
+        };
+        double2 v = ld2(a.g1, u);
+        const double2 g = v;
+        load(bufA, 0);
         double2 x = make_double2(0.0, 0.0);
         if (a.xt) x = ld2(a.x1, u);
-        double2 q = g;
-#pragma unroll 4
-        for (int t = 0; t < k; t++) {
-            const double2 y = ld2(a.Y + (size_t)order[t] * a.ld, u);
-            const double al = coef_y[t];
-            q.x = __dadd_rn(q.x, -__dmul_rn(al, y.x));
-            q.y = __dadd_rn(q.y, -__dmul_rn(al, y.y));
+        auto apply = [&](const double2 (&b)[CH], int c) {
+#pragma unroll
+            for (int i = 0; i < CH; i++) {
+                const int o = c * CH + i;
+                if (o < nops) {
+                    if (o == k) { v.x = __dmul_rn(gamma, v.x); v.y = __dmul_rn(gamma, v.y); }
+                    const double cf = coef[o];
+                    v.x = __dadd_rn(v.x, __dmul_rn(cf, b[i].x));
+                    v.y = __dadd_rn(v.y, __dmul_rn(cf, b[i].y));
+                }
+            }
+        };
+        for (int c = 0; c < nchunks; c += 2) {
+            if (c + 1 < nchunks) load(bufB, c + 1);
+            apply(bufA, c);
+            if (c + 2 < nchunks) load(bufA, c + 2);
+            if (c + 1 < nchunks) apply(bufB, c + 1);
         }
-        double2 r = make_double2(__dmul_rn(gamma, q.x), __dmul_rn(gamma, q.y));
-#pragma unroll 4
-        for (int t = k - 1; t >= 0; t--) {
-            const double2 s = ld2(a.S + (size_t)order[t] * a.ld, u);
-            const double e = coef_s[t];
-            r.x = __dadd_rn(r.x, __dmul_rn(e, s.x));
-            r.y = __dadd_rn(r.y, __dmul_rn(e, s.y));
-        }
-        const double2 pv = make_double2(-r.x, -r.y);
+        const double2 pv = make_double2(-v.x, -v.y);
         st2(a.p, u, pv);
         if (a.xt) st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
         acc[0] = fma(g.y, pv.y, fma(g.x, pv.x, acc[0]));
@@ -536,11 +572,12 @@ static __global__ void __launch_bounds__(kThreads) k3_direction_kernel(K3Args a)
     if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         const int64_t i = a.n - 1;
         const double g = a.g1[i];
-        double q = g;
-        for (int t = 0; t < k; t++) q = __dadd_rn(q, -__dmul_rn(coef_y[t], a.Y[(size_t)order[t] * a.ld + i]));
-        double r = __dmul_rn(gamma, q);
-        for (int t = k - 1; t >= 0; t--) r = __dadd_rn(r, __dmul_rn(coef_s[t], a.S[(size_t)order[t] * a.ld + i]));
-        const double pv = -r;
+        double v = g;
+        for (int o = 0; o < nops; o++) {
+            if (o == k) v = __dmul_rn(gamma, v);
+            v = __dadd_rn(v, __dmul_rn(coef[o], col[o][i]));
+        }
+        const double pv = -v;
         a.p[i] = pv;
         if (a.xt) a.xt[i] = a.x1[i] + pv;
         acc[0] = fma(g, pv, acc[0]);

@@ -62,19 +62,19 @@ def parity(n=10_000):
                 compare(f"cg {M} {nm} {kw} ffd={int(use)}", tr, ob, xa, x.numpy(), x0)
 
 
-def timing(n, mem=10, iters=30, kind=fl.OBJ_ROSENBROCK, start=fl.START_ROSEN_PERT, cg=None):
+def timing(n, mem=10, iters=30, kind=fl.OBJ_ROSENBROCK, start=fl.START_ROSEN_PERT, cg=None, fused=True):
     x = fl.DeviceVector.start(start, n, seed=7)
     ob = fl.Observer()
     t = time.time()
     if cg:
         st = fl.ConjugateGradient(fl.builtin_problem(kind), x, Method=cg, observer=ob, Warning=False,
-                                  MaxIteration=iters, time_kernels=True)
+                                  MaxIteration=iters, time_kernels=True, fused=fused)
     else:
         st = fl.LBFGS(fl.builtin_problem(kind), x, Memory=mem, observer=ob, Warning=False, MaxIteration=iters,
-                      time_kernels=True)
+                      time_kernels=True, fused=fused)
     dt = time.time() - t
     kt = fl.kernel_times()
-    print(f"--- n={n} mem={mem} cg={cg}: iterations={st.iterations} trials={st.n_trials} wall={dt:.3f}s "
+    print(f"--- n={n} mem={mem} cg={cg} fused={fused}: iterations={st.iterations} trials={st.n_trials} wall={dt:.3f}s "
           f"it/s={st.iterations / dt:.2f} launches={st.gpu_launches} syncs={st.host_syncs}", flush=True)
     tot = sum(v["ms"] for v in kt.values())
     for name, v in sorted(kt.items(), key=lambda kv: -kv[1]["ms"]):
@@ -86,9 +86,13 @@ def timing(n, mem=10, iters=30, kind=fl.OBJ_ROSENBROCK, start=fl.START_ROSEN_PER
 
 if __name__ == "__main__":
     print(fl.lib().flgpu_version().decode(), "devices", fl.device_count(), flush=True)
-    parity()
-    for n in (1 << 20, 1 << 24, 1 << 26):
+    if "parity" in sys.argv:
+        parity()
+    for n in (1 << 20, 1 << 24):
         timing(n)
     timing(1 << 26, mem=30, kind=fl.OBJ_DIAGQUAD, start=fl.START_ZERO)
+    timing(1 << 26, mem=5)
     timing(1 << 26, kind=fl.OBJ_QUARTIC, start=fl.START_QUARTIC_U, cg="DY")
+    timing(1 << 26, kind=fl.OBJ_QUARTIC, start=fl.START_QUARTIC_U, cg="PR", fused=False)
+    timing(1 << 28, fused=False)
     timing(1 << 28)

@@ -1,0 +1,104 @@
+"""Row-sharded run on N GPUs (one process per GPU, NCCL), checked against the single-GPU run.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 \
+        tests/gpu_multi.py [log2n]
+
+Checks (exit status 0 iff all hold):
+  * every rank sees bitwise identical scalars (step, f, phi'(0), trials) at every iteration -- the
+    rank-ordered combination makes all ranks take identical branch decisions;
+  * the gathered shards of the first directions and of the minimiser agree with the 1-GPU run of the same
+    global problem within the summation-order noise (the split changes the order of the partial sums);
+  * iteration counts within 2 %.
+Not a pytest file; tests/test_gpu.py::test_row_sharded_nccl launches it when >= 2 GPUs are visible."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np          # noqa: E402
+import torch                # noqa: E402
+import torch.distributed as dist   # noqa: E402
+
+import fortran_library_b200 as fl  # noqa: E402
+
+
+def main():
+    log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def bcast(data):
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+    comm = fl.comm_create(rank, world, bcast)
+    n = 1 << log2n
+    lo = (n * rank // world) // 2 * 2
+    hi = n if rank == world - 1 else (n * (rank + 1) // world) // 2 * 2
+    ok = True
+    cases = [("lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10, MaxIteration=60)),
+             ("lbfgs", fl.OBJ_DIAGQUAD, fl.START_ZERO, 0, dict(Memory=30, MaxIteration=40)),
+             ("lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=5, MaxIteration=40, fused=False)),
+             ("cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY")),
+             ("cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="PR"))]
+    for algo, kind, start, seed, kw in cases:
+        run = fl.LBFGS if algo == "lbfgs" else fl.ConjugateGradient
+        prob = fl.builtin_problem(kind)
+        x = fl.DeviceVector.start(start, hi - lo, seed=seed, offset=lo, n_global=n)
+        ob = fl.Observer(keep_vectors=True, max_vec_iters=10)
+        st = run(prob, x, observer=ob, Warning=False, comm=comm, offset=lo, n_global=n, **kw)
+        # identical scalars on every rank
+        mine = torch.tensor([v for r in ob.rows for v in (r[1], r[2], r[3], float(r[4]))] + [float(st.iterations)],
+                            dtype=torch.float64, device="cuda")
+        count = torch.tensor([mine.numel()], device="cuda")
+        cmax = count.clone()
+        dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        same = int(cmax.item()) == int(count.item())
+        if same:
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            same = bool(torch.equal(ref.view(torch.int64), mine.view(torch.int64)))
+        flag = torch.tensor([int(same)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item())
+        # gather shards on rank 0
+        def gather(v):
+            t = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+            outs = []
+            for r in range(world):
+                size = (n if r == world - 1 else (n * (r + 1) // world) // 2 * 2) - (n * r // world) // 2 * 2
+                buf = t if r == rank else torch.empty(size, dtype=torch.float64, device="cuda")
+                dist.broadcast(buf, r)
+                outs.append(buf.clone())
+            return torch.cat(outs).cpu().numpy()
+        xg = gather(x.numpy())
+        pg = [gather(p) for p in ob.p[:6]]
+        if rank == 0:
+            x1 = fl.DeviceVector.start(start, n, seed=seed)
+            ob1 = fl.Observer(keep_vectors=True, max_vec_iters=10)
+            st1 = run(prob, x1, observer=ob1, Warning=False, **kw)
+            xs = x1.numpy()
+            scale = max(np.linalg.norm(xs), 1.0)
+            dx = np.linalg.norm(xg - xs) / scale
+            dp = max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(pg, ob1.p[:6]))
+            its_ok = abs(st.iterations - st1.iterations) <= max(1, 0.02 * st1.iterations)
+            good = same and dx < 1e-8 and dp < 1e-9 and its_ok and st.status == st1.status
+            print(f"[{world} ranks] {algo} kind={kind} {kw}: iterations {st.iterations}/{st1.iterations} "
+                  f"ranks_identical={same} |dx|={dx:.2e} max|dp|(first 6)={dp:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+            ok = ok and good
+            x1.free()
+        x.free()
+    fl.lib().flgpu_comm_destroy(comm)
+    okt = torch.tensor([int(ok)], device="cuda")
+    dist.broadcast(okt, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if okt.item() else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -302,6 +302,19 @@ def test_cpp_dropin_program_runs(fl, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_row_sharded_nccl(fl):
+    """Row-sharded over every visible GPU (one process per GPU, NCCL exchange) against the 1-GPU run.
+    Needs >= 2 GPUs; the round-end single-GPU run skips it (the CPU suite covers the same host logic with
+    gloo at world_size 2: tests/test_hostsim.py::test_row_sharded_two_ranks_gloo)."""
+    ngpu = fl.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(ngpu, 8)}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29512",
+                        os.path.join(ROOT, "tests", "gpu_multi.py"), "20"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_edge_cases(fl):
     for fn in (fl.LBFGS, fl.ConjugateGradient):                 # start at the minimiser (f90:443 / 237)
