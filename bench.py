@@ -36,7 +36,13 @@ UNIT = "it/s"
 
 def workload(n, mem):
     return (f"LBFGS m={mem} extended Rosenbrock n=2^{n.bit_length() - 1} fp64, start R1 = (-1.2,1)+0.1(u-0.5) "
-            f"seed {SEED}, f_fd CUDA callback, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
+            f"seed {SEED}, f_fd present, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
+
+
+LS_MODES = {True: "fused (flgpu_fused_fn: objective kernel forms x0+a*p; 2n doubles per trial + 4n per accepted step)",
+            False: "plain (opaque f/fd/f_fd device callbacks; 7n doubles per f+g trial)"}
+NCU_NAMES = {"k1_update_dots": "k1_update_dots_kernel", "k3_direction": "k3_direction_kernel", "trial_x": "trial_kernel",
+             "dot": "dot_kernel", "cg_dots": "cg_dots_kernel", "cg_update": "cg_update_kernel"}
 
 
 # --------------------------------------------------------------------------- clocks
@@ -171,7 +177,7 @@ def run_ours(args):
     prob = fl.builtin_problem(fl.OBJ_ROSENBROCK)
     first, last = mem + W - 1, mem + W + K - 1   # observer indices bracketing exactly K main-loop iterations
 
-    def timed_run(time_kernels):
+    def timed_run(time_kernels, fused=True):
         x = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_local, seed=SEED, offset=lo, n_global=n)
         ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         mark = {}
@@ -195,7 +201,7 @@ def run_ours(args):
             return False
         ob = fl.Observer(on_iteration=on_iter)
         st = fl.LBFGS(prob, x, Memory=mem, Warning=False, MaxIteration=W + K, observer=ob, comm=comm, offset=lo,
-                      n_global=n, time_kernels=time_kernels)
+                      n_global=n, time_kernels=time_kernels, fused=fused)
         if "t1" not in mark:
             raise SystemExit(f"bench.py: optimizer stopped after {st.iterations} iterations (status {st.status}) "
                              f"before {last + 1}; lower --steps")
@@ -207,7 +213,8 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, mark, st, _ = timed_run(False)
+    fused = not args.plain
+    ms, mark, st, _ = timed_run(False, fused)
     clocks = sampler.stop(mark["t0"], mark["t1"]) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -217,7 +224,14 @@ def run_ours(args):
     trials = mark["c1"][2] - mark["c0"][2]
 
     # ---- pass 2: per-kernel CUDA-event times over the same timed region -> roofline of the dominant kernel
-    ms2, mark2, st2, kt = timed_run(True)
+    ms2, mark2, st2, kt = timed_run(True, fused)
+    # ---- pass 3: the other line-search mode, for the record (same iterates up to summation order)
+    ms3, mark3, _, _ = timed_run(False, not fused)
+    t3 = torch.tensor([ms3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    other = {"line_search": LS_MODES[not fused], "value": K / (float(t3.item()) * 1e-3), "unit": UNIT,
+             "trials_in_timed_region": mark3["c1"][2] - mark3["c0"][2]}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -235,7 +249,7 @@ def run_ours(args):
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = prof.get(top, {}).get("dram_bytes_per_launch")
+        traffic = prof.get(NCU_NAMES.get(top, top), {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     total_bytes = sum(v["bytes"] for v in kt.values())
@@ -260,6 +274,8 @@ def run_ours(args):
     e0.record()
     te = time.time()
     if world == 1:
+        if not fused:
+            os.environ["FLGPU_NO_FUSED"] = "1"
         L = fl.lib()
         f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
         L.flgpu_builtin_ref_callbacks(fl.OBJ_ROSENBROCK, C.byref(f), C.byref(fd), C.byref(ffd))
@@ -270,7 +286,8 @@ def run_ours(args):
         L.flgpu_last_stats(C.byref(ste))
         e2e_call = "__nonlinearoptimization_MOD_lbfgs (host x, device-pointer callbacks)"
     else:
-        ste = fl.LBFGS(prob, xh, Memory=mem, Warning=False, MaxIteration=Ke, comm=comm, offset=lo, n_global=n)
+        ste = fl.LBFGS(prob, xh, Memory=mem, Warning=False, MaxIteration=Ke, comm=comm, offset=lo, n_global=n,
+                       fused=fused)
         e2e_call = "flgpu_lbfgs (host x shard, NCCL communicator)"
     e1.record()
     barrier()
@@ -296,8 +313,10 @@ def run_ours(args):
                 "config": {"workload": workload(n, mem), "n_global": n, "rows_per_gpu": n_local,
                            "parallelism": f"row-shard x{world}" if world > 1 else "1 GPU",
                            "l2": "inputs (2 GiB/vector) exceed L2; no flush needed",
+                           "line_search": LS_MODES[fused],
                            "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "other_line_search_mode": other}
         print(json.dumps(line), flush=True)
     if comm is not None:
         fl.lib().flgpu_comm_destroy(comm)
@@ -314,7 +333,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="override the global dimension (debugging only)")
     ap.add_argument("--mem", type=int, default=MEM)
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--plain", action="store_true", help="headline with opaque callbacks (no fused line-search evaluation)")
     ap.add_argument("--cpu-log2n", type=int, default=21, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -46,7 +46,7 @@ def lib():
     L.flgpu_comm_destroy.argtypes = [C.c_void_p]
     L.flgpu_comm_unique_id.argtypes = [C.c_void_p]
     L.flgpu_current_stream.restype = C.c_void_p
-    for name in ("flgpu_lbfgs", "flgpu_conjugate_gradient"):
+    for name in ("flgpu_lbfgs", "flgpu_conjugate_gradient", "flgpu_steepest_descent"):
         getattr(L, name).argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Options), C.c_void_p, C.c_int64,
                                      C.c_int, C.POINTER(capi.Stats)]
     L.flgpu_kernel_times.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64),
@@ -228,6 +228,18 @@ def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIte
                 dict(Method=Method, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                      Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
                      WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp), fused=fused))
+
+
+def SteepestDescent(problem, x, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
+                    WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None, comm=None,
+                    offset=0, n_global=0, time_kernels=False, fused=True):
+    """Steepest descent (reference: SteepestDescent, f90:55-188): p = -f'(x) through the same line searchers."""
+    ptr, n, space = _resolve_x(x)
+    return _run(lib().flgpu_steepest_descent, False, problem, ptr, n, space, observer, stream, comm, offset,
+                n_global, time_kernels,
+                dict(Strong=Strong, Warning=Warning, MaxIteration=MaxIteration, Precision=Precision,
+                     MinStepLength=MinStepLength, WolfeConst1=WolfeConst1, WolfeConst2=WolfeConst2,
+                     Increment=Increment, fused=fused))
 
 
 class History:

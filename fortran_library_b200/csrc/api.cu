@@ -54,19 +54,22 @@ int cb_space_now() {
     return v >= 0 ? v : space_from_env("FLGPU_CALLBACK_SPACE", FLGPU_SPACE_DEVICE);
 }
 
-int run(bool cg, const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n, int x_space,
+enum Algo { ALGO_LBFGS = 0, ALGO_CG = 1, ALGO_SD = 2 };
+
+int run(int algo, const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n, int x_space,
         flgpu_stats *stats) {
     require_device();
     if (!prob || !prob->f || !prob->fd) fatal("flgpu: f and fd callbacks are required (f90:40)");
     if (n < 0) fatal("flgpu: negative dimension");
     CudaBackend B(*prob, n, *opt);
-    Params P = params_from_options(*opt, cg, prob->f_fd != nullptr);
+    Params P = params_from_options(*opt, algo == ALGO_CG, prob->f_fd != nullptr);
     ThreadState saved = tls;
     tls.stream = B.stream_handle();
     tls.backend = &B;
     FLGPU_CUDA_CHECK(cudaGetDevice(&tls.device));
     flgpu_stats st;
-    if (cg) run_cg(B, P, x, x_space, &st);
+    if (algo == ALGO_CG) run_cg(B, P, x, x_space, &st);
+    else if (algo == ALGO_SD) run_sd(B, P, x, x_space, &st);
     else run_lbfgs(B, P, x, x_space, &st);
     B.resolve_times();
     tls.stream = saved.stream;
@@ -135,7 +138,7 @@ void ad_ffd(const flgpu_eval_ctx *c, double *f_dev, double *g, const double *x, 
     k::set_scalar_kernel<<<1, 1, 0, s>>>(f_dev, fx);
 }
 
-void run_ref(bool cg, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
+void run_ref(int algo, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
              flgpu_options &o) {
     require_device();
     RefAdapter A;
@@ -160,7 +163,7 @@ void run_ref(bool cg, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_
     o.observer_user = tls.observer_user;
     const char *nf = std::getenv("FLGPU_NO_FUSED");
     if (nf && nf[0] && nf[0] != '0') o.no_fused = 1;
-    run(cg, &prob, &o, x, dim, x_space_now(), nullptr);
+    run(algo, &prob, &o, x, dim, x_space_now(), nullptr);
     if (A.xh) cudaFreeHost(A.xh);
     if (A.gh) cudaFreeHost(A.gh);
 }
@@ -215,11 +218,15 @@ void flgpu_options_default(flgpu_options *o, int for_cg) {
 
 int flgpu_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local, int x_space,
                 flgpu_stats *stats) {
-    return run(false, prob, opt, x, n_local, x_space, stats);
+    return run(ALGO_LBFGS, prob, opt, x, n_local, x_space, stats);
 }
 int flgpu_conjugate_gradient(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local,
                              int x_space, flgpu_stats *stats) {
-    return run(true, prob, opt, x, n_local, x_space, stats);
+    return run(ALGO_CG, prob, opt, x, n_local, x_space, stats);
+}
+int flgpu_steepest_descent(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local,
+                           int x_space, flgpu_stats *stats) {
+    return run(ALGO_SD, prob, opt, x, n_local, x_space, stats);
 }
 
 void flgpu_set_x_space(int space) { g_x_space.store(space); }
@@ -285,7 +292,27 @@ void __nonlinearoptimization_MOD_lbfgs(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, dou
     flgpu_options_default(&o, 0);
     if (Memory) o.memory = *Memory;
     fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
-    run_ref(false, f, fd, f_fd, x, *dim, o);
+    run_ref(ALGO_LBFGS, f, fd, f_fd, x, *dim, o);
+}
+
+void __nonlinearoptimization_MOD_steepestdescent(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
+                                                 flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+                                                 const int32_t *Warning, const int *MaxIteration,
+                                                 const double *Precision, const double *MinStepLength,
+                                                 const double *WolfeConst1, const double *WolfeConst2,
+                                                 const double *Increment) {
+    flgpu_options o;
+    flgpu_options_default(&o, 0);   // c2 default 0.9 (f90:84)
+    fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
+    run_ref(ALGO_SD, f, fd, f_fd, x, *dim, o);
+}
+void nonlinearoptimization_mp_steepestdescent_(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
+                                               flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning,
+                                               const int *MaxIteration, const double *Precision,
+                                               const double *MinStepLength, const double *WolfeConst1,
+                                               const double *WolfeConst2, const double *Increment) {
+    __nonlinearoptimization_MOD_steepestdescent(f, fd, x, dim, f_fd, Strong, Warning, MaxIteration, Precision,
+                                                MinStepLength, WolfeConst1, WolfeConst2, Increment);
 }
 
 void __nonlinearoptimization_MOD_conjugategradient(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,
@@ -298,7 +325,7 @@ void __nonlinearoptimization_MOD_conjugategradient(flgpu_ref_f_fn f, flgpu_ref_f
     flgpu_options_default(&o, 1);
     if (Method) o.method = parse_method(Method, len_Method, false);
     fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
-    run_ref(true, f, fd, f_fd, x, *dim, o);
+    run_ref(ALGO_CG, f, fd, f_fd, x, *dim, o);
 }
 
 void __nonlinearoptimization_MOD_conjugategradient_basic(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x,
@@ -312,7 +339,7 @@ void __nonlinearoptimization_MOD_conjugategradient_basic(flgpu_ref_f_fn f, flgpu
     o.method = parse_method(Method, len_Method, true);
     o.no_clamp = 1;  // f90:2265-2278: tunables used as given
     fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
-    run_ref(true, f, fd, nullptr, x, *dim, o);
+    run_ref(ALGO_CG, f, fd, nullptr, x, *dim, o);
 }
 
 void nonlinearoptimization_mp_lbfgs_(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim,

@@ -491,6 +491,66 @@ finish:
     st.gpu_launches = B.launches;
 }
 
+// --------------------------------------------------------------------------- SteepestDescent
+// f90:55-188.  After() (f90:172-187): g.g, p.p a^2, p = -g, a = a*phidold/phidnew.  p.p needs no pass:
+// p = -f'old, so dot_product(p,p) is the previous g.g bit for bit.
+void run_sd(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *stp) {
+    flgpu_stats &st = *stp;
+    std::memset(&st, 0, sizeof st);
+    double slots[NSLOTS];
+    double *xc = B.vec_alloc(), *xo = B.vec_alloc();
+    double *gc = B.vec_alloc(), *go = B.vec_alloc();
+    double *p = B.vec_alloc();
+    B.upload(xc, x_user, x_space);
+    if (P.has_f_fd) { B.eval_fg(xc, gc); st.n_f_fd++; }                      // f90:86-90
+    else { B.eval_f(xc); st.n_f++; B.eval_g(xc, gc); st.n_fd++; }
+    B.dot(gc, gc, SL_GG);
+    B.fetch(slots); st.host_syncs++;
+    double fnew = slots[SL_F];
+    double gg = slots[SL_GG];
+    st.f = fnew; st.gnorm2 = gg;
+    if (gg < P.tol) { st.status = FLGPU_INITIAL_CONVERGED; goto finish; }    // f90:93
+    {
+        B.neg(p, gc);                                                        // f90:92
+        double phidnew = -gg;
+        double a = (fnew == 0.0) ? 1.0 : std::fabs(fnew) / std::sqrt(gg);    // f90:94-95
+        st.status = FLGPU_MAX_ITERATION;
+        int64_t it = 0;
+        for (int iIteration = 1; iIteration <= P.maxit; iIteration++) {
+            const double phidold = phidnew;
+            const double pp = gg;                                            // dot_product(p,p), p = -f'old
+            // Strong -> StrongWolfe(_fdwithf); else Wolfe / Wolfe_fdwithf, which never calls f_fd (f90:1373)
+            SearchResult r = line_search(B, st, P, P.strong, P.has_f_fd && P.strong, xc, xo, go, p, a, fnew,
+                                         phidnew, 0, 0.0, 0.0);
+            std::swap(xc, xo); std::swap(gc, go);
+            a = r.a; fnew = r.fx;
+            st.iterations = ++it;
+            st.f = fnew;
+            const bool stop = observe(P, B, st, it - 1, a, fnew, phidold, r.trials, p, xc, gc);
+            B.dot(gc, gc, SL_GG);                                            // After() f90:172-187
+            B.fetch(slots); st.host_syncs++;
+            gg = slots[SL_GG];
+            st.gnorm2 = gg;
+            if (gg < P.tol) { st.status = FLGPU_CONVERGED; break; }
+            if (pp * a * a < P.minstep) {
+                if (P.warn) step_warning("Steepest descent", gg);
+                st.status = FLGPU_STEP_CONVERGED; break;
+            }
+            if (stop) { st.status = FLGPU_STOPPED_BY_OBSERVER; break; }
+            B.neg(p, gc);
+            phidnew = -gg;
+            a = a * phidold / phidnew;
+        }
+        if (st.status == FLGPU_MAX_ITERATION && P.warn) {                    // f90:168-171
+            std::printf(" Failed steepest descent: max iteration exceeded!\n");
+            std::printf(" Euclidean norm of gradient = %.17g\n", std::sqrt(gg));
+        }
+    }
+finish:
+    B.download(x_user, xc, x_space);
+    st.gpu_launches = B.launches;
+}
+
 }  // namespace flgpu
 
 namespace flgpu {

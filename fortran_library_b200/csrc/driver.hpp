@@ -25,6 +25,7 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd);
 
 void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *st);
 void run_cg(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *st);
+void run_sd(Backend &B, const Params &P, double *x_user, int x_space, flgpu_stats *st);
 
 }  // namespace flgpu
 

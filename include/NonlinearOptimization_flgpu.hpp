@@ -25,6 +25,11 @@ typedef int (*f_fd_t)(double &, double *, const double *, const int &);
 #endif
 
 extern "C" {
+    void FLGPU_SYM(steepestdescent)(
+        f_t f, fd_t fd, double * x, const int & dim, f_fd_t f_fd,
+        const int32_t & Strong, const int32_t & Warning, const int & MaxIteration,
+        const double & Precision, const double & MinStepLength,
+        const double & WolfeConst1, const double & WolfeConst2, const double & Increment);
     void FLGPU_SYM(conjugategradient_basic)(
         f_t f, fd_t fd, double * x, const int & dim, const char * Method,
         const int32_t & Strong, const int32_t & Warning, const int & MaxIteration,
@@ -42,6 +47,16 @@ extern "C" {
         const int32_t & Strong, const int32_t & Warning, const int & MaxIteration,
         const double & Precision, const double & MinStepLength,
         const double & WolfeConst1, const double & WolfeConst2, const double & Increment);
+}
+
+// SteepestDescent (f90:55), as reference hpp:395-411
+inline void SteepestDescent(f_t f, fd_t fd, f_fd_t f_fd, double * x, const int & dim,
+    const bool & Strong = true, const bool & Warning = true,
+    const int & MaxIteration = 1000, const double & Precision = 1e-15, const double & MinStepLength = 1e-15,
+    const double & WolfeConst1 = 1e-4, const double & WolfeConst2 = 0.9, const double & Increment = 1.05) {
+    const int32_t s = Strong ? -1 : 0, w = Warning ? -1 : 0;
+    FLGPU_SYM(steepestdescent)(f, fd, x, dim, f_fd, s, w, MaxIteration, Precision, MinStepLength,
+        WolfeConst1, WolfeConst2, Increment);
 }
 
 // f and f' evaluated separately -> ConjugateGradient_basic (f90:2249), as reference hpp:414-432

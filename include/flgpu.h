@@ -5,6 +5,7 @@
  * Reference interfaces replaced ("f90:" = source/NonlinearOptimization.f90,
  * "hpp:" = cpp/NonlinearOptimization.hpp of YifanShenSZ/Fortran-Library):
  *   LBFGS                   f90:398-400   (no hpp declaration exists; added by analogy)
+ *   SteepestDescent         f90:55-56     hpp:279-291 (gnu) / hpp:11-23 (intel)   [SURVEY 8f row N1]
  *   ConjugateGradient       f90:193-195   hpp:310-324 (gnu) / hpp:42-56 (intel)
  *   ConjugateGradient_basic f90:2249-2251 hpp:292-306 (gnu) / hpp:24-38 (intel)
  *   Strong-Wolfe / Wolfe line searchers f90:1286,1373,1462,1582 (internal to the above)
@@ -160,6 +161,9 @@ int flgpu_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, 
                 int x_space, flgpu_stats *stats);
 int flgpu_conjugate_gradient(const flgpu_problem *prob, const flgpu_options *opt, double *x,
                              int64_t n_local, int x_space, flgpu_stats *stats);
+/* SteepestDescent (f90:55-188): the same line searchers and kernels with p = -f'(x) */
+int flgpu_steepest_descent(const flgpu_problem *prob, const flgpu_options *opt, double *x,
+                           int64_t n_local, int x_space, flgpu_stats *stats);
 
 /* ------------------------------------------------------------------ multi-GPU (row shards) */
 /* One process per GPU.  Rank 0 obtains a 128-byte id, the caller distributes it
@@ -194,6 +198,11 @@ void __nonlinearoptimization_MOD_lbfgs(
     flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
     const double *Precision, const double *MinStepLength, const double *WolfeConst1,
     const double *WolfeConst2, const double *Increment);
+void __nonlinearoptimization_MOD_steepestdescent( /* f90:55-56, hpp:279-291 */
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, flgpu_ref_f_fd_fn f_fd,
+    const int32_t *Strong, const int32_t *Warning, const int *MaxIteration, const double *Precision,
+    const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
+    const double *Increment);
 void __nonlinearoptimization_MOD_conjugategradient(
     flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const char *Method,
     flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
@@ -210,6 +219,11 @@ void nonlinearoptimization_mp_lbfgs_(
     flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,
     const double *Precision, const double *MinStepLength, const double *WolfeConst1,
     const double *WolfeConst2, const double *Increment);
+void nonlinearoptimization_mp_steepestdescent_( /* hpp:11-23 */
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, flgpu_ref_f_fd_fn f_fd,
+    const int32_t *Strong, const int32_t *Warning, const int *MaxIteration, const double *Precision,
+    const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
+    const double *Increment);
 void nonlinearoptimization_mp_conjugategradient_(
     flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const char *Method,
     flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,

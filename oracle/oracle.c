@@ -591,3 +591,58 @@ void orc_conjugategradient_basic(orc_f_t f, orc_fd_t fd, double *x, const int *d
             *Precision * *Precision, *MinStepLength * *MinStepLength, *WolfeConst1, *WolfeConst2,
             Increment);
 }
+
+/* ------------------------------------------------------------------ SteepestDescent f90:55-188 */
+/* The 8 textual copies of the main loop (f90:101-167) differ only in the line searcher called:
+ * Strong -> StrongWolfe(_fdwithf when f_fd is present), else Wolfe(_fdwithf == Wolfe, f90:1373). */
+void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, orc_ffd_t f_fd,
+                         const int *Strong, const int *Warning, const int *MaxIteration,
+                         const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+                         const double *WolfeConst2, const double *Increment) {
+    int dim = *dim_, sw, warn, maxit, iIteration, i, outer = 0;
+    double tol, minstep, c1, c2, a, fnew, fold, phidnew, phidold;
+    double *p = valloc(dim), *fdnew = valloc(dim), *fdold = valloc(dim);
+    long tb;
+    (void)fold;
+    memset(&g_st, 0, sizeof g_st);
+    if (Strong) sw = (*Strong != 0); else sw = 1;                                     /* f90:72-85 */
+    if (Warning) warn = (*Warning != 0); else warn = 1;
+    if (MaxIteration) maxit = *MaxIteration; else maxit = 1000;
+    if (Precision) tol = *Precision * *Precision; else tol = 1e-30;
+    if (MinStepLength) minstep = *MinStepLength * *MinStepLength; else minstep = 1e-30;
+    if (WolfeConst1) c1 = fmax(1e-15, *WolfeConst1); else c1 = 1e-4;
+    if (WolfeConst2) c2 = fmin(1.0 - 1e-15, fmax(c1 + 1e-15, *WolfeConst2)); else c2 = 0.9;
+    if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }                    /* f90:86-90 */
+    else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
+    for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:92 */
+    phidnew = -dot(fdnew, fdnew, dim);
+    if (-phidnew < tol) { g_st.status = 3; goto done; }
+    if (fnew == 0.0) a = 1.0; else a = fabs(fnew) / sqrt(-phidnew);                   /* f90:94-95 */
+    for (iIteration = 1; iIteration <= maxit; iIteration++) {
+        double phid0;
+        fold = fnew; memcpy(fdold, fdnew, sizeof(double) * (size_t)dim); phidold = phidnew;
+        tb = g_st.n_trials; phid0 = phidnew;
+        line_search(sw, f_fd != NULL, c1, c2, f, fd, f_fd, x, &a, p, &fnew, phidnew, fdnew, dim, Increment);
+        trace(outer++, dim, p, x, fdnew, a, fnew, phid0, tb);
+        /* After() f90:172-187 */
+        phidnew = dot(fdnew, fdnew, dim);
+        if (phidnew < tol) { g_st.status = 0; goto done; }
+        if (dot(p, p, dim) * a * a < minstep) {
+            if (warn) {
+                printf(" Steepest descent warning: step length has converged, but gradient norm has not met accuracy goal\n");
+                printf(" Euclidean norm of gradient = %.17g\n", sqrt(phidnew));
+            }
+            g_st.status = 1; goto done;
+        }
+        for (i = 0; i < dim; i++) p[i] = -fdnew[i];
+        phidnew = -dot(fdnew, fdnew, dim);
+        a = a * phidold / phidnew;
+    }
+    g_st.status = 2;
+    if (warn) {                                                                       /* f90:168-171 */
+        printf(" Failed steepest descent: max iteration exceeded!\n");
+        printf(" Euclidean norm of gradient = %.17g\n", sqrt(dot(fdnew, fdnew, dim)));
+    }
+done:
+    free(p); free(fdnew); free(fdold);
+}

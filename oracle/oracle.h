@@ -4,6 +4,7 @@
  * CPU restatement (plain C, strict IEEE: -O2 -ffp-contract=off, sequential sums)
  * of the reference's large-dimension unconstrained-optimizer path in
  * /root/reference/source/NonlinearOptimization.f90:
+ *     SteepestDescent          f90:55-188
  *     ConjugateGradient        f90:193-394
  *     LBFGS                    f90:398-625
  *     Wolfe / Wolfe_fdwithf    f90:1286-1459
@@ -73,6 +74,12 @@ void orc_conjugategradient_basic(orc_f_t f, orc_fd_t fd, double *x, const int *d
                                  const double *Precision, const double *MinStepLength,
                                  const double *WolfeConst1, const double *WolfeConst2,
                                  const double *Increment, int len_Method);
+
+/* f90:55-188 */
+void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim, orc_ffd_t f_fd,
+                         const int *Strong, const int *Warning, const int *MaxIteration,
+                         const double *Precision, const double *MinStepLength, const double *WolfeConst1,
+                         const double *WolfeConst2, const double *Increment);
 
 /* line searchers, f90:1286,1373,1462,1582 (exported like the reference's module procedures) */
 void orc_wolfe(const double *c1, const double *c2, orc_f_t f, orc_fd_t fd, double *x, double *a,

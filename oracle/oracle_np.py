@@ -366,6 +366,39 @@ def conjugate_gradient(f, fd, x, Method=None, f_fd=None, Strong=None, Warning=No
     return x, cnt
 
 
+# ----------------------------------------------------------------- SteepestDescent f90:55-188
+def steepest_descent(f, fd, x, f_fd=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
+                     MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None):
+    cnt = Counters()
+    x = np.array(x, dtype=np.float64)
+    sw, warn, maxit, tol, minstep, c1, c2 = _defaults(Strong, Warning, MaxIteration, Precision,
+                                                      MinStepLength, WolfeConst1, WolfeConst2, 0.9)
+    if f_fd is not None:                            # f90:86-90
+        fnew, fdnew = f_fd(x); cnt.n_ffd += 1
+    else:
+        fnew = f(x); cnt.n_f += 1; fdnew = fd(x); cnt.n_fd += 1
+    p = -fdnew; phidnew = -dot(fdnew, fdnew)        # f90:92
+    if -phidnew < tol:
+        cnt.status = 3; return x, cnt
+    a = 1.0 if fnew == 0.0 else div(abs(fnew), math.sqrt(-phidnew))
+    for _ in range(maxit):                          # f90:101-167: one of 8 copies, same body
+        phidold = phidnew
+        t0 = cnt.trials
+        x, a, fnew, fdnew = _search(sw, f_fd is not None, c1, c2, f, fd, f_fd, x, a, p, fnew, phidnew,
+                                    Increment, cnt)
+        cnt.history.append((p.copy(), x.copy(), fdnew.copy(), a, fnew, phidold, cnt.trials - t0))
+        cnt.iters += 1
+        phidnew = dot(fdnew, fdnew)                 # After() f90:172-187
+        if phidnew < tol:
+            cnt.status = 0; return x, cnt
+        if dot(p, p) * a * a < minstep:
+            cnt.status = 1; return x, cnt
+        p = -fdnew; phidnew = -dot(fdnew, fdnew)
+        a = div(a * phidold, phidnew)
+    cnt.status = 2
+    return x, cnt
+
+
 # ----------------------------------------------------------------- objectives (same op order as objectives.c)
 def quartic():
     def f(x):

@@ -6,16 +6,16 @@
 # Outputs land in gpurun_out/; summaries are made here with profiles/summarise.py and committed under profiles/.
 set -u
 TAG=${1:-r01}
-CMD="python bench.py --steps 5 --warmup 3 --no-cpu --e2e-steps 2"
+CMD="python bench.py --steps 4 --warmup 3 --no-cpu --e2e-steps 2"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 cat gpurun_out/${TAG}_plain.json | cut -c1-400
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'k1_update_dots|k3_direction' -s 24 -c 4 \
+ncu --set full --clock-control none --import-source on -k regex:'k1_update_dots|k3_direction' -s 24 -c 2 \
     -f -o gpurun_out/${TAG}_k1k3 $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "k1k3 rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:'trial_kernel|dot_kernel|objective_kernel' -s 700 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:'objective_kernel' -s 300 -c 5 \
     -f -o gpurun_out/${TAG}_ls $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "ls rc=$?"
 ls -la gpurun_out/

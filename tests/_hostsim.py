@@ -78,6 +78,10 @@ def cg(kind, x, **kw):
     return _run("flgpu_hostsim_cg", True, kind, x, **kw)
 
 
+def sd(kind, x, **kw):
+    return _run("flgpu_hostsim_sd", False, kind, x, **kw)
+
+
 class History:
     """flgpu_hostsim_history_*: the two-loop recursion as an operator (host pointers)."""
 

@@ -156,6 +156,29 @@ def cg(cbs, x, Method=None, use_ffd=False, Strong=None, Warning=None, MaxIterati
     return x, stats()
 
 
+def sd(cbs, x, use_ffd=False, Strong=None, Warning=None, MaxIteration=None, Precision=None,
+       MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, trace=None, sum_mode=0):
+    """orc_steepestdescent (f90:55-188) with the reference's optional-argument semantics."""
+    L = lib()
+    f, fd, ffd = cbs
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n = C.c_int(x.size)
+    L.orc_set_sum_mode(sum_mode)
+    if trace is not None:
+        trace.install()
+    try:
+        L.orc_steepestdescent(f, fd, x.ctypes.data_as(C.c_void_p), C.byref(n), ffd if use_ffd else None,
+                              _opt(C.c_int, None if Strong is None else int(Strong)),
+                              _opt(C.c_int, None if Warning is None else int(Warning)),
+                              _opt(C.c_int, MaxIteration), _opt(C.c_double, Precision),
+                              _opt(C.c_double, MinStepLength), _opt(C.c_double, WolfeConst1),
+                              _opt(C.c_double, WolfeConst2), _opt(C.c_double, Increment))
+    finally:
+        Trace.uninstall()
+        L.orc_set_sum_mode(0)
+    return x, stats()
+
+
 def cg_basic(cbs, x, Method="DY", Strong=True, Warning=True, MaxIteration=1000, Precision=1e-15,
              MinStepLength=1e-15, WolfeConst1=1e-4, WolfeConst2=0.45, Increment=1.05, trace=None):
     L = lib()

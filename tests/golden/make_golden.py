@@ -43,6 +43,9 @@ CASES = [
     ("lbfgs_diag_60_m30", "lbfgs", "diag", 60, dict(use_ffd=True, Memory=30, MaxIteration=40)),
     ("cg_dy_quartic_200", "cg", "quartic", 200, dict(Method="DY", use_ffd=True)),        # BASELINE configs[2] shape
     ("cg_pr_quartic_200", "cg", "quartic", 200, dict(Method="PR", use_ffd=True)),
+    ("sd_quartic10", "sd", "quartic", 10, dict(MaxIteration=40)),                         # test.f90:336-339 shape
+    ("sd_quartic10_ffd", "sd", "quartic", 10, dict(use_ffd=True, MaxIteration=40)),       # test.f90:341-344 shape
+    ("sd_rosenR1_64", "sd", "rosenR1", 64, dict(use_ffd=True, MaxIteration=40)),
 ]
 
 
@@ -60,7 +63,7 @@ def run_case(algo, name, n, kw):
     kind = _cases.OBJECTIVES[name][0]
     x0 = _cases.start(name, n)
     tr = O.Trace()
-    run = O.lbfgs if algo == "lbfgs" else O.cg
+    run = {"lbfgs": O.lbfgs, "cg": O.cg, "sd": O.sd}[algo]
     x, st = run(O.builtin_callbacks(kind, 0, n), x0.copy(), use_ffd=use, Warning=False, trace=tr, **kw)
     return x0, x, st, tr, use
 
@@ -69,7 +72,7 @@ def cross_check(algo, name, n, kw, x, tr):
     kw = dict(kw)
     use = kw.pop("use_ffd", False)
     f, fd, ffd = _np_objective(name, n)
-    run = N.lbfgs if algo == "lbfgs" else N.conjugate_gradient
+    run = {"lbfgs": N.lbfgs, "cg": N.conjugate_gradient, "sd": N.steepest_descent}[algo]
     with np.errstate(all="ignore"):
         xb, c = run(f, fd, _cases.start(name, n), f_fd=ffd if use else None, Warning=False, **kw)
     assert np.array_equal(x, xb), "oracle.c and oracle_np.py disagree"

@@ -245,6 +245,16 @@ int flgpu_hostsim_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, dou
     return 0;
 }
 
+int flgpu_hostsim_sd(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n,
+                     flgpu_stats *stats) {
+    HostBackend B(*prob, n, opt->offset, opt->n_global);
+    flgpu::Params P = flgpu::params_from_options(*opt, false, prob->f_fd != nullptr);
+    flgpu_stats st;
+    flgpu::run_sd(B, P, x, 0, &st);
+    if (stats) *stats = st;
+    return 0;
+}
+
 int flgpu_hostsim_cg(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n,
                      flgpu_stats *stats) {
     HostBackend B(*prob, n, opt->offset, opt->n_global);

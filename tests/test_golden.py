@@ -13,7 +13,7 @@ import _oracle as O
 
 # cases whose stored run ends in a long chaotic tail (MaxIteration hit mid-descent / hundreds of
 # 1e-15-sized steps): only the early iterations and the exit status are compared
-TAIL_UNSTABLE = {"lbfgs_diag_60_m30", "lbfgs_rosenR1_64_m5", "cg_dy_quartic10_weak"}
+TAIL_UNSTABLE = {"lbfgs_diag_60_m30", "lbfgs_rosenR1_64_m5", "cg_dy_quartic10_weak", "sd_rosenR1_64"}
 
 
 def _check_against_golden(d, x, iterations, status, rows, name):
@@ -40,7 +40,7 @@ def test_oracle_reproduces_golden_bitwise(name):
     kind = _cases.OBJECTIVES[d["objective"]][0]
     assert np.array_equal(_cases.start(d["objective"], d["n"]), d["x0"])
     tr = O.Trace()
-    run = O.lbfgs if d["algorithm"] == "lbfgs" else O.cg
+    run = {"lbfgs": O.lbfgs, "cg": O.cg, "sd": O.sd}[d["algorithm"]]
     x, st = run(O.builtin_callbacks(kind, 0, d["n"]), d["x0"].copy(), use_ffd=use, Warning=False, trace=tr, **kw)
     assert np.array_equal(x, d["x_final"])
     assert (st.n_iter, st.status, st.n_f, st.n_fd, st.n_ffd, st.n_trials) == \
@@ -58,7 +58,7 @@ def test_host_control_flow_lands_on_golden(name, fused):
     kw = dict(d["options"])
     use = kw.pop("use_ffd", False)
     kind = _cases.OBJECTIVES[d["objective"]][0]
-    run = H.lbfgs if d["algorithm"] == "lbfgs" else H.cg
+    run = {"lbfgs": H.lbfgs, "cg": H.cg, "sd": H.sd}[d["algorithm"]]
     ob = H.Observer(keep_vectors=False)
     x, st = run(kind, d["x0"], observer=ob, use_ffd=use, Warning=False, n_global=d["n"], fused=fused, **kw)
     _check_against_golden(d, x, st.iterations, st.status, ob.rows, name)
@@ -78,7 +78,7 @@ def test_gpu_lands_on_golden(name, fused):
         prob.f_fd = None
     x = d["x0"].copy()                       # host x in/out, as the reference's callers pass it
     ob = fl.Observer()
-    run = fl.LBFGS if d["algorithm"] == "lbfgs" else fl.ConjugateGradient
+    run = {"lbfgs": fl.LBFGS, "cg": fl.ConjugateGradient, "sd": fl.SteepestDescent}[d["algorithm"]]
     st = run(prob, x, observer=ob, Warning=False, fused=fused, **kw)
     assert st.gpu_launches > 0
     _check_against_golden(d, x, st.iterations, st.status, ob.rows, name)

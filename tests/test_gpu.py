@@ -202,6 +202,24 @@ def test_cg_trajectory_within_oracle_envelope(fl, method, name, kw, fused):
     _cases.check_envelope(traces, ob.p, f"cg {method} {name} {kw}")
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
+@pytest.mark.parametrize("name,kw", [("quartic", dict(MaxIteration=40)), ("rosenR1", dict(MaxIteration=40)),
+                                     ("diag", dict(MaxIteration=40, Strong=False)),
+                                     ("quartic", dict(MaxIteration=40, use_ffd=False))])
+def test_sd_trajectory_within_oracle_envelope(fl, name, kw, fused):
+    """SteepestDescent (f90:55-188) through the same kernels."""
+    n = 10_000
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.sd(cbs, x, use_ffd=use, **k), **kw)
+    ob = fl.Observer(keep_vectors=True, max_vec_iters=20)
+    x = _dev_start(fl, name, n)
+    st = fl.SteepestDescent(_problem(fl, name, use), x, observer=ob, Warning=False, fused=fused, **kw)
+    _cases.check_envelope(traces, ob.p, f"sd {name} {kw}")
+    assert np.array_equal(ob.p[0], traces[0].p[0])
+    assert st.iterations == len(traces[0].rows)
+
+
 def test_minimisers_and_iteration_counts(fl):
     n = 10_000
     for name in ("rosenR0", "rosenR1"):
@@ -289,6 +307,34 @@ def test_fortran_abi_device_callbacks_lbfgs(fl):
     L.nonlinearoptimization_mp_lbfgs_(f, fd, x2.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)), None, ffd, None,
                                       C.byref(C.c_int32(0)), None, None, None, None, None, None)
     assert np.array_equal(x2, x)
+
+
+def test_fortran_abi_steepest_descent(fl):
+    """__nonlinearoptimization_MOD_steepestdescent (hpp:279-291) with host callbacks staged by the library:
+    dim = 1, so the result must equal the oracle's bit for bit."""
+    x0, (f, g) = _cases.TORTURE_1D["quartic1"]
+    L = fl.lib()
+    for use in (False, True):
+        fa = _cases.Fuse(f, g)
+        cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
+        keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+        xa, s = O.sd(tuple(C.cast(k, C.c_void_p) for k in keep), np.array([x0]), use_ffd=use, Warning=False,
+                     MaxIteration=25)
+        fb = _cases.Fuse(f, g)
+        cf2, cfd2, cffd2 = _cases.make_ref_callbacks(fb.f, fb.g, fb.fg)
+        keep2 = (fl.capi.REF_F_FN(cf2), fl.capi.REF_FD_FN(cfd2), fl.capi.REF_F_FD_FN(cffd2))
+        x = np.array([x0])
+        L.flgpu_set_callback_space(fl.SPACE_HOST)
+        try:
+            L.__getattr__("__nonlinearoptimization_MOD_steepestdescent")(
+                keep2[0], keep2[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), keep2[2] if use else None,
+                None, C.byref(C.c_int32(0)), C.byref(C.c_int(25)), None, None, None, None, None)
+        finally:
+            L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+        st = fl.capi.Stats()
+        L.flgpu_last_stats(C.byref(st))
+        assert fa.xs == fb.xs, "different trial points"
+        assert np.array_equal(x, xa, equal_nan=True) and st.iterations == s.n_iter and st.status == s.status
 
 
 def test_cpp_dropin_program_runs(fl, tmp_path):

@@ -58,6 +58,22 @@ def test_cg_directions_within_oracle_envelope(method, name, kw):
     _check_envelope(traces, ob.p, f"cg {method} {name} {kw}")
 
 
+@pytest.mark.parametrize("name,kw", [("quartic", dict(MaxIteration=40)), ("rosenR1", dict(MaxIteration=40)),
+                                     ("diag", dict(MaxIteration=40, Strong=False)),
+                                     ("quartic", dict(MaxIteration=40, use_ffd=False))])
+def test_sd_directions_within_oracle_envelope(name, kw):
+    """SteepestDescent (f90:55-188) through the product's driver."""
+    n = 2000
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    kind = _cases.OBJECTIVES[name][0]
+    traces, env = _cases.oracle_envelope(name, n, lambda cbs, x, **k: O.sd(cbs, x, use_ffd=use, **k), **kw)
+    ob = H.Observer(max_vec_iters=20)
+    x, st = H.sd(kind, _cases.start(name, n), observer=ob, use_ffd=use, Warning=False, n_global=n, **kw)
+    _check_envelope(traces, ob.p, f"sd {name} {kw}")
+    assert np.array_equal(ob.p[0], traces[0].p[0])
+
+
 @pytest.mark.parametrize("name,mem", [("rosenR1", 10), ("rosenR1", 3), ("quartic", 10), ("diag", 30), ("rosenR0", 5),
                                       ("quartic", 1)])
 def test_one_step_direction_parity_1e12(name, mem):
@@ -89,6 +105,7 @@ def test_minimisers_and_iteration_counts():
     (True, "quartic", dict(Memory=5, Strong=False)), (True, "diag", dict(Memory=7, MaxIteration=60)),
     (False, "quartic", dict(Method="DY")), (False, "quartic", dict(Method="PR", use_ffd=False)),
     (False, "rosenR1", dict(Method="DY", Strong=False, MaxIteration=80)),
+    ("sd", "quartic", dict(MaxIteration=50)), ("sd", "rosenR1", dict(MaxIteration=50, Strong=False)),
 ])
 def test_fused_line_search_is_the_same_algorithm(lbfgs, name, kw):
     """flgpu_fused_fn changes where trial points live, not what is computed: with the host simulator
@@ -96,7 +113,7 @@ def test_fused_line_search_is_the_same_algorithm(lbfgs, name, kw):
     direction, step, iterate and evaluation count."""
     n = 3001
     kind = _cases.OBJECTIVES[name][0]
-    run = H.lbfgs if lbfgs else H.cg
+    run = H.sd if lbfgs == "sd" else (H.lbfgs if lbfgs else H.cg)
     out = []
     for fused in (True, False):
         ob = H.Observer(max_vec_iters=10**9)

@@ -85,6 +85,33 @@ def test_cg_c_equals_numpy_bitwise(method, name, n, kw):
     assert c.status == s.status
 
 
+SD_CASES = [
+    ("quartic", 10, dict(MaxIteration=60)),                        # test.f90:336-339 shape
+    ("quartic", 10, dict(use_ffd=True, MaxIteration=60)),          # test.f90:341-344
+    ("quartic", 10, dict(Strong=False, MaxIteration=60)),
+    ("quartic", 10, dict(Strong=False, use_ffd=True, MaxIteration=60)),   # Wolfe_fdwithf (never calls f_fd)
+    ("rosenR1", 100, dict(use_ffd=True, MaxIteration=80)),
+    ("diag", 150, dict(use_ffd=True, MaxIteration=80, WolfeConst2=0.4)),
+]
+
+
+@pytest.mark.parametrize("name,n,kw", SD_CASES)
+def test_sd_c_equals_numpy_bitwise(name, n, kw):
+    """SteepestDescent (f90:55-188): the two transcriptions agree bit for bit."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", False)
+    kind = _cases.OBJECTIVES[name][0]
+    x0 = _cases.start(name, n)
+    tr = O.Trace()
+    xa, s = O.sd(O.builtin_callbacks(kind, 0, n), x0.copy(), use_ffd=use, Warning=False, trace=tr, **kw)
+    f, fd, ffd = _np_objective(name, n)
+    with np.errstate(all="ignore"):
+        xb, c = N.steepest_descent(f, fd, x0.copy(), f_fd=ffd if use else None, Warning=False, **kw)
+    _same_history(c.history, tr)
+    assert np.array_equal(xa, xb)
+    assert c.status == s.status and c.trials == s.n_trials
+
+
 @pytest.mark.parametrize("case", sorted(_cases.TORTURE_1D))
 @pytest.mark.parametrize("method", ["DY", "PR"])
 def test_torture_1d_c_equals_numpy(case, method):
