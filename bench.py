@@ -163,6 +163,7 @@ def run_ours(args):
             dist.broadcast(t, 0)
             return bytes(t.cpu().numpy().tobytes())
         comm = fl.comm_create(rank, world, bcast)
+        fl.lib().flgpu_comm_uses_peer_memory.argtypes = [C.c_void_p]
 
     def barrier():
         torch.cuda.synchronize()
@@ -312,6 +313,9 @@ def run_ours(args):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload(n, mem), "n_global": n, "rows_per_gpu": n_local,
                            "parallelism": f"row-shard x{world}" if world > 1 else "1 GPU",
+                           "exchange": (None if comm is None else
+                                        ("one kernel over IPC-mapped peer memory (NVLink stores + flags), rank-ordered sum"
+                                         if fl.lib().flgpu_comm_uses_peer_memory(comm) else "ncclAllGather + combine kernel")),
                            "l2": "inputs (2 GiB/vector) exceed L2; no flush needed",
                            "line_search": LS_MODES[fused],
                            "trials_in_timed_region": trials, "trials_per_iteration": trials / K},

@@ -40,7 +40,7 @@ struct NcclApi {
     void *handle = nullptr;
     int (*GetUniqueId)(UniqueId *) = nullptr;
     int (*CommInitRank)(void **, int, UniqueId, int) = nullptr;
-    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;  // datatype: 0 int8, 8 f64
     int (*CommDestroy)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
@@ -73,6 +73,69 @@ void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t 
     nccl_check(nccl().AllGather(send, recv, count, /*ncclFloat64*/ 8, c->nccl_comm, s), "ncclAllGather");
 }
 
+// ---- peer-memory mailboxes: allocate, exchange CUDA IPC handles through NCCL, map every peer.
+// Any failure (IPC unavailable in this container, no peer access) leaves p2p = false on ALL ranks and the
+// exchange falls back to ncclAllGather + combine_kernel; FLGPU_EXCHANGE=nccl forces that.
+namespace {
+struct HandleMsg { cudaIpcMemHandle_t h; int ok; int pad; };
+void setup_p2p(flgpu_comm *c) {
+    const int G = c->nranks;
+    const char *mode = std::getenv("FLGPU_EXCHANGE");
+    int want = !(mode && !std::strcmp(mode, "nccl")) && G <= k::kMaxRanks;
+    HandleMsg mine;
+    std::memset(&mine, 0, sizeof mine);
+    if (want) {
+        if (cudaMalloc((void **)&c->local, sizeof(k::Mailbox)) == cudaSuccess &&
+            cudaMemset(c->local, 0, sizeof(k::Mailbox)) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.h, c->local) == cudaSuccess)
+            mine.ok = 1;
+        else
+            cudaGetLastError();
+    }
+    cudaStream_t s;
+    FLGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    char *dsend = nullptr, *drecv = nullptr;
+    FLGPU_CUDA_CHECK(cudaMalloc((void **)&dsend, sizeof(HandleMsg)));
+    FLGPU_CUDA_CHECK(cudaMalloc((void **)&drecv, sizeof(HandleMsg) * G));
+    std::vector<HandleMsg> all(G);
+    auto gather = [&]() {
+        FLGPU_CUDA_CHECK(cudaMemcpyAsync(dsend, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
+        nccl_check(nccl().AllGather(dsend, drecv, sizeof(HandleMsg), /*ncclInt8*/ 0, c->nccl_comm, s), "ncclAllGather");
+        FLGPU_CUDA_CHECK(cudaMemcpyAsync(all.data(), drecv, sizeof(HandleMsg) * G, cudaMemcpyDeviceToHost, s));
+        FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
+    };
+    gather();                                       // round 1: handles
+    int ok = 1;
+    for (int r = 0; r < G; r++) ok = ok && all[r].ok;
+    if (ok) {
+        for (int r = 0; r < G; r++) {
+            if (r == c->rank) { c->peers.box[r] = c->local; continue; }
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            c->peers.box[r] = (k::Mailbox *)ptr;
+        }
+    }
+    mine.ok = ok;
+    gather();                                       // round 2: did every rank map every peer?
+    int all_ok = 1;
+    for (int r = 0; r < G; r++) all_ok = all_ok && all[r].ok;
+    c->p2p = all_ok != 0;
+    if (!c->p2p && want && c->rank == 0)
+        std::fprintf(stderr, "flgpu: peer-memory exchange unavailable (CUDA IPC / peer access); using ncclAllGather\n");
+    if (!c->p2p) {
+        for (int r = 0; r < G; r++)
+            if (r != c->rank && c->peers.box[r]) { cudaIpcCloseMemHandle(c->peers.box[r]); c->peers.box[r] = nullptr; }
+    }
+    cudaFree(dsend);
+    cudaFree(drecv);
+    cudaStreamDestroy(s);
+}
+}  // namespace
+
 }  // namespace flgpu
 
 extern "C" int flgpu_comm_unique_id(void *id128) {
@@ -90,10 +153,17 @@ extern "C" flgpu_comm *flgpu_comm_create(const void *id128, int rank, int nranks
     flgpu::UniqueId id;
     std::memcpy(&id, id128, 128);
     flgpu::nccl_check(flgpu::nccl().CommInitRank(&c->nccl_comm, nranks, id, rank), "ncclCommInitRank");
+    flgpu::setup_p2p(c);
     return c;
 }
+extern "C" int flgpu_comm_uses_peer_memory(const flgpu_comm *c) { return c && c->p2p ? 1 : 0; }
 extern "C" void flgpu_comm_destroy(flgpu_comm *c) {
     if (!c) return;
+    cudaDeviceSynchronize();
+    if (c->p2p)
+        for (int r = 0; r < c->nranks; r++)
+            if (r != c->rank && c->peers.box[r]) cudaIpcCloseMemHandle(c->peers.box[r]);
+    if (c->local) cudaFree(c->local);
     if (c->nccl_comm) flgpu::nccl().CommDestroy(c->nccl_comm);
     delete c;
 }
@@ -140,6 +210,7 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
     R = (double *)dalloc(nres * sizeof(double));
     Rall = (double *)dalloc(nres * sizeof(double) * G);
     Rglob = (double *)dalloc(NSLOTS * sizeof(double));
+    Dsum = (double *)dalloc(nd_of(k::kMaxMem) * sizeof(double));
     work.partials = (double *)dalloc((size_t)k::kMaxGrid * nd_of(k::kMaxMem) * sizeof(double));
     work.ticket = (unsigned int *)dalloc(64);
     FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, NSLOTS * sizeof(double)));
@@ -337,8 +408,8 @@ void CudaBackend::lbfgs_solve(int kk, int recent) {
     const int G = ctx.nranks;
     const double *Dall = R + NSLOTS;
     if (G > 1) {
-        nccl_allgather_f64(comm, R + NSLOTS, Rall, (size_t)nd, stream);
-        Dall = Rall;
+        exchange(R + NSLOTS, nd, Dsum);
+        Dall = Dsum;
     }
     const int t = time_begin("k2_solve", 0.0);
     const size_t smem = (size_t)(nd + 2 * mem * mem) * sizeof(double);
@@ -349,7 +420,7 @@ void CudaBackend::lbfgs_solve(int kk, int recent) {
             attr_set = true;
         }
     }
-    k::k2_solve_kernel<<<1, 32, smem, stream>>>(mem, kk, recent, Dall, G, SY, YY, C);
+    k::k2_solve_kernel<<<1, 32, smem, stream>>>(mem, kk, recent, Dall, 1, SY, YY, C);
     time_end(t);
     launches++;
 }
@@ -379,13 +450,25 @@ void CudaBackend::cg_update(double *p, const double *g1, double beta) {
     launches++;
 }
 
+// ---- ranks: out[i] = sum_r src_r[i] in rank order, identical bits on every rank
+void CudaBackend::exchange(const double *src, int count, double *out) {
+    const int t = time_begin("c1_exchange", 0.0);
+    if (comm->p2p) {
+        k::exchange_kernel<<<1, k::kMailWidth, 0, stream>>>(comm->peers, comm->rank, comm->nranks, ++comm->seq, src,
+                                                           count, out);
+    } else {
+        nccl_allgather_f64(comm, src, Rall, (size_t)count, stream);
+        k::combine_kernel<<<1, k::kMailWidth, 0, stream>>>(Rall, ctx.nranks, count, out);
+    }
+    time_end(t);
+    launches++;
+}
+
 // ---- host <- device: one 128-byte copy and one stream synchronisation
 void CudaBackend::fetch(double *host_slots) {
     const double *src = R;
     if (ctx.nranks > 1) {
-        nccl_allgather_f64(comm, R, Rall, (size_t)NSLOTS, stream);
-        k::combine_kernel<<<1, 32, 0, stream>>>(Rall, ctx.nranks, NSLOTS, Rglob);
-        launches++;
+        exchange(R, NSLOTS, Rglob);
         src = Rglob;
     }
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned, src, NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream));

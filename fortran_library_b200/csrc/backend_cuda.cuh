@@ -16,8 +16,13 @@
     } while (0)
 
 struct flgpu_comm {
-    void *nccl_comm = nullptr;  // ncclComm_t
+    void *nccl_comm = nullptr;  // ncclComm_t (plumbing: rendezvous, IPC-handle exchange, fallback all-gather)
     int rank = 0, nranks = 1;
+    // peer-memory exchange (kernels.cuh C1): this rank's mailbox and the IPC-mapped mailboxes of its peers
+    bool p2p = false;
+    flgpu::k::Mailbox *local = nullptr;
+    flgpu::k::PeerTable peers{};
+    unsigned long long seq = 0;
 };
 
 namespace flgpu {
@@ -82,7 +87,9 @@ private:
     int device = 0, num_sms = 148;
     std::vector<void *> owned;
     k::Work work{};
-    double *Rall = nullptr;       // [G][NSLOTS + nd] all-gathered results
+    double *Rall = nullptr;       // [G][NSLOTS + nd] all-gathered results (NCCL fallback only)
+    double *Dsum = nullptr;       // [nd] rank-ordered sum of the K1 dots
+    void exchange(const double *src, int count, double *out);   // out = sum over ranks, in rank order
     double *Rglob = nullptr;      // [NSLOTS] combined slots
     double *host_pinned = nullptr;
     bool timing = false;

@@ -587,6 +587,71 @@ static __global__ void __launch_bounds__(kThreads, 2) k3_direction_kernel(K3Args
     reduce_finish<2>(acc, d, a.w, a.R);
 }
 
+// ------------------------------------------------------------------ C1: rank exchange over peer memory
+// Row-sharded runs combine each reduction's per-rank partial sums.  Instead of a library all-gather
+// followed by a combine kernel, ONE single-block kernel per exchange does both over NVLink/NVSwitch
+// peer memory: every rank stores its `count` partials straight into slot [me] of every peer's mailbox
+// (plain st.global on IPC-mapped peer pointers), publishes a sequence number, waits until the G slots of
+// its OWN mailbox carry this sequence number, and sums them in rank order -- identical bits on all ranks.
+// Mailboxes are double-buffered on the sequence parity: a peer can be at most one exchange ahead (it
+// needs this rank's flag of exchange seq+1 before it can start seq+2), so two buffers suffice.
+constexpr int kMailWidth = 320;       // doubles per rank slot: >= NSLOTS + nd_of(kMaxMem)
+constexpr int kMaxRanks = 16;
+
+struct Mailbox {
+    double data[2][kMaxRanks][kMailWidth];
+    unsigned long long flag[2][kMaxRanks];
+    unsigned long long error;         // set to the offending sequence number on a wait timeout
+};
+
+struct PeerTable { Mailbox *box[kMaxRanks]; };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth).
+static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable peers, int me, int G,
+                                                                       unsigned long long seq, const double *src,
+                                                                       int count, double *out) {
+    const int par = (int)(seq & 1ull);
+    const int t = threadIdx.x;
+    if (t < count) {
+        const double v = src[t];
+        for (int r = 0; r < G; r++) peers.box[r]->data[par][me][t] = v;      // r == me: the local slot
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < G) st_release_sys(&peers.box[t]->flag[par][me], seq);
+    Mailbox *mine = peers.box[me];
+    if (t < G) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(&mine->flag[par][t]) < seq) {
+            if (global_timer_ns() - t0 > 20000000000ull) {                  // 20 s: a peer died; fail loudly
+                mine->error = seq;
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+    if (t < count) {
+        double s = __ldcv(&mine->data[par][0][t]);
+        for (int r = 1; r < G; r++) s += __ldcv(&mine->data[par][r][t]);
+        out[t] = s;
+    }
+}
+
 // ------------------------------------------------------------------ multi-rank combine of the slots
 static __global__ void combine_kernel(const double *all, int G, int count, double *out) {
     const int i = threadIdx.x;

@@ -171,6 +171,9 @@ int flgpu_steepest_descent(const flgpu_problem *prob, const flgpu_options *opt, 
 int flgpu_comm_unique_id(void *id128);
 flgpu_comm *flgpu_comm_create(const void *id128, int rank, int nranks);
 void flgpu_comm_destroy(flgpu_comm *c);
+/* 1 when the per-reduction exchange runs as one kernel over IPC-mapped peer memory (NVLink/NVSwitch
+ * stores + flags), 0 when it fell back to ncclAllGather (FLGPU_EXCHANGE=nccl forces the fallback). */
+int flgpu_comm_uses_peer_memory(const flgpu_comm *c);
 
 /* ------------------------------------------------------------------ Fortran ABI (drop-in symbols) */
 /* Where x and the callbacks' vectors live for the entry points below.  Defaults:

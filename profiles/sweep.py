@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""profiles/sweep.py -- BASELINE.json configs[2] and [4] on the GPUs visible to this process (1 GPU, or N under
+torchrun): n = 2^26..2^28 (per-GPU rows under torchrun: weak scaling) x {LBFGS m=5,10,30 on Rosenbrock /
+diag-quadratic, CG-DY and CG-PR on the quartic, SteepestDescent}, K timed iterations each after the warm-up
+iterations, per-kernel CUDA-event totals -> achieved GB/s over the algorithmic bytes.
+
+    python profiles/sweep.py [--out gpurun_out/sweep.md] [--max-log2n 28]
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import fortran_library_b200 as fl  # noqa: E402
+
+PEAK = 6467.7
+
+
+def one(algo, kind, start, seed, n, K, W, **kw):
+    x = fl.DeviceVector.start(start, n, seed=seed)
+    mem = kw.get("Memory", 0)
+    first = (mem if algo == "lbfgs" else 1) + W - 1
+    last = first + K
+    mark = {}
+
+    def on_iter(i):
+        if i.iteration == first:
+            fl.lib().flgpu_reset_kernel_times()
+            mark["t0"], mark["tr0"] = time.perf_counter(), i.total_trials
+        elif i.iteration == last:
+            fl.lib().flgpu_memcpy(None, None, 0, 1, 1, i.stream)       # drain the stream
+            mark["t1"], mark["tr1"] = time.perf_counter(), i.total_trials
+            return True
+        return False
+    ob = fl.Observer(on_iteration=on_iter)
+    run = {"lbfgs": fl.LBFGS, "cg": fl.ConjugateGradient, "sd": fl.SteepestDescent}[algo]
+    st = run(fl.builtin_problem(kind), x, observer=ob, Warning=False, MaxIteration=W + K + 1, time_kernels=True, **kw)
+    x.free()
+    if "t1" not in mark:
+        return None
+    kt = fl.kernel_times()
+    ms = sum(v["ms"] for v in kt.values())
+    gb = sum(v["bytes"] for v in kt.values()) / 1e9
+    wall = mark["t1"] - mark["t0"]
+    return {"it_per_s": K / wall, "trials_per_it": (mark["tr1"] - mark["tr0"]) / K, "kernel_ms_per_it": ms / K,
+            "GBps": gb / (ms * 1e-3), "frac": gb / (ms * 1e-3) / PEAK, "GB_per_it": gb / K}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep.md"))
+    ap.add_argument("--min-log2n", type=int, default=26)
+    ap.add_argument("--max-log2n", type=int, default=28)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    a = ap.parse_args()
+    fl.require_gpu()
+    rows = []
+    cases = [("LBFGS m=5 Rosenbrock", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=5)),
+             ("LBFGS m=10 Rosenbrock", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10)),
+             ("LBFGS m=10 Rosenbrock, plain callbacks", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10, fused=False)),
+             ("LBFGS m=30 diag-quadratic", "lbfgs", fl.OBJ_DIAGQUAD, fl.START_ZERO, 0, dict(Memory=30)),
+             ("CG DY quartic", "cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY")),
+             ("CG PR quartic", "cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="PR")),
+             ("CG DY quartic, plain callbacks", "cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY", fused=False)),
+             ("SteepestDescent Rosenbrock", "sd", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict())]
+    for log2n in range(a.min_log2n, a.max_log2n + 1):
+        n = 1 << log2n
+        for label, algo, kind, start, seed, kw in cases:
+            mem = kw.get("Memory", 0)
+            if (2 * mem + 6) * 8 * n > 170e9:
+                continue
+            r = one(algo, kind, start, seed, n, a.steps, a.warmup, **kw)
+            if r is None:
+                print(f"2^{log2n} {label}: converged before the timed window", flush=True)
+                continue
+            rows.append((log2n, label, r))
+            print(f"2^{log2n} {label:42s} {r['it_per_s']:8.2f} it/s  {r['trials_per_it']:5.1f} trials/it  "
+                  f"{r['GB_per_it']:7.1f} GB/it  {r['GBps']:7.0f} GB/s ({r['frac']:.0%} of measured)", flush=True)
+    with open(a.out, "w") as fh:
+        fh.write("| n | workload | it/s (wall) | trials/it | algorithmic GB/it | kernel ms/it | achieved GB/s | of measured 6467.7 |\n")
+        fh.write("|---|---|---:|---:|---:|---:|---:|---:|\n")
+        for log2n, label, r in rows:
+            fh.write(f"| 2^{log2n} | {label} | {r['it_per_s']:.2f} | {r['trials_per_it']:.1f} | {r['GB_per_it']:.1f} | "
+                     f"{r['kernel_ms_per_it']:.2f} | {r['GBps']:.0f} | {r['frac']:.1%} |\n")
+
+
+if __name__ == "__main__":
+    main()

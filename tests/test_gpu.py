@@ -221,20 +221,18 @@ def test_sd_trajectory_within_oracle_envelope(fl, name, kw, fused):
 
 
 def test_minimisers_and_iteration_counts(fl):
+    """north_star: minimisers to 1e-8 relative; iteration counts within 2 % of the oracle's own range under
+    one-ULP perturbations (_cases.oracle_iteration_range explains why a single count is not a target)."""
     n = 10_000
     for name in ("rosenR0", "rosenR1"):
-        kind = _cases.OBJECTIVES[name][0]
-        x0 = _cases.start(name, n)
-        runs = [O.lbfgs(O.builtin_callbacks(kind, 0, n), x0.copy(), use_ffd=True, Warning=False, sum_mode=m)
-                for m in (0, 1, 2)]
-        its = [r[1].n_iter for r in runs]
-        spread = (max(its) - min(its)) / min(its)
+        counts, statuses, x_ref = _cases.oracle_iteration_range(
+            name, n, lambda cbs, x, **k: O.lbfgs(cbs, x, use_ffd=True, **k))
         for fused in (True, False):
             x = _dev_start(fl, name, n)
             st = fl.LBFGS(_problem(fl, name), x, Warning=False, fused=fused)
-            assert _cases.rel(x.numpy(), runs[0][0]) < 1e-8          # minimiser, relative 1e-8
-            assert abs(st.iterations - its[0]) / its[0] <= max(0.02, 1.5 * spread)
-            assert st.status == runs[0][1].status
+            assert _cases.rel(x.numpy(), x_ref) < 1e-8              # minimiser, relative 1e-8
+            _cases.check_iteration_count(st.iterations, counts, f"lbfgs {name} fused={fused}")
+            assert st.status in statuses
     # CG on the quartic (config 3): x* = 0, scale by |x0| (SURVEY.md 7 "x*=0 objectives")
     x0 = _cases.start("quartic", n)
     for M in ("DY", "PR"):
