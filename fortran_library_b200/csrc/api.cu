@@ -16,6 +16,7 @@ using namespace flgpu;
 
 namespace flgpu {
 flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f);   // objectives.cu
+extern int g_k1_shape[2];                             // backend_cuda.cu
 }
 
 namespace {
@@ -239,6 +240,11 @@ void flgpu_register_fused(flgpu_ref_f_fn f, flgpu_fused_fn fused, void *user) {
     std::lock_guard<std::mutex> lock(g_fused_mu);
     if (fused) g_fused[f] = FusedEntry{fused, user};
     else g_fused.erase(f);
+}
+
+void flgpu_debug_set_k1_shape(int columns_per_group, int groups) {
+    flgpu::g_k1_shape[0] = columns_per_group;
+    flgpu::g_k1_shape[1] = groups;
 }
 
 void flgpu_reset_kernel_times(void) {

@@ -365,10 +365,23 @@ void CudaBackend::neg(double *p, const double *g) {
 }
 
 // ---- L-BFGS
+int g_k1_shape[2] = {0, 0};
 namespace {
+// grid = SMs x CTAs actually resident for this instantiation (one full wave), capped by the work
 template <int MT, int NG>
-void launch_k1(const k::K1Args &a, int grid, cudaStream_t s) {
-    k::k1_update_dots_kernel<MT, NG><<<grid, k::kThreads, 0, s>>>(a);
+void launch_k1(const k::K1Args &a, int num_sms, int64_t units, cudaStream_t s) {
+    static int resident = 0;
+    if (!resident) {
+        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::k1_update_dots_kernel<MT, NG>,
+                                                                       k::kThreads, 0));
+        if (resident < 1) resident = 1;
+    }
+    constexpr int TX = k::kThreads / NG;
+    int64_t need = (units + TX - 1) / TX;
+    int64_t grid = (int64_t)num_sms * resident;
+    if (grid > k::kMaxGrid) grid = k::kMaxGrid;
+    if (need < grid) grid = need < 1 ? 1 : need;
+    k::k1_update_dots_kernel<MT, NG><<<(int)grid, k::kThreads, 0, s>>>(a);
 }
 }  // namespace
 
@@ -381,23 +394,27 @@ void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const do
     a.m = mem; a.new_slot = new_slot; a.k_after = k_after; a.w = work; a.R = R;
     int age = 1;
     bool first = true;
-    // one pass covers NG*MT older columns; more than 64 older columns never occurs (kMaxMem)
+    // one pass covers NG*MT older columns
     do {
         a.age_base = age;
         a.write_new = first ? 1 : 0;
         const int rem = nother - (age - 1);
-        int cover;
-        if (rem <= 2)       { cover = 2;  launch_k1<2, 1>(a, grid_for(n / 2 + 1, 256, 2), stream); }
-        else if (rem <= 4)  { cover = 4;  launch_k1<4, 1>(a, grid_for(n / 2 + 1, 256, 2), stream); }
-        else if (rem <= 5)  { cover = 5;  launch_k1<5, 1>(a, grid_for(n / 2 + 1, 256, 2), stream); }
-        else if (rem <= 8)  { cover = 8;  launch_k1<4, 2>(a, grid_for(n / 2 + 1, 128, 2), stream); }
-        else if (rem <= 10) { cover = 10; launch_k1<5, 2>(a, grid_for(n / 2 + 1, 128, 2), stream); }
-        else if (rem <= 16) { cover = 16; launch_k1<4, 4>(a, grid_for(n / 2 + 1, 64, 2), stream); }
-        else if (rem <= 20) { cover = 20; launch_k1<5, 4>(a, grid_for(n / 2 + 1, 64, 2), stream); }
-        else if (rem <= 32) { cover = 32; launch_k1<8, 4>(a, grid_for(n / 2 + 1, 64, 2), stream); }
-        else                { cover = 64; launch_k1<8, 8>(a, grid_for(n / 2 + 1, 32, 2), stream); }
+        int mt, ng;
+        if (g_k1_shape[0] > 0) { mt = g_k1_shape[0]; ng = g_k1_shape[1]; }   // tuning override (flgpu_debug_set_k1_shape)
+        else if (rem <= 2)  { mt = 2; ng = 1; }
+        else if (rem <= 4)  { mt = 4; ng = 1; }
+        else if (rem <= 5)  { mt = 5; ng = 1; }
+        else if (rem <= 8)  { mt = 4; ng = 2; }
+        else                { mt = 5; ng = 2; }   // 10 columns per pass; m = 30 takes 3 passes
+        // Measured on B200 (profiles/r01_k1_shapes.md): shapes with 4 or 8 groups per warp (128 / 64-byte
+        // column runs) or more than 5 columns per thread (> 128 registers, 1 CTA/SM) run at 2.6-5.6 TB/s;
+        // <5,2> (256-byte runs, 2 CTAs/SM) sustains 6.3-7.0 TB/s even counting the re-read of x, g per pass.
+#define FLGPU_K1_CASE(MT, NG) if (mt == MT && ng == NG) launch_k1<MT, NG>(a, num_sms, n / 2 + 1, stream); else
+        FLGPU_K1_CASE(2, 1) FLGPU_K1_CASE(4, 1) FLGPU_K1_CASE(5, 1) FLGPU_K1_CASE(4, 2) FLGPU_K1_CASE(5, 2)
+        fatal("K1: unsupported (columns per group, groups) shape");
+#undef FLGPU_K1_CASE
         launches++;
-        age += cover;
+        age += mt * ng;
         first = false;
     } while (age - 1 < nother);
     time_end(t);

@@ -82,12 +82,15 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
         for (int i = threadIdx.x; i < 768; i += kThreads) tab[i] = a.tables[i];
         __syncthreads();
     }
-    auto coeff = [&](int64_t i) -> double {
+    // d_i = 10^(6 q / 2^24), q = trunc(i * scale) <= 2^24 (oracle/objectives.c orc_diag_coeff); the index arrives
+    // as a double (exact below 2^53) and the truncation is a 32-bit conversion: same bits, no 64-bit I2F/F2I
+    auto coeff = [&](double i) -> double {
         if (a.n_global <= 1) return 1.0;
-        const unsigned long long q = (unsigned long long)mul((double)i, a.scale);
+        const unsigned int q = __double2uint_rz(mul(i, a.scale));
         if (q >> 24) return 1.0e6;
         return mul(mul(tab[512 + ((q >> 16) & 255)], tab[256 + ((q >> 8) & 255)]), tab[q & 255]);
     };
+    const double offset_d = (double)a.offset;
     constexpr bool NEED_G = WANT_GP || WRITE_G;
     double fsum = 0.0, gpsum = 0.0;
     const double step = a.a;
@@ -113,8 +116,8 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
                 g.y = mul(200.0, t1);
             }
         } else {
-            const int64_t i = a.offset + 2 * u;
-            const double d0 = coeff(i), d1 = coeff(i + 1);
+            const double i = offset_d + (double)(2 * u);   // exact: both terms and the sum are integers < 2^53
+            const double d0 = coeff(i), d1 = coeff(i + 1.0);
             const double t0 = sub(x.x, 1.0), t1 = sub(x.y, 1.0);
             if (WANT_F) { fsum += mul(mul(mul(0.5, d0), t0), t0); fsum += mul(mul(mul(0.5, d1), t1), t1); }
             if (NEED_G) { g.x = mul(d0, t0); g.y = mul(d1, t1); }
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
             if (WANT_F) fsum += mul(t2, t2);
             g = mul(-2.0, t2);
         } else {
-            const double d = coeff(a.offset + i), t = sub(x, 1.0);
+            const double d = coeff((double)(a.offset + i)), t = sub(x, 1.0);
             if (WANT_F) fsum += mul(mul(mul(0.5, d), t), t);
             g = mul(d, t);
         }

@@ -284,6 +284,8 @@ const char *flgpu_version(void);
 /* Per-kernel accumulated CUDA-event time of the last call run with time_kernels=1.
  * names/ms/launches/bytes: arrays of capacity cap; returns the number of kernels. */
 int flgpu_kernel_times(const char **names, double *ms, int64_t *launches, double *bytes, int cap);
+/* Tuning aid: force K1's (columns per group, groups) shape; (0,0) restores the built-in table. */
+void flgpu_debug_set_k1_shape(int columns_per_group, int groups);
 /* From inside an observer: zero the accumulators of the call in progress (to time a window). */
 void flgpu_reset_kernel_times(void);
 

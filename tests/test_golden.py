@@ -13,7 +13,9 @@ import _oracle as O
 
 # cases whose stored run ends in a long chaotic tail (MaxIteration hit mid-descent / hundreds of
 # 1e-15-sized steps): only the early iterations and the exit status are compared
-TAIL_UNSTABLE = {"lbfgs_diag_60_m30", "lbfgs_rosenR1_64_m5", "cg_dy_quartic10_weak", "sd_rosenR1_64"}
+TAIL_UNSTABLE = {"lbfgs_diag_60_m30", "lbfgs_rosenR1_64_m5", "cg_dy_quartic10_weak", "sd_rosenR1_64",
+                 # steepest descent zig-zags into x* = 0: the last iterates (|x| ~ 1e-6) flip sign under rounding noise
+                 "sd_quartic10", "sd_quartic10_ffd"}
 
 
 def _check_against_golden(d, x, iterations, status, rows, name):
