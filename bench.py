@@ -34,7 +34,10 @@ METRIC = "lbfgs_iterations_per_sec"
 UNIT = "it/s"
 
 
-def workload(n, mem):
+def workload(n, mem, objective="rosenbrock"):
+    if objective == "diag":
+        return (f"LBFGS m={mem} diagonal-scaled quadratic (condition 1e6) n=2^{n.bit_length() - 1} fp64, start x=0, "
+                f"f_fd present, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
     return (f"LBFGS m={mem} extended Rosenbrock n=2^{n.bit_length() - 1} fp64, start R1 = (-1.2,1)+0.1(u-0.5) "
             f"seed {SEED}, f_fd present, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
 
@@ -175,11 +178,13 @@ def run_ours(args):
     lo = (n * rank // world) // 2 * 2            # even boundaries: Rosenbrock pairs never straddle shards
     hi = n if rank == world - 1 else (n * (rank + 1) // world) // 2 * 2
     n_local = hi - lo
-    prob = fl.builtin_problem(fl.OBJ_ROSENBROCK)
+    diag = args.objective == "diag"
+    OBJ, START = (fl.OBJ_DIAGQUAD, fl.START_ZERO) if diag else (fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT)
+    prob = fl.builtin_problem(OBJ)
     first, last = mem + W - 1, mem + W + K - 1   # observer indices bracketing exactly K main-loop iterations
 
     def timed_run(time_kernels, fused=True):
-        x = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_local, seed=SEED, offset=lo, n_global=n)
+        x = fl.DeviceVector.start(START, n_local, seed=SEED, offset=lo, n_global=n)
         ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         mark = {}
 
@@ -267,7 +272,7 @@ def run_ours(args):
     # ---- e2e: the reference-facing call with HOST buffers (pinned), H2D/D2H and work-space allocation inside
     Ke = args.e2e_steps
     xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
-    x0 = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_local, seed=SEED, offset=lo, n_global=n)
+    x0 = fl.DeviceVector.start(START, n_local, seed=SEED, offset=lo, n_global=n)
     fl.lib().flgpu_memcpy(xh.data_ptr(), x0.ptr, n_local * 8, fl.SPACE_HOST, fl.SPACE_DEVICE, None)
     x0.free()
     barrier()
@@ -279,7 +284,7 @@ def run_ours(args):
             os.environ["FLGPU_NO_FUSED"] = "1"
         L = fl.lib()
         f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
-        L.flgpu_builtin_ref_callbacks(fl.OBJ_ROSENBROCK, C.byref(f), C.byref(fd), C.byref(ffd))
+        L.flgpu_builtin_ref_callbacks(OBJ, C.byref(f), C.byref(fd), C.byref(ffd))
         L.__getattr__("__nonlinearoptimization_MOD_lbfgs")(
             f, fd, C.c_void_p(xh.data_ptr()), C.byref(C.c_int(n_local)), C.byref(C.c_int(mem)), ffd, None,
             C.byref(C.c_int32(0)), C.byref(C.c_int(Ke)), None, None, None, None, None)
@@ -304,14 +309,14 @@ def run_ours(args):
                    f"{Ke} main iterations, D2H of x; bytes/step = 8n/iterations (x crosses PCIe once per call)"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not diag:
         cpu = cpu_lbfgs(1 << min(args.log2n, args.cpu_log2n), mem, min(W, 3), min(K, 10), n)
 
     if rank == 0:
         line = {"metric": METRIC, "value": K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload(n, mem), "n_global": n, "rows_per_gpu": n_local,
+                "config": {"workload": workload(n, mem, args.objective), "n_global": n, "rows_per_gpu": n_local,
                            "parallelism": f"row-shard x{world}" if world > 1 else "1 GPU",
                            "exchange": (None if comm is None else
                                         ("one kernel over IPC-mapped peer memory (NVLink stores + flags), rank-ordered sum"
@@ -337,6 +342,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="override the global dimension (debugging only)")
     ap.add_argument("--mem", type=int, default=MEM)
+    ap.add_argument("--objective", default="rosenbrock", choices=["rosenbrock", "diag"],
+                    help="diag = BASELINE.json configs[3] (with --mem 30 --log2n 31 --gpus 8); not the headline")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--plain", action="store_true", help="headline with opaque callbacks (no fused line-search evaluation)")
     ap.add_argument("--cpu-log2n", type=int, default=21, help="size of the bounded CPU sample")

@@ -388,6 +388,7 @@ void launch_k1(const k::K1Args &a, int num_sms, int64_t units, cudaStream_t s) {
 void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const double *g1,
                                     const double *g0, int new_slot, int k_after) {
     const int nother = k_after - 1;
+    // algorithmic bytes: one ideal pass (the g1, g0 re-reads of extra passes at m > 11 are overhead, not credit)
     const int t = time_begin("k1_update_dots", 8.0 * n * (2.0 * nother + 6.0));
     k::K1Args a;
     a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.S = S; a.Y = Y; a.ld = ld; a.n = n;

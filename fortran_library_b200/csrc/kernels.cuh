@@ -293,7 +293,9 @@ static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args 
     const int64_t nu = a.n >> 1;
     const int64_t stride = (int64_t)gridDim.x * TX;
     for (int64_t u = (int64_t)blockIdx.x * TX + tx; u < nu; u += stride) {
-        const double2 x1 = ld2(a.x1, u), x0 = ld2(a.x0, u), g1 = ld2(a.g1, u), g0 = ld2(a.g0, u);
+        const double2 g1 = ld2(a.g1, u), g0 = ld2(a.g0, u);
+        double2 x1 = make_double2(0.0, 0.0), x0 = x1;
+        if (a.write_new) { x1 = ld2(a.x1, u); x0 = ld2(a.x0, u); }   // later passes need only y_new = g1 - g0
         double2 s[MT], y[MT];
 #pragma unroll
         for (int c = 0; c < MT; c++)

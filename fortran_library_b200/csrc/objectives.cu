@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
         for (int i = threadIdx.x; i < 768; i += kThreads) tab[i] = a.tables[i];
         __syncthreads();
     }
-    // d_i = 10^(6 q / 2^24), q = trunc(i * scale) <= 2^24 (oracle/objectives.c orc_diag_coeff); the index arrives
+    // d_i = 10^(6 q / 2^24), q = trunc(i * scale) <= 2^24 (diagonal quadratic); the index arrives
     // as a double (exact below 2^53) and the truncation is a 32-bit conversion: same bits, no 64-bit I2F/F2I
     auto coeff = [&](double i) -> double {
         if (a.n_global <= 1) return 1.0;
