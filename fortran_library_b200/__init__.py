@@ -282,6 +282,15 @@ class History:
             self.h = None
 
 
+def set_workspace_cache(on):
+    """Keep the device work space of finished calls for the next call (flgpu_set_workspace_cache)."""
+    lib().flgpu_set_workspace_cache(int(bool(on)))
+
+
+def release_workspace():
+    lib().flgpu_release_workspace()
+
+
 def kernel_times():
     """Per-kernel CUDA-event totals of the last call made with time_kernels=True."""
     cap = 64

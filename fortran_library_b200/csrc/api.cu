@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -57,28 +58,50 @@ int cb_space_now() {
 
 enum Algo { ALGO_LBFGS = 0, ALGO_CG = 1, ALGO_SD = 2 };
 
+double wall_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int run(int algo, const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n, int x_space,
         flgpu_stats *stats) {
     require_device();
     if (!prob || !prob->f || !prob->fd) fatal("flgpu: f and fd callbacks are required (f90:40)");
     if (n < 0) fatal("flgpu: negative dimension");
-    CudaBackend B(*prob, n, *opt);
-    Params P = params_from_options(*opt, algo == ALGO_CG, prob->f_fd != nullptr);
-    ThreadState saved = tls;
-    tls.stream = B.stream_handle();
-    tls.backend = &B;
-    FLGPU_CUDA_CHECK(cudaGetDevice(&tls.device));
+    const char *tr = std::getenv("FLGPU_TRACE_PHASES");   // wall-clock phases of one call, to stderr
+    const bool trace = tr && tr[0] && tr[0] != '0';
+    const double t0 = wall_ms();
+    double t1, t2;
     flgpu_stats st;
-    if (algo == ALGO_CG) run_cg(B, P, x, x_space, &st);
-    else if (algo == ALGO_SD) run_sd(B, P, x, x_space, &st);
-    else run_lbfgs(B, P, x, x_space, &st);
-    B.resolve_times();
+    ThreadState saved = tls;
+    {
+        CudaBackend B(*prob, n, *opt);
+        Params P = params_from_options(*opt, algo == ALGO_CG, prob->f_fd != nullptr);
+        tls.stream = B.stream_handle();
+        tls.backend = &B;
+        FLGPU_CUDA_CHECK(cudaGetDevice(&tls.device));
+        t1 = wall_ms();
+        if (algo == ALGO_CG) run_cg(B, P, x, x_space, &st);
+        else if (algo == ALGO_SD) run_sd(B, P, x, x_space, &st);
+        else run_lbfgs(B, P, x, x_space, &st);
+        B.resolve_times();
+        tls.times = B.times;
+        t2 = wall_ms();
+        if (trace)
+            std::fprintf(stderr, "flgpu phases: cudaMalloc %.1f ms, x upload %.1f ms, x download %.1f ms\n", B.alloc_ms,
+                         B.upload_ms, B.download_ms);
+    }   // work space released here (~CudaBackend)
+    const double t3 = wall_ms();
     tls.stream = saved.stream;
     tls.device = saved.device;
     tls.backend = saved.backend;
     tls.last = st;
-    tls.times = B.times;
     if (stats) *stats = st;
+    if (trace)
+        std::fprintf(stderr, "flgpu phases: setup %.1f ms, optimise (incl. work-space allocation, x transfers) %.1f ms, "
+                             "release %.1f ms; %lld iterations, %lld trials\n",
+                     t1 - t0, t2 - t1, t3 - t2, (long long)st.iterations, (long long)st.n_trials);
     return 0;
 }
 
@@ -241,6 +264,9 @@ void flgpu_register_fused(flgpu_ref_f_fn f, flgpu_fused_fn fused, void *user) {
     if (fused) g_fused[f] = FusedEntry{fused, user};
     else g_fused.erase(f);
 }
+
+void flgpu_set_workspace_cache(int on) { flgpu::ws_set_enabled(on != 0); }
+void flgpu_release_workspace(void) { flgpu::ws_release(); }
 
 void flgpu_debug_set_k1_shape(int columns_per_group, int groups) {
     flgpu::g_k1_shape[0] = columns_per_group;

@@ -6,8 +6,74 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <map>
+#include <mutex>
 
 namespace flgpu {
+
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// ---- work-space cache (opt-in): device buffers of a finished call are kept for the next call on the same
+// device instead of going back to the driver (cudaFree of a 50 GiB work space costs 0.25-0.55 s on B200:
+// profiles/r01_e2e_phases.md).  Off by default: like the reference, nothing then persists between calls.
+namespace {
+struct WsCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_;
+    bool enabled = false, env_read = false;
+} g_ws;
+bool ws_enabled() {
+    if (!g_ws.env_read) {
+        const char *v = std::getenv("FLGPU_WORKSPACE_CACHE");
+        if (v && v[0] && v[0] != '0') g_ws.enabled = true;
+        g_ws.env_read = true;
+    }
+    return g_ws.enabled;
+}
+}  // namespace
+void *ws_alloc(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_ws.mu);
+        auto it = g_ws.free_.find(std::make_pair(dev, bytes));
+        if (it != g_ws.free_.end()) { void *p = it->second; g_ws.free_.erase(it); return p; }
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {            // out of memory with buffers parked in the cache: release them and retry
+        cudaGetLastError();
+        ws_release();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) cuda_fail("cudaMalloc (work space)", e, __FILE__, __LINE__);
+    return p;
+}
+void ws_free(void *p, size_t bytes) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    if (ws_enabled()) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        g_ws.free_.emplace(std::make_pair(dev, bytes), p);
+    } else {
+        cudaFree(p);
+    }
+}
+void ws_release() {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    for (auto &kv : g_ws.free_) cudaFree(kv.second);
+    g_ws.free_.clear();
+}
+void ws_set_enabled(bool on) {
+    { std::lock_guard<std::mutex> lock(g_ws.mu); g_ws.enabled = on; g_ws.env_read = true; }
+    if (!on) ws_release();
+}
 
 void cuda_fail(const char *what, cudaError_t e, const char *file, int line) {
     std::fprintf(stderr, "flgpu: CUDA failure %s (%s) at %s:%d -- no CPU fallback exists, aborting\n",
@@ -201,10 +267,9 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
     const int G = ctx.nranks;
     const size_t nres = NSLOTS + nd_of(k::kMaxMem);
     auto dalloc = [&](size_t bytes) {
-        void *p = nullptr;
-        FLGPU_CUDA_CHECK(cudaMalloc(&p, bytes));
+        void *p = ws_alloc(bytes);
         FLGPU_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream));
-        owned.push_back(p);
+        owned.emplace_back(p, bytes);
         return p;
     };
     R = (double *)dalloc(nres * sizeof(double));
@@ -218,7 +283,7 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
 
 CudaBackend::~CudaBackend() {
     cudaStreamSynchronize(stream);
-    for (void *p : owned) cudaFree(p);
+    for (auto &pb : owned) ws_free(pb.first, pb.second);
     if (host_pinned) cudaFreeHost(host_pinned);
     for (auto &pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
@@ -227,9 +292,11 @@ CudaBackend::~CudaBackend() {
 
 double *CudaBackend::vec_alloc() {
     void *p = nullptr;
-    FLGPU_CUDA_CHECK(cudaMalloc(&p, (size_t)ld * sizeof(double)));
+    const double t0 = now_ms();
+    p = ws_alloc((size_t)ld * sizeof(double));
+    alloc_ms += now_ms() - t0;
     FLGPU_CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)ld * sizeof(double), stream));
-    owned.push_back(p);
+    owned.emplace_back(p, (size_t)ld * sizeof(double));
     return (double *)p;
 }
 
@@ -241,8 +308,10 @@ void CudaBackend::lbfgs_alloc(int m) {
     mem = m;
     auto dalloc = [&](size_t bytes) {
         void *p = nullptr;
-        FLGPU_CUDA_CHECK(cudaMalloc(&p, bytes));
-        owned.push_back(p);
+        const double t0 = now_ms();
+        p = ws_alloc(bytes);
+        alloc_ms += now_ms() - t0;
+        owned.emplace_back(p, bytes);
         return p;
     };
     // ring buffers: column-major (ld, m) like the reference's s(dim,0:mem), y(dim,0:mem) (f90:435)
@@ -257,16 +326,21 @@ void CudaBackend::lbfgs_alloc(int m) {
 }
 
 void CudaBackend::upload(double *dst, const double *user_x, int x_space) {
+    const double t0 = now_ms();
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(dst, user_x, (size_t)n * sizeof(double),
                                      x_space == FLGPU_SPACE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                      stream));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+    upload_ms += now_ms() - t0;
 }
 void CudaBackend::download(double *user_x, const double *src, int x_space) {
+    FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const double t0 = now_ms();
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(user_x, src, (size_t)n * sizeof(double),
                                      x_space == FLGPU_SPACE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                                      stream));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+    download_ms += now_ms() - t0;
     resolve_times();
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/flgpu.h"
@@ -31,6 +32,12 @@ namespace flgpu {
 [[noreturn]] void fatal(const char *msg);
 // Aborts with a message unless a CUDA device is usable (the library has no CPU path).
 int require_device();
+
+// ---- work-space allocation (optionally cached between calls: flgpu_set_workspace_cache)
+void *ws_alloc(size_t bytes);
+void ws_free(void *p, size_t bytes);
+void ws_release();
+void ws_set_enabled(bool on);
 
 // ---- NCCL (resolved with dlopen so single-GPU use has no NCCL dependency)
 void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s);
@@ -78,6 +85,7 @@ public:
     cudaStream_t stream = nullptr;
     std::vector<KernelTime> times;
     void resolve_times();
+    double alloc_ms = 0.0, upload_ms = 0.0, download_ms = 0.0;   // wall clock, for FLGPU_TRACE_PHASES
 
 private:
     flgpu_problem prob;
@@ -85,7 +93,7 @@ private:
     flgpu_comm *comm = nullptr;
     bool own_stream = false;
     int device = 0, num_sms = 148;
-    std::vector<void *> owned;
+    std::vector<std::pair<void *, size_t>> owned;
     k::Work work{};
     double *Rall = nullptr;       // [G][NSLOTS + nd] all-gathered results (NCCL fallback only)
     double *Dsum = nullptr;       // [nd] rank-ordered sum of the K1 dots

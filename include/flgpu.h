@@ -279,6 +279,14 @@ void flgpu_free(void *dev_ptr);
 int flgpu_memcpy(void *dst, const void *src, size_t bytes, int dst_space, int src_space, void *stream);
 int flgpu_device_count(void); /* 0 when no CUDA device is usable; never aborts */
 
+/* Work-space cache.  By default every call allocates its work space ((2m+5) n doubles) and returns it to the
+ * driver before it returns, like the reference (f90:435, 584).  With the cache on (or FLGPU_WORKSPACE_CACHE=1) the
+ * buffers are parked for the next call on the same device -- repeated solves (e.g. an augmented-Lagrangian outer
+ * loop, f90:2150-2185) then skip cudaMalloc/cudaFree, which cost 0.3-0.6 s for 50 GiB.  flgpu_release_workspace()
+ * returns parked buffers to the driver; switching the cache off does so too. */
+void flgpu_set_workspace_cache(int on);
+void flgpu_release_workspace(void);
+
 /* ------------------------------------------------------------------ introspection */
 const char *flgpu_version(void);
 /* Per-kernel accumulated CUDA-event time of the last call run with time_kernels=1.
