@@ -500,7 +500,7 @@ void CudaBackend::lbfgs_solve(int kk, int recent) {
     const int G = ctx.nranks;
     const double *Dall = R + NSLOTS;
     if (G > 1) {
-        exchange(R + NSLOTS, nd, Dsum);
+        exchange(R + NSLOTS, nd, Dsum, nullptr);
         Dall = Dsum;
     }
     const int t = time_begin("k2_solve", 0.0);
@@ -543,27 +543,32 @@ void CudaBackend::cg_update(double *p, const double *g1, double beta) {
 }
 
 // ---- ranks: out[i] = sum_r src_r[i] in rank order, identical bits on every rank
-void CudaBackend::exchange(const double *src, int count, double *out) {
+bool CudaBackend::exchange(const double *src, int count, double *out, double *host_out) {
     const int t = time_begin("c1_exchange", 0.0);
+    bool host_written = false;
     if (comm->p2p) {
         k::exchange_kernel<<<1, k::kMailWidth, 0, stream>>>(comm->peers, comm->rank, comm->nranks, ++comm->seq, src,
-                                                           count, out);
+                                                           count, out, host_out);
+        host_written = host_out != nullptr;
     } else {
         nccl_allgather_f64(comm, src, Rall, (size_t)count, stream);
         k::combine_kernel<<<1, k::kMailWidth, 0, stream>>>(Rall, ctx.nranks, count, out);
     }
     time_end(t);
     launches++;
+    return host_written;
 }
 
 // ---- host <- device: one 128-byte copy and one stream synchronisation
 void CudaBackend::fetch(double *host_slots) {
     const double *src = R;
+    bool on_host = false;
     if (ctx.nranks > 1) {
-        exchange(R, NSLOTS, Rglob);
+        on_host = exchange(R, NSLOTS, Rglob, host_pinned);   // pinned memory is device-addressable (UVA)
         src = Rglob;
     }
-    FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned, src, NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (!on_host)
+        FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned, src, NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) cuda_fail("kernel launch", e, __FILE__, __LINE__);

@@ -97,7 +97,8 @@ private:
     k::Work work{};
     double *Rall = nullptr;       // [G][NSLOTS + nd] all-gathered results (NCCL fallback only)
     double *Dsum = nullptr;       // [nd] rank-ordered sum of the K1 dots
-    void exchange(const double *src, int count, double *out);   // out = sum over ranks, in rank order
+    // out = sum over ranks, in rank order; returns true when the sums were also stored into host_out
+    bool exchange(const double *src, int count, double *out, double *host_out);
     double *Rglob = nullptr;      // [NSLOTS] combined slots
     double *host_pinned = nullptr;
     bool timing = false;

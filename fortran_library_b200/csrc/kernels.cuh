@@ -622,10 +622,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth).
+// src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth); host_out (optional):
+// the same sums stored straight into pinned host memory, so the host needs no copy after the stream drains.
 static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable peers, int me, int G,
                                                                        unsigned long long seq, const double *src,
-                                                                       int count, double *out) {
+                                                                       int count, double *out, double *host_out) {
     const int par = (int)(seq & 1ull);
     const int t = threadIdx.x;
     if (t < count) {
@@ -651,6 +652,7 @@ static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable p
         double s = __ldcv(&mine->data[par][0][t]);
         for (int r = 1; r < G; r++) s += __ldcv(&mine->data[par][r][t]);
         out[t] = s;
+        if (host_out) host_out[t] = s;
     }
 }
 
