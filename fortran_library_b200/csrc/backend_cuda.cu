@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <ctime>
 #include <map>
@@ -278,7 +279,10 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
     Dsum = (double *)dalloc(nd_of(k::kMaxMem) * sizeof(double));
     work.partials = (double *)dalloc((size_t)k::kMaxGrid * nd_of(k::kMaxMem) * sizeof(double));
     work.ticket = (unsigned int *)dalloc(64);
-    FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, NSLOTS * sizeof(double)));
+    FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, (NSLOTS + 8) * sizeof(double)));   // slots + flag word
+    std::memset(host_pinned, 0, (NSLOTS + 8) * sizeof(double));
+    const char *sync_mode = std::getenv("FLGPU_SYNC");
+    poll_sync = !(sync_mode && !std::strcmp(sync_mode, "stream"));
 }
 
 CudaBackend::~CudaBackend() {
@@ -548,7 +552,7 @@ bool CudaBackend::exchange(const double *src, int count, double *out, double *ho
     bool host_written = false;
     if (comm->p2p) {
         k::exchange_kernel<<<1, k::kMailWidth, 0, stream>>>(comm->peers, comm->rank, comm->nranks, ++comm->seq, src,
-                                                           count, out, host_out);
+                                                           count, out, host_out, host_seq + 1);
         host_written = host_out != nullptr;
     } else {
         nccl_allgather_f64(comm, src, Rall, (size_t)count, stream);
@@ -559,17 +563,39 @@ bool CudaBackend::exchange(const double *src, int count, double *out, double *ho
     return host_written;
 }
 
-// ---- host <- device: one 128-byte copy and one stream synchronisation
+// ---- host <- device.  The last kernel of the chain stores the 16 slots and then a sequence number into pinned
+// host memory; the host polls that word (no DMA copy, no driver synchronisation: ~20 us -> a few us per trial).
+// FLGPU_SYNC=stream selects the plain cudaMemcpyAsync + cudaStreamSynchronize path.
 void CudaBackend::fetch(double *host_slots) {
     const double *src = R;
     bool on_host = false;
     if (ctx.nranks > 1) {
-        on_host = exchange(R, NSLOTS, Rglob, host_pinned);   // pinned memory is device-addressable (UVA)
+        on_host = exchange(R, NSLOTS, Rglob, poll_sync ? host_pinned : nullptr);
         src = Rglob;
     }
-    if (!on_host)
+    if (poll_sync) {
+        if (!on_host) {
+            k::publish_kernel<<<1, 32, 0, stream>>>(src, host_pinned, host_seq + 1);
+            launches++;
+        }
+        host_seq++;
+        volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(host_pinned + NSLOTS);
+        unsigned long long spins = 0;
+        while (*flag != host_seq) {
+            if ((++spins & 0xffffu) == 0) {          // every 65536 polls make sure the stream is still healthy
+                cudaError_t q = cudaStreamQuery(stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) cuda_fail("waiting for results", q, __FILE__, __LINE__);
+                if (q == cudaSuccess && *flag != host_seq) fatal("result flag was not published (internal error)");
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
         FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned, src, NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+        FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) cuda_fail("kernel launch", e, __FILE__, __LINE__);
     std::memcpy(host_slots, host_pinned, NSLOTS * sizeof(double));

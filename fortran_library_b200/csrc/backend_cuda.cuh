@@ -100,7 +100,9 @@ private:
     // out = sum over ranks, in rank order; returns true when the sums were also stored into host_out
     bool exchange(const double *src, int count, double *out, double *host_out);
     double *Rglob = nullptr;      // [NSLOTS] combined slots
-    double *host_pinned = nullptr;
+    double *host_pinned = nullptr;   // [NSLOTS] results + [NSLOTS] flag word, pinned (device-addressable under UVA)
+    unsigned long long host_seq = 0; // value of the flag word after the last fetch()
+    bool poll_sync = true;
     bool timing = false;
     struct Pending { int idx; cudaEvent_t a, b; };
     std::vector<Pending> pending;

@@ -623,10 +623,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth); host_out (optional):
-// the same sums stored straight into pinned host memory, so the host needs no copy after the stream drains.
+// the same sums stored straight into pinned host memory followed by the flag word host_out[NSLOTS] = seq_host.
 static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable peers, int me, int G,
                                                                        unsigned long long seq, const double *src,
-                                                                       int count, double *out, double *host_out) {
+                                                                       int count, double *out, double *host_out,
+                                                                       unsigned long long seq_host) {
     const int par = (int)(seq & 1ull);
     const int t = threadIdx.x;
     if (t < count) {
@@ -654,6 +655,20 @@ static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable p
         out[t] = s;
         if (host_out) host_out[t] = s;
     }
+    if (host_out) {                    // publish: data, system-wide fence, then the flag the host polls
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) *reinterpret_cast<volatile unsigned long long *>(host_out + NSLOTS) = seq_host;
+    }
+}
+
+// Single GPU: the 16 result slots go to pinned host memory the same way (data, fence, flag), so the host polls a
+// cache line instead of paying a DMA copy plus a driver synchronisation per line-search trial.
+static __global__ void __launch_bounds__(32) publish_kernel(const double *src, double *host_out, unsigned long long seq_host) {
+    if (threadIdx.x < NSLOTS) host_out[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+    __syncwarp();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(host_out + NSLOTS) = seq_host;
 }
 
 // ------------------------------------------------------------------ multi-rank combine of the slots
