@@ -29,10 +29,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("FLGPU_LIBRARY", LIB_PATH)   # development: an alternative build of the same library
+    if not os.path.exists(path):
         raise FlgpuError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                          "g.build()'` (nvcc, sm_100a). There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
     L.flgpu_version.restype = C.c_char_p
     L.flgpu_malloc.restype = C.c_void_p
     L.flgpu_malloc.argtypes = [C.c_size_t]

@@ -425,11 +425,15 @@ extern "C" flgpu_history *flgpu_history_create(int64_t n_local, int memory, void
 }
 extern "C" int flgpu_history_push(flgpu_history *h, const double *x1_dev, const double *x0_dev, const double *g1_dev,
                                   const double *g0_dev) {
+    require_aligned16(x1_dev, "flgpu_history_push: x1"); require_aligned16(x0_dev, "flgpu_history_push: x0");
+    require_aligned16(g1_dev, "flgpu_history_push: g1"); require_aligned16(g0_dev, "flgpu_history_push: g0");
     h->H->push(x1_dev, x0_dev, g1_dev, g0_dev);
     return 0;
 }
 extern "C" int flgpu_history_direction(flgpu_history *h, const double *g1_dev, const double *x1_dev, double *p_dev,
                                        double *xt_dev, double *gp, double *pp) {
+    require_aligned16(g1_dev, "flgpu_history_direction: g1"); require_aligned16(x1_dev, "flgpu_history_direction: x1");
+    require_aligned16(p_dev, "flgpu_history_direction: p"); require_aligned16(xt_dev, "flgpu_history_direction: xt");
     h->H->direction(g1_dev, x1_dev, p_dev, xt_dev, gp, pp);
     return 0;
 }

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
+#include <cstdint>
 #include <cstring>
 #include <ctime>
 #include <map>
@@ -80,6 +81,12 @@ void cuda_fail(const char *what, cudaError_t e, const char *file, int line) {
     std::fprintf(stderr, "flgpu: CUDA failure %s (%s) at %s:%d -- no CPU fallback exists, aborting\n",
                  cudaGetErrorString(e), what, file, line);
     std::abort();
+}
+void require_aligned16(const void *p, const char *what) {
+    if (reinterpret_cast<uintptr_t>(p) & 15u) {
+        std::fprintf(stderr, "flgpu: %s must be 16-byte aligned (the kernels use 128-bit accesses)\n", what);
+        std::abort();
+    }
 }
 void fatal(const char *msg) {
     std::fprintf(stderr, "flgpu: %s\n", msg);

@@ -30,6 +30,7 @@ namespace flgpu {
 
 [[noreturn]] void cuda_fail(const char *what, cudaError_t e, const char *file, int line);
 [[noreturn]] void fatal(const char *msg);
+void require_aligned16(const void *p, const char *what);   // aborts with a message otherwise
 // Aborts with a message unless a CUDA device is usable (the library has no CPU path).
 int require_device();
 

@@ -36,7 +36,7 @@ __device__ __forceinline__ double2 ld2(const double *p, int64_t u) {
     return __ldg(reinterpret_cast<const double2 *>(p) + u);
 }
 __device__ __forceinline__ void st2(double *p, int64_t u, double2 v) {
-    reinterpret_cast<double2 *>(p)[u] = v;
+    reinterpret_cast<double2 *>(p)[u] = v;   // cache-streaming stores (__stcs) measured: no difference (profiles/r01_store_policy.md)
 }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -230,6 +230,8 @@ static int obj_grid(int64_t n) {
 void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp_dev, double *x_out, double *g_dev,
                       const double *x_dev, const double *p_dev, double step, int64_t n, int64_t offset,
                       int64_t n_global, cudaStream_t s) {
+    require_aligned16(x_dev, "objective: x"); require_aligned16(p_dev, "objective: p");
+    require_aligned16(x_out, "objective: x_out"); require_aligned16(g_dev, "objective: f'");
     Scratch &sc = scratch_for(s);
     k::ObjArgs a;
     a.x = x_dev; a.p = p_dev; a.a = step; a.x_out = x_out; a.g = g_dev; a.f_out = f_dev; a.gp_out = gp_dev;
@@ -359,6 +361,7 @@ extern "C" int flgpu_fill_start(int start_kind, uint64_t seed, double *x_dev, in
 
 extern "C" int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *out_dev, void *stream) {
     require_device();
+    require_aligned16(a_dev, "flgpu_vec_dot: a"); require_aligned16(b_dev, "flgpu_vec_dot: b");
     cudaStream_t s = (cudaStream_t)stream;
     Scratch &sc = scratch_for(s);
     k::dot_kernel<<<obj_grid(n), k::kThreads, 0, s>>>(a_dev, b_dev, n, sc.work, out_dev, 0);
@@ -369,6 +372,8 @@ extern "C" int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n
 extern "C" int flgpu_vec_trial(double *x_dev, const double *x0_dev, const double *p_dev, double a, int64_t n,
                                void *stream) {
     require_device();
+    require_aligned16(x_dev, "flgpu_vec_trial: x"); require_aligned16(x0_dev, "flgpu_vec_trial: x0");
+    require_aligned16(p_dev, "flgpu_vec_trial: p");
     k::trial_kernel<<<obj_grid(n), k::kThreads, 0, (cudaStream_t)stream>>>(x_dev, x0_dev, p_dev, a, n);
     FLGPU_CUDA_CHECK(cudaGetLastError());
     return 0;

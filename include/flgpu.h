@@ -250,6 +250,9 @@ int flgpu_builtin_ref_callbacks(int kind, flgpu_ref_f_fn *f, flgpu_ref_fd_fn *fd
 int flgpu_fill_start(int start_kind, uint64_t seed, double *x_dev, int64_t offset, int64_t n_local,
                      int64_t n_global, void *stream);
 
+/* Device vectors handed to the primitives, the history operator and the built-in objectives must be 16-byte
+ * aligned (128-bit accesses; cudaMalloc / flgpu_malloc pointers are).  x passed to the optimizers may have any
+ * alignment: it is copied into library-owned work space. */
 /* ------------------------------------------------------------------ vector primitives (a8) */
 /* Deterministic device primitives the optimizers are built from; exported for tests and
  * for users writing device callbacks.  All enqueue on `stream`; *_dev outputs are device

@@ -132,6 +132,70 @@ def test_vector_primitives(fl, n):
         assert out.numpy()[0] == first
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 255, 257, 4097, 100003])
+def test_no_out_of_bounds_writes(fl, n):
+    """compute-sanitizer is closed on this pool, so every kernel that writes a caller-visible vector is run on a
+    buffer embedded between canary zones (odd lengths, odd 8-byte alignments) and the canaries are checked."""
+    G = 67
+    canary = -7.25e300
+    rng = np.random.default_rng(n)
+
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    Ga = G + 1                                                 # vectors must stay 16-byte aligned (double2 accesses)
+
+    def guarded_al(values=None):
+        host = np.full(n + 2 * Ga, canary)
+        if values is not None:
+            host[Ga:Ga + n] = values
+        return fl.DeviceVector.from_numpy(host)
+    def inner_al(v):
+        return v.ptr + 8 * Ga
+
+    def intact_al(v):
+        h = v.numpy()
+        return bool(np.all(h[:Ga] == canary) and np.all(h[Ga + n:] == canary)), h[Ga:Ga + n]
+
+    ad, bd, xd = guarded_al(a), guarded_al(b), guarded_al()
+    fl.lib().flgpu_vec_trial(inner_al(xd), inner_al(ad), inner_al(bd), 0.5, n, None)
+    ok, x = intact_al(xd)
+    assert ok and np.array_equal(x, a + 0.5 * b)
+    for name in ("quartic", "rosenR1", "diag"):
+        prob = fl.builtin_problem(_cases.OBJECTIVES[name][0])
+        ctx = fl.capi.EvalCtx(None, None, 0, n, 0, 1, 0)
+        gd, xo, sc = guarded_al(), guarded_al(), fl.DeviceVector(4)
+        C.cast(prob.f_fd, fl.capi.F_FD_FN)(C.byref(ctx), sc.ptr, inner_al(gd), inner_al(ad), n)
+        assert intact_al(gd)[0], name
+        W = fl.capi
+        C.cast(prob.fused, fl.capi.FUSED_FN)(C.byref(ctx), W.WRITE_X | W.WRITE_G, sc.ptr, sc.ptr + 8, inner_al(xo),
+                                             inner_al(gd), inner_al(ad), inner_al(bd), 0.25, n)
+        assert intact_al(gd)[0] and intact_al(xo)[0], name
+    # K1 + K2 + K3 through the history operator: p and the trial point are caller buffers
+    L = fl.lib()
+    L.flgpu_history_create.restype = C.c_void_p
+    L.flgpu_history_create.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    L.flgpu_history_push.argtypes = [C.c_void_p] * 5
+    L.flgpu_history_direction.argtypes = [C.c_void_p] * 7
+    L.flgpu_history_destroy.argtypes = [C.c_void_p]
+    h = L.flgpu_history_create(n, 12, None, None)
+    d = np.exp(rng.uniform(0, 1, n))
+    x0 = rng.standard_normal(n)
+    pd, xt = guarded_al(), guarded_al()
+    for _ in range(14):                                       # more pushes than memory: every K1 shape and the wrap-around
+        x1 = x0 + 0.1 * rng.standard_normal(n)
+        vs = [guarded_al(v) for v in (x1, x0, d * x1, d * x0)]
+        L.flgpu_history_push(h, *[inner_al(v) for v in vs])
+        gp, pp = C.c_double(), C.c_double()
+        L.flgpu_history_direction(h, inner_al(vs[2]), inner_al(vs[0]), inner_al(pd), inner_al(xt), C.addressof(gp),
+                                  C.addressof(pp))
+        ok_p, pv = intact_al(pd)
+        ok_x, xv = intact_al(xt)
+        assert ok_p and ok_x
+        assert all(intact_al(v)[0] for v in vs)               # inputs untouched outside AND inside
+        assert np.array_equal(xv, x1 + pv)
+        x0 = x1
+    L.flgpu_history_destroy(h)
+
+
 # ----------------------------------------------------------------------------- parity: strict tier
 @pytest.mark.parametrize("name,mem", [("rosenR1", 10), ("rosenR1", 3), ("quartic", 10), ("diag", 30), ("rosenR0", 5),
                                       ("quartic", 1), ("rosenR1", 17)])
