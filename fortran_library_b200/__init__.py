@@ -13,7 +13,8 @@ import os
 from . import _capi as capi
 from ._capi import (CG_DY, CG_PR, SPACE_HOST, SPACE_DEVICE, OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD,  # noqa: F401
                     START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO, CONVERGED,
-                    STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER)
+                    STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER, AL_LBFGS, AL_CG,
+                    CON_SPHERE)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libflgpu.so")
@@ -241,6 +242,45 @@ def SteepestDescent(problem, x, Strong=None, Warning=None, MaxIteration=None, Pr
                 dict(Strong=Strong, Warning=Warning, MaxIteration=MaxIteration, Precision=Precision,
                      MinStepLength=MinStepLength, WolfeConst1=WolfeConst1, WolfeConst2=WolfeConst2,
                      Increment=Increment, fused=fused))
+
+
+def builtin_constraints(kind=CON_SPHERE):
+    """The reference's test constraint (test.f90:692-705): unit sphere, c = x.x - 1, as CUDA kernels."""
+    c = capi.Constraints()
+    if lib().flgpu_builtin_constraints(kind, C.byref(c)) != 0:
+        raise ValueError(f"unknown built-in constraint {kind}")
+    return c
+
+
+def AugmentedLagrangian(problem, constraints, x, UnconstrainedSolver="LBFGS", lambda0=None, miu0=None, Memory=None,
+                        Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
+                        WolfeConst1=None, WolfeConst2=None, Increment=None, stream=None, comm=None, offset=0, n_global=0):
+    """Equality-constrained minimisation (reference: AugmentedLagrangian, f90:2005-2241) with the hot path as inner
+    solver: UnconstrainedSolver 'LBFGS' or 'ConjugateGradient' (the dense-Hessian solvers are outside the GPU path)."""
+    import numpy as np
+    if UnconstrainedSolver not in ("LBFGS", "ConjugateGradient"):
+        raise SystemExit("Program abort: unsupported unconstrained solver " + str(UnconstrainedSolver))
+    require_gpu()
+    L = lib()
+    L.flgpu_augmented_lagrangian.argtypes = [C.POINTER(capi.Problem), C.POINTER(capi.Constraints),
+                                             C.POINTER(capi.ALOptions), C.c_void_p, C.c_int64, C.c_int,
+                                             C.POINTER(capi.ALStats)]
+    o = capi.ALOptions()
+    L.flgpu_al_options_default(C.byref(o), capi.AL_CG if UnconstrainedSolver == "ConjugateGradient" else capi.AL_LBFGS)
+    capi.apply_options(o.inner, Memory=Memory, Method=Method, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
+                       Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
+                       WolfeConst2=WolfeConst2, Increment=Increment)
+    o.inner.stream, o.inner.comm, o.inner.offset, o.inner.n_global = stream, comm, offset, n_global
+    lam = None
+    if lambda0 is not None:
+        lam = np.ascontiguousarray(lambda0, dtype=np.float64)
+        o.lambda0 = lam.ctypes.data
+    if miu0 is not None:
+        o.miu0 = miu0
+    ptr, n, space = _resolve_x(x)
+    st = capi.ALStats()
+    L.flgpu_augmented_lagrangian(C.byref(problem), C.byref(constraints), C.byref(o), ptr, n, space, C.byref(st))
+    return st
 
 
 class History:

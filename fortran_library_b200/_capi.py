@@ -65,6 +65,29 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+# AugmentedLagrangian (flgpu_constraints, flgpu_al_options, flgpu_al_stats)
+AL_LBFGS, AL_CG = 0, 1
+CON_SPHERE = 0
+C_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_void_p, C.c_void_p, C.c_int, C.c_int64)
+CD_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64)
+REF_C_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int))
+REF_CD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int))
+
+
+class Constraints(C.Structure):
+    _fields_ = [("c", C.c_void_p), ("cd", C.c_void_p), ("m", C.c_int)]
+
+
+class ALOptions(C.Structure):
+    _fields_ = [("solver", C.c_int), ("lambda0", C.c_void_p), ("miu0", C.c_double), ("inner", Options)]
+
+
+class ALStats(C.Structure):
+    _fields_ = [("outer_iterations", C.c_int64), ("inner_iterations", C.c_int64), ("trials", C.c_int64),
+                ("status", C.c_int), ("cnorm2", C.c_double), ("miu", C.c_double), ("f", C.c_double),
+                ("gpu_launches", C.c_int64)]
+
+
 def apply_options(o, **kw):
     """Set Options fields from reference-style keyword names (None = leave default)."""
     names = {"Memory": "memory", "Method": "method", "Strong": "strong", "Warning": "warning",

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "api_internal.hpp"
 #include "backend_cuda.cuh"
 #include "driver.hpp"
 
@@ -20,7 +21,7 @@ flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f);   // objectives.cu
 extern int g_k1_shape[2];                             // backend_cuda.cu
 }
 
-namespace {
+namespace flgpu_api {
 
 // flgpu_register_fused: reference-ABI objective -> fused line-search evaluation
 struct FusedEntry { flgpu_fused_fn fn; void *user; };
@@ -55,8 +56,6 @@ int cb_space_now() {
     int v = g_cb_space.load();
     return v >= 0 ? v : space_from_env("FLGPU_CALLBACK_SPACE", FLGPU_SPACE_DEVICE);
 }
-
-enum Algo { ALGO_LBFGS = 0, ALGO_CG = 1, ALGO_SD = 2 };
 
 double wall_ms() {
     timespec ts;
@@ -106,15 +105,7 @@ int run(int algo, const flgpu_problem *prob, const flgpu_options *opt, double *x
 }
 
 // ---- adapter: reference-ABI callbacks (f90:33-38) behind the 64-bit device-callback interface
-struct RefAdapter {
-    flgpu_ref_f_fn f;
-    flgpu_ref_fd_fn fd;
-    flgpu_ref_f_fd_fn f_fd;
-    int cb_space;
-    double *xh = nullptr, *gh = nullptr;  // pinned staging (callback space HOST)
-    flgpu_fused_fn fused = nullptr;       // registered with flgpu_register_fused for this f
-    void *fused_user = nullptr;
-};
+// (struct RefAdapter: api_internal.hpp)
 void ad_fused(const flgpu_eval_ctx *c, int flags, double *f_dev, double *gp_dev, double *x_out, double *g_out,
               const double *x0, const double *p, double a, int64_t n) {
     const RefAdapter *A = (const RefAdapter *)c->user;
@@ -162,18 +153,15 @@ void ad_ffd(const flgpu_eval_ctx *c, double *f_dev, double *g, const double *x, 
     k::set_scalar_kernel<<<1, 1, 0, s>>>(f_dev, fx);
 }
 
-void run_ref(int algo, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
-             flgpu_options &o) {
-    require_device();
-    RefAdapter A;
+void ref_adapter_init(RefAdapter &A, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, int dim,
+                      flgpu_problem *prob) {
     A.f = f; A.fd = fd; A.f_fd = f_fd; A.cb_space = cb_space_now();
     if (A.cb_space == FLGPU_SPACE_HOST) {
         FLGPU_CUDA_CHECK(cudaMallocHost((void **)&A.xh, sizeof(double) * (size_t)(dim > 0 ? dim : 1)));
         FLGPU_CUDA_CHECK(cudaMallocHost((void **)&A.gh, sizeof(double) * (size_t)(dim > 0 ? dim : 1)));
     }
-    flgpu_problem prob;
-    prob.f = ad_f; prob.fd = ad_fd; prob.f_fd = f_fd ? ad_ffd : nullptr; prob.user = &A;
-    prob.fused = nullptr;
+    prob->f = ad_f; prob->fd = ad_fd; prob->f_fd = f_fd ? ad_ffd : nullptr; prob->user = &A;
+    prob->fused = nullptr;
     if (A.cb_space == FLGPU_SPACE_DEVICE) {
         {
             std::lock_guard<std::mutex> lock(g_fused_mu);
@@ -181,15 +169,30 @@ void run_ref(int algo, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f
             if (it != g_fused.end()) { A.fused = it->second.fn; A.fused_user = it->second.user; }
         }
         if (!A.fused) A.fused = builtin_fused_for(f);
-        if (A.fused) prob.fused = ad_fused;
+        if (A.fused) prob->fused = ad_fused;
     }
+}
+void ref_adapter_free(RefAdapter &A) {
+    if (A.xh) cudaFreeHost(A.xh);
+    if (A.gh) cudaFreeHost(A.gh);
+    A.xh = A.gh = nullptr;
+}
+void apply_thread_settings(flgpu_options &o) {
     o.observer = tls.observer;
     o.observer_user = tls.observer_user;
     const char *nf = std::getenv("FLGPU_NO_FUSED");
     if (nf && nf[0] && nf[0] != '0') o.no_fused = 1;
+}
+
+void run_ref(int algo, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
+             flgpu_options &o) {
+    require_device();
+    RefAdapter A;
+    flgpu_problem prob;
+    ref_adapter_init(A, f, fd, f_fd, dim, &prob);
+    apply_thread_settings(o);
     run(algo, &prob, &o, x, dim, x_space_now(), nullptr);
-    if (A.xh) cudaFreeHost(A.xh);
-    if (A.gh) cudaFreeHost(A.gh);
+    ref_adapter_free(A);
 }
 
 // Fortran OPTIONAL -> options (NULL = absent keeps the default, f90:417-434 / 212-229)
@@ -220,7 +223,10 @@ int parse_method(const char *Method, int len, bool whole_string) {
     std::exit(1);  // the reference executes `stop` (f90:345)
 }
 
-}  // namespace
+void set_last_stats(const flgpu_stats &st) { tls.last = st; }
+
+}  // namespace flgpu_api
+using namespace flgpu_api;
 
 extern "C" {
 

@@ -72,6 +72,10 @@ void ws_release() {
     for (auto &kv : g_ws.free_) cudaFree(kv.second);
     g_ws.free_.clear();
 }
+bool ws_is_enabled() {
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    return ws_enabled();
+}
 void ws_set_enabled(bool on) {
     { std::lock_guard<std::mutex> lock(g_ws.mu); g_ws.enabled = on; g_ws.env_read = true; }
     if (!on) ws_release();
@@ -554,17 +558,25 @@ void CudaBackend::cg_update(double *p, const double *g1, double beta) {
 }
 
 // ---- ranks: out[i] = sum_r src_r[i] in rank order, identical bits on every rank
+// out[i] = sum_r src_r[i] in rank order (identical bits on every rank).  One kernel over peer memory, or the
+// ncclAllGather + combine fallback (gather: [G][count] device scratch).  host_out (optional, peer-memory path
+// only): pinned host array that receives the sums followed by the flag word host_seq_next; returns whether it did.
+bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, double *out, double *gather,
+              double *host_out, unsigned long long host_seq_next) {
+    if (count > k::kMailWidth) fatal("rank_sum: more values than one mailbox slot holds");
+    if (c->p2p) {
+        k::exchange_kernel<<<1, k::kMailWidth, 0, s>>>(c->peers, c->rank, c->nranks, ++c->seq, src, count, out, host_out,
+                                                      host_seq_next);
+        return host_out != nullptr;
+    }
+    nccl_allgather_f64(c, src, gather, (size_t)count, s);
+    k::combine_kernel<<<1, k::kMailWidth, 0, s>>>(gather, c->nranks, count, out);
+    return false;
+}
+
 bool CudaBackend::exchange(const double *src, int count, double *out, double *host_out) {
     const int t = time_begin("c1_exchange", 0.0);
-    bool host_written = false;
-    if (comm->p2p) {
-        k::exchange_kernel<<<1, k::kMailWidth, 0, stream>>>(comm->peers, comm->rank, comm->nranks, ++comm->seq, src,
-                                                           count, out, host_out, host_seq + 1);
-        host_written = host_out != nullptr;
-    } else {
-        nccl_allgather_f64(comm, src, Rall, (size_t)count, stream);
-        k::combine_kernel<<<1, k::kMailWidth, 0, stream>>>(Rall, ctx.nranks, count, out);
-    }
+    const bool host_written = rank_sum(comm, stream, src, count, out, Rall, host_out, host_seq + 1);
     time_end(t);
     launches++;
     return host_written;

@@ -39,9 +39,13 @@ void *ws_alloc(size_t bytes);
 void ws_free(void *p, size_t bytes);
 void ws_release();
 void ws_set_enabled(bool on);
+bool ws_is_enabled();
 
 // ---- NCCL (resolved with dlopen so single-GPU use has no NCCL dependency)
 void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s);
+// rank-ordered sum of `count` (<= k::kMailWidth) doubles over the communicator (backend_cuda.cu)
+bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, double *out, double *gather,
+              double *host_out, unsigned long long host_seq_next);
 
 // ---- per-kernel CUDA-event timing (flgpu_options.time_kernels)
 struct KernelTime {

@@ -682,6 +682,7 @@ static __global__ void combine_kernel(const double *all, int G, int count, doubl
 }
 
 static __global__ void set_scalar_kernel(double *dst, double v) { *dst = v; }
+static __global__ void add_scalar_kernel(double *dst, double v) { *dst = __dadd_rn(*dst, v); }
 
 }  // namespace k
 }  // namespace flgpu

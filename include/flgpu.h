@@ -6,6 +6,7 @@
  * "hpp:" = cpp/NonlinearOptimization.hpp of YifanShenSZ/Fortran-Library):
  *   LBFGS                   f90:398-400   (no hpp declaration exists; added by analogy)
  *   SteepestDescent         f90:55-56     hpp:279-291 (gnu) / hpp:11-23 (intel)   [SURVEY 8f row N1]
+ *   AugmentedLagrangian     f90:2005-2008 hpp:369-392 (gnu), LBFGS / ConjugateGradient branches [SURVEY 8f row N2]
  *   ConjugateGradient       f90:193-195   hpp:310-324 (gnu) / hpp:42-56 (intel)
  *   ConjugateGradient_basic f90:2249-2251 hpp:292-306 (gnu) / hpp:24-38 (intel)
  *   Strong-Wolfe / Wolfe line searchers f90:1286,1373,1462,1582 (internal to the above)
@@ -165,6 +166,50 @@ int flgpu_conjugate_gradient(const flgpu_problem *prob, const flgpu_options *opt
 int flgpu_steepest_descent(const flgpu_problem *prob, const flgpu_options *opt, double *x,
                            int64_t n_local, int x_space, flgpu_stats *stats);
 
+/* ------------------------------------------------------------------ AugmentedLagrangian over LBFGS / CG */
+/* Reference: AugmentedLagrangian (f90:2005-2241), branches UnconstrainedSolver = 'LBFGS' (f90:2150-2167) and
+ * 'ConjugateGradient' (f90:2168-2185) -- the only in-library caller of the hot path.  Minimises
+ * f(x) subject to c(x) = 0 (M equality constraints) by repeated unconstrained solves of
+ * L(x) = f - lambda.c + miu/2 c.c (f90:2193-2228) followed by lambda -= miu c, miu *= Increment.
+ * Device callbacks: c stores this rank's PARTIAL values of the M constraints (constants such as the "-1" of a
+ * sphere constraint belong to rank 0 only); cd stores the local rows of the N x M Jacobian, column-major with
+ * leading dimension ld (cdx(N,M) of the reference).  M <= 64. */
+typedef void (*flgpu_c_fn)(const flgpu_eval_ctx *ctx, double *c_dev, const double *x_dev, int m, int64_t n_local);
+typedef void (*flgpu_cd_fn)(const flgpu_eval_ctx *ctx, double *cd_dev, const double *x_dev, int m, int64_t n_local,
+                            int64_t ld);
+typedef struct flgpu_constraints {
+    flgpu_c_fn c;
+    flgpu_cd_fn cd;
+    int m;
+} flgpu_constraints;
+enum { FLGPU_AL_LBFGS = 0, FLGPU_AL_CG = 1 };
+typedef struct flgpu_al_options {
+    int solver;             /* FLGPU_AL_LBFGS / FLGPU_AL_CG */
+    const double *lambda0;  /* host, m values; NULL = 0 (f90:2037-2038) */
+    double miu0;            /* default 1, clamped max(1,.) (f90:2039-2040) */
+    flgpu_options inner;    /* Memory, Method, Strong, Warning, MaxIteration (also the outer limit), Precision (also the
+                               |c| tolerance), MinStepLength, WolfeConst1/2, Increment (also the miu growth), stream,
+                               comm, offset, n_global: passed to every inner solve as the reference does */
+} flgpu_al_options;
+typedef struct flgpu_al_stats {
+    int64_t outer_iterations, inner_iterations, trials;
+    int status;             /* 0 = |c|^2 < Precision^2, FLGPU_MAX_ITERATION otherwise */
+    double cnorm2, miu, f;
+    int64_t gpu_launches;
+} flgpu_al_stats;
+void flgpu_al_options_default(flgpu_al_options *o, int solver);   /* WolfeConst2 0.45 for CG, 0.9 otherwise (f90:2060-2067) */
+int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraints *con, const flgpu_al_options *opt,
+                               double *x, int64_t n_local, int x_space, flgpu_al_stats *stats);
+void flgpu_last_al_stats(flgpu_al_stats *out);
+/* the reference's test constraint (test.f90:692-705): unit sphere, c = x.x - 1, cd = 2x, as CUDA kernels */
+enum { FLGPU_CON_SPHERE = 0 };
+int flgpu_builtin_constraints(int kind, flgpu_constraints *out);
+/* reference-ABI constraint callbacks (hpp:372-373): c(cx, x, M, N), cd(cdx, x, M, N); with device callback space x
+ * and cdx are device pointers and cx is a HOST array the callback must have filled when it returns */
+typedef void (*flgpu_ref_c_fn)(double *cx, const double *x, const int *M, const int *N);
+typedef void (*flgpu_ref_cd_fn)(double *cdx, const double *x, const int *M, const int *N);
+int flgpu_builtin_ref_constraints(int kind, flgpu_ref_c_fn *c, flgpu_ref_cd_fn *cd);
+
 /* ------------------------------------------------------------------ multi-GPU (row shards) */
 /* One process per GPU.  Rank 0 obtains a 128-byte id, the caller distributes it
  * (MPI / torch.distributed / file), every rank creates the communicator. */
@@ -216,7 +261,24 @@ void __nonlinearoptimization_MOD_conjugategradient_basic(
     const int32_t *Strong, const int32_t *Warning, const int *MaxIteration, const double *Precision,
     const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
     const double *Increment, int len_Method);
+/* f90:2005-2008, hpp:369-392.  Only UnconstrainedSolver = 'LBFGS' / 'ConjugateGradient' run here; the dense-Hessian
+ * solvers ('BFGS' -- the reference default --, 'NewtonRaphson') print a message and exit.  fdd, cdd, ExactStep are
+ * accepted and ignored (they serve those solvers only). */
+void __nonlinearoptimization_MOD_augmentedlagrangian(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_c_fn c, flgpu_ref_cd_fn cd, double *x, const int *N, const int *M,
+    const char *UnconstrainedSolver, const double *lambda0, const double *miu0, void *fdd, void *cdd,
+    const int *ExactStep, const int *Memory, const char *Method, flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+    const int32_t *Warning, const int *MaxIteration, const double *Precision, const double *MinStepLength,
+    const double *WolfeConst1, const double *WolfeConst2, const double *Increment, int len_UnconstrainedSolver,
+    int len_Method);
 /* ifort names (hpp:9-276 "#ifdef __INTEL_COMPILER") */
+void nonlinearoptimization_mp_augmentedlagrangian_(
+    flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_c_fn c, flgpu_ref_cd_fn cd, double *x, const int *N, const int *M,
+    const char *UnconstrainedSolver, const double *lambda0, const double *miu0, void *fdd, void *cdd,
+    const int *ExactStep, const int *Memory, const char *Method, flgpu_ref_f_fd_fn f_fd, const int32_t *Strong,
+    const int32_t *Warning, const int *MaxIteration, const double *Precision, const double *MinStepLength,
+    const double *WolfeConst1, const double *WolfeConst2, const double *Increment, int len_UnconstrainedSolver,
+    int len_Method);
 void nonlinearoptimization_mp_lbfgs_(
     flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, double *x, const int *dim, const int *Memory,
     flgpu_ref_f_fd_fn f_fd, const int32_t *Strong, const int32_t *Warning, const int *MaxIteration,

@@ -137,3 +137,15 @@ void orc_obj_fd(double *fdx, const double *x, const int *dim) { eval(0, fdx, x, 
 int orc_obj_f_fd(double *fx, double *fdx, const double *x, const int *dim) {
     return eval(fx, fdx, x, *dim);
 }
+
+/* test.f90:692-705: the unit-sphere equality constraint used by the reference's AugmentedLagrangian smoke test */
+void orc_con_sphere_c(double *cx, const double *x, const int *M, const int *N) {
+    double s = 0.0;
+    (void)M;
+    for (int i = 0; i < *N; i++) s = s + x[i] * x[i];
+    cx[0] = s - 1.0;
+}
+void orc_con_sphere_cd(double *cdx, const double *x, const int *M, const int *N) {
+    (void)M;
+    for (int i = 0; i < *N; i++) cdx[i] = 2.0 * x[i];
+}

@@ -646,3 +646,123 @@ void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, orc
 done:
     free(p); free(fdnew); free(fdold);
 }
+
+/* ------------------------------------------------------------------ AugmentedLagrangian f90:2005-2241 */
+/* Only the branches that call the hot path are restated: UnconstrainedSolver = 'LBFGS' (f90:2150-2167) and
+ * 'ConjugateGradient' (f90:2168-2185).  The internal procedures L, Ld, L_Ld, L_Ld_fdwithf (f90:2193-2228) reach
+ * the host variables lambda, miu, cx, cdx by host association; C has no closures, so they live in this struct. */
+static struct {
+    orc_f_t f; orc_fd_t fd; orc_ffd_t f_fd; orc_c_t c; orc_cd_t cd;
+    int M; double miu; double *lambda, *cx, *cdx;
+} AL;
+static orc_al_stats_t g_al;
+
+static void al_terms(double *Lx, int N) {                /* Lx = Lx - dot(lambda,cx) + miu/2*dot(cx,cx) */
+    double d1 = 0.0, d2 = 0.0;
+    int j;
+    (void)N;
+    for (j = 0; j < AL.M; j++) d1 += AL.lambda[j] * AL.cx[j];
+    for (j = 0; j < AL.M; j++) d2 += AL.cx[j] * AL.cx[j];
+    *Lx = *Lx - d1 + AL.miu / 2.0 * d2;
+}
+static void al_grad(double *Ldx, int N) {                /* Ldx = Ldx + matmul(cdx, miu*cx-lambda), cdx(N,M) */
+    int i, j;
+    for (i = 0; i < N; i++) {
+        double r = 0.0;
+        for (j = 0; j < AL.M; j++) r += AL.cdx[(size_t)j * (size_t)N + i] * (AL.miu * AL.cx[j] - AL.lambda[j]);
+        Ldx[i] = Ldx[i] + r;
+    }
+}
+static void al_L(double *Lx, const double *x, const int *N) {                  /* f90:2193-2199 */
+    AL.f(Lx, x, N); AL.c(AL.cx, x, &AL.M, N);
+    al_terms(Lx, *N);
+}
+static void al_Ld(double *Ldx, const double *x, const int *N) {                /* f90:2200-2206 */
+    AL.fd(Ldx, x, N); AL.c(AL.cx, x, &AL.M, N); AL.cd(AL.cdx, x, &AL.M, N);
+    al_grad(Ldx, *N);
+}
+static int al_L_Ld(double *Lx, double *Ldx, const double *x, const int *N) {   /* f90:2207-2217 */
+    AL.f(Lx, x, N); AL.c(AL.cx, x, &AL.M, N);
+    al_terms(Lx, *N);
+    AL.fd(Ldx, x, N); AL.cd(AL.cdx, x, &AL.M, N);
+    al_grad(Ldx, *N);
+    return 0;
+}
+static int al_L_Ld_fdwithf(double *Lx, double *Ldx, const double *x, const int *N) { /* f90:2218-2228 */
+    (void)AL.f_fd(Lx, Ldx, x, N); AL.c(AL.cx, x, &AL.M, N);
+    al_terms(Lx, *N);
+    AL.cd(AL.cdx, x, &AL.M, N);
+    al_grad(Ldx, *N);
+    return 0;
+}
+void orc_get_al_stats(orc_al_stats_t *out) { *out = g_al; }
+
+static int str_is(const char *s, int len, const char *lit) { /* Fortran == on blank-padded strings */
+    int n = (int)strlen(lit), i;
+    if (!s) return 0;
+    for (i = 0; i < n; i++) if (i >= len || s[i] != lit[i]) return 0;
+    for (i = n; i < len; i++) if (s[i] != ' ') return 0;
+    return 1;
+}
+
+void orc_augmentedlagrangian(orc_f_t f, orc_fd_t fd, orc_c_t c, orc_cd_t cd, double *x, const int *N_, const int *M_,
+                             const char *UnconstrainedSolver, const double *lambda0, const double *miu0,
+                             const void *fdd, const void *cdd, const int *ExactStep, const int *Memory,
+                             const char *Method, orc_ffd_t f_fd, const int *Strong, const int *Warning,
+                             const int *MaxIteration, const double *Precision, const double *MinStepLength,
+                             const double *WolfeConst1, const double *WolfeConst2, const double *Increment,
+                             int len_solver, int len_Method) {
+    const int N = *N_, M = *M_;
+    int sw, warn, maxit, mem, iIteration, j, is_cg;
+    double tol, minstep, c1, c2, incrmt, tolsq, cc = 0.0;
+    char type[32];
+    (void)fdd; (void)cdd; (void)ExactStep;
+    memset(&g_al, 0, sizeof g_al);
+    AL.f = f; AL.fd = fd; AL.f_fd = f_fd; AL.c = c; AL.cd = cd; AL.M = M;
+    AL.lambda = valloc(M); AL.cx = valloc(M); AL.cdx = valloc((long)N * M);
+    for (j = 0; j < M; j++) AL.lambda[j] = lambda0 ? lambda0[j] : 0.0;                 /* f90:2037-2038 */
+    if (miu0) AL.miu = fmax(1.0, *miu0); else AL.miu = 1.0;                           /* f90:2039-2040 */
+    if (Strong) sw = (*Strong != 0); else sw = 1;                                     /* f90:2042-2075 */
+    if (Warning) warn = (*Warning != 0); else warn = 1;
+    if (MaxIteration) maxit = *MaxIteration; else maxit = 1000;
+    if (Precision) tol = *Precision; else tol = 1e-15;
+    if (MinStepLength) minstep = *MinStepLength; else minstep = 1e-15;
+    if (WolfeConst1) c1 = fmax(1e-15, *WolfeConst1); else c1 = 1e-4;
+    is_cg = str_is(UnconstrainedSolver, len_solver, "ConjugateGradient");
+    if (WolfeConst2) c2 = fmin(1.0 - 1e-15, fmax(c1 + 1e-15, *WolfeConst2));
+    else c2 = is_cg ? 0.45 : 0.9;
+    if (Increment) incrmt = *Increment; else incrmt = 1.05;
+    if (Memory) mem = *Memory > 1 ? *Memory : 1; else mem = 10;
+    memset(type, ' ', sizeof type);
+    if (Method) memcpy(type, Method, (size_t)(len_Method < 32 ? len_Method : 32)); else { type[0] = 'D'; type[1] = 'Y'; }
+    tolsq = tol * tol;
+    if (!is_cg && !str_is(UnconstrainedSolver, len_solver, "LBFGS")) {
+        printf(" oracle: AugmentedLagrangian is restated for UnconstrainedSolver = LBFGS / ConjugateGradient only\n");
+        exit(2);
+    }
+    for (iIteration = 1; iIteration <= maxit; iIteration++) {                         /* f90:2150-2185 */
+        orc_ffd_t inner_ffd = f_fd ? al_L_Ld_fdwithf : al_L_Ld;
+        if (is_cg)
+            orc_conjugategradient(al_L, al_Ld, x, &N, type, inner_ffd, &sw, &warn, &maxit, &tol, &minstep, &c1, &c2,
+                                  &incrmt, 32);
+        else
+            orc_lbfgs(al_L, al_Ld, x, &N, &mem, inner_ffd, &sw, &warn, &maxit, &tol, &minstep, &c1, &c2, &incrmt);
+        g_al.inner_iterations += g_st.n_iter;
+        g_al.trials += g_st.n_trials;
+        g_al.outer_iterations = iIteration;
+        c(AL.cx, x, &M, &N);
+        cc = 0.0;
+        for (j = 0; j < M; j++) cc += AL.cx[j] * AL.cx[j];
+        g_al.cnorm2 = cc;
+        if (cc < tolsq) break;
+        for (j = 0; j < M; j++) AL.lambda[j] = AL.lambda[j] - AL.miu * AL.cx[j];
+        AL.miu = AL.miu * incrmt;
+    }
+    g_al.miu = AL.miu;
+    g_al.status = iIteration > maxit ? 2 : 0;
+    if (iIteration > maxit && warn) {                                                 /* f90:2187-2190 */
+        printf(" Failed augmented Lagrangian: max iteration exceeded!\n");
+        printf(" Euclidean norm of constraint violation = %.17g\n", sqrt(cc));
+    }
+    free(AL.lambda); free(AL.cx); free(AL.cdx);
+}

@@ -10,6 +10,7 @@
  *     Wolfe / Wolfe_fdwithf    f90:1286-1459
  *     StrongWolfe / _fdwithf   f90:1462-1698
  *     ConjugateGradient_basic  f90:2249-2346
+ *     AugmentedLagrangian      f90:2005-2241 (LBFGS / ConjugateGradient branches)
  *
  * PARITY UNPINNED: the reference cannot be compiled here (no Fortran compiler,
  * no MKL: SURVEY.md F1/F2) and its tests hold no golden vectors for this path
@@ -80,6 +81,29 @@ void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim, orc_
                          const int *Strong, const int *Warning, const int *MaxIteration,
                          const double *Precision, const double *MinStepLength, const double *WolfeConst1,
                          const double *WolfeConst2, const double *Increment);
+
+/* constraint callbacks of AugmentedLagrangian (f90:2012, test.f90:692-705; hpp:372-373): c(cx,x,M,N), cd(cdx,x,M,N)
+ * with cdx(N,M) column-major */
+typedef void (*orc_c_t)(double *cx, const double *x, const int *M, const int *N);
+typedef void (*orc_cd_t)(double *cdx, const double *x, const int *M, const int *N);
+typedef struct {
+    long outer_iterations, inner_iterations, trials;
+    int status;        /* 0 constraint converged, 2 max iteration */
+    double cnorm2, miu;
+} orc_al_stats_t;
+/* f90:2005-2241, branches UnconstrainedSolver = 'LBFGS' / 'ConjugateGradient' only (the others are dense
+ * Newton / BFGS solvers outside the hot path).  Argument order and hidden lengths as hpp:369-392. */
+void orc_augmentedlagrangian(orc_f_t f, orc_fd_t fd, orc_c_t c, orc_cd_t cd, double *x, const int *N, const int *M,
+                             const char *UnconstrainedSolver, const double *lambda0, const double *miu0,
+                             const void *fdd, const void *cdd, const int *ExactStep, const int *Memory,
+                             const char *Method, orc_ffd_t f_fd, const int *Strong, const int *Warning,
+                             const int *MaxIteration, const double *Precision, const double *MinStepLength,
+                             const double *WolfeConst1, const double *WolfeConst2, const double *Increment,
+                             int len_solver, int len_Method);
+void orc_get_al_stats(orc_al_stats_t *out);
+/* the reference's test constraint (test.f90:692-705): unit sphere, cx(1) = dot_product(x,x) - 1, cdx(:,1) = 2 x */
+void orc_con_sphere_c(double *cx, const double *x, const int *M, const int *N);
+void orc_con_sphere_cd(double *cdx, const double *x, const int *M, const int *N);
 
 /* line searchers, f90:1286,1373,1462,1582 (exported like the reference's module procedures) */
 void orc_wolfe(const double *c1, const double *c2, orc_f_t f, orc_fd_t fd, double *x, double *a,

@@ -399,6 +399,92 @@ def steepest_descent(f, fd, x, f_fd=None, Strong=None, Warning=None, MaxIteratio
     return x, cnt
 
 
+# ----------------------------------------------------------------- AugmentedLagrangian f90:2005-2241
+def augmented_lagrangian(f, fd, c, cd, x, M, UnconstrainedSolver=None, lambda0=None, miu0=None, Memory=None,
+                         Method=None, f_fd=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
+                         MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None):
+    """Branches 'LBFGS' (f90:2150-2167) and 'ConjugateGradient' (f90:2168-2185) only.  c(x) -> ndarray (M,),
+    cd(x) -> ndarray (N, M).  Returns x, dict(outer, inner, trials, cnorm2, miu, status)."""
+    x = np.array(x, dtype=np.float64)
+    solver = "BFGS" if UnconstrainedSolver is None else UnconstrainedSolver
+    lam = np.zeros(M) if lambda0 is None else np.array(lambda0, dtype=np.float64)
+    miu = 1.0 if miu0 is None else max(1.0, miu0)
+    sw = True if Strong is None else bool(Strong)
+    warn = True if Warning is None else bool(Warning)
+    maxit = 1000 if MaxIteration is None else MaxIteration
+    tol = 1e-15 if Precision is None else Precision
+    minstep = 1e-15 if MinStepLength is None else MinStepLength
+    c1 = 1e-4 if WolfeConst1 is None else max(1e-15, WolfeConst1)
+    if WolfeConst2 is not None:
+        c2 = min(1.0 - 1e-15, max(c1 + 1e-15, WolfeConst2))
+    else:
+        c2 = 0.45 if solver == "ConjugateGradient" else 0.9
+    incrmt = 1.05 if Increment is None else Increment
+    mem = 10 if Memory is None else max(1, Memory)
+    typ = "DY" if Method is None else Method
+    tolsq = tol * tol
+    if solver not in ("LBFGS", "ConjugateGradient"):
+        raise SystemExit("oracle_np: AugmentedLagrangian is transcribed for LBFGS / ConjugateGradient only")
+    state = {"lam": lam, "miu": miu}
+
+    def terms(Lx, cx):                              # Lx - dot(lambda,cx) + miu/2*dot(cx,cx)
+        return Lx - dot(state["lam"], cx) + state["miu"] / 2.0 * dot(cx, cx)
+
+    def grad(Ldx, cx, cdx):                         # Ldx + matmul(cdx, miu*cx-lambda), ascending constraint index
+        w = state["miu"] * cx - state["lam"]
+        r = np.zeros_like(Ldx)
+        for j in range(M):
+            r = r + cdx[:, j] * w[j]
+        return Ldx + r
+
+    def L(xx):                                      # f90:2193-2199
+        return terms(f(xx), c(xx))
+
+    def Ld(xx):                                     # f90:2200-2206
+        g = fd(xx); cx = c(xx); cdx = cd(xx)
+        return grad(g, cx, cdx)
+
+    def L_Ld(xx):                                   # f90:2207-2217
+        Lx = f(xx); cx = c(xx); Lx = terms(Lx, cx)
+        g = fd(xx); cdx = cd(xx)
+        return Lx, grad(g, cx, cdx)
+
+    def L_Ld_fdwithf(xx):                           # f90:2218-2228
+        Lx, g = f_fd(xx); cx = c(xx); Lx = terms(Lx, cx)
+        return Lx, grad(g, cx, cd(xx))
+
+    out = {"outer": 0, "inner": 0, "trials": 0, "cnorm2": 0.0, "status": 2}
+    inner_ffd = L_Ld_fdwithf if f_fd is not None else L_Ld
+    for it in range(1, maxit + 1):
+        if solver == "LBFGS":
+            x, cnt = lbfgs(L, Ld, x, Memory=mem, f_fd=inner_ffd, Strong=sw, Warning=warn, MaxIteration=maxit,
+                           Precision=tol, MinStepLength=minstep, WolfeConst1=c1, WolfeConst2=c2, Increment=incrmt)
+        else:
+            x, cnt = conjugate_gradient(L, Ld, x, Method=typ, f_fd=inner_ffd, Strong=sw, Warning=warn,
+                                        MaxIteration=maxit, Precision=tol, MinStepLength=minstep, WolfeConst1=c1,
+                                        WolfeConst2=c2, Increment=incrmt)
+        out["outer"] = it; out["inner"] += cnt.iters; out["trials"] += cnt.trials
+        cx = c(x)
+        out["cnorm2"] = dot(cx, cx)
+        if out["cnorm2"] < tolsq:
+            out["status"] = 0
+            break
+        state["lam"] = state["lam"] - state["miu"] * cx
+        state["miu"] = state["miu"] * incrmt
+    out["miu"] = state["miu"]
+    return x, out
+
+
+def sphere_constraint():
+    """test.f90:692-705: cx(1) = dot_product(x,x) - 1, cdx(:,1) = 2 x."""
+    def c(x):
+        return np.array([dot(x, x) - 1.0])
+
+    def cd(x):
+        return (2.0 * x).reshape(-1, 1)
+    return c, cd
+
+
 # ----------------------------------------------------------------- objectives (same op order as objectives.c)
 def quartic():
     def f(x):

@@ -179,6 +179,42 @@ def sd(cbs, x, use_ffd=False, Strong=None, Warning=None, MaxIteration=None, Prec
     return x, stats()
 
 
+class ALStats(C.Structure):
+    _fields_ = [("outer_iterations", C.c_long), ("inner_iterations", C.c_long), ("trials", C.c_long),
+                ("status", C.c_int), ("cnorm2", C.c_double), ("miu", C.c_double)]
+
+
+def sphere_constraint():
+    L = lib()
+    return C.cast(L.orc_con_sphere_c, C.c_void_p), C.cast(L.orc_con_sphere_cd, C.c_void_p)
+
+
+def al(cbs, con, x, M=1, UnconstrainedSolver="LBFGS", lambda0=None, miu0=None, Memory=None, Method=None, use_ffd=False,
+       Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None, WolfeConst1=None,
+       WolfeConst2=None, Increment=None):
+    """orc_augmentedlagrangian (f90:2005-2241; LBFGS / ConjugateGradient branches)."""
+    L = lib()
+    f, fd, ffd = cbs
+    c, cd = con
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    n, m = C.c_int(x.size), C.c_int(M)
+    solver = UnconstrainedSolver.encode()
+    meth = None if Method is None else Method.encode()
+    lam = None if lambda0 is None else np.ascontiguousarray(lambda0, dtype=np.float64)
+    L.orc_augmentedlagrangian(f, fd, c, cd, x.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(m), solver,
+                              None if lam is None else lam.ctypes.data_as(C.c_void_p), _opt(C.c_double, miu0), None, None,
+                              None, _opt(C.c_int, Memory), meth, ffd if use_ffd else None,
+                              _opt(C.c_int, None if Strong is None else int(Strong)),
+                              _opt(C.c_int, None if Warning is None else int(Warning)),
+                              _opt(C.c_int, MaxIteration), _opt(C.c_double, Precision),
+                              _opt(C.c_double, MinStepLength), _opt(C.c_double, WolfeConst1),
+                              _opt(C.c_double, WolfeConst2), _opt(C.c_double, Increment),
+                              C.c_int(len(solver)), C.c_int(0 if meth is None else len(meth)))
+    st = ALStats()
+    L.orc_get_al_stats(C.byref(st))
+    return x, st
+
+
 def cg_basic(cbs, x, Method="DY", Strong=True, Warning=True, MaxIteration=1000, Precision=1e-15,
              MinStepLength=1e-15, WolfeConst1=1e-4, WolfeConst2=0.45, Increment=1.05, trace=None):
     L = lib()

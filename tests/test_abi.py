@@ -69,6 +69,9 @@ def test_struct_layout_matches_ctypes(tmp_path):
         "flgpu_iter_info": [f for f, _ in capi.IterInfo._fields_],
         "flgpu_eval_ctx": [f for f, _ in capi.EvalCtx._fields_],
         "flgpu_problem": [f for f, _ in capi.Problem._fields_],
+        "flgpu_constraints": [f for f, _ in capi.Constraints._fields_],
+        "flgpu_al_options": [f for f, _ in capi.ALOptions._fields_],
+        "flgpu_al_stats": [f for f, _ in capi.ALStats._fields_],
     }
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(void){"]
     for s, fs in fields.items():
@@ -81,7 +84,8 @@ def test_struct_layout_matches_ctypes(tmp_path):
     subprocess.run(["gcc", str(prog), "-o", str(exe)], check=True)
     got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
     mirror = {"flgpu_options": capi.Options, "flgpu_stats": capi.Stats, "flgpu_iter_info": capi.IterInfo,
-              "flgpu_eval_ctx": capi.EvalCtx, "flgpu_problem": capi.Problem}
+              "flgpu_eval_ctx": capi.EvalCtx, "flgpu_problem": capi.Problem, "flgpu_constraints": capi.Constraints,
+              "flgpu_al_options": capi.ALOptions, "flgpu_al_stats": capi.ALStats}
     for s, cls in mirror.items():
         assert int(got[s]) == C.sizeof(cls), s
         for f, _ in cls._fields_:

@@ -399,6 +399,77 @@ def test_fortran_abi_steepest_descent(fl):
         assert np.array_equal(x, xa, equal_nan=True) and st.iterations == s.n_iter and st.status == s.status
 
 
+# ----------------------------------------------------------------------------- AugmentedLagrangian
+@pytest.mark.parametrize("solver,kw", [("LBFGS", dict()), ("LBFGS", dict(Memory=5, miu0=4.0, lambda0=[0.3], Increment=1.3)),
+                                       ("ConjugateGradient", dict()), ("ConjugateGradient", dict(Method="PR"))])
+@pytest.mark.parametrize("n", [10, 4097])
+def test_augmented_lagrangian_vs_oracle(fl, solver, kw, n):
+    """f = sum x^4 on the unit sphere (the reference's own smoke case, test.f90:466-478, at dim 10 and larger):
+    lands on the sphere, same outer iteration count and multiplier growth as the oracle, minimiser to 1e-8."""
+    x0 = _cases.start("quartic", n)
+    xr, sr = O.al(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), O.sphere_constraint(), x0.copy(), UnconstrainedSolver=solver,
+                  use_ffd=True, Warning=False, MaxIteration=60, Precision=1e-10, **kw)
+    x = x0.copy()
+    st = fl.AugmentedLagrangian(fl.builtin_problem(fl.OBJ_QUARTIC), fl.builtin_constraints(), x, UnconstrainedSolver=solver,
+                                Warning=False, MaxIteration=60, Precision=1e-10, **kw)
+    assert st.status == 0 and sr.status == 0
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-9                      # "norm2(x)-1 should print close to 0"
+    assert st.outer_iterations == sr.outer_iterations and st.miu == sr.miu
+    assert _cases.rel(x, xr) < 1e-8
+    assert st.gpu_launches > 0
+
+
+def test_fortran_abi_augmented_lagrangian(fl):
+    """__nonlinearoptimization_MOD_augmentedlagrangian (hpp:369-392) with the built-in CUDA objective and constraint
+    in reference-ABI form (device pointers, host scalars), host x in/out; and with plain host callbacks."""
+    n = 10
+    L = fl.lib()
+    f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
+    L.flgpu_builtin_ref_callbacks(fl.OBJ_QUARTIC, C.byref(f), C.byref(fd), C.byref(ffd))
+    c, cd = fl.capi.REF_C_FN(), fl.capi.REF_CD_FN()
+    L.flgpu_builtin_ref_constraints(fl.CON_SPHERE, C.byref(c), C.byref(cd))
+    x0 = _cases.start("quartic", n)
+    for solver in (b"LBFGS", b"ConjugateGradient"):
+        xr, sr = O.al(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), O.sphere_constraint(), x0.copy(),
+                      UnconstrainedSolver=solver.decode(), use_ffd=True, Warning=False, MaxIteration=60, Precision=1e-10)
+        x = x0.copy()
+        L.__getattr__("__nonlinearoptimization_MOD_augmentedlagrangian")(
+            f, fd, c, cd, x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)), C.byref(C.c_int(1)), solver, None, None,
+            None, None, None, None, None, ffd, None, C.byref(C.c_int32(0)), C.byref(C.c_int(60)),
+            C.byref(C.c_double(1e-10)), None, None, None, None, C.c_int(len(solver)), C.c_int(0))
+        st = fl.capi.ALStats()
+        L.flgpu_last_al_stats(C.byref(st))
+        assert st.status == 0 and st.outer_iterations == sr.outer_iterations
+        assert abs(np.linalg.norm(x) - 1.0) < 1e-9 and _cases.rel(x, xr) < 1e-8
+    # host callbacks (the reference's own test functions, test.f90:630-705) staged by the library
+    def hf(fx, xp, dim):
+        v = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (dim[0],))
+        fx[0] = float(np.sum(v ** 4))
+
+    def hfd(gp, xp, dim):
+        v = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (dim[0],))
+        np.ctypeslib.as_array(C.cast(gp, C.POINTER(C.c_double)), (dim[0],))[:] = 4.0 * v ** 3
+
+    def hc(cx, xp, M, N):
+        v = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (N[0],))
+        cx[0] = float(np.dot(v, v)) - 1.0
+
+    def hcd(cdp, xp, M, N):
+        v = np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (N[0],))
+        np.ctypeslib.as_array(C.cast(cdp, C.POINTER(C.c_double)), (N[0],))[:] = 2.0 * v
+    keep = (fl.capi.REF_F_FN(hf), fl.capi.REF_FD_FN(hfd), fl.capi.REF_C_FN(hc), fl.capi.REF_CD_FN(hcd))
+    x = x0.copy()
+    L.flgpu_set_callback_space(fl.SPACE_HOST)
+    try:
+        L.__getattr__("__nonlinearoptimization_MOD_augmentedlagrangian")(
+            keep[0], keep[1], keep[2], keep[3], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)), C.byref(C.c_int(1)),
+            b"LBFGS", None, None, None, None, None, None, None, None, None, C.byref(C.c_int32(0)),
+            C.byref(C.c_int(60)), C.byref(C.c_double(1e-10)), None, None, None, None, C.c_int(5), C.c_int(0))
+    finally:
+        L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-9
+
+
 def test_cpp_dropin_program_runs(fl, tmp_path):
     """tests/link/cpp_dropin.cpp = the reference's test.cpp optimizer section with host callbacks."""
     exe = tmp_path / "cpp_dropin"

@@ -112,6 +112,32 @@ def test_sd_c_equals_numpy_bitwise(name, n, kw):
     assert c.status == s.status and c.trials == s.n_trials
 
 
+@pytest.mark.parametrize("solver,kw", [
+    ("LBFGS", dict()), ("LBFGS", dict(use_ffd=True, Memory=5)), ("ConjugateGradient", dict()),
+    ("ConjugateGradient", dict(Method="PR", use_ffd=True)), ("LBFGS", dict(miu0=4.0, lambda0=[0.3], Increment=1.3)),
+])
+def test_augmented_lagrangian_c_equals_numpy_bitwise(solver, kw):
+    """AugmentedLagrangian over LBFGS / CG (f90:2150-2185) on the reference's own smoke case
+    (test.f90:466-478: f = sum x^4 on the unit sphere, dim = 10): the two transcriptions agree bit for bit and
+    land on the sphere."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", False)
+    n = 10
+    x0 = _cases.start("quartic", n)
+    xa, st = O.al(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), O.sphere_constraint(), x0.copy(), UnconstrainedSolver=solver,
+                  use_ffd=use, Warning=False, MaxIteration=60, Precision=1e-10, **kw)
+    f, fd, ffd = N.quartic()
+    c, cd = N.sphere_constraint()
+    with np.errstate(all="ignore"):
+        xb, out = N.augmented_lagrangian(f, fd, c, cd, x0.copy(), 1, UnconstrainedSolver=solver, f_fd=ffd if use else None,
+                                         Warning=False, MaxIteration=60, Precision=1e-10, **kw)
+    assert np.array_equal(xa, xb)
+    assert (st.outer_iterations, st.inner_iterations, st.trials, st.status) == \
+        (out["outer"], out["inner"], out["trials"], out["status"])
+    assert st.cnorm2 == out["cnorm2"] and st.miu == out["miu"]
+    assert st.status == 0 and abs(np.linalg.norm(xa) - 1.0) < 1e-9      # "norm2(x)-1 should print close to 0"
+
+
 @pytest.mark.parametrize("case", sorted(_cases.TORTURE_1D))
 @pytest.mark.parametrize("method", ["DY", "PR"])
 def test_torture_1d_c_equals_numpy(case, method):
