@@ -9,14 +9,20 @@
 #ifndef NonlinearOptimization_flgpu_hpp
 #define NonlinearOptimization_flgpu_hpp
 
+#include <algorithm>
 #include <cstdint>
 #include <string>
+#include <vector>
 
 namespace FL { namespace NO {
 
 typedef void (*f_t)(double &, const double *, const int &);
 typedef void (*fd_t)(double *, const double *, const int &);
 typedef int (*f_fd_t)(double &, double *, const double *, const int &);
+typedef void (*c_t)(double *, const double *, const int &, const int &);    // c(cx, x, M, N)
+typedef void (*cd_t)(double *, const double *, const int &, const int &);   // cd(cdx(N,M), x, M, N)
+typedef int (*fdd_t)(double *, const double *, const int &);
+typedef int (*cdd_t)(double *, const double *, const int &, const int &);
 
 #ifdef __INTEL_COMPILER
 #define FLGPU_SYM(lower) nonlinearoptimization_mp_##lower##_
@@ -42,6 +48,14 @@ extern "C" {
         const double & Precision, const double & MinStepLength,
         const double & WolfeConst1, const double & WolfeConst2, const double & Increment,
         int len_Method);
+    void FLGPU_SYM(augmentedlagrangian)(
+        f_t f, fd_t fd, c_t c, cd_t cd, double * x, const int & N, const int & M,
+        const char * UnconstrainedSolver, const double * lambda0, const double & miu0,
+        fdd_t fdd, cdd_t cdd, const int & ExactStep, const int & Memory, const char * Method, f_fd_t f_fd,
+        const int32_t & Strong, const int32_t & Warning, const int & MaxIteration,
+        const double & Precision, const double & MinStepLength,
+        const double & WolfeConst1, const double & WolfeConst2, const double & Increment,
+        int len_UnconstrainedSolver, int len_Method);
     void FLGPU_SYM(lbfgs)(
         f_t f, fd_t fd, double * x, const int & dim, const int & Memory, f_fd_t f_fd,
         const int32_t & Strong, const int32_t & Warning, const int & MaxIteration,
@@ -94,6 +108,24 @@ inline void LBFGS(f_t f, fd_t fd, double * x, const int & dim, const int & Memor
     const double & WolfeConst1 = 1e-4, const double & WolfeConst2 = 0.9, const double & Increment = 1.05) {
     LBFGS(f, fd, nullptr, x, dim, Memory, Strong, Warning, MaxIteration, Precision, MinStepLength,
           WolfeConst1, WolfeConst2, Increment);
+}
+
+// AugmentedLagrangian (f90:2005), as reference hpp:514-545.  libflgpu serves UnconstrainedSolver = "LBFGS" and
+// "ConjugateGradient" (the default here is "LBFGS": the reference's default "BFGS" is a dense-Hessian solver outside
+// the GPU path); fdd / cdd are accepted for signature compatibility and ignored.
+inline void AugmentedLagrangian(f_t f, fd_t fd, f_fd_t f_fd, fdd_t fdd, c_t c, cd_t cd, cdd_t cdd,
+    double * x, const int & N, const int & M,
+    const std::string & UnconstrainedSolver = "LBFGS", std::vector<double> lambda0 = {}, const double & miu0 = 1.0,
+    const int & ExactStep = 20, const int & Memory = 10, const std::string & Method = "DY",
+    const bool & Strong = true, const bool & Warning = true,
+    const int & MaxIteration = 1000, const double & Precision = 1e-15, const double & MinStepLength = 1e-15,
+    const double & WolfeConst1 = 1e-4, double WolfeConst2 = 0.9, const double & Increment = 1.05) {
+    if (lambda0.empty()) lambda0.assign((size_t)M, 0.0);
+    const int32_t s = Strong ? -1 : 0, w = Warning ? -1 : 0;
+    if (UnconstrainedSolver == "ConjugateGradient" && WolfeConst2 == 0.9) WolfeConst2 = 0.45;   // hpp:536
+    FLGPU_SYM(augmentedlagrangian)(f, fd, c, cd, x, N, M, UnconstrainedSolver.c_str(), lambda0.data(), miu0,
+        fdd, cdd, ExactStep, Memory, Method.c_str(), f_fd, s, w, MaxIteration, Precision, MinStepLength,
+        WolfeConst1, WolfeConst2, Increment, (int)UnconstrainedSolver.size(), (int)Method.size());
 }
 
 } }

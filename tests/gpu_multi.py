@@ -118,6 +118,33 @@ def main():
             ok = ok and good
             x1.free()
         x.free()
+    # AugmentedLagrangian: the constraint values are exchanged inside the composed callbacks
+    na = 4096
+    lo_a, hi_a = na * rank // world, na * (rank + 1) // world
+    prob, con = fl.builtin_problem(fl.OBJ_QUARTIC), fl.builtin_constraints()
+    for solver in ("LBFGS", "ConjugateGradient"):
+        xa = fl.DeviceVector.start(fl.START_QUARTIC_U, hi_a - lo_a, seed=12345, offset=lo_a, n_global=na)
+        sa = fl.AugmentedLagrangian(prob, con, xa, UnconstrainedSolver=solver, Warning=False, MaxIteration=60,
+                                    Precision=1e-6, comm=comm, offset=lo_a, n_global=na)
+        t = torch.from_numpy(xa.numpy()).cuda()
+        parts = [torch.empty(na * (r + 1) // world - na * r // world, dtype=torch.float64, device="cuda") for r in range(world)]
+        for r in range(world):
+            buf = t if r == rank else parts[r]
+            dist.broadcast(buf, r)
+            parts[r] = buf.clone()
+        xg = torch.cat(parts).cpu().numpy()
+        if rank == 0:
+            x1 = fl.DeviceVector.start(fl.START_QUARTIC_U, na, seed=12345)
+            s1 = fl.AugmentedLagrangian(prob, con, x1, UnconstrainedSolver=solver, Warning=False, MaxIteration=60,
+                                        Precision=1e-6)
+            dx = np.linalg.norm(xg - x1.numpy()) / np.linalg.norm(x1.numpy())
+            good = (sa.status == 0 and s1.status == 0 and abs(np.linalg.norm(xg) - 1.0) < 1e-6
+                    and abs(sa.outer_iterations - s1.outer_iterations) <= 1 and dx < 1e-6 * na)
+            print(f"[{world} ranks] AugmentedLagrangian/{solver}: outer {sa.outer_iterations}/{s1.outer_iterations} "
+                  f"| |x|-1 = {abs(np.linalg.norm(xg) - 1.0):.1e} |dx| = {dx:.1e} -> {'OK' if good else 'FAIL'}", flush=True)
+            ok = ok and good
+            x1.free()
+        xa.free()
     fl.lib().flgpu_comm_destroy(comm)
     fl.lib().flgpu_comm_destroy(comm_nccl)
     okt = torch.tensor([int(ok)], device="cuda")
