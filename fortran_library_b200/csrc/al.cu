@@ -3,6 +3,8 @@
 // procedures over host-associated lambda, miu, cx, cdx (f90:2193-2228) and hands them to LBFGS / ConjugateGradient;
 // here they are device callbacks composed from the user's f, fd, f_fd, c, cd plus two small kernels, and x, the
 // Jacobian and the multipliers stay in HBM across the outer iterations.  "f90:" = NonlinearOptimization.f90.
+#include <dlfcn.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -331,18 +333,31 @@ void __nonlinearoptimization_MOD_augmentedlagrangian(
     const int32_t *Warning, const int *MaxIteration, const double *Precision, const double *MinStepLength,
     const double *WolfeConst1, const double *WolfeConst2, const double *Increment, int len_UnconstrainedSolver,
     int len_Method) {
-    (void)fdd; (void)cdd; (void)ExactStep;
-    require_device();
     const bool is_cg = str_is(UnconstrainedSolver, len_UnconstrainedSolver, "ConjugateGradient");
     if (!is_cg && !str_is(UnconstrainedSolver, len_UnconstrainedSolver, "LBFGS")) {
+        // 'BFGS' (the reference default) and 'NewtonRaphson' are dense-Hessian solvers outside the GPU hot path: hand
+        // the call to the next definition of this symbol (libFL linked or loaded after libflgpu), if there is one
+        typedef void (*next_fn)(flgpu_ref_f_fn, flgpu_ref_fd_fn, flgpu_ref_c_fn, flgpu_ref_cd_fn, double *, const int *,
+                                const int *, const char *, const double *, const double *, void *, void *, const int *,
+                                const int *, const char *, flgpu_ref_f_fd_fn, const int32_t *, const int32_t *,
+                                const int *, const double *, const double *, const double *, const double *,
+                                const double *, int, int);
+        next_fn next = (next_fn)dlsym(RTLD_NEXT, "__nonlinearoptimization_MOD_augmentedlagrangian");
+        if (next) {
+            next(f, fd, c, cd, x, N, M, UnconstrainedSolver, lambda0, miu0, fdd, cdd, ExactStep, Memory, Method, f_fd,
+                 Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment,
+                 len_UnconstrainedSolver, len_Method);
+            return;
+        }
         std::string name(UnconstrainedSolver ? UnconstrainedSolver : "BFGS",
                          UnconstrainedSolver ? (size_t)(len_UnconstrainedSolver > 0 ? len_UnconstrainedSolver : 0) : 4);
         std::printf(" Program abort: unconstrained solver %s is a dense-Hessian method outside the GPU hot path; "
-                    "libflgpu serves UnconstrainedSolver = LBFGS or ConjugateGradient (link libFL for the others)\n",
-                    name.c_str());
+                    "libflgpu serves UnconstrainedSolver = LBFGS or ConjugateGradient (link libFL after libflgpu for "
+                    "the others)\n", name.c_str());
         std::fflush(stdout);
         std::exit(1);
     }
+    require_device();
     flgpu_al_options o;
     flgpu_al_options_default(&o, is_cg ? FLGPU_AL_CG : FLGPU_AL_LBFGS);
     o.lambda0 = lambda0;

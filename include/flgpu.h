@@ -261,9 +261,10 @@ void __nonlinearoptimization_MOD_conjugategradient_basic(
     const int32_t *Strong, const int32_t *Warning, const int *MaxIteration, const double *Precision,
     const double *MinStepLength, const double *WolfeConst1, const double *WolfeConst2,
     const double *Increment, int len_Method);
-/* f90:2005-2008, hpp:369-392.  Only UnconstrainedSolver = 'LBFGS' / 'ConjugateGradient' run here; the dense-Hessian
- * solvers ('BFGS' -- the reference default --, 'NewtonRaphson') print a message and exit.  fdd, cdd, ExactStep are
- * accepted and ignored (they serve those solvers only). */
+/* f90:2005-2008, hpp:369-392.  UnconstrainedSolver = 'LBFGS' / 'ConjugateGradient' run here; the dense-Hessian
+ * solvers ('BFGS' -- the reference default --, 'NewtonRaphson') are forwarded to the next definition of this symbol
+ * (libFL linked after libflgpu) or, if there is none, print a message and exit.  fdd, cdd, ExactStep serve those
+ * solvers only. */
 void __nonlinearoptimization_MOD_augmentedlagrangian(
     flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_c_fn c, flgpu_ref_cd_fn cd, double *x, const int *N, const int *M,
     const char *UnconstrainedSolver, const double *lambda0, const double *miu0, void *fdd, void *cdd,
