@@ -125,6 +125,43 @@ int main() { double x[10] = {0.5}; FL::NO::ConjugateGradient(f, fd, x, 10); FL::
                     "-Wl,-rpath," + os.path.dirname(LIB)], check=True)
 
 
+def test_augmented_lagrangian_forwards_dense_solvers_to_libfl(tmp_path):
+    """UnconstrainedSolver = 'BFGS' / 'NewtonRaphson' are outside the GPU path: libflgpu hands the call to the next
+    definition of __nonlinearoptimization_MOD_augmentedlagrangian (libFL linked after it).  Needs no GPU."""
+    fake = tmp_path / "fakefl.c"
+    fake.write_text(
+        '#include <stdio.h>\n'
+        'void __nonlinearoptimization_MOD_augmentedlagrangian(void *f, void *fd, void *c, void *cd, double *x, const int *N,\n'
+        '    const int *M, const char *solver, const double *l0, const double *m0, void *fdd, void *cdd, const int *es,\n'
+        '    const int *mem, const char *meth, void *ffd, const int *s, const int *w, const int *mi, const double *p,\n'
+        '    const double *ms, const double *c1, const double *c2, const double *inc, int ls, int lm) {\n'
+        '    printf("libFL got %.*s N=%d M=%d\\n", ls, solver, *N, *M); x[0] = 42.0; }\n')
+    prog = tmp_path / "prog.cpp"
+    prog.write_text(
+        '#include <cstdio>\n#include "%s"\n'
+        'static void f(double &fx, const double *, const int &) { fx = 0; }\n'
+        'static void fd(double *, const double *, const int &) {}\n'
+        'static void c(double *, const double *, const int &, const int &) {}\n'
+        'int main() { double x[3] = {1, 2, 3};\n'
+        '  FL::NO::AugmentedLagrangian(f, fd, nullptr, nullptr, c, c, nullptr, x, 3, 1, "BFGS");\n'
+        '  std::printf("x0=%%g\\n", x[0]); return x[0] == 42.0 ? 0 : 1; }\n'
+        % os.path.join(ROOT, "include", "NonlinearOptimization_flgpu.hpp"))
+    libdir = os.path.join(ROOT, "fortran_library_b200")
+    subprocess.run(["gcc", "-shared", "-fPIC", str(fake), "-o", str(tmp_path / "libfakeFL.so")], check=True)
+    exe = tmp_path / "prog"
+    # --no-as-needed: this toy program needs nothing else from "libFL", a real one does (every other module)
+    subprocess.run(["g++", "-std=c++11", str(prog), "-o", str(exe), "-Wl,--no-as-needed", "-L" + libdir, "-lflgpu",
+                    "-L" + str(tmp_path), "-lfakeFL", "-Wl,-rpath," + libdir, "-Wl,-rpath," + str(tmp_path)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "libFL got BFGS N=3 M=1" in r.stdout, r.stdout + r.stderr
+    # without a libFL behind it: the message, exit status 1
+    exe2 = tmp_path / "prog2"
+    subprocess.run(["g++", "-std=c++11", str(prog), "-o", str(exe2), "-L" + libdir, "-lflgpu", "-Wl,-rpath," + libdir],
+                   check=True)
+    r = subprocess.run([str(exe2)], capture_output=True, text=True)
+    assert r.returncode == 1 and "dense-Hessian" in r.stdout
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device every compute entry point aborts with a message; nothing is computed on the
     CPU.  (Skipped on a GPU box, where the same call simply runs.)"""
