@@ -61,6 +61,8 @@ def main():
     cases = [("LBFGS m=5 Rosenbrock", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=5)),
              ("LBFGS m=10 Rosenbrock", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10)),
              ("LBFGS m=10 Rosenbrock, plain callbacks", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10, fused=False)),
+             ("LBFGS m=10 Rosenbrock, Increment=2 (a reference tunable; NOT the default)", "lbfgs", fl.OBJ_ROSENBROCK,
+              fl.START_ROSEN_PERT, 7, dict(Memory=10, Increment=2.0)),
              ("LBFGS m=30 diag-quadratic", "lbfgs", fl.OBJ_DIAGQUAD, fl.START_ZERO, 0, dict(Memory=30)),
              ("CG DY quartic", "cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY")),
              ("CG PR quartic", "cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="PR")),
@@ -77,7 +79,7 @@ def main():
                 print(f"2^{log2n} {label}: converged before the timed window", flush=True)
                 continue
             rows.append((log2n, label, r))
-            print(f"2^{log2n} {label:42s} {r['it_per_s']:8.2f} it/s  {r['trials_per_it']:5.1f} trials/it  "
+            print(f"2^{log2n} {label:48.48s} {r['it_per_s']:8.2f} it/s  {r['trials_per_it']:5.1f} trials/it  "
                   f"{r['GB_per_it']:7.1f} GB/it  {r['GBps']:7.0f} GB/s ({r['frac']:.0%} of measured)", flush=True)
     with open(a.out, "w") as fh:
         fh.write("| n | workload | it/s (wall) | trials/it | algorithmic GB/it | kernel ms/it | achieved GB/s | of measured 6467.7 |\n")

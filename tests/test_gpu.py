@@ -514,6 +514,9 @@ def test_edge_cases(fl):
         x = fl.DeviceVector.from_numpy(np.ones(10))
         st = fn(_problem(fl, "rosenR0"), x, Warning=False)
         assert st.status == fl.INITIAL_CONVERGED and st.iterations == 0 and np.array_equal(x.numpy(), np.ones(10))
+    for fn in (fl.LBFGS, fl.ConjugateGradient, fl.SteepestDescent):   # dim = 0: nothing to do, nothing to touch
+        st = fn(_problem(fl, "quartic"), np.zeros(0), Warning=False)
+        assert st.status == fl.INITIAL_CONVERGED and st.iterations == 0
     for n in (1, 2, 3, 7, 33, 1001):                            # tiny, odd, not a multiple of the vector width
         x0 = _cases.start("quartic", n)
         xr, sr = O.lbfgs(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Memory=4, Warning=False, MaxIteration=5)
