@@ -23,6 +23,10 @@ import sys
 import threading
 import time
 
+# rank 0 prints exactly ONE line on stdout (the JSON); NCCL's banner ("NCCL version ...", printed on stdout when
+# NCCL_DEBUG is VERSION or WARN) and any NCCL warning go to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
