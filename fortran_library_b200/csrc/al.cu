@@ -126,12 +126,11 @@ void sphere_cd(const flgpu_eval_ctx *ctx, double *cd_dev, const double *x, int m
 void ref_sphere_c(double *cx, const double *x, const int *M, const int *N) {
     (void)M;
     cudaStream_t s = (cudaStream_t)flgpu_current_stream();
-    double *tmp = (double *)flgpu_malloc(sizeof(double));
+    double *tmp = scratch_scalar(s) + 2;          // [0] is the f scalar of the built-in objectives
     flgpu_vec_dot(x, x, *N, tmp, s);
     double v = 0.0;
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(&v, tmp, sizeof(double), cudaMemcpyDeviceToHost, s));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
-    flgpu_free(tmp);
     cx[0] = v - 1.0;
 }
 void ref_sphere_cd(double *cdx, const double *x, const int *M, const int *N) {
@@ -319,7 +318,7 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
     ws_free(S.cglob, sizeof(double) * kMaxConstraints);
     ws_free(S.gather, sizeof(double) * kMaxConstraints * (size_t)(G > 1 ? G : 1));
     ws_free(S.cd_dev, sizeof(double) * (size_t)S.ld * (size_t)m);
-    if (own_stream) cudaStreamDestroy(s);
+    if (own_stream) { scratch_release(s); cudaStreamDestroy(s); }
     if (!cache_was_on) ws_set_enabled(false);       // returns the parked work space to the driver
     tls_al = A;
     if (stats) *stats = A;

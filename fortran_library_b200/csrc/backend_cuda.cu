@@ -302,7 +302,7 @@ CudaBackend::~CudaBackend() {
     if (host_pinned) cudaFreeHost(host_pinned);
     for (auto &pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
-    if (own_stream) cudaStreamDestroy(stream);
+    if (own_stream) { scratch_release(stream); cudaStreamDestroy(stream); }
 }
 
 double *CudaBackend::vec_alloc() {

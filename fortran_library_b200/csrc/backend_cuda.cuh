@@ -41,6 +41,10 @@ void ws_release();
 void ws_set_enabled(bool on);
 bool ws_is_enabled();
 
+// ---- per-stream scratch of the built-in objectives / primitives (objectives.cu)
+void scratch_release(cudaStream_t s);
+double *scratch_scalar(cudaStream_t s);   // device double[4] private to the stream
+
 // ---- NCCL (resolved with dlopen so single-GPU use has no NCCL dependency)
 void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s);
 // rank-ordered sum of `count` (<= k::kMailWidth) doubles over the communicator (backend_cuda.cu)

@@ -50,6 +50,22 @@ Scratch &scratch_for(cudaStream_t s) {
     return g_scratch.emplace(key, sc).first->second;
 }
 
+// Called when a library-owned stream is destroyed: its scratch would otherwise stay in the map forever.
+void scratch_release(cudaStream_t s) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    auto it = g_scratch.find(std::make_pair(dev, (void *)s));
+    if (it == g_scratch.end()) return;
+    cudaFree(it->second.work.partials);
+    cudaFree(it->second.work.ticket);
+    cudaFree(it->second.scalar);
+    cudaFreeHost(it->second.host_scalar);
+    cudaFree(it->second.tables);
+    g_scratch.erase(it);
+}
+double *scratch_scalar(cudaStream_t s) { return scratch_for(s).scalar; }
+
 namespace k {
 
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
