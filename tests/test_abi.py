@@ -107,8 +107,10 @@ def test_cpp_wrappers_link(tmp_path):
 @pytest.mark.skipif(not os.path.exists("/root/reference/cpp/NonlinearOptimization.hpp"),
                     reason="the reference tree is only mounted in the build container")
 def test_unmodified_reference_header_links(tmp_path):
-    """A program using the UNMODIFIED reference header's ConjugateGradient wrappers (hpp:414-454) links
-    against libflgpu.so: the binary drop-in claim for this path."""
+    """A program using the UNMODIFIED reference header's SteepestDescent, ConjugateGradient and AugmentedLagrangian
+    wrappers (hpp:395-454, 514-545) links against libflgpu.so: the binary drop-in claim for this path."""
+    if not os.path.exists("/root/reference/cpp/NonlinearOptimization.hpp"):
+        pytest.skip("the reference tree is not mounted here")
     _build()
     src = tmp_path / "ref_hdr.cpp"
     src.write_text(r'''
@@ -118,7 +120,11 @@ def test_unmodified_reference_header_links(tmp_path):
 static void f(double & fx, const double * x, const int & dim) { fx = 0; for (int i = 0; i < dim; i++) fx += x[i]*x[i]*x[i]*x[i]; }
 static void fd(double * g, const double * x, const int & dim) { for (int i = 0; i < dim; i++) g[i] = 4*x[i]*x[i]*x[i]; }
 static int f_fd(double & fx, double * g, const double * x, const int & dim) { f(fx, x, dim); fd(g, x, dim); return 0; }
-int main() { double x[10] = {0.5}; FL::NO::ConjugateGradient(f, fd, x, 10); FL::NO::ConjugateGradient(f, fd, f_fd, x, 10, "PR"); return 0; }
+static void c(double * cx, const double * x, const int & M, const int & N) { cx[0] = -1; for (int i = 0; i < N; i++) cx[0] += x[i]*x[i]; (void)M; }
+static void cd(double * cdx, const double * x, const int & M, const int & N) { for (int i = 0; i < N; i++) cdx[i] = 2*x[i]; (void)M; }
+int main() { double x[10] = {0.5}; FL::NO::ConjugateGradient(f, fd, x, 10); FL::NO::ConjugateGradient(f, fd, f_fd, x, 10, "PR");
+  FL::NO::SteepestDescent(f, fd, f_fd, x, 10);
+  FL::NO::AugmentedLagrangian(f, fd, f_fd, nullptr, c, cd, nullptr, x, 10, 1, "LBFGS"); return 0; }
 ''')
     exe = tmp_path / "ref_hdr"
     subprocess.run(["g++", "-std=c++11", str(src), "-o", str(exe), "-L" + os.path.dirname(LIB), "-lflgpu",

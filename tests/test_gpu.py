@@ -508,6 +508,17 @@ def test_row_sharded_nccl(fl):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_reference_header_program_runs(fl):
+    """tests/link/ref_header_prog: user code + the UNMODIFIED reference header (compiled by __graft_entry__.build()
+    where the reference tree is mounted), linked against libflgpu.so, run here with host callbacks."""
+    exe = os.path.join(ROOT, "tests", "link", "ref_header_prog")
+    if not os.path.exists(exe):
+        pytest.skip("tests/link/ref_header_prog was not built (reference header not mounted at build time)")
+    env = dict(os.environ, FLGPU_CALLBACK_SPACE="host")
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 # ----------------------------------------------------------------------------- edge cases
 def test_edge_cases(fl):
     for fn in (fl.LBFGS, fl.ConjugateGradient):                 # start at the minimiser (f90:443 / 237)
