@@ -25,6 +25,9 @@ import time
 
 # rank 0 prints exactly ONE line on stdout (the JSON); NCCL's banner ("NCCL version ...", printed on stdout when
 # NCCL_DEBUG is VERSION or WARN) and any NCCL warning go to stderr instead
+# (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION is raised to WARN)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
