@@ -375,6 +375,15 @@ extern "C" int flgpu_fill_start(int start_kind, uint64_t seed, double *x_dev, in
     return 0;
 }
 
+extern "C" int flgpu_reduction_workspace(void *stream, double **partials, unsigned int **ticket, int *max_blocks) {
+    require_device();
+    Scratch &sc = scratch_for((cudaStream_t)stream);
+    *partials = sc.work.partials;
+    *ticket = sc.work.ticket;
+    *max_blocks = k::kMaxGrid;
+    return 0;
+}
+
 extern "C" int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *out_dev, void *stream) {
     require_device();
     require_aligned16(a_dev, "flgpu_vec_dot: a"); require_aligned16(b_dev, "flgpu_vec_dot: b");

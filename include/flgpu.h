@@ -337,6 +337,11 @@ int flgpu_history_direction(flgpu_history *h, const double *g1_dev, const double
                             double *xt_dev, double *gp, double *pp);
 void flgpu_history_destroy(flgpu_history *h);
 
+/* Reduction work space private to `stream` (library-owned; valid until the stream's scratch is released): room
+ * for 8 partial sums from each of *max_blocks thread blocks, and the zero-initialised ticket counter of the
+ * "last block finishes" scheme.  Used by include/flgpu_objective.cuh; kernels sharing it must be stream-ordered. */
+int flgpu_reduction_workspace(void *stream, double **partials, unsigned int **ticket, int *max_blocks);
+
 /* ------------------------------------------------------------------ device memory helpers */
 /* Thin wrappers (cudaMalloc / cudaFree / cudaMemcpyAsync + stream sync) so that C, Fortran
  * (iso_c_binding) and ctypes callers need no CUDA runtime binding of their own. */

@@ -1,0 +1,207 @@
+// flgpu_objective.cuh -- write an objective once as a device functor, get all four libflgpu callbacks.
+//
+// The reference asks the user for f, fd and optionally f_fd (NonlinearOptimization.f90:33-43).  On the GPU those are
+// kernels, and the line search is fastest when the objective kernel also forms the trial point x0 + a*p itself
+// (flgpu_fused_fn, flgpu.h).  For objectives that are sums of terms over single elements or over pairs
+// (x_{2j}, x_{2j+1}) -- the quartic of the reference's own tests, extended Rosenbrock, diagonal quadratics, any
+// separable loss -- this header generates f, fd, f_fd AND the fused evaluation from one functor, with the library's
+// deterministic reduction (fixed per-thread order, shuffle butterfly, fixed-order sum over blocks by the last block).
+//
+//   struct Quartic {                                   // f = sum x^4 (test/test.f90:630-663)
+//       static constexpr int WIDTH = 1;                // 1: element-local, 2: pairs (x_{2j}, x_{2j+1})
+//       __device__ void eval(int64_t i, double x, double &f, double &g) const { f = x*x*x*x; g = 4*x*x*x; }
+//   };
+//   flgpu_problem prob = flgpu_obj::make_problem<Quartic>(&my_functor_on_the_host);   // keeps the pointer, not a copy
+//   flgpu_lbfgs(&prob, &opt, x, n, FLGPU_SPACE_DEVICE, &stats);
+//
+// WIDTH = 2 functors implement
+//       __device__ void eval2(int64_t i, double xa, double xb, double &f, double &ga, double &gb) const;   // i even
+//       __device__ void eval_tail(int64_t i, double x, double &f, double &g) const;                        // odd n
+// `i` is the GLOBAL index (row-sharded runs: ctx->offset + local index; shards start on even indices).  The functor
+// is passed to the kernels by value: keep it small and trivially copyable (pointers to device tables are fine).
+// Compile the including file with nvcc -std=c++17 for sm_100a and link libflgpu.so.  Vectors are 16-byte aligned (they are the
+// library's own work space).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#include "flgpu.h"
+
+namespace flgpu_obj {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block tree + last-block finish; out[i] receives accumulator i (fixed order: bitwise repeatable)
+template <int NACC>
+__device__ __forceinline__ void reduce_to(double (&acc)[NACC], double *(&out)[NACC], double *partials,
+                                          unsigned int *ticket) {
+    __shared__ double sh[NACC][kThreads / 32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; i++) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) sh[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
+        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < NACC) {
+        double s = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * NACC + warp]);
+        s = warp_sum(s);
+        if (lane == 0) *out[warp] = s;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+struct Args {
+    const double *x;      // the point, or x0 when FUSED
+    const double *p;      // FUSED
+    double a;             // FUSED
+    double *x_out, *g_out, *f_out, *gp_out;
+    int64_t n, offset;
+    double *partials;
+    unsigned int *ticket;
+};
+
+template <class Obj, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
+__global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a) {
+    double fsum = 0.0, gpsum = 0.0;
+    const int64_t nu = a.n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
+        double2 x = __ldg(reinterpret_cast<const double2 *>(a.x) + u), pv = make_double2(0.0, 0.0);
+        if (FUSED) {
+            pv = __ldg(reinterpret_cast<const double2 *>(a.p) + u);
+            x.x = __dadd_rn(x.x, __dmul_rn(a.a, pv.x));      // multiply, then add: the reference's x0+a*p (f90:1482)
+            x.y = __dadd_rn(x.y, __dmul_rn(a.a, pv.y));
+            if (WRITE_X) reinterpret_cast<double2 *>(a.x_out)[u] = x;
+        }
+        const int64_t i = a.offset + 2 * u;
+        double2 g;
+        if constexpr (Obj::WIDTH == 2) {
+            double f = 0.0;
+            obj.eval2(i, x.x, x.y, f, g.x, g.y);
+            if (WANT_F) fsum += f;
+        } else {
+            double f0 = 0.0, f1 = 0.0;
+            obj.eval(i, x.x, f0, g.x);
+            obj.eval(i + 1, x.y, f1, g.y);
+            if (WANT_F) { fsum += f0; fsum += f1; }
+        }
+        if (WRITE_G) reinterpret_cast<double2 *>(a.g_out)[u] = g;
+        if (WANT_GP) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
+    }
+    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // last element of an odd-length shard
+        const int64_t k = a.n - 1;
+        double x = a.x[k], pv = 0.0, f = 0.0, g = 0.0;
+        if (FUSED) {
+            pv = a.p[k];
+            x = __dadd_rn(x, __dmul_rn(a.a, pv));
+            if (WRITE_X) a.x_out[k] = x;
+        }
+        if constexpr (Obj::WIDTH == 2) obj.eval_tail(a.offset + k, x, f, g);
+        else obj.eval(a.offset + k, x, f, g);
+        if (WANT_F) fsum += f;
+        if (WRITE_G) a.g_out[k] = g;
+        if (WANT_GP) gpsum = fma(g, pv, gpsum);
+    }
+    if (WANT_F && WANT_GP) {
+        double acc[2] = {fsum, gpsum};
+        double *out[2] = {a.f_out, a.gp_out};
+        reduce_to<2>(acc, out, a.partials, a.ticket);
+    } else if (WANT_F) {
+        double acc[1] = {fsum};
+        double *out[1] = {a.f_out};
+        reduce_to<1>(acc, out, a.partials, a.ticket);
+    } else if (WANT_GP) {
+        double acc[1] = {gpsum};
+        double *out[1] = {a.gp_out};
+        reduce_to<1>(acc, out, a.partials, a.ticket);
+    }
+}
+
+template <class Obj>
+struct Callbacks {
+    template <bool FUSED, bool F, bool GP, bool WX, bool WG>
+    static void launch(const flgpu_eval_ctx *ctx, double *f_dev, double *gp_dev, double *x_out, double *g_out,
+                       const double *x, const double *p, double a, int64_t n) {
+        cudaStream_t s = (cudaStream_t)ctx->stream;
+        Args A;
+        int max_blocks = 0;
+        flgpu_reduction_workspace(ctx->stream, &A.partials, &A.ticket, &max_blocks);   // per-stream, library-owned
+        A.x = x; A.p = p; A.a = a; A.x_out = x_out; A.g_out = g_out; A.f_out = f_dev; A.gp_out = gp_dev;
+        A.n = n; A.offset = ctx->offset;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int64_t need = (n / 2 + kThreads) / kThreads, grid = (int64_t)sms * 4;       // one full wave of resident CTAs
+        if (grid > max_blocks) grid = max_blocks;
+        if (need < grid) grid = need < 1 ? 1 : need;
+        objective_kernel<Obj, FUSED, F, GP, WX, WG><<<(int)grid, kThreads, 0, s>>>(*(const Obj *)ctx->user, A);
+    }
+    static void f(const flgpu_eval_ctx *ctx, double *f_dev, const double *x, int64_t n) {
+        launch<false, true, false, false, false>(ctx, f_dev, nullptr, nullptr, nullptr, x, nullptr, 0.0, n);
+    }
+    static void fd(const flgpu_eval_ctx *ctx, double *g, const double *x, int64_t n) {
+        launch<false, false, false, false, true>(ctx, nullptr, nullptr, nullptr, g, x, nullptr, 0.0, n);
+    }
+    static void f_fd(const flgpu_eval_ctx *ctx, double *f_dev, double *g, const double *x, int64_t n) {
+        launch<false, true, false, false, true>(ctx, f_dev, nullptr, nullptr, g, x, nullptr, 0.0, n);
+    }
+    static void fused(const flgpu_eval_ctx *ctx, int flags, double *f_dev, double *gp_dev, double *x_out, double *g_out,
+                      const double *x0, const double *p, double a, int64_t n) {
+        switch (flags) {
+        case FLGPU_WANT_F | FLGPU_WANT_GP:
+            launch<true, true, true, false, false>(ctx, f_dev, gp_dev, nullptr, nullptr, x0, p, a, n); break;
+        case FLGPU_WANT_F:
+            launch<true, true, false, false, false>(ctx, f_dev, nullptr, nullptr, nullptr, x0, p, a, n); break;
+        case FLGPU_WANT_GP:
+            launch<true, false, true, false, false>(ctx, nullptr, gp_dev, nullptr, nullptr, x0, p, a, n); break;
+        case FLGPU_WRITE_X | FLGPU_WRITE_G:
+            launch<true, false, false, true, true>(ctx, nullptr, nullptr, x_out, g_out, x0, p, a, n); break;
+        case FLGPU_WRITE_G:
+            launch<true, false, false, false, true>(ctx, nullptr, nullptr, nullptr, g_out, x0, p, a, n); break;
+        case FLGPU_WRITE_X:
+            launch<true, false, false, true, false>(ctx, nullptr, nullptr, x_out, nullptr, x0, p, a, n); break;
+        case FLGPU_WANT_F | FLGPU_WANT_GP | FLGPU_WRITE_X | FLGPU_WRITE_G:
+            launch<true, true, true, true, true>(ctx, f_dev, gp_dev, x_out, g_out, x0, p, a, n); break;
+        default:
+            std::fprintf(stderr, "flgpu_obj: unsupported fused evaluation request %d\n", flags);
+            std::abort();
+        }
+    }
+};
+
+// `obj` must stay alive while the problem is in use (the callbacks read it through ctx->user).
+template <class Obj>
+inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool with_fused = true) {
+    flgpu_problem p;
+    p.f = Callbacks<Obj>::f;
+    p.fd = Callbacks<Obj>::fd;
+    p.f_fd = with_f_fd ? Callbacks<Obj>::f_fd : nullptr;
+    p.user = (void *)obj;
+    p.fused = with_fused ? Callbacks<Obj>::fused : nullptr;
+    return p;
+}
+
+}  // namespace flgpu_obj

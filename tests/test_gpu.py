@@ -399,6 +399,102 @@ def test_fortran_abi_steepest_descent(fl):
         assert np.array_equal(x, xa, equal_nan=True) and st.iterations == s.n_iter and st.status == s.status
 
 
+# ----------------------------------------------------------------------------- user objectives (flgpu_objective.cuh)
+def _np_user_objective(which, n):
+    """NumPy statement of tests/link/user_objective.cu (same operation order, no FMA)."""
+    if which == 0:
+        w = 1.0 + (np.arange(n) % 7).astype(np.float64)
+
+        def fg(x):
+            t = x - 1.0
+            t2 = t * t
+            return float(np.cumsum(w * (t2 * t2) + t2)[-1]), (4.0 * w) * (t2 * t) + 2.0 * t
+    else:
+        def fg(x):
+            a, b = x[0:n - n % 2:2], x[1::2]
+            t1, t2 = a - 2.0, b - a * a
+            terms = t1 * t1 + (5.0 * t2) * t2
+            g = np.empty(n)
+            g[0:n - n % 2:2] = 2.0 * t1 - (20.0 * a) * t2
+            g[1::2] = 10.0 * t2
+            f = float(np.cumsum(terms)[-1]) if terms.size else 0.0
+            if n % 2:
+                t = x[-1] - 2.0
+                f += float(t * t)
+                g[-1] = 2.0 * t
+            return f, g
+    return fg
+
+
+@pytest.fixture(scope="module")
+def user_objective_lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("user_objective") / "libuser_objective.so"
+    libdir = os.path.join(ROOT, "fortran_library_b200")
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler",
+                    "-fPIC", "-shared", "-o", str(out), os.path.join(ROOT, "tests", "link", "user_objective.cu"),
+                    "-L" + libdir, "-lflgpu", "-Xlinker", "-rpath," + libdir], check=True)
+    return C.CDLL(str(out))
+
+
+@pytest.mark.parametrize("which,n", [(0, 1000), (0, 1001), (1, 1000), (1, 777)])
+def test_user_objective_header(fl, user_objective_lib, which, n):
+    """include/flgpu_objective.cuh: one device functor -> f, fd, f_fd and the fused evaluation.  Gradients bit-exact
+    against the NumPy statement of the same formulas, and L-BFGS / CG on it (fused and plain) land where the oracle
+    lands with the same objective given as host callbacks."""
+    prob = fl.capi.Problem()
+    user_objective_lib.user_problem(which, C.byref(prob))
+    fg = _np_user_objective(which, n)
+    rng = np.random.default_rng(n + which)
+    x0 = rng.uniform(-0.5, 1.5, n)
+    # kernels vs NumPy
+    xd, gd, sc = fl.DeviceVector.from_numpy(x0), fl.DeviceVector(n), fl.DeviceVector(4)
+    ctx = fl.capi.EvalCtx(C.c_void_p(prob.user), None, 0, n, 0, 1, 0)
+    C.cast(prob.f_fd, fl.capi.F_FD_FN)(C.byref(ctx), sc.ptr, gd.ptr, xd.ptr, n)
+    f_ref, g_ref = fg(x0)
+    assert np.array_equal(gd.numpy(), g_ref)
+    assert abs(sc.numpy()[0] - f_ref) <= 1e-13 * abs(f_ref)
+    p = rng.standard_normal(n)
+    pd, xo, go = fl.DeviceVector.from_numpy(p), fl.DeviceVector(n), fl.DeviceVector(n)
+    W = fl.capi
+    C.cast(prob.fused, fl.capi.FUSED_FN)(C.byref(ctx), W.WANT_F | W.WANT_GP | W.WRITE_X | W.WRITE_G, sc.ptr, sc.ptr + 8,
+                                         xo.ptr, go.ptr, xd.ptr, pd.ptr, 0.125, n)
+    xt = x0 + 0.125 * p
+    ft, gt = fg(xt)
+    out = sc.numpy()
+    assert np.array_equal(xo.numpy(), xt) and np.array_equal(go.numpy(), gt)
+    assert abs(out[0] - ft) <= 1e-13 * abs(ft) and abs(out[1] - float(np.dot(gt, p))) <= 1e-12 * float(np.abs(gt * p).sum())
+    # optimizers vs the oracle on the same objective through host callbacks
+    def cf(fx, xp, dim):
+        fx[0] = fg(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (dim[0],)))[0]
+
+    def cfd(gp, xp, dim):
+        np.ctypeslib.as_array(C.cast(gp, C.POINTER(C.c_double)), (dim[0],))[:] = \
+            fg(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (dim[0],)))[1]
+
+    def cffd(fx, gp, xp, dim):
+        fv, gv = fg(np.ctypeslib.as_array(C.cast(xp, C.POINTER(C.c_double)), (dim[0],)))
+        fx[0] = fv
+        np.ctypeslib.as_array(C.cast(gp, C.POINTER(C.c_double)), (dim[0],))[:] = gv
+        return 0
+    keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+    cbs = tuple(C.cast(k, C.c_void_p) for k in keep)
+    tr = O.Trace(keep_vectors=False)
+    xr, sr = O.lbfgs(cbs, x0.copy(), use_ffd=True, Warning=False, MaxIteration=300, trace=tr)
+    for fused in (True, False):
+        x = x0.copy()
+        ob = fl.Observer()
+        st = fl.LBFGS(prob, x, Warning=False, MaxIteration=300, observer=ob, fused=fused)
+        assert _cases.rel(x, xr) < 1e-8 and st.status == sr.status
+        for k in range(5):                                   # same searches at the start: trial counts and f
+            assert ob.rows[k][4] == tr.rows[k][4] and abs(ob.rows[k][2] - tr.rows[k][2]) <= 1e-10 * abs(tr.rows[k][2])
+    xr, sr = O.cg(cbs, x0.copy(), Method="PR", use_ffd=True, Warning=False, MaxIteration=300)
+    x = x0.copy()
+    st = fl.ConjugateGradient(prob, x, Method="PR", Warning=False, MaxIteration=300)
+    assert _cases.rel(x, xr) < 1e-7
+
+
 # ----------------------------------------------------------------------------- AugmentedLagrangian (SURVEY 8f N2)
 @pytest.mark.parametrize("solver,kw", [("LBFGS", dict()), ("LBFGS", dict(Memory=5, miu0=4.0, lambda0=[0.3], Increment=1.3)),
                                        ("ConjugateGradient", dict()), ("ConjugateGradient", dict(Method="PR"))])
