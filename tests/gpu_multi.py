@@ -118,6 +118,51 @@ def main():
             ok = ok and good
             x1.free()
         x.free()
+    # the two-loop operator (flgpu_history_*) on row shards: K1's dots are rank-summed before K2
+    nh = 1 << 14
+    lo_h, hi_h = nh * rank // world, nh * (rank + 1) // world
+    rng = np.random.default_rng(5)
+    d = np.exp(rng.uniform(0, 1, nh))
+    L = fl.lib()
+    L.flgpu_history_create.restype = C.c_void_p
+    L.flgpu_history_create.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    L.flgpu_history_push.argtypes = [C.c_void_p] * 5
+    L.flgpu_history_direction.argtypes = [C.c_void_p] * 7
+    L.flgpu_history_destroy.argtypes = [C.c_void_p]
+    hs = L.flgpu_history_create(hi_h - lo_h, 6, None, comm)
+    h1 = L.flgpu_history_create(nh, 6, None, None) if rank == 0 else None
+    x0 = rng.standard_normal(nh)
+    worst = 0.0
+    for _ in range(9):
+        x1 = x0 + 0.1 * rng.standard_normal(nh)
+        sh = [fl.DeviceVector.from_numpy(v[lo_h:hi_h]) for v in (x1, x0, d * x1, d * x0)]
+        L.flgpu_history_push(hs, *[v.ptr for v in sh])
+        ps, xs = fl.DeviceVector(hi_h - lo_h), fl.DeviceVector(hi_h - lo_h)
+        gp, pp = C.c_double(), C.c_double()
+        L.flgpu_history_direction(hs, sh[2].ptr, sh[0].ptr, ps.ptr, xs.ptr, C.addressof(gp), C.addressof(pp))
+        t = torch.from_numpy(ps.numpy()).cuda()
+        parts = []
+        for r in range(world):
+            buf = t if r == rank else torch.empty(nh * (r + 1) // world - nh * r // world, dtype=torch.float64, device="cuda")
+            dist.broadcast(buf, r)
+            parts.append(buf.clone())
+        pg = torch.cat(parts).cpu().numpy()
+        if rank == 0:
+            fu = [fl.DeviceVector.from_numpy(v) for v in (x1, x0, d * x1, d * x0)]
+            L.flgpu_history_push(h1, *[v.ptr for v in fu])
+            p1, xt1 = fl.DeviceVector(nh), fl.DeviceVector(nh)
+            gp1, pp1 = C.c_double(), C.c_double()
+            L.flgpu_history_direction(h1, fu[2].ptr, fu[0].ptr, p1.ptr, xt1.ptr, C.addressof(gp1), C.addressof(pp1))
+            worst = max(worst, np.linalg.norm(pg - p1.numpy()) / np.linalg.norm(p1.numpy()),
+                        abs(gp.value - gp1.value) / abs(gp1.value), abs(pp.value - pp1.value) / abs(pp1.value))
+        x0 = x1
+    L.flgpu_history_destroy(hs)
+    if rank == 0:
+        L.flgpu_history_destroy(h1)
+        good = worst < 1e-12
+        print(f"[{world} ranks] two-loop operator on shards vs 1 GPU: worst relative difference {worst:.2e} -> "
+              f"{'OK' if good else 'FAIL'}", flush=True)
+        ok = ok and good
     # AugmentedLagrangian: the constraint values are exchanged inside the composed callbacks
     na = 4096
     lo_a, hi_a = na * rank // world, na * (rank + 1) // world

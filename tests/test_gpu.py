@@ -604,6 +604,41 @@ def test_row_sharded_nccl(fl):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_fortran_abi_device_x_and_stream_sync_mode(fl):
+    """Two switches of the drop-in layer: x handed over as a DEVICE pointer (flgpu_set_x_space) gives the same bits
+    as host x; FLGPU_SYNC=stream (cudaStreamSynchronize per round trip instead of the polled flag) gives the same bits
+    as the default -- both only change how results travel, never what is computed."""
+    n = 4097
+    L = fl.lib()
+    f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
+    L.flgpu_builtin_ref_callbacks(fl.OBJ_ROSENBROCK, C.byref(f), C.byref(fd), C.byref(ffd))
+    sym = L.__getattr__("__nonlinearoptimization_MOD_lbfgs")
+
+    def call(xptr):
+        sym(f, fd, C.c_void_p(xptr), C.byref(C.c_int(n)), C.byref(C.c_int(7)), ffd, None, C.byref(C.c_int32(0)),
+            C.byref(C.c_int(25)), None, None, None, None, None)
+    xh = _cases.start("rosenR1", n)
+    call(xh.ctypes.data)
+    xd = _dev_start(fl, "rosenR1", n)
+    L.flgpu_set_x_space(fl.SPACE_DEVICE)
+    try:
+        call(xd.ptr)
+    finally:
+        L.flgpu_set_x_space(fl.SPACE_HOST)
+    assert np.array_equal(xd.numpy(), xh)
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\nimport numpy as np, fortran_library_b200 as fl\n"
+            "x = fl.DeviceVector.start(fl.START_ROSEN_PERT, %d, seed=7)\n"
+            "fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=7, Warning=False, MaxIteration=25)\n"
+            "np.save(sys.argv[1], x.numpy())\n" % (ROOT, os.path.join(ROOT, "tests"), n))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "x.npy")
+        r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, FLGPU_SYNC="stream"),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert np.array_equal(np.load(out), xh)
+
+
 def test_reference_header_program_runs(fl):
     """tests/link/ref_header_prog: user code + the UNMODIFIED reference header (compiled by __graft_entry__.build()
     where the reference tree is mounted), linked against libflgpu.so, run here with host callbacks."""
