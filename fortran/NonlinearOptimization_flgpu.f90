@@ -1,6 +1,6 @@
 !Fortran host side of libflgpu.so: a module with the reference's own procedure names, argument order,
 !optional arguments and defaults for the hot path (reference: source/NonlinearOptimization.f90
-!LBFGS 398-400, ConjugateGradient 193-195, ConjugateGradient_basic 2249-2251), so that a program
+!LBFGS 398-400, ConjugateGradient 193-195, SteepestDescent 55-56), so that a program
 !written against `use NonlinearOptimization` switches to the B200 path by compiling against this
 !module and linking -lflgpu instead of -lFL.  Host control flow stays in the library's C++ driver;
 !this file only maps Fortran OPTIONAL / LOGICAL / CHARACTER(*) onto the iso_c_binding C-ABI of
@@ -26,6 +26,15 @@ module NonlinearOptimization_flgpu
             type(c_ptr), value :: Memory, Strong, Warning, MaxIteration, Precision, MinStepLength, &
                 WolfeConst1, WolfeConst2, Increment
         end subroutine flgpu_lbfgs_ref
+        subroutine flgpu_sd_ref(f, fd, x, dim, f_fd, Strong, Warning, MaxIteration, Precision, &
+                MinStepLength, WolfeConst1, WolfeConst2, Increment) bind(C, name='__nonlinearoptimization_MOD_steepestdescent')
+            import :: c_funptr, c_ptr, c_int, c_double
+            type(c_funptr), value :: f, fd, f_fd
+            real(c_double), dimension(*), intent(inout) :: x
+            integer(c_int), intent(in) :: dim
+            type(c_ptr), value :: Strong, Warning, MaxIteration, Precision, MinStepLength, &
+                WolfeConst1, WolfeConst2, Increment
+        end subroutine flgpu_sd_ref
         subroutine flgpu_cg_ref(f, fd, x, dim, Method, f_fd, Strong, Warning, MaxIteration, Precision, &
                 MinStepLength, WolfeConst1, WolfeConst2, Increment, len_Method) &
                 bind(C, name='__nonlinearoptimization_MOD_conjugategradient')
@@ -72,6 +81,25 @@ contains
             iptr(MaxIteration), dptr(Precision), dptr(MinStepLength), dptr(WolfeConst1), dptr(WolfeConst2), &
             dptr(Increment))
     end subroutine LBFGS
+
+    !Same dummy-argument list as the reference's SteepestDescent (f90:55-56)
+    subroutine SteepestDescent(f, fd, x, dim, f_fd, Strong, Warning, MaxIteration, Precision, MinStepLength, &
+            WolfeConst1, WolfeConst2, Increment)
+        external :: f, fd
+        integer, external, optional :: f_fd
+        integer, intent(in) :: dim
+        real*8, dimension(dim), intent(inout), target :: x
+        integer, intent(in), optional, target :: MaxIteration
+        logical, intent(in), optional :: Strong, Warning
+        real*8, intent(in), optional, target :: Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment
+        integer(c_int), target :: istrong, iwarning
+        type(c_funptr) :: cffd
+        type(c_ptr) :: pstrong, pwarning
+        cffd = c_null_funptr; if (present(f_fd)) cffd = c_funloc(f_fd)
+        call logical_arg(Strong, istrong, pstrong); call logical_arg(Warning, iwarning, pwarning)
+        call flgpu_sd_ref(c_funloc(f), c_funloc(fd), x, dim, cffd, pstrong, pwarning, iptr(MaxIteration), &
+            dptr(Precision), dptr(MinStepLength), dptr(WolfeConst1), dptr(WolfeConst2), dptr(Increment))
+    end subroutine SteepestDescent
 
     !Same dummy-argument list as the reference's ConjugateGradient (f90:193-195)
     subroutine ConjugateGradient(f, fd, x, dim, Method, f_fd, Strong, Warning, MaxIteration, Precision, &
