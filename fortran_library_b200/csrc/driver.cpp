@@ -13,6 +13,7 @@
 //    the convergence tests of After() are applied to the scalars that chain returns.
 // Every branch, comparison, default and exit test follows the reference statement by statement.
 #include "driver.hpp"
+#include "search_core.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -48,21 +49,16 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
 
 namespace {
 
-// One line search along p from x0 (device buffers); trial points go to xt, trial gradients to gt.
-struct Search {
+// One line search along p from x0 (device buffers); trial points go to xt, trial gradients to gt.  The reference's
+// control flow is SearchCore (search_core.hpp); this class supplies the evaluations: asynchronous kernels plus one
+// host round trip whenever a value steers a branch.
+struct Search : SearchCore<Search> {
     Backend &B;
     flgpu_stats &st;
     const double *x0;
     double *xt, *gt;
     const double *p;
-    double c1, c2abs, fx0, phid0, incr;
-    bool fdwithf;
-    double a;              // Fortran `a`
     int64_t trials = 0;
-    // the first trial may already have been formed/evaluated by the caller's chain:
-    // 0 nothing, 2 x formed and f known, 3 x formed, f, f' and f'.p known
-    int pre = 0;
-    double pre_f = 0.0, pre_gp = 0.0;
 
     Search(Backend &b, flgpu_stats &s) : B(b), st(s) {}
 
@@ -77,6 +73,7 @@ struct Search {
     }
     double fx() { if (f_pending) sync(); return fx_; }
     void set_fx(double v) { f_pending = false; fx_ = v; }
+    void count_f_only() { st.n_f_only_trials++; }
 
     // Fused mode (flgpu_fused_fn): a trial point exists only as its step a_x until the search returns;
     // each callback of the reference becomes one probe kernel that forms x0+a_x*p on the fly, and
@@ -104,7 +101,6 @@ struct Search {
         else B.eval_fg(xt, gt);
         st.n_f_fd++; f_pending = true;
     }
-    void both() { if (fdwithf) call_ffd(); else { call_f(); call_fd(); } }
     double slope() {                                                                 // dot_product(fdx,p)
         if (!fused) B.dot(gt, p, SL_GP);       // fused: f'.p was reduced by the probe that evaluated f'
         sync();
@@ -123,167 +119,6 @@ struct Search {
         } else {                               // never taken by the reference's searchers; kept for fidelity
             if (have_x) B.trial_x(xt, x0, p, a_x);
             if (have_g) B.fused_eval(FLGPU_WRITE_G, a_g, x0, p, nullptr, gt);
-        }
-    }
-    bool armijo_violated() { return fx() > fx0 + c1 * a * phid0; }
-    static bool collapsed(double low, double up) {
-        return std::fabs(up - low) < 1e-15 ||
-               std::fabs(up - low) / std::fmax(std::fabs(low), std::fabs(up)) < 1e-15;
-    }
-
-    // ---------------- Wolfe / Wolfe_fdwithf, f90:1286-1459 (quadratic zoom f90:1347-1370)
-    void wolfe_zoom(double &low, double &up, double &flow, double &fup, double &phidlow) {
-        double phidlow_m_a = phidlow * a;
-        for (;;) {
-            a = phidlow_m_a * a / 2.0 / (flow + phidlow_m_a - fup);
-            if (!(a > low && a < up)) a = (low + up) / 2.0;
-            form(a); call_f();
-            if (armijo_violated()) {
-                up = a;
-                if (up - low < 1e-15 || (up - low) / std::fmax(std::fabs(low), std::fabs(up)) < 1e-15) {
-                    call_fd(); return;
-                }
-                fup = fx();
-            } else {
-                call_fd();
-                const double phidnew = slope();
-                if (phidnew > c2abs) return;
-                low = a;
-                if (up - low < 1e-15 || (up - low) / std::fmax(std::fabs(low), std::fabs(up)) < 1e-15) return;
-                flow = fx(); phidlow = phidnew; phidlow_m_a = phidlow * a;
-            }
-        }
-    }
-    void wolfe() {
-        double aold, fold, atemp, ftemp, phidx;
-        if (pre == 0) { form(a); call_f(); } else { adopt_pre(); }                   // f90:1306
-        if (!armijo_violated()) {
-            for (;;) {
-                aold = a; fold = fx();
-                a = aold * incr; form(a); call_f();
-                if (armijo_violated()) {
-                    form(aold);                                                      // f90:1312
-                    call_fd();
-                    phidx = slope();
-                    if (phidx > c2abs) {
-                        a = aold; set_fx(fold);
-                    } else {
-                        atemp = a; ftemp = fx();
-                        wolfe_zoom(aold, atemp, fold, ftemp, phidx);
-                    }
-                    return;
-                }
-            }
-        } else {
-            for (;;) {
-                aold = a; fold = fx();
-                a = aold / incr; form(a); call_f();
-                if (!armijo_violated()) {
-                    call_fd();
-                    phidx = slope();
-                    if (phidx < c2abs) {
-                        atemp = a; ftemp = fx();
-                        wolfe_zoom(atemp, aold, ftemp, fold, phidx);
-                    }
-                    return;
-                }
-                if (a < 1e-15) { call_fd(); return; }
-            }
-        }
-    }
-
-    // ---------------- StrongWolfe / StrongWolfe_fdwithf, f90:1462-1698 (cubic zoom f90:1557-1579)
-    // The six zoom arguments alias the caller's locals exactly as the Fortran by-reference dummies do.
-    void strong_zoom(double &low, double &up, double &flow, double &fup, double &phidlow, double &phidup) {
-        for (;;) {
-            double d1 = phidlow + phidup - 3.0 * (flow - fup) / (low - up);
-            double d2 = up - low;
-            if (d2 > 0.0) d2 = std::sqrt(d1 * d1 - phidlow * phidup);
-            else d2 = -std::sqrt(d1 * d1 - phidlow * phidup);
-            a = up - (up - low) * (phidup + d2 - d1) / (phidup - phidlow + 2.0 * d2);
-            if (!(a > std::fmin(low, up) && a < std::fmax(low, up))) a = (low + up) / 2.0;
-            form(a); both();
-            const double phidnew = slope();
-            if (armijo_violated() || fx() >= flow) {
-                up = a; fup = fx(); phidup = phidnew;
-            } else {
-                if (std::fabs(phidnew) <= c2abs) return;
-                if (phidnew * (up - low) >= 0.0) { up = low; fup = flow; phidup = phidlow; }
-                low = a; flow = fx(); phidlow = phidnew;
-            }
-            if (collapsed(low, up)) return;
-        }
-    }
-    void strongwolfe() {
-        double aold = 0, fold = 0, atemp, ftemp, phidnew, phidold = 0;
-        if (pre == 0) {                                                  // f90:1482 / 1604
-            form(a);
-            if (fdwithf) call_ffd(); else call_f();
-        } else {
-            adopt_pre();
-        }
-        if (!armijo_violated()) {
-            if (!fdwithf) call_fd();
-            phidnew = (pre == 3) ? pre_gp : slope();
-            if (phidnew > 0.0) {
-                if (std::fabs(phidnew) <= c2abs) return;
-                for (;;) {                                               // f90:1488-1497
-                    aold = a; fold = fx(); phidold = phidnew;
-                    a = aold / incr; form(a); both(); phidnew = slope();
-                    if (fx() >= fold || phidnew <= 0.0) {
-                        atemp = a; ftemp = fx();
-                        strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
-                        return;
-                    }
-                    if (a < 1e-15) return;
-                }
-            } else {
-                for (;;) {                                               // f90:1499-1515
-                    aold = a; fold = fx(); phidold = phidnew;
-                    a = aold * incr; form(a); both(); phidnew = slope();
-                    if (armijo_violated() || fx() >= fold) {
-                        atemp = a; ftemp = fx();
-                        strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
-                        return;
-                    }
-                    if (phidnew > 0.0) {
-                        if (std::fabs(phidnew) <= c2abs) return;
-                        atemp = a; ftemp = fx();
-                        strong_zoom(atemp, aold, ftemp, fold, phidnew, phidold);
-                        if (fdwithf) return;                             // f90:1632
-                        set_fx(fx0);                                     // f90:1512 (no return there)
-                    }
-                }
-            }
-        } else {                                                         // f90:1517-1546
-            for (;;) {
-                aold = a; fold = fx();
-                a = aold / incr; form(a); call_f();
-                st.n_f_only_trials++;
-                if (!armijo_violated()) {
-                    call_fd();
-                    phidnew = slope();
-                    if (std::fabs(phidnew) <= c2abs) return;
-                    if (phidnew < 0.0) {
-                        form(aold); call_fd(); phidold = slope();        // f90:1526
-                        atemp = a; ftemp = fx();
-                        strong_zoom(atemp, aold, ftemp, fold, phidnew, phidold);
-                        return;
-                    } else {
-                        for (;;) {
-                            aold = a; fold = fx(); phidold = phidnew;
-                            a = aold / incr; form(a); both(); phidnew = slope();
-                            if (fx() >= fold || phidnew <= 0.0) {
-                                atemp = a; ftemp = fx();
-                                strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
-                                return;
-                            }
-                            if (a < 1e-15) return;
-                        }
-                    }
-                }
-                if (a < 1e-15) { call_fd(); return; }
-            }
         }
     }
 };

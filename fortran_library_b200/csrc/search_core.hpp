@@ -1,0 +1,218 @@
+// search_core.hpp -- the reference's line searchers as ONE piece of source for the host driver and for device code.
+//
+// Wolfe / Wolfe_fdwithf (f90:1286-1459, quadratic zoom f90:1347-1370) and StrongWolfe / StrongWolfe_fdwithf
+// (f90:1462-1698, cubic zoom f90:1557-1579) of NonlinearOptimization.f90, statement by statement.  The control flow
+// lives here once; WHERE a trial point is formed and evaluated is supplied by the derived class (CRTP):
+//     form(step)            x = x0 + step*p                         (f90:1482 and every later trial)
+//     call_f / call_fd / call_ffd                                   the user callbacks
+//     slope()               dot_product(fdx, p) at the last gradient
+//     fx() / set_fx(v)      Fortran `fx` (may be fetched lazily)
+//     adopt_pre()           the first trial was already formed/evaluated by the caller's chain (pre != 0)
+//     count_f_only()        statistics hook (branch D's f-only probes, f90:1518-1520)
+// driver.cpp derives the host version (asynchronous kernels + one host round trip per evaluation); a device kernel can
+// derive a version whose evaluations are grid-wide cooperative reductions.  Arithmetic that the host compiles without
+// FMA contraction (-ffp-contract=off) is written with nf_mul / nf_add so device code rounds identically.
+#pragma once
+#include <cmath>
+
+#ifdef __CUDACC__
+#define FLGPU_SC_HD __host__ __device__
+#else
+#define FLGPU_SC_HD
+#endif
+
+namespace flgpu {
+
+FLGPU_SC_HD inline double nf_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+FLGPU_SC_HD inline double nf_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+template <class Derived>
+struct SearchCore {
+    double c1 = 0.0, c2abs = 0.0, fx0 = 0.0, phid0 = 0.0, incr = 0.0;
+    bool fdwithf = false;
+    double a = 0.0;        // Fortran `a`
+    // the first trial may already have been formed/evaluated by the caller's chain:
+    // 0 nothing, 2 x formed and f known, 3 x formed, f, f' and f'.p known
+    int pre = 0;
+    double pre_f = 0.0, pre_gp = 0.0;
+
+    FLGPU_SC_HD Derived &self() { return *static_cast<Derived *>(this); }
+    FLGPU_SC_HD void both() { if (fdwithf) self().call_ffd(); else { self().call_f(); self().call_fd(); } }
+    // fx > fx0 + c1*a*phid0
+    FLGPU_SC_HD bool armijo_violated() { return self().fx() > nf_add(fx0, nf_mul(nf_mul(c1, a), phid0)); }
+    FLGPU_SC_HD static bool collapsed(double low, double up) {
+        return fabs(up - low) < 1e-15 || fabs(up - low) / fmax(fabs(low), fabs(up)) < 1e-15;
+    }
+
+    // ---------------- Wolfe / Wolfe_fdwithf, f90:1286-1459 (quadratic zoom f90:1347-1370)
+    FLGPU_SC_HD void wolfe_zoom(double &low, double &up, double &flow, double &fup, double &phidlow) {
+        double phidlow_m_a = nf_mul(phidlow, a);
+        for (;;) {
+            a = nf_mul(phidlow_m_a, a) / 2.0 / nf_add(nf_add(flow, phidlow_m_a), -fup);
+            if (!(a > low && a < up)) a = (low + up) / 2.0;
+            self().form(a); self().call_f();
+            if (armijo_violated()) {
+                up = a;
+                if (up - low < 1e-15 || (up - low) / fmax(fabs(low), fabs(up)) < 1e-15) {
+                    self().call_fd(); return;
+                }
+                fup = self().fx();
+            } else {
+                self().call_fd();
+                const double phidnew = self().slope();
+                if (phidnew > c2abs) return;
+                low = a;
+                if (up - low < 1e-15 || (up - low) / fmax(fabs(low), fabs(up)) < 1e-15) return;
+                flow = self().fx(); phidlow = phidnew; phidlow_m_a = nf_mul(phidlow, a);
+            }
+        }
+    }
+    FLGPU_SC_HD void wolfe() {
+        double aold, fold, atemp, ftemp, phidx;
+        if (pre == 0) { self().form(a); self().call_f(); } else { self().adopt_pre(); }          // f90:1306
+        if (!armijo_violated()) {
+            for (;;) {
+                aold = a; fold = self().fx();
+                a = nf_mul(aold, incr); self().form(a); self().call_f();
+                if (armijo_violated()) {
+                    self().form(aold);                                               // f90:1312
+                    self().call_fd();
+                    phidx = self().slope();
+                    if (phidx > c2abs) {
+                        a = aold; self().set_fx(fold);
+                    } else {
+                        atemp = a; ftemp = self().fx();
+                        wolfe_zoom(aold, atemp, fold, ftemp, phidx);
+                    }
+                    return;
+                }
+            }
+        } else {
+            for (;;) {
+                aold = a; fold = self().fx();
+                a = aold / incr; self().form(a); self().call_f();
+                if (!armijo_violated()) {
+                    self().call_fd();
+                    phidx = self().slope();
+                    if (phidx < c2abs) {
+                        atemp = a; ftemp = self().fx();
+                        wolfe_zoom(atemp, aold, ftemp, fold, phidx);
+                    }
+                    return;
+                }
+                if (a < 1e-15) { self().call_fd(); return; }
+            }
+        }
+    }
+
+    // ---------------- StrongWolfe / StrongWolfe_fdwithf, f90:1462-1698 (cubic zoom f90:1557-1579)
+    // The six zoom arguments alias the caller's locals exactly as the Fortran by-reference dummies do.
+    FLGPU_SC_HD void strong_zoom(double &low, double &up, double &flow, double &fup, double &phidlow, double &phidup) {
+        for (;;) {
+            double d1 = nf_add(nf_add(phidlow, phidup), -(nf_mul(3.0, flow - fup) / (low - up)));
+            double d2 = up - low;
+            const double disc = nf_add(nf_mul(d1, d1), -nf_mul(phidlow, phidup));
+            if (d2 > 0.0) d2 = sqrt(disc);
+            else d2 = -sqrt(disc);
+            a = nf_add(up, -(nf_mul(up - low, nf_add(nf_add(phidup, d2), -d1)) /
+                             nf_add(nf_add(phidup, -phidlow), nf_mul(2.0, d2))));
+            if (!(a > fmin(low, up) && a < fmax(low, up))) a = (low + up) / 2.0;
+            self().form(a); both();
+            const double phidnew = self().slope();
+            if (armijo_violated() || self().fx() >= flow) {
+                up = a; fup = self().fx(); phidup = phidnew;
+            } else {
+                if (fabs(phidnew) <= c2abs) return;
+                if (nf_mul(phidnew, up - low) >= 0.0) { up = low; fup = flow; phidup = phidlow; }
+                low = a; flow = self().fx(); phidlow = phidnew;
+            }
+            if (collapsed(low, up)) return;
+        }
+    }
+    FLGPU_SC_HD void strongwolfe() {
+        double aold = 0, fold = 0, atemp, ftemp, phidnew, phidold = 0;
+        if (pre == 0) {                                                  // f90:1482 / 1604
+            self().form(a);
+            if (fdwithf) self().call_ffd(); else self().call_f();
+        } else {
+            self().adopt_pre();
+        }
+        if (!armijo_violated()) {
+            if (!fdwithf) self().call_fd();
+            phidnew = (pre == 3) ? pre_gp : self().slope();
+            if (phidnew > 0.0) {
+                if (fabs(phidnew) <= c2abs) return;
+                for (;;) {                                               // f90:1488-1497
+                    aold = a; fold = self().fx(); phidold = phidnew;
+                    a = aold / incr; self().form(a); both(); phidnew = self().slope();
+                    if (self().fx() >= fold || phidnew <= 0.0) {
+                        atemp = a; ftemp = self().fx();
+                        strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
+                        return;
+                    }
+                    if (a < 1e-15) return;
+                }
+            } else {
+                for (;;) {                                               // f90:1499-1515
+                    aold = a; fold = self().fx(); phidold = phidnew;
+                    a = nf_mul(aold, incr); self().form(a); both(); phidnew = self().slope();
+                    if (armijo_violated() || self().fx() >= fold) {
+                        atemp = a; ftemp = self().fx();
+                        strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
+                        return;
+                    }
+                    if (phidnew > 0.0) {
+                        if (fabs(phidnew) <= c2abs) return;
+                        atemp = a; ftemp = self().fx();
+                        strong_zoom(atemp, aold, ftemp, fold, phidnew, phidold);
+                        if (fdwithf) return;                             // f90:1632
+                        self().set_fx(fx0);                              // f90:1512 (no return there)
+                    }
+                }
+            }
+        } else {                                                         // f90:1517-1546
+            for (;;) {
+                aold = a; fold = self().fx();
+                a = aold / incr; self().form(a); self().call_f();
+                self().count_f_only();
+                if (!armijo_violated()) {
+                    self().call_fd();
+                    phidnew = self().slope();
+                    if (fabs(phidnew) <= c2abs) return;
+                    if (phidnew < 0.0) {
+                        self().form(aold); self().call_fd(); phidold = self().slope();   // f90:1526
+                        atemp = a; ftemp = self().fx();
+                        strong_zoom(atemp, aold, ftemp, fold, phidnew, phidold);
+                        return;
+                    } else {
+                        for (;;) {
+                            aold = a; fold = self().fx(); phidold = phidnew;
+                            a = aold / incr; self().form(a); both(); phidnew = self().slope();
+                            if (self().fx() >= fold || phidnew <= 0.0) {
+                                atemp = a; ftemp = self().fx();
+                                strong_zoom(aold, atemp, fold, ftemp, phidold, phidnew);
+                                return;
+                            }
+                            if (a < 1e-15) return;
+                        }
+                    }
+                }
+                if (a < 1e-15) { self().call_fd(); return; }
+            }
+        }
+    }
+};
+
+}  // namespace flgpu
