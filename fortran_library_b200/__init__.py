@@ -175,6 +175,7 @@ def _run(fn, for_cg, problem, x, n, x_space, observer, stream, comm, offset, n_g
     require_gpu()
     o = default_options(for_cg)
     o.no_fused = int(not kw.pop("fused", True))
+    o.device_search = int(bool(kw.pop("device_search", False)))
     capi.apply_options(o, **kw)
     o.stream = stream
     o.comm = comm
@@ -205,7 +206,7 @@ def _resolve_x(x):
 
 def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
           MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None,
-          comm=None, offset=0, n_global=0, time_kernels=False, fused=True):
+          comm=None, offset=0, n_global=0, time_kernels=False, fused=True, device_search=False):
     """Limited-memory BFGS (reference: LBFGS, NonlinearOptimization.f90:398-625).  x is updated in
     place with the minimiser; returns the run statistics.  `problem.f_fd` present selects the
     _fdwithf line searcher exactly as the reference's optional f_fd does.  fused=False ignores
@@ -214,12 +215,12 @@ def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None,
     return _run(lib().flgpu_lbfgs, False, problem, ptr, n, space, observer, stream, comm, offset, n_global,
                 time_kernels, dict(Memory=Memory, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                                    Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                                   WolfeConst2=WolfeConst2, Increment=Increment, fused=fused))
+                                   WolfeConst2=WolfeConst2, Increment=Increment, fused=fused, device_search=device_search))
 
 
 def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
                       MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None,
-                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True):
+                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True, device_search=False):
     """Nonlinear conjugate gradient, Method 'DY' (default) or 'PR' (reference: ConjugateGradient,
     f90:193-394; no_clamp=True gives ConjugateGradient_basic, f90:2249-2346)."""
     if Method is not None and Method not in ("DY", "PR", CG_DY, CG_PR):
@@ -229,19 +230,19 @@ def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIte
                 n_global, time_kernels,
                 dict(Method=Method, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                      Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                     WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp), fused=fused))
+                     WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp), fused=fused, device_search=device_search))
 
 
 def SteepestDescent(problem, x, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
                     WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None, comm=None,
-                    offset=0, n_global=0, time_kernels=False, fused=True):
+                    offset=0, n_global=0, time_kernels=False, fused=True, device_search=False):
     """Steepest descent (reference: SteepestDescent, f90:55-188): p = -f'(x) through the same line searchers."""
     ptr, n, space = _resolve_x(x)
     return _run(lib().flgpu_steepest_descent, False, problem, ptr, n, space, observer, stream, comm, offset,
                 n_global, time_kernels,
                 dict(Strong=Strong, Warning=Warning, MaxIteration=MaxIteration, Precision=Precision,
                      MinStepLength=MinStepLength, WolfeConst1=WolfeConst1, WolfeConst2=WolfeConst2,
-                     Increment=Increment, fused=fused))
+                     Increment=Increment, fused=fused, device_search=device_search))
 
 
 def builtin_constraints(kind=CON_SPHERE):

@@ -32,7 +32,7 @@ FUSED_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_int, C.c_void_p, C.c_void_p
 
 class Problem(C.Structure):
     _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p),
-                ("fused", C.c_void_p)]
+                ("fused", C.c_void_p), ("search", C.c_void_p)]
 
 
 class IterInfo(C.Structure):
@@ -52,7 +52,8 @@ class Options(C.Structure):
                 ("wolfe_c1", C.c_double), ("wolfe_c2", C.c_double), ("increment", C.c_double),
                 ("no_clamp", C.c_int), ("stream", C.c_void_p), ("comm", C.c_void_p),
                 ("offset", C.c_int64), ("n_global", C.c_int64), ("observer", C.c_void_p),
-                ("observer_user", C.c_void_p), ("time_kernels", C.c_int), ("no_fused", C.c_int)]
+                ("observer_user", C.c_void_p), ("time_kernels", C.c_int), ("no_fused", C.c_int),
+                ("device_search", C.c_int)]
 
 
 class Stats(C.Structure):

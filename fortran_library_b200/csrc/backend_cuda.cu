@@ -288,10 +288,11 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
     Rall = (double *)dalloc(nres * sizeof(double) * G);
     Rglob = (double *)dalloc(NSLOTS * sizeof(double));
     Dsum = (double *)dalloc(nd_of(k::kMaxMem) * sizeof(double));
+    Rsearch = (double *)dalloc(FLGPU_SEARCH_RESULT_DOUBLES * sizeof(double));
     work.partials = (double *)dalloc((size_t)k::kMaxGrid * nd_of(k::kMaxMem) * sizeof(double));
     work.ticket = (unsigned int *)dalloc(64);
-    FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, (NSLOTS + 8) * sizeof(double)));   // slots + flag word
-    std::memset(host_pinned, 0, (NSLOTS + 8) * sizeof(double));
+    FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, (NSLOTS + 16) * sizeof(double)));
+    std::memset(host_pinned, 0, (NSLOTS + 16) * sizeof(double));
     const char *sync_mode = std::getenv("FLGPU_SYNC");
     poll_sync = !(sync_mode && !std::strcmp(sync_mode, "stream"));
 }
@@ -431,6 +432,21 @@ void CudaBackend::fused_eval(int flags, double a, const double *x0, const double
     const int t = time_begin(name, 8.0 * n * words);
     prob.fused(&ctx, flags, R + SL_F, R + SL_GP, x_out, g_out, x0, p, a, n);
     time_end(t);
+}
+
+void CudaBackend::device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0,
+                                double incr, double a, const double *x0, const double *p, double *xt, double *gt) {
+    flgpu_search_args A;
+    A.x0_dev = x0; A.p_dev = p; A.x_out = xt; A.g_out = gt;
+    A.c1 = c1; A.c2abs = c2abs; A.fx0 = fx0; A.phid0 = phid0; A.incr = incr; A.a = a;
+    A.strong = strong ? 1 : 0; A.fdwithf = fdwithf ? 1 : 0;
+    A.result_dev = Rsearch;
+    const int t = time_begin("callback:device_search", 0.0);   // bytes depend on the trial count: see flgpu_stats
+    prob.search(&ctx, &A, n);
+    time_end(t);
+}
+void CudaBackend::search_result(double *out) {
+    std::memcpy(out, host_pinned + NSLOTS + 8, FLGPU_SEARCH_RESULT_DOUBLES * sizeof(double));
 }
 
 // ---- primitives
@@ -594,7 +610,7 @@ void CudaBackend::fetch(double *host_slots) {
     }
     if (poll_sync) {
         if (!on_host) {
-            k::publish_kernel<<<1, 32, 0, stream>>>(src, host_pinned, host_seq + 1);
+            k::publish_kernel<<<1, 32, 0, stream>>>(src, host_pinned, host_seq + 1, Rsearch);
             launches++;
         }
         host_seq++;
@@ -613,6 +629,8 @@ void CudaBackend::fetch(double *host_slots) {
         std::atomic_thread_fence(std::memory_order_acquire);
     } else {
         FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned, src, NSLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        FLGPU_CUDA_CHECK(cudaMemcpyAsync(host_pinned + NSLOTS + 8, Rsearch, FLGPU_SEARCH_RESULT_DOUBLES * sizeof(double),
+                                         cudaMemcpyDeviceToHost, stream));
         FLGPU_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
     cudaError_t e = cudaGetLastError();

@@ -73,6 +73,10 @@ public:
     void eval_fg(const double *x, double *g) override;
     bool fused_available() const override { return prob.fused != nullptr; }
     void fused_eval(int flags, double a, const double *x0, const double *p, double *x_out, double *g_out) override;
+    bool device_search_available() const override { return prob.search != nullptr && ctx.nranks == 1; }
+    void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
+                       double a, const double *x0, const double *p, double *xt, double *gt) override;
+    void search_result(double *out) override;
     void trial_x(double *x, const double *x0, const double *p, double a) override;
     void dot(const double *a, const double *b, int slot) override;
     void neg(double *p, const double *g) override;
@@ -106,10 +110,12 @@ private:
     k::Work work{};
     double *Rall = nullptr;       // [G][NSLOTS + nd] all-gathered results (NCCL fallback only)
     double *Dsum = nullptr;       // [nd] rank-ordered sum of the K1 dots
+    double *Rsearch = nullptr;    // [FLGPU_SEARCH_RESULT_DOUBLES] scalars of the last device-resident search
     // out = sum over ranks, in rank order; returns true when the sums were also stored into host_out
     bool exchange(const double *src, int count, double *out, double *host_out);
     double *Rglob = nullptr;      // [NSLOTS] combined slots
-    double *host_pinned = nullptr;   // [NSLOTS] results + [NSLOTS] flag word, pinned (device-addressable under UVA)
+    // pinned, device-addressable under UVA: [0,NSLOTS) result slots, [NSLOTS] flag word, [NSLOTS+8, +16) search scalars
+    double *host_pinned = nullptr;
     unsigned long long host_seq = 0; // value of the flag word after the last fetch()
     bool poll_sync = true;
     bool timing = false;

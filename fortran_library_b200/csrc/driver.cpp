@@ -41,6 +41,7 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
     P.incr = std::fmax(1.0 + 1e-15, o.increment);                           // f90:1478
     P.has_f_fd = has_f_fd;
     P.fused = !o.no_fused;
+    P.device_search = o.device_search != 0 && P.fused;
     P.observer = o.observer;
     P.observer_user = o.observer_user;
     (void)for_cg;
@@ -136,6 +137,18 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     S.pre = pre; S.pre_f = pre_f; S.pre_gp = pre_gp;
     S.fused = P.fused && B.fused_available();
     st.n_linesearch++;
+    if (P.device_search && S.fused && pre == 0 && B.device_search_available()) {
+        // the same SearchCore, run by every thread of one cooperative kernel; one host round trip per search
+        double res[FLGPU_SEARCH_RESULT_DOUBLES], slots[NSLOTS];
+        B.device_search(strong, fdwithf, S.c1, S.c2abs, fx0, phid0, S.incr, a, x0, p, xt, gt);
+        B.fetch(slots); st.host_syncs++;
+        B.search_result(res);
+        st.n_trials += (int64_t)res[2]; st.n_f += (int64_t)res[3]; st.n_fd += (int64_t)res[4];
+        st.n_f_fd += (int64_t)res[5]; st.n_f_only_trials += (int64_t)res[6];
+        SearchResult r;
+        r.a = res[0]; r.fx = res[1]; r.trials = (int64_t)res[2];
+        return r;
+    }
     if (strong) S.strongwolfe(); else S.wolfe();
     S.finish();
     SearchResult r;
@@ -172,6 +185,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
     double *p = B.vec_alloc();
     const int mem = P.mem;
     const bool fused = P.fused && B.fused_available();
+    const bool dsearch = fused && P.device_search && B.device_search_available();   // search kernel does every trial
     B.lbfgs_alloc(mem);
     B.upload(xc, x_user, x_space);
 
@@ -215,7 +229,9 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             } else {
                 B.lbfgs_update_dots(xc, xo, gc, go, new_slot, k_after);      // K1
                 B.lbfgs_solve(k_after, new_slot);                            // K2
-                if (fused) {                                                 // K3: new p; first trial (a=1) probed
+                if (dsearch) {                                               // K3: new p only
+                    B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);
+                } else if (fused) {                                          // K3: new p; first trial (a=1) probed
                     B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);
                     st.n_trials++;
                     if (next_fdwithf) { B.fused_eval(FLGPU_WANT_F | FLGPU_WANT_GP, 1.0, xc, p, nullptr, nullptr); st.n_f_fd++; }
@@ -248,7 +264,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             phid0 = slots[SL_GP0];                                           // f90:607
             pp = slots[SL_PP];
             a = 1.0;
-            pre = next_fdwithf ? 3 : 2;
+            pre = dsearch ? 0 : (next_fdwithf ? 3 : 2);
             pre_f = slots[SL_F];
             pre_gp = slots[SL_GP];
         }

@@ -664,8 +664,10 @@ static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable p
 
 // Single GPU: the 16 result slots go to pinned host memory the same way (data, fence, flag), so the host polls a
 // cache line instead of paying a DMA copy plus a driver synchronisation per line-search trial.
-static __global__ void __launch_bounds__(32) publish_kernel(const double *src, double *host_out, unsigned long long seq_host) {
+static __global__ void __launch_bounds__(32) publish_kernel(const double *src, double *host_out, unsigned long long seq_host,
+                                                            const double *extra) {
     if (threadIdx.x < NSLOTS) host_out[threadIdx.x] = src[threadIdx.x];
+    if (extra && threadIdx.x < 8) host_out[NSLOTS + 8 + threadIdx.x] = extra[threadIdx.x];   // device-search scalars
     __threadfence_system();
     __syncwarp();
     if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(host_out + NSLOTS) = seq_host;

@@ -8,11 +8,14 @@
 //
 // Element-wise arithmetic uses separate multiply/add roundings in the same order as the CPU
 // oracle's objectives so that f' agrees bit for bit for the same x.
+#include <cooperative_groups.h>
+
 #include <cmath>
 #include <map>
 #include <mutex>
 
 #include "backend_cuda.cuh"
+#include "search_core.hpp"
 
 namespace flgpu {
 
@@ -86,18 +89,14 @@ struct ObjArgs {
     Work w;
 };
 
-// One kernel serves the plain callbacks (f, fd, f_fd) and the fused line-search evaluation
-// (flgpu_fused_fn).  FUSED: the point is formed as x0 + a*p (multiply, then add: f90:1482) instead of
-// being loaded; WANT_GP: f'(x).p is reduced alongside f; WRITE_X / WRITE_G: store the point / gradient.
-// The thread-to-element mapping and the accumulation order of f do not depend on the flags, so f has
-// the same bits on the fused and the unfused path.
+// FUSED: the point is formed as x0 + a*p (multiply, then add: f90:1482) instead of being loaded; WANT_GP:
+// f'(x).p is reduced alongside f; WRITE_X / WRITE_G: store the point / gradient.  The thread-to-element mapping and
+// the accumulation order of f do not depend on the flags, so f has the same bits on the fused and the unfused path.
+// Per-thread part of every objective evaluation: this thread's share of the units, in grid-stride order.  Shared by
+// objective_kernel (one evaluation per launch) and search_kernel (a whole line search per launch), so both produce
+// the same bits for f and f'.p.  tab: the diag-quad factor tables in shared memory (unused otherwise).
 template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
-__global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
-    __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
-    if (KIND == FLGPU_OBJ_DIAGQUAD) {
-        for (int i = threadIdx.x; i < 768; i += kThreads) tab[i] = a.tables[i];
-        __syncthreads();
-    }
+__device__ __forceinline__ void objective_accumulate(const ObjArgs &a, const double *tab, double &fsum, double &gpsum) {
     // d_i = 10^(6 q / 2^24), q = trunc(i * scale) <= 2^24 (diagonal quadratic); the index arrives
     // as a double (exact below 2^53) and the truncation is a 32-bit conversion: same bits, no 64-bit I2F/F2I
     auto coeff = [&](double i) -> double {
@@ -108,7 +107,6 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
     };
     const double offset_d = (double)a.offset;
     constexpr bool NEED_G = WANT_GP || WRITE_G;
-    double fsum = 0.0, gpsum = 0.0;
     const double step = a.a;
     const int64_t nu = a.n >> 1;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
@@ -185,6 +183,23 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
         if (WRITE_G) a.g[i] = g;
         if (WANT_GP) gpsum = fma(g, pv, gpsum);
     }
+}
+
+template <int KIND>
+__device__ __forceinline__ void load_tables(const ObjArgs &a, double *tab) {
+    if (KIND == FLGPU_OBJ_DIAGQUAD) {
+        for (int i = threadIdx.x; i < 768; i += kThreads) tab[i] = a.tables[i];
+        __syncthreads();
+    }
+}
+
+// One kernel serves the plain callbacks (f, fd, f_fd) and the fused line-search evaluation (flgpu_fused_fn).
+template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
+__global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
+    __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
+    load_tables<KIND>(a, tab);
+    double fsum = 0.0, gpsum = 0.0;
+    objective_accumulate<KIND, FUSED, WANT_F, WANT_GP, WRITE_X, WRITE_G>(a, tab, fsum, gpsum);
     if (WANT_F && WANT_GP) {
         double acc[2] = {fsum, gpsum};
         double *out[2] = {a.f_out, a.gp_out};
@@ -197,6 +212,109 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
         double acc[1] = {gpsum};
         double *out[1] = {a.gp_out};
         reduce_finish_to<1>(acc, out, a.w);
+    }
+}
+
+// ------------------------------------------------------------------ device-resident line search (flgpu_search_fn)
+// The whole Wolfe / Strong-Wolfe search in ONE cooperative kernel.  Every thread of every block runs the same state
+// machine (SearchCore, the source the host driver compiles too) on the same values, so control flow is uniform across
+// the grid; an evaluation is this thread's share of the units (objective_accumulate, as in objective_kernel), the
+// block tree, one grid-wide barrier, and the fixed-order sum over blocks -- repeated by every block, which saves the
+// second barrier a broadcast would need.  Partials are double-buffered on the evaluation parity: a block can be at
+// most one evaluation ahead of the slowest reader.  Launch geometry equals objective_kernel's, so f and f'.p carry
+// the same bits as on the host-driven fused path and both paths take the same decisions.
+struct SearchKArgs {
+    ObjArgs o;              // x = x0, p, x_out / g = accepted point / gradient; a is set per evaluation
+    double c1, c2abs, fx0, phid0, incr, a0;
+    int strong, fdwithf;
+    double *partials;       // [2][gridDim.x][2]
+    double *result;         // FLGPU_SEARCH_RESULT_DOUBLES
+};
+
+template <int KIND>
+struct DevSearch : SearchCore<DevSearch<KIND>> {
+    const SearchKArgs &K;
+    const double *tab;
+    double (*sh)[kThreads / 32];   // [2][8] block scratch
+    double *bc;                    // [2] block broadcast
+    double f_cur = 0.0, gp_cur = 0.0, a_x = 0.0, a_g = 0.0;
+    bool have_x = false, have_g = false;
+    int parity = 0;
+    double trials = 0.0, n_f = 0.0, n_fd = 0.0, n_ffd = 0.0, n_fonly = 0.0;
+
+    __device__ DevSearch(const SearchKArgs &k, const double *t, double (*s)[kThreads / 32], double *b)
+        : K(k), tab(t), sh(s), bc(b) {}
+
+    template <bool F, bool GP>
+    __device__ void eval() {
+        constexpr int NACC = (F && GP) ? 2 : 1;
+        ObjArgs o = K.o;
+        o.a = a_x;
+        double fsum = 0.0, gpsum = 0.0;
+        objective_accumulate<KIND, true, F, GP, false, false>(o, tab, fsum, gpsum);
+        double acc[2] = {F ? fsum : gpsum, gpsum};
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < NACC; i++) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) sh[i][warp] = v;
+        }
+        __syncthreads();
+        double *part = K.partials + (size_t)parity * gridDim.x * 2;
+        if (threadIdx.x < NACC) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
+            part[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+        }
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+        if (warp < NACC) {
+            double s = 0.0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&part[(size_t)b * 2 + warp]);
+            s = warp_sum(s);
+            if (lane == 0) bc[warp] = s;
+        }
+        __syncthreads();
+        if (F) f_cur = bc[0];
+        if (GP) gp_cur = bc[NACC - 1];
+        __syncthreads();
+        parity ^= 1;
+    }
+    __device__ void form(double step) { a_x = step; have_x = true; trials += 1.0; }
+    __device__ void call_f() { eval<true, false>(); n_f += 1.0; }
+    __device__ void call_fd() { eval<false, true>(); a_g = a_x; have_g = true; n_fd += 1.0; }
+    __device__ void call_ffd() { eval<true, true>(); a_g = a_x; have_g = true; n_ffd += 1.0; }
+    __device__ double slope() { return gp_cur; }
+    __device__ double fx() { return f_cur; }
+    __device__ void set_fx(double v) { f_cur = v; }
+    __device__ void adopt_pre() {}
+    __device__ void count_f_only() { n_fonly += 1.0; }
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 4) search_kernel(SearchKArgs K) {
+    __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
+    __shared__ double sh[2][kThreads / 32];
+    __shared__ double bc[2];
+    load_tables<KIND>(K.o, tab);
+    DevSearch<KIND> S(K, tab, sh, bc);
+    S.c1 = K.c1; S.c2abs = K.c2abs; S.fx0 = K.fx0; S.phid0 = K.phid0; S.incr = K.incr;
+    S.fdwithf = K.fdwithf != 0; S.a = K.a0; S.f_cur = K.fx0; S.pre = 0;
+    if (K.strong) S.strongwolfe(); else S.wolfe();
+    // the point and gradient the reference leaves in x / fdx
+    ObjArgs o = K.o;
+    double f0 = 0.0, g0 = 0.0;
+    if (S.have_x && S.have_g && S.a_x == S.a_g) {
+        o.a = S.a_x;
+        objective_accumulate<KIND, true, false, false, true, true>(o, tab, f0, g0);
+    } else {                                       // never taken by the reference's searchers; kept for fidelity
+        if (S.have_x) { o.a = S.a_x; objective_accumulate<KIND, true, false, false, true, false>(o, tab, f0, g0); }
+        if (S.have_g) { o.a = S.a_g; objective_accumulate<KIND, true, false, false, false, true>(o, tab, f0, g0); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
+        K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly; K.result[7] = 0.0;
     }
 }
 
@@ -309,6 +427,36 @@ static void dev_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp,
                      (cudaStream_t)c->stream);
 }
 
+// device-resident search: same grid as the probes (bit-identical sums), capped by what can be co-resident
+template <int KIND>
+static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int64_t n) {
+    cudaStream_t s = (cudaStream_t)c->stream;
+    Scratch &sc = scratch_for(s);
+    static int resident = 0, sms = 0;
+    if (!resident) {
+        int dev = 0;
+        FLGPU_CUDA_CHECK(cudaGetDevice(&dev));
+        FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::search_kernel<KIND>, k::kThreads, 0));
+        int coop = 0;
+        FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        if (!coop || resident < 1) fatal("device-resident line search needs cooperative kernel launch");
+    }
+    int grid = obj_grid(n);
+    if (grid > resident * sms) grid = resident * sms;
+    k::SearchKArgs K;
+    K.o.x = A->x0_dev; K.o.p = A->p_dev; K.o.a = 0.0; K.o.x_out = A->x_out; K.o.g = A->g_out; K.o.f_out = nullptr;
+    K.o.gp_out = nullptr; K.o.n = n; K.o.offset = c->offset; K.o.n_global = c->n_global;
+    K.o.scale = c->n_global > 1 ? 16777216.0 / (double)(c->n_global - 1) : 0.0;
+    K.o.tables = sc.tables; K.o.w = sc.work;
+    K.c1 = A->c1; K.c2abs = A->c2abs; K.fx0 = A->fx0; K.phid0 = A->phid0; K.incr = A->incr; K.a0 = A->a;
+    K.strong = A->strong; K.fdwithf = A->fdwithf;
+    K.partials = sc.work.partials;      // [2][grid][2] <= kMaxGrid * 8 doubles
+    K.result = A->result_dev;
+    void *params[] = {&K};
+    FLGPU_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k::search_kernel<KIND>, dim3(grid), dim3(k::kThreads), params, 0, s));
+}
+
 // reference-ABI flavour: device x / f' pointers, host f, runs on the current call's stream
 static double ref_eval(int kind, bool want_f, double *g, const double *x, int dim) {
     cudaStream_t s = (cudaStream_t)flgpu_current_stream();
@@ -337,9 +485,9 @@ using namespace flgpu;
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {
-    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; return 0;
-    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; return 0;
-    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; return 0;
+    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; return 0;
+    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; return 0;
+    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; return 0;
     }
     return 1;
 }

@@ -77,12 +77,32 @@ typedef void (*flgpu_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *f_d
                                double *x_out, double *g_out, const double *x0_dev, const double *p_dev,
                                double a, int64_t n_local);
 
+/* Optional DEVICE-RESIDENT line search (an extension beyond flgpu_fused_fn).  One cooperative kernel runs the whole
+ * Wolfe / Strong-Wolfe search of the reference (f90:1286-1698) on the device: every thread executes the same state
+ * machine (csrc/search_core.hpp, the source the host driver uses too), every evaluation is a grid-wide reduction with
+ * the library's fixed summation order, and the accepted point and gradient are stored by the same kernel -- no host
+ * round trip per trial.  result_dev receives FLGPU_SEARCH_RESULT_DOUBLES doubles:
+ *   [0] accepted step a  [1] f at it  [2] trial points formed  [3] f calls  [4] fd calls  [5] f_fd calls
+ *   [6] f-only trials (branch D)  [7] reserved
+ * The decisions and the values are those of the host-driven fused search, bit for bit.  Single GPU only. */
+#define FLGPU_SEARCH_RESULT_DOUBLES 8
+typedef struct flgpu_search_args {
+    const double *x0_dev, *p_dev;   /* start point and direction */
+    double *x_out, *g_out;          /* accepted point and its gradient */
+    double c1, c2abs;               /* WolfeConst1, WolfeConst2 * |phi'(0)| */
+    double fx0, phid0, incr, a;     /* f(x0), phi'(0), Increment, first step */
+    int strong, fdwithf;            /* which of the four searchers */
+    double *result_dev;
+} flgpu_search_args;
+typedef void (*flgpu_search_fn)(const flgpu_eval_ctx *ctx, const flgpu_search_args *args, int64_t n_local);
+
 typedef struct flgpu_problem {
     flgpu_f_fn f;       /* required */
     flgpu_fd_fn fd;     /* required */
     flgpu_f_fd_fn f_fd; /* optional (NULL = absent, f90:42-43) */
     void *user;
     flgpu_fused_fn fused; /* optional (NULL = trial points are materialised and f / fd / f_fd are called) */
+    flgpu_search_fn search; /* optional (NULL = the host drives the search, one round trip per evaluation) */
 } flgpu_problem;
 
 /* ------------------------------------------------------------------ options / results */
@@ -140,6 +160,7 @@ typedef struct flgpu_options {
     void *observer_user;
     int time_kernels;       /* 1 = bracket every library kernel with CUDA events (flgpu_kernel_times) */
     int no_fused;           /* 1 = ignore flgpu_problem.fused (always materialise trial points) */
+    int device_search;      /* 1 = use flgpu_problem.search when present (single GPU, fused mode); default 0 */
 } flgpu_options;
 
 typedef struct flgpu_stats {

@@ -201,6 +201,7 @@ inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool wi
     p.f_fd = with_f_fd ? Callbacks<Obj>::f_fd : nullptr;
     p.user = (void *)obj;
     p.fused = with_fused ? Callbacks<Obj>::fused : nullptr;
+    p.search = nullptr;
     return p;
 }
 

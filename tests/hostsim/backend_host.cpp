@@ -226,6 +226,7 @@ void flgpu_hostsim_set_obj_sum_mode(int mode) { g_obj_sum_mode = mode; }
 void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->f = obj_f; out->fd = obj_fd; out->f_fd = obj_ffd; out->user = (void *)(intptr_t)kind;
     out->fused = obj_fused;
+    out->search = nullptr;
 }
 
 void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {

@@ -399,6 +399,38 @@ def test_fortran_abi_steepest_descent(fl):
         assert np.array_equal(x, xa, equal_nan=True) and st.iterations == s.n_iter and st.status == s.status
 
 
+# ----------------------------------------------------------------------------- device-resident line search
+@pytest.mark.parametrize("algo,name,kw", [
+    ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=60)), ("lbfgs", "rosenR1", dict(Memory=5, use_ffd=False, MaxIteration=40)),
+    ("lbfgs", "quartic", dict(Memory=7)), ("lbfgs", "diag", dict(Memory=30, MaxIteration=40)),
+    ("lbfgs", "rosenR1", dict(Memory=4, Strong=False, MaxIteration=40)),
+    ("cg", "quartic", dict(Method="DY")), ("cg", "quartic", dict(Method="PR", use_ffd=False)),
+    ("cg", "rosenR1", dict(Method="DY", Strong=False, MaxIteration=60)), ("sd", "rosenR1", dict(MaxIteration=40)),
+    ("sd", "quartic", dict(MaxIteration=40, Strong=False)),
+])
+@pytest.mark.parametrize("n", [10_000, 4097])
+def test_device_resident_search_is_the_same_algorithm(fl, algo, name, kw, n):
+    """flgpu_search_fn: the whole line search in one cooperative kernel, driven by the same SearchCore source as the
+    host.  Same launch geometry -> same bits for f and f'.p -> same decisions: every step, f, trial count, iterate
+    and evaluation counter must be IDENTICAL to the host-driven fused search."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    run = {"lbfgs": fl.LBFGS, "cg": fl.ConjugateGradient, "sd": fl.SteepestDescent}[algo]
+    out = []
+    for dev in (False, True):
+        x = _dev_start(fl, name, n)
+        ob = fl.Observer(keep_vectors=True, max_vec_iters=12)
+        st = run(_problem(fl, name, use), x, observer=ob, Warning=False, device_search=dev, **kw)
+        out.append((x.numpy(), st, ob))
+    (xa, sa, oa), (xb, sb, ob_) = out
+    assert oa.rows == ob_.rows
+    assert np.array_equal(xa, xb)
+    assert all(np.array_equal(u, v) for u, v in zip(oa.p, ob_.p))
+    for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
+        assert getattr(sa, k) == getattr(sb, k), k
+    assert sb.host_syncs < sa.host_syncs            # the point of it: fewer host round trips
+
+
 # ----------------------------------------------------------------------------- user objectives (flgpu_objective.cuh)
 def _np_user_objective(which, n):
     """NumPy statement of tests/link/user_objective.cu (same operation order, no FMA)."""
