@@ -175,7 +175,8 @@ def _run(fn, for_cg, problem, x, n, x_space, observer, stream, comm, offset, n_g
     require_gpu()
     o = default_options(for_cg)
     o.no_fused = int(not kw.pop("fused", True))
-    o.device_search = int(bool(kw.pop("device_search", False)))
+    ds = kw.pop("device_search", None)                    # None = auto (by size), True / False = force
+    o.device_search = 2 if ds is None else int(bool(ds))
     capi.apply_options(o, **kw)
     o.stream = stream
     o.comm = comm
@@ -206,7 +207,7 @@ def _resolve_x(x):
 
 def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
           MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None,
-          comm=None, offset=0, n_global=0, time_kernels=False, fused=True, device_search=False):
+          comm=None, offset=0, n_global=0, time_kernels=False, fused=True, device_search=None):
     """Limited-memory BFGS (reference: LBFGS, NonlinearOptimization.f90:398-625).  x is updated in
     place with the minimiser; returns the run statistics.  `problem.f_fd` present selects the
     _fdwithf line searcher exactly as the reference's optional f_fd does.  fused=False ignores
@@ -220,7 +221,7 @@ def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None,
 
 def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
                       MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None,
-                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True, device_search=False):
+                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True, device_search=None):
     """Nonlinear conjugate gradient, Method 'DY' (default) or 'PR' (reference: ConjugateGradient,
     f90:193-394; no_clamp=True gives ConjugateGradient_basic, f90:2249-2346)."""
     if Method is not None and Method not in ("DY", "PR", CG_DY, CG_PR):
@@ -235,7 +236,7 @@ def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIte
 
 def SteepestDescent(problem, x, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
                     WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None, comm=None,
-                    offset=0, n_global=0, time_kernels=False, fused=True, device_search=False):
+                    offset=0, n_global=0, time_kernels=False, fused=True, device_search=None):
     """Steepest descent (reference: SteepestDescent, f90:55-188): p = -f'(x) through the same line searchers."""
     ptr, n, space = _resolve_x(x)
     return _run(lib().flgpu_steepest_descent, False, problem, ptr, n, space, observer, stream, comm, offset,

@@ -183,6 +183,8 @@ void apply_thread_settings(flgpu_options &o) {
     o.observer_user = tls.observer_user;
     const char *nf = std::getenv("FLGPU_NO_FUSED");
     if (nf && nf[0] && nf[0] != '0') o.no_fused = 1;
+    const char *ds = std::getenv("FLGPU_DEVICE_SEARCH");   // 0 / 1 / 2 as flgpu_options.device_search
+    if (ds && ds[0] >= '0' && ds[0] <= '2') o.device_search = ds[0] - '0';
 }
 
 void run_ref(int algo, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
@@ -245,6 +247,7 @@ void flgpu_options_default(flgpu_options *o, int for_cg) {
     o->wolfe_c1 = 1e-4;
     o->wolfe_c2 = for_cg ? 0.45 : 0.9;
     o->increment = 1.05;
+    o->device_search = 2;
 }
 
 int flgpu_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local, int x_space,

@@ -41,7 +41,7 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
     P.incr = std::fmax(1.0 + 1e-15, o.increment);                           // f90:1478
     P.has_f_fd = has_f_fd;
     P.fused = !o.no_fused;
-    P.device_search = o.device_search != 0 && P.fused;
+    P.device_search = o.device_search;   // 0 off, 1 on, 2 auto (by size, see use_device_search)
     P.observer = o.observer;
     P.observer_user = o.observer_user;
     (void)for_cg;
@@ -124,6 +124,15 @@ struct Search : SearchCore<Search> {
     }
 };
 
+// Device-resident search (flgpu_search_fn) gives the same bits as the host-driven fused search; it pays when the
+// host round trip per trial (~15 us) is visible next to a probe kernel, i.e. below ~2^25 rows (2.3x at 2^14, 1.07x
+// at 2^24, -0.4 % at 2^28: profiles/r01_device_search.md).  Auto mode switches by size.
+bool use_device_search(const Params &P, Backend &B) {
+    if (!P.fused || P.device_search == 0 || !B.device_search_available()) return false;
+    if (P.device_search == 1) return true;
+    return B.n <= ((int64_t)1 << 25);
+}
+
 // Runs one line search; on return xt/gt hold the accepted point and gradient.
 struct SearchResult { double a, fx; int64_t trials; };
 
@@ -137,7 +146,7 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     S.pre = pre; S.pre_f = pre_f; S.pre_gp = pre_gp;
     S.fused = P.fused && B.fused_available();
     st.n_linesearch++;
-    if (P.device_search && S.fused && pre == 0 && B.device_search_available()) {
+    if (S.fused && pre == 0 && use_device_search(P, B)) {
         // the same SearchCore, run by every thread of one cooperative kernel; one host round trip per search
         double res[FLGPU_SEARCH_RESULT_DOUBLES], slots[NSLOTS];
         B.device_search(strong, fdwithf, S.c1, S.c2abs, fx0, phid0, S.incr, a, x0, p, xt, gt);
@@ -185,7 +194,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
     double *p = B.vec_alloc();
     const int mem = P.mem;
     const bool fused = P.fused && B.fused_available();
-    const bool dsearch = fused && P.device_search && B.device_search_available();   // search kernel does every trial
+    const bool dsearch = fused && use_device_search(P, B);   // the search kernel does every trial
     B.lbfgs_alloc(mem);
     B.upload(xc, x_user, x_space);
 
@@ -246,12 +255,20 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             B.fetch(slots); st.host_syncs++;
             gg = slots[SL_GG];
             st.gnorm2 = gg;
-            if (gg < P.tol) { st.status = FLGPU_CONVERGED; break; }          // f90:611-614
+            // the first trial of the next search was evaluated speculatively; if the run ends here the reference
+            // never makes that evaluation, so it is taken back out of the statistics
+            auto uncount_speculative = [&]() {
+                if (last || dsearch) return;
+                st.n_trials--;
+                if (next_fdwithf) st.n_f_fd--; else st.n_f--;
+            };
+            if (gg < P.tol) { uncount_speculative(); st.status = FLGPU_CONVERGED; break; }   // f90:611-614
             if (pp * a * a < P.minstep) {                                    // f90:615-621
                 if (P.warn) step_warning(it <= mem ? "BFGS" : "L-BFGS", gg);
+                uncount_speculative();
                 st.status = FLGPU_STEP_CONVERGED; break;
             }
-            if (stop) { st.status = FLGPU_STOPPED_BY_OBSERVER; break; }
+            if (stop) { uncount_speculative(); st.status = FLGPU_STOPPED_BY_OBSERVER; break; }
             if (last) {                                                      // f90:580-583
                 st.status = FLGPU_MAX_ITERATION;
                 if (P.warn) {

@@ -16,7 +16,7 @@ struct Params {
     double c1 = 1e-4, c2 = 0.9, incr = 1.05;
     bool has_f_fd = false;
     bool fused = true;   // use flgpu_problem.fused when the problem supplies it
-    bool device_search = false;   // use flgpu_problem.search (whole line search in one cooperative kernel)
+    int device_search = 2;   // flgpu_problem.search (whole line search in one cooperative kernel): 0 off, 1 on, 2 auto
     flgpu_observer_fn observer = nullptr;
     void *observer_user = nullptr;
 };

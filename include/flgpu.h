@@ -160,7 +160,8 @@ typedef struct flgpu_options {
     void *observer_user;
     int time_kernels;       /* 1 = bracket every library kernel with CUDA events (flgpu_kernel_times) */
     int no_fused;           /* 1 = ignore flgpu_problem.fused (always materialise trial points) */
-    int device_search;      /* 1 = use flgpu_problem.search when present (single GPU, fused mode); default 0 */
+    int device_search;      /* flgpu_problem.search (single GPU, fused mode): 0 never, 1 always, 2 = auto (default):
+                               used up to 2^25 rows, where the per-trial host round trip shows; same bits either way */
 } flgpu_options;
 
 typedef struct flgpu_stats {

@@ -233,7 +233,7 @@ void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {
     std::memset(o, 0, sizeof *o);
     o->memory = 10; o->method = FLGPU_CG_DY; o->strong = 1; o->warning = 1; o->max_iteration = 1000;
     o->precision = 1e-15; o->min_step_length = 1e-15; o->wolfe_c1 = 1e-4;
-    o->wolfe_c2 = for_cg ? 0.45 : 0.9; o->increment = 1.05;
+    o->wolfe_c2 = for_cg ? 0.45 : 0.9; o->increment = 1.05; o->device_search = 2;
 }
 
 int flgpu_hostsim_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n,
