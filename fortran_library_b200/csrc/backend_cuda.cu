@@ -163,8 +163,8 @@ void setup_p2p(flgpu_comm *c) {
     HandleMsg mine;
     std::memset(&mine, 0, sizeof mine);
     if (want) {
-        if (cudaMalloc((void **)&c->local, sizeof(k::Mailbox)) == cudaSuccess &&
-            cudaMemset(c->local, 0, sizeof(k::Mailbox)) == cudaSuccess &&
+        if (cudaMalloc((void **)&c->local, sizeof(k::MailboxPair)) == cudaSuccess &&
+            cudaMemset(c->local, 0, sizeof(k::MailboxPair)) == cudaSuccess &&
             cudaIpcGetMemHandle(&mine.h, c->local) == cudaSuccess)
             mine.ok = 1;
         else
@@ -187,14 +187,19 @@ void setup_p2p(flgpu_comm *c) {
     for (int r = 0; r < G; r++) ok = ok && all[r].ok;
     if (ok) {
         for (int r = 0; r < G; r++) {
-            if (r == c->rank) { c->peers.box[r] = c->local; continue; }
+            if (r == c->rank) {
+                c->peers.box[r] = &c->local->host_driven;
+                c->peers_search.box[r] = &c->local->device_search;
+                continue;
+            }
             void *ptr = nullptr;
             if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
                 ok = 0;
                 break;
             }
-            c->peers.box[r] = (k::Mailbox *)ptr;
+            c->peers.box[r] = &((k::MailboxPair *)ptr)->host_driven;
+            c->peers_search.box[r] = &((k::MailboxPair *)ptr)->device_search;
         }
     }
     mine.ok = ok;
@@ -207,6 +212,7 @@ void setup_p2p(flgpu_comm *c) {
     if (!c->p2p) {
         for (int r = 0; r < G; r++)
             if (r != c->rank && c->peers.box[r]) { cudaIpcCloseMemHandle(c->peers.box[r]); c->peers.box[r] = nullptr; }
+        // (host_driven is the first member: its address is the mapping's base address)
     }
     cudaFree(dsend);
     cudaFree(drecv);
@@ -441,6 +447,7 @@ void CudaBackend::device_search(bool strong, bool fdwithf, double c1, double c2a
     A.c1 = c1; A.c2abs = c2abs; A.fx0 = fx0; A.phid0 = phid0; A.incr = incr; A.a = a;
     A.strong = strong ? 1 : 0; A.fdwithf = fdwithf ? 1 : 0;
     A.result_dev = Rsearch;
+    A.comm = ctx.nranks > 1 ? comm : nullptr;
     const int t = time_begin("callback:device_search", 0.0);   // bytes depend on the trial count: see flgpu_stats
     prob.search(&ctx, &A, n);
     time_end(t);
@@ -578,11 +585,11 @@ void CudaBackend::cg_update(double *p, const double *g1, double beta) {
 // ncclAllGather + combine fallback (gather: [G][count] device scratch).  host_out (optional, peer-memory path
 // only): pinned host array that receives the sums followed by the flag word host_seq_next; returns whether it did.
 bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, double *out, double *gather,
-              double *host_out, unsigned long long host_seq_next) {
+              double *host_out, unsigned long long host_seq_next, const double *extra) {
     if (count > k::kMailWidth) fatal("rank_sum: more values than one mailbox slot holds");
     if (c->p2p) {
         k::exchange_kernel<<<1, k::kMailWidth, 0, s>>>(c->peers, c->rank, c->nranks, ++c->seq, src, count, out, host_out,
-                                                      host_seq_next);
+                                                      host_seq_next, extra);
         return host_out != nullptr;
     }
     nccl_allgather_f64(c, src, gather, (size_t)count, s);
@@ -592,7 +599,8 @@ bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, doubl
 
 bool CudaBackend::exchange(const double *src, int count, double *out, double *host_out) {
     const int t = time_begin("c1_exchange", 0.0);
-    const bool host_written = rank_sum(comm, stream, src, count, out, Rall, host_out, host_seq + 1);
+    const bool host_written = rank_sum(comm, stream, src, count, out, Rall, host_out, host_seq + 1,
+                                       host_out ? Rsearch : nullptr);
     time_end(t);
     launches++;
     return host_written;

@@ -21,8 +21,9 @@ struct flgpu_comm {
     int rank = 0, nranks = 1;
     // peer-memory exchange (kernels.cuh C1): this rank's mailbox and the IPC-mapped mailboxes of its peers
     bool p2p = false;
-    flgpu::k::Mailbox *local = nullptr;
-    flgpu::k::PeerTable peers{};
+    flgpu::k::MailboxPair *local = nullptr;
+    flgpu::k::PeerTable peers{};        // host-driven exchanges (exchange_kernel); seq = last sequence number used
+    flgpu::k::PeerTable peers_search{}; // exchanges made inside a device-resident line search; counter local->dseq
     unsigned long long seq = 0;
 };
 
@@ -49,7 +50,7 @@ double *scratch_scalar(cudaStream_t s);   // device double[4] private to the str
 void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s);
 // rank-ordered sum of `count` (<= k::kMailWidth) doubles over the communicator (backend_cuda.cu)
 bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, double *out, double *gather,
-              double *host_out, unsigned long long host_seq_next);
+              double *host_out, unsigned long long host_seq_next, const double *extra = nullptr);
 
 // ---- per-kernel CUDA-event timing (flgpu_options.time_kernels)
 struct KernelTime {
@@ -73,7 +74,9 @@ public:
     void eval_fg(const double *x, double *g) override;
     bool fused_available() const override { return prob.fused != nullptr; }
     void fused_eval(int flags, double a, const double *x0, const double *p, double *x_out, double *g_out) override;
-    bool device_search_available() const override { return prob.search != nullptr && ctx.nranks == 1; }
+    bool device_search_available() const override {
+        return prob.search != nullptr && (ctx.nranks == 1 || (comm && comm->p2p));
+    }
     void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
                        double a, const double *x0, const double *p, double *xt, double *gt) override;
     void search_result(double *out) override;

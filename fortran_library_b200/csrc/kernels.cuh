@@ -608,6 +608,16 @@ struct Mailbox {
 
 struct PeerTable { Mailbox *box[kMaxRanks]; };
 
+// One IPC-shared allocation per rank: the mailbox of the host-driven exchanges (exchange_kernel), a second one for
+// the exchanges a device-resident line search performs on its own, and that search's sequence counter (the host
+// cannot know how many evaluations a search will make, so the counter lives on the device; every rank makes the
+// same evaluations, so the counters agree without communication).
+struct MailboxPair {
+    Mailbox host_driven;
+    Mailbox device_search;
+    unsigned long long dseq;
+};
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -622,17 +632,14 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
-// src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth); host_out (optional):
-// the same sums stored straight into pinned host memory followed by the flag word host_out[NSLOTS] = seq_host.
-static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable peers, int me, int G,
-                                                                       unsigned long long seq, const double *src,
-                                                                       int count, double *out, double *host_out,
-                                                                       unsigned long long seq_host) {
-    const int par = (int)(seq & 1ull);
-    const int t = threadIdx.x;
+// Executed by ONE block: store vals[0..count) (count <= blockDim.x) into slot [me] of every rank's mailbox, publish
+// `seq`, wait for every rank's slot of this rank's mailbox, return the rank-ordered sums in out[0..count).
+__device__ __forceinline__ void mailbox_exchange_block(const PeerTable &peers, int me, int G, unsigned long long seq,
+                                                       const double *vals, int count, double *out) {
+    const int par = (int)(seq & 1ull), t = threadIdx.x;
     if (t < count) {
-        const double v = src[t];
-        for (int r = 0; r < G; r++) peers.box[r]->data[par][me][t] = v;      // r == me: the local slot
+        const double v = vals[t];
+        for (int r = 0; r < G; r++) peers.box[r]->data[par][me][t] = v;
     }
     __threadfence_system();
     __syncthreads();
@@ -641,7 +648,7 @@ static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable p
     if (t < G) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(&mine->flag[par][t]) < seq) {
-            if (global_timer_ns() - t0 > 20000000000ull) {                  // 20 s: a peer died; fail loudly
+            if (global_timer_ns() - t0 > 20000000000ull) {
                 mine->error = seq;
                 __threadfence_system();
                 __trap();
@@ -653,9 +660,27 @@ static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable p
         double s = __ldcv(&mine->data[par][0][t]);
         for (int r = 1; r < G; r++) s += __ldcv(&mine->data[par][r][t]);
         out[t] = s;
-        if (host_out) host_out[t] = s;
+    }
+}
+
+
+// src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth); host_out (optional):
+// the same sums stored straight into pinned host memory followed by the flag word host_out[NSLOTS] = seq_host.
+static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable peers, int me, int G,
+                                                                       unsigned long long seq, const double *src,
+                                                                       int count, double *out, double *host_out,
+                                                                       unsigned long long seq_host, const double *extra) {
+    __shared__ double vals[kMailWidth], sums[kMailWidth];
+    const int t = threadIdx.x;
+    if (t < count) vals[t] = src[t];
+    __syncthreads();
+    mailbox_exchange_block(peers, me, G, seq, vals, count, sums);
+    if (t < count) {
+        out[t] = sums[t];
+        if (host_out) host_out[t] = sums[t];
     }
     if (host_out) {                    // publish: data, system-wide fence, then the flag the host polls
+        if (extra && t < 8) host_out[NSLOTS + 8 + t] = extra[t];      // device-search scalars (identical on all ranks)
         __threadfence_system();
         __syncthreads();
         if (t == 0) *reinterpret_cast<volatile unsigned long long *>(host_out + NSLOTS) = seq_host;

@@ -229,6 +229,11 @@ struct SearchKArgs {
     int strong, fdwithf;
     double *partials;       // [2][gridDim.x][2]
     double *result;         // FLGPU_SEARCH_RESULT_DOUBLES
+    // row-sharded runs: the rank exchange happens inside the kernel (block 0) over the search mailboxes
+    PeerTable peers;
+    int me, G;
+    unsigned long long *dseq;   // this rank's sequence counter for those mailboxes (device memory)
+    double *glob;               // [2][2] rank-summed values for the other blocks
 };
 
 template <int KIND>
@@ -241,9 +246,12 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
     bool have_x = false, have_g = false;
     int parity = 0;
     double trials = 0.0, n_f = 0.0, n_fd = 0.0, n_ffd = 0.0, n_fonly = 0.0;
+    unsigned long long seq_base = 0, nexch = 0;   // exchanges made so far (uniform over the grid)
 
     __device__ DevSearch(const SearchKArgs &k, const double *t, double (*s)[kThreads / 32], double *b)
-        : K(k), tab(t), sh(s), bc(b) {}
+        : K(k), tab(t), sh(s), bc(b) {
+        if (K.G > 1) seq_base = *K.dseq;
+    }
 
     template <bool F, bool GP>
     __device__ void eval() {
@@ -276,8 +284,24 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
             if (lane == 0) bc[warp] = s;
         }
         __syncthreads();
-        if (F) f_cur = bc[0];
-        if (GP) gp_cur = bc[NACC - 1];
+        if (K.G > 1) {
+            // every block holds this rank's sums; block 0 trades them with the other ranks (stores into their
+            // mailboxes, flags, rank-ordered sum) and a second barrier hands the result to the rest of the grid
+            nexch++;
+            double *gl = K.glob + parity * 2;
+            if (blockIdx.x == 0) {
+                __shared__ double summed[2];
+                mailbox_exchange_block(K.peers, K.me, K.G, seq_base + nexch, bc, NACC, summed);
+                if (threadIdx.x < NACC) gl[threadIdx.x] = summed[threadIdx.x];
+                __threadfence();
+            }
+            cooperative_groups::this_grid().sync();
+            if (F) f_cur = __ldcg(&gl[0]);
+            if (GP) gp_cur = __ldcg(&gl[NACC - 1]);
+        } else {
+            if (F) f_cur = bc[0];
+            if (GP) gp_cur = bc[NACC - 1];
+        }
         __syncthreads();
         parity ^= 1;
     }
@@ -314,7 +338,8 @@ __global__ void __launch_bounds__(kThreads, 4) search_kernel(SearchKArgs K) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
-        K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly; K.result[7] = 0.0;
+        K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly; K.result[7] = (double)S.nexch;
+        if (K.G > 1) *K.dseq = S.seq_base + S.nexch;
     }
 }
 
@@ -451,8 +476,15 @@ static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int6
     K.o.tables = sc.tables; K.o.w = sc.work;
     K.c1 = A->c1; K.c2abs = A->c2abs; K.fx0 = A->fx0; K.phid0 = A->phid0; K.incr = A->incr; K.a0 = A->a;
     K.strong = A->strong; K.fdwithf = A->fdwithf;
-    K.partials = sc.work.partials;      // [2][grid][2] <= kMaxGrid * 8 doubles
+    K.partials = sc.work.partials;      // [2][grid][2] doubles at the front of the kMaxGrid * 8 ...
+    K.glob = sc.work.partials + (size_t)k::kMaxGrid * 8 - 4;   // ... and the 4 at its very end
     K.result = A->result_dev;
+    const flgpu_comm *comm = (const flgpu_comm *)A->comm;
+    K.G = 1; K.me = 0; K.dseq = nullptr;
+    if (comm && comm->nranks > 1) {
+        if (!comm->p2p) fatal("device-resident line search on row shards needs the peer-memory exchange");
+        K.peers = comm->peers_search; K.me = comm->rank; K.G = comm->nranks; K.dseq = &comm->local->dseq;
+    }
     void *params[] = {&K};
     FLGPU_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k::search_kernel<KIND>, dim3(grid), dim3(k::kThreads), params, 0, s));
 }

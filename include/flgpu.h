@@ -42,6 +42,8 @@ typedef void (*flgpu_ref_f_fn)(double *fx, const double *x, const int *dim);
 typedef void (*flgpu_ref_fd_fn)(double *fdx, const double *x, const int *dim);
 typedef int (*flgpu_ref_f_fd_fn)(double *fx, double *fdx, const double *x, const int *dim);
 
+typedef struct flgpu_comm flgpu_comm; /* row-shard communicator (peer-memory mailboxes + NCCL plumbing) */
+
 /* Context handed to the 64-bit device callbacks. */
 typedef struct flgpu_eval_ctx {
     void *user;       /* flgpu_problem.user */
@@ -83,8 +85,10 @@ typedef void (*flgpu_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *f_d
  * the library's fixed summation order, and the accepted point and gradient are stored by the same kernel -- no host
  * round trip per trial.  result_dev receives FLGPU_SEARCH_RESULT_DOUBLES doubles:
  *   [0] accepted step a  [1] f at it  [2] trial points formed  [3] f calls  [4] fd calls  [5] f_fd calls
- *   [6] f-only trials (branch D)  [7] reserved
- * The decisions and the values are those of the host-driven fused search, bit for bit.  Single GPU only. */
+ *   [6] f-only trials (branch D)  [7] rank exchanges made inside the kernel
+ * The decisions and the values are those of the host-driven fused search, bit for bit.  On row-sharded runs block 0
+ * trades the partial sums with the other ranks inside the kernel (peer-memory mailboxes; needs the peer-memory
+ * exchange, not the ncclAllGather fallback). */
 #define FLGPU_SEARCH_RESULT_DOUBLES 8
 typedef struct flgpu_search_args {
     const double *x0_dev, *p_dev;   /* start point and direction */
@@ -93,6 +97,7 @@ typedef struct flgpu_search_args {
     double fx0, phid0, incr, a;     /* f(x0), phi'(0), Increment, first step */
     int strong, fdwithf;            /* which of the four searchers */
     double *result_dev;
+    flgpu_comm *comm;               /* row-sharded runs: the communicator whose search mailboxes carry the exchanges */
 } flgpu_search_args;
 typedef void (*flgpu_search_fn)(const flgpu_eval_ctx *ctx, const flgpu_search_args *args, int64_t n_local);
 
@@ -118,7 +123,6 @@ enum {
     FLGPU_STOPPED_BY_OBSERVER = 4
 };
 
-typedef struct flgpu_comm flgpu_comm; /* row-shard communicator (NCCL) */
 
 /* Per outer iteration, called on the host after the line search accepted a step.
  * Device pointers stay valid until the observer returns.  Return non-zero to stop. */

@@ -93,6 +93,13 @@ def main():
         st2 = run(prob, x2, Warning=False, comm=comm_nccl, offset=lo, n_global=n, **kw)
         modes_equal = bool(np.array_equal(x.numpy(), x2.numpy())) and st2.iterations == st.iterations
         x2.free()
+        # the first run used the device-resident search (auto mode, exchanges inside the cooperative kernel); a
+        # host-driven search over the same peer-memory exchange must give the same bits again
+        x3 = fl.DeviceVector.start(start, hi - lo, seed=seed, offset=lo, n_global=n)
+        st3 = run(prob, x3, Warning=False, comm=comm, offset=lo, n_global=n, device_search=False, **kw)
+        modes_equal = modes_equal and bool(np.array_equal(x.numpy(), x3.numpy())) and st3.iterations == st.iterations \
+            and (kw.get("fused", True) is False or st3.host_syncs > st.host_syncs)
+        x3.free()
         flag = torch.tensor([int(modes_equal)], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         modes_equal = bool(flag.item())
@@ -114,7 +121,7 @@ def main():
             good = (same and modes_equal and dx < (1e-8 if converged else 1e-4) and dp < 1e-9 and its_ok
                     and st.status == st1.status)
             print(f"[{world} ranks] {algo} kind={kind} {kw}: iterations {st.iterations}/{st1.iterations} "
-                  f"ranks_identical={same} p2p==nccl:{modes_equal} |dx|={dx:.2e} max|dp|(first 6)={dp:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+                  f"ranks_identical={same} device-search==host-driven==nccl:{modes_equal} |dx|={dx:.2e} max|dp|(first 6)={dp:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
             ok = ok and good
             x1.free()
         x.free()
