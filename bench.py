@@ -217,7 +217,7 @@ def run_ours(args):
             return False
         ob = fl.Observer(on_iteration=on_iter)
         st = fl.LBFGS(prob, x, Memory=mem, Warning=False, MaxIteration=W + K, observer=ob, comm=comm, offset=lo,
-                      n_global=n, time_kernels=time_kernels, fused=fused)
+                      n_global=n, time_kernels=time_kernels, fused=fused, device_search=DS)
         if "t1" not in mark:
             raise SystemExit(f"bench.py: optimizer stopped after {st.iterations} iterations (status {st.status}) "
                              f"before {last + 1}; lower --steps")
@@ -230,6 +230,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     fused = not args.plain
+    DS = {"auto": None, "on": True, "off": False}[args.device_search]
+    ds_active = fused and (DS is True or (DS is None and n_local <= (1 << 25))) and \
+        (comm is None or bool(fl.lib().flgpu_comm_uses_peer_memory(comm)))
     ms, mark, st, _ = timed_run(False, fused)
     clocks = sampler.stop(mark["t0"], mark["t1"]) if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -347,6 +350,9 @@ def run_ours(args):
                                          if fl.lib().flgpu_comm_uses_peer_memory(comm) else "ncclAllGather + combine kernel")),
                            "l2": "inputs (2 GiB/vector) exceed L2; no flush needed",
                            "line_search": LS_MODES[fused],
+                           "device_resident_search": (f"{args.device_search}: " + (
+                               "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
+                               "off at this size (host-driven, one round trip per trial)")),
                            "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "other_line_search_mode": other}
@@ -369,6 +375,8 @@ def main():
     ap.add_argument("--objective", default="rosenbrock", choices=["rosenbrock", "diag"],
                     help="diag = BASELINE.json configs[3] (with --mem 30 --log2n 31 --gpus 8); not the headline")
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--device-search", default="auto", choices=["auto", "on", "off"],
+                    help="flgpu_options.device_search; auto = up to 2^25 rows per GPU (same bits either way)")
     ap.add_argument("--plain", action="store_true", help="headline with opaque callbacks (no fused line-search evaluation)")
     ap.add_argument("--cpu-log2n", type=int, default=None, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

@@ -58,6 +58,8 @@ public:
                                double /*phid0*/, double /*incr*/, double /*a*/, const double * /*x0*/,
                                const double * /*p*/, double * /*xt*/, double * /*gt*/) {}
     virtual void search_result(double * /*out: FLGPU_SEARCH_RESULT_DOUBLES*/) {}
+    // algorithmic bytes of the last device_search(), known only once its evaluation count is (kernel timing)
+    virtual void credit_search_bytes(double /*bytes*/) {}
 
     // ---- primitives
     virtual void trial_x(double *x, const double *x0, const double *p, double a) = 0;  // x = x0 + a*p

@@ -452,6 +452,9 @@ void CudaBackend::device_search(bool strong, bool fdwithf, double c1, double c2a
     prob.search(&ctx, &A, n);
     time_end(t);
 }
+void CudaBackend::credit_search_bytes(double bytes) {
+    if (timing) times[time_index("callback:device_search")].bytes += bytes;
+}
 void CudaBackend::search_result(double *out) {
     std::memcpy(out, host_pinned + NSLOTS + 8, FLGPU_SEARCH_RESULT_DOUBLES * sizeof(double));
 }

@@ -80,6 +80,7 @@ public:
     void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
                        double a, const double *x0, const double *p, double *xt, double *gt) override;
     void search_result(double *out) override;
+    void credit_search_bytes(double bytes) override;
     void trial_x(double *x, const double *x0, const double *p, double a) override;
     void dot(const double *a, const double *b, int slot) override;
     void neg(double *p, const double *g) override;

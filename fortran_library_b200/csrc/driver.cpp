@@ -154,6 +154,7 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
         B.search_result(res);
         st.n_trials += (int64_t)res[2]; st.n_f += (int64_t)res[3]; st.n_fd += (int64_t)res[4];
         st.n_f_fd += (int64_t)res[5]; st.n_f_only_trials += (int64_t)res[6];
+        B.credit_search_bytes(8.0 * (double)B.n * (2.0 * (res[3] + res[4] + res[5]) + 4.0));   // 2n per evaluation + the store
         SearchResult r;
         r.a = res[0]; r.fx = res[1]; r.trials = (int64_t)res[2];
         return r;
