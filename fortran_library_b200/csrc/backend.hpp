@@ -32,6 +32,7 @@ public:
     virtual ~Backend() {}
     int64_t n = 0;          // local rows
     int64_t launches = 0;   // library kernels enqueued
+    int64_t callback_launches = 0;   // objective callbacks invoked (f, fd, f_fd, fused, search): one kernel each for the built-ins
     int64_t syncs = 0;      // host synchronisations
 
     // ---- memory (library-owned work space, f90:413-415, 435, 1476)

@@ -419,16 +419,19 @@ void CudaBackend::eval_f(const double *x) {
     const int t = time_begin("callback:f", 8.0 * n);
     prob.f(&ctx, R + SL_F, x, n);
     time_end(t);
+    callback_launches++;
 }
 void CudaBackend::eval_g(const double *x, double *g) {
     const int t = time_begin("callback:fd", 16.0 * n);
     prob.fd(&ctx, g, x, n);
     time_end(t);
+    callback_launches++;
 }
 void CudaBackend::eval_fg(const double *x, double *g) {
     const int t = time_begin("callback:f_fd", 16.0 * n);
     prob.f_fd(&ctx, R + SL_F, g, x, n);
     time_end(t);
+    callback_launches++;
 }
 
 void CudaBackend::fused_eval(int flags, double a, const double *x0, const double *p, double *x_out,
@@ -438,6 +441,7 @@ void CudaBackend::fused_eval(int flags, double a, const double *x0, const double
     const int t = time_begin(name, 8.0 * n * words);
     prob.fused(&ctx, flags, R + SL_F, R + SL_GP, x_out, g_out, x0, p, a, n);
     time_end(t);
+    callback_launches++;
 }
 
 void CudaBackend::device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0,
@@ -451,6 +455,7 @@ void CudaBackend::device_search(bool strong, bool fdwithf, double c1, double c2a
     const int t = time_begin("callback:device_search", 0.0);   // bytes depend on the trial count: see flgpu_stats
     prob.search(&ctx, &A, n);
     time_end(t);
+    callback_launches++;
 }
 void CudaBackend::credit_search_bytes(double bytes) {
     if (timing) times[time_index("callback:device_search")].bytes += bytes;

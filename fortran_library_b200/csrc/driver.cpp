@@ -174,7 +174,7 @@ bool observe(const Params &P, Backend &B, const flgpu_stats &st, int64_t it, dou
     flgpu_iter_info info;
     info.iteration = it; info.n_local = B.n; info.step = a; info.f = f; info.phid0 = phid0;
     info.trials = trials; info.p_dev = p; info.x_dev = x; info.g_dev = g; info.stream = B.stream_handle();
-    info.gpu_launches = B.launches; info.callbacks = st.n_f + st.n_fd + st.n_f_fd; info.total_trials = st.n_trials;
+    info.gpu_launches = B.launches; info.callbacks = B.callback_launches; info.total_trials = st.n_trials;
     return P.observer(P.observer_user, &info) != 0;
 }
 

@@ -136,7 +136,8 @@ typedef struct flgpu_iter_info {
     const double *p_dev, *x_dev, *g_dev;
     void *stream;
     int64_t gpu_launches; /* library kernels enqueued so far in this call */
-    int64_t callbacks;    /* f + fd + f_fd invocations so far in this call */
+    int64_t callbacks;    /* objective callbacks invoked so far in this call (f, fd, f_fd, fused, search: one kernel
+                             launch each for the built-in objectives) */
     int64_t total_trials; /* trial points formed so far in this call */
 } flgpu_iter_info;
 typedef int (*flgpu_observer_fn)(void *user, const flgpu_iter_info *info);

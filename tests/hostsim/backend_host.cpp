@@ -75,13 +75,14 @@ public:
     void upload(double *dst, const double *user_x, int) override { std::memcpy(dst, user_x, sizeof(double) * n); }
     void download(double *user_x, const double *src, int) override { std::memcpy(user_x, src, sizeof(double) * n); }
 
-    void eval_f(const double *x) override { prob.f(&ctx, &slots[flgpu::SL_F], x, n); }
-    void eval_g(const double *x, double *g) override { prob.fd(&ctx, g, x, n); }
-    void eval_fg(const double *x, double *g) override { prob.f_fd(&ctx, &slots[flgpu::SL_F], g, x, n); }
+    void eval_f(const double *x) override { prob.f(&ctx, &slots[flgpu::SL_F], x, n); callback_launches++; }
+    void eval_g(const double *x, double *g) override { prob.fd(&ctx, g, x, n); callback_launches++; }
+    void eval_fg(const double *x, double *g) override { prob.f_fd(&ctx, &slots[flgpu::SL_F], g, x, n); callback_launches++; }
 
     bool fused_available() const override { return prob.fused != nullptr; }
     void fused_eval(int flags, double a, const double *x0, const double *p, double *x_out, double *g_out) override {
         prob.fused(&ctx, flags, &slots[flgpu::SL_F], &slots[flgpu::SL_GP], x_out, g_out, x0, p, a, n);
+        callback_launches++;
     }
     void trial_x(double *x, const double *x0, const double *p, double a) override {
         launches++;
