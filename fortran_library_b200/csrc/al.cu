@@ -270,7 +270,7 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
 
     flgpu_problem L;
     L.f = al_f; L.fd = al_fd; L.f_fd = al_ffd;       // the reference always passes f_fd = L_Ld / L_Ld_fdwithf
-    L.user = &S; L.fused = nullptr; L.search = nullptr;
+    L.user = &S; L.fused = nullptr; L.search = nullptr; L.search_caps = 0;
     flgpu_eval_ctx ctx;
     ctx.user = prob->user; ctx.stream = (void *)s; ctx.offset = in.offset; ctx.n_global = in.n_global ? in.n_global : n;
     ctx.rank = S.comm ? S.comm->rank : 0; ctx.nranks = G; ctx.device = dev;

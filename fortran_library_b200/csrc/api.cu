@@ -163,6 +163,7 @@ void ref_adapter_init(RefAdapter &A, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu
     prob->f = ad_f; prob->fd = ad_fd; prob->f_fd = f_fd ? ad_ffd : nullptr; prob->user = &A;
     prob->fused = nullptr;
     prob->search = nullptr;
+    prob->search_caps = 0;
     if (A.cb_space == FLGPU_SPACE_DEVICE) {
         {
             std::lock_guard<std::mutex> lock(g_fused_mu);

@@ -75,7 +75,8 @@ public:
     bool fused_available() const override { return prob.fused != nullptr; }
     void fused_eval(int flags, double a, const double *x0, const double *p, double *x_out, double *g_out) override;
     bool device_search_available() const override {
-        return prob.search != nullptr && (ctx.nranks == 1 || (comm && comm->p2p));
+        return prob.search != nullptr &&
+               (ctx.nranks == 1 || (comm && comm->p2p && (prob.search_caps & FLGPU_SEARCH_ROW_SHARDS)));
     }
     void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
                        double a, const double *x0, const double *p, double *xt, double *gt) override;

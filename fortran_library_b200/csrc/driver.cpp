@@ -13,7 +13,7 @@
 //    the convergence tests of After() are applied to the scalars that chain returns.
 // Every branch, comparison, default and exit test follows the reference statement by statement.
 #include "driver.hpp"
-#include "search_core.hpp"
+#include "../../include/flgpu_search_core.hpp"
 
 #include <cmath>
 #include <cstdio>
@@ -51,7 +51,7 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
 namespace {
 
 // One line search along p from x0 (device buffers); trial points go to xt, trial gradients to gt.  The reference's
-// control flow is SearchCore (search_core.hpp); this class supplies the evaluations: asynchronous kernels plus one
+// control flow is SearchCore (flgpu_search_core.hpp); this class supplies the evaluations: asynchronous kernels plus one
 // host round trip whenever a value steers a branch.
 struct Search : SearchCore<Search> {
     Backend &B;

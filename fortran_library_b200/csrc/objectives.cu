@@ -15,7 +15,7 @@
 #include <mutex>
 
 #include "backend_cuda.cuh"
-#include "search_core.hpp"
+#include "../../include/flgpu_search_core.hpp"
 
 namespace flgpu {
 
@@ -517,9 +517,9 @@ using namespace flgpu;
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {
-    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; return 0;
-    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; return 0;
-    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; return 0;
+    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; return 0;
+    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; return 0;
+    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; return 0;
     }
     return 1;
 }

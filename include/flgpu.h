@@ -81,7 +81,7 @@ typedef void (*flgpu_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *f_d
 
 /* Optional DEVICE-RESIDENT line search (an extension beyond flgpu_fused_fn).  One cooperative kernel runs the whole
  * Wolfe / Strong-Wolfe search of the reference (f90:1286-1698) on the device: every thread executes the same state
- * machine (csrc/search_core.hpp, the source the host driver uses too), every evaluation is a grid-wide reduction with
+ * machine (include/flgpu_search_core.hpp, the source the host driver uses too), every evaluation is a grid-wide reduction with
  * the library's fixed summation order, and the accepted point and gradient are stored by the same kernel -- no host
  * round trip per trial.  result_dev receives FLGPU_SEARCH_RESULT_DOUBLES doubles:
  *   [0] accepted step a  [1] f at it  [2] trial points formed  [3] f calls  [4] fd calls  [5] f_fd calls
@@ -90,6 +90,7 @@ typedef void (*flgpu_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *f_d
  * trades the partial sums with the other ranks inside the kernel (peer-memory mailboxes; needs the peer-memory
  * exchange, not the ncclAllGather fallback). */
 #define FLGPU_SEARCH_RESULT_DOUBLES 8
+#define FLGPU_SEARCH_ROW_SHARDS 1
 typedef struct flgpu_search_args {
     const double *x0_dev, *p_dev;   /* start point and direction */
     double *x_out, *g_out;          /* accepted point and its gradient */
@@ -108,6 +109,7 @@ typedef struct flgpu_problem {
     void *user;
     flgpu_fused_fn fused; /* optional (NULL = trial points are materialised and f / fd / f_fd are called) */
     flgpu_search_fn search; /* optional (NULL = the host drives the search, one round trip per evaluation) */
+    int search_caps;        /* FLGPU_SEARCH_ROW_SHARDS if `search` handles flgpu_search_args.comm != NULL; else 0 */
 } flgpu_problem;
 
 /* ------------------------------------------------------------------ options / results */

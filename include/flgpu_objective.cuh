@@ -22,12 +22,15 @@
 // Compile the including file with nvcc -std=c++17 for sm_100a and link libflgpu.so.  Vectors are 16-byte aligned (they are the
 // library's own work space).
 #pragma once
+#include <cooperative_groups.h>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "flgpu.h"
+#include "flgpu_search_core.hpp"
 
 namespace flgpu_obj {
 
@@ -83,9 +86,9 @@ struct Args {
     unsigned int *ticket;
 };
 
+// this thread's share of the units, in grid-stride order (shared by objective_kernel and search_kernel: same bits)
 template <class Obj, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
-__global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a) {
-    double fsum = 0.0, gpsum = 0.0;
+__device__ __forceinline__ void accumulate(const Obj &obj, const Args &a, double &fsum, double &gpsum) {
     const int64_t nu = a.n >> 1;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
@@ -125,6 +128,12 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a)
         if (WRITE_G) a.g_out[k] = g;
         if (WANT_GP) gpsum = fma(g, pv, gpsum);
     }
+}
+
+template <class Obj, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
+__global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a) {
+    double fsum = 0.0, gpsum = 0.0;
+    accumulate<Obj, FUSED, WANT_F, WANT_GP, WRITE_X, WRITE_G>(obj, a, fsum, gpsum);
     if (WANT_F && WANT_GP) {
         double acc[2] = {fsum, gpsum};
         double *out[2] = {a.f_out, a.gp_out};
@@ -140,6 +149,101 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a)
     }
 }
 
+// ---- device-resident line search (flgpu_search_fn) for functor objectives: the whole Wolfe / Strong-Wolfe search in
+// one cooperative kernel.  Every thread runs the same SearchCore state machine (flgpu_search_core.hpp, the source the
+// host driver compiles) on the same values; an evaluation = accumulate() + block tree + one grid barrier + the
+// fixed-order sum over blocks, repeated by every block.  Same grid as objective_kernel => same bits as the host-driven
+// fused search => same decisions.  Single GPU (row-sharded runs fall back to the host-driven search).
+struct SearchArgs {
+    Args o;                                  // x = x0; x_out / g_out = accepted point / gradient
+    double c1, c2abs, fx0, phid0, incr, a0;
+    int strong, fdwithf;
+    double *partials;                        // [2][gridDim.x][2]
+    double *result;
+};
+
+template <class Obj>
+struct DevSearch : flgpu::SearchCore<DevSearch<Obj>> {
+    const Obj &obj;
+    const SearchArgs &K;
+    double (*sh)[kThreads / 32];
+    double *bc;
+    double f_cur = 0.0, gp_cur = 0.0, a_x = 0.0, a_g = 0.0;
+    bool have_x = false, have_g = false;
+    int parity = 0;
+    double trials = 0.0, n_f = 0.0, n_fd = 0.0, n_ffd = 0.0, n_fonly = 0.0;
+    __device__ DevSearch(const Obj &o, const SearchArgs &k, double (*s)[kThreads / 32], double *b)
+        : obj(o), K(k), sh(s), bc(b) {}
+    template <bool F, bool GP>
+    __device__ void eval() {
+        constexpr int NACC = (F && GP) ? 2 : 1;
+        Args o = K.o;
+        o.a = a_x;
+        double fsum = 0.0, gpsum = 0.0;
+        accumulate<Obj, true, F, GP, false, false>(obj, o, fsum, gpsum);
+        double acc[2] = {F ? fsum : gpsum, gpsum};
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int i = 0; i < NACC; i++) {
+            const double v = warp_sum(acc[i]);
+            if (lane == 0) sh[i][warp] = v;
+        }
+        __syncthreads();
+        double *part = K.partials + (size_t)parity * gridDim.x * 2;
+        if (threadIdx.x < NACC) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
+            part[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+        }
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+        if (warp < NACC) {
+            double s = 0.0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&part[(size_t)b * 2 + warp]);
+            s = warp_sum(s);
+            if (lane == 0) bc[warp] = s;
+        }
+        __syncthreads();
+        if (F) f_cur = bc[0];
+        if (GP) gp_cur = bc[NACC - 1];
+        __syncthreads();
+        parity ^= 1;
+    }
+    __device__ void form(double step) { a_x = step; have_x = true; trials += 1.0; }
+    __device__ void call_f() { eval<true, false>(); n_f += 1.0; }
+    __device__ void call_fd() { eval<false, true>(); a_g = a_x; have_g = true; n_fd += 1.0; }
+    __device__ void call_ffd() { eval<true, true>(); a_g = a_x; have_g = true; n_ffd += 1.0; }
+    __device__ double slope() { return gp_cur; }
+    __device__ double fx() { return f_cur; }
+    __device__ void set_fx(double v) { f_cur = v; }
+    __device__ void adopt_pre() {}
+    __device__ void count_f_only() { n_fonly += 1.0; }
+};
+
+template <class Obj>
+__global__ void __launch_bounds__(kThreads, 4) search_kernel(Obj obj, SearchArgs K) {
+    __shared__ double sh[2][kThreads / 32];
+    __shared__ double bc[2];
+    DevSearch<Obj> S(obj, K, sh, bc);
+    S.c1 = K.c1; S.c2abs = K.c2abs; S.fx0 = K.fx0; S.phid0 = K.phid0; S.incr = K.incr;
+    S.fdwithf = K.fdwithf != 0; S.a = K.a0; S.f_cur = K.fx0; S.pre = 0;
+    if (K.strong) S.strongwolfe(); else S.wolfe();
+    Args o = K.o;
+    double f0 = 0.0, g0 = 0.0;
+    if (S.have_x && S.have_g && S.a_x == S.a_g) {
+        o.a = S.a_x;
+        accumulate<Obj, true, false, false, true, true>(obj, o, f0, g0);
+    } else {                                  // never taken by the reference's searchers; kept for fidelity
+        if (S.have_x) { o.a = S.a_x; accumulate<Obj, true, false, false, true, false>(obj, o, f0, g0); }
+        if (S.have_g) { o.a = S.a_g; accumulate<Obj, true, false, false, false, true>(obj, o, f0, g0); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
+        K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly; K.result[7] = 0.0;
+    }
+}
+
 template <class Obj>
 struct Callbacks {
     template <bool FUSED, bool F, bool GP, bool WX, bool WG>
@@ -151,13 +255,38 @@ struct Callbacks {
         flgpu_reduction_workspace(ctx->stream, &A.partials, &A.ticket, &max_blocks);   // per-stream, library-owned
         A.x = x; A.p = p; A.a = a; A.x_out = x_out; A.g_out = g_out; A.f_out = f_dev; A.gp_out = gp_dev;
         A.n = n; A.offset = ctx->offset;
+        objective_kernel<Obj, FUSED, F, GP, WX, WG><<<grid_for(n, max_blocks), kThreads, 0, s>>>(*(const Obj *)ctx->user, A);
+    }
+    static int grid_for(int64_t n, int max_blocks) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         int64_t need = (n / 2 + kThreads) / kThreads, grid = (int64_t)sms * 4;       // one full wave of resident CTAs
         if (grid > max_blocks) grid = max_blocks;
         if (need < grid) grid = need < 1 ? 1 : need;
-        objective_kernel<Obj, FUSED, F, GP, WX, WG><<<(int)grid, kThreads, 0, s>>>(*(const Obj *)ctx->user, A);
+        return (int)grid;
+    }
+    static void search(const flgpu_eval_ctx *ctx, const flgpu_search_args *A, int64_t n) {
+        if (A->comm) { std::fprintf(stderr, "flgpu_obj: the header's device-resident search is single-GPU\n"); std::abort(); }
+        SearchArgs K;
+        int max_blocks = 0;
+        flgpu_reduction_workspace(ctx->stream, &K.partials, &K.o.ticket, &max_blocks);
+        K.o.partials = K.partials;
+        K.o.x = A->x0_dev; K.o.p = A->p_dev; K.o.a = 0.0; K.o.x_out = A->x_out; K.o.g_out = A->g_out;
+        K.o.f_out = nullptr; K.o.gp_out = nullptr; K.o.n = n; K.o.offset = ctx->offset;
+        K.c1 = A->c1; K.c2abs = A->c2abs; K.fx0 = A->fx0; K.phid0 = A->phid0; K.incr = A->incr; K.a0 = A->a;
+        K.strong = A->strong; K.fdwithf = A->fdwithf; K.result = A->result_dev;
+        int resident = 0, sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, search_kernel<Obj>, kThreads, 0);
+        int grid = grid_for(n, max_blocks);
+        if (grid > resident * sms) grid = resident * sms;
+        Obj obj = *(const Obj *)ctx->user;
+        void *params[] = {&obj, &K};
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)search_kernel<Obj>, dim3(grid), dim3(kThreads), params, 0,
+                                                    (cudaStream_t)ctx->stream);
+        if (e != cudaSuccess) { std::fprintf(stderr, "flgpu_obj: cooperative launch failed: %s\n", cudaGetErrorString(e)); std::abort(); }
     }
     static void f(const flgpu_eval_ctx *ctx, double *f_dev, const double *x, int64_t n) {
         launch<false, true, false, false, false>(ctx, f_dev, nullptr, nullptr, nullptr, x, nullptr, 0.0, n);
@@ -194,14 +323,15 @@ struct Callbacks {
 
 // `obj` must stay alive while the problem is in use (the callbacks read it through ctx->user).
 template <class Obj>
-inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool with_fused = true) {
+inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool with_fused = true, bool with_search = true) {
     flgpu_problem p;
     p.f = Callbacks<Obj>::f;
     p.fd = Callbacks<Obj>::fd;
     p.f_fd = with_f_fd ? Callbacks<Obj>::f_fd : nullptr;
     p.user = (void *)obj;
     p.fused = with_fused ? Callbacks<Obj>::fused : nullptr;
-    p.search = nullptr;
+    p.search = (with_fused && with_search) ? Callbacks<Obj>::search : nullptr;
+    p.search_caps = 0;                        // single GPU: row-sharded runs use the host-driven search
     return p;
 }
 

@@ -1,4 +1,5 @@
-// search_core.hpp -- the reference's line searchers as ONE piece of source for the host driver and for device code.
+// flgpu_search_core.hpp -- the reference's line searchers as ONE piece of source for the host driver and for device
+// code (libflgpu's own kernels and include/flgpu_objective.cuh).
 //
 // Wolfe / Wolfe_fdwithf (f90:1286-1459, quadratic zoom f90:1347-1370) and StrongWolfe / StrongWolfe_fdwithf
 // (f90:1462-1698, cubic zoom f90:1557-1579) of NonlinearOptimization.f90, statement by statement.  The control flow

@@ -228,6 +228,7 @@ void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->f = obj_f; out->fd = obj_fd; out->f_fd = obj_ffd; out->user = (void *)(intptr_t)kind;
     out->fused = obj_fused;
     out->search = nullptr;
+    out->search_caps = 0;
 }
 
 void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {

@@ -525,6 +525,15 @@ def test_user_objective_header(fl, user_objective_lib, which, n):
     x = x0.copy()
     st = fl.ConjugateGradient(prob, x, Method="PR", Warning=False, MaxIteration=300)
     assert _cases.rel(x, xr) < 1e-7
+    # the header's device-resident search (one cooperative kernel per line search) == the host-driven fused search
+    res = []
+    for dev in (False, True):
+        x = x0.copy()
+        ob = fl.Observer()
+        st = fl.LBFGS(prob, x, Memory=6, Warning=False, MaxIteration=80, observer=ob, device_search=dev)
+        res.append((x, ob.rows, st.n_trials, st.n_f_fd, st.n_f, st.n_fd, st.host_syncs))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1] == res[1][1] and res[0][2:6] == res[1][2:6]
+    assert res[1][6] < res[0][6]
 
 
 # ----------------------------------------------------------------------------- AugmentedLagrangian
