@@ -381,8 +381,8 @@ def main():
     ap.add_argument("--cpu-log2n", type=int, default=None, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
-    if args.cpu_log2n is None:       # bounded CPU sample: ~25 s of one core for the reference arm, ~2 s inside our arm
-        args.cpu_log2n = 23 if args.impl == "reference" else 21
+    if args.cpu_log2n is None:       # bounded CPU sample: ~40 s of one core for the reference arm, ~5 s inside our arm
+        args.cpu_log2n = 23 if args.impl == "reference" else 22
     if args.warmup < 0 or args.steps < 1:
         raise SystemExit("need --steps >= 1 and --warmup >= 0")
     return run_reference(args) if args.impl == "reference" else run_ours(args)
