@@ -374,7 +374,8 @@ def main():
     ap.add_argument("--mem", type=int, default=MEM)
     ap.add_argument("--objective", default="rosenbrock", choices=["rosenbrock", "diag"],
                     help="diag = BASELINE.json configs[3] (with --mem 30 --log2n 31 --gpus 8); not the headline")
-    ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--e2e-steps", type=int, default=100,
+                    help="main-loop iterations of the end-to-end optimizer call (its 487-trial prologue is amortised over them)")
     ap.add_argument("--device-search", default="auto", choices=["auto", "on", "off"],
                     help="flgpu_options.device_search; auto = up to 2^25 rows per GPU (same bits either way)")
     ap.add_argument("--plain", action="store_true", help="headline with opaque callbacks (no fused line-search evaluation)")
