@@ -75,6 +75,7 @@ struct Search : SearchCore<Search> {
     double fx() { if (f_pending) sync(); return fx_; }
     void set_fx(double v) { f_pending = false; fx_ = v; }
     void count_f_only() { st.n_f_only_trials++; }
+    static bool aborted() { return false; }   // the reference searches until its own exit tests fire
 
     // Fused mode (flgpu_fused_fn): a trial point exists only as its step a_x until the search returns;
     // each callback of the reference becomes one probe kernel that forms x0+a_x*p on the fly, and
@@ -155,6 +156,9 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
         st.n_trials += (int64_t)res[2]; st.n_f += (int64_t)res[3]; st.n_fd += (int64_t)res[4];
         st.n_f_fd += (int64_t)res[5]; st.n_f_only_trials += (int64_t)res[6];
         B.credit_search_bytes(8.0 * (double)B.n * (2.0 * (res[3] + res[4] + res[5]) + 4.0));   // 2n per evaluation + the store
+        if (res[7] < 0.0)
+            std::printf(" Line search warning: the device-resident search gave up after %.0f evaluations "
+                        "(does the objective return NaN?)\n", res[3] + res[4] + res[5]);
         SearchResult r;
         r.a = res[0]; r.fx = res[1]; r.trials = (int64_t)res[2];
         return r;

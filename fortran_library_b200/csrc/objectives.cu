@@ -236,6 +236,8 @@ struct SearchKArgs {
     double *glob;               // [2][2] rank-summed values for the other blocks
 };
 
+constexpr double kEvalBudget = 100000.0;
+
 template <int KIND>
 struct DevSearch : SearchCore<DevSearch<KIND>> {
     const SearchKArgs &K;
@@ -314,6 +316,9 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
     __device__ void set_fx(double v) { f_cur = v; }
     __device__ void adopt_pre() {}
     __device__ void count_f_only() { n_fonly += 1.0; }
+    // a kernel must terminate whatever the objective returns: after kEvalBudget evaluations the search gives up
+    // (result[7] < 0 tells the host); a finite objective needs a few hundred at most
+    __device__ bool aborted() const { return n_f + n_fd + n_ffd > kEvalBudget; }
 };
 
 template <int KIND>
@@ -338,7 +343,8 @@ __global__ void __launch_bounds__(kThreads, 4) search_kernel(SearchKArgs K) {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
-        K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly; K.result[7] = (double)S.nexch;
+        K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly;
+        K.result[7] = S.aborted() ? -1.0 : (double)S.nexch;
         if (K.G > 1) *K.dseq = S.seq_base + S.nexch;
     }
 }

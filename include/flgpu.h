@@ -85,7 +85,8 @@ typedef void (*flgpu_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *f_d
  * the library's fixed summation order, and the accepted point and gradient are stored by the same kernel -- no host
  * round trip per trial.  result_dev receives FLGPU_SEARCH_RESULT_DOUBLES doubles:
  *   [0] accepted step a  [1] f at it  [2] trial points formed  [3] f calls  [4] fd calls  [5] f_fd calls
- *   [6] f-only trials (branch D)  [7] rank exchanges made inside the kernel
+ *   [6] f-only trials (branch D)  [7] rank exchanges made inside the kernel, or -1 if the search gave up after its
+ *   evaluation budget (100000: a kernel must terminate even if the objective returns NaN, where the reference spins)
  * The decisions and the values are those of the host-driven fused search, bit for bit.  On row-sharded runs block 0
  * trades the partial sums with the other ranks inside the kernel (peer-memory mailboxes; needs the peer-memory
  * exchange, not the ncclAllGather fallback). */

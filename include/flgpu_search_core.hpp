@@ -10,6 +10,9 @@
 //     fx() / set_fx(v)      Fortran `fx` (may be fetched lazily)
 //     adopt_pre()           the first trial was already formed/evaluated by the caller's chain (pre != 0)
 //     count_f_only()        statistics hook (branch D's f-only probes, f90:1518-1520)
+//     aborted()             checked at the top of every loop; the host version always answers false (the reference has
+//                           no such exit: a NaN objective makes its zoom spin forever, f90:1684,1695), the device
+//                           version answers true after an evaluation budget so a kernel can never hang the GPU
 // driver.cpp derives the host version (asynchronous kernels + one host round trip per evaluation); a device kernel can
 // derive a version whose evaluations are grid-wide cooperative reductions.  Arithmetic that the host compiles without
 // FMA contraction (-ffp-contract=off) is written with nf_mul / nf_add so device code rounds identically.
@@ -61,6 +64,7 @@ struct SearchCore {
     FLGPU_SC_HD void wolfe_zoom(double &low, double &up, double &flow, double &fup, double &phidlow) {
         double phidlow_m_a = nf_mul(phidlow, a);
         for (;;) {
+            if (self().aborted()) return;
             a = nf_mul(phidlow_m_a, a) / 2.0 / nf_add(nf_add(flow, phidlow_m_a), -fup);
             if (!(a > low && a < up)) a = (low + up) / 2.0;
             self().form(a); self().call_f();
@@ -85,6 +89,7 @@ struct SearchCore {
         if (pre == 0) { self().form(a); self().call_f(); } else { self().adopt_pre(); }          // f90:1306
         if (!armijo_violated()) {
             for (;;) {
+            if (self().aborted()) return;
                 aold = a; fold = self().fx();
                 a = nf_mul(aold, incr); self().form(a); self().call_f();
                 if (armijo_violated()) {
@@ -102,6 +107,7 @@ struct SearchCore {
             }
         } else {
             for (;;) {
+            if (self().aborted()) return;
                 aold = a; fold = self().fx();
                 a = aold / incr; self().form(a); self().call_f();
                 if (!armijo_violated()) {
@@ -122,6 +128,7 @@ struct SearchCore {
     // The six zoom arguments alias the caller's locals exactly as the Fortran by-reference dummies do.
     FLGPU_SC_HD void strong_zoom(double &low, double &up, double &flow, double &fup, double &phidlow, double &phidup) {
         for (;;) {
+            if (self().aborted()) return;
             double d1 = nf_add(nf_add(phidlow, phidup), -(nf_mul(3.0, flow - fup) / (low - up)));
             double d2 = up - low;
             const double disc = nf_add(nf_mul(d1, d1), -nf_mul(phidlow, phidup));
@@ -155,7 +162,8 @@ struct SearchCore {
             phidnew = (pre == 3) ? pre_gp : self().slope();
             if (phidnew > 0.0) {
                 if (fabs(phidnew) <= c2abs) return;
-                for (;;) {                                               // f90:1488-1497
+                for (;;) {
+            if (self().aborted()) return;                                               // f90:1488-1497
                     aold = a; fold = self().fx(); phidold = phidnew;
                     a = aold / incr; self().form(a); both(); phidnew = self().slope();
                     if (self().fx() >= fold || phidnew <= 0.0) {
@@ -166,7 +174,8 @@ struct SearchCore {
                     if (a < 1e-15) return;
                 }
             } else {
-                for (;;) {                                               // f90:1499-1515
+                for (;;) {
+            if (self().aborted()) return;                                               // f90:1499-1515
                     aold = a; fold = self().fx(); phidold = phidnew;
                     a = nf_mul(aold, incr); self().form(a); both(); phidnew = self().slope();
                     if (armijo_violated() || self().fx() >= fold) {
@@ -185,6 +194,7 @@ struct SearchCore {
             }
         } else {                                                         // f90:1517-1546
             for (;;) {
+            if (self().aborted()) return;
                 aold = a; fold = self().fx();
                 a = aold / incr; self().form(a); self().call_f();
                 self().count_f_only();
@@ -199,6 +209,7 @@ struct SearchCore {
                         return;
                     } else {
                         for (;;) {
+            if (self().aborted()) return;
                             aold = a; fold = self().fx(); phidold = phidnew;
                             a = aold / incr; self().form(a); both(); phidnew = self().slope();
                             if (self().fx() >= fold || phidnew <= 0.0) {

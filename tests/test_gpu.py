@@ -431,6 +431,18 @@ def test_device_resident_search_is_the_same_algorithm(fl, algo, name, kw, n):
     assert sb.host_syncs < sa.host_syncs            # the point of it: fewer host round trips
 
 
+def test_device_resident_search_terminates_on_nan():
+    """A NaN objective makes the reference's zoom spin forever (f90:1684,1695) -- acceptable on a CPU, not inside a GPU
+    kernel: the device-resident search gives up after its evaluation budget and says so."""
+    code = ("import sys; sys.path.insert(0, %r)\nimport numpy as np, fortran_library_b200 as fl\n"
+            "x = np.full(64, np.nan)\n"
+            "st = fl.LBFGS(fl.builtin_problem(fl.OBJ_QUARTIC), x, Memory=3, MaxIteration=0, device_search=True)\n"
+            "print('returned', st.iterations)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "returned" in r.stdout, r.stdout + r.stderr
+    assert "gave up after" in r.stdout
+
+
 # ----------------------------------------------------------------------------- user objectives (flgpu_objective.cuh)
 def _np_user_objective(which, n):
     """NumPy statement of tests/link/user_objective.cu (same operation order, no FMA)."""
