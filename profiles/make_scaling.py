@@ -15,9 +15,8 @@ base = rows[0][1]['value']
 out = ["# Scaling of the headline workload (bench.py, this round's builder runs; the driver re-measures at round end)", "",
        "## Strong scaling: n = 2^28 global (rows per GPU = 2^28 / N)", "",
        "LBFGS m=10, extended Rosenbrock, fused line search, 30 timed iterations after 3 warm-up, CUDA events, max over ranks.",
-       "Exchange per reduction: one kernel over IPC-mapped peer memory (DESIGN.md section 5). N = 1 and 8 are from the final",
-       "builds (N = 8: device-resident line search, auto mode at 2^25 rows per GPU); N = 2 and 4 from an earlier build",
-       "(host-driven search, cudaStreamSynchronize per trial).", "",
+       "Exchange per reduction: one kernel over IPC-mapped peer memory (DESIGN.md section 5). All four lines are from the final",
+       "build; device-resident line search in auto mode = on at N = 8 (2^25 rows per GPU), host-driven at N = 1, 2, 4.", "",
        "| GPUs | it/s | ms/step | speed-up | efficiency | kernel GB/s per GPU (whole step) | e2e it/s (host x) | plain-callback it/s |",
        "|---:|---:|---:|---:|---:|---:|---:|---:|"]
 for n, d in rows:
