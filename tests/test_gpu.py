@@ -787,6 +787,31 @@ def test_full_size_properties(fl):
     assert results[0] == results[1], "two identical runs must give identical bits"
 
 
+def test_beyond_int32_rows(fl):
+    """n = 2^31 + 4098 rows on one GPU (the reference's `dim` is a 32-bit integer; the flgpu_* entry points
+    take int64): 64-bit indexing in the start, objective, K1, K3 and line-search kernels.  Memory = 1 keeps the work
+    space at 7 vectors (112 GiB)."""
+    n = (1 << 31) + 4098
+    L = fl.lib()
+    x = fl.DeviceVector.start(fl.START_QUARTIC_U, n, seed=12345)
+    # the start kernel indexes with 64 bits: the tail equals a small vector generated at the same global offset
+    tail = fl.copy_to_numpy(x.ptr + 8 * (n - 1000), 1000)
+    assert np.array_equal(tail, O.start_vector(O.START_QUARTIC_U, 1000, seed=12345, offset=n - 1000, n_global=n))
+    out = fl.DeviceVector(1)
+    L.flgpu_vec_dot(x.ptr, x.ptr, n, out.ptr, None)
+    xx = out.numpy()[0]
+    assert abs(xx / n - 1.0 / 3.0) < 1e-4                      # u ~ U[0,1): E[u^2] = 1/3 over ALL 2^31+ rows
+    ob = fl.Observer()
+    st = fl.LBFGS(fl.builtin_problem(fl.OBJ_QUARTIC), x, Memory=1, Warning=False, MaxIteration=3, observer=ob)
+    assert st.iterations == 4 and st.status == fl.MAX_ITERATION
+    fs = [r[2] for r in ob.rows]
+    assert all(b < a for a, b in zip(fs, fs[1:]))               # f decreases at every accepted step
+    assert abs(fs[0]) < n / 5.0 * 1.01                          # f0 = sum u^4 ~ n/5: every row contributed once
+    tail2 = fl.copy_to_numpy(x.ptr + 8 * (n - 1000), 1000)
+    assert np.all(np.abs(tail2) < np.abs(tail) + 1e-300) and not np.array_equal(tail2, tail)   # the tail was optimised too
+    x.free()
+
+
 def test_full_size_cg_quartic(fl):
     """BASELINE configs[2]: CG DY and PR+ on the separable quartic, n = 2^28: monotone decrease and the
     closed-form symmetry of the problem (f = sum x^4 decreases; x stays in [0,1))."""
