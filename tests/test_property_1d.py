@@ -1,0 +1,77 @@
+"""Property-based check of the host control flow (driver.cpp + flgpu_search_core.hpp over the host simulator)
+against the oracle in ONE dimension, where no summation order exists: for random objectives, starts and tunables
+(WolfeConst1/2, Increment, Strong, Method, f_fd present or not) every trial point, every accepted step and the
+result must be IDENTICAL, bit for bit -- for ConjugateGradient (f90:193-394) and SteepestDescent (f90:55-188) through
+all four line searchers (f90:1286-1698).  (L-BFGS is excluded: its Gram-space recurrences reorder arithmetic even in
+one dimension; it is covered by the envelope and one-step tests.)"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import _cases
+import _hostsim as H
+import _oracle as O
+from test_hostsim import _py_problem
+
+capi = H.capi
+
+
+def _objective(kind, p, q, r):
+    """Families with different line-search behaviour; evaluated with Python floats (IEEE double)."""
+    if kind == "quartic":       # flat bottom: long grow loops
+        return (lambda x: p * (x - q) ** 4 + r * (x - q) ** 2), (lambda x: 4.0 * p * (x - q) ** 3 + 2.0 * r * (x - q))
+    if kind == "steep":         # Armijo fails first (branch D)
+        return (lambda x: 50.0 * p * (x - q) ** 2 + r), (lambda x: 100.0 * p * (x - q))
+    if kind == "cosh":          # asymmetric growth
+        return (lambda x: p * math.cosh(min(abs(x - q), 300.0)) + r), \
+               (lambda x: p * math.copysign(math.sinh(min(abs(x - q), 300.0)), x - q))
+    # "well": steep wall on one side
+    return (lambda x: p * (x - q) ** 2 + r * math.exp(min(-(x - q), 300.0))), \
+           (lambda x: 2.0 * p * (x - q) - r * math.exp(min(-(x - q), 300.0)))
+
+
+@settings(max_examples=400, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(algo=st.sampled_from(["cg", "sd"]), kind=st.sampled_from(["quartic", "steep", "cosh", "well"]),
+       p=st.floats(0.1, 10.0), q=st.floats(-2.0, 2.0), r=st.floats(0.01, 3.0), x0=st.floats(-3.0, 3.0),
+       method=st.sampled_from(["DY", "PR"]), strong=st.booleans(), use=st.booleans(),
+       c1=st.floats(1e-6, 0.3), c2frac=st.floats(0.05, 0.95), incr=st.floats(1.02, 3.0), fused=st.booleans())
+def test_cg_and_sd_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0, method, strong, use, c1, c2frac, incr,
+                                                        fused):
+    f, g = _objective(kind, p, q, r)
+    c2 = c1 + c2frac * (0.99 - c1)
+    opts = dict(Strong=strong, Warning=False, MaxIteration=12, WolfeConst1=c1, WolfeConst2=c2, Increment=incr)
+    fa = _cases.Fuse(f, g, limit=600)
+    cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
+    keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+    cbs = tuple(C.cast(k, C.c_void_p) for k in keep)
+    tr = O.Trace()
+    with np.errstate(all="ignore"):
+        if algo == "cg":
+            xa, s = O.cg(cbs, np.array([x0]), Method=method, use_ffd=use, trace=tr, **opts)
+        else:
+            xa, s = O.sd(cbs, np.array([x0]), use_ffd=use, trace=tr, **opts)
+    if any(not math.isfinite(v) for v in fa.xs) or fa.calls > fa.limit:
+        return                    # NaN / runaway steps: the reference itself has no defined behaviour there
+    fb = _cases.Fuse(f, g, limit=600)
+    prob = _py_problem(fb)
+    if not use:
+        prob.f_fd = None
+    L = H.lib()
+    o = capi.Options()
+    L.flgpu_hostsim_options_default(C.byref(o), int(algo == "cg"))
+    capi.apply_options(o, Method=method if algo == "cg" else None, **opts)
+    o.no_fused = int(not fused)     # _py_problem supplies no fused callback: both settings must take the plain path
+    ob = H.Observer()
+    o.observer = C.cast(ob.cb, C.c_void_p)
+    x = np.array([x0])
+    stt = capi.Stats()
+    fn = L.flgpu_hostsim_cg if algo == "cg" else L.flgpu_hostsim_sd
+    fn(C.byref(prob), C.byref(o), x.ctypes.data_as(C.c_void_p), C.c_int64(1), C.byref(stt))
+    assert fa.xs == fb.xs, "different trial points"
+    assert np.array_equal(x, xa, equal_nan=True)
+    assert stt.iterations == s.n_iter and stt.status == s.status
+    assert [r_[1:] for r_ in ob.rows] == [r_[1:] for r_ in tr.rows]
