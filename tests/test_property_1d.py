@@ -18,6 +18,7 @@ import _oracle as O
 from test_hostsim import _py_problem
 
 capi = H.capi
+COUNTS = {"compared": 0, "skipped": 0}      # how many generated cases reach the comparison (reported by the last test)
 
 
 def _objective(kind, p, q, r):
@@ -55,7 +56,9 @@ def test_cg_and_sd_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0,
         else:
             xa, s = O.sd(cbs, np.array([x0]), use_ffd=use, trace=tr, **opts)
     if any(not math.isfinite(v) for v in fa.xs) or fa.calls > fa.limit:
+        COUNTS["skipped"] += 1
         return                    # NaN / runaway steps: the reference itself has no defined behaviour there
+    COUNTS["compared"] += 1
     fb = _cases.Fuse(f, g, limit=600)
     prob = _py_problem(fb)
     if not use:
@@ -75,3 +78,9 @@ def test_cg_and_sd_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0,
     assert np.array_equal(x, xa, equal_nan=True)
     assert stt.iterations == s.n_iter and stt.status == s.status
     assert [r_[1:] for r_ in ob.rows] == [r_[1:] for r_ in tr.rows]
+
+
+def test_property_cases_are_not_vacuous():
+    """Runs after the property test (file order): most generated cases must have reached the bitwise comparison."""
+    total = COUNTS["compared"] + COUNTS["skipped"]
+    assert total == 0 or COUNTS["compared"] >= 0.7 * total, COUNTS
