@@ -80,6 +80,57 @@ def test_cg_and_sd_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0,
     assert [r_[1:] for r_ in ob.rows] == [r_[1:] for r_ in tr.rows]
 
 
+@pytest.mark.gpu
+@settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(algo=st.sampled_from(["cg", "sd"]), kind=st.sampled_from(["quartic", "steep", "cosh", "well"]),
+       p=st.floats(0.1, 10.0), q=st.floats(-2.0, 2.0), r=st.floats(0.01, 3.0), x0=st.floats(-3.0, 3.0),
+       method=st.sampled_from(["DY", "PR"]), strong=st.booleans(), use=st.booleans(),
+       c1=st.floats(1e-6, 0.3), c2frac=st.floats(0.05, 0.95), incr=st.floats(1.02, 3.0))
+def test_gpu_fortran_abi_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0, method, strong, use, c1, c2frac, incr):
+    """The same property through libflgpu.so's reference symbols on the GPU (host callbacks staged by the library):
+    __nonlinearoptimization_MOD_conjugategradient / _steepestdescent with every optional present."""
+    import fortran_library_b200 as fl
+    fl.require_gpu()
+    f, g = _objective(kind, p, q, r)
+    c2 = c1 + c2frac * (0.99 - c1)
+    opts = dict(Strong=strong, Warning=False, MaxIteration=12, WolfeConst1=c1, WolfeConst2=c2, Increment=incr)
+    fa = _cases.Fuse(f, g, limit=600)
+    cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
+    keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+    cbs = tuple(C.cast(k, C.c_void_p) for k in keep)
+    with np.errstate(all="ignore"):
+        if algo == "cg":
+            xa, s = O.cg(cbs, np.array([x0]), Method=method, use_ffd=use, **opts)
+        else:
+            xa, s = O.sd(cbs, np.array([x0]), use_ffd=use, **opts)
+    if any(not math.isfinite(v) for v in fa.xs) or fa.calls > fa.limit:
+        return
+    fb = _cases.Fuse(f, g, limit=600)
+    cf2, cfd2, cffd2 = _cases.make_ref_callbacks(fb.f, fb.g, fb.fg)
+    k2 = (fl.capi.REF_F_FN(cf2), fl.capi.REF_FD_FN(cfd2), fl.capi.REF_F_FD_FN(cffd2))
+    L = fl.lib()
+    x = np.array([x0])
+    common = (C.byref(C.c_int32(-1 if strong else 0)), C.byref(C.c_int32(0)), C.byref(C.c_int(12)), None, None,
+              C.byref(C.c_double(c1)), C.byref(C.c_double(c2)), C.byref(C.c_double(incr)))
+    L.flgpu_set_callback_space(fl.SPACE_HOST)
+    try:
+        if algo == "cg":
+            m = method.encode()
+            L.__getattr__("__nonlinearoptimization_MOD_conjugategradient")(
+                k2[0], k2[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), m, k2[2] if use else None, *common,
+                C.c_int(len(m)))
+        else:
+            L.__getattr__("__nonlinearoptimization_MOD_steepestdescent")(
+                k2[0], k2[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), k2[2] if use else None, *common)
+    finally:
+        L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+    stt = fl.capi.Stats()
+    L.flgpu_last_stats(C.byref(stt))
+    assert fa.xs == fb.xs, "different trial points"
+    assert np.array_equal(x, xa, equal_nan=True)
+    assert stt.iterations == s.n_iter and stt.status == s.status
+
+
 def test_property_cases_are_not_vacuous():
     """Runs after the property test (file order): most generated cases must have reached the bitwise comparison."""
     total = COUNTS["compared"] + COUNTS["skipped"]
