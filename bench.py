@@ -104,7 +104,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU baseline (oracle = checker, timed)
-def cpu_lbfgs(n_sample, mem, warmup, steps, n_target):
+def cpu_lbfgs(n_sample, mem, warmup, steps, n_target, objective="rosenbrock"):
     """Times the oracle (C restatement of the reference, strict IEEE, sequential sums, ONE thread -- the
     reference has no threading on this path) on a bounded sample of the same workload and
     scales the iteration rate linearly in n (a streaming workload)."""
@@ -115,9 +115,10 @@ def cpu_lbfgs(n_sample, mem, warmup, steps, n_target):
         def _on(self, user, it, dim, p, x, g, a, fx, phid0, trials):
             marks[it] = (time.perf_counter(), trials)
 
-    x0 = O.start_vector(O.START_ROSEN_PERT, n_sample, seed=SEED)
+    obj, start = (O.OBJ_DIAGQUAD, O.START_ZERO) if objective == "diag" else (O.OBJ_ROSENBROCK, O.START_ROSEN_PERT)
+    x0 = O.start_vector(start, n_sample, seed=SEED)
     tr = T(keep_vectors=False)
-    x, st = O.lbfgs(O.builtin_callbacks(O.OBJ_ROSENBROCK, 0, n_sample), x0, Memory=mem, use_ffd=True, Warning=False,
+    x, st = O.lbfgs(O.builtin_callbacks(obj, 0, n_sample), x0, Memory=mem, use_ffd=True, Warning=False,
                     MaxIteration=warmup + steps, trace=tr)
     first, last = mem + warmup - 1, mem + warmup + steps - 1
     if last not in marks:                      # converged early (never at these sizes)
@@ -140,11 +141,12 @@ def run_reference(args):
     n = 1 << args.log2n
     n_sample = 1 << min(args.log2n, args.cpu_log2n)
     t0 = time.time()
-    cb = cpu_lbfgs(n_sample, args.mem, args.warmup, args.steps, n)
+    cb = cpu_lbfgs(n_sample, args.mem, args.warmup, args.steps, n, args.objective)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload(n, args.mem), "timing": "host perf_counter around oracle iterations"},
+            "config": {"workload": workload(n, args.mem, args.objective),
+                       "timing": "host perf_counter around oracle iterations"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
