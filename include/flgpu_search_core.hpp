@@ -54,8 +54,11 @@ struct SearchCore {
 
     FLGPU_SC_HD Derived &self() { return *static_cast<Derived *>(this); }
     FLGPU_SC_HD void both() { if (fdwithf) self().call_ffd(); else { self().call_f(); self().call_fd(); } }
-    // fx > fx0 + c1*a*phid0
+    // The reference writes the sufficient-decrease test in two forms, `fx>fx0+c1*a*phid0` (f90:1311,1356,1502,1568,...)
+    // and `fx<=fx0+c1*a*phid0` (f90:1307,1328,1483,1521,...).  They are complements except for a NaN objective value,
+    // where both are false -- so both forms exist here and each site uses the one the reference uses.
     FLGPU_SC_HD bool armijo_violated() { return self().fx() > nf_add(fx0, nf_mul(nf_mul(c1, a), phid0)); }
+    FLGPU_SC_HD bool armijo_ok() { return self().fx() <= nf_add(fx0, nf_mul(nf_mul(c1, a), phid0)); }
     FLGPU_SC_HD static bool collapsed(double low, double up) {
         return fabs(up - low) < 1e-15 || fabs(up - low) / fmax(fabs(low), fabs(up)) < 1e-15;
     }
@@ -87,7 +90,7 @@ struct SearchCore {
     FLGPU_SC_HD void wolfe() {
         double aold, fold, atemp, ftemp, phidx;
         if (pre == 0) { self().form(a); self().call_f(); } else { self().adopt_pre(); }          // f90:1306
-        if (!armijo_violated()) {
+        if (armijo_ok()) {                                                           // f90:1307
             for (;;) {
             if (self().aborted()) return;
                 aold = a; fold = self().fx();
@@ -110,7 +113,7 @@ struct SearchCore {
             if (self().aborted()) return;
                 aold = a; fold = self().fx();
                 a = aold / incr; self().form(a); self().call_f();
-                if (!armijo_violated()) {
+                if (armijo_ok()) {                                                   // f90:1328
                     self().call_fd();
                     phidx = self().slope();
                     if (phidx < c2abs) {
@@ -157,7 +160,7 @@ struct SearchCore {
         } else {
             self().adopt_pre();
         }
-        if (!armijo_violated()) {
+        if (armijo_ok()) {                                               // f90:1483 / 1605
             if (!fdwithf) self().call_fd();
             phidnew = (pre == 3) ? pre_gp : self().slope();
             if (phidnew > 0.0) {
@@ -198,7 +201,7 @@ struct SearchCore {
                 aold = a; fold = self().fx();
                 a = aold / incr; self().form(a); self().call_f();
                 self().count_f_only();
-                if (!armijo_violated()) {
+                if (armijo_ok()) {                                       // f90:1521 / 1640
                     self().call_fd();
                     phidnew = self().slope();
                     if (fabs(phidnew) <= c2abs) return;

@@ -101,6 +101,9 @@ static void call_f(ls_t *L) { L->f(L->fx, L->x, &L->dim); g_st.n_f++; }
 static void call_fd(ls_t *L) { L->fd(L->fdx, L->x, &L->dim); g_st.n_fd++; }
 static void call_ffd(ls_t *L) { (void)L->f_fd(L->fx, L->fdx, L->x, &L->dim); g_st.n_ffd++; }
 static double slope(ls_t *L) { return dot(L->fdx, L->p, L->dim); }
+static int armijo_ok(ls_t *L) { /* fx<=fx0+c1*a*phid0 (f90:1307,1328,1483,1521): NOT the complement of the next for NaN */
+    return *L->fx <= L->fx0 + L->c1 * (*L->a) * L->phid0;
+}
 static int armijo_violated(ls_t *L) { /* fx>fx0+c1*a*phid0 */
     return *L->fx > L->fx0 + L->c1 * (*L->a) * L->phid0;
 }
@@ -148,7 +151,7 @@ static void wolfe_impl(double c1, double c2, orc_f_t f, orc_fd_t fd, double *x, 
     L.f = f; L.fd = fd; L.f_fd = NULL; L.x = x; L.x0 = x0; L.p = p; L.fdx = fdx; L.a = a; L.fx = fx;
     L.dim = dim;
     trial_x(&L); call_f(&L);                                                   /* f90:1306 */
-    if (!armijo_violated(&L)) {                                                /* f90:1307 */
+    if (armijo_ok(&L)) {                                                /* f90:1307 */
         for (;;) {
             aold = *a; fold = *fx;
             *a = aold * incrmt; trial_x(&L); call_f(&L);                       /* f90:1310 */
@@ -170,7 +173,7 @@ static void wolfe_impl(double c1, double c2, orc_f_t f, orc_fd_t fd, double *x, 
         for (;;) {
             aold = *a; fold = *fx;
             *a = aold / incrmt; trial_x(&L); call_f(&L);                       /* f90:1327 */
-            if (!armijo_violated(&L)) {
+            if (armijo_ok(&L)) {
                 call_fd(&L);
                 phidx = slope(&L);
                 if (phidx < L.c2_m_abs_phid0) {                                /* f90:1331 */
@@ -247,7 +250,7 @@ static void strongwolfe_impl(int fdwithf, double c1, double c2, orc_f_t f, orc_f
     /* f90:1482 / f90:1604 */
     trial_x(&L);
     if (fdwithf) call_ffd(&L); else call_f(&L);
-    if (!armijo_violated(&L)) {                                                 /* f90:1483 */
+    if (armijo_ok(&L)) {                                                 /* f90:1483 */
         if (!fdwithf) call_fd(&L);                                              /* f90:1484 */
         phidnew = slope(&L);
         if (phidnew > 0.0) {                                                    /* f90:1486 */
@@ -285,7 +288,7 @@ static void strongwolfe_impl(int fdwithf, double c1, double c2, orc_f_t f, orc_f
         for (;;) {
             aold = *a; fold = *fx;
             *a = aold / incrmt; trial_x(&L); call_f(&L);                        /* f90:1520 */
-            if (!armijo_violated(&L)) {                                         /* f90:1521 */
+            if (armijo_ok(&L)) {                                         /* f90:1521 */
                 call_fd(&L);
                 phidnew = slope(&L);
                 if (fabs(phidnew) <= L.c2_m_abs_phid0) { free(x0); return; }    /* f90:1524 */

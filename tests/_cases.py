@@ -166,6 +166,9 @@ TORTURE_1D = {
     "flat": (2.0, (lambda x: 1e-3 * _pw(x - 1.0, 2) + 1.0, lambda x: 2e-3 * (x - 1.0))),  # long grow loop (branch C)
     "cosh": (1.5, (lambda x: float(np.cosh(min(x, 700.0))), lambda x: float(np.sinh(min(x, 700.0))))),
     "wall": (0.2, _poly_wall(2.0, 41)),
+    # f is NaN beyond x = 2: the first trial lands there and `fx<=fx0+c1*a*phid0` (f90:1483) must read it as a
+    # violation, not as a pass (the `>` form of the test, f90:1502, is false for NaN too)
+    "nan_region": (-3.0, (lambda x: x * x if x < 2.0 else float("nan"), lambda x: 2.0 * x if x < 2.0 else float("nan"))),
 }
 
 
