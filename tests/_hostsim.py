@@ -60,6 +60,8 @@ def _run(fn_name, for_cg, kind, x, observer=None, use_ffd=True, offset=0, n_glob
     o = capi.Options()
     L.flgpu_hostsim_options_default(C.byref(o), int(for_cg))
     o.no_fused = int(not kw.pop("fused", True))
+    ds = kw.pop("device_search", False)          # the simulator's eager "device-resident" search: off unless asked
+    o.device_search = 2 if ds is None else int(bool(ds))
     capi.apply_options(o, **kw)
     o.offset, o.n_global = offset, n_global
     if observer is not None:

@@ -17,6 +17,7 @@
 #include "../../fortran_library_b200/csrc/backend.hpp"
 #include "../../fortran_library_b200/csrc/driver.hpp"
 #include "../../fortran_library_b200/csrc/lbfgs_gram.hpp"
+#include "../../include/flgpu_search_core.hpp"
 #include "../../oracle/oracle.h"
 
 namespace {
@@ -84,6 +85,54 @@ public:
         prob.fused(&ctx, flags, &slots[flgpu::SL_F], &slots[flgpu::SL_GP], x_out, g_out, x0, p, a, n);
         callback_launches++;
     }
+    // "device-resident" search on the host: the same SearchCore the CUDA search kernels instantiate, with EAGER
+    // evaluations (every call computes f / f'.p at once, as a cooperative kernel does) instead of the driver's lazy
+    // ones -- so the driver's device-search branch and the eager evaluator semantics are testable without a GPU.
+    struct EagerSearch : flgpu::SearchCore<EagerSearch> {
+        HostBackend &B;
+        const double *x0, *p;
+        double f_cur = 0.0, gp_cur = 0.0, a_x = 0.0, a_g = 0.0;
+        bool have_x = false, have_g = false;
+        double trials = 0, n_f = 0, n_fd = 0, n_ffd = 0, n_fonly = 0;
+        EagerSearch(HostBackend &b, const double *x0_, const double *p_) : B(b), x0(x0_), p(p_) {}
+        void eval(int flags) {
+            double fv = 0.0, gv = 0.0;
+            B.prob.fused(&B.ctx, flags, &fv, &gv, nullptr, nullptr, x0, p, a_x, B.n);
+            if (flags & FLGPU_WANT_F) f_cur = fv;
+            if (flags & FLGPU_WANT_GP) gp_cur = gv;
+        }
+        void form(double step) { a_x = step; have_x = true; trials += 1; }
+        void call_f() { eval(FLGPU_WANT_F); n_f += 1; }
+        void call_fd() { eval(FLGPU_WANT_GP); a_g = a_x; have_g = true; n_fd += 1; }
+        void call_ffd() { eval(FLGPU_WANT_F | FLGPU_WANT_GP); a_g = a_x; have_g = true; n_ffd += 1; }
+        double slope() { return gp_cur; }
+        double fx() { return f_cur; }
+        void set_fx(double v) { f_cur = v; }
+        void adopt_pre() {}
+        void count_f_only() { n_fonly += 1; }
+        static bool aborted() { return false; }
+    };
+    double search_res[FLGPU_SEARCH_RESULT_DOUBLES] = {0};
+    bool device_search_available() const override { return prob.fused != nullptr && g_nranks <= 1; }
+    void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
+                       double a, const double *x0, const double *p, double *xt, double *gt) override {
+        callback_launches++;
+        EagerSearch S(*this, x0, p);
+        S.c1 = c1; S.c2abs = c2abs; S.fx0 = fx0; S.phid0 = phid0; S.incr = incr; S.fdwithf = fdwithf;
+        S.a = a; S.f_cur = fx0; S.pre = 0;
+        if (strong) S.strongwolfe(); else S.wolfe();
+        double fv, gv;
+        if (S.have_x && S.have_g && S.a_x == S.a_g) {
+            prob.fused(&ctx, FLGPU_WRITE_X | FLGPU_WRITE_G, &fv, &gv, xt, gt, x0, p, S.a_x, n);
+        } else {
+            if (S.have_x) prob.fused(&ctx, FLGPU_WRITE_X, &fv, &gv, xt, nullptr, x0, p, S.a_x, n);
+            if (S.have_g) prob.fused(&ctx, FLGPU_WRITE_G, &fv, &gv, nullptr, gt, x0, p, S.a_g, n);
+        }
+        const double r[FLGPU_SEARCH_RESULT_DOUBLES] = {S.a, S.f_cur, S.trials, S.n_f, S.n_fd, S.n_ffd, S.n_fonly, 0.0};
+        std::memcpy(search_res, r, sizeof r);
+    }
+    void search_result(double *out) override { std::memcpy(out, search_res, sizeof search_res); }
+
     void trial_x(double *x, const double *x0, const double *p, double a) override {
         launches++;
         for (long i = 0; i < n; i++) x[i] = x0[i] + a * p[i];

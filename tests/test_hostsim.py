@@ -107,16 +107,24 @@ def test_minimisers_and_iteration_counts():
 def test_fused_line_search_is_the_same_algorithm(lbfgs, name, kw):
     """flgpu_fused_fn changes where trial points live, not what is computed: with the host simulator
     (identical reductions on both paths) the fused and the unfused run must agree bit for bit in every
-    direction, step, iterate and evaluation count."""
+    direction, step, iterate and evaluation count.  The third run takes the driver's device-resident-search branch
+    (SearchCore with eager evaluations, as the cooperative CUDA kernels instantiate it) and must agree as well."""
     n = 3001
     kind = _cases.OBJECTIVES[name][0]
     run = H.sd if lbfgs == "sd" else (H.lbfgs if lbfgs else H.cg)
     out = []
-    for fused in (True, False):
+    for fused, dsearch in ((True, False), (False, False), (True, True)):
         ob = H.Observer(max_vec_iters=10**9)
-        x, st = run(kind, _cases.start(name, n), observer=ob, Warning=False, n_global=n, fused=fused, **kw)
+        x, st = run(kind, _cases.start(name, n), observer=ob, Warning=False, n_global=n, fused=fused,
+                    device_search=dsearch, **kw)
         out.append((x, st, ob))
-    (xa, sa, oa), (xb, sb, ob_) = out
+    (xa, sa, oa), (xb, sb, ob_) = out[0], out[1]
+    (xc, sc, oc) = out[2]
+    assert np.array_equal(xa, xc) and oa.rows == oc.rows
+    assert all(np.array_equal(u, v) for u, v in zip(oa.p, oc.p))
+    for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
+        assert getattr(sa, k) == getattr(sc, k), ("device-search", k)
+    assert sc.host_syncs < sa.host_syncs
     assert np.array_equal(xa, xb)
     assert oa.rows == ob_.rows
     assert all(np.array_equal(u, v) for u, v in zip(oa.p, ob_.p))
