@@ -168,6 +168,25 @@ def test_augmented_lagrangian_forwards_dense_solvers_to_libfl(tmp_path):
     assert r.returncode == 1 and "dense-Hessian" in r.stdout
 
 
+def test_objective_helper_header_compiles_for_sm_100a(tmp_path):
+    """include/flgpu_objective.cuh (+ flgpu_search_core.hpp) cross-compiles with nvcc for sm_100a without a GPU: the
+    user-objective fixture the GPU tests run, its four callbacks and the cooperative search kernel."""
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    _build()
+    out = tmp_path / "libuser_objective.so"
+    libdir = os.path.join(ROOT, "fortran_library_b200")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-fmad=false", "-std=c++17", "-Xcompiler",
+                    "-fPIC", "-shared", "-o", str(out), os.path.join(ROOT, "tests", "link", "user_objective.cu"),
+                    "-L" + libdir, "-lflgpu", "-Xlinker", "-rpath," + libdir], check=True)
+    sass = subprocess.run(["cuobjdump", "-sass", str(out)], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass and "search_kernel" in sass and "DADD" in sass
+    lib = C.CDLL(str(out))                       # loads (against libflgpu.so) and exports the fixture's entry point
+    assert hasattr(lib, "user_problem")
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device every compute entry point aborts with a message; nothing is computed on the
     CPU.  (Skipped on a GPU box, where the same call simply runs.)"""
