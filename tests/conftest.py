@@ -14,6 +14,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(items):
+    """Every test gets a ceiling (pytest-timeout): the reference algorithm can spin forever on NaN input, and a hang
+    must fail the run instead of stalling it."""
+    for item in items:
+        if item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(1200))
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import _oracle

@@ -21,8 +21,24 @@ capi = H.capi
 COUNTS = {"compared": 0, "skipped": 0}      # how many generated cases reach the comparison (reported by the last test)
 
 
+def _guard(fn, big):
+    """Beyond |x| = 1e40 the polynomial families overflow (Python raises, IEEE gives inf - inf = NaN, and a NaN step
+    makes the reference's zoom spin forever, f90:1684,1695): clamp to a huge finite value there.  Both sides call the
+    same functions, so the comparison is unaffected."""
+    def g(x):
+        if not (abs(x) < 1e40):
+            return big if x > 0 or big > 1e250 else -big
+        return fn(x)
+    return g
+
+
 def _objective(kind, p, q, r):
     """Families with different line-search behaviour; evaluated with Python floats (IEEE double)."""
+    f, g = _objective_raw(kind, p, q, r)
+    return _guard(f, 1e300), _guard(g, 1e200)
+
+
+def _objective_raw(kind, p, q, r):
     if kind == "quartic":       # flat bottom: long grow loops
         return (lambda x: p * (x - q) ** 4 + r * (x - q) ** 2), (lambda x: 4.0 * p * (x - q) ** 3 + 2.0 * r * (x - q))
     if kind == "steep":         # Armijo fails first (branch D)
@@ -35,6 +51,7 @@ def _objective(kind, p, q, r):
            (lambda x: 2.0 * p * (x - q) - r * math.exp(min(-(x - q), 300.0)))
 
 
+@pytest.mark.timeout(300)        # a hang must fail the run, not stall it (pytest-timeout kills the process)
 @settings(max_examples=400, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(algo=st.sampled_from(["cg", "sd"]), kind=st.sampled_from(["quartic", "steep", "cosh", "well"]),
        p=st.floats(0.1, 10.0), q=st.floats(-2.0, 2.0), r=st.floats(0.01, 3.0), x0=st.floats(-3.0, 3.0),
@@ -81,6 +98,7 @@ def test_cg_and_sd_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0,
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(600)
 @settings(max_examples=150, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(algo=st.sampled_from(["cg", "sd"]), kind=st.sampled_from(["quartic", "steep", "cosh", "well"]),
        p=st.floats(0.1, 10.0), q=st.floats(-2.0, 2.0), r=st.floats(0.01, 3.0), x0=st.floats(-3.0, 3.0),
