@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 from . import _capi as capi
-from ._capi import (CG_DY, CG_PR, SPACE_HOST, SPACE_DEVICE, OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD,  # noqa: F401
+from ._capi import (CG_DY, CG_PR, LS_REFERENCE, LS_FAST, SPACE_HOST, SPACE_DEVICE, OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD,  # noqa: F401
                     START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO, CONVERGED,
                     STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER, AL_LBFGS, AL_CG,
                     CON_SPHERE)
@@ -207,21 +207,26 @@ def _resolve_x(x):
 
 def LBFGS(problem, x, Memory=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
           MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None,
-          comm=None, offset=0, n_global=0, time_kernels=False, fused=True, device_search=None):
+          comm=None, offset=0, n_global=0, time_kernels=False, fused=True, device_search=None,
+          line_search=None):
     """Limited-memory BFGS (reference: LBFGS, NonlinearOptimization.f90:398-625).  x is updated in
     place with the minimiser; returns the run statistics.  `problem.f_fd` present selects the
     _fdwithf line searcher exactly as the reference's optional f_fd does.  fused=False ignores
-    `problem.fused` (trial points are then materialised and the plain callbacks called)."""
+    `problem.fused` (trial points are then materialised and the plain callbacks called).
+    line_search="fast" (default "reference") selects FLGPU_LS_FAST, an accept-at-first-Wolfe-point searcher that is
+    NOT a reference routine (include/flgpu.h); available on every optimizer here."""
     ptr, n, space = _resolve_x(x)
     return _run(lib().flgpu_lbfgs, False, problem, ptr, n, space, observer, stream, comm, offset, n_global,
                 time_kernels, dict(Memory=Memory, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                                    Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                                   WolfeConst2=WolfeConst2, Increment=Increment, fused=fused, device_search=device_search))
+                                   WolfeConst2=WolfeConst2, Increment=Increment, fused=fused, device_search=device_search,
+                     line_search=line_search))
 
 
 def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None,
                       MinStepLength=None, WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None,
-                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True, device_search=None):
+                      stream=None, comm=None, offset=0, n_global=0, time_kernels=False, no_clamp=False, fused=True, device_search=None,
+          line_search=None):
     """Nonlinear conjugate gradient, Method 'DY' (default) or 'PR' (reference: ConjugateGradient,
     f90:193-394; no_clamp=True gives ConjugateGradient_basic, f90:2249-2346)."""
     if Method is not None and Method not in ("DY", "PR", CG_DY, CG_PR):
@@ -231,19 +236,22 @@ def ConjugateGradient(problem, x, Method=None, Strong=None, Warning=None, MaxIte
                 n_global, time_kernels,
                 dict(Method=Method, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                      Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                     WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp), fused=fused, device_search=device_search))
+                     WolfeConst2=WolfeConst2, Increment=Increment, no_clamp=int(no_clamp), fused=fused, device_search=device_search,
+                     line_search=line_search))
 
 
 def SteepestDescent(problem, x, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
                     WolfeConst1=None, WolfeConst2=None, Increment=None, observer=None, stream=None, comm=None,
-                    offset=0, n_global=0, time_kernels=False, fused=True, device_search=None):
+                    offset=0, n_global=0, time_kernels=False, fused=True, device_search=None,
+          line_search=None):
     """Steepest descent (reference: SteepestDescent, f90:55-188): p = -f'(x) through the same line searchers."""
     ptr, n, space = _resolve_x(x)
     return _run(lib().flgpu_steepest_descent, False, problem, ptr, n, space, observer, stream, comm, offset,
                 n_global, time_kernels,
                 dict(Strong=Strong, Warning=Warning, MaxIteration=MaxIteration, Precision=Precision,
                      MinStepLength=MinStepLength, WolfeConst1=WolfeConst1, WolfeConst2=WolfeConst2,
-                     Increment=Increment, fused=fused, device_search=device_search))
+                     Increment=Increment, fused=fused, device_search=device_search,
+                     line_search=line_search))
 
 
 def builtin_constraints(kind=CON_SPHERE):

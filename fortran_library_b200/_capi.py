@@ -3,6 +3,7 @@ import ctypes as C
 
 # enums
 CG_DY, CG_PR = 0, 1
+LS_REFERENCE, LS_FAST = 0, 1
 SPACE_HOST, SPACE_DEVICE = 0, 1
 CONVERGED, STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER = 0, 1, 2, 3, 4
 OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD = 0, 1, 2
@@ -53,7 +54,7 @@ class Options(C.Structure):
                 ("no_clamp", C.c_int), ("stream", C.c_void_p), ("comm", C.c_void_p),
                 ("offset", C.c_int64), ("n_global", C.c_int64), ("observer", C.c_void_p),
                 ("observer_user", C.c_void_p), ("time_kernels", C.c_int), ("no_fused", C.c_int),
-                ("device_search", C.c_int)]
+                ("device_search", C.c_int), ("line_search", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -100,6 +101,8 @@ def apply_options(o, **kw):
         field = names.get(k, k)
         if field == "method" and isinstance(v, str):
             v = {"DY": CG_DY, "PR": CG_PR}[v]
+        if field == "line_search" and isinstance(v, str):
+            v = {"reference": LS_REFERENCE, "fast": LS_FAST}[v]
         if field in ("strong", "warning"):
             v = int(bool(v))
         setattr(o, field, v)

@@ -36,6 +36,7 @@ struct ThreadState {
     flgpu_observer_fn observer = nullptr;
     void *observer_user = nullptr;
     CudaBackend *backend = nullptr;   // the call currently executing on this thread
+    int line_search = -1;             // flgpu_set_line_search; -1 = FLGPU_LINE_SEARCH decides
 };
 thread_local ThreadState tls;
 
@@ -186,6 +187,13 @@ void apply_thread_settings(flgpu_options &o) {
     if (nf && nf[0] && nf[0] != '0') o.no_fused = 1;
     const char *ds = std::getenv("FLGPU_DEVICE_SEARCH");   // 0 / 1 / 2 as flgpu_options.device_search
     if (ds && ds[0] >= '0' && ds[0] <= '2') o.device_search = ds[0] - '0';
+    if (tls.line_search >= 0) {
+        o.line_search = tls.line_search;
+    } else {
+        const char *ls = std::getenv("FLGPU_LINE_SEARCH");   // reference | fast
+        if (ls && (!std::strcmp(ls, "fast") || !std::strcmp(ls, "FAST") || !std::strcmp(ls, "1")))
+            o.line_search = FLGPU_LS_FAST;
+    }
 }
 
 void run_ref(int algo, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, double *x, int dim,
@@ -270,6 +278,7 @@ void *flgpu_current_stream(void) { return tls.stream; }
 int flgpu_current_device(void) { return tls.device; }
 void flgpu_last_stats(flgpu_stats *out) { *out = tls.last; }
 void flgpu_set_observer(flgpu_observer_fn fn, void *user) { tls.observer = fn; tls.observer_user = user; }
+void flgpu_set_line_search(int policy) { tls.line_search = policy; }
 void flgpu_register_fused(flgpu_ref_f_fn f, flgpu_fused_fn fused, void *user) {
     std::lock_guard<std::mutex> lock(g_fused_mu);
     if (fused) g_fused[f] = FusedEntry{fused, user};

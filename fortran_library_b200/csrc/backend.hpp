@@ -55,7 +55,8 @@ public:
     // ---- device-resident line search (flgpu_search_fn): the whole search in one cooperative kernel; the accepted
     // point / gradient land in xt / gt, the scalars in search_result() after the next fetch()
     virtual bool device_search_available() const { return false; }
-    virtual void device_search(bool /*strong*/, bool /*fdwithf*/, double /*c1*/, double /*c2abs*/, double /*fx0*/,
+    virtual void device_search(int /*policy: FLGPU_LS_* */, bool /*strong*/, bool /*fdwithf*/, double /*c1*/,
+                               double /*c2abs*/, double /*fx0*/,
                                double /*phid0*/, double /*incr*/, double /*a*/, const double * /*x0*/,
                                const double * /*p*/, double * /*xt*/, double * /*gt*/) {}
     virtual void search_result(double * /*out: FLGPU_SEARCH_RESULT_DOUBLES*/) {}

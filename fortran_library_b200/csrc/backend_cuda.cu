@@ -444,12 +444,13 @@ void CudaBackend::fused_eval(int flags, double a, const double *x0, const double
     callback_launches++;
 }
 
-void CudaBackend::device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0,
+void CudaBackend::device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0,
                                 double incr, double a, const double *x0, const double *p, double *xt, double *gt) {
     flgpu_search_args A;
     A.x0_dev = x0; A.p_dev = p; A.x_out = xt; A.g_out = gt;
     A.c1 = c1; A.c2abs = c2abs; A.fx0 = fx0; A.phid0 = phid0; A.incr = incr; A.a = a;
     A.strong = strong ? 1 : 0; A.fdwithf = fdwithf ? 1 : 0;
+    A.policy = policy;
     A.result_dev = Rsearch;
     A.comm = ctx.nranks > 1 ? comm : nullptr;
     const int t = time_begin("callback:device_search", 0.0);   // bytes depend on the trial count: see flgpu_stats

@@ -78,7 +78,7 @@ public:
         return prob.search != nullptr &&
                (ctx.nranks == 1 || (comm && comm->p2p && (prob.search_caps & FLGPU_SEARCH_ROW_SHARDS)));
     }
-    void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
+    void device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
                        double a, const double *x0, const double *p, double *xt, double *gt) override;
     void search_result(double *out) override;
     void credit_search_bytes(double bytes) override;

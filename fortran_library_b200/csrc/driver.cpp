@@ -42,6 +42,7 @@ Params params_from_options(const flgpu_options &o, bool for_cg, bool has_f_fd) {
     P.has_f_fd = has_f_fd;
     P.fused = !o.no_fused;
     P.device_search = o.device_search;   // 0 off, 1 on, 2 auto (by size, see use_device_search)
+    P.line_search = o.line_search == FLGPU_LS_FAST ? FLGPU_LS_FAST : FLGPU_LS_REFERENCE;
     P.observer = o.observer;
     P.observer_user = o.observer_user;
     (void)for_cg;
@@ -131,8 +132,15 @@ struct Search : SearchCore<Search> {
 bool use_device_search(const Params &P, Backend &B) {
     if (!P.fused || P.device_search == 0 || !B.device_search_available()) return false;
     if (P.device_search == 1) return true;
+    // FLGPU_LS_FAST accepts the first trial most of the time, and LBFGS evaluates that trial inside the speculative
+    // K1->K2->K3 chain: the host-driven search already costs one round trip per iteration, a search kernel would add one
+    if (P.line_search == FLGPU_LS_FAST) return false;
     return B.n <= ((int64_t)1 << 25);
 }
+
+// FLGPU_LS_FAST asks for f and f' at every trial.  A fused probe delivers both in one pass whether or not the problem
+// has an f_fd callback; on the unfused path f_fd is used when present, else f then fd.
+bool fast_uses_ffd(const Params &P, Backend &B) { return P.has_f_fd || (P.fused && B.fused_available()); }
 
 // Runs one line search; on return xt/gt hold the accepted point and gradient.
 struct SearchResult { double a, fx; int64_t trials; };
@@ -143,14 +151,18 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     Search S(B, st);
     S.x0 = x0; S.xt = xt; S.gt = gt; S.p = p;
     S.c1 = P.c1; S.c2abs = P.c2 * std::fabs(phid0); S.fx0 = fx0; S.phid0 = phid0; S.incr = P.incr;
-    S.fdwithf = fdwithf; S.a = a; S.fx_ = fx0;
+    S.a = a; S.fx_ = fx0;
     S.pre = pre; S.pre_f = pre_f; S.pre_gp = pre_gp;
     S.fused = P.fused && B.fused_available();
+    const bool fast = P.line_search == FLGPU_LS_FAST;
+    // FLGPU_LS_FAST evaluates f and f' together at every trial: one fused probe, else f_fd when the problem has one
+    if (fast) fdwithf = fast_uses_ffd(P, B);
+    S.fdwithf = fdwithf;
     st.n_linesearch++;
     if (S.fused && pre == 0 && use_device_search(P, B)) {
         // the same SearchCore, run by every thread of one cooperative kernel; one host round trip per search
         double res[FLGPU_SEARCH_RESULT_DOUBLES], slots[NSLOTS];
-        B.device_search(strong, fdwithf, S.c1, S.c2abs, fx0, phid0, S.incr, a, x0, p, xt, gt);
+        B.device_search(P.line_search, strong, fdwithf, S.c1, S.c2abs, fx0, phid0, S.incr, a, x0, p, xt, gt);
         B.fetch(slots); st.host_syncs++;
         B.search_result(res);
         st.n_trials += (int64_t)res[2]; st.n_f += (int64_t)res[3]; st.n_fd += (int64_t)res[4];
@@ -163,7 +175,8 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
         r.a = res[0]; r.fx = res[1]; r.trials = (int64_t)res[2];
         return r;
     }
-    if (strong) S.strongwolfe(); else S.wolfe();
+    if (fast) S.fast(strong);
+    else if (strong) S.strongwolfe(); else S.wolfe();
     S.finish();
     SearchResult r;
     r.fx = S.fx();
@@ -237,7 +250,10 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             int new_slot, k_after;
             if (it <= mem) { new_slot = recent + 1; k_after = k + 1; }       // f90:470,508 (append)
             else { new_slot = (recent + 1) % mem; k_after = mem; }           // f90:622 (overwrite oldest)
-            const bool next_fdwithf = (it >= mem) && P.has_f_fd && P.strong;
+            const bool fast = P.line_search == FLGPU_LS_FAST;
+            // fast: f and f' at the first trial of every search; reference: f_fd only in the main loop (f90:448-498)
+            const bool next_both = fast;
+            const bool next_fdwithf = fast ? fast_uses_ffd(P, B) : (it >= mem) && P.has_f_fd && P.strong;
             if (last) {
                 B.dot(gc, gc, SL_GG);
             } else {
@@ -254,6 +270,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
                     B.lbfgs_direction(p, xo, gc, xc, k_after, new_slot);     // K3: new p, first trial point (a=1)
                     st.n_trials++;
                     if (next_fdwithf) { B.eval_fg(xo, go); st.n_f_fd++; B.dot(go, p, SL_GP); }
+                    else if (next_both) { B.eval_f(xo); st.n_f++; B.eval_g(xo, go); st.n_fd++; B.dot(go, p, SL_GP); }
                     else { B.eval_f(xo); st.n_f++; }
                 }
             }
@@ -265,7 +282,8 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             auto uncount_speculative = [&]() {
                 if (last || dsearch) return;
                 st.n_trials--;
-                if (next_fdwithf) st.n_f_fd--; else st.n_f--;
+                if (next_fdwithf) st.n_f_fd--;
+                else { st.n_f--; if (next_both) st.n_fd--; }
             };
             if (gg < P.tol) { uncount_speculative(); st.status = FLGPU_CONVERGED; break; }   // f90:611-614
             if (pp * a * a < P.minstep) {                                    // f90:615-621
@@ -286,7 +304,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             phid0 = slots[SL_GP0];                                           // f90:607
             pp = slots[SL_PP];
             a = 1.0;
-            pre = dsearch ? 0 : (next_fdwithf ? 3 : 2);
+            pre = dsearch ? 0 : ((next_fdwithf || next_both) ? 3 : 2);
             pre_f = slots[SL_F];
             pre_gp = slots[SL_GP];
         }

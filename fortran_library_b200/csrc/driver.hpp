@@ -17,6 +17,7 @@ struct Params {
     bool has_f_fd = false;
     bool fused = true;   // use flgpu_problem.fused when the problem supplies it
     int device_search = 2;   // flgpu_problem.search (whole line search in one cooperative kernel): 0 off, 1 on, 2 auto
+    int line_search = FLGPU_LS_REFERENCE;   // FLGPU_LS_FAST: accept-at-first-Wolfe-point searcher (not a reference routine)
     flgpu_observer_fn observer = nullptr;
     void *observer_user = nullptr;
 };

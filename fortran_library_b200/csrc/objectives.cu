@@ -321,7 +321,9 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
     __device__ bool aborted() const { return n_f + n_fd + n_ffd > kEvalBudget; }
 };
 
-template <int KIND>
+// FAST = the FLGPU_LS_FAST searcher (SearchCore::fast); a template parameter so that the reference-exact kernel's code
+// and register allocation do not depend on it
+template <int KIND, bool FAST>
 __global__ void __launch_bounds__(kThreads, 4) search_kernel(SearchKArgs K) {
     __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
     __shared__ double sh[2][kThreads / 32];
@@ -330,7 +332,8 @@ __global__ void __launch_bounds__(kThreads, 4) search_kernel(SearchKArgs K) {
     DevSearch<KIND> S(K, tab, sh, bc);
     S.c1 = K.c1; S.c2abs = K.c2abs; S.fx0 = K.fx0; S.phid0 = K.phid0; S.incr = K.incr;
     S.fdwithf = K.fdwithf != 0; S.a = K.a0; S.f_cur = K.fx0; S.pre = 0;
-    if (K.strong) S.strongwolfe(); else S.wolfe();
+    if (FAST) S.fast(K.strong != 0);
+    else if (K.strong) S.strongwolfe(); else S.wolfe();
     // the point and gradient the reference leaves in x / fdx
     ObjArgs o = K.o;
     double f0 = 0.0, g0 = 0.0;
@@ -459,8 +462,8 @@ static void dev_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp,
 }
 
 // device-resident search: same grid as the probes (bit-identical sums), capped by what can be co-resident
-template <int KIND>
-static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int64_t n) {
+template <int KIND, bool FAST>
+static void dev_search_policy(const flgpu_eval_ctx *c, const flgpu_search_args *A, int64_t n) {
     cudaStream_t s = (cudaStream_t)c->stream;
     Scratch &sc = scratch_for(s);
     static int resident = 0, sms = 0;
@@ -468,7 +471,7 @@ static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int6
         int dev = 0;
         FLGPU_CUDA_CHECK(cudaGetDevice(&dev));
         FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::search_kernel<KIND>, k::kThreads, 0));
+        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::search_kernel<KIND, FAST>, k::kThreads, 0));
         int coop = 0;
         FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         if (!coop || resident < 1) fatal("device-resident line search needs cooperative kernel launch");
@@ -492,7 +495,12 @@ static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int6
         K.peers = comm->peers_search; K.me = comm->rank; K.G = comm->nranks; K.dseq = &comm->local->dseq;
     }
     void *params[] = {&K};
-    FLGPU_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k::search_kernel<KIND>, dim3(grid), dim3(k::kThreads), params, 0, s));
+    FLGPU_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k::search_kernel<KIND, FAST>, dim3(grid), dim3(k::kThreads), params, 0, s));
+}
+template <int KIND>
+static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int64_t n) {
+    if (A->policy == FLGPU_LS_FAST) dev_search_policy<KIND, true>(c, A, n);
+    else dev_search_policy<KIND, false>(c, A, n);
 }
 
 // reference-ABI flavour: device x / f' pointers, host f, runs on the current call's stream

@@ -100,6 +100,7 @@ typedef struct flgpu_search_args {
     int strong, fdwithf;            /* which of the four searchers */
     double *result_dev;
     flgpu_comm *comm;               /* row-sharded runs: the communicator whose search mailboxes carry the exchanges */
+    int policy;                     /* FLGPU_LS_REFERENCE: the reference's searchers; FLGPU_LS_FAST: SearchCore::fast(strong) */
 } flgpu_search_args;
 typedef void (*flgpu_search_fn)(const flgpu_eval_ctx *ctx, const flgpu_search_args *args, int64_t n_local);
 
@@ -116,6 +117,15 @@ typedef struct flgpu_problem {
 /* ------------------------------------------------------------------ options / results */
 
 enum { FLGPU_CG_DY = 0, FLGPU_CG_PR = 1 };
+/* flgpu_options.line_search.  REFERENCE (default): Wolfe / StrongWolfe(_fdwithf) of f90:1286-1698, statement by
+ * statement -- same trial points, same evaluation counts as the reference.  FAST (not a reference
+ * routine, iterates differ): the bracketing / cubic-zoom scheme of Nocedal & Wright Alg. 3.5/3.6 with
+ * More'-Thuente-style safeguards (include/flgpu_search_core.hpp, SearchCore::fast): f and f' are evaluated together
+ * at every trial and the first trial that satisfies the (strong, or with Strong = 0 the weak) Wolfe conditions for
+ * the given WolfeConst1/2 is accepted, where the reference keeps growing the step by Increment while the slope is
+ * negative (f90:1498-1515).  Increment is not used by FAST.  f_fd (or the fused evaluation) is used from the first
+ * line search on, not only in the main loop. */
+enum { FLGPU_LS_REFERENCE = 0, FLGPU_LS_FAST = 1 };
 enum { FLGPU_SPACE_HOST = 0, FLGPU_SPACE_DEVICE = 1 };
 /* flgpu_stats.status */
 enum {
@@ -170,6 +180,7 @@ typedef struct flgpu_options {
     int no_fused;           /* 1 = ignore flgpu_problem.fused (always materialise trial points) */
     int device_search;      /* flgpu_problem.search (single GPU, fused mode): 0 never, 1 always, 2 = auto (default):
                                used up to 2^25 rows, where the per-trial host round trip shows; same bits either way */
+    int line_search;        /* FLGPU_LS_REFERENCE (default) / FLGPU_LS_FAST */
 } flgpu_options;
 
 typedef struct flgpu_stats {
@@ -269,6 +280,9 @@ void flgpu_set_observer(flgpu_observer_fn fn, void *user);
  * a later Fortran-ABI call whose `f` argument equals `f` uses it.  fused = NULL removes the entry.
  * `user` is handed to the fused callback as ctx->user.  The built-in objectives are pre-registered. */
 void flgpu_register_fused(flgpu_ref_f_fn f, flgpu_fused_fn fused, void *user);
+/* Line-search policy (FLGPU_LS_*) of later Fortran-ABI calls on this thread; the reference signatures have no room
+ * for it.  -1 = unset: the environment variable FLGPU_LINE_SEARCH = reference|fast decides (default reference). */
+void flgpu_set_line_search(int policy);
 
 /* gfortran names (hpp:278-393 "#elif __GNUC__") */
 void __nonlinearoptimization_MOD_lbfgs(

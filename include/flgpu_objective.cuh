@@ -226,14 +226,16 @@ struct DevSearch : flgpu::SearchCore<DevSearch<Obj>> {
     __device__ bool aborted() const { return n_f + n_fd + n_ffd > kEvalBudget; }
 };
 
-template <class Obj>
+// FAST = the FLGPU_LS_FAST searcher (SearchCore::fast), a template parameter: the reference-exact kernel stays as it is
+template <class Obj, bool FAST>
 __global__ void __launch_bounds__(kThreads, 4) search_kernel(Obj obj, SearchArgs K) {
     __shared__ double sh[2][kThreads / 32];
     __shared__ double bc[2];
     DevSearch<Obj> S(obj, K, sh, bc);
     S.c1 = K.c1; S.c2abs = K.c2abs; S.fx0 = K.fx0; S.phid0 = K.phid0; S.incr = K.incr;
     S.fdwithf = K.fdwithf != 0; S.a = K.a0; S.f_cur = K.fx0; S.pre = 0;
-    if (K.strong) S.strongwolfe(); else S.wolfe();
+    if (FAST) S.fast(K.strong != 0);
+    else if (K.strong) S.strongwolfe(); else S.wolfe();
     Args o = K.o;
     double f0 = 0.0, g0 = 0.0;
     if (S.have_x && S.have_g && S.a_x == S.a_g) {
@@ -273,6 +275,10 @@ struct Callbacks {
         return (int)grid;
     }
     static void search(const flgpu_eval_ctx *ctx, const flgpu_search_args *A, int64_t n) {
+        if (A->policy == FLGPU_LS_FAST) search_policy<true>(ctx, A, n); else search_policy<false>(ctx, A, n);
+    }
+    template <bool FAST>
+    static void search_policy(const flgpu_eval_ctx *ctx, const flgpu_search_args *A, int64_t n) {
         if (A->comm) { std::fprintf(stderr, "flgpu_obj: the header's device-resident search is single-GPU\n"); std::abort(); }
         SearchArgs K;
         int max_blocks = 0;
@@ -285,12 +291,12 @@ struct Callbacks {
         int resident = 0, sms = 148, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, search_kernel<Obj>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, search_kernel<Obj, FAST>, kThreads, 0);
         int grid = grid_for(n, max_blocks);
         if (grid > resident * sms) grid = resident * sms;
         Obj obj = *(const Obj *)ctx->user;
         void *params[] = {&obj, &K};
-        cudaError_t e = cudaLaunchCooperativeKernel((void *)search_kernel<Obj>, dim3(grid), dim3(kThreads), params, 0,
+        cudaError_t e = cudaLaunchCooperativeKernel((void *)search_kernel<Obj, FAST>, dim3(grid), dim3(kThreads), params, 0,
                                                     (cudaStream_t)ctx->stream);
         if (e != cudaSuccess) { std::fprintf(stderr, "flgpu_obj: cooperative launch failed: %s\n", cudaGetErrorString(e)); std::abort(); }
     }

@@ -228,6 +228,76 @@ struct SearchCore {
             }
         }
     }
+
+    // ---------------- FLGPU_LS_FAST: NOT a reference routine (flgpu_options.line_search).
+    // The reference's StrongWolfe never returns from a trial whose slope is still negative, even when that trial
+    // already satisfies both Wolfe conditions: it keeps multiplying the step by Increment (1.05) until f rises or the
+    // slope turns, then zooms (f90:1498-1515) -- 8 to 30 objective passes per accepted step.  This searcher
+    // is the textbook bracketing/zoom scheme (Nocedal & Wright, Numerical Optimization, Alg. 3.5/3.6) with
+    // More'-Thuente-style safeguards: every trial evaluates f and f' together and is ACCEPTED AS SOON AS it satisfies
+    //     f(a) <= f(0) + c1 a phi'(0)   and   |phi'(a)| <= c2 |phi'(0)|   (weak form: phi'(a) >= -c2 |phi'(0)|);
+    // while no bracket exists the step grows to the minimiser of the cubic through the last two trials, kept inside
+    // [a + 1.1 (a - a_prev), a + 4 (a - a_prev)]; inside a bracket the cubic minimiser is kept 5 % away from both
+    // ends.  A NaN or +inf objective counts as an Armijo violation (the bracket shrinks away from it).  If the
+    // bracket collapses, or after 40 growth / 60 zoom steps, the best Armijo point found so far is returned.
+    // The accepted step always satisfies the conditions above unless one of those exits fired.
+    FLGPU_SC_HD bool fast_curvature_ok(bool strong, double phid) const {
+        return strong ? fabs(phid) <= c2abs : phid >= -c2abs;
+    }
+    // minimiser of the cubic interpolating (u, fu, gu) and (v, fv, gv); NaN when it has none
+    FLGPU_SC_HD static double cubic_minimiser(double u, double v, double fu, double fv, double gu, double gv) {
+        const double d1 = nf_add(nf_add(gu, gv), -(nf_mul(3.0, fu - fv) / (u - v)));
+        const double disc = nf_add(nf_mul(d1, d1), -nf_mul(gu, gv));
+        const double d2 = (v - u > 0.0) ? sqrt(disc) : -sqrt(disc);
+        return nf_add(v, -(nf_mul(v - u, nf_add(nf_add(gv, d2), -d1)) / nf_add(nf_add(gv, -gu), nf_mul(2.0, d2))));
+    }
+    // lo: best point with sufficient decrease so far (slope glo points towards hi); hi: the other end
+    FLGPU_SC_HD void fast_zoom(bool strong, double lo, double hi, double flo, double fhi, double glo, double ghi) {
+        for (int it = 0;; it++) {
+            if (self().aborted()) return;
+            const double w = hi - lo;
+            double t = (cubic_minimiser(lo, hi, flo, fhi, glo, ghi) - lo) / w;
+            if (!(t > 0.0 && t < 1.0)) t = 0.5;
+            else if (t < 0.05) t = 0.05;
+            else if (t > 0.95) t = 0.95;
+            a = nf_add(lo, nf_mul(t, w));
+            self().form(a); both();
+            const double g = self().slope();
+            const double f = self().fx();
+            if (!armijo_ok() || f >= flo) {
+                hi = a; fhi = f; ghi = g;
+            } else {
+                if (fast_curvature_ok(strong, g)) return;
+                if (nf_mul(g, hi - lo) >= 0.0) { hi = lo; fhi = flo; ghi = glo; }
+                lo = a; flo = f; glo = g;
+            }
+            if (collapsed(lo, hi) || it >= 59) {
+                if (a != lo) { a = lo; self().form(a); both(); (void)self().slope(); }
+                return;
+            }
+        }
+    }
+    // pre must be 0 or 3 (the caller's chain evaluated f, f' and f'.p at the first trial)
+    FLGPU_SC_HD void fast(bool strong) {
+        double a_lo = 0.0, f_lo = fx0, g_lo = phid0;
+        if (pre == 0) { self().form(a); both(); } else { self().adopt_pre(); }
+        double g = (pre == 3) ? pre_gp : self().slope();
+        for (int grow = 0;; grow++) {
+            if (self().aborted()) return;
+            const double f = self().fx();
+            if (!armijo_ok() || (grow > 0 && f >= f_lo)) { fast_zoom(strong, a_lo, a, f_lo, f, g_lo, g); return; }
+            if (fast_curvature_ok(strong, g)) return;
+            if (g >= 0.0) { fast_zoom(strong, a, a_lo, f, f_lo, g, g_lo); return; }
+            if (grow >= 39) return;
+            double an = cubic_minimiser(a_lo, a, f_lo, f, g_lo, g);
+            const double lo_b = nf_add(a, nf_mul(1.1, a - a_lo)), hi_b = nf_add(a, nf_mul(4.0, a - a_lo));
+            if (!(an <= hi_b)) an = hi_b;
+            if (an < lo_b) an = lo_b;
+            a_lo = a; f_lo = f; g_lo = g;
+            a = an;
+            self().form(a); both(); g = self().slope();
+        }
+    }
 };
 
 }  // namespace flgpu

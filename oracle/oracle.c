@@ -14,6 +14,7 @@
 #include "oracle.h"
 
 #include <math.h>
+#include <setjmp.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -23,6 +24,26 @@ static orc_trace_t g_trace = NULL;
 static void *g_trace_user = NULL;
 static int g_sum_mode = 0;
 static orc_stats_t g_st;
+
+/* Evaluation budget (a test-harness guard, not reference behaviour).  The reference's searchers never terminate once
+ * the step is NaN (f90:1518-1546: `a<1d-15` and both Armijo forms are false for NaN), and nothing a callback returns
+ * can end such a loop.  With a budget set, the driver gives up after that many callback invocations: status 9, x left
+ * as it was at that moment (the search's private copy of x0 is not freed).  0 = unlimited = the reference. */
+static long g_eval_budget = 0, g_evals = 0;
+static int g_armed = 0;
+static jmp_buf g_abort;
+void orc_set_eval_budget(long n) { g_eval_budget = n; }
+static void count_eval(void) {
+    if (g_armed && ++g_evals > g_eval_budget) { g_armed = 0; longjmp(g_abort, 1); }
+}
+#define ORC_ARM_BUDGET(label)                                                          \
+    do {                                                                               \
+        g_evals = 0; g_armed = 0;                                                      \
+        if (g_eval_budget > 0) {                                                       \
+            if (setjmp(g_abort)) { g_st.status = 9; goto label; }                      \
+            g_armed = 1;                                                               \
+        }                                                                              \
+    } while (0)
 
 void orc_set_trace(orc_trace_t cb, void *user) { g_trace = cb; g_trace_user = user; }
 void orc_set_sum_mode(int mode) { g_sum_mode = mode; orc_obj_set_sum_mode(mode); }
@@ -97,9 +118,9 @@ static void trial_x(ls_t *L) {
     for (int i = 0; i < L->dim; i++) L->x[i] = L->x0[i] + a * L->p[i];
     g_st.n_trials++;
 }
-static void call_f(ls_t *L) { L->f(L->fx, L->x, &L->dim); g_st.n_f++; }
-static void call_fd(ls_t *L) { L->fd(L->fdx, L->x, &L->dim); g_st.n_fd++; }
-static void call_ffd(ls_t *L) { (void)L->f_fd(L->fx, L->fdx, L->x, &L->dim); g_st.n_ffd++; }
+static void call_f(ls_t *L) { count_eval(); L->f(L->fx, L->x, &L->dim); g_st.n_f++; }
+static void call_fd(ls_t *L) { count_eval(); L->fd(L->fdx, L->x, &L->dim); g_st.n_fd++; }
+static void call_ffd(ls_t *L) { count_eval(); (void)L->f_fd(L->fx, L->fdx, L->x, &L->dim); g_st.n_ffd++; }
 static double slope(ls_t *L) { return dot(L->fdx, L->p, L->dim); }
 static int armijo_ok(ls_t *L) { /* fx<=fx0+c1*a*phid0 (f90:1307,1328,1483,1521): NOT the complement of the next for NaN */
     return *L->fx <= L->fx0 + L->c1 * (*L->a) * L->phid0;
@@ -329,10 +350,84 @@ void orc_strongwolfe_fdwithf(const double *c1, const double *c2, orc_f_t f, orc_
     strongwolfe_impl(1, *c1, *c2, f, fd, f_fd, x, a, p, fx, *phid0, fdx, *dim, Increment);
 }
 
+/* ------------------------------------------------------------------ FLGPU_LS_FAST (NOT a reference routine)
+ * Restates the product's optional accept-at-first-Wolfe-point searcher (include/flgpu_search_core.hpp,
+ * SearchCore::fast; flgpu_options.line_search = FLGPU_LS_FAST) so that the host-driven and the
+ * device-resident implementations can be checked bit for bit.  The reference has no counterpart: with this policy the
+ * oracle pins the PRODUCT's published algorithm (Nocedal & Wright Alg. 3.5/3.6 + the safeguards below), nothing else.
+ * Selected by orc_set_line_search(1); the drivers below are unchanged (they all search through line_search()). */
+static int g_ls_policy = 0;
+void orc_set_line_search(int policy) { g_ls_policy = policy; }
+
+static double cubic_minimiser(double u, double v, double fu, double fv, double gu, double gv) {
+    const double d1 = gu + gv - 3.0 * (fu - fv) / (u - v);
+    const double disc = d1 * d1 - gu * gv;
+    const double d2 = (v - u > 0.0) ? sqrt(disc) : -sqrt(disc);
+    return v - (v - u) * (gv + d2 - d1) / (gv - gu + 2.0 * d2);
+}
+static int fast_curvature_ok(const ls_t *L, int strong, double phid) {
+    return strong ? fabs(phid) <= L->c2_m_abs_phid0 : phid >= -L->c2_m_abs_phid0;
+}
+static void fast_zoom(ls_t *L, int strong, int ffd, double lo, double hi, double flo, double fhi, double glo,
+                      double ghi) {
+    int it;
+    for (it = 0;; it++) {
+        const double w = hi - lo;
+        double t = (cubic_minimiser(lo, hi, flo, fhi, glo, ghi) - lo) / w, g, f;
+        if (!(t > 0.0 && t < 1.0)) t = 0.5;             /* no interior minimiser (or NaN): bisect */
+        else if (t < 0.05) t = 0.05;
+        else if (t > 0.95) t = 0.95;
+        *L->a = lo + t * w;
+        trial_x(L); eval_both(L, ffd); g = slope(L); f = *L->fx;
+        if (!armijo_ok(L) || f >= flo) {
+            hi = *L->a; fhi = f; ghi = g;
+        } else {
+            if (fast_curvature_ok(L, strong, g)) return;
+            if (g * (hi - lo) >= 0.0) { hi = lo; fhi = flo; ghi = glo; }
+            lo = *L->a; flo = f; glo = g;
+        }
+        if (collapsed(lo, hi) || it >= 59) {            /* give back the best sufficient-decrease point */
+            if (*L->a != lo) { *L->a = lo; trial_x(L); eval_both(L, ffd); }
+            return;
+        }
+    }
+}
+static void fast_impl(int strong, double c1, double c2, orc_f_t f, orc_fd_t fd, orc_ffd_t f_fd, double *x, double *a,
+                      const double *p, double *fx, double phid0, double *fdx, int dim) {
+    const int ffd = f_fd != NULL;
+    double a_lo = 0.0, f_lo = *fx, g_lo = phid0, g;
+    double *x0 = valloc(dim);
+    int grow;
+    ls_t L;
+    g_st.n_linesearch++;
+    memcpy(x0, x, sizeof(double) * (size_t)dim);
+    L.c1 = c1; L.c2_m_abs_phid0 = c2 * fabs(phid0); L.fx0 = *fx; L.phid0 = phid0;
+    L.f = f; L.fd = fd; L.f_fd = f_fd; L.x = x; L.x0 = x0; L.p = p; L.fdx = fdx; L.a = a; L.fx = fx;
+    L.dim = dim;
+    trial_x(&L); eval_both(&L, ffd); g = slope(&L);
+    for (grow = 0;; grow++) {
+        const double fa = *fx;
+        double an, lo_b, hi_b;
+        if (!armijo_ok(&L) || (grow > 0 && fa >= f_lo)) { fast_zoom(&L, strong, ffd, a_lo, *a, f_lo, fa, g_lo, g); break; }
+        if (fast_curvature_ok(&L, strong, g)) break;
+        if (g >= 0.0) { fast_zoom(&L, strong, ffd, *a, a_lo, fa, f_lo, g, g_lo); break; }
+        if (grow >= 39) break;
+        an = cubic_minimiser(a_lo, *a, f_lo, fa, g_lo, g);
+        lo_b = *a + 1.1 * (*a - a_lo); hi_b = *a + 4.0 * (*a - a_lo);
+        if (!(an <= hi_b)) an = hi_b;
+        if (an < lo_b) an = lo_b;
+        a_lo = *a; f_lo = fa; g_lo = g;
+        *a = an;
+        trial_x(&L); eval_both(&L, ffd); g = slope(&L);
+    }
+    free(x0);
+}
+
 /* Dispatch that every driver's 8-way (or 4-way) textual copy reduces to. */
 static void line_search(int strong, int use_ffd, double c1, double c2, orc_f_t f, orc_fd_t fd,
                         orc_ffd_t f_fd, double *x, double *a, const double *p, double *fx,
                         double phid0, double *fdx, int dim, const double *Increment) {
+    if (g_ls_policy == 1) { fast_impl(strong, c1, c2, f, fd, f_fd, x, a, p, fx, phid0, fdx, dim); return; }
     if (strong) strongwolfe_impl(use_ffd, c1, c2, f, fd, f_fd, x, a, p, fx, phid0, fdx, dim, Increment);
     else wolfe_impl(c1, c2, f, fd, x, a, p, fx, phid0, fdx, dim, Increment);
 }
@@ -369,6 +464,7 @@ void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, const int *Me
     s = valloc((long)dim * mem); y = valloc((long)dim * mem);
 #define S(i) (s + (long)(i) * dim)
 #define Y(i) (y + (long)(i) * dim)
+    ORC_ARM_BUDGET(done);
     /* f90:436-440 */
     if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }
     else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
@@ -483,6 +579,7 @@ void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, const int *Me
         printf(" Euclidean norm of gradient = %.17g\n", sqrt(dot(fdnew, fdnew, dim)));
     }
 done:
+    g_armed = 0;
     free(p); free(fdnew); free(xold); free(fdold); free(rho); free(alpha); free(s); free(y);
 #undef S
 #undef Y
@@ -526,6 +623,7 @@ static void cg_core(orc_f_t f, orc_fd_t fd, orc_ffd_t f_fd, double *x, int dim, 
     long tb;
     (void)fold;
     memset(&g_st, 0, sizeof g_st);
+    ORC_ARM_BUDGET(done);
     if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }                    /* f90:230-234 */
     else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
     for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:236 */
@@ -553,6 +651,7 @@ static void cg_core(orc_f_t f, orc_fd_t fd, orc_ffd_t f_fd, double *x, int dim, 
         printf(" Euclidean norm of gradient = %.17g\n", sqrt(dot(fdnew, fdnew, dim)));
     }
 done:
+    g_armed = 0;
     free(p); free(fdnew); free(fdold);
 }
 
@@ -615,6 +714,7 @@ void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, orc
     if (MinStepLength) minstep = *MinStepLength * *MinStepLength; else minstep = 1e-30;
     if (WolfeConst1) c1 = fmax(1e-15, *WolfeConst1); else c1 = 1e-4;
     if (WolfeConst2) c2 = fmin(1.0 - 1e-15, fmax(c1 + 1e-15, *WolfeConst2)); else c2 = 0.9;
+    ORC_ARM_BUDGET(done);
     if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }                    /* f90:86-90 */
     else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
     for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:92 */
@@ -647,6 +747,7 @@ void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, orc
         printf(" Euclidean norm of gradient = %.17g\n", sqrt(dot(fdnew, fdnew, dim)));
     }
 done:
+    g_armed = 0;
     free(p); free(fdnew); free(fdold);
 }
 

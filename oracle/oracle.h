@@ -57,6 +57,12 @@ void orc_set_trace(orc_trace_t cb, void *user);
  * 2 = pairwise double.  Modes 1/2 exist only to bound summation noise. */
 void orc_set_sum_mode(int mode);
 void orc_get_stats(orc_stats_t *out);
+/* Test-harness guard: give up (status 9) after n callback invocations inside line searches; 0 = unlimited.  The
+ * reference itself never terminates once a step is NaN (f90:1518-1546). */
+void orc_set_eval_budget(long n);
+/* 0 (default) = the reference's searchers.  1 = the product's optional FLGPU_LS_FAST searcher (NOT in the reference;
+ * restated here only so its host and device implementations can be compared bit for bit -- see oracle.c). */
+void orc_set_line_search(int policy);
 
 /* f90:398-625 */
 void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim, const int *Memory, orc_ffd_t f_fd,

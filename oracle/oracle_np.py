@@ -226,7 +226,96 @@ def strongwolfe(c1, c2, f, fd, f_fd, x, a, p, fx, phid0, Increment, cnt, fdwithf
                 cfd(); return finish()
 
 
+# ----------------------------------------------------------------- FLGPU_LS_FAST (NOT a reference routine)
+LINE_SEARCH_POLICY = 0   # 1 = the product's optional accept-at-first-Wolfe-point searcher (flgpu_options.line_search)
+
+
+def _cubic_minimiser(u, v, fu, fv, gu, gv):
+    """Minimiser of the cubic through (u, fu, gu), (v, fv, gv); NaN when there is none."""
+    d1 = gu + gv - div(3.0 * (fu - fv), u - v)
+    disc = d1 * d1 - gu * gv
+    root = math.sqrt(disc) if disc >= 0.0 else float("nan")
+    d2 = root if v - u > 0.0 else -root
+    return v - div((v - u) * (gv + d2 - d1), gv - gu + 2.0 * d2)
+
+
+def fast_search(strong, c1, c2, f, fd, f_fd, x, a, p, fx, phid0, cnt):
+    """Written from the algorithm's description in include/flgpu.h / flgpu_search_core.hpp (SearchCore::fast): Nocedal &
+    Wright Alg. 3.5/3.6; f and f' at every trial; accept the first trial with sufficient decrease and (strong or weak)
+    curvature; grow to the cubic minimiser clipped to [a+1.1(a-a_prev), a+4(a-a_prev)] (40 trials at most); zoom with
+    the cubic minimiser kept 5 % off both ends (60 trials at most), NaN counting as insufficient decrease; on a
+    collapsed bracket return the best sufficient-decrease point.  The reference has no such routine."""
+    x0 = x.copy(); fx0 = fx
+    c2abs = c2 * abs(phid0)
+    st = {"x": x, "fx": fx, "g": None}
+
+    def evaluate(aa):
+        st["x"] = x0 + aa * p; cnt.trials += 1
+        if f_fd is not None:
+            st["fx"], st["g"] = f_fd(st["x"]); cnt.n_ffd += 1
+        else:
+            st["fx"] = f(st["x"]); cnt.n_f += 1
+            st["g"] = fd(st["x"]); cnt.n_fd += 1
+        return st["fx"], dot(st["g"], p)
+
+    def decrease(aa, fa):
+        return fa <= fx0 + c1 * aa * phid0           # False for NaN
+
+    def curvature(ga):
+        return abs(ga) <= c2abs if strong else ga >= -c2abs
+
+    def zoom(lo, hi, flo, fhi, glo, ghi):
+        it = 0
+        while True:
+            w = hi - lo
+            t = div(_cubic_minimiser(lo, hi, flo, fhi, glo, ghi) - lo, w)
+            if not (0.0 < t < 1.0):
+                t = 0.5
+            else:
+                t = min(max(t, 0.05), 0.95)
+            aa = lo + t * w
+            fa, ga = evaluate(aa)
+            if (not decrease(aa, fa)) or fa >= flo:
+                hi, fhi, ghi = aa, fa, ga
+            else:
+                if curvature(ga):
+                    return aa
+                if ga * (hi - lo) >= 0.0:
+                    hi, fhi, ghi = lo, flo, glo
+                lo, flo, glo = aa, fa, ga
+            gap = abs(hi - lo)
+            if gap < 1e-15 or div(gap, max(abs(lo), abs(hi))) < 1e-15 or it >= 59:
+                if aa != lo:
+                    evaluate(lo)
+                return lo
+            it += 1
+
+    prev = (0.0, fx0, phid0)
+    fa, ga = evaluate(a)
+    for grow in range(40):
+        if (not decrease(a, fa)) or (grow > 0 and fa >= prev[1]):
+            a = zoom(prev[0], a, prev[1], fa, prev[2], ga); break
+        if curvature(ga):
+            break
+        if ga >= 0.0:
+            a = zoom(a, prev[0], fa, prev[1], ga, prev[2]); break
+        if grow == 39:
+            break
+        nxt = _cubic_minimiser(prev[0], a, prev[1], fa, prev[2], ga)
+        lo_b = a + 1.1 * (a - prev[0]); hi_b = a + 4.0 * (a - prev[0])
+        if not (nxt <= hi_b):
+            nxt = hi_b
+        if nxt < lo_b:
+            nxt = lo_b
+        prev = (a, fa, ga)
+        a = nxt
+        fa, ga = evaluate(a)
+    return st["x"], a, st["fx"], st["g"]
+
+
 def _search(strong, fdwithf, c1, c2, f, fd, f_fd, x, a, p, fx, phid0, Increment, cnt):
+    if LINE_SEARCH_POLICY == 1:
+        return fast_search(strong, c1, c2, f, fd, f_fd, x, a, p, fx, phid0, cnt)
     if strong:
         return strongwolfe(c1, c2, f, fd, f_fd, x, a, p, fx, phid0, Increment, cnt, fdwithf)
     return wolfe(c1, c2, f, fd, x, a, p, fx, phid0, Increment, cnt)

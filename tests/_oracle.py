@@ -55,7 +55,39 @@ def lib():
                                        C.c_longlong]
         _lib.orc_set_trace.argtypes = [C.c_void_p, C.c_void_p]
         _lib.orc_set_sum_mode.argtypes = [C.c_int]
+        _lib.orc_set_line_search.argtypes = [C.c_int]
+        _lib.orc_set_eval_budget.argtypes = [C.c_long]
     return _lib
+
+
+class eval_budget:
+    """Context manager: the oracle gives up (status 9) after n callback invocations inside line searches.  The
+    reference never terminates once a step is NaN (f90:1518-1546) and a ctypes callback cannot unwind C, so tests that
+    generate objectives at random run the oracle under a budget and skip the cases that exhaust it."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        lib().orc_set_eval_budget(self.n)
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_eval_budget(0)
+        return False
+
+
+class fast_line_search:
+    """Context manager: the oracle's drivers search with its restatement of the product's FLGPU_LS_FAST policy
+    (NOT a reference routine, see oracle.c) instead of the reference's searchers."""
+
+    def __enter__(self):
+        lib().orc_set_line_search(1)
+        return self
+
+    def __exit__(self, *exc):
+        lib().orc_set_line_search(0)
+        return False
 
 
 def _opt(ctype, v):

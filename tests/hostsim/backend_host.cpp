@@ -114,13 +114,14 @@ public:
     };
     double search_res[FLGPU_SEARCH_RESULT_DOUBLES] = {0};
     bool device_search_available() const override { return prob.fused != nullptr && g_nranks <= 1; }
-    void device_search(bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
+    void device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
                        double a, const double *x0, const double *p, double *xt, double *gt) override {
         callback_launches++;
         EagerSearch S(*this, x0, p);
         S.c1 = c1; S.c2abs = c2abs; S.fx0 = fx0; S.phid0 = phid0; S.incr = incr; S.fdwithf = fdwithf;
         S.a = a; S.f_cur = fx0; S.pre = 0;
-        if (strong) S.strongwolfe(); else S.wolfe();
+        if (policy == FLGPU_LS_FAST) S.fast(strong);
+        else if (strong) S.strongwolfe(); else S.wolfe();
         double fv, gv;
         if (S.have_x && S.have_g && S.a_x == S.a_g) {
             prob.fused(&ctx, FLGPU_WRITE_X | FLGPU_WRITE_G, &fv, &gv, xt, gt, x0, p, S.a_x, n);

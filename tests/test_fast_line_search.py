@@ -1,0 +1,330 @@
+"""FLGPU_LS_FAST (flgpu_options.line_search = "fast"): the optional accept-at-first-Wolfe-point
+searcher.  It is NOT a reference routine -- the reference-exact searchers stay the default and every parity test
+elsewhere runs them -- so what is checked here is
+  (a) the product's published algorithm (include/flgpu.h, flgpu_search_core.hpp SearchCore::fast) against two
+      independent restatements (oracle.c, oracle_np.py): identical bits in 1-D and on small n-D problems;
+  (b) the properties that define it: every accepted step satisfies the Wolfe conditions it was searched for, f
+      decreases monotonically, the minimiser is the reference policy's, and it needs far fewer objective passes;
+  (c) that where the trial point lives (fused / plain / device-resident search) does not change a single bit.
+The GPU half (-m gpu) runs the same checks through libflgpu.so."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _cases
+import _hostsim as H
+import _oracle as O
+import oracle_np as N
+
+capi = H.capi
+
+
+@pytest.fixture
+def np_fast():
+    N.LINE_SEARCH_POLICY = 1
+    yield
+    N.LINE_SEARCH_POLICY = 0
+
+
+def _np_objective(name, n):
+    if name.startswith("rosen"):
+        return N.rosenbrock()
+    if name == "quartic":
+        return N.quartic()
+    return N.diagquad(np.array([O.lib().orc_diag_coeff(i, n) for i in range(n)]))
+
+
+def _same_history(hist, tr):
+    assert len(hist) == len(tr.rows)
+    for k, (h, r) in enumerate(zip(hist, tr.rows)):
+        assert np.array_equal(np.array(h[3:7], dtype=float), np.array(r[1:5], dtype=float), equal_nan=True), \
+            f"scalars differ at iteration {k}"
+        assert np.array_equal(h[0], tr.p[k], equal_nan=True) and np.array_equal(h[1], tr.x[k], equal_nan=True), \
+            f"vectors differ at iteration {k}"
+
+
+def _same_points(a, b):
+    """Trial points as lists of floats; NaN equals NaN (f9_quirk is unbounded below for x < 0: once a step lands there
+    every implementation runs off to -inf and NaN in the same way)."""
+    return len(a) == len(b) and np.array_equal(np.array(a), np.array(b), equal_nan=True)
+
+
+def _same_rows(a, b):
+    return len(a) == len(b) and all(np.array_equal(np.array(u[1:], dtype=float), np.array(v[1:], dtype=float),
+                                                   equal_nan=True) for u, v in zip(a, b))
+
+
+# ----------------------------------------------------------------------------- (a) the two restatements agree
+ND_CASES = [
+    ("lbfgs", "rosenR1", 64, dict(Memory=5)), ("lbfgs", "rosenR1", 100, dict(use_ffd=True)),
+    ("lbfgs", "rosenR0", 100, dict(use_ffd=True, Memory=3)), ("lbfgs", "quartic", 10, dict()),
+    ("lbfgs", "rosenR1", 100, dict(Strong=False, use_ffd=True, MaxIteration=80)),
+    ("lbfgs", "diag", 200, dict(Memory=30, use_ffd=True, MaxIteration=80)),
+    ("lbfgs", "rosenR1", 100, dict(WolfeConst2=0.1, use_ffd=True)),
+    ("cg", "quartic", 10, dict(Method="DY")), ("cg", "quartic", 300, dict(Method="PR", use_ffd=True)),
+    ("cg", "rosenR1", 100, dict(Method="DY", use_ffd=True, MaxIteration=150)),
+    ("cg", "diag", 200, dict(Method="PR", MaxIteration=100)),
+    ("cg", "quartic", 50, dict(Method="DY", Strong=False, use_ffd=True)),
+    ("sd", "quartic", 20, dict(MaxIteration=60)), ("sd", "rosenR1", 64, dict(MaxIteration=60, use_ffd=True)),
+]
+
+
+@pytest.mark.parametrize("algo,name,n,kw", ND_CASES)
+def test_fast_c_equals_numpy_bitwise(np_fast, algo, name, n, kw):
+    kw = dict(kw)
+    use = kw.pop("use_ffd", False)
+    kind = _cases.OBJECTIVES[name][0]
+    x0 = _cases.start(name, n)
+    tr = O.Trace()
+    crun = {"lbfgs": O.lbfgs, "cg": O.cg, "sd": O.sd}[algo]
+    nrun = {"lbfgs": N.lbfgs, "cg": N.conjugate_gradient, "sd": N.steepest_descent}[algo]
+    with O.fast_line_search():
+        xa, s = crun(O.builtin_callbacks(kind, 0, n), x0.copy(), use_ffd=use, Warning=False, trace=tr, **kw)
+    f, fd, ffd = _np_objective(name, n)
+    with np.errstate(all="ignore"):
+        xb, c = nrun(f, fd, x0.copy(), f_fd=ffd if use else None, Warning=False, **kw)
+    _same_history(c.history, tr)
+    assert np.array_equal(xa, xb)
+    assert c.status == s.status and c.trials == s.n_trials
+    assert (c.n_f, c.n_fd, c.n_ffd) == (s.n_f, s.n_fd, s.n_ffd)
+
+
+# The 1-D torture functions of the reference-policy tests, except the two odd-power walls: those are unbounded below
+# for x < 0, a searcher that extrapolates lands there and every implementation then runs off to -inf / NaN, where
+# C and Python disagree on fmax(NaN, x).  Their even-power twins (bounded below) take their place.
+TORTURE = {k: v for k, v in _cases.TORTURE_1D.items() if k not in ("f9_quirk", "wall")}
+TORTURE["f9_even"] = (0.0, _cases._poly_wall(1.05 / 1.01748, 42))
+TORTURE["wall_even"] = (0.2, _cases._poly_wall(2.0, 42))
+TORTURE["far_start"] = (40.0, (lambda x: 0.5 * (x - 1.0) ** 2 + 0.1 * np.cos(3.0 * x).item(),
+                               lambda x: (x - 1.0) - 0.3 * np.sin(3.0 * x).item()))
+TORTURE["tiny_first_step"] = (5.0, (lambda x: 1e6 * _cases._pw(x, 2) + 1.0, lambda x: 2e6 * x))
+
+
+def _run_1d_oracle(case, method, use):
+    x0, (f, g) = TORTURE[case]
+    fa = _cases.Fuse(f, g)
+    cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
+    keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+    tr = O.Trace()
+    with O.fast_line_search():
+        xa, s = O.cg(tuple(C.cast(k, C.c_void_p) for k in keep), np.array([x0]), Method=method, use_ffd=use,
+                     Warning=False, MaxIteration=30, trace=tr)
+    return fa, xa, s, tr
+
+
+@pytest.mark.parametrize("case", sorted(TORTURE))
+@pytest.mark.parametrize("method", ["DY", "PR"])
+def test_fast_torture_1d_c_equals_numpy(np_fast, case, method):
+    """The 1-D functions that steer a searcher through bracketing, both zoom orientations, bisection and NaN regions."""
+    x0, (f, g) = TORTURE[case]
+    for use in (False, True):
+        fa, xa, s, tr = _run_1d_oracle(case, method, use)
+        fb = _cases.Fuse(f, g)
+        with np.errstate(all="ignore"):
+            xb, c = N.conjugate_gradient(lambda x: fb.f(float(x[0])), lambda x: np.array([fb.g(float(x[0]))]),
+                                         np.array([x0]), Method=method, Warning=False, MaxIteration=30,
+                                         f_fd=(lambda x: (lambda r: (r[0], np.array([r[1]])))(fb.fg(float(x[0]))))
+                                         if use else None)
+        assert _same_points(fa.xs, fb.xs), "the two restatements evaluated different trial points"
+        _same_history(c.history, tr)
+        assert np.array_equal(xa, xb, equal_nan=True)
+
+
+# ----------------------------------------------------------------------------- (a) product host control flow
+def _py_problem(fuse):
+    def f(ctx, fp, xp, n):
+        C.cast(fp, C.POINTER(C.c_double))[0] = fuse.f(C.cast(xp, C.POINTER(C.c_double))[0])
+
+    def fd(ctx, gp, xp, n):
+        C.cast(gp, C.POINTER(C.c_double))[0] = fuse.g(C.cast(xp, C.POINTER(C.c_double))[0])
+
+    def ffd(ctx, fp, gp, xp, n):
+        fv, gv = fuse.fg(C.cast(xp, C.POINTER(C.c_double))[0])
+        C.cast(fp, C.POINTER(C.c_double))[0] = fv
+        C.cast(gp, C.POINTER(C.c_double))[0] = gv
+    keep = (capi.F_FN(f), capi.FD_FN(fd), capi.F_FD_FN(ffd))
+    p = capi.Problem()
+    p.f, p.fd, p.f_fd = (C.cast(k, C.c_void_p) for k in keep)
+    p._keep = keep
+    return p
+
+
+@pytest.mark.parametrize("case", sorted(TORTURE))
+@pytest.mark.parametrize("method", ["DY", "PR"])
+def test_fast_torture_1d_driver_bitwise_vs_oracle(case, method):
+    """driver.cpp + SearchCore::fast over the host simulator: dim = 1 has no summation order, so every trial point,
+    step and iterate must equal the oracle's."""
+    x0, (f, g) = TORTURE[case]
+    for use in (False, True):
+        fa, xa, s, tr = _run_1d_oracle(case, method, use)
+        fb = _cases.Fuse(f, g)
+        prob = _py_problem(fb)
+        if not use:
+            prob.f_fd = None
+        L = H.lib()
+        o = capi.Options()
+        L.flgpu_hostsim_options_default(C.byref(o), 1)
+        capi.apply_options(o, Method=method, Warning=False, MaxIteration=30, line_search="fast")
+        ob = H.Observer()
+        o.observer = C.cast(ob.cb, C.c_void_p)
+        x = np.array([x0])
+        st = capi.Stats()
+        L.flgpu_hostsim_cg(C.byref(prob), C.byref(o), x.ctypes.data_as(C.c_void_p), C.c_int64(1), C.byref(st))
+        assert _same_points(fa.xs, fb.xs), "different trial points"
+        assert np.array_equal(x, xa, equal_nan=True)
+        assert st.iterations == s.n_iter and st.status == s.status
+        assert _same_rows(ob.rows, tr.rows)
+        assert (st.n_f, st.n_fd, st.n_f_fd, st.n_trials) == (s.n_f, s.n_fd, s.n_ffd, s.n_trials)
+
+
+RUNS = {"lbfgs": (H.lbfgs, O.lbfgs), "cg": (H.cg, O.cg), "sd": (H.sd, O.sd)}
+TRAJ_CASES = [
+    ("lbfgs", "rosenR1", dict(Memory=10)), ("lbfgs", "rosenR1", dict(Memory=3, use_ffd=False)),
+    ("lbfgs", "quartic", dict(Memory=5, Strong=False)), ("lbfgs", "diag", dict(Memory=7, MaxIteration=60)),
+    ("cg", "quartic", dict(Method="DY")), ("cg", "quartic", dict(Method="PR", use_ffd=False)),
+    ("cg", "rosenR1", dict(Method="DY", Strong=False, MaxIteration=80)),
+    ("sd", "quartic", dict(MaxIteration=50)), ("sd", "rosenR1", dict(MaxIteration=50, Strong=False)),
+]
+
+
+@pytest.mark.parametrize("algo,name,kw", TRAJ_CASES)
+def test_fast_trajectory_within_oracle_envelope(algo, name, kw):
+    """n-D: the driver's first 20 directions against the oracle's fast-policy run, inside the oracle's own
+    summation-order envelope (the same criterion the reference-exact policy is held to)."""
+    n = 2000
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    kind = _cases.OBJECTIVES[name][0]
+    hrun, orun = RUNS[algo]
+    with O.fast_line_search():
+        traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: orun(cbs, x, use_ffd=use, **k), **kw)
+    ob = H.Observer(max_vec_iters=20)
+    # plain mode: the oracle has no fused evaluation, so evaluation counters are comparable as well
+    x, st = hrun(kind, _cases.start(name, n), observer=ob, use_ffd=use, Warning=False, n_global=n, fused=False,
+                 line_search="fast", **kw)
+    _cases.check_envelope(traces, ob.p, f"fast {algo} {name} {kw}")
+    assert [r[4] for r in ob.rows[:5]] == [r[4] for r in traces[0].rows[:5]]     # trial counts of the first searches
+
+
+# ----------------------------------------------------------------------------- (c) fused = plain = device-resident
+@pytest.mark.parametrize("algo,name,kw", TRAJ_CASES)
+def test_fast_fused_plain_and_device_search_identical(algo, name, kw):
+    n = 3001
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    kind = _cases.OBJECTIVES[name][0]
+    out = []
+    for fused, dsearch in ((True, False), (False, False), (True, True)):
+        ob = H.Observer(max_vec_iters=10**9)
+        x, st = RUNS[algo][0](kind, _cases.start(name, n), observer=ob, Warning=False, n_global=n, fused=fused,
+                              device_search=dsearch, use_ffd=use, line_search="fast", **kw)
+        out.append((x, st, ob))
+    (xa, sa, oa) = out[0]
+    for tag, (xb, sb, ob_) in (("plain", out[1]), ("device-search", out[2])):
+        assert np.array_equal(xa, xb), tag
+        assert oa.rows == ob_.rows, tag
+        assert all(np.array_equal(u, v) for u, v in zip(oa.p, ob_.p)), tag
+        assert all(np.array_equal(u, v) for u, v in zip(oa.x, ob_.x)), tag
+        assert all(np.array_equal(u, v) for u, v in zip(oa.g, ob_.g)), tag
+        assert (sa.iterations, sa.status, sa.n_trials, sa.n_linesearch) == \
+               (sb.iterations, sb.status, sb.n_trials, sb.n_linesearch), tag
+        # one evaluation of f and f' per trial on every path; a fused probe counts as f_fd, separate callbacks as f + fd
+        assert sa.n_f + sa.n_f_fd == sb.n_f + sb.n_f_fd and sa.n_fd + sa.n_f_fd == sb.n_fd + sb.n_f_fd, tag
+    if algo == "lbfgs":
+        # the first trial of every search rides on the speculative K1->K2->K3 chain and is usually accepted: about one
+        # host round trip per iteration, which is why device_search = auto stays off under this policy
+        assert sa.host_syncs < 1.6 * sa.iterations + 20
+
+
+# ----------------------------------------------------------------------------- (b) defining properties
+def check_wolfe_rows(rows, ps, gs, f_start, c1, c2, strong, what, rtol=1e-9):
+    """rows[k] = (iteration, step, f, phid0, trials), ps/gs = direction searched / gradient accepted.  Every accepted
+    step must satisfy sufficient decrease and the curvature condition for (c1, c2); f must not increase."""
+    f_prev, checked = f_start, 0
+    for k, (row, p, g) in enumerate(zip(rows, ps, gs)):
+        _, a, f, phid0, trials = row
+        if f_prev <= 1e-16 * abs(f_start):
+            break            # the tail where f is rounding noise (x = x* to 1e-13): searches end on their safeguards
+        checked += 1
+        assert phid0 < 0.0
+        slack = rtol * (abs(f_prev) + abs(f)) + 1e-300
+        assert f <= f_prev + c1 * a * phid0 + slack, f"{what}: step {k} violates sufficient decrease"
+        gp = float(np.dot(g, p))
+        cslack = rtol * float(np.linalg.norm(g) * np.linalg.norm(p)) + 1e-300
+        if strong:
+            assert abs(gp) <= c2 * abs(phid0) + cslack, f"{what}: step {k} violates strong curvature ({gp} vs {phid0})"
+        else:
+            assert gp >= -c2 * abs(phid0) - cslack, f"{what}: step {k} violates weak curvature"
+        f_prev = f
+    return checked
+
+
+def _objective_value(kind, x):
+    fo = C.c_double()
+    n = x.size
+    O.lib().orc_obj_select(kind, 0, n)
+    O.lib().orc_obj_f(C.byref(fo), x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(n)))
+    return fo.value
+
+
+@pytest.mark.parametrize("algo,name,kw,c2", [
+    ("lbfgs", "rosenR1", dict(Memory=10), 0.9), ("lbfgs", "rosenR1", dict(Memory=5, WolfeConst2=0.1), 0.1),
+    ("lbfgs", "quartic", dict(Memory=5, Strong=False), 0.9), ("lbfgs", "diag", dict(Memory=30, MaxIteration=300), 0.9),
+    ("cg", "quartic", dict(Method="DY"), 0.45), ("cg", "rosenR1", dict(Method="PR", MaxIteration=400), 0.45),
+    ("cg", "quartic", dict(Method="DY", Strong=False), 0.45), ("sd", "quartic", dict(MaxIteration=80), 0.9),
+])
+def test_fast_steps_satisfy_the_wolfe_conditions(algo, name, kw, c2):
+    n = 2000
+    kind = _cases.OBJECTIVES[name][0]
+    x0 = _cases.start(name, n)
+    ob = H.Observer()
+    x, st = RUNS[algo][0](kind, x0, observer=ob, Warning=False, n_global=n, line_search="fast", **kw)
+    strong = kw.get("Strong", True) or kw.get("Method") == "PR"
+    rows = ob.rows
+    # the run may end on a collapsed bracket (step-length convergence): the last step is then exempt
+    if st.status == capi.STEP_CONVERGED:
+        rows = rows[:-1]
+    assert check_wolfe_rows(rows, ob.p, ob.g, _objective_value(kind, x0), 1e-4, c2, strong, f"{algo} {name}") > 3
+
+
+@pytest.mark.parametrize("name,mem", [("rosenR0", 10), ("rosenR1", 10), ("rosenR1", 5)])
+def test_fast_reaches_the_reference_minimiser_with_fewer_passes(name, mem):
+    """Same minimiser as the reference-exact policy (north_star's 1e-8), at a fraction of the objective passes."""
+    n = 2000
+    kind = _cases.OBJECTIVES[name][0]
+    xr, sr = H.lbfgs(kind, _cases.start(name, n), Warning=False, n_global=n, Memory=mem)
+    xf, sf = H.lbfgs(kind, _cases.start(name, n), Warning=False, n_global=n, Memory=mem, line_search="fast")
+    assert sf.status in (capi.CONVERGED, capi.STEP_CONVERGED)
+    assert _cases.rel(xf, xr) < 1e-8 and np.abs(xf - 1.0).max() < 1e-8
+    # one f and f' per trial: trials + the initial evaluation
+    assert sf.n_f_fd == sf.n_trials + 1 and sf.n_f == 0 and sf.n_fd == 0
+    assert sf.n_trials / sf.iterations < 2.0 < sr.n_trials / sr.iterations
+    assert sf.n_trials < 0.5 * sr.n_trials, (sf.n_trials, sr.n_trials)
+
+
+def test_fast_default_is_reference_and_increment_is_ignored():
+    n = 500
+    kind = _cases.OBJECTIVES["rosenR1"][0]
+    xa, sa = H.lbfgs(kind, _cases.start("rosenR1", n), Warning=False, n_global=n, MaxIteration=30)
+    xb, sb = H.lbfgs(kind, _cases.start("rosenR1", n), Warning=False, n_global=n, MaxIteration=30, line_search="reference")
+    assert np.array_equal(xa, xb) and sa.n_trials == sb.n_trials
+    xc, sc = H.lbfgs(kind, _cases.start("rosenR1", n), Warning=False, n_global=n, MaxIteration=30, line_search="fast")
+    xd, sd_ = H.lbfgs(kind, _cases.start("rosenR1", n), Warning=False, n_global=n, MaxIteration=30, line_search="fast",
+                      Increment=3.0)
+    assert np.array_equal(xc, xd) and sc.n_trials == sd_.n_trials
+    assert not np.array_equal(xa, xc)
+
+
+def test_fast_nan_objective_terminates():
+    """A NaN objective value counts as insufficient decrease: the bracket shrinks away from it and the search ends."""
+    fa = _cases.Fuse(*_cases.TORTURE_1D["nan_region"][1], limit=10**9)
+    prob = _py_problem(fa)
+    L = H.lib()
+    o = capi.Options()
+    L.flgpu_hostsim_options_default(C.byref(o), 1)
+    capi.apply_options(o, Warning=False, MaxIteration=50, line_search="fast")
+    x = np.array([_cases.TORTURE_1D["nan_region"][0]])
+    st = capi.Stats()
+    L.flgpu_hostsim_cg(C.byref(prob), C.byref(o), x.ctypes.data_as(C.c_void_p), C.c_int64(1), C.byref(st))
+    assert abs(x[0]) < 1e-7 and st.n_trials < 400

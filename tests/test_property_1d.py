@@ -67,7 +67,7 @@ def test_cg_and_sd_trajectories_are_bitwise_the_oracles(algo, kind, p, q, r, x0,
     keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
     cbs = tuple(C.cast(k, C.c_void_p) for k in keep)
     tr = O.Trace()
-    with np.errstate(all="ignore"):
+    with np.errstate(all="ignore"), O.eval_budget(20 * fa.limit):
         if algo == "cg":
             xa, s = O.cg(cbs, np.array([x0]), Method=method, use_ffd=use, trace=tr, **opts)
         else:
@@ -116,7 +116,7 @@ def test_gpu_fortran_abi_trajectories_are_bitwise_the_oracles(algo, kind, p, q, 
     cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
     keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
     cbs = tuple(C.cast(k, C.c_void_p) for k in keep)
-    with np.errstate(all="ignore"):
+    with np.errstate(all="ignore"), O.eval_budget(20 * fa.limit):
         if algo == "cg":
             xa, s = O.cg(cbs, np.array([x0]), Method=method, use_ffd=use, **opts)
         else:
