@@ -49,6 +49,9 @@ def workload(n, mem, objective="rosenbrock"):
             f"seed {SEED}, f_fd present, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
 
 
+POLICIES = {"reference": "reference (StrongWolfe_fdwithf f90:1582-1698, statement by statement)",
+            "fast": "fast (FLGPU_LS_FAST: first trial satisfying the strong Wolfe conditions is accepted; not a "
+                    "reference routine)"}
 LS_MODES = {True: "fused (flgpu_fused_fn: objective kernel forms x0+a*p; 2n doubles per trial + 4n per accepted step)",
             False: "plain (opaque f/fd/f_fd device callbacks; 7n doubles per f+g trial)"}
 NCU_NAMES = {"k1_update_dots": "k1_update_dots_kernel", "k3_direction": "k3_direction_kernel", "trial_x": "trial_kernel",
@@ -195,7 +198,8 @@ def run_ours(args):
     prob = fl.builtin_problem(OBJ)
     first, last = mem + W - 1, mem + W + K - 1   # observer indices bracketing exactly K main-loop iterations
 
-    def timed_run(time_kernels, fused=True):
+    def timed_run(time_kernels, fused=True, policy=None):
+        policy = policy or args.line_search
         x = fl.DeviceVector.start(START, n_local, seed=SEED, offset=lo, n_global=n)
         ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         mark = {}
@@ -219,7 +223,7 @@ def run_ours(args):
             return False
         ob = fl.Observer(on_iteration=on_iter)
         st = fl.LBFGS(prob, x, Memory=mem, Warning=False, MaxIteration=W + K, observer=ob, comm=comm, offset=lo,
-                      n_global=n, time_kernels=time_kernels, fused=fused, device_search=DS)
+                      n_global=n, time_kernels=time_kernels, fused=fused, device_search=DS, line_search=policy)
         if "t1" not in mark:
             raise SystemExit(f"bench.py: optimizer stopped after {st.iterations} iterations (status {st.status}) "
                              f"before {last + 1}; lower --steps")
@@ -253,6 +257,19 @@ def run_ours(args):
         dist.all_reduce(t3, op=dist.ReduceOp.MAX)
     other = {"line_search": LS_MODES[not fused], "value": K / (float(t3.item()) * 1e-3), "unit": UNIT,
              "trials_in_timed_region": mark3["c1"][2] - mark3["c0"][2]}
+    # ---- pass 4: the optional FLGPU_LS_FAST policy (NOT the reference's searcher: iterates differ, so this is a
+    # separate record and never the headline)
+    fast = None
+    if args.line_search == "reference":
+        ms4, mark4, _, _ = timed_run(False, fused, "fast")
+        t4 = torch.tensor([ms4], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        tr4 = mark4["c1"][2] - mark4["c0"][2]
+        fast = {"line_search_policy": POLICIES["fast"], "value": K / (float(t4.item()) * 1e-3), "unit": UNIT,
+                "ms_per_step": float(t4.item()) / K, "trials_in_timed_region": tr4, "trials_per_iteration": tr4 / K,
+                "note": "same K-iteration window of a run made with line_search=fast; iteration rate, not time to "
+                        "solution (DESIGN.md 3.2: with WolfeConst2 = 0.9 this policy needs more iterations on Rosenbrock)"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -293,6 +310,7 @@ def run_ours(args):
     L = fl.lib()
     if world == 1 and not fused:
         os.environ["FLGPU_NO_FUSED"] = "1"
+    L.flgpu_set_line_search(fl.LS_FAST if args.line_search == "fast" else fl.LS_REFERENCE)   # Fortran-ABI calls
     ref_cbs = (fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN())
     L.flgpu_builtin_ref_callbacks(OBJ, C.byref(ref_cbs[0]), C.byref(ref_cbs[1]), C.byref(ref_cbs[2]))
 
@@ -312,7 +330,7 @@ def run_ours(args):
             L.flgpu_last_stats(C.byref(ste))
         else:
             ste = fl.LBFGS(prob, xh, Memory=mem, Warning=False, MaxIteration=maxit, comm=comm, offset=lo, n_global=n,
-                           fused=fused)
+                           fused=fused, line_search=args.line_search)
         e1.record()
         barrier()
         ms = max(e0.elapsed_time(e1), (time.time() - te) * 1e3)
@@ -352,12 +370,13 @@ def run_ours(args):
                                          if fl.lib().flgpu_comm_uses_peer_memory(comm) else "ncclAllGather + combine kernel")),
                            "l2": "inputs (2 GiB/vector) exceed L2; no flush needed",
                            "line_search": LS_MODES[fused],
+                           "line_search_policy": POLICIES[args.line_search],
                            "device_resident_search": (f"{args.device_search}: " + (
                                "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
                                "off at this size (host-driven, one round trip per trial)")),
                            "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "other_line_search_mode": other}
+                "other_line_search_mode": other, "fast_line_search_policy": fast}
         print(json.dumps(line), flush=True)
     if comm is not None:
         fl.lib().flgpu_comm_destroy(comm)
@@ -380,6 +399,9 @@ def main():
                     help="main-loop iterations of the end-to-end optimizer call (its 487-trial prologue is amortised over them)")
     ap.add_argument("--device-search", default="auto", choices=["auto", "on", "off"],
                     help="flgpu_options.device_search; auto = up to 2^25 rows per GPU (same bits either way)")
+    ap.add_argument("--line-search", default="reference", choices=["reference", "fast"],
+                    help="flgpu_options.line_search for the whole run; the headline is `reference` (the default run "
+                         "also records the `fast` rate beside it)")
     ap.add_argument("--plain", action="store_true", help="headline with opaque callbacks (no fused line-search evaluation)")
     ap.add_argument("--cpu-log2n", type=int, default=None, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

@@ -54,6 +54,11 @@ module NonlinearOptimization_flgpu
             import :: c_int
             integer(c_int), value :: space
         end subroutine flgpu_set_x_space
+        !0 = the reference's line searchers (default), 1 = FLGPU_LS_FAST (not a reference routine), -1 = unset
+        subroutine flgpu_set_line_search(policy) bind(C, name='flgpu_set_line_search')
+            import :: c_int
+            integer(c_int), value :: policy
+        end subroutine flgpu_set_line_search
         function flgpu_current_stream() bind(C, name='flgpu_current_stream') result(stream)
             import :: c_ptr
             type(c_ptr) :: stream

@@ -328,3 +328,134 @@ def test_fast_nan_objective_terminates():
     st = capi.Stats()
     L.flgpu_hostsim_cg(C.byref(prob), C.byref(o), x.ctypes.data_as(C.c_void_p), C.c_int64(1), C.byref(st))
     assert abs(x[0]) < 1e-7 and st.n_trials < 400
+
+
+# ============================================================================= GPU half (libflgpu.so, -m gpu)
+@pytest.fixture(scope="module")
+def fl():
+    import fortran_library_b200 as fl
+    fl.require_gpu()          # fails loudly: there is no fallback to test instead
+    return fl
+
+
+def _gpu_problem(fl, name, use_ffd=True):
+    p = fl.builtin_problem(_cases.OBJECTIVES[name][0])
+    if not use_ffd:
+        p.f_fd = None
+    return p
+
+
+def _gpu_start(fl, name, n):
+    kind, st, seed = _cases.OBJECTIVES[name]
+    return fl.DeviceVector.start(st, n, seed=seed)
+
+
+def _gpu_run(fl, algo):
+    return {"lbfgs": fl.LBFGS, "cg": fl.ConjugateGradient, "sd": fl.SteepestDescent}[algo]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(TORTURE))
+@pytest.mark.parametrize("method", ["DY", "PR"])
+def test_gpu_fast_fortran_abi_torture_1d_bitwise(fl, case, method):
+    """The reference's own symbol with the policy set through flgpu_set_line_search (the Fortran signature has no room
+    for it), host callbacks staged by the library: every trial point and the result equal the oracle's fast-policy
+    run bit for bit."""
+    x0, (f, g) = TORTURE[case]
+    L = fl.lib()
+    for use in (False, True):
+        fa, xa, s, tr = _run_1d_oracle(case, method, use)
+        fb = _cases.Fuse(f, g)
+        cf, cfd, cffd = _cases.make_ref_callbacks(fb.f, fb.g, fb.fg)
+        keep = (fl.capi.REF_F_FN(cf), fl.capi.REF_FD_FN(cfd), fl.capi.REF_F_FD_FN(cffd))
+        x = np.array([x0])
+        m = method.encode()
+        L.flgpu_set_callback_space(fl.SPACE_HOST)
+        L.flgpu_set_line_search(fl.LS_FAST)
+        try:
+            L.__getattr__("__nonlinearoptimization_MOD_conjugategradient")(
+                keep[0], keep[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), m, keep[2] if use else None,
+                None, C.byref(C.c_int32(0)), C.byref(C.c_int(30)), None, None, None, None, None, C.c_int(len(m)))
+        finally:
+            L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+            L.flgpu_set_line_search(-1)
+        st = fl.capi.Stats()
+        L.flgpu_last_stats(C.byref(st))
+        assert _same_points(fa.xs, fb.xs), "different trial points"
+        assert np.array_equal(x, xa, equal_nan=True)
+        assert st.iterations == s.n_iter and st.status == s.status
+        assert (st.n_f, st.n_fd, st.n_f_fd, st.n_trials) == (s.n_f, s.n_fd, s.n_ffd, s.n_trials)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
+@pytest.mark.parametrize("algo,name,kw", TRAJ_CASES)
+def test_gpu_fast_trajectory_within_oracle_envelope(fl, algo, name, kw, fused):
+    n = 10_000
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    orun = RUNS[algo][1]
+    with O.fast_line_search():
+        traces, _ = _cases.oracle_envelope(name, n, lambda cbs, x, **k: orun(cbs, x, use_ffd=use, **k), **kw)
+    ob = fl.Observer(keep_vectors=True, max_vec_iters=20)
+    x = _gpu_start(fl, name, n)
+    st = _gpu_run(fl, algo)(_gpu_problem(fl, name, use), x, observer=ob, Warning=False, fused=fused, line_search="fast", **kw)
+    _cases.check_envelope(traces, ob.p, f"gpu fast {algo} {name} {kw} fused={fused}")
+    assert ob.rows[0][4] == traces[0].rows[0][4]          # first search: same trial count as the oracle's
+    assert st.gpu_launches > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [10_000, 4097])
+@pytest.mark.parametrize("algo,name,kw", TRAJ_CASES)
+def test_gpu_fast_device_resident_search_identical(fl, algo, name, kw, n):
+    """search_kernel<KIND, FAST = true>: SearchCore::fast run by every thread of one cooperative kernel gives the bits
+    of the host-driven fused search (same launch geometry, same reductions)."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    out = []
+    for dev in (False, True):
+        x = _gpu_start(fl, name, n)
+        ob = fl.Observer(keep_vectors=True, max_vec_iters=12)
+        st = _gpu_run(fl, algo)(_gpu_problem(fl, name, use), x, observer=ob, Warning=False, device_search=dev,
+                                line_search="fast", **kw)
+        out.append((x.numpy(), st, ob))
+    (xa, sa, oa), (xb, sb, ob_) = out
+    assert oa.rows == ob_.rows
+    assert np.array_equal(xa, xb)
+    assert all(np.array_equal(u, v) for u, v in zip(oa.p, ob_.p))
+    for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_linesearch"):
+        assert getattr(sa, k) == getattr(sb, k), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo,name,kw,c2", [
+    ("lbfgs", "rosenR1", dict(Memory=10), 0.9), ("lbfgs", "rosenR1", dict(Memory=5, WolfeConst2=0.1), 0.1),
+    ("lbfgs", "quartic", dict(Memory=5, Strong=False), 0.9), ("cg", "quartic", dict(Method="DY"), 0.45),
+    ("cg", "rosenR1", dict(Method="PR", MaxIteration=400), 0.45), ("sd", "quartic", dict(MaxIteration=80), 0.9),
+])
+def test_gpu_fast_steps_satisfy_the_wolfe_conditions(fl, algo, name, kw, c2):
+    n = 10_000
+    kind = _cases.OBJECTIVES[name][0]
+    ob = fl.Observer(keep_vectors=True)
+    x = _gpu_start(fl, name, n)
+    st = _gpu_run(fl, algo)(_gpu_problem(fl, name), x, observer=ob, Warning=False, line_search="fast", **kw)
+    strong = kw.get("Strong", True) or kw.get("Method") == "PR"
+    rows = ob.rows[:-1] if st.status == fl.STEP_CONVERGED else ob.rows
+    assert check_wolfe_rows(rows, ob.p, ob.g, _objective_value(kind, _cases.start(name, n)), 1e-4, c2, strong,
+                            f"gpu {algo} {name}") > 3
+
+
+@pytest.mark.gpu
+def test_gpu_fast_reaches_the_reference_minimiser_with_fewer_passes(fl):
+    n = 10_000
+    for name in ("rosenR0", "rosenR1"):
+        xr = _gpu_start(fl, name, n)
+        sr = fl.LBFGS(_gpu_problem(fl, name), xr, Warning=False)
+        xf = _gpu_start(fl, name, n)
+        sf = fl.LBFGS(_gpu_problem(fl, name), xf, Warning=False, line_search="fast")
+        assert _cases.rel(xf.numpy(), xr.numpy()) < 1e-8 and np.abs(xf.numpy() - 1.0).max() < 1e-8
+        assert sf.n_f_fd == sf.n_trials + 1 and sf.n_f == 0 and sf.n_fd == 0
+        assert sf.n_trials / sf.iterations < 2.0 < sr.n_trials / sr.iterations
+        # the first trial rides on the speculative K1 -> K2 -> K3 chain: about one host round trip per iteration
+        assert sf.host_syncs < 1.6 * sf.iterations + 20
