@@ -264,9 +264,11 @@ def builtin_constraints(kind=CON_SPHERE):
 
 def AugmentedLagrangian(problem, constraints, x, UnconstrainedSolver="LBFGS", lambda0=None, miu0=None, Memory=None,
                         Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
-                        WolfeConst1=None, WolfeConst2=None, Increment=None, stream=None, comm=None, offset=0, n_global=0):
+                        WolfeConst1=None, WolfeConst2=None, Increment=None, stream=None, comm=None, offset=0, n_global=0,
+                        line_search=None):
     """Equality-constrained minimisation (reference: AugmentedLagrangian, f90:2005-2241) with the hot path as inner
-    solver: UnconstrainedSolver 'LBFGS' or 'ConjugateGradient' (the dense-Hessian solvers are outside the GPU path)."""
+    solver: UnconstrainedSolver 'LBFGS' or 'ConjugateGradient' (the dense-Hessian solvers are outside the GPU path).
+    line_search="fast" runs every inner solve with FLGPU_LS_FAST (not a reference routine)."""
     import numpy as np
     if UnconstrainedSolver not in ("LBFGS", "ConjugateGradient"):
         raise SystemExit("Program abort: unsupported unconstrained solver " + str(UnconstrainedSolver))
@@ -279,7 +281,7 @@ def AugmentedLagrangian(problem, constraints, x, UnconstrainedSolver="LBFGS", la
     L.flgpu_al_options_default(C.byref(o), capi.AL_CG if UnconstrainedSolver == "ConjugateGradient" else capi.AL_LBFGS)
     capi.apply_options(o.inner, Memory=Memory, Method=Method, Strong=Strong, Warning=Warning, MaxIteration=MaxIteration,
                        Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
-                       WolfeConst2=WolfeConst2, Increment=Increment)
+                       WolfeConst2=WolfeConst2, Increment=Increment, line_search=line_search)
     o.inner.stream, o.inner.comm, o.inner.offset, o.inner.n_global = stream, comm, offset, n_global
     lam = None
     if lambda0 is not None:

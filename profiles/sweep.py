@@ -20,6 +20,7 @@ PEAK = 6467.7
 
 def one(algo, kind, start, seed, n, K, W, **kw):
     x = fl.DeviceVector.start(start, n, seed=seed)
+    kw = dict(kw)
     mem = kw.get("Memory", 0)
     first = (mem if algo == "lbfgs" else 1) + W - 1
     last = first + K
@@ -55,6 +56,9 @@ def main():
     ap.add_argument("--max-log2n", type=int, default=28)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--line-search", default="reference", choices=["reference", "fast"],
+                    help="flgpu_options.line_search for every case (fast = FLGPU_LS_FAST, not a reference routine)")
+    ap.add_argument("--skip", default="", help="comma-separated substrings of case labels to leave out")
     a = ap.parse_args()
     fl.require_gpu()
     rows = []
@@ -71,6 +75,11 @@ def main():
     for log2n in range(a.min_log2n, a.max_log2n + 1):
         n = 1 << log2n
         for label, algo, kind, start, seed, kw in cases:
+            if any(t and t in label for t in a.skip.split(",")):
+                continue
+            if a.line_search != "reference":
+                kw = dict(kw, line_search=a.line_search)
+                label += f", line_search={a.line_search}"
             mem = kw.get("Memory", 0)
             if (2 * mem + 6) * 8 * n > 170e9:
                 continue

@@ -459,3 +459,29 @@ def test_gpu_fast_reaches_the_reference_minimiser_with_fewer_passes(fl):
         assert sf.n_trials / sf.iterations < 2.0 < sr.n_trials / sr.iterations
         # the first trial rides on the speculative K1 -> K2 -> K3 chain: about one host round trip per iteration
         assert sf.host_syncs < 1.6 * sf.iterations + 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solver,kw", [("LBFGS", dict()), ("ConjugateGradient", dict())])
+@pytest.mark.parametrize("n", [10, 4097])
+def test_gpu_fast_augmented_lagrangian(fl, solver, kw, n):
+    """AugmentedLagrangian (f90:2005-2241) hands `inner.line_search` to every inner solve.  sum x^4 on the unit sphere has
+    2^n equivalent minimisers (|x_i| = n^-1/2), so the comparison with the oracle's fast-policy run is on what they share:
+    the constraint, the objective value 1/n and the outer-iteration count."""
+    x0 = _cases.start("quartic", n)
+    prob, con = fl.builtin_problem(fl.OBJ_QUARTIC), fl.builtin_constraints()
+    with O.fast_line_search():
+        xr, sr = O.al(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), O.sphere_constraint(), x0.copy(),
+                      UnconstrainedSolver=solver, use_ffd=True, Warning=False, MaxIteration=60, Precision=1e-6, **kw)
+    x = x0.copy()
+    st = fl.AugmentedLagrangian(prob, con, x, UnconstrainedSolver=solver, Warning=False, MaxIteration=60, Precision=1e-6,
+                                line_search="fast", **kw)
+    assert st.status == 0 and sr.status == 0 and st.gpu_launches > 0
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-6
+    assert abs(float(np.sum(x ** 4)) - float(np.sum(xr ** 4))) < 1e-5 / n
+    assert abs(st.outer_iterations - sr.outer_iterations) <= 1
+    # far fewer objective passes than the reference policy needs for the same job
+    xs = x0.copy()
+    ss = fl.AugmentedLagrangian(prob, con, xs, UnconstrainedSolver=solver, Warning=False, MaxIteration=60, Precision=1e-6,
+                                **kw)
+    assert st.trials < 0.5 * ss.trials

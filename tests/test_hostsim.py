@@ -249,7 +249,9 @@ dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("lbfgs,name,kw", [(True, "rosenR1", dict(Memory=6)), (True, "diag", dict(Memory=4)),
-                                           (False, "quartic", dict(Method="PR"))])
+                                           (False, "quartic", dict(Method="PR")),
+                                           (True, "rosenR1", dict(Memory=6, line_search="fast")),
+                                           (False, "quartic", dict(Method="DY", line_search="fast"))])
 def test_row_sharded_two_ranks_gloo(tmp_path, lbfgs, name, kw):
     """N>1 path on CPU: two processes, each owning a row shard, exchanging only the partial dots
     (all-gather over gloo) and summing them in rank order.  Both ranks must take identical decisions
@@ -277,6 +279,7 @@ def test_row_sharded_two_ranks_gloo(tmp_path, lbfgs, name, kw):
     x2 = np.concatenate([r0["x"], r1["x"]])
     p2 = np.concatenate([r0["p"], r1["p"]], axis=1)
     assert st.iterations == int(r0["iters"])
-    assert _cases.rel(x2, xs) < 1e-7
+    # relative 1e-7, scaled by |x0| where the minimiser is 0 (quartic: |x| ~ 1e-3 |x0| after 25 iterations)
+    assert np.linalg.norm(x2 - xs) / max(np.linalg.norm(xs), np.linalg.norm(x0)) < 1e-7
     for k in range(min(len(ob.p), len(p2), 8)):
         assert _cases.rel(p2[k], ob.p[k]) < 1e-9
