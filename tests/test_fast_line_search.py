@@ -485,3 +485,78 @@ def test_gpu_fast_augmented_lagrangian(fl, solver, kw, n):
     ss = fl.AugmentedLagrangian(prob, con, xs, UnconstrainedSolver=solver, Warning=False, MaxIteration=60, Precision=1e-6,
                                 **kw)
     assert st.trials < 0.5 * ss.trials
+
+
+# ============================================================================= property test (CPU)
+from hypothesis import HealthCheck, given, settings      # noqa: E402
+from hypothesis import strategies as hst                 # noqa: E402
+from test_property_1d import _objective                  # noqa: E402  (the objective families of the reference-policy property test)
+
+FAST_COUNTS = {"compared": 0, "skipped": 0}
+
+
+@pytest.mark.timeout(300)
+@settings(max_examples=300, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(algo=hst.sampled_from(["cg", "sd"]), kind=hst.sampled_from(["quartic", "steep", "cosh", "well"]),
+       p=hst.floats(0.1, 10.0), q=hst.floats(-2.0, 2.0), r=hst.floats(0.01, 3.0), x0=hst.floats(-3.0, 3.0),
+       method=hst.sampled_from(["DY", "PR"]), strong=hst.booleans(), use=hst.booleans(),
+       c1=hst.floats(1e-6, 0.3), c2frac=hst.floats(0.05, 0.95), fused=hst.booleans())
+def test_fast_property_1d_driver_bitwise_vs_oracle(algo, kind, p, q, r, x0, method, strong, use, c1, c2frac, fused):
+    """Random objective families, starts and tunables in ONE dimension (no summation order): driver.cpp + SearchCore::fast
+    over the host simulator must reproduce the oracle's fast-policy run bit for bit -- every trial point, accepted step,
+    evaluation counter and the result -- and every accepted step must satisfy the Wolfe conditions it was searched for."""
+    f, g = _objective(kind, p, q, r)
+    c2 = c1 + c2frac * (0.99 - c1)
+    opts = dict(Strong=strong, Warning=False, MaxIteration=12, WolfeConst1=c1, WolfeConst2=c2)
+    fa = _cases.Fuse(f, g, limit=10**9)
+    cf, cfd, cffd = _cases.make_ref_callbacks(fa.f, fa.g, fa.fg)
+    keep = (O.F_T(cf), O.FD_T(cfd), O.FFD_T(cffd))
+    cbs = tuple(C.cast(k, C.c_void_p) for k in keep)
+    tr = O.Trace()
+    with np.errstate(all="ignore"), O.fast_line_search(), O.eval_budget(20000):
+        if algo == "cg":
+            xa, s = O.cg(cbs, np.array([x0]), Method=method, use_ffd=use, trace=tr, **opts)
+        else:
+            xa, s = O.sd(cbs, np.array([x0]), use_ffd=use, trace=tr, **opts)
+    assert s.status != 9, "the fast searcher is bounded: 100 trials per search at most"
+    if any(not np.isfinite(v) for v in fa.xs):
+        FAST_COUNTS["skipped"] += 1
+        return                    # a step ran off to inf / NaN (the guarded families saturate at 1e300)
+    FAST_COUNTS["compared"] += 1
+    fb = _cases.Fuse(f, g, limit=10**9)
+    prob = _py_problem(fb)
+    if not use:
+        prob.f_fd = None
+    L = H.lib()
+    o = capi.Options()
+    L.flgpu_hostsim_options_default(C.byref(o), int(algo == "cg"))
+    capi.apply_options(o, Method=method if algo == "cg" else None, line_search="fast", **opts)
+    o.no_fused = int(not fused)     # _py_problem supplies no fused callback: both settings must take the plain path
+    ob = H.Observer()
+    o.observer = C.cast(ob.cb, C.c_void_p)
+    x = np.array([x0])
+    stt = capi.Stats()
+    fn = L.flgpu_hostsim_cg if algo == "cg" else L.flgpu_hostsim_sd
+    fn(C.byref(prob), C.byref(o), x.ctypes.data_as(C.c_void_p), C.c_int64(1), C.byref(stt))
+    assert _same_points(fa.xs, fb.xs), "different trial points"
+    assert np.array_equal(x, xa, equal_nan=True)
+    assert stt.iterations == s.n_iter and stt.status == s.status
+    assert _same_rows(ob.rows, tr.rows)
+    assert (stt.n_f, stt.n_fd, stt.n_f_fd, stt.n_trials) == (s.n_f, s.n_fd, s.n_ffd, s.n_trials)
+    assert max(r_[4] for r_ in ob.rows) <= 101 if ob.rows else True
+    # Wolfe conditions of every accepted step, from the observer's exact scalars (1-D: phi'(a) = g(x) * p)
+    is_strong = strong or (algo == "cg" and method == "PR")
+    f_prev = f(x0)
+    for k, (row, pk, gk) in enumerate(zip(ob.rows, ob.p, ob.g)):
+        _, a, fk, phid0, trials = row
+        if trials >= 40 or not (phid0 < 0.0) or abs(a * phid0) <= 1e-13 * abs(f_prev):
+            break                 # a safeguard exit (growth / zoom cap, collapsed bracket) or the rounding floor
+        assert fk <= f_prev + c1 * a * phid0
+        gp = float(gk[0] * pk[0])
+        assert (abs(gp) <= c2 * abs(phid0)) if is_strong else (gp >= -c2 * abs(phid0))
+        f_prev = fk
+
+
+def test_fast_property_cases_are_not_vacuous():
+    total = FAST_COUNTS["compared"] + FAST_COUNTS["skipped"]
+    assert total == 0 or FAST_COUNTS["compared"] >= 0.7 * total, FAST_COUNTS
