@@ -9,7 +9,8 @@ A "step" is one main-loop L-BFGS iteration = Before + line search + After of the
 m-1 pre-iterations (f90:442-510) always run first and are never timed.
 
   python bench.py [--gpus N --steps K --warmup W]         our arm (one JSON line on rank 0)
-  python bench.py --impl reference [...]                   the reference's CPU algorithm (oracle port)
+  python bench.py --impl reference [...]                   the reference's CPU algorithm (oracle port): one thread
+                                                           (its own semantics) and, as the line's value, all host cores
 
 Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
 Inputs are 2 GiB per vector (>> 126 MB L2), so no L2 flush is needed between iterations.
@@ -130,11 +131,38 @@ def cpu_lbfgs(n_sample, mem, warmup, steps, n_target, objective="rosenbrock"):
     its = last - first
     trials = sum(marks[i][1] for i in range(first + 1, last + 1))
     rate_sample = its / dt
-    return {"value": rate_sample * n_sample / n_target, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": (f"oracle/liboracle.so (gcc -O2 -ffp-contract=off, 1 thread) on n=2^{n_sample.bit_length() - 1}: "
+    threads = int(O.lib().orc_threads())
+    build = ("oracle/liboracle_omp.so (the same source with OpenMP-parallel loops and dots, gcc -O3 -march=native "
+             f"-fopenmp, {threads} threads: a GENEROUS baseline, the reference itself is serial)" if O.OMP_VARIANT else
+             "oracle/liboracle.so (gcc -O2 -ffp-contract=off, 1 thread = the reference's semantics)")
+    return {"value": rate_sample * n_sample / n_target, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"{build} on n=2^{n_sample.bit_length() - 1}: "
                        f"{its} main-loop iterations, {trials} trials, {dt:.2f} s = {rate_sample:.3f} it/s; scaled by "
                        f"n_sample/n (streaming)"),
             "sample_it_per_s": rate_sample, "sample_trials_per_iteration": trials / max(its, 1)}
+
+
+def cpu_lbfgs_all_cores(n_sample, mem, warmup, steps, n_target, objective="rosenbrock"):
+    """The generous CPU row of BASELINE.md section 3: the oracle's OpenMP build on every host core, in a subprocess
+    (the in-process oracle is the strict single-thread library).  None if that build is not possible here."""
+    env = dict(os.environ, FLGPU_ORACLE_VARIANT="omp")
+    env.pop("OMP_NUM_THREADS", None)           # torchrun sets it to 1; this row is about all the cores
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--cpu-log2n", str(n_sample.bit_length() - 1),
+           "--log2n", str(n_target.bit_length() - 1), "--mem", str(mem), "--warmup", str(warmup), "--steps", str(steps),
+           "--objective", objective]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        return json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else None
+    except (subprocess.SubprocessError, ValueError, IndexError):
+        return None
+
+
+def run_cpu_sample(args):
+    """bench.py --impl cpu-sample: one cpu_lbfgs() record as JSON (helper of cpu_lbfgs_all_cores)."""
+    n = 1 << args.log2n
+    print(json.dumps(cpu_lbfgs(1 << min(args.log2n, args.cpu_log2n), args.mem, args.warmup, args.steps, n,
+                               args.objective)), flush=True)
+    return 0
 
 
 def run_reference(args):
@@ -144,13 +172,18 @@ def run_reference(args):
     n = 1 << args.log2n
     n_sample = 1 << min(args.log2n, args.cpu_log2n)
     t0 = time.time()
-    cb = cpu_lbfgs(n_sample, args.mem, args.warmup, args.steps, n, args.objective)
+    # the reference's algorithm on ONE thread (its own semantics: it has no threading on this path) ...
+    single = cpu_lbfgs(n_sample, args.mem, args.warmup, args.steps, n, args.objective)
+    # ... and on all host cores (OpenMP build of the same port).  The line's value is the faster, all-cores one, so the
+    # driver's ours/reference ratio is the conservative reading; the single-thread sample is reported beside it.
+    cb = cpu_lbfgs_all_cores(n_sample, args.mem, args.warmup, args.steps, n, args.objective) or single
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload(n, args.mem, args.objective),
                        "timing": "host perf_counter around oracle iterations"},
-            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": cb, "single_thread": single,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
     return 0
@@ -355,9 +388,10 @@ def run_ours(args):
                    "from an untimed warm-up call (flgpu_set_workspace_cache); bytes/step = 8n/iterations (x crosses "
                    "PCIe once per call)"}
 
-    cpu = None
+    cpu = cpu_all = None
     if rank == 0 and world == 1 and not args.no_cpu and not diag:
         cpu = cpu_lbfgs(1 << min(args.log2n, args.cpu_log2n), mem, min(W, 3), min(K, 10), n)
+        cpu_all = cpu_lbfgs_all_cores(1 << min(args.log2n, args.cpu_log2n), mem, min(W, 3), min(K, 10), n)
 
     if rank == 0:
         line = {"metric": METRIC, "value": K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -376,6 +410,7 @@ def run_ours(args):
                                "off at this size (host-driven, one round trip per trial)")),
                            "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "cpu_baseline_all_cores": cpu_all,
                 "other_line_search_mode": other, "fast_line_search_policy": fast}
         print(json.dumps(line), flush=True)
     if comm is not None:
@@ -390,7 +425,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-sample"])
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="override the global dimension (debugging only)")
     ap.add_argument("--mem", type=int, default=MEM)
     ap.add_argument("--objective", default="rosenbrock", choices=["rosenbrock", "diag"],
@@ -410,6 +445,8 @@ def main():
         args.cpu_log2n = 23 if args.impl == "reference" else 22
     if args.warmup < 0 or args.steps < 1:
         raise SystemExit("need --steps >= 1 and --warmup >= 0")
+    if args.impl == "cpu-sample":
+        return run_cpu_sample(args)
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 

@@ -14,6 +14,9 @@
 
 #include <math.h>
 #include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 static int g_kind = ORC_OBJ_QUARTIC;
 static long long g_offset = 0, g_nglobal = 0;
@@ -97,38 +100,66 @@ void orc_obj_start(int start_kind, unsigned long long seed, double *x, long long
     }
 }
 
-static int eval(double *fx, double *g, const double *x, int n) {
+/* rows [lo, hi) of the current objective; lo is even (Rosenbrock pairs), hi == n closes an odd-length problem.
+ * The sequential build evaluates [0, n) in one call: the loops below are the whole of the reference-order arithmetic. */
+static double eval_range(int want_f, double *g, const double *x, long lo, long hi, long n) {
     facc_t f;
     facc_init(&f);
     if (g_kind == ORC_OBJ_QUARTIC) {
-        for (int i = 0; i < n; i++) {
+        for (long i = lo; i < hi; i++) {
             const double x2 = x[i] * x[i];
-            if (fx) facc_add(&f, x2 * x2);
+            if (want_f) facc_add(&f, x2 * x2);
             if (g) g[i] = 4.0 * (x2 * x[i]);
         }
     } else if (g_kind == ORC_OBJ_ROSENBROCK) {
         /* pairs (2j, 2j+1) in GLOBAL indexing; shards start on even offsets */
-        int i = 0;
-        for (; i + 1 < n; i += 2) {
+        long i = lo;
+        for (; i + 1 < hi; i += 2) {
             const double a = x[i], b = x[i + 1];
             const double t1 = b - a * a, t2 = 1.0 - a;
-            if (fx) facc_add(&f, (100.0 * t1) * t1 + t2 * t2);
+            if (want_f) facc_add(&f, (100.0 * t1) * t1 + t2 * t2);
             if (g) { g[i] = (-400.0 * a) * t1 - 2.0 * t2; g[i + 1] = 200.0 * t1; }
         }
-        if (i < n) { /* unpaired last element of an odd-length problem */
+        if (i < hi && hi == n) { /* unpaired last element of an odd-length problem */
             const double t2 = 1.0 - x[i];
-            if (fx) facc_add(&f, t2 * t2);
+            if (want_f) facc_add(&f, t2 * t2);
             if (g) g[i] = -2.0 * t2;
         }
     } else {
-        for (int i = 0; i < n; i++) {
+        for (long i = lo; i < hi; i++) {
             const double d = orc_diag_coeff(g_offset + i, g_nglobal);
             const double t = x[i] - 1.0;
-            if (fx) facc_add(&f, ((0.5 * d) * t) * t);
+            if (want_f) facc_add(&f, ((0.5 * d) * t) * t);
             if (g) g[i] = d * t;
         }
     }
-    if (fx) *fx = facc_value(&f);
+    return want_f ? facc_value(&f) : 0.0;
+}
+
+static int eval(double *fx, double *g, const double *x, int n) {
+#ifdef _OPENMP
+    /* liboracle_omp.so only (the generous CPU baseline of bench.py; never a checker): one even-aligned block per thread,
+     * partial sums added in thread order */
+    double part[256];
+    int nt_used = 1;
+    if (!g_tables) build_tables();
+#pragma omp parallel
+    {
+        int nt = omp_get_num_threads(), t = omp_get_thread_num();
+        if (nt > 256) nt = 256;
+        if (t < nt) {
+            const long chunk = ((long)n / nt) & ~1L;
+            const long lo = (long)t * chunk, hi = (t == nt - 1) ? (long)n : lo + chunk;
+            part[t] = eval_range(fx != 0, g, x, lo, hi, n);
+        }
+#pragma omp single
+        nt_used = nt;
+    }
+    if (fx) { double s = 0.0; for (int t = 0; t < nt_used; t++) s += part[t]; *fx = s; }
+#else
+    const double f = eval_range(fx != 0, g, x, 0, n, n);
+    if (fx) *fx = f;
+#endif
     return 0;
 }
 

@@ -19,6 +19,30 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* ------------------------------------------------------------------ OpenMP build (liboracle_omp.so ONLY)
+ * The reference runs this path on ONE thread (no OpenMP / MPI / BLAS: SURVEY.md F4) and so does liboracle.so, the
+ * checker: without -fopenmp the macros below are empty and this file is the strict sequential restatement, bit for
+ * bit what it was.  `make liboracle_omp.so` (-O3 -march=native -fopenmp) turns the element-wise loops and the dot
+ * products into parallel loops: a GENEROUS CPU baseline for bench.py, labelled as such.
+ * Its sums are reassociated, so it is never used as a checker. */
+#ifdef _OPENMP
+#include <omp.h>
+#define OMP_FOR _Pragma("omp parallel for schedule(static)")
+#define OMP_FOR_SUM_S _Pragma("omp parallel for schedule(static) reduction(+:s)")
+#else
+#define OMP_FOR
+#define OMP_FOR_SUM_S
+#endif
+
+/* threads the element-wise loops and dots run on: 1 for liboracle.so (the checker, = the reference) */
+int orc_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------ state */
 static orc_trace_t g_trace = NULL;
 static void *g_trace_user = NULL;
@@ -70,6 +94,7 @@ static double dot(const double *a, const double *b, int n) {
     }
     if (g_sum_mode == 2) return pairwise(a, NULL, b, n);
     double s = 0.0;
+    OMP_FOR_SUM_S
     for (int i = 0; i < n; i++) s += a[i] * b[i];
     return s;
 }
@@ -82,6 +107,7 @@ static double dot_diff_l(const double *a, const double *b, const double *c, int 
     }
     if (g_sum_mode == 2) return pairwise(a, b, c, n);
     double s = 0.0;
+    OMP_FOR_SUM_S
     for (int i = 0; i < n; i++) s += (a[i] - b[i]) * c[i];
     return s;
 }
@@ -94,9 +120,20 @@ static double dot_diff_r(const double *c, const double *a, const double *b, int 
     }
     if (g_sum_mode == 2) return pairwise(a, b, c, n);
     double s = 0.0;
+    OMP_FOR_SUM_S
     for (int i = 0; i < n; i++) s += c[i] * (a[i] - b[i]);
     return s;
 }
+/* array assignment a = b */
+static void vcopy(double *dst, const double *src, int n) {
+#ifdef _OPENMP
+    OMP_FOR
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+#else
+    memcpy(dst, src, sizeof(double) * (size_t)n);
+#endif
+}
+
 static double *valloc(long n) {
     double *v = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (!v) { fprintf(stderr, "oracle: out of memory\n"); abort(); }
@@ -115,6 +152,7 @@ typedef struct {
 /* x=x0+a*p (e.g. f90:1482): element-wise, multiply then add, no FMA */
 static void trial_x(ls_t *L) {
     const double a = *L->a;
+    OMP_FOR
     for (int i = 0; i < L->dim; i++) L->x[i] = L->x0[i] + a * L->p[i];
     g_st.n_trials++;
 }
@@ -167,7 +205,7 @@ static void wolfe_impl(double c1, double c2, orc_f_t f, orc_fd_t fd, double *x, 
     ls_t L;
     g_st.n_linesearch++;
     if (Increment) incrmt = fmax(1.0 + 1e-15, *Increment); else incrmt = 1.05; /* f90:1302-1303 */
-    memcpy(x0, x, sizeof(double) * (size_t)dim);                               /* f90:1304 */
+    vcopy(x0, x, dim);                               /* f90:1304 */
     L.c1 = c1; L.c2_m_abs_phid0 = c2 * fabs(phid0); L.fx0 = *fx; L.phid0 = phid0;
     L.f = f; L.fd = fd; L.f_fd = NULL; L.x = x; L.x0 = x0; L.p = p; L.fdx = fdx; L.a = a; L.fx = fx;
     L.dim = dim;
@@ -263,7 +301,7 @@ static void strongwolfe_impl(int fdwithf, double c1, double c2, orc_f_t f, orc_f
     ls_t L;
     g_st.n_linesearch++;
     if (Increment) incrmt = fmax(1.0 + 1e-15, *Increment); else incrmt = 1.05;  /* f90:1478-1479 */
-    memcpy(x0, x, sizeof(double) * (size_t)dim);                                /* f90:1480 */
+    vcopy(x0, x, dim);                                /* f90:1480 */
     L.c1 = c1; L.c2_m_abs_phid0 = c2 * fabs(phid0); L.fx0 = *fx; L.phid0 = phid0;
     L.f = f; L.fd = fd; L.f_fd = f_fd; L.x = x; L.x0 = x0; L.p = p; L.fdx = fdx; L.a = a; L.fx = fx;
     L.dim = dim;
@@ -400,7 +438,7 @@ static void fast_impl(int strong, double c1, double c2, orc_f_t f, orc_fd_t fd, 
     int grow;
     ls_t L;
     g_st.n_linesearch++;
-    memcpy(x0, x, sizeof(double) * (size_t)dim);
+    vcopy(x0, x, dim);
     L.c1 = c1; L.c2_m_abs_phid0 = c2 * fabs(phid0); L.fx0 = *fx; L.phid0 = phid0;
     L.f = f; L.fd = fd; L.f_fd = f_fd; L.x = x; L.x0 = x0; L.p = p; L.fdx = fdx; L.a = a; L.fx = fx;
     L.dim = dim;
@@ -469,11 +507,11 @@ void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, const int *Me
     if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }
     else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
     /* f90:442-446 */
-    for (i = 0; i < dim; i++) p[i] = -fdnew[i];
+    OMP_FOR for (i = 0; i < dim; i++) p[i] = -fdnew[i];
     phidnew = -dot(fdnew, fdnew, dim);
     if (-phidnew < tol) { g_st.status = 3; goto done; }
     if (fnew == 0.0) a = 1.0; else a = fabs(fnew) / sqrt(-phidnew);
-    memcpy(xold, x, sizeof(double) * (size_t)dim); memcpy(fdold, fdnew, sizeof(double) * (size_t)dim);
+    vcopy(xold, x, dim); vcopy(fdold, fdnew, dim);
     /* f90:448-460: never the _fdwithf variant here */
     tb = g_st.n_trials; phid0 = phidnew;
     line_search(sw, 0, c1, c2, f, fd, f_fd, x, &a, p, &fnew, phidnew, fdnew, dim, Increment);
@@ -490,26 +528,26 @@ void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, const int *Me
     }
     /* f90:470-471 */
     recent = 0;
-    for (i = 0; i < dim; i++) { S(0)[i] = x[i] - xold[i]; Y(0)[i] = fdnew[i] - fdold[i]; }
+    OMP_FOR for (i = 0; i < dim; i++) { S(0)[i] = x[i] - xold[i]; Y(0)[i] = fdnew[i] - fdold[i]; }
     rho[0] = 1.0 / dot(Y(0), S(0), dim);
     /* f90:472-510 pre-iterations */
     for (iIteration = 1; iIteration <= mem - 1; iIteration++) {
         int k;
-        memcpy(xold, x, sizeof(double) * (size_t)dim); memcpy(fdold, fdnew, sizeof(double) * (size_t)dim);
-        memcpy(p, fdnew, sizeof(double) * (size_t)dim);                               /* f90:475 */
+        vcopy(xold, x, dim); vcopy(fdold, fdnew, dim);
+        vcopy(p, fdnew, dim);                               /* f90:475 */
         for (i = recent; i >= 0; i--) {                                               /* f90:476-479 */
             alpha[i] = rho[i] * dot(S(i), p, dim);
-            for (k = 0; k < dim; k++) p[k] = p[k] - alpha[i] * Y(i)[k];
+            OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] - alpha[i] * Y(i)[k];
         }
         {   /* f90:480 p=p/rho(recent)/dot_product(y,y) */
             const double r = rho[recent], yy = dot(Y(recent), Y(recent), dim);
-            for (k = 0; k < dim; k++) p[k] = p[k] / r / yy;
+            OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] / r / yy;
         }
         for (i = 0; i <= recent; i++) {                                               /* f90:481-484 */
             phidnew = rho[i] * dot(Y(i), p, dim);
-            { const double c = alpha[i] - phidnew; for (k = 0; k < dim; k++) p[k] = p[k] + c * S(i)[k]; }
+            { const double c = alpha[i] - phidnew; OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] + c * S(i)[k]; }
         }
-        for (k = 0; k < dim; k++) p[k] = -p[k];
+        OMP_FOR for (k = 0; k < dim; k++) p[k] = -p[k];
         phidnew = dot(fdnew, p, dim); a = 1.0;                                        /* f90:485 */
         tb = g_st.n_trials; phid0 = phidnew;
         line_search(sw, 0, c1, c2, f, fd, f_fd, x, &a, p, &fnew, phidnew, fdnew, dim, Increment);
@@ -524,36 +562,36 @@ void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, const int *Me
             g_st.status = 1; goto done;
         }
         recent = recent + 1;                                                          /* f90:508-509 */
-        for (k = 0; k < dim; k++) { S(recent)[k] = x[k] - xold[k]; Y(recent)[k] = fdnew[k] - fdold[k]; }
+        OMP_FOR for (k = 0; k < dim; k++) { S(recent)[k] = x[k] - xold[k]; Y(recent)[k] = fdnew[k] - fdold[k]; }
         rho[recent] = 1.0 / dot(Y(recent), S(recent), dim);
     }
     /* f90:511-579 main loop */
     for (iIteration = 1; iIteration <= maxit; iIteration++) {
         int k;
         /* Before() f90:586-608 */
-        memcpy(xold, x, sizeof(double) * (size_t)dim); memcpy(fdold, fdnew, sizeof(double) * (size_t)dim);
-        memcpy(p, fdnew, sizeof(double) * (size_t)dim);
+        vcopy(xold, x, dim); vcopy(fdold, fdnew, dim);
+        vcopy(p, fdnew, dim);
         for (i = recent; i >= 0; i--) {
             alpha[i] = rho[i] * dot(S(i), p, dim);
-            for (k = 0; k < dim; k++) p[k] = p[k] - alpha[i] * Y(i)[k];
+            OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] - alpha[i] * Y(i)[k];
         }
         for (i = mem - 1; i >= recent + 1; i--) {
             alpha[i] = rho[i] * dot(S(i), p, dim);
-            for (k = 0; k < dim; k++) p[k] = p[k] - alpha[i] * Y(i)[k];
+            OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] - alpha[i] * Y(i)[k];
         }
         {
             const double r = rho[recent], yy = dot(Y(recent), Y(recent), dim);        /* f90:598 */
-            for (k = 0; k < dim; k++) p[k] = p[k] / r / yy;
+            OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] / r / yy;
         }
         for (i = recent + 1; i <= mem - 1; i++) {
             phidnew = rho[i] * dot(Y(i), p, dim);
-            { const double c = alpha[i] - phidnew; for (k = 0; k < dim; k++) p[k] = p[k] + c * S(i)[k]; }
+            { const double c = alpha[i] - phidnew; OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] + c * S(i)[k]; }
         }
         for (i = 0; i <= recent; i++) {
             phidnew = rho[i] * dot(Y(i), p, dim);
-            { const double c = alpha[i] - phidnew; for (k = 0; k < dim; k++) p[k] = p[k] + c * S(i)[k]; }
+            { const double c = alpha[i] - phidnew; OMP_FOR for (k = 0; k < dim; k++) p[k] = p[k] + c * S(i)[k]; }
         }
-        for (k = 0; k < dim; k++) p[k] = -p[k];
+        OMP_FOR for (k = 0; k < dim; k++) p[k] = -p[k];
         phidnew = dot(fdnew, p, dim); a = 1.0;                                        /* f90:607 */
         /* line search: _fdwithf iff f_fd present */
         tb = g_st.n_trials; phid0 = phidnew;
@@ -570,7 +608,7 @@ void orc_lbfgs(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, const int *Me
             g_st.status = 1; goto done;
         }
         recent = (recent + 1) % mem;
-        for (k = 0; k < dim; k++) { S(recent)[k] = x[k] - xold[k]; Y(recent)[k] = fdnew[k] - fdold[k]; }
+        OMP_FOR for (k = 0; k < dim; k++) { S(recent)[k] = x[k] - xold[k]; Y(recent)[k] = fdnew[k] - fdold[k]; }
         rho[recent] = 1.0 / dot(Y(recent), S(recent), dim);
     }
     g_st.status = 2;
@@ -604,10 +642,10 @@ static int cg_after(int is_pr, int warn, double tol, double minstep, int dim, do
     }
     if (is_pr) beta = dot_diff_r(fdnew, fdnew, fdold, dim) / dot(fdold, fdold, dim);  /* f90:387 */
     else beta = dot(fdnew, fdnew, dim) / dot_diff_l(fdnew, fdold, p, dim);            /* f90:366 */
-    for (k = 0; k < dim; k++) p[k] = -fdnew[k] + beta * p[k];
+    OMP_FOR for (k = 0; k < dim; k++) p[k] = -fdnew[k] + beta * p[k];
     *phidnew = dot(fdnew, p, dim);
     if (*phidnew > 0.0) {                                                             /* f90:368-370 */
-        for (k = 0; k < dim; k++) p[k] = -fdnew[k];
+        OMP_FOR for (k = 0; k < dim; k++) p[k] = -fdnew[k];
         *phidnew = -dot(fdnew, fdnew, dim);
     }
     *a = *a * phidold / *phidnew;                                                     /* f90:371 */
@@ -626,7 +664,7 @@ static void cg_core(orc_f_t f, orc_fd_t fd, orc_ffd_t f_fd, double *x, int dim, 
     ORC_ARM_BUDGET(done);
     if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }                    /* f90:230-234 */
     else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
-    for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:236 */
+    OMP_FOR for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:236 */
     phidnew = -dot(fdnew, fdnew, dim);
     if (-phidnew < tol) { g_st.status = 3; goto done; }
     if (fnew == 0.0) a = 1.0; else a = fabs(fnew) / sqrt(-phidnew);
@@ -639,7 +677,7 @@ static void cg_core(orc_f_t f, orc_fd_t fd, orc_ffd_t f_fd, double *x, int dim, 
     for (iIteration = 1; iIteration <= maxit; iIteration++) {
         const int strong = is_pr ? 1 : sw; /* PR always strong Wolfe, f90:311-344 */
         double phid0;
-        fold = fnew; memcpy(fdold, fdnew, sizeof(double) * (size_t)dim); phidold = phidnew;
+        fold = fnew; vcopy(fdold, fdnew, dim); phidold = phidnew;
         tb = g_st.n_trials; phid0 = phidnew;
         line_search(strong, f_fd != NULL, c1, c2, f, fd, f_fd, x, &a, p, &fnew, phidnew, fdnew, dim, Increment);
         trace(outer++, dim, p, x, fdnew, a, fnew, phid0, tb);
@@ -717,13 +755,13 @@ void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, orc
     ORC_ARM_BUDGET(done);
     if (f_fd) { (void)f_fd(&fnew, fdnew, x, &dim); g_st.n_ffd++; }                    /* f90:86-90 */
     else { f(&fnew, x, &dim); g_st.n_f++; fd(fdnew, x, &dim); g_st.n_fd++; }
-    for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:92 */
+    OMP_FOR for (i = 0; i < dim; i++) p[i] = -fdnew[i];                                       /* f90:92 */
     phidnew = -dot(fdnew, fdnew, dim);
     if (-phidnew < tol) { g_st.status = 3; goto done; }
     if (fnew == 0.0) a = 1.0; else a = fabs(fnew) / sqrt(-phidnew);                   /* f90:94-95 */
     for (iIteration = 1; iIteration <= maxit; iIteration++) {
         double phid0;
-        fold = fnew; memcpy(fdold, fdnew, sizeof(double) * (size_t)dim); phidold = phidnew;
+        fold = fnew; vcopy(fdold, fdnew, dim); phidold = phidnew;
         tb = g_st.n_trials; phid0 = phidnew;
         line_search(sw, f_fd != NULL, c1, c2, f, fd, f_fd, x, &a, p, &fnew, phidnew, fdnew, dim, Increment);
         trace(outer++, dim, p, x, fdnew, a, fnew, phid0, tb);
@@ -737,7 +775,7 @@ void orc_steepestdescent(orc_f_t f, orc_fd_t fd, double *x, const int *dim_, orc
             }
             g_st.status = 1; goto done;
         }
-        for (i = 0; i < dim; i++) p[i] = -fdnew[i];
+        OMP_FOR for (i = 0; i < dim; i++) p[i] = -fdnew[i];
         phidnew = -dot(fdnew, fdnew, dim);
         a = a * phidold / phidnew;
     }

@@ -52,6 +52,9 @@ typedef struct {
     int status;             /* 0 converged(g), 1 step converged, 2 max iteration, 3 initial g small */
 } orc_stats_t;
 
+/* 1 for liboracle.so (sequential, as the reference); the host's thread count for liboracle_omp.so, the separately
+ * built generous CPU baseline of bench.py, which is never used as a checker */
+int orc_threads(void);
 void orc_set_trace(orc_trace_t cb, void *user);
 /* 0 = sequential double (reference semantics), 1 = long double accumulate,
  * 2 = pairwise double.  Modes 1/2 exist only to bound summation noise. */

@@ -226,3 +226,36 @@ def test_summation_noise_is_above_1e12():
                                          MaxIteration=15)
     assert max(env[:20]) > 1e-12
     assert env[1] < 1e-12     # ... while the first direction after the steepest-descent step agrees
+
+
+def test_openmp_build_is_a_baseline_not_a_checker():
+    """oracle/liboracle_omp.so (bench.py's generous all-cores CPU row) is the same source with
+    parallel loops: it must solve the same problem (same trial counts early on, same minimiser) -- and the library the
+    tests check against must be the strict single-thread one."""
+    import json
+    import os
+    import subprocess
+    import sys
+    assert O.lib().orc_threads() == 1 and not O.OMP_VARIANT
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "import numpy as np, _oracle as O, _cases\n"
+            "n = 5000\n"
+            "tr = O.Trace(keep_vectors=False)\n"
+            "x, st = O.lbfgs(O.builtin_callbacks(O.OBJ_ROSENBROCK, 0, n), _cases.start('rosenR0', n), use_ffd=True,\n"
+            "                Warning=False, trace=tr)\n"
+            "print(json.dumps({'threads': int(O.lib().orc_threads()), 'iters': int(st.n_iter), 'status': int(st.status),\n"
+            "                  'trials': [r[4] for r in tr.rows[:6]], 'err': float(np.abs(x - 1.0).max())}))\n"
+            % os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, FLGPU_ORACLE_VARIANT="omp", OMP_NUM_THREADS="4"))
+    if r.returncode != 0 and "make" in r.stderr:
+        pytest.skip("no OpenMP-capable compiler here: " + r.stderr.strip().splitlines()[-1])
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    n = 5000
+    tr = O.Trace(keep_vectors=False)
+    x, st = O.lbfgs(O.builtin_callbacks(O.OBJ_ROSENBROCK, 0, n), _cases.start("rosenR0", n), use_ffd=True, Warning=False,
+                    trace=tr)
+    assert got["threads"] == 4
+    assert got["trials"] == [r_[4] for r_ in tr.rows[:6]]
+    assert got["err"] < 1e-8 and abs(got["iters"] - st.n_iter) <= max(2, 0.1 * st.n_iter)
