@@ -237,7 +237,19 @@ def run_ours(args):
         ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         mark = {}
 
+        per = mark["per"] = []          # one event per iteration boundary inside the window (median)
+
+        def stamp(i):
+            try:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(torch.cuda.ExternalStream(i.stream))
+                per.append(e)
+            except Exception:           # the per-iteration figures are a by-product: never let them break the metric
+                mark["per"] = None
+
         def on_iter(i):
+            if first < i.iteration < last and mark["per"] is not None:
+                stamp(i)
             if i.iteration == first or i.iteration == last:
                 s = torch.cuda.ExternalStream(i.stream)
                 if i.iteration == first:
@@ -247,7 +259,11 @@ def run_ours(args):
                     if time_kernels:
                         fl.lib().flgpu_reset_kernel_times()
                     ev[0].record(s)
+                    if mark["per"] is not None:
+                        stamp(i)
                 else:
+                    if mark["per"] is not None:
+                        stamp(i)
                     ev[1].record(s)
                     barrier()
                     mark["t1"] = time.time()
@@ -261,6 +277,11 @@ def run_ours(args):
             raise SystemExit(f"bench.py: optimizer stopped after {st.iterations} iterations (status {st.status}) "
                              f"before {last + 1}; lower --steps")
         ms = ev[0].elapsed_time(ev[1])
+        try:
+            evs = mark.get("per") or []
+            mark["iter_ms"] = sorted(evs[k].elapsed_time(evs[k + 1]) for k in range(len(evs) - 1))
+        except Exception:
+            mark["iter_ms"] = []
         x.free()
         return ms, mark, st, fl.kernel_times() if time_kernels else None
 
@@ -280,6 +301,10 @@ def run_ours(args):
     ms_max = float(t.item())
     launches = (mark["c1"][0] - mark["c0"][0]) + (mark["c1"][1] - mark["c0"][1])   # library kernels + objective kernels
     trials = mark["c1"][2] - mark["c0"][2]
+    it_ms = mark.get("iter_ms") or []
+    per_iteration = ({"median_ms": it_ms[len(it_ms) // 2], "min_ms": it_ms[0], "max_ms": it_ms[-1], "n": len(it_ms),
+                      "note": "this rank's CUDA-event time between consecutive accepted steps inside the timed window "
+                              "(iterations differ by their trial counts)"} if it_ms else None)
 
     # ---- pass 2: per-kernel CUDA-event times over the same timed region -> roofline of the dominant kernel
     ms2, mark2, st2, kt = timed_run(True, fused)
@@ -408,7 +433,9 @@ def run_ours(args):
                            "device_resident_search": (f"{args.device_search}: " + (
                                "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
                                "off at this size (host-driven, one round trip per trial)")),
-                           "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
+                           "trials_in_timed_region": trials, "trials_per_iteration": trials / K,
+                           "trials_per_sec": trials / (ms_max * 1e-3)},
+                "per_iteration": per_iteration,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "cpu_baseline_all_cores": cpu_all,
                 "other_line_search_mode": other, "fast_line_search_policy": fast}
