@@ -128,5 +128,11 @@ inline void AugmentedLagrangian(f_t f, fd_t fd, f_fd_t f_fd, fdd_t fdd, c_t c, c
         WolfeConst1, WolfeConst2, Increment, (int)UnconstrainedSolver.size(), (int)Method.size());
 }
 
+// Line-search policy of later calls on this thread (an extension: the reference signatures have no room for it).
+// false (default) = the reference's Wolfe / StrongWolfe searchers, trial for trial; true = FLGPU_LS_FAST, which accepts
+// the first trial satisfying the Wolfe conditions (include/flgpu.h; not a reference routine, Increment unused).
+extern "C" void flgpu_set_line_search(int policy);
+inline void FastLineSearch(const bool & on) { flgpu_set_line_search(on ? 1 : 0); }
+
 } }
 #endif
