@@ -330,6 +330,81 @@ def test_fast_nan_objective_terminates():
     assert abs(x[0]) < 1e-7 and st.n_trials < 400
 
 
+# ----------------------------------------------------------------------------- known-answer vectors (CPU)
+import glob            # noqa: E402
+import json            # noqa: E402
+import os              # noqa: E402
+
+GOLDEN_FAST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_fast")
+GOLDEN_FAST_NAMES = sorted(os.path.splitext(os.path.basename(q))[0] for q in glob.glob(os.path.join(GOLDEN_FAST, "*.json")))
+# runs that end in a long tail of rounding-noise steps: only the early iterations and the exit status are compared
+GOLDEN_FAST_TAIL = {"fast_lbfgs_rosenR1_64_m5_c2_01", "fast_lbfgs_diag_60_m30", "fast_cg_dy_rosenR1_64", "fast_sd_quartic10",
+                    # CG creeps into the quartic's flat bottom (|x| ~ 1e-6 at exit): the last iterates move by 1e-6 under
+                    # summation-order noise, 1e-7 of |x0|
+                    "fast_cg_pr_quartic_200"}
+
+
+def _load_golden_fast(name):
+    with open(os.path.join(GOLDEN_FAST, name + ".json")) as fh:
+        d = json.load(fh)
+    d["x0"] = np.array([float.fromhex(v) for v in d["x0"]])
+    d["x_final"] = np.array([float.fromhex(v) for v in d["x_final"]])
+    d["rows"] = [(r[0], float.fromhex(r[1]), float.fromhex(r[2]), float.fromhex(r[3]), r[4]) for r in d["rows"]]
+    d["p_first"] = [np.array([float.fromhex(v) for v in q]) for q in d["p_first"]]
+    return d
+
+
+def test_golden_fast_vectors_exist():
+    assert len(GOLDEN_FAST_NAMES) >= 9
+
+
+@pytest.mark.parametrize("name", GOLDEN_FAST_NAMES)
+def test_fast_oracle_reproduces_golden_bitwise(name):
+    """tests/golden_fast/*.json (made by make_golden_fast.py): the oracle's fast-policy restatement must reproduce every
+    stored bit -- regression protection for the algorithm itself."""
+    d = _load_golden_fast(name)
+    kw = dict(d["options"])
+    use = kw.pop("use_ffd", False)
+    kind = _cases.OBJECTIVES[d["objective"]][0]
+    assert np.array_equal(_cases.start(d["objective"], d["n"]), d["x0"])
+    tr = O.Trace()
+    with O.fast_line_search():
+        x, st = RUNS[d["algorithm"]][1](O.builtin_callbacks(kind, 0, d["n"]), d["x0"].copy(), use_ffd=use, Warning=False,
+                                        trace=tr, **kw)
+    assert np.array_equal(x, d["x_final"])
+    assert (st.n_iter, st.status, st.n_f, st.n_fd, st.n_ffd, st.n_trials) == \
+        (d["iterations"], d["status"], d["n_f"], d["n_fd"], d["n_ffd"], d["n_trials"])
+    assert [tuple(r) for r in tr.rows] == d["rows"]
+    for q, gq in zip(tr.p, d["p_first"]):
+        assert np.array_equal(q, gq)
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
+@pytest.mark.parametrize("name", GOLDEN_FAST_NAMES)
+def test_fast_host_control_flow_lands_on_golden(name, fused):
+    """driver.cpp + SearchCore::fast over the host simulator from the stored starts: same trial counts and (to 1e-9) the
+    same steps over the first 8 iterations, same exit status; minimiser to 1e-8 and iteration count to 2 % where the
+    stored run does not end in a rounding-noise tail (the criteria tests/test_golden.py applies to the reference policy)."""
+    d = _load_golden_fast(name)
+    kw = dict(d["options"])
+    use = kw.pop("use_ffd", False)
+    kind = _cases.OBJECTIVES[d["objective"]][0]
+    ob = H.Observer(keep_vectors=False)
+    x, st = RUNS[d["algorithm"]][0](kind, d["x0"], observer=ob, use_ffd=use, Warning=False, n_global=d["n"], fused=fused,
+                                    line_search="fast", **kw)
+    assert st.status == d["status"]
+    for k in range(min(8, len(ob.rows), len(d["rows"]))):
+        (_, a, f, phid0, trials), (_, ga, gf, gphid0, gtrials) = ob.rows[k], d["rows"][k]
+        assert trials == gtrials, f"{name}: iteration {k} took {trials} trials, stored {gtrials}"
+        assert abs(a - ga) <= 1e-9 * abs(ga) and abs(f - gf) <= 1e-9 * abs(gf) + 1e-300
+        assert abs(phid0 - gphid0) <= 1e-8 * abs(gphid0)
+    if name in GOLDEN_FAST_TAIL:
+        return
+    scale = max(np.linalg.norm(d["x_final"]), np.linalg.norm(d["x0"]))
+    assert np.linalg.norm(x - d["x_final"]) <= 1e-8 * scale
+    assert abs(st.iterations - d["iterations"]) <= max(1, 0.02 * d["iterations"])
+
+
 # ============================================================================= GPU half (libflgpu.so, -m gpu)
 @pytest.fixture(scope="module")
 def fl():
