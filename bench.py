@@ -318,7 +318,7 @@ def run_ours(args):
     # ---- pass 4: the optional FLGPU_LS_FAST policy (NOT the reference's searcher: iterates differ, so this is a
     # separate record and never the headline)
     fast = None
-    if args.line_search == "reference":
+    if args.line_search == "reference" and world == 1:   # 1 GPU only: the policy has not been run on row shards yet
         ms4, mark4, _, _ = timed_run(False, fused, "fast")
         t4 = torch.tensor([ms4], dtype=torch.float64, device="cuda")
         if dist is not None:
