@@ -1,10 +1,15 @@
 #!/usr/bin/env python
-"""profiles/sweep.py -- BASELINE.json configs[2] and [4] on the GPUs visible to this process (1 GPU, or N under
-torchrun): n = 2^26..2^28 (per-GPU rows under torchrun: weak scaling) x {LBFGS m=5,10,30 on Rosenbrock /
-diag-quadratic, CG-DY and CG-PR on the quartic, SteepestDescent}, K timed iterations each after the warm-up
-iterations, per-kernel CUDA-event totals -> achieved GB/s over the algorithmic bytes.
+"""profiles/sweep.py -- BASELINE.json configs[2] and [4]: n = 2^26..2^28 (GLOBAL n; under torchrun the rows are
+sharded over the ranks: strong scaling, raise --max-log2n for the weak-scaling cells) x {LBFGS m=5,10,30 on
+Rosenbrock / diag-quadratic, CG-DY and CG-PR on the quartic, SteepestDescent}, K timed iterations each after the
+warm-up iterations, per-kernel CUDA-event totals of rank 0 -> achieved GB/s per GPU over the algorithmic bytes
+(DESIGN.md section 3).
 
-    python profiles/sweep.py [--out gpurun_out/sweep.md] [--max-log2n 28]
+    python profiles/sweep.py [--out gpurun_out/sweep.md] [--max-log2n 28] [--line-search fast]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 profiles/sweep.py ...
+
+The single-GPU path is the one the round-1 tables were made with; the torchrun path (row shards through the same
+communicator set-up as bench.py) was written without a GPU at hand and has not been run yet.
 """
 import argparse
 import os
@@ -18,9 +23,39 @@ import fortran_library_b200 as fl  # noqa: E402
 PEAK = 6467.7
 
 
+RANK = int(os.environ.get("RANK", "0"))
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+COMM = None          # row-shard communicator under torchrun
+
+
+def setup_comm():
+    """One process per GPU; the 128-byte communicator id travels over torch.distributed (as in bench.py)."""
+    global COMM
+    if WORLD == 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def bcast(data):
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if RANK == 0:
+            t.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+    COMM = fl.comm_create(RANK, WORLD, bcast)
+    return dist
+
+
 def one(algo, kind, start, seed, n, K, W, **kw):
-    x = fl.DeviceVector.start(start, n, seed=seed)
+    lo = (n * RANK // WORLD) // 2 * 2            # even boundaries: Rosenbrock pairs never straddle shards
+    hi = n if RANK == WORLD - 1 else (n * (RANK + 1) // WORLD) // 2 * 2
+    x = fl.DeviceVector.start(start, hi - lo, seed=seed, offset=lo, n_global=n)
     kw = dict(kw)
+    if COMM is not None:
+        kw.update(comm=COMM, offset=lo, n_global=n)
     mem = kw.get("Memory", 0)
     first = (mem if algo == "lbfgs" else 1) + W - 1
     last = first + K
@@ -61,6 +96,7 @@ def main():
     ap.add_argument("--skip", default="", help="comma-separated substrings of case labels to leave out")
     a = ap.parse_args()
     fl.require_gpu()
+    dist = setup_comm()
     rows = []
     cases = [("LBFGS m=5 Rosenbrock", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=5)),
              ("LBFGS m=10 Rosenbrock", "lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10)),
@@ -81,15 +117,22 @@ def main():
                 kw = dict(kw, line_search=a.line_search)
                 label += f", line_search={a.line_search}"
             mem = kw.get("Memory", 0)
-            if (2 * mem + 6) * 8 * n > 170e9:
+            if (2 * mem + 6) * 8 * n / WORLD > 170e9:
                 continue
             r = one(algo, kind, start, seed, n, a.steps, a.warmup, **kw)
+            if RANK != 0:
+                continue
             if r is None:
                 print(f"2^{log2n} {label}: converged before the timed window", flush=True)
                 continue
             rows.append((log2n, label, r))
             print(f"2^{log2n} {label:48.48s} {r['it_per_s']:8.2f} it/s  {r['trials_per_it']:5.1f} trials/it  "
                   f"{r['GB_per_it']:7.1f} GB/it  {r['GBps']:7.0f} GB/s ({r['frac']:.0%} of measured)", flush=True)
+    if dist is not None:
+        fl.lib().flgpu_comm_destroy(COMM)
+        dist.destroy_process_group()
+    if RANK != 0:
+        return
     with open(a.out, "w") as fh:
         fh.write("| n | workload | it/s (wall) | trials/it | algorithmic GB/it | kernel ms/it | achieved GB/s | of measured 6467.7 |\n")
         fh.write("|---|---|---:|---:|---:|---:|---:|---:|\n")
