@@ -165,6 +165,13 @@ class Observer:
         return stop
 
 
+def set_line_search(policy):
+    """Line-search policy of later Fortran-ABI calls (`__nonlinearoptimization_MOD_*`) on this thread: "reference"
+    (default), "fast" (FLGPU_LS_FAST, not a reference routine) or None = let FLGPU_LINE_SEARCH decide."""
+    code = {None: -1, "reference": LS_REFERENCE, "fast": LS_FAST}.get(policy, policy)
+    lib().flgpu_set_line_search(int(code))
+
+
 def default_options(for_cg=False):
     o = capi.Options()
     lib().flgpu_options_default(C.byref(o), int(for_cg))

@@ -330,6 +330,28 @@ def test_fast_nan_objective_terminates():
     assert abs(x[0]) < 1e-7 and st.n_trials < 400
 
 
+def test_fast_edge_cases():
+    """Start at the minimiser, tiny dimensions, Memory = 1 and more pairs than dimensions: same exits as the reference
+    policy (f90:443 / 237 initial test) and agreement with the oracle's fast-policy run."""
+    for fn in (H.lbfgs, H.cg, H.sd):
+        x, st = fn(O.OBJ_ROSENBROCK, np.ones(10), Warning=False, n_global=10, line_search="fast")
+        assert st.status == capi.INITIAL_CONVERGED and st.iterations == 0 and np.array_equal(x, np.ones(10))
+    for n in (1, 2, 3, 7):
+        x0 = _cases.start("quartic", n)
+        with O.fast_line_search():
+            xa, sa = O.lbfgs(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Memory=4, Warning=False, MaxIteration=5)
+        xb, stb = H.lbfgs(O.OBJ_QUARTIC, x0, Memory=4, Warning=False, MaxIteration=5, n_global=n, use_ffd=False,
+                          line_search="fast")
+        assert stb.iterations == sa.n_iter and _cases.rel(xb, xa) < 1e-6
+    n = 400
+    x0 = _cases.start("rosenR1", n)
+    with O.fast_line_search():
+        xa, sa = O.lbfgs(O.builtin_callbacks(O.OBJ_ROSENBROCK, 0, n), x0.copy(), Memory=1, use_ffd=True, Warning=False,
+                         MaxIteration=25)
+    xb, stb = H.lbfgs(O.OBJ_ROSENBROCK, x0, Memory=1, Warning=False, MaxIteration=25, n_global=n, line_search="fast")
+    assert stb.iterations == sa.n_iter and stb.n_trials == sa.n_trials and _cases.rel(xb, xa) < 1e-9
+
+
 # ----------------------------------------------------------------------------- known-answer vectors (CPU)
 import glob            # noqa: E402
 import json            # noqa: E402
