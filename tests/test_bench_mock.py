@@ -1,7 +1,6 @@
 """bench.py's own control flow (window marking, the four passes, the e2e calls, the CPU rows, the JSON line) executed on
 a machine without a GPU, against stand-ins for `torch.cuda` and for the package: a Python error in bench.py would
 otherwise only show at round end on the GPU box.  Nothing here measures anything; the numbers are fake by design."""
-import ctypes as C
 import importlib
 import io
 import json
