@@ -50,7 +50,7 @@ def test_start_vectors_bit_exact(fl, name, n):
 
 
 @pytest.mark.parametrize("name", ["quartic", "rosenR1", "diag"])
-@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537])
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537, 1 << 22, (1 << 22) + 3])   # the last two: full grid, unrolled trips, tail
 def test_objective_kernels_vs_oracle(fl, name, n):
     """K6: f' bit-exact (same operation order, no FMA), f to summation-order accuracy."""
     kind = _cases.OBJECTIVES[name][0]
@@ -62,8 +62,9 @@ def test_objective_kernels_vs_oracle(fl, name, n):
     prob = fl.builtin_problem(kind)
     xd, gd, fd_ = fl.DeviceVector.from_numpy(x), fl.DeviceVector(n), fl.DeviceVector(2)
     ctx = fl.capi.EvalCtx(None, None, 0, n, 0, 1, 0)
+    zeros = np.zeros(n)                     # kept alive: a temporary would be unmapped before the copy reads it
     for which in ("f_fd", "f", "fd"):
-        fl.lib().flgpu_memcpy(gd.ptr, np.zeros(n).ctypes.data, n * 8, 1, 0, None)
+        fl.lib().flgpu_memcpy(gd.ptr, zeros.ctypes.data, n * 8, 1, 0, None)
         if which == "f_fd":
             C.cast(prob.f_fd, fl.capi.F_FD_FN)(C.byref(ctx), fd_.ptr, gd.ptr, xd.ptr, n)
         elif which == "f":
@@ -77,7 +78,7 @@ def test_objective_kernels_vs_oracle(fl, name, n):
 
 
 @pytest.mark.parametrize("name", ["quartic", "rosenR1", "diag"])
-@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537])
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 65537, 1 << 22, (1 << 22) + 3])
 def test_fused_evaluation_vs_plain_callbacks(fl, name, n):
     """flgpu_fused_fn of the built-in objectives: the point it forms equals flgpu_vec_trial bit for bit,
     f and f' equal the plain callbacks' bit for bit (same mapping, same order), f'.p to dot accuracy."""
@@ -98,7 +99,8 @@ def test_fused_evaluation_vs_plain_callbacks(fl, name, n):
     W = fl.capi
     for flags in (W.WANT_F | W.WANT_GP, W.WANT_F, W.WANT_GP, W.WRITE_X | W.WRITE_G, W.WRITE_G, W.WRITE_X,
                   W.WANT_F | W.WANT_GP | W.WRITE_X | W.WRITE_G):
-        fl.lib().flgpu_memcpy(sc.ptr, np.full(4, np.nan).ctypes.data, 32, 1, 0, None)
+        nans = np.full(4, np.nan)
+        fl.lib().flgpu_memcpy(sc.ptr, nans.ctypes.data, 32, 1, 0, None)
         fused(C.byref(ctx), flags, sc.ptr, sc.ptr + 8, xo.ptr, go.ptr, x0d.ptr, pd.ptr, a, n)
         out = sc.numpy()
         if flags & W.WANT_F:
@@ -112,7 +114,7 @@ def test_fused_evaluation_vs_plain_callbacks(fl, name, n):
             assert np.array_equal(go.numpy(), g_plain)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100003, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 257, 100003, 1 << 20, 1 << 22, (1 << 22) + 3])
 def test_vector_primitives(fl, n):
     rng = np.random.default_rng(n)
     a, b = rng.standard_normal(n), rng.standard_normal(n)
@@ -130,6 +132,11 @@ def test_vector_primitives(fl, n):
     for _ in range(3):
         fl.lib().flgpu_vec_dot(ad.ptr, bd.ptr, n, out.ptr, None)
         assert out.numpy()[0] == first
+    # integer-valued data: every partial sum is exact, so ANY summation order must give the exact dot, bit for bit
+    ai, bi = rng.integers(-30, 31, n), rng.integers(-30, 31, n)
+    aid, bid = fl.DeviceVector.from_numpy(ai.astype(np.float64)), fl.DeviceVector.from_numpy(bi.astype(np.float64))
+    fl.lib().flgpu_vec_dot(aid.ptr, bid.ptr, n, out.ptr, None)
+    assert out.numpy()[0] == float(int(np.dot(ai, bi)))
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 255, 257, 4097, 100003])
