@@ -109,7 +109,7 @@ thread_local flgpu_al_stats tls_al{};
 // ---- built-in constraint: unit sphere (test.f90:692-705)
 void sphere_c(const flgpu_eval_ctx *ctx, double *c_dev, const double *x, int m, int64_t n) {
     (void)m;
-    flgpu_vec_dot(x, x, n, c_dev, ctx->stream);                        // partial sum of x.x
+    flgpu_vec_dot_sharded(x, x, n, ctx->n_global, c_dev, ctx->stream);   // this rank's root of x.x
     if (ctx->rank == 0) k::add_scalar_kernel<<<1, 1, 0, (cudaStream_t)ctx->stream>>>(c_dev, -1.0);
 }
 __global__ void __launch_bounds__(k::kThreads) scale2_kernel(double *out, const double *x, int64_t n) {

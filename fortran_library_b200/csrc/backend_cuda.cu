@@ -237,6 +237,10 @@ extern "C" flgpu_comm *flgpu_comm_create(const void *id128, int rank, int nranks
     flgpu::UniqueId id;
     std::memcpy(&id, id128, 128);
     flgpu::nccl_check(flgpu::nccl().CommInitRank(&c->nccl_comm, nranks, id, rank), "ncclCommInitRank");
+    if (const char *ts = std::getenv("FLGPU_EXCHANGE_TIMEOUT_S")) {      // e.g. under a debugger or a slow host callback
+        const double sec = std::atof(ts);
+        if (sec > 0.0) c->timeout_ns = (unsigned long long)(sec * 1e9);
+    }
     flgpu::setup_p2p(c);
     return c;
 }
@@ -295,8 +299,10 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
     Rglob = (double *)dalloc(NSLOTS * sizeof(double));
     Dsum = (double *)dalloc(nd_of(k::kMaxMem) * sizeof(double));
     Rsearch = (double *)dalloc(FLGPU_SEARCH_RESULT_DOUBLES * sizeof(double));
-    work.partials = (double *)dalloc((size_t)k::kMaxGrid * nd_of(k::kMaxMem) * sizeof(double));
-    work.ticket = (unsigned int *)dalloc(64);
+    // reduction geometry: chunk size from the GLOBAL dimension (flgpu_reduce.cuh), one partial per chunk and accumulator
+    ch = red::chunk_elems(ctx.n_global);
+    nchunks = red::num_chunks(n, ch);
+    alloc_work(8);
     FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, (NSLOTS + 16) * sizeof(double)));
     std::memset(host_pinned, 0, (NSLOTS + 16) * sizeof(double));
     const char *sync_mode = std::getenv("FLGPU_SYNC");
@@ -310,6 +316,32 @@ CudaBackend::~CudaBackend() {
     for (auto &pe : pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : event_pool) cudaEventDestroy(e);
     if (own_stream) { scratch_release(stream); cudaStreamDestroy(stream); }
+}
+
+// rows of chunk sums (one per accumulator of the widest kernel), block values and tickets of the tree kernel
+void CudaBackend::alloc_work(int rows) {
+    if (rows <= work_rows) return;
+    auto dalloc = [&](size_t bytes) {
+        void *p = ws_alloc(bytes);
+        FLGPU_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream));
+        owned.emplace_back(p, bytes);
+        return p;
+    };
+    work.stride = nchunks;
+    work.partials = (double *)dalloc((size_t)rows * (size_t)nchunks * sizeof(double));
+    work.blockvals = (double *)dalloc((size_t)rows * red::kTopMax * sizeof(double));
+    work.tickets = (unsigned int *)dalloc((size_t)rows * sizeof(unsigned int));
+    work_rows = rows;
+}
+
+// chunk sums of rows [0, nrows) -> this rank's roots at out[row] (nrows <= 8)
+void CudaBackend::tree(int nrows, double *const *out) {
+    k::TreeArgs a;
+    a.w = work; a.nchunks = nchunks; a.lin_out = nullptr; a.dup_row = -1; a.dup_out = nullptr;
+    for (int i = 0; i < 8; i++) a.out[i] = i < nrows ? out[i] : nullptr;
+    const int nblk = (int)((nchunks + red::kBlockChunks - 1) / red::kBlockChunks);
+    k::tree_kernel<<<dim3(nblk, nrows), k::kThreads, 0, stream>>>(a);
+    launches++;
 }
 
 double *CudaBackend::vec_alloc() {
@@ -328,6 +360,7 @@ void CudaBackend::lbfgs_alloc(int m) {
         std::abort();
     }
     mem = m;
+    alloc_work(nd_of(m));
     auto dalloc = [&](size_t bytes) {
         void *p = nullptr;
         const double t0 = now_ms();
@@ -366,14 +399,20 @@ void CudaBackend::download(double *user_x, const double *src, int x_space) {
     resolve_times();
 }
 
-// ---- launch geometry: a multiple of the SM count, bounded by the work and the partial buffers
-int CudaBackend::grid_for(int64_t units, int tpb, int blocks_per_sm) const {
-    int64_t need = (units + tpb - 1) / tpb;
-    if (need < 1) need = 1;
+// ---- launch geometry: one full wave of resident CTAs (a multiple of the SM count), never more blocks than chunks
+int CudaBackend::grid_for(int blocks_per_sm) const {
+    int64_t g = (int64_t)num_sms * blocks_per_sm;
+    if (g > k::kMaxGrid) g = k::kMaxGrid;
+    if (nchunks < g) g = nchunks;
+    return (int)(g < 1 ? 1 : g);
+}
+// element-wise kernels without a reduction: plain grid-stride over 16-byte units
+int CudaBackend::grid_units(int64_t units, int blocks_per_sm) const {
+    int64_t need = (units + k::kThreads - 1) / k::kThreads;
     int64_t g = (int64_t)num_sms * blocks_per_sm;
     if (g > k::kMaxGrid) g = k::kMaxGrid;
     if (need < g) g = need;
-    return (int)g;
+    return (int)(g < 1 ? 1 : g);
 }
 
 // ---- timing
@@ -451,6 +490,7 @@ void CudaBackend::device_search(int policy, bool strong, bool fdwithf, double c1
     A.c1 = c1; A.c2abs = c2abs; A.fx0 = fx0; A.phid0 = phid0; A.incr = incr; A.a = a;
     A.strong = strong ? 1 : 0; A.fdwithf = fdwithf ? 1 : 0;
     A.policy = policy;
+    A.no_store = 0;
     A.result_dev = Rsearch;
     A.comm = ctx.nranks > 1 ? comm : nullptr;
     const int t = time_begin("callback:device_search", 0.0);   // bytes depend on the trial count: see flgpu_stats
@@ -468,19 +508,21 @@ void CudaBackend::search_result(double *out) {
 // ---- primitives
 void CudaBackend::trial_x(double *x, const double *x0, const double *p, double a) {
     const int t = time_begin("trial_x", 24.0 * n);
-    k::trial_kernel<<<grid_for(n / 8 + 1, k::kThreads, 8), k::kThreads, 0, stream>>>(x, x0, p, a, n);
+    k::trial_kernel<<<grid_units(n / 8 + 1, 8), k::kThreads, 0, stream>>>(x, x0, p, a, n);
     time_end(t);
     launches++;
 }
 void CudaBackend::dot(const double *a, const double *b, int slot) {
-    const int t = time_begin("dot", 16.0 * n);
-    k::dot_kernel<<<grid_for(n / 8 + 1, k::kThreads, 8), k::kThreads, 0, stream>>>(a, b, n, work, R, slot);
-    time_end(t);
+    const int t = time_begin("dot", (a == b ? 8.0 : 16.0) * n);
+    k::dot_kernel<<<grid_for(8), k::kThreads, 0, stream>>>(a, b, n, ch, work, 0);
     launches++;
+    double *out[1] = {R + slot};
+    tree(1, out);
+    time_end(t);
 }
 void CudaBackend::neg(double *p, const double *g) {
     const int t = time_begin("neg", 16.0 * n);
-    k::neg_kernel<<<grid_for(n / 2 + 1, k::kThreads, 8), k::kThreads, 0, stream>>>(p, g, n);
+    k::neg_kernel<<<grid_units(n / 2 + 1, 8), k::kThreads, 0, stream>>>(p, g, n);
     time_end(t);
     launches++;
 }
@@ -488,58 +530,79 @@ void CudaBackend::neg(double *p, const double *g) {
 // ---- L-BFGS
 int g_k1_shape[2] = {0, 0};
 namespace {
-// grid = SMs x CTAs actually resident for this instantiation (one full wave), capped by the work
-template <int MT, int NG>
-void launch_k1(const k::K1Args &a, int num_sms, int64_t units, cudaStream_t s) {
-    static int resident = 0;
+// per-device launch facts (a process may drive several GPUs: never cache these per process)
+struct DeviceFacts { int k1_resident[8] = {0}; bool k2_attr = false; int k3_tma_attr[2] = {0, 0}; int k3_mode = -1; };
+DeviceFacts &facts(int device) {
+    static std::mutex mu;
+    static std::map<int, DeviceFacts> m;
+    std::lock_guard<std::mutex> lock(mu);
+    return m[device];
+}
+// grid = SMs x CTAs actually resident for this instantiation (one full wave), capped by the number of chunks
+template <int MT, int NG, class Src>
+void launch_k1(const k::K1Args &a, const Src &src, int device, int shape_id, int num_sms, int64_t nchunks, cudaStream_t s) {
+    int &resident = facts(device).k1_resident[shape_id];
     if (!resident) {
-        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::k1_update_dots_kernel<MT, NG>,
+        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::k1_update_dots_kernel<MT, NG, Src>,
                                                                        k::kThreads, 0));
         if (resident < 1) resident = 1;
     }
-    constexpr int TX = k::kThreads / NG;
-    int64_t need = (units + TX - 1) / TX;
     int64_t grid = (int64_t)num_sms * resident;
     if (grid > k::kMaxGrid) grid = k::kMaxGrid;
-    if (need < grid) grid = need < 1 ? 1 : need;
-    k::k1_update_dots_kernel<MT, NG><<<(int)grid, k::kThreads, 0, s>>>(a);
+    if (nchunks < grid) grid = nchunks < 1 ? 1 : nchunks;
+    k::k1_update_dots_kernel<MT, NG, Src><<<(int)grid, k::kThreads, 0, s>>>(a, src);
 }
 }  // namespace
+
+// K1 shape for `rem` older columns still to be covered: (columns per group, groups per warp)
+void k1_shape_for(int rem, int &mt, int &ng) {
+    if (g_k1_shape[0] > 0) { mt = g_k1_shape[0]; ng = g_k1_shape[1]; }   // tuning override (flgpu_debug_set_k1_shape)
+    else if (rem <= 2)  { mt = 2; ng = 1; }
+    else if (rem <= 4)  { mt = 4; ng = 1; }
+    else if (rem <= 5)  { mt = 5; ng = 1; }
+    else if (rem <= 8)  { mt = 4; ng = 2; }
+    else                { mt = 5; ng = 2; }   // 10 columns per pass; m = 30 takes 3 passes
+    // Measured on B200 (profiles/r01_k1_shapes.md): shapes with 4 or 8 groups per warp (128 / 64-byte
+    // column runs) or more than 5 columns per thread (> 128 registers, 1 CTA/SM) run at 2.6-5.6 TB/s;
+    // <5,2> (256-byte runs, 2 CTAs/SM) sustains 6.3-7.0 TB/s even counting the re-read of x, g per pass.
+}
 
 void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const double *g1,
                                     const double *g0, int new_slot, int k_after) {
     const int nother = k_after - 1;
     // algorithmic bytes: one ideal pass (the g1, g0 re-reads of extra passes at m > 11 are overhead, not credit)
     const int t = time_begin("k1_update_dots", 8.0 * n * (2.0 * nother + 6.0));
-    k::K1Args a;
-    a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.S = S; a.Y = Y; a.ld = ld; a.n = n;
-    a.m = mem; a.new_slot = new_slot; a.k_after = k_after; a.w = work; a.R = R;
+    k::K1Args a{};
+    a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.S = S; a.Y = Y; a.ld = ld; a.n = n; a.ch = ch;
+    a.m = mem; a.new_slot = new_slot; a.k_after = k_after; a.w = work;
     int age = 1;
     bool first = true;
     // one pass covers NG*MT older columns
     do {
         a.age_base = age;
         a.write_new = first ? 1 : 0;
-        const int rem = nother - (age - 1);
         int mt, ng;
-        if (g_k1_shape[0] > 0) { mt = g_k1_shape[0]; ng = g_k1_shape[1]; }   // tuning override (flgpu_debug_set_k1_shape)
-        else if (rem <= 2)  { mt = 2; ng = 1; }
-        else if (rem <= 4)  { mt = 4; ng = 1; }
-        else if (rem <= 5)  { mt = 5; ng = 1; }
-        else if (rem <= 8)  { mt = 4; ng = 2; }
-        else                { mt = 5; ng = 2; }   // 10 columns per pass; m = 30 takes 3 passes
-        // Measured on B200 (profiles/r01_k1_shapes.md): shapes with 4 or 8 groups per warp (128 / 64-byte
-        // column runs) or more than 5 columns per thread (> 128 registers, 1 CTA/SM) run at 2.6-5.6 TB/s;
-        // <5,2> (256-byte runs, 2 CTAs/SM) sustains 6.3-7.0 TB/s even counting the re-read of x, g per pass.
-#define FLGPU_K1_CASE(MT, NG) if (mt == MT && ng == NG) launch_k1<MT, NG>(a, num_sms, n / 2 + 1, stream); else
-        FLGPU_K1_CASE(2, 1) FLGPU_K1_CASE(4, 1) FLGPU_K1_CASE(5, 1) FLGPU_K1_CASE(4, 2) FLGPU_K1_CASE(5, 2)
+        k1_shape_for(nother - (age - 1), mt, ng);
+#define FLGPU_K1_CASE(MT, NG, ID) if (mt == MT && ng == NG) launch_k1<MT, NG, k::PlainSrc>(a, k::PlainSrc(), device, ID, num_sms, nchunks, stream); else
+        FLGPU_K1_CASE(2, 1, 0) FLGPU_K1_CASE(4, 1, 1) FLGPU_K1_CASE(5, 1, 2) FLGPU_K1_CASE(4, 2, 3) FLGPU_K1_CASE(5, 2, 4)
         fatal("K1: unsupported (columns per group, groups) shape");
 #undef FLGPU_K1_CASE
         launches++;
         age += mt * ng;
         first = false;
     } while (age - 1 < nother);
+    lbfgs_dots_tree();
     time_end(t);
+}
+
+// chunk sums of all nd dots -> R[kResSlots + d]; g.g also to its result slot
+void CudaBackend::lbfgs_dots_tree() {
+    k::TreeArgs a;
+    a.w = work; a.nchunks = nchunks; a.lin_out = R + k::kResSlots; a.dup_row = d_GG(mem); a.dup_out = R + SL_GG;
+    for (int i = 0; i < 8; i++) a.out[i] = nullptr;
+    const int nblk = (int)((nchunks + red::kBlockChunks - 1) / red::kBlockChunks);
+    k::tree_kernel<<<dim3(nblk, nd_of(mem)), k::kThreads, 0, stream>>>(a);
+    launches++;
 }
 
 void CudaBackend::lbfgs_solve(int kk, int recent) {
@@ -553,10 +616,10 @@ void CudaBackend::lbfgs_solve(int kk, int recent) {
     const int t = time_begin("k2_solve", 0.0);
     const size_t smem = (size_t)(nd + 2 * mem * mem) * sizeof(double);
     if (smem > 48 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
+        DeviceFacts &f = facts(device);
+        if (!f.k2_attr) {
             FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k2_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            attr_set = true;
+            f.k2_attr = true;
         }
     }
     k::k2_solve_kernel<<<1, 32, smem, stream>>>(mem, kk, recent, Dall, 1, SY, YY, C);
@@ -568,29 +631,51 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
                                   int recent) {
     const int t = time_begin("k3_direction", 8.0 * n * (2.0 * kk + (xt ? 4.0 : 2.0)));
     k::K3Args a;
-    a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n;
-    a.m = mem; a.k = kk; a.recent = recent; a.w = work; a.R = R;
-    k::k3_direction_kernel<8><<<grid_for(n / 2 + 1, k::kThreads, 2), k::kThreads, 0, stream>>>(a);
-    time_end(t);
+    a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n; a.ch = ch;
+    a.m = mem; a.k = kk; a.recent = recent; a.w = work;
+    DeviceFacts &f = facts(device);
+    if (f.k3_mode < 0) {                  // FLGPU_K3 = regs | tma (default) | tma4 (4 pieces x 6 stages)
+        const char *v = std::getenv("FLGPU_K3");
+        f.k3_mode = (v && !std::strcmp(v, "regs")) ? 0 : (v && !std::strcmp(v, "tma4")) ? 2 : 1;
+    }
+    if (f.k3_mode == 0) {
+        k::k3_direction_kernel<8><<<grid_for(2), k::kThreads, 0, stream>>>(a);
+    } else {
+        constexpr size_t smem = 3 * 8 * k::kThreads * sizeof(double2);       // 96 KB ring: 2 CTAs per SM
+        int &attr = f.k3_tma_attr[f.k3_mode - 1];
+        if (f.k3_mode == 1) {
+            if (!attr) { FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = 1; }
+            k::k3_direction_tma_kernel<8, 3><<<grid_for(2), k::kThreads + 32, smem, stream>>>(a);
+        } else {
+            if (!attr) { FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = 1; }
+            k::k3_direction_tma_kernel<4, 6><<<grid_for(2), k::kThreads + 32, smem, stream>>>(a);
+        }
+    }
     launches++;
+    double *out[2] = {R + SL_GP0, R + SL_PP};
+    tree(2, out);
+    time_end(t);
 }
 
 // ---- CG
 void CudaBackend::cg_dots(const double *g1, const double *g0, const double *p) {
     const int t = time_begin("cg_dots", 24.0 * n);
-    k::cg_dots_kernel<<<grid_for(n / 4 + 1, k::kThreads, 6), k::kThreads, 0, stream>>>(g1, g0, p, n, work, R);
-    time_end(t);
+    k::cg_dots_kernel<<<grid_for(6), k::kThreads, 0, stream>>>(g1, g0, p, n, ch, work);
     launches++;
+    double *out[5] = {R + SL_GG, R + SL_PP, R + SL_DGP, R + SL_GDG, R + SL_G0G0};
+    tree(5, out);
+    time_end(t);
 }
 void CudaBackend::cg_update(double *p, const double *g1, double beta) {
     const int t = time_begin("cg_update", 24.0 * n);
-    k::cg_update_kernel<<<grid_for(n / 4 + 1, k::kThreads, 6), k::kThreads, 0, stream>>>(p, g1, beta, n, work, R);
-    time_end(t);
+    k::cg_update_kernel<<<grid_for(6), k::kThreads, 0, stream>>>(p, g1, beta, n, ch, work);
     launches++;
+    double *out[1] = {R + SL_GP0};
+    tree(1, out);
+    time_end(t);
 }
 
-// ---- ranks: out[i] = sum_r src_r[i] in rank order, identical bits on every rank
-// out[i] = sum_r src_r[i] in rank order (identical bits on every rank).  One kernel over peer memory, or the
+// ---- ranks: out[i] = rank tree (red::rank_tree) of src_r[i]: identical bits on every rank.  One kernel over peer memory, or the
 // ncclAllGather + combine fallback (gather: [G][count] device scratch).  host_out (optional, peer-memory path
 // only): pinned host array that receives the sums followed by the flag word host_seq_next; returns whether it did.
 bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, double *out, double *gather,
@@ -598,7 +683,7 @@ bool rank_sum(flgpu_comm *c, cudaStream_t s, const double *src, int count, doubl
     if (count > k::kMailWidth) fatal("rank_sum: more values than one mailbox slot holds");
     if (c->p2p) {
         k::exchange_kernel<<<1, k::kMailWidth, 0, s>>>(c->peers, c->rank, c->nranks, ++c->seq, src, count, out, host_out,
-                                                      host_seq_next, extra);
+                                                      host_seq_next, extra, c->timeout_ns);
         return host_out != nullptr;
     }
     nccl_allgather_f64(c, src, gather, (size_t)count, s);

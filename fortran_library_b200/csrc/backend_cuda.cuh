@@ -25,6 +25,7 @@ struct flgpu_comm {
     flgpu::k::PeerTable peers{};        // host-driven exchanges (exchange_kernel); seq = last sequence number used
     flgpu::k::PeerTable peers_search{}; // exchanges made inside a device-resident line search; counter local->dseq
     unsigned long long seq = 0;
+    unsigned long long timeout_ns = 20000000000ull;   // a peer silent for this long is reported and the exchange traps
 };
 
 namespace flgpu {
@@ -99,6 +100,7 @@ public:
     double *S = nullptr, *Y = nullptr, *SY = nullptr, *YY = nullptr, *C = nullptr;
     int mem = 0;
     int64_t ld = 0;
+    int64_t ch = 1024, nchunks = 1;   // reduction geometry (flgpu_reduce.cuh): chunk elements, local chunks
     double *R = nullptr;          // [NSLOTS + nd] device results
     cudaStream_t stream = nullptr;
     std::vector<KernelTime> times;
@@ -127,7 +129,12 @@ private:
     struct Pending { int idx; cudaEvent_t a, b; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
-    int grid_for(int64_t units, int threads_per_block, int blocks_per_sm) const;
+    int grid_for(int blocks_per_sm) const;                       // reducing kernels: <= one block per chunk
+    int grid_units(int64_t units, int blocks_per_sm) const;      // element-wise kernels
+    void alloc_work(int rows);
+    void tree(int nrows, double *const *out);                    // chunk sums of rows [0, nrows) -> out[row]
+    void lbfgs_dots_tree();
+    int work_rows = 0;
     int time_begin(const char *name, double bytes);
     void time_end(int token);
     cudaEvent_t get_event();

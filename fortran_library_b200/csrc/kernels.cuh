@@ -1,12 +1,13 @@
 // kernels.cuh -- hand-written fp64 CUDA kernels (sm_100a) of the L-BFGS / CG hot path.
 //
-// Every kernel is a streaming pass bounded by HBM bandwidth (<= 0.25 flop/B): no tensor cores,
-// no shared-memory tiling of the data (each element is used once), 128-bit coalesced accesses,
-// grid = a multiple of the SM count, grid-stride loops with several independent 16-byte loads
-// in flight per thread.  Reductions are deterministic: per-thread accumulation in a fixed
-// element order, xor-butterfly warp shuffles, a fixed-order sum over warps in shared memory,
-// one partial per block in global memory, and a fixed-order final sum performed by the last
-// block to finish (ticket counter) -- the value never depends on which block that is.
+// Every kernel is a streaming pass bounded by HBM bandwidth (<= 0.25 flop/B): no tensor cores, 128-bit coalesced
+// accesses, grid = a multiple of the SM count, several independent 16-byte loads in flight per thread (K3 stages its
+// columns through a shared-memory ring filled by bulk async copies instead, see there).
+//
+// Reductions are deterministic AND partition-independent (include/flgpu_reduce.cuh): the vector is cut into chunks of
+// CH = chunk_elems(n_global) elements; a thread block sums one chunk at a time in a fixed order and stores the chunk's
+// sums; tree_kernel combines the chunk sums by the aligned binary tree over the chunk index and delivers the rank's
+// root; ranks are combined by the same tree over the rank index.  Which block sums which chunk never matters.
 //
 // Element-wise results that the reference defines with separate multiply and add roundings
 // (x0+a*p f90:1482, p-alpha*y f90:592, -g+beta*p f90:366) use __dmul_rn/__dadd_rn so they do
@@ -15,21 +16,24 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/flgpu_reduce.cuh"
 #include "backend.hpp"
 #include "lbfgs_gram.hpp"
 
 namespace flgpu {
 namespace k {
 
-constexpr int kThreads = 256;
-constexpr int kMaxGrid = 148 * 8;     // partial buffers are sized for this many blocks
+constexpr int kThreads = red::kThreads;
+constexpr int kMaxGrid = 148 * 8;     // largest grid any streaming kernel is launched with
 constexpr int kMaxMem = 64;           // largest LBFGS Memory supported by K1/K2/K3
 constexpr int kResSlots = NSLOTS;     // R[0..16) = slots, R[16..) = K1 dots
 
-// Reduction workspace shared by all library kernels of one backend (stream-ordered use).
+// Reduction workspace shared by all library kernels of one backend / stream (stream-ordered use).
 struct Work {
-    double *partials;        // [kMaxGrid][stride]
-    unsigned int *ticket;    // zero between kernels
+    double *partials;        // [rows][stride]: chunk sums, one row per accumulator
+    int64_t stride;          // chunk capacity of a row
+    double *blockvals;       // [rows][red::kTopMax]: roots of 4096-chunk blocks (rows with more than 4096 chunks)
+    unsigned int *tickets;   // [rows], zero between kernels
 };
 
 __device__ __forceinline__ double2 ld2(const double *p, int64_t u) {
@@ -38,88 +42,54 @@ __device__ __forceinline__ double2 ld2(const double *p, int64_t u) {
 __device__ __forceinline__ void st2(double *p, int64_t u, double2 v) {
     reinterpret_cast<double2 *>(p)[u] = v;   // cache-streaming stores (__stcs) measured: no difference (profiles/r01_store_policy.md)
 }
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
-// butterfly over aligned segments of SEG lanes (SEG = 32: the whole warp)
-template <int SEG>
-__device__ __forceinline__ double seg_sum(double v) {
-#pragma unroll
-    for (int o = SEG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+// Chunk geometry of a streaming kernel: chunk c covers the 16-byte units [c*cu, min(nu, (c+1)*cu)); the odd last
+// element of an odd-length shard belongs to the last chunk and is added by its thread 0 after that thread's units.
+struct Chunks {
+    int64_t nu, cu, nchunks;
+    bool odd;
+    __device__ Chunks(int64_t n, int64_t ch) : nu(n >> 1), cu(ch >> 1), nchunks(red::num_chunks(n, ch)), odd(n & 1) {}
+    __device__ int64_t lo(int64_t c) const { return c * cu; }
+    __device__ int64_t hi(int64_t c) const { const int64_t h = (c + 1) * cu; return h < nu ? h : nu; }
+    __device__ bool tail_here(int64_t c) const { return odd && c == nchunks - 1; }
+};
 
-// Block-level reduction of NACC per-thread accumulators followed by the grid-level finish.
-// dest[i] = index into R receiving accumulator i.  All kThreads threads must call this.
-template <int NACC>
-__device__ __forceinline__ void reduce_finish(double (&acc)[NACC], const int (&dest)[NACC], Work w,
-                                              double *R) {
-    __shared__ double sh[NACC][kThreads / 32];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-        const double v = warp_sum(acc[i]);
-        if (lane == 0) sh[i][warp] = v;
+// ------------------------------------------------------------------ tree: chunk sums -> this rank's root
+// grid (blocks of 4096 chunks, rows).  Row r of the partials is reduced to one value which goes to out[r] (rows <= 8),
+// or to lin_out[r] (K1's dots); one row may be delivered to a second place (K1: g.g is also a result slot).
+struct TreeArgs {
+    Work w;
+    int64_t nchunks;
+    double *out[8];
+    double *lin_out;
+    int dup_row;
+    double *dup_out;
+};
+static __global__ void __launch_bounds__(kThreads) tree_kernel(TreeArgs a) {
+    __shared__ double sh[red::kWarps];
+    __shared__ bool last;
+    const int row = blockIdx.y, b = blockIdx.x, nblk = gridDim.x;
+    const int64_t lo = (int64_t)b * red::kBlockChunks;
+    const int64_t rem = a.nchunks - lo;
+    double r = red::cta_tree(a.w.partials + (int64_t)row * a.w.stride + lo,
+                             (int)(rem < red::kBlockChunks ? rem : red::kBlockChunks), sh);
+    if (nblk > 1) {
+        if (threadIdx.x == 0) {
+            a.w.blockvals[row * red::kTopMax + b] = r;
+            __threadfence();
+            last = atomicAdd(&a.w.tickets[row], 1u) == (unsigned)nblk - 1;
+        }
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+        r = red::top_tree<true>(a.w.blockvals + row * red::kTopMax, nblk);
+        if (threadIdx.x == 0) a.w.tickets[row] = 0u;
     }
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
-        w.partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
+    if (threadIdx.x == 0) {
+        double *dst = a.lin_out ? a.lin_out + row : a.out[row];
+        if (dst) *dst = r;
+        if (row == a.dup_row && a.dup_out) *a.dup_out = r;
     }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(w.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // final: warp q handles accumulators q, q+8, ...; lanes stride over blocks, then butterfly
-    for (int i = warp; i < NACC; i += kThreads / 32) {
-        double s = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&w.partials[(size_t)b * NACC + i]);
-        s = warp_sum(s);
-        if (lane == 0) R[dest[i]] = s;
-    }
-    if (threadIdx.x == 0) *w.ticket = 0u;
-}
-
-// Same reduction with one output pointer per accumulator (objective kernels: f and f'.p go to
-// caller-supplied device scalars).
-template <int NACC>
-__device__ __forceinline__ void reduce_finish_to(double (&acc)[NACC], double *(&out)[NACC], Work w) {
-    __shared__ double sh[NACC][kThreads / 32];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-        const double v = warp_sum(acc[i]);
-        if (lane == 0) sh[i][warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
-        w.partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(w.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (warp < NACC) {
-        double s = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&w.partials[(size_t)b * NACC + warp]);
-        s = warp_sum(s);
-        if (lane == 0) *out[warp] = s;
-    }
-    if (threadIdx.x == 0) *w.ticket = 0u;
 }
 
 // ------------------------------------------------------------------ K4a: x = x0 + a*p (f90:1482)
@@ -155,108 +125,139 @@ static __global__ void __launch_bounds__(kThreads) neg_kernel(double *__restrict
 }
 
 // ------------------------------------------------------------------ K4b: dot_product(a,b) (f90:1485)
+// chunk sums of a.b go to row `row` of the partials
 static __global__ void __launch_bounds__(kThreads) dot_kernel(const double *__restrict__ a, const double *__restrict__ b,
-                                                       int64_t n, Work w, double *R, int dest) {
-    const int64_t nu = n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (; u + 3 * stride < nu; u += 4 * stride) {
-        double2 a0 = ld2(a, u), a1 = ld2(a, u + stride), a2 = ld2(a, u + 2 * stride), a3 = ld2(a, u + 3 * stride);
-        double2 b0 = ld2(b, u), b1 = ld2(b, u + stride), b2 = ld2(b, u + 2 * stride), b3 = ld2(b, u + 3 * stride);
-        s0 = fma(a0.y, b0.y, fma(a0.x, b0.x, s0));
-        s1 = fma(a1.y, b1.y, fma(a1.x, b1.x, s1));
-        s2 = fma(a2.y, b2.y, fma(a2.x, b2.x, s2));
-        s3 = fma(a3.y, b3.y, fma(a3.x, b3.x, s3));
+                                                       int64_t n, int64_t ch, Work w, int row) {
+    const Chunks C(n, ch);
+    double *part = w.partials + (int64_t)row * w.stride;
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+        const int64_t hi = C.hi(c);
+        double s = 0.0;
+        int64_t u = C.lo(c) + threadIdx.x;
+        for (; u + 3 * kThreads < hi; u += 4 * kThreads) {      // four units per trip, all loads issued first
+            double2 a0 = ld2(a, u), a1 = ld2(a, u + kThreads), a2 = ld2(a, u + 2 * kThreads), a3 = ld2(a, u + 3 * kThreads);
+            double2 b0 = ld2(b, u), b1 = ld2(b, u + kThreads), b2 = ld2(b, u + 2 * kThreads), b3 = ld2(b, u + 3 * kThreads);
+            s = fma(a0.y, b0.y, fma(a0.x, b0.x, s));
+            s = fma(a1.y, b1.y, fma(a1.x, b1.x, s));
+            s = fma(a2.y, b2.y, fma(a2.x, b2.x, s));
+            s = fma(a3.y, b3.y, fma(a3.x, b3.x, s));
+        }
+        for (; u < hi; u += kThreads) {
+            double2 a0 = ld2(a, u), b0 = ld2(b, u);
+            s = fma(a0.y, b0.y, fma(a0.x, b0.x, s));
+        }
+        if (C.tail_here(c) && threadIdx.x == 0) s = fma(a[n - 1], b[n - 1], s);
+        const double acc[1] = {s};
+        red::chunk_flush<1>(acc, parity, part, w.stride, c);
     }
-    for (; u < nu; u += stride) {
-        double2 a0 = ld2(a, u), b0 = ld2(b, u);
-        s0 = fma(a0.y, b0.y, fma(a0.x, b0.x, s0));
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) s0 = fma(a[n - 1], b[n - 1], s0);
-    double acc[1] = {(s0 + s1) + (s2 + s3)};
-    const int d[1] = {dest};
-    reduce_finish<1>(acc, d, w, R);
 }
 
 // ------------------------------------------------------------------ K5a: CG dots (f90:354-366, 375-387)
-// one pass over f'new, f'old, p:  g.g, p.p, (g-gold).p, g.(g-gold), gold.gold
+// one pass over f'new, f'old, p:  g.g, p.p, (g-gold).p, g.(g-gold), gold.gold  -> rows 0..4
 static __global__ void __launch_bounds__(kThreads) cg_dots_kernel(const double *__restrict__ g1, const double *__restrict__ g0,
-                                                           const double *__restrict__ p, int64_t n, Work w, double *R) {
-    const int64_t nu = n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    auto term = [&](double a, double b, double c) {
-        const double d = a - b;                 // fdnew-fdold, rounded as in the reference
-        acc[0] = fma(a, a, acc[0]);
-        acc[1] = fma(c, c, acc[1]);
-        acc[2] = fma(d, c, acc[2]);
-        acc[3] = fma(a, d, acc[3]);
-        acc[4] = fma(b, b, acc[4]);
-    };
-    int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    for (; u + stride < nu; u += 2 * stride) {
-        double2 a0 = ld2(g1, u), a1 = ld2(g1, u + stride);
-        double2 b0 = ld2(g0, u), b1 = ld2(g0, u + stride);
-        double2 c0 = ld2(p, u), c1 = ld2(p, u + stride);
-        term(a0.x, b0.x, c0.x); term(a0.y, b0.y, c0.y);
-        term(a1.x, b1.x, c1.x); term(a1.y, b1.y, c1.y);
+                                                           const double *__restrict__ p, int64_t n, int64_t ch, Work w) {
+    const Chunks C(n, ch);
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+        const int64_t hi = C.hi(c);
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        auto term = [&](double a, double b, double q) {
+            const double d = a - b;                 // fdnew-fdold, rounded as in the reference
+            acc[0] = fma(a, a, acc[0]);
+            acc[1] = fma(q, q, acc[1]);
+            acc[2] = fma(d, q, acc[2]);
+            acc[3] = fma(a, d, acc[3]);
+            acc[4] = fma(b, b, acc[4]);
+        };
+        int64_t u = C.lo(c) + threadIdx.x;
+        for (; u + kThreads < hi; u += 2 * kThreads) {
+            double2 a0 = ld2(g1, u), a1 = ld2(g1, u + kThreads);
+            double2 b0 = ld2(g0, u), b1 = ld2(g0, u + kThreads);
+            double2 c0 = ld2(p, u), c1 = ld2(p, u + kThreads);
+            term(a0.x, b0.x, c0.x); term(a0.y, b0.y, c0.y);
+            term(a1.x, b1.x, c1.x); term(a1.y, b1.y, c1.y);
+        }
+        for (; u < hi; u += kThreads) {
+            double2 a0 = ld2(g1, u), b0 = ld2(g0, u), c0 = ld2(p, u);
+            term(a0.x, b0.x, c0.x); term(a0.y, b0.y, c0.y);
+        }
+        if (C.tail_here(c) && threadIdx.x == 0) term(g1[n - 1], g0[n - 1], p[n - 1]);
+        red::chunk_flush<5>(acc, parity, w.partials, w.stride, c);
     }
-    for (; u < nu; u += stride) {
-        double2 a0 = ld2(g1, u), b0 = ld2(g0, u), c0 = ld2(p, u);
-        term(a0.x, b0.x, c0.x); term(a0.y, b0.y, c0.y);
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) term(g1[n - 1], g0[n - 1], p[n - 1]);
-    const int d[5] = {SL_GG, SL_PP, SL_DGP, SL_GDG, SL_G0G0};
-    reduce_finish<5>(acc, d, w, R);
 }
 
-// ------------------------------------------------------------------ K5b: p = -g + beta*p; g.p (f90:366-367)
+// ------------------------------------------------------------------ K5b: p = -g + beta*p; g.p (f90:366-367) -> row 0
 static __global__ void __launch_bounds__(kThreads) cg_update_kernel(double *__restrict__ p, const double *__restrict__ g1,
-                                                             double beta, int64_t n, Work w, double *R) {
-    const int64_t nu = n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    double acc[1] = {0.0};
-    int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    for (; u + stride < nu; u += 2 * stride) {
-        double2 a0 = ld2(g1, u), a1 = ld2(g1, u + stride);
-        double2 c0 = reinterpret_cast<const double2 *>(p)[u], c1 = reinterpret_cast<const double2 *>(p)[u + stride];
-        c0.x = __dadd_rn(-a0.x, __dmul_rn(beta, c0.x)); c0.y = __dadd_rn(-a0.y, __dmul_rn(beta, c0.y));
-        c1.x = __dadd_rn(-a1.x, __dmul_rn(beta, c1.x)); c1.y = __dadd_rn(-a1.y, __dmul_rn(beta, c1.y));
-        st2(p, u, c0); st2(p, u + stride, c1);
-        acc[0] = fma(a0.y, c0.y, fma(a0.x, c0.x, acc[0]));
-        acc[0] = fma(a1.y, c1.y, fma(a1.x, c1.x, acc[0]));
+                                                             double beta, int64_t n, int64_t ch, Work w) {
+    const Chunks C(n, ch);
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+        const int64_t hi = C.hi(c);
+        double acc[1] = {0.0};
+        int64_t u = C.lo(c) + threadIdx.x;
+        for (; u + kThreads < hi; u += 2 * kThreads) {
+            double2 a0 = ld2(g1, u), a1 = ld2(g1, u + kThreads);
+            double2 c0 = reinterpret_cast<const double2 *>(p)[u], c1 = reinterpret_cast<const double2 *>(p)[u + kThreads];
+            c0.x = __dadd_rn(-a0.x, __dmul_rn(beta, c0.x)); c0.y = __dadd_rn(-a0.y, __dmul_rn(beta, c0.y));
+            c1.x = __dadd_rn(-a1.x, __dmul_rn(beta, c1.x)); c1.y = __dadd_rn(-a1.y, __dmul_rn(beta, c1.y));
+            st2(p, u, c0); st2(p, u + kThreads, c1);
+            acc[0] = fma(a0.y, c0.y, fma(a0.x, c0.x, acc[0]));
+            acc[0] = fma(a1.y, c1.y, fma(a1.x, c1.x, acc[0]));
+        }
+        for (; u < hi; u += kThreads) {
+            double2 a0 = ld2(g1, u);
+            double2 c0 = reinterpret_cast<const double2 *>(p)[u];
+            c0.x = __dadd_rn(-a0.x, __dmul_rn(beta, c0.x)); c0.y = __dadd_rn(-a0.y, __dmul_rn(beta, c0.y));
+            st2(p, u, c0);
+            acc[0] = fma(a0.y, c0.y, fma(a0.x, c0.x, acc[0]));
+        }
+        if (C.tail_here(c) && threadIdx.x == 0) {
+            const double v = __dadd_rn(-g1[n - 1], __dmul_rn(beta, p[n - 1]));
+            p[n - 1] = v;
+            acc[0] = fma(g1[n - 1], v, acc[0]);
+        }
+        red::chunk_flush<1>(acc, parity, w.partials, w.stride, c);
     }
-    for (; u < nu; u += stride) {
-        double2 a0 = ld2(g1, u);
-        double2 c0 = reinterpret_cast<const double2 *>(p)[u];
-        c0.x = __dadd_rn(-a0.x, __dmul_rn(beta, c0.x)); c0.y = __dadd_rn(-a0.y, __dmul_rn(beta, c0.y));
-        st2(p, u, c0);
-        acc[0] = fma(a0.y, c0.y, fma(a0.x, c0.x, acc[0]));
-    }
-    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const double v = __dadd_rn(-g1[n - 1], __dmul_rn(beta, p[n - 1]));
-        p[n - 1] = v;
-        acc[0] = fma(g1[n - 1], v, acc[0]);
-    }
-    const int d[1] = {SL_GP0};
-    reduce_finish<1>(acc, d, w, R);
 }
 
 // ------------------------------------------------------------------ K1: ring update + all dots
 // Replaces f90:609-624 (After: g.g, s=x-xold, y=g-gold, rho) and the 2k dot products of the next
-// Before (f90:590-606).  Block = TX x NG threads: thread row tx walks the vector, thread group ty
-// owns MT of the k_after-1 older columns; group 0 also owns the new column, which it builds in
-// registers from x1,x0,g1,g0 and stores to ring slot new_slot.
+// Before (f90:590-606).  Thread group ty owns MT of the k_after-1 older columns; group 0 also owns the new
+// column, which it builds in registers and stores to ring slot new_slot.  The chunk sums of dot d go to row d of the
+// partials (d = the index of lbfgs_gram.hpp's layout); tree_kernel delivers row d to R[kResSlots + d].
+//
+// Where the accepted point comes from is a policy (Src): PlainSrc loads x1 and f'(x1) from memory; a fused source
+// (objectives.cu, flgpu_objective.cuh) forms x1 = x0 + a*p and f'(x1) in registers and STORES them -- the separate
+// "store the accepted point" pass of the line search disappears (10n -> 7n doubles per iteration).
 struct K1Args {
-    const double *x1, *x0, *g1, *g0;
+    const double *x1, *x0, *g1, *g0;   // PlainSrc: x1, g1 read.  Fused: x1 = x1_out, g1 = g1_out are written by pass 1
+    const double *p;                   // fused source only
+    double step;                       // fused source only
+    double *x1_out, *g1_out;           // fused source only
     double *S, *Y;
-    int64_t ld, n;
+    int64_t ld, n, ch;
+    int64_t offset, n_global;          // fused source only (index-dependent objectives)
+    const double *tables;              // fused source only
     int m, new_slot, k_after;
     int age_base;       // first age handled by this pass (1 for the first pass)
     int write_new;      // 1 on the first pass: store the new column and accumulate its dots
     Work w;
-    double *R;          // dots land at R[kResSlots + d_*]
+};
+
+struct PlainSrc {
+    static constexpr bool kFused = false;
+    __device__ void init(const K1Args &) {}
+    // unit u: the accepted point and its gradient
+    __device__ __forceinline__ void unit(const K1Args &a, int64_t u, bool, double2 x0, double2 &x1, double2 &g1) const {
+        (void)x0;
+        g1 = ld2(a.g1, u);
+        if (a.write_new) x1 = ld2(a.x1, u);
+    }
+    __device__ __forceinline__ void tail(const K1Args &a, int64_t i, bool, double x0, double &x1, double &g1) const {
+        (void)x0;
+        x1 = a.x1[i]; g1 = a.g1[i];
+    }
 };
 
 // Thread layout: every warp is cut into NG segments of SEG = 32/NG lanes; segment ty is column group
@@ -264,151 +265,129 @@ struct K1Args {
 // of x1, x0, g1, g0 that every group needs are therefore issued with identical addresses inside one warp
 // instruction and coalesce into a single request (no re-read of those four vectors per group), while
 // each group's column loads stay contiguous runs of SEG*16 bytes.
-template <int MT, int NG>
-static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args a) {
+template <int MT, int NG, class Src>
+static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args a, Src src) {
     constexpr int SEG = 32 / NG;                     // lanes per column group inside a warp
     constexpr int TX = kThreads / NG;                // double2 elements per block and loop trip
     constexpr int NW = kThreads / 32;                // every warp contributes to every group
+    constexpr int NE = 4 * MT + 5;                   // sums per group (the 5 extra ones: group 0 only)
+    __shared__ double sh[2][NG][NE][NW];
+    src.init(a);
     const int ty = (threadIdx.x & 31) / SEG;
     const int tx = (threadIdx.x >> 5) * SEG + (threadIdx.x & 31) % SEG;
     const int m = a.m;
     const double *cs[MT], *cy[MT];
     bool valid[MT];
-    int slot[MT];
 #pragma unroll
     for (int c = 0; c < MT; c++) {
         const int age = a.age_base + ty * MT + c;
         valid[c] = age < a.k_after;
-        slot[c] = slot_of_age(a.new_slot, valid[c] ? age : 0, m);
-        cs[c] = a.S + (size_t)slot[c] * a.ld;
-        cy[c] = a.Y + (size_t)slot[c] * a.ld;
+        const int slot = slot_of_age(a.new_slot, valid[c] ? age : 0, m);
+        cs[c] = a.S + (size_t)slot * a.ld;
+        cy[c] = a.Y + (size_t)slot * a.ld;
     }
-    double acc[MT][4];
-#pragma unroll
-    for (int c = 0; c < MT; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
-    double ex[5] = {0.0, 0.0, 0.0, 0.0, 0.0};        // g.g, sn.g, yn.g, sn.yn, yn.yn
     const bool own_new = (ty == 0) && a.write_new;
     double *sn_col = a.S + (size_t)a.new_slot * a.ld, *yn_col = a.Y + (size_t)a.new_slot * a.ld;
-
-    const int64_t nu = a.n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * TX;
-    for (int64_t u = (int64_t)blockIdx.x * TX + tx; u < nu; u += stride) {
-        const double2 g1 = ld2(a.g1, u), g0 = ld2(a.g0, u);
-        double2 x1 = make_double2(0.0, 0.0), x0 = x1;
-        if (a.write_new) { x1 = ld2(a.x1, u); x0 = ld2(a.x0, u); }   // later passes need only y_new = g1 - g0
-        double2 s[MT], y[MT];
-#pragma unroll
-        for (int c = 0; c < MT; c++)
-            if (valid[c]) { s[c] = ld2(cs[c], u); y[c] = ld2(cy[c], u); }
-        const double2 sn = make_double2(x1.x - x0.x, x1.y - x0.y);   // s=x-xold  f90:623
-        const double2 yn = make_double2(g1.x - g0.x, g1.y - g0.y);   // y=fdnew-fdold
-        if (own_new) {
-            st2(sn_col, u, sn); st2(yn_col, u, yn);
-            ex[0] = fma(g1.y, g1.y, fma(g1.x, g1.x, ex[0]));
-            ex[1] = fma(sn.y, g1.y, fma(sn.x, g1.x, ex[1]));
-            ex[2] = fma(yn.y, g1.y, fma(yn.x, g1.x, ex[2]));
-            ex[3] = fma(sn.y, yn.y, fma(sn.x, yn.x, ex[3]));
-            ex[4] = fma(yn.y, yn.y, fma(yn.x, yn.x, ex[4]));
-        }
-#pragma unroll
-        for (int c = 0; c < MT; c++)
-            if (valid[c]) {
-                acc[c][0] = fma(s[c].y, g1.y, fma(s[c].x, g1.x, acc[c][0]));
-                acc[c][1] = fma(y[c].y, g1.y, fma(y[c].x, g1.x, acc[c][1]));
-                acc[c][2] = fma(s[c].y, yn.y, fma(s[c].x, yn.x, acc[c][2]));
-                acc[c][3] = fma(y[c].y, yn.y, fma(y[c].x, yn.x, acc[c][3]));
-            }
-    }
-    if ((a.n & 1) && blockIdx.x == 0 && tx == 0) {   // odd tail element (one thread per column group)
-        const int64_t i = a.n - 1;
-        const double x1 = a.x1[i], x0 = a.x0[i], g1 = a.g1[i], g0 = a.g0[i];
-        const double sn = x1 - x0, yn = g1 - g0;
-        if (own_new) {
-            sn_col[i] = sn; yn_col[i] = yn;
-            ex[0] = fma(g1, g1, ex[0]); ex[1] = fma(sn, g1, ex[1]); ex[2] = fma(yn, g1, ex[2]);
-            ex[3] = fma(sn, yn, ex[3]); ex[4] = fma(yn, yn, ex[4]);
-        }
-#pragma unroll
-        for (int c = 0; c < MT; c++)
-            if (valid[c]) {
-                const double s = cs[c][i], y = cy[c][i];
-                acc[c][0] = fma(s, g1, acc[c][0]); acc[c][1] = fma(y, g1, acc[c][1]);
-                acc[c][2] = fma(s, yn, acc[c][2]); acc[c][3] = fma(y, yn, acc[c][3]);
-            }
-    }
-
-    // ---- block reduction: within each column group, then one partial per (block, dot)
-    const int nd = nd_of(m);
-    __shared__ double sh[NG][4 * MT + 5][NW];
-    __shared__ bool is_last;
     const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
     const bool seg_head = (lane % SEG) == 0;
+    const Chunks C(a.n, a.ch);
+    int parity = 0;
+
+    for (int64_t chunk = blockIdx.x; chunk < C.nchunks; chunk += gridDim.x) {
+        const int64_t hi = C.hi(chunk);
+        double acc[MT][4];
 #pragma unroll
-    for (int c = 0; c < MT; c++)
+        for (int c = 0; c < MT; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
+        double ex[5] = {0.0, 0.0, 0.0, 0.0, 0.0};        // g.g, sn.g, yn.g, sn.yn, yn.yn
+        for (int64_t u = C.lo(chunk) + tx; u < hi; u += TX) {
+            const double2 g0 = ld2(a.g0, u);
+            double2 x0 = make_double2(0.0, 0.0);
+            if (a.write_new) x0 = ld2(a.x0, u);          // later passes need only y_new = g1 - g0
+            double2 s[MT], y[MT];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const double v = seg_sum<SEG>(acc[c][q]);
-            if (seg_head) sh[ty][4 * c + q][wg] = v;
-        }
-#pragma unroll
-    for (int q = 0; q < 5; q++) {
-        const double v = seg_sum<SEG>(ex[q]);
-        if (seg_head) sh[ty][4 * MT + q][wg] = v;
-    }
-    __syncthreads();
-    double *part = a.w.partials + (size_t)blockIdx.x * nd;
-    for (int idx = threadIdx.x; idx < NG * (4 * MT + 5); idx += kThreads) {
-        const int g = idx / (4 * MT + 5), e = idx % (4 * MT + 5);
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < NW; q++) s += sh[g][e][q];
-        if (e < 4 * MT) {
-            const int c = e >> 2, q = e & 3;
-            const int age = a.age_base + g * MT + c;
-            if (age < a.k_after) {
-                const int j = slot_of_age(a.new_slot, age, m);
-                const int d = q == 0 ? d_A(m, j) : q == 1 ? d_B(m, j) : q == 2 ? d_SYN(m, j) : d_YYN(m, j);
-                part[d] = s;
+            for (int c = 0; c < MT; c++)
+                if (valid[c]) { s[c] = ld2(cs[c], u); y[c] = ld2(cy[c], u); }
+            double2 x1 = make_double2(0.0, 0.0), g1;
+            src.unit(a, u, own_new, x0, x1, g1);
+            const double2 sn = make_double2(x1.x - x0.x, x1.y - x0.y);   // s=x-xold  f90:623
+            const double2 yn = make_double2(g1.x - g0.x, g1.y - g0.y);   // y=fdnew-fdold
+            if (own_new) {
+                st2(sn_col, u, sn); st2(yn_col, u, yn);
+                ex[0] = fma(g1.y, g1.y, fma(g1.x, g1.x, ex[0]));
+                ex[1] = fma(sn.y, g1.y, fma(sn.x, g1.x, ex[1]));
+                ex[2] = fma(yn.y, g1.y, fma(yn.x, g1.x, ex[2]));
+                ex[3] = fma(sn.y, yn.y, fma(sn.x, yn.x, ex[3]));
+                ex[4] = fma(yn.y, yn.y, fma(yn.x, yn.x, ex[4]));
             }
-        } else if (g == 0 && a.write_new) {
-            const int q = e - 4 * MT, j = a.new_slot;
-            const int d = q == 0 ? d_GG(m) : q == 1 ? d_A(m, j) : q == 2 ? d_B(m, j) : q == 3 ? d_SYN(m, j) : d_YYN(m, j);
-            part[d] = s;
+#pragma unroll
+            for (int c = 0; c < MT; c++)
+                if (valid[c]) {
+                    acc[c][0] = fma(s[c].y, g1.y, fma(s[c].x, g1.x, acc[c][0]));
+                    acc[c][1] = fma(y[c].y, g1.y, fma(y[c].x, g1.x, acc[c][1]));
+                    acc[c][2] = fma(s[c].y, yn.y, fma(s[c].x, yn.x, acc[c][2]));
+                    acc[c][3] = fma(y[c].y, yn.y, fma(y[c].x, yn.x, acc[c][3]));
+                }
         }
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(a.w.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // final fixed-order sum over blocks for the dots this pass produced
-    const int warp = threadIdx.x >> 5;
-    for (int d = warp; d < nd; d += kThreads / 32) {
-        // which dots belong to this pass: column j with age in [age_base, age_base+NG*MT) or the new column
-        int j, is_col = 1;
-        if (d == d_GG(m)) { is_col = 0; j = a.new_slot; }
-        else j = d < 2 * m ? d % m : (d - 2 * m - 1) % m;
-        const int age = (a.new_slot - j + m) % m;
-        bool mine;
-        if (age == 0) mine = a.write_new != 0;
-        else mine = age >= a.age_base && age < a.age_base + NG * MT && age < a.k_after;
-        (void)is_col;
-        if (!mine) continue;
-        double s = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&a.w.partials[(size_t)b * nd + d]);
-        s = warp_sum(s);
-        if (lane == 0) {
-            a.R[kResSlots + d] = s;
-            if (d == d_GG(m)) a.R[SL_GG] = s;
+        if (C.tail_here(chunk) && tx == 0) {             // odd tail element (one thread per column group)
+            const int64_t i = a.n - 1;
+            const double g0 = a.g0[i], x0 = a.write_new ? a.x0[i] : 0.0;
+            double x1 = 0.0, g1;
+            src.tail(a, i, own_new, x0, x1, g1);
+            if (!a.write_new) x1 = 0.0;
+            const double sn = x1 - x0, yn = g1 - g0;
+            if (own_new) {
+                sn_col[i] = sn; yn_col[i] = yn;
+                ex[0] = fma(g1, g1, ex[0]); ex[1] = fma(sn, g1, ex[1]); ex[2] = fma(yn, g1, ex[2]);
+                ex[3] = fma(sn, yn, ex[3]); ex[4] = fma(yn, yn, ex[4]);
+            }
+#pragma unroll
+            for (int c = 0; c < MT; c++)
+                if (valid[c]) {
+                    const double s = cs[c][i], y = cy[c][i];
+                    acc[c][0] = fma(s, g1, acc[c][0]); acc[c][1] = fma(y, g1, acc[c][1]);
+                    acc[c][2] = fma(s, yn, acc[c][2]); acc[c][3] = fma(y, yn, acc[c][3]);
+                }
         }
+        // ---- this chunk's sums: butterfly inside each column group's lanes, the 8 warps left to right
+#pragma unroll
+        for (int c = 0; c < MT; c++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double v = red::seg_butterfly<SEG>(acc[c][q]);
+                if (seg_head) sh[parity][ty][4 * c + q][wg] = v;
+            }
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            const double v = red::seg_butterfly<SEG>(ex[q]);
+            if (seg_head) sh[parity][ty][4 * MT + q][wg] = v;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NG * NE; idx += kThreads) {
+            const int g = idx / NE, e = idx % NE;
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < NW; q++) s += sh[parity][g][e][q];
+            int d = -1;
+            if (e < 4 * MT) {
+                const int c = e >> 2, q = e & 3;
+                const int age = a.age_base + g * MT + c;
+                if (age < a.k_after) {
+                    const int j = slot_of_age(a.new_slot, age, m);
+                    d = q == 0 ? d_A(m, j) : q == 1 ? d_B(m, j) : q == 2 ? d_SYN(m, j) : d_YYN(m, j);
+                }
+            } else if (g == 0 && a.write_new) {
+                const int q = e - 4 * MT, j = a.new_slot;
+                d = q == 0 ? d_GG(m) : q == 1 ? d_A(m, j) : q == 2 ? d_B(m, j) : q == 3 ? d_SYN(m, j) : d_YYN(m, j);
+            }
+            if (d >= 0) a.w.partials[(int64_t)d * a.w.stride + chunk] = s;
+        }
+        parity ^= 1;
     }
-    if (threadIdx.x == 0) *a.w.ticket = 0u;
 }
 
 // ------------------------------------------------------------------ K2: Gram-space two-loop, one warp
 // Lane-parallel form of lbfgs_gram_solve(): lane L owns ring slots L and L+32.  Dall = dots of all
-// ranks ([G][nd], rank-major) summed here in rank order, or the local dots when G == 1.
+// ranks ([G][nd], rank-major) combined here by the rank tree, or the local dots when G == 1.
 static __global__ void __launch_bounds__(32) k2_solve_kernel(int m, int k, int recent, const double *Dall, int G,
                                                       double *SY, double *YY, double *C) {
     extern __shared__ double smem[];
@@ -417,11 +396,7 @@ static __global__ void __launch_bounds__(32) k2_solve_kernel(int m, int k, int r
     double *sSY = sD + nd;             // m*m
     double *sYY = sSY + m * m;         // m*m
     const int lane = threadIdx.x;
-    for (int i = lane; i < nd; i += 32) {
-        double s = Dall[i];
-        for (int r = 1; r < G; r++) s += Dall[(size_t)r * nd + i];
-        sD[i] = s;
-    }
+    for (int i = lane; i < nd; i += 32) sD[i] = G > 1 ? red::rank_tree(Dall + i, G, nd) : Dall[i];
     __syncwarp();
     const int r = recent;
     // ages and validity of the (up to two) slots this lane owns
@@ -498,107 +473,251 @@ static __global__ void __launch_bounds__(32) k2_solve_kernel(int m, int k, int r
 
 // ------------------------------------------------------------------ K3: direction + first trial point
 // p = -( gamma (g - sum_newest..oldest alpha_i y_i) + sum_oldest..newest e_i s_i )   (f90:589-607)
-// xt = x1 + p (the a=1 trial of the next line search, f90:607+1482), g.p and p.p reduced.
+// xt = x1 + p (the a=1 trial of the next line search, f90:607+1482); chunk sums of g.p -> row 0, p.p -> row 1.
 struct K3Args {
     double *p, *xt;
     const double *g1, *x1, *S, *Y, *C;
-    int64_t ld, n;
+    int64_t ld, n, ch;
     int m, k, recent;
     Work w;
-    double *R;
 };
 
 // The 2k column operations are one list in the reference's order -- y_newest..y_oldest (q -= alpha y),
-// the gamma scaling, s_oldest..s_newest (r += e s) -- walked in chunks of CH columns with two register
-// buffers: the loads of chunk c+1 are in flight while chunk c is applied, for any k with a fixed
-// register budget.  -(alpha*y) == (-alpha)*y exactly, so both phases are v = v + coef*col.
+// the gamma scaling, s_oldest..s_newest (r += e s); -(alpha*y) == (-alpha)*y exactly, so both phases are
+// v = v + coef*col.  Coefficient / column tables in shared memory, built by every block.
+struct K3Tables {
+    double coef[2 * kMaxMem];
+    const double *col[2 * kMaxMem];
+    double gamma;
+};
+__device__ __forceinline__ void k3_build_tables(const K3Args &a, K3Tables &T, int nthreads) {
+    const int m = a.m, k = a.k;
+    for (int t = threadIdx.x; t < k; t += nthreads) {
+        const int j = slot_of_age(a.recent, t, m);
+        T.coef[t] = -a.C[1 + j];                       // op t        : y of age t
+        T.col[t] = a.Y + (size_t)j * a.ld;
+        T.coef[2 * k - 1 - t] = a.C[1 + m + j];        // op 2k-1-t   : s of age t
+        T.col[2 * k - 1 - t] = a.S + (size_t)j * a.ld;
+    }
+    if (threadIdx.x == 0) T.gamma = a.C[0];
+}
+__device__ __forceinline__ void k3_tail(const K3Args &a, const K3Tables &T, double (&acc)[2]) {
+    const int64_t i = a.n - 1;
+    const int nops = 2 * a.k;
+    const double g = a.g1[i];
+    double v = g;
+    for (int o = 0; o < nops; o++) {
+        if (o == a.k) v = __dmul_rn(T.gamma, v);
+        v = __dadd_rn(v, __dmul_rn(T.coef[o], T.col[o][i]));
+    }
+    const double pv = -v;
+    a.p[i] = pv;
+    if (a.xt) a.xt[i] = a.x1[i] + pv;
+    acc[0] = fma(g, pv, acc[0]);
+    acc[1] = fma(pv, pv, acc[1]);
+}
+
+// ---- K3, register version (FLGPU_K3=regs; the r01 kernel on the chunked reduction): the column list is walked in
+// chunks of CH columns with two register buffers, the loads of group c+1 in flight while group c is applied.
 template <int CH>
 static __global__ void __launch_bounds__(kThreads, 2) k3_direction_kernel(K3Args a) {
-    __shared__ double coef[2 * kMaxMem];
-    __shared__ const double *col[2 * kMaxMem];
-    __shared__ double s_gamma;
-    const int m = a.m, k = a.k;
-    for (int t = threadIdx.x; t < k; t += kThreads) {
-        const int j = slot_of_age(a.recent, t, m);
-        coef[t] = -a.C[1 + j];                       // op t        : y of age t
-        col[t] = a.Y + (size_t)j * a.ld;
-        coef[2 * k - 1 - t] = a.C[1 + m + j];        // op 2k-1-t   : s of age t
-        col[2 * k - 1 - t] = a.S + (size_t)j * a.ld;
-    }
-    if (threadIdx.x == 0) s_gamma = a.C[0];
+    __shared__ K3Tables T;
+    k3_build_tables(a, T, kThreads);
     __syncthreads();
-    const double gamma = s_gamma;
+    const int k = a.k;
+    const double gamma = T.gamma;
     const int nops = 2 * k;
-    const int nchunks = (nops + CH - 1) / CH;
-    double acc[2] = {0.0, 0.0};
-    const int64_t nu = a.n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
-        double2 bufA[CH], bufB[CH];
-        auto load = [&](double2 (&b)[CH], int c) {
+    const int ngroups = (nops + CH - 1) / CH;
+    const Chunks C(a.n, a.ch);
+    int parity = 0;
+    for (int64_t chunk = blockIdx.x; chunk < C.nchunks; chunk += gridDim.x) {
+        const int64_t hi = C.hi(chunk);
+        double acc[2] = {0.0, 0.0};
+        for (int64_t u = C.lo(chunk) + threadIdx.x; u < hi; u += kThreads) {
+            double2 bufA[CH], bufB[CH];
+            auto load = [&](double2 (&b)[CH], int c) {
 #pragma unroll
-            for (int i = 0; i < CH; i++) {
-                const int o = c * CH + i;
-                if (o < nops) b[i] = ld2(col[o], u);
+                for (int i = 0; i < CH; i++) {
+                    const int o = c * CH + i;
+                    if (o < nops) b[i] = ld2(T.col[o], u);
+                }
+            };
+            double2 v = ld2(a.g1, u);
+            const double2 g = v;
+            load(bufA, 0);
+            double2 x = make_double2(0.0, 0.0);
+            if (a.xt) x = ld2(a.x1, u);
+            auto apply = [&](const double2 (&b)[CH], int c) {
+#pragma unroll
+                for (int i = 0; i < CH; i++) {
+                    const int o = c * CH + i;
+                    if (o < nops) {
+                        if (o == k) { v.x = __dmul_rn(gamma, v.x); v.y = __dmul_rn(gamma, v.y); }
+                        const double cf = T.coef[o];
+                        v.x = __dadd_rn(v.x, __dmul_rn(cf, b[i].x));
+                        v.y = __dadd_rn(v.y, __dmul_rn(cf, b[i].y));
+                    }
+                }
+            };
+            for (int c = 0; c < ngroups; c += 2) {
+                if (c + 1 < ngroups) load(bufB, c + 1);
+                apply(bufA, c);
+                if (c + 2 < ngroups) load(bufA, c + 2);
+                if (c + 1 < ngroups) apply(bufB, c + 1);
             }
-        };
-        double2 v = ld2(a.g1, u);
-        const double2 g = v;
-        load(bufA, 0);
-        double2 x = make_double2(0.0, 0.0);
-        if (a.xt) x = ld2(a.x1, u);
-        auto apply = [&](const double2 (&b)[CH], int c) {
-#pragma unroll
-            for (int i = 0; i < CH; i++) {
-                const int o = c * CH + i;
-                if (o < nops) {
-                    if (o == k) { v.x = __dmul_rn(gamma, v.x); v.y = __dmul_rn(gamma, v.y); }
-                    const double cf = coef[o];
-                    v.x = __dadd_rn(v.x, __dmul_rn(cf, b[i].x));
-                    v.y = __dadd_rn(v.y, __dmul_rn(cf, b[i].y));
+            const double2 pv = make_double2(-v.x, -v.y);
+            st2(a.p, u, pv);
+            if (a.xt) st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
+            acc[0] = fma(g.y, pv.y, fma(g.x, pv.x, acc[0]));
+            acc[1] = fma(pv.y, pv.y, fma(pv.x, pv.x, acc[1]));
+        }
+        if (C.tail_here(chunk) && threadIdx.x == 0) k3_tail(a, T, acc);
+        red::chunk_flush<2>(acc, parity, a.w.partials, a.w.stride, chunk);
+    }
+}
+
+// ---- K3, bulk-async version (default).  The register version keeps at most two buffers of 8 columns x 16 B per
+// thread in flight (its register budget), which left it 10 % below K1's per-byte rate (profiles/r01c_kernels.md:
+// 79.6 % DRAM utilisation, 10 long-scoreboard stalls per issue).  Here one elected thread of a producer warp streams
+// the 2k+1 (+1) input vectors of a tile of 256 units as 4 KB pieces into a shared-memory ring with 1-D bulk async
+// copies (cp.async.bulk, SASS UBLKCP) that signal an mbarrier per stage; the 8 consumer warps apply the pieces in the
+// reference's order out of shared memory.  Bytes in flight per SM are then the ring size (2 x NST x P x 4 KB), not a
+// register budget, and the consumers need ~40 registers.  Same arithmetic in the same order as the register version:
+// identical bits.
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+}  // namespace tma
+
+template <int P, int NST>
+static __global__ void __launch_bounds__(kThreads + 32, 2) k3_direction_tma_kernel(K3Args a) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    double2 *ring = reinterpret_cast<double2 *>(dyn);            // [NST][P][kThreads]
+    __shared__ K3Tables T;
+    __shared__ __align__(8) uint64_t full[NST], empty[NST];
+    k3_build_tables(a, T, kThreads + 32);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) { tma::mbar_init(&full[s], 1); tma::mbar_init(&empty[s], red::kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int k = a.k;
+    const int npieces = 2 * k + 1 + (a.xt ? 1 : 0);              // g, the 2k columns, (x)
+    const int ngroups = (npieces + P - 1) / P;
+    const Chunks C(a.n, a.ch);
+    const bool producer = threadIdx.x >= kThreads;
+
+    if (producer) {
+        if (threadIdx.x != kThreads) return;                     // one elected thread issues every copy
+        uint32_t it = 0;
+        for (int64_t chunk = blockIdx.x; chunk < C.nchunks; chunk += gridDim.x) {
+            const int64_t hi = C.hi(chunk);
+            for (int64_t t0 = C.lo(chunk); t0 < hi; t0 += kThreads) {
+                const uint32_t units = (uint32_t)((hi - t0) < kThreads ? (hi - t0) : kThreads);
+                const uint32_t bytes = units * 16u;
+                for (int grp = 0; grp < ngroups; grp++, it++) {
+                    const int s = it % NST;
+                    tma::mbar_wait(&empty[s], ((it / NST) & 1u) ^ 1u);
+                    const int cnt = (npieces - grp * P) < P ? (npieces - grp * P) : P;
+                    tma::mbar_expect_tx(&full[s], bytes * (uint32_t)cnt);
+                    for (int i = 0; i < cnt; i++) {
+                        const int j = grp * P + i;
+                        const double *src = j == 0 ? a.g1 : (j <= 2 * k ? T.col[j - 1] : a.x1);
+                        tma::bulk_g2s(ring + ((size_t)s * P + i) * kThreads, reinterpret_cast<const double2 *>(src) + t0,
+                                      bytes, &full[s]);
+                    }
                 }
             }
-        };
-        for (int c = 0; c < nchunks; c += 2) {
-            if (c + 1 < nchunks) load(bufB, c + 1);
-            apply(bufA, c);
-            if (c + 2 < nchunks) load(bufA, c + 2);
-            if (c + 1 < nchunks) apply(bufB, c + 1);
         }
-        const double2 pv = make_double2(-v.x, -v.y);
-        st2(a.p, u, pv);
-        if (a.xt) st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
-        acc[0] = fma(g.y, pv.y, fma(g.x, pv.x, acc[0]));
-        acc[1] = fma(pv.y, pv.y, fma(pv.x, pv.x, acc[1]));
+        return;
     }
-    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-        const int64_t i = a.n - 1;
-        const double g = a.g1[i];
-        double v = g;
-        for (int o = 0; o < nops; o++) {
-            if (o == k) v = __dmul_rn(gamma, v);
-            v = __dadd_rn(v, __dmul_rn(coef[o], col[o][i]));
+
+    // ---- consumers (threads 0..255): barrier 1 is theirs alone
+    const double gamma = T.gamma;
+    const int lane = threadIdx.x & 31;
+    uint32_t it = 0;
+    int parity = 0;
+    for (int64_t chunk = blockIdx.x; chunk < C.nchunks; chunk += gridDim.x) {
+        const int64_t hi = C.hi(chunk);
+        double acc[2] = {0.0, 0.0};
+        for (int64_t t0 = C.lo(chunk); t0 < hi; t0 += kThreads) {
+            const int64_t u = t0 + threadIdx.x;
+            const bool active = u < hi;
+            double2 v = make_double2(0.0, 0.0), g = v, x = v;
+            for (int grp = 0; grp < ngroups; grp++, it++) {
+                const int s = it % NST;
+                tma::mbar_wait(&full[s], (it / NST) & 1u);
+                if (active) {
+                    const double2 *st = ring + (size_t)s * P * kThreads + threadIdx.x;
+#pragma unroll
+                    for (int i = 0; i < P; i++) {
+                        const int j = grp * P + i;
+                        if (j < npieces) {
+                            const double2 b = st[(size_t)i * kThreads];
+                            if (j == 0) { v = b; g = b; }
+                            else if (j <= 2 * k) {
+                                const int o = j - 1;
+                                if (o == k) { v.x = __dmul_rn(gamma, v.x); v.y = __dmul_rn(gamma, v.y); }
+                                const double cf = T.coef[o];
+                                v.x = __dadd_rn(v.x, __dmul_rn(cf, b.x));
+                                v.y = __dadd_rn(v.y, __dmul_rn(cf, b.y));
+                            } else {
+                                x = b;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) tma::mbar_arrive(&empty[s]);      // this warp is done with the stage
+            }
+            if (active) {
+                const double2 pv = make_double2(-v.x, -v.y);
+                st2(a.p, u, pv);
+                if (a.xt) st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
+                acc[0] = fma(g.y, pv.y, fma(g.x, pv.x, acc[0]));
+                acc[1] = fma(pv.y, pv.y, fma(pv.x, pv.x, acc[1]));
+            }
         }
-        const double pv = -v;
-        a.p[i] = pv;
-        if (a.xt) a.xt[i] = a.x1[i] + pv;
-        acc[0] = fma(g, pv, acc[0]);
-        acc[1] = fma(pv, pv, acc[1]);
+        if (C.tail_here(chunk) && threadIdx.x == 0) k3_tail(a, T, acc);
+        red::chunk_flush<2, 1>(acc, parity, a.w.partials, a.w.stride, chunk);
     }
-    const int d[2] = {SL_GP0, SL_PP};
-    reduce_finish<2>(acc, d, a.w, a.R);
 }
 
 // ------------------------------------------------------------------ C1: rank exchange over peer memory
-// Row-sharded runs combine each reduction's per-rank partial sums.  Instead of a library all-gather
+// Row-sharded runs combine each reduction's per-rank roots.  Instead of a library all-gather
 // followed by a combine kernel, ONE single-block kernel per exchange does both over NVLink/NVSwitch
-// peer memory: every rank stores its `count` partials straight into slot [me] of every peer's mailbox
+// peer memory: every rank stores its `count` values straight into slot [me] of every peer's mailbox
 // (plain st.global on IPC-mapped peer pointers), publishes a sequence number, waits until the G slots of
-// its OWN mailbox carry this sequence number, and sums them in rank order -- identical bits on all ranks.
+// its OWN mailbox carry this sequence number, and combines them by the rank tree (red::rank_tree) -- identical bits
+// on all ranks, and the bits of the single-GPU tree when the shards are aligned subtrees (flgpu_reduce.cuh).
 // Mailboxes are double-buffered on the sequence parity: a peer can be at most one exchange ahead (it
 // needs this rank's flag of exchange seq+1 before it can start seq+2), so two buffers suffice.
 constexpr int kMailWidth = 320;       // doubles per rank slot: >= NSLOTS + nd_of(kMaxMem)
-constexpr int kMaxRanks = 16;
+constexpr int kMaxRanks = red::kMaxRanks;
 
 struct Mailbox {
     double data[2][kMaxRanks][kMailWidth];
@@ -633,9 +752,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // Executed by ONE block: store vals[0..count) (count <= blockDim.x) into slot [me] of every rank's mailbox, publish
-// `seq`, wait for every rank's slot of this rank's mailbox, return the rank-ordered sums in out[0..count).
+// `seq`, wait for every rank's slot of this rank's mailbox, return the rank-tree sums in out[0..count).
+// timeout_ns: how long a peer may stay silent before this rank records the failure in its mailbox and traps.
 __device__ __forceinline__ void mailbox_exchange_block(const PeerTable &peers, int me, int G, unsigned long long seq,
-                                                       const double *vals, int count, double *out) {
+                                                       const double *vals, int count, double *out,
+                                                       unsigned long long timeout_ns) {
     const int par = (int)(seq & 1ull), t = threadIdx.x;
     if (t < count) {
         const double v = vals[t];
@@ -648,7 +769,7 @@ __device__ __forceinline__ void mailbox_exchange_block(const PeerTable &peers, i
     if (t < G) {
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(&mine->flag[par][t]) < seq) {
-            if (global_timer_ns() - t0 > 20000000000ull) {
+            if (global_timer_ns() - t0 > timeout_ns) {
                 mine->error = seq;
                 __threadfence_system();
                 __trap();
@@ -657,24 +778,25 @@ __device__ __forceinline__ void mailbox_exchange_block(const PeerTable &peers, i
     }
     __syncthreads();
     if (t < count) {
-        double s = __ldcv(&mine->data[par][0][t]);
-        for (int r = 1; r < G; r++) s += __ldcv(&mine->data[par][r][t]);
-        out[t] = s;
+        double v[kMaxRanks];
+        for (int r = 0; r < G; r++) v[r] = __ldcv(&mine->data[par][r][t]);
+        out[t] = red::rank_tree(v, G);
     }
 }
 
 
-// src: this rank's `count` partial sums; out: their rank-ordered sum (count <= kMailWidth); host_out (optional):
+// src: this rank's `count` values; out: their rank-tree sum (count <= kMailWidth); host_out (optional):
 // the same sums stored straight into pinned host memory followed by the flag word host_out[NSLOTS] = seq_host.
 static __global__ void __launch_bounds__(kMailWidth) exchange_kernel(PeerTable peers, int me, int G,
                                                                        unsigned long long seq, const double *src,
                                                                        int count, double *out, double *host_out,
-                                                                       unsigned long long seq_host, const double *extra) {
+                                                                       unsigned long long seq_host, const double *extra,
+                                                                       unsigned long long timeout_ns) {
     __shared__ double vals[kMailWidth], sums[kMailWidth];
     const int t = threadIdx.x;
     if (t < count) vals[t] = src[t];
     __syncthreads();
-    mailbox_exchange_block(peers, me, G, seq, vals, count, sums);
+    mailbox_exchange_block(peers, me, G, seq, vals, count, sums, timeout_ns);
     if (t < count) {
         out[t] = sums[t];
         if (host_out) host_out[t] = sums[t];
@@ -698,14 +820,10 @@ static __global__ void __launch_bounds__(32) publish_kernel(const double *src, d
     if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(host_out + NSLOTS) = seq_host;
 }
 
-// ------------------------------------------------------------------ multi-rank combine of the slots
+// ------------------------------------------------------------------ multi-rank combine of the slots (NCCL fallback)
 static __global__ void combine_kernel(const double *all, int G, int count, double *out) {
     const int i = threadIdx.x;
-    if (i < count) {
-        double s = all[i];
-        for (int r = 1; r < G; r++) s += all[(size_t)r * count + i];
-        out[i] = s;
-    }
+    if (i < count) out[i] = red::rank_tree(all + i, G, count);
 }
 
 static __global__ void set_scalar_kernel(double *dst, double v) { *dst = v; }

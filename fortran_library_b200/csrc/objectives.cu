@@ -21,36 +21,48 @@ namespace flgpu {
 
 // ---- per-stream scratch for library kernels launched outside a CudaBackend (callbacks, primitives)
 struct Scratch {
-    k::Work work;
+    k::Work work;         // 8 rows of chunk sums (grown on demand), block values, tickets
     double *scalar;       // device double[4]
     double *host_scalar;  // pinned double[4]
     double *tables;       // device double[768], diag-quad factors
 };
+constexpr int kScratchRows = 8;
 static std::mutex g_scratch_mu;
 static std::map<std::pair<int, void *>, Scratch> g_scratch;
 
-Scratch &scratch_for(cudaStream_t s) {
+// nchunks: chunk sums per row the caller is about to produce (the partial buffer grows to hold them)
+Scratch &scratch_for(cudaStream_t s, int64_t nchunks) {
     int dev = 0;
     FLGPU_CUDA_CHECK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_scratch_mu);
     auto key = std::make_pair(dev, (void *)s);
     auto it = g_scratch.find(key);
-    if (it != g_scratch.end()) return it->second;
-    Scratch sc;
-    FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.work.partials, (size_t)k::kMaxGrid * 8 * sizeof(double)));
-    FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.work.ticket, 64));
-    FLGPU_CUDA_CHECK(cudaMemset(sc.work.ticket, 0, 64));
-    FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.scalar, 4 * sizeof(double)));
-    FLGPU_CUDA_CHECK(cudaMallocHost((void **)&sc.host_scalar, 4 * sizeof(double)));
-    FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.tables, 768 * sizeof(double)));
-    double h[768];
-    for (int q = 0; q < 256; q++) {
-        h[q] = std::pow(10.0, 6.0 * (double)q / 16777216.0);
-        h[256 + q] = std::pow(10.0, 6.0 * (double)q / 65536.0);
-        h[512 + q] = std::pow(10.0, 6.0 * (double)q / 256.0);
+    if (it == g_scratch.end()) {
+        Scratch sc{};
+        FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.work.blockvals, (size_t)kScratchRows * red::kTopMax * sizeof(double)));
+        FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.work.tickets, kScratchRows * sizeof(unsigned int)));
+        FLGPU_CUDA_CHECK(cudaMemset(sc.work.tickets, 0, kScratchRows * sizeof(unsigned int)));
+        FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.scalar, 4 * sizeof(double)));
+        FLGPU_CUDA_CHECK(cudaMallocHost((void **)&sc.host_scalar, 4 * sizeof(double)));
+        FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.tables, 768 * sizeof(double)));
+        double h[768];
+        for (int q = 0; q < 256; q++) {
+            h[q] = std::pow(10.0, 6.0 * (double)q / 16777216.0);
+            h[256 + q] = std::pow(10.0, 6.0 * (double)q / 65536.0);
+            h[512 + q] = std::pow(10.0, 6.0 * (double)q / 256.0);
+        }
+        FLGPU_CUDA_CHECK(cudaMemcpy(sc.tables, h, sizeof h, cudaMemcpyHostToDevice));
+        it = g_scratch.emplace(key, sc).first;
     }
-    FLGPU_CUDA_CHECK(cudaMemcpy(sc.tables, h, sizeof h, cudaMemcpyHostToDevice));
-    return g_scratch.emplace(key, sc).first->second;
+    Scratch &sc = it->second;
+    if (nchunks > sc.work.stride) {        // grow (cudaFree waits for work still using the old buffer)
+        int64_t cap = sc.work.stride > 0 ? sc.work.stride : 1024;
+        while (cap < nchunks) cap *= 2;
+        if (sc.work.partials) cudaFree(sc.work.partials);
+        FLGPU_CUDA_CHECK(cudaMalloc((void **)&sc.work.partials, (size_t)kScratchRows * (size_t)cap * sizeof(double)));
+        sc.work.stride = cap;
+    }
+    return sc;
 }
 
 // Called when a library-owned stream is destroyed: its scratch would otherwise stay in the map forever.
@@ -61,13 +73,23 @@ void scratch_release(cudaStream_t s) {
     auto it = g_scratch.find(std::make_pair(dev, (void *)s));
     if (it == g_scratch.end()) return;
     cudaFree(it->second.work.partials);
-    cudaFree(it->second.work.ticket);
+    cudaFree(it->second.work.blockvals);
+    cudaFree(it->second.work.tickets);
     cudaFree(it->second.scalar);
     cudaFreeHost(it->second.host_scalar);
     cudaFree(it->second.tables);
     g_scratch.erase(it);
 }
-double *scratch_scalar(cudaStream_t s) { return scratch_for(s).scalar; }
+double *scratch_scalar(cudaStream_t s) { return scratch_for(s, 1).scalar; }
+
+// chunk sums of rows [0, nrows) of `w` -> out[row] (device pointers; null = skip)
+void launch_tree(const k::Work &w, int64_t nchunks, int nrows, double *const *out, cudaStream_t s) {
+    k::TreeArgs a;
+    a.w = w; a.nchunks = nchunks; a.lin_out = nullptr; a.dup_row = -1; a.dup_out = nullptr;
+    for (int i = 0; i < 8; i++) a.out[i] = i < nrows ? out[i] : nullptr;
+    const int nblk = (int)((nchunks + red::kBlockChunks - 1) / red::kBlockChunks);
+    k::tree_kernel<<<dim3(nblk, nrows), k::kThreads, 0, s>>>(a);
+}
 
 namespace k {
 
@@ -81,36 +103,78 @@ struct ObjArgs {
     double a;           // fused only
     double *x_out;      // fused + FLGPU_WRITE_X
     double *g;          // may be null (f only)
-    double *f_out;      // device scalar, may be null (f' only)
-    double *gp_out;     // device scalar (FLGPU_WANT_GP)
-    int64_t n, offset, n_global;
+    int64_t n, offset, n_global, ch;
     double scale;       // diag quad: 2^24/(n_global-1)
     const double *tables;
-    Work w;
+    Work w;             // chunk sums: f -> row 0 (or the only row), f'.p -> the next row
 };
 
-// FUSED: the point is formed as x0 + a*p (multiply, then add: f90:1482) instead of being loaded; WANT_GP:
-// f'(x).p is reduced alongside f; WRITE_X / WRITE_G: store the point / gradient.  The thread-to-element mapping and
-// the accumulation order of f do not depend on the flags, so f has the same bits on the fused and the unfused path.
-// Per-thread part of every objective evaluation: this thread's share of the units, in grid-stride order.  Shared by
-// objective_kernel (one evaluation per launch) and search_kernel (a whole line search per launch), so both produce
-// the same bits for f and f'.p.  tab: the diag-quad factor tables in shared memory (unused otherwise).
-template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
-__device__ __forceinline__ void objective_accumulate(const ObjArgs &a, const double *tab, double &fsum, double &gpsum) {
+// What an objective needs to know about where a unit sits in the global vector.
+struct ObjIndex {
+    double offset_d, scale;
+    int64_t n_global;
+    const double *tab;   // the diag-quad factor tables in shared memory (unused otherwise)
     // d_i = 10^(6 q / 2^24), q = trunc(i * scale) <= 2^24 (diagonal quadratic); the index arrives
     // as a double (exact below 2^53) and the truncation is a 32-bit conversion: same bits, no 64-bit I2F/F2I
-    auto coeff = [&](double i) -> double {
-        if (a.n_global <= 1) return 1.0;
-        const unsigned int q = __double2uint_rz(mul(i, a.scale));
+    __device__ __forceinline__ double coeff(double i) const {
+        if (n_global <= 1) return 1.0;
+        const unsigned int q = __double2uint_rz(mul(i, scale));
         if (q >> 24) return 1.0e6;
         return mul(mul(tab[512 + ((q >> 16) & 255)], tab[256 + ((q >> 8) & 255)]), tab[q & 255]);
-    };
-    const double offset_d = (double)a.offset;
+    }
+};
+
+// One 16-byte unit of objective KIND at local unit index u: f terms are ADDED to fsum in element order, f' -> g.
+template <int KIND, bool WANT_F, bool NEED_G>
+__device__ __forceinline__ void objective_unit(const ObjIndex &ix, int64_t u, const double2 x, double &fsum, double2 &g) {
+    if (KIND == FLGPU_OBJ_QUARTIC) {
+        const double x2 = mul(x.x, x.x), y2 = mul(x.y, x.y);
+        if (WANT_F) { fsum += mul(x2, x2); fsum += mul(y2, y2); }
+        if (NEED_G) { g.x = mul(4.0, mul(x2, x.x)); g.y = mul(4.0, mul(y2, x.y)); }
+    } else if (KIND == FLGPU_OBJ_ROSENBROCK) {
+        const double t1 = sub(x.y, mul(x.x, x.x)), t2 = sub(1.0, x.x);
+        if (WANT_F) fsum += add(mul(mul(100.0, t1), t1), mul(t2, t2));
+        if (NEED_G) {
+            g.x = sub(mul(mul(-400.0, x.x), t1), mul(2.0, t2));
+            g.y = mul(200.0, t1);
+        }
+    } else {
+        const double i = ix.offset_d + (double)(2 * u);   // exact: both terms and the sum are integers < 2^53
+        const double d0 = ix.coeff(i), d1 = ix.coeff(i + 1.0);
+        const double t0 = sub(x.x, 1.0), t1 = sub(x.y, 1.0);
+        if (WANT_F) { fsum += mul(mul(mul(0.5, d0), t0), t0); fsum += mul(mul(mul(0.5, d1), t1), t1); }
+        if (NEED_G) { g.x = mul(d0, t0); g.y = mul(d1, t1); }
+    }
+}
+// the unpaired last element of an odd-length shard (local element index i)
+template <int KIND, bool WANT_F>
+__device__ __forceinline__ void objective_tail(const ObjIndex &ix, int64_t i, const double x, double &fsum, double &g) {
+    if (KIND == FLGPU_OBJ_QUARTIC) {
+        const double x2 = mul(x, x);
+        if (WANT_F) fsum += mul(x2, x2);
+        g = mul(4.0, mul(x2, x));
+    } else if (KIND == FLGPU_OBJ_ROSENBROCK) {
+        const double t2 = sub(1.0, x);
+        if (WANT_F) fsum += mul(t2, t2);
+        g = mul(-2.0, t2);
+    } else {
+        const double d = ix.coeff(ix.offset_d + (double)i), t = sub(x, 1.0);
+        if (WANT_F) fsum += mul(mul(mul(0.5, d), t), t);
+        g = mul(d, t);
+    }
+}
+
+// FUSED: the point is formed as x0 + a*p (multiply, then add: f90:1482) instead of being loaded; WANT_GP:
+// f'(x).p is reduced alongside f; WRITE_X / WRITE_G: store the point / gradient.
+// One CHUNK of an objective evaluation (flgpu_reduce.cuh): this thread's units of chunk c in order, f and f'.p
+// accumulated into fsum / gpsum.  Shared by objective_kernel (one evaluation per launch) and search_kernel (a whole
+// line search per launch), so both produce the same chunk sums; the accumulation order of f does not depend on the
+// flags either, so f has the same bits on the fused and the unfused path.
+template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
+__device__ __forceinline__ void objective_chunk(const ObjArgs &a, const ObjIndex &ix, const Chunks &C, int64_t c,
+                                                double &fsum, double &gpsum) {
     constexpr bool NEED_G = WANT_GP || WRITE_G;
     const double step = a.a;
-    const int64_t nu = a.n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    // one double2 unit: x (loaded or formed from x0, p), objective terms, optional stores
     auto unit = [&](int64_t u, double2 x, const double2 pv) {
         if (FUSED) {
             x.x = add(x.x, mul(step, pv.x));
@@ -118,47 +182,30 @@ __device__ __forceinline__ void objective_accumulate(const ObjArgs &a, const dou
             if (WRITE_X) st2(a.x_out, u, x);
         }
         double2 g = make_double2(0.0, 0.0);
-        if (KIND == FLGPU_OBJ_QUARTIC) {
-            const double x2 = mul(x.x, x.x), y2 = mul(x.y, x.y);
-            if (WANT_F) { fsum += mul(x2, x2); fsum += mul(y2, y2); }
-            if (NEED_G) { g.x = mul(4.0, mul(x2, x.x)); g.y = mul(4.0, mul(y2, x.y)); }
-        } else if (KIND == FLGPU_OBJ_ROSENBROCK) {
-            const double t1 = sub(x.y, mul(x.x, x.x)), t2 = sub(1.0, x.x);
-            if (WANT_F) fsum += add(mul(mul(100.0, t1), t1), mul(t2, t2));
-            if (NEED_G) {
-                g.x = sub(mul(mul(-400.0, x.x), t1), mul(2.0, t2));
-                g.y = mul(200.0, t1);
-            }
-        } else {
-            const double i = offset_d + (double)(2 * u);   // exact: both terms and the sum are integers < 2^53
-            const double d0 = coeff(i), d1 = coeff(i + 1.0);
-            const double t0 = sub(x.x, 1.0), t1 = sub(x.y, 1.0);
-            if (WANT_F) { fsum += mul(mul(mul(0.5, d0), t0), t0); fsum += mul(mul(mul(0.5, d1), t1), t1); }
-            if (NEED_G) { g.x = mul(d0, t0); g.y = mul(d1, t1); }
-        }
+        objective_unit<KIND, WANT_F, NEED_G>(ix, u, x, fsum, g);
         if (WRITE_G) st2(a.g, u, g);
         if (WANT_GP) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
     };
-    // four units per trip with all loads issued first (8 x 16 B in flight per thread on the fused path);
-    // units are visited in the same order as a plain grid-stride loop, so f has the same bits
+    // four units per trip with all loads issued first (8 x 16 B in flight per thread on the fused path)
     const double2 zero2 = make_double2(0.0, 0.0);
-    int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    for (; u + 3 * stride < nu; u += 4 * stride) {
-        const double2 x0v = ld2(a.x, u), x1v = ld2(a.x, u + stride), x2v = ld2(a.x, u + 2 * stride),
-                      x3v = ld2(a.x, u + 3 * stride);
+    const int64_t hi = C.hi(c);
+    int64_t u = C.lo(c) + threadIdx.x;
+    for (; u + 3 * kThreads < hi; u += 4 * kThreads) {
+        const double2 x0v = ld2(a.x, u), x1v = ld2(a.x, u + kThreads), x2v = ld2(a.x, u + 2 * kThreads),
+                      x3v = ld2(a.x, u + 3 * kThreads);
         double2 p0v = zero2, p1v = zero2, p2v = zero2, p3v = zero2;
         if (FUSED) {
-            p0v = ld2(a.p, u); p1v = ld2(a.p, u + stride); p2v = ld2(a.p, u + 2 * stride); p3v = ld2(a.p, u + 3 * stride);
+            p0v = ld2(a.p, u); p1v = ld2(a.p, u + kThreads); p2v = ld2(a.p, u + 2 * kThreads); p3v = ld2(a.p, u + 3 * kThreads);
         }
-        unit(u, x0v, p0v); unit(u + stride, x1v, p1v); unit(u + 2 * stride, x2v, p2v); unit(u + 3 * stride, x3v, p3v);
+        unit(u, x0v, p0v); unit(u + kThreads, x1v, p1v); unit(u + 2 * kThreads, x2v, p2v); unit(u + 3 * kThreads, x3v, p3v);
     }
-    for (; u < nu; u += stride) {
+    for (; u < hi; u += kThreads) {
         const double2 xv = ld2(a.x, u);
         double2 pv = zero2;
         if (FUSED) pv = ld2(a.p, u);
         unit(u, xv, pv);
     }
-    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (C.tail_here(c) && threadIdx.x == 0) {
         const int64_t i = a.n - 1;
         double x = a.x[i], pv = 0.0;
         if (FUSED) {
@@ -167,73 +214,67 @@ __device__ __forceinline__ void objective_accumulate(const ObjArgs &a, const dou
             if (WRITE_X) a.x_out[i] = x;
         }
         double g = 0.0;
-        if (KIND == FLGPU_OBJ_QUARTIC) {
-            const double x2 = mul(x, x);
-            if (WANT_F) fsum += mul(x2, x2);
-            g = mul(4.0, mul(x2, x));
-        } else if (KIND == FLGPU_OBJ_ROSENBROCK) {   // unpaired last element
-            const double t2 = sub(1.0, x);
-            if (WANT_F) fsum += mul(t2, t2);
-            g = mul(-2.0, t2);
-        } else {
-            const double d = coeff((double)(a.offset + i)), t = sub(x, 1.0);
-            if (WANT_F) fsum += mul(mul(mul(0.5, d), t), t);
-            g = mul(d, t);
-        }
+        objective_tail<KIND, WANT_F>(ix, i, x, fsum, g);
         if (WRITE_G) a.g[i] = g;
         if (WANT_GP) gpsum = fma(g, pv, gpsum);
     }
 }
 
 template <int KIND>
-__device__ __forceinline__ void load_tables(const ObjArgs &a, double *tab) {
+__device__ __forceinline__ ObjIndex load_tables(int64_t offset, int64_t n_global, double scale, const double *tables, double *tab,
+                                                int nthreads) {
     if (KIND == FLGPU_OBJ_DIAGQUAD) {
-        for (int i = threadIdx.x; i < 768; i += kThreads) tab[i] = a.tables[i];
+        for (int i = threadIdx.x; i < 768; i += nthreads) tab[i] = tables[i];
         __syncthreads();
     }
+    ObjIndex ix;
+    ix.offset_d = (double)offset; ix.scale = scale; ix.n_global = n_global; ix.tab = tab;
+    return ix;
 }
 
 // One kernel serves the plain callbacks (f, fd, f_fd) and the fused line-search evaluation (flgpu_fused_fn).
 template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
 __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
     __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
-    load_tables<KIND>(a, tab);
-    double fsum = 0.0, gpsum = 0.0;
-    objective_accumulate<KIND, FUSED, WANT_F, WANT_GP, WRITE_X, WRITE_G>(a, tab, fsum, gpsum);
-    if (WANT_F && WANT_GP) {
-        double acc[2] = {fsum, gpsum};
-        double *out[2] = {a.f_out, a.gp_out};
-        reduce_finish_to<2>(acc, out, a.w);
-    } else if (WANT_F) {
-        double acc[1] = {fsum};
-        double *out[1] = {a.f_out};
-        reduce_finish_to<1>(acc, out, a.w);
-    } else if (WANT_GP) {
-        double acc[1] = {gpsum};
-        double *out[1] = {a.gp_out};
-        reduce_finish_to<1>(acc, out, a.w);
+    const ObjIndex ix = load_tables<KIND>(a.offset, a.n_global, a.scale, a.tables, tab, kThreads);
+    const Chunks C(a.n, a.ch);
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+        double fsum = 0.0, gpsum = 0.0;
+        objective_chunk<KIND, FUSED, WANT_F, WANT_GP, WRITE_X, WRITE_G>(a, ix, C, c, fsum, gpsum);
+        if (WANT_F && WANT_GP) {
+            const double acc[2] = {fsum, gpsum};
+            red::chunk_flush<2>(acc, parity, a.w.partials, a.w.stride, c);
+        } else if (WANT_F) {
+            const double acc[1] = {fsum};
+            red::chunk_flush<1>(acc, parity, a.w.partials, a.w.stride, c);
+        } else if (WANT_GP) {
+            const double acc[1] = {gpsum};
+            red::chunk_flush<1>(acc, parity, a.w.partials, a.w.stride, c);
+        }
     }
 }
 
 // ------------------------------------------------------------------ device-resident line search (flgpu_search_fn)
 // The whole Wolfe / Strong-Wolfe search in ONE cooperative kernel.  Every thread of every block runs the same state
 // machine (SearchCore, the source the host driver compiles too) on the same values, so control flow is uniform across
-// the grid; an evaluation is this thread's share of the units (objective_accumulate, as in objective_kernel), the
-// block tree, one grid-wide barrier, and the fixed-order sum over blocks -- repeated by every block, which saves the
-// second barrier a broadcast would need.  Partials are double-buffered on the evaluation parity: a block can be at
-// most one evaluation ahead of the slowest reader.  Launch geometry equals objective_kernel's, so f and f'.p carry
-// the same bits as on the host-driven fused path and both paths take the same decisions.
+// the grid; an evaluation is this block's chunks (objective_chunk, as in objective_kernel), one grid-wide barrier, and
+// the tree over the chunk sums (flgpu_reduce.cuh) -- repeated by every block, which saves the second barrier a
+// broadcast would need.  Chunk sums are double-buffered on the evaluation parity: a block can be at most one
+// evaluation ahead of the slowest reader.  Chunk sums and tree are those of objective_kernel + tree_kernel, so f and
+// f'.p carry the same bits as on the host-driven fused path and both paths take the same decisions.
 struct SearchKArgs {
-    ObjArgs o;              // x = x0, p, x_out / g = accepted point / gradient; a is set per evaluation
+    ObjArgs o;              // x = x0, p, x_out / g = accepted point / gradient; a is set per evaluation;
+                            // o.w.partials: rows [2 * parity + i]
     double c1, c2abs, fx0, phid0, incr, a0;
-    int strong, fdwithf;
-    double *partials;       // [2][gridDim.x][2]
+    int strong, fdwithf, store;   // store = 0: the caller's K1 forms and stores the accepted point itself
     double *result;         // FLGPU_SEARCH_RESULT_DOUBLES
     // row-sharded runs: the rank exchange happens inside the kernel (block 0) over the search mailboxes
     PeerTable peers;
     int me, G;
     unsigned long long *dseq;   // this rank's sequence counter for those mailboxes (device memory)
-    double *glob;               // [2][2] rank-summed values for the other blocks
+    double *glob;               // [2][2] rank-combined values for the other blocks
+    unsigned long long timeout_ns;
 };
 
 constexpr double kEvalBudget = 100000.0;
@@ -241,17 +282,15 @@ constexpr double kEvalBudget = 100000.0;
 template <int KIND>
 struct DevSearch : SearchCore<DevSearch<KIND>> {
     const SearchKArgs &K;
-    const double *tab;
-    double (*sh)[kThreads / 32];   // [2][8] block scratch
-    double *bc;                    // [2] block broadcast
+    const ObjIndex &ix;
+    double *rsh;                   // red::kWarps + red::kTopMax doubles of block scratch
     double f_cur = 0.0, gp_cur = 0.0, a_x = 0.0, a_g = 0.0;
     bool have_x = false, have_g = false;
-    int parity = 0;
+    int parity = 0, fpar = 0;
     double trials = 0.0, n_f = 0.0, n_fd = 0.0, n_ffd = 0.0, n_fonly = 0.0;
     unsigned long long seq_base = 0, nexch = 0;   // exchanges made so far (uniform over the grid)
 
-    __device__ DevSearch(const SearchKArgs &k, const double *t, double (*s)[kThreads / 32], double *b)
-        : K(k), tab(t), sh(s), bc(b) {
+    __device__ DevSearch(const SearchKArgs &k, const ObjIndex &i, double *s) : K(k), ix(i), rsh(s) {
         if (K.G > 1) seq_base = *K.dseq;
     }
 
@@ -260,40 +299,37 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
         constexpr int NACC = (F && GP) ? 2 : 1;
         ObjArgs o = K.o;
         o.a = a_x;
-        double fsum = 0.0, gpsum = 0.0;
-        objective_accumulate<KIND, true, F, GP, false, false>(o, tab, fsum, gpsum);
-        double acc[2] = {F ? fsum : gpsum, gpsum};
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int i = 0; i < NACC; i++) {
-            const double v = warp_sum(acc[i]);
-            if (lane == 0) sh[i][warp] = v;
-        }
-        __syncthreads();
-        double *part = K.partials + (size_t)parity * gridDim.x * 2;
-        if (threadIdx.x < NACC) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
-            part[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+        const Chunks C(o.n, o.ch);
+        double *rows = o.w.partials + (int64_t)(2 * parity) * o.w.stride;
+        for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+            double fsum = 0.0, gpsum = 0.0;
+            objective_chunk<KIND, true, F, GP, false, false>(o, ix, C, c, fsum, gpsum);
+            if (NACC == 2) {
+                const double acc[2] = {fsum, gpsum};
+                red::chunk_flush<2>(acc, fpar, rows, o.w.stride, c);
+            } else {
+                const double acc[1] = {F ? fsum : gpsum};
+                red::chunk_flush<1>(acc, fpar, rows, o.w.stride, c);
+            }
         }
         __threadfence();
         cooperative_groups::this_grid().sync();
-        if (warp < NACC) {
-            double s = 0.0;
-            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&part[(size_t)b * 2 + warp]);
-            s = warp_sum(s);
-            if (lane == 0) bc[warp] = s;
+        double v[2] = {0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < NACC; i++) {
+            v[i] = red::cta_root(rows + (int64_t)i * o.w.stride, C.nchunks, rsh);
+            __syncthreads();
         }
-        __syncthreads();
         if (K.G > 1) {
-            // every block holds this rank's sums; block 0 trades them with the other ranks (stores into their
-            // mailboxes, flags, rank-ordered sum) and a second barrier hands the result to the rest of the grid
+            // every block holds this rank's roots; block 0 trades them with the other ranks (stores into their
+            // mailboxes, flags, rank tree) and a second barrier hands the result to the rest of the grid
             nexch++;
             double *gl = K.glob + parity * 2;
             if (blockIdx.x == 0) {
-                __shared__ double summed[2];
-                mailbox_exchange_block(K.peers, K.me, K.G, seq_base + nexch, bc, NACC, summed);
+                __shared__ double mine[2], summed[2];
+                if (threadIdx.x < NACC) mine[threadIdx.x] = v[threadIdx.x];
+                __syncthreads();
+                mailbox_exchange_block(K.peers, K.me, K.G, seq_base + nexch, mine, NACC, summed, K.timeout_ns);
                 if (threadIdx.x < NACC) gl[threadIdx.x] = summed[threadIdx.x];
                 __threadfence();
             }
@@ -301,10 +337,9 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
             if (F) f_cur = __ldcg(&gl[0]);
             if (GP) gp_cur = __ldcg(&gl[NACC - 1]);
         } else {
-            if (F) f_cur = bc[0];
-            if (GP) gp_cur = bc[NACC - 1];
+            if (F) f_cur = v[0];
+            if (GP) gp_cur = v[NACC - 1];
         }
-        __syncthreads();
         parity ^= 1;
     }
     __device__ void form(double step) { a_x = step; have_x = true; trials += 1.0; }
@@ -324,25 +359,29 @@ struct DevSearch : SearchCore<DevSearch<KIND>> {
 // FAST = the FLGPU_LS_FAST searcher (SearchCore::fast); a template parameter so that the reference-exact kernel's code
 // and register allocation do not depend on it
 template <int KIND, bool FAST>
-__global__ void __launch_bounds__(kThreads, 4) search_kernel(SearchKArgs K) {
+__global__ void __launch_bounds__(kThreads, 3) search_kernel(SearchKArgs K) {
     __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
-    __shared__ double sh[2][kThreads / 32];
-    __shared__ double bc[2];
-    load_tables<KIND>(K.o, tab);
-    DevSearch<KIND> S(K, tab, sh, bc);
+    __shared__ double rsh[red::kWarps + red::kTopMax];
+    const ObjIndex ix = load_tables<KIND>(K.o.offset, K.o.n_global, K.o.scale, K.o.tables, tab, kThreads);
+    DevSearch<KIND> S(K, ix, rsh);
     S.c1 = K.c1; S.c2abs = K.c2abs; S.fx0 = K.fx0; S.phid0 = K.phid0; S.incr = K.incr;
     S.fdwithf = K.fdwithf != 0; S.a = K.a0; S.f_cur = K.fx0; S.pre = 0;
     if (FAST) S.fast(K.strong != 0);
     else if (K.strong) S.strongwolfe(); else S.wolfe();
     // the point and gradient the reference leaves in x / fdx
     ObjArgs o = K.o;
+    const Chunks C(o.n, o.ch);
     double f0 = 0.0, g0 = 0.0;
-    if (S.have_x && S.have_g && S.a_x == S.a_g) {
-        o.a = S.a_x;
-        objective_accumulate<KIND, true, false, false, true, true>(o, tab, f0, g0);
-    } else {                                       // never taken by the reference's searchers; kept for fidelity
-        if (S.have_x) { o.a = S.a_x; objective_accumulate<KIND, true, false, false, true, false>(o, tab, f0, g0); }
-        if (S.have_g) { o.a = S.a_g; objective_accumulate<KIND, true, false, false, false, true>(o, tab, f0, g0); }
+    if (K.store) {
+        for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+            if (S.have_x && S.have_g && S.a_x == S.a_g) {
+                o.a = S.a_x;
+                objective_chunk<KIND, true, false, false, true, true>(o, ix, C, c, f0, g0);
+            } else {                                   // never taken by the reference's searchers; kept for fidelity
+                if (S.have_x) { o.a = S.a_x; objective_chunk<KIND, true, false, false, true, false>(o, ix, C, c, f0, g0); }
+                if (S.have_g) { o.a = S.a_g; objective_chunk<KIND, true, false, false, false, true>(o, ix, C, c, f0, g0); }
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
@@ -380,16 +419,28 @@ __global__ void __launch_bounds__(kThreads) start_kernel(int kind, unsigned long
 }  // namespace k
 
 // ---- launcher shared by both callback flavours
-static int obj_grid(int64_t n) {
-    static int sms = 0;
+static int device_sms() {
+    static std::mutex mu;
+    static std::map<int, int> sms_of;            // per device: a process may drive several GPUs
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    int &sms = sms_of[dev];
     if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
+    return sms;
+}
+// grid of a reducing kernel: one full wave of resident CTAs (`per_sm` per SM), never more blocks than chunks
+static int chunk_grid(int64_t nchunks, int per_sm) {
+    int64_t g = (int64_t)device_sms() * per_sm;
+    if (g > k::kMaxGrid) g = k::kMaxGrid;
+    return (int)(nchunks < g ? (nchunks < 1 ? 1 : nchunks) : g);
+}
+static int unit_grid(int64_t n) {
     int64_t need = (n / 2 + k::kThreads) / k::kThreads;
-    int64_t g = (int64_t)sms * 4;   // = resident CTAs per SM (__launch_bounds__(256, 4)): one full wave
+    int64_t g = (int64_t)device_sms() * 8;
     if (g > k::kMaxGrid) g = k::kMaxGrid;
     return (int)(need < g ? (need < 1 ? 1 : need) : g);
 }
@@ -400,13 +451,15 @@ void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp
                       int64_t n_global, cudaStream_t s) {
     require_aligned16(x_dev, "objective: x"); require_aligned16(p_dev, "objective: p");
     require_aligned16(x_out, "objective: x_out"); require_aligned16(g_dev, "objective: f'");
-    Scratch &sc = scratch_for(s);
+    if (n_global < n) n_global = n;
+    const int64_t ch = red::chunk_elems(n_global), nchunks = red::num_chunks(n, ch);
+    Scratch &sc = scratch_for(s, nchunks);
     k::ObjArgs a;
-    a.x = x_dev; a.p = p_dev; a.a = step; a.x_out = x_out; a.g = g_dev; a.f_out = f_dev; a.gp_out = gp_dev;
-    a.n = n; a.offset = offset; a.n_global = n_global;
+    a.x = x_dev; a.p = p_dev; a.a = step; a.x_out = x_out; a.g = g_dev;
+    a.n = n; a.offset = offset; a.n_global = n_global; a.ch = ch;
     a.scale = n_global > 1 ? 16777216.0 / (double)(n_global - 1) : 0.0;
     a.tables = sc.tables; a.w = sc.work;
-    const int grid = obj_grid(n);
+    const int grid = chunk_grid(nchunks, 4);     // = resident CTAs per SM (__launch_bounds__(256, 4)): one full wave
 #define FLGPU_OBJ_CASE(KIND, FU, F, GP, WX, WG)                                                                 \
     k::objective_kernel<KIND, FU, F, GP, WX, WG><<<grid, k::kThreads, 0, s>>>(a)
 #define FLGPU_OBJ_LAUNCH(KIND)                                                                                  \
@@ -436,6 +489,12 @@ void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp
     }
 #undef FLGPU_OBJ_LAUNCH
 #undef FLGPU_OBJ_CASE
+    // chunk sums -> this rank's roots: f in row 0 (or f'.p when only that was asked for), f'.p in the next row
+    const bool wf = (flags & FLGPU_WANT_F) != 0, wgp = (flags & FLGPU_WANT_GP) != 0;
+    if (wf || wgp) {
+        double *out[2] = {wf ? f_dev : gp_dev, gp_dev};
+        launch_tree(sc.work, nchunks, wf && wgp ? 2 : 1, out, s);
+    }
 }
 
 // 64-bit device-callback flavour
@@ -461,38 +520,36 @@ static void dev_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp,
                      (cudaStream_t)c->stream);
 }
 
-// device-resident search: same grid as the probes (bit-identical sums), capped by what can be co-resident
+// device-resident search: same chunk sums and tree as the probes (bit-identical f, f'.p); the grid is capped by what
+// can be co-resident (any grid gives the same bits: the chunk sums do not depend on which block forms them)
 template <int KIND, bool FAST>
 static void dev_search_policy(const flgpu_eval_ctx *c, const flgpu_search_args *A, int64_t n) {
     cudaStream_t s = (cudaStream_t)c->stream;
-    Scratch &sc = scratch_for(s);
-    static int resident = 0, sms = 0;
-    if (!resident) {
-        int dev = 0;
-        FLGPU_CUDA_CHECK(cudaGetDevice(&dev));
-        FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::search_kernel<KIND, FAST>, k::kThreads, 0));
-        int coop = 0;
-        FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-        if (!coop || resident < 1) fatal("device-resident line search needs cooperative kernel launch");
-    }
-    int grid = obj_grid(n);
-    if (grid > resident * sms) grid = resident * sms;
+    const int64_t n_global = c->n_global < n ? n : c->n_global;
+    const int64_t ch = red::chunk_elems(n_global), nchunks = red::num_chunks(n, ch);
+    Scratch &sc = scratch_for(s, nchunks);
+    int dev = 0, resident = 0, coop = 0;
+    FLGPU_CUDA_CHECK(cudaGetDevice(&dev));
+    FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::search_kernel<KIND, FAST>, k::kThreads, 0));
+    FLGPU_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop || resident < 1) fatal("device-resident line search needs cooperative kernel launch");
+    int grid = chunk_grid(nchunks, 4);
+    if (grid > resident * device_sms()) grid = resident * device_sms();
     k::SearchKArgs K;
-    K.o.x = A->x0_dev; K.o.p = A->p_dev; K.o.a = 0.0; K.o.x_out = A->x_out; K.o.g = A->g_out; K.o.f_out = nullptr;
-    K.o.gp_out = nullptr; K.o.n = n; K.o.offset = c->offset; K.o.n_global = c->n_global;
-    K.o.scale = c->n_global > 1 ? 16777216.0 / (double)(c->n_global - 1) : 0.0;
-    K.o.tables = sc.tables; K.o.w = sc.work;
+    K.o.x = A->x0_dev; K.o.p = A->p_dev; K.o.a = 0.0; K.o.x_out = A->x_out; K.o.g = A->g_out;
+    K.o.n = n; K.o.offset = c->offset; K.o.n_global = n_global; K.o.ch = ch;
+    K.o.scale = n_global > 1 ? 16777216.0 / (double)(n_global - 1) : 0.0;
+    K.o.tables = sc.tables; K.o.w = sc.work;       // rows 0..3: [evaluation parity][f, f'.p]
     K.c1 = A->c1; K.c2abs = A->c2abs; K.fx0 = A->fx0; K.phid0 = A->phid0; K.incr = A->incr; K.a0 = A->a;
-    K.strong = A->strong; K.fdwithf = A->fdwithf;
-    K.partials = sc.work.partials;      // [2][grid][2] doubles at the front of the kMaxGrid * 8 ...
-    K.glob = sc.work.partials + (size_t)k::kMaxGrid * 8 - 4;   // ... and the 4 at its very end
+    K.strong = A->strong; K.fdwithf = A->fdwithf; K.store = A->no_store ? 0 : 1;
+    K.glob = sc.work.blockvals + (size_t)(kScratchRows - 1) * red::kTopMax;   // 4 doubles nobody else uses during a search
     K.result = A->result_dev;
     const flgpu_comm *comm = (const flgpu_comm *)A->comm;
-    K.G = 1; K.me = 0; K.dseq = nullptr;
+    K.G = 1; K.me = 0; K.dseq = nullptr; K.timeout_ns = 0;
     if (comm && comm->nranks > 1) {
         if (!comm->p2p) fatal("device-resident line search on row shards needs the peer-memory exchange");
         K.peers = comm->peers_search; K.me = comm->rank; K.G = comm->nranks; K.dseq = &comm->local->dseq;
+        K.timeout_ns = comm->timeout_ns;
     }
     void *params[] = {&K};
     FLGPU_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k::search_kernel<KIND, FAST>, dim3(grid), dim3(k::kThreads), params, 0, s));
@@ -506,7 +563,7 @@ static void dev_search(const flgpu_eval_ctx *c, const flgpu_search_args *A, int6
 // reference-ABI flavour: device x / f' pointers, host f, runs on the current call's stream
 static double ref_eval(int kind, bool want_f, double *g, const double *x, int dim) {
     cudaStream_t s = (cudaStream_t)flgpu_current_stream();
-    Scratch &sc = scratch_for(s);
+    Scratch &sc = scratch_for(s, 1);
     launch_objective(kind, false, (want_f ? FLGPU_WANT_F : 0) | (g ? FLGPU_WRITE_G : 0), want_f ? sc.scalar : nullptr,
                      nullptr, nullptr, g, x, nullptr, 0.0, dim, 0, dim, s);
     if (!want_f) return 0.0;
@@ -569,23 +626,42 @@ extern "C" int flgpu_fill_start(int start_kind, uint64_t seed, double *x_dev, in
     return 0;
 }
 
-extern "C" int flgpu_reduction_workspace(void *stream, double **partials, unsigned int **ticket, int *max_blocks) {
+extern "C" int flgpu_reduction_workspace(void *stream, int64_t nchunks, double **partials, int64_t *stride) {
     require_device();
-    Scratch &sc = scratch_for((cudaStream_t)stream);
+    Scratch &sc = scratch_for((cudaStream_t)stream, nchunks < 1 ? 1 : nchunks);
     *partials = sc.work.partials;
-    *ticket = sc.work.ticket;
-    *max_blocks = k::kMaxGrid;
+    *stride = sc.work.stride;
     return 0;
 }
 
-extern "C" int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *out_dev, void *stream) {
+extern "C" int flgpu_reduce_tree(void *stream, int64_t nchunks, int nrows, double *const *out_dev) {
+    require_device();
+    if (nrows < 1 || nrows > kScratchRows) fatal("flgpu_reduce_tree: between 1 and 8 rows");
+    Scratch &sc = scratch_for((cudaStream_t)stream, nchunks < 1 ? 1 : nchunks);
+    launch_tree(sc.work, nchunks < 1 ? 1 : nchunks, nrows, out_dev, (cudaStream_t)stream);
+    FLGPU_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int64_t flgpu_chunk_elems(int64_t n_global) { return red::chunk_elems(n_global); }
+
+// a.b over a shard of a vector of n_global elements: this rank's root of the partition-independent tree
+extern "C" int flgpu_vec_dot_sharded(const double *a_dev, const double *b_dev, int64_t n, int64_t n_global, double *out_dev,
+                                     void *stream) {
     require_device();
     require_aligned16(a_dev, "flgpu_vec_dot: a"); require_aligned16(b_dev, "flgpu_vec_dot: b");
     cudaStream_t s = (cudaStream_t)stream;
-    Scratch &sc = scratch_for(s);
-    k::dot_kernel<<<obj_grid(n), k::kThreads, 0, s>>>(a_dev, b_dev, n, sc.work, out_dev, 0);
+    if (n_global < n) n_global = n;
+    const int64_t ch = red::chunk_elems(n_global), nchunks = red::num_chunks(n, ch);
+    Scratch &sc = scratch_for(s, nchunks);
+    k::dot_kernel<<<chunk_grid(nchunks, 8), k::kThreads, 0, s>>>(a_dev, b_dev, n, ch, sc.work, 0);
+    double *out[1] = {out_dev};
+    launch_tree(sc.work, nchunks, 1, out, s);
     FLGPU_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+extern "C" int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *out_dev, void *stream) {
+    return flgpu_vec_dot_sharded(a_dev, b_dev, n, n, out_dev, stream);
 }
 
 extern "C" int flgpu_vec_trial(double *x_dev, const double *x0_dev, const double *p_dev, double a, int64_t n,
@@ -593,7 +669,7 @@ extern "C" int flgpu_vec_trial(double *x_dev, const double *x0_dev, const double
     require_device();
     require_aligned16(x_dev, "flgpu_vec_trial: x"); require_aligned16(x0_dev, "flgpu_vec_trial: x0");
     require_aligned16(p_dev, "flgpu_vec_trial: p");
-    k::trial_kernel<<<obj_grid(n), k::kThreads, 0, (cudaStream_t)stream>>>(x_dev, x0_dev, p_dev, a, n);
+    k::trial_kernel<<<unit_grid(n), k::kThreads, 0, (cudaStream_t)stream>>>(x_dev, x0_dev, p_dev, a, n);
     FLGPU_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -101,6 +101,7 @@ typedef struct flgpu_search_args {
     double *result_dev;
     flgpu_comm *comm;               /* row-sharded runs: the communicator whose search mailboxes carry the exchanges */
     int policy;                     /* FLGPU_LS_REFERENCE: the reference's searchers; FLGPU_LS_FAST: SearchCore::fast(strong) */
+    int no_store;                   /* 1: leave x_out / g_out alone (the caller's fused K1 forms the accepted point itself) */
 } flgpu_search_args;
 typedef void (*flgpu_search_fn)(const flgpu_eval_ctx *ctx, const flgpu_search_args *args, int64_t n_local);
 
@@ -365,6 +366,9 @@ int flgpu_fill_start(int start_kind, uint64_t seed, double *x_dev, int64_t offse
  * for users writing device callbacks.  All enqueue on `stream`; *_dev outputs are device
  * scalars.  Replaces the dot_product / array-expression sites of f90:591-606,1482,1485. */
 int flgpu_vec_dot(const double *a_dev, const double *b_dev, int64_t n, double *out_dev, void *stream);
+/* the same over one shard (n local rows) of a vector of n_global rows: this rank's root of the tree above */
+int flgpu_vec_dot_sharded(const double *a_dev, const double *b_dev, int64_t n, int64_t n_global, double *out_dev,
+                          void *stream);
 int flgpu_vec_trial(double *x_dev, const double *x0_dev, const double *p_dev, double a, int64_t n,
                     void *stream); /* x = x0 + a*p, multiply then add (no FMA), f90:1482 */
 
@@ -381,10 +385,19 @@ int flgpu_history_direction(flgpu_history *h, const double *g1_dev, const double
                             double *xt_dev, double *gp, double *pp);
 void flgpu_history_destroy(flgpu_history *h);
 
-/* Reduction work space private to `stream` (library-owned; valid until the stream's scratch is released): room
- * for 8 partial sums from each of *max_blocks thread blocks, and the zero-initialised ticket counter of the
- * "last block finishes" scheme.  Used by include/flgpu_objective.cuh; kernels sharing it must be stream-ordered. */
-int flgpu_reduction_workspace(void *stream, double **partials, unsigned int **ticket, int *max_blocks);
+/* ------------------------------------------------------------------ reductions (include/flgpu_reduce.cuh) */
+/* Every sum the library forms is deterministic and PARTITION-INDEPENDENT: the vector is cut into chunks of
+ * flgpu_chunk_elems(n_global) consecutive elements, a thread block sums one chunk in a fixed order, and the chunk
+ * sums are combined by the aligned binary tree over the chunk index, then over the rank index.  Shards that hold the
+ * same power-of-two number of whole chunks (any power-of-two dimension on 1, 2, 4, 8 GPUs) therefore give the bits
+ * of the single-GPU run; other partitions give a deterministic, rank-identical sum.
+ * Kernels written with flgpu_reduce.cuh (flgpu_objective.cuh does) store chunk sums into the work space of their
+ * stream -- 8 rows, row r at partials + r * *stride, each with room for at least `nchunks` values -- and call
+ * flgpu_reduce_tree(), which enqueues the tree kernel: root of row r -> out_dev[r] (device pointers, NULL = skip).
+ * The work space is library-owned and valid until the stream's scratch is released; users must be stream-ordered. */
+int64_t flgpu_chunk_elems(int64_t n_global);
+int flgpu_reduction_workspace(void *stream, int64_t nchunks, double **partials, int64_t *stride);
+int flgpu_reduce_tree(void *stream, int64_t nchunks, int nrows, double *const *out_dev);
 
 /* ------------------------------------------------------------------ device memory helpers */
 /* Thin wrappers (cudaMalloc / cudaFree / cudaMemcpyAsync + stream sync) so that C, Fortran

@@ -5,7 +5,7 @@
 // (flgpu_fused_fn, flgpu.h).  For objectives that are sums of terms over single elements or over pairs
 // (x_{2j}, x_{2j+1}) -- the quartic of the reference's own tests, extended Rosenbrock, diagonal quadratics, any
 // separable loss -- this header generates f, fd, f_fd AND the fused evaluation from one functor, with the library's
-// deterministic reduction (fixed per-thread order, shuffle butterfly, fixed-order sum over blocks by the last block).
+// deterministic, partition-independent reduction (include/flgpu_reduce.cuh: fixed chunks, aligned binary tree).
 //
 //   struct Quartic {                                   // f = sum x^4 (test/test.f90:630-663)
 //       static constexpr int WIDTH = 1;                // 1: element-local, 2: pairs (x_{2j}, x_{2j+1})
@@ -30,68 +30,31 @@
 #include <cuda_runtime.h>
 
 #include "flgpu.h"
+#include "flgpu_reduce.cuh"
 #include "flgpu_search_core.hpp"
 
 namespace flgpu_obj {
 
-constexpr int kThreads = 256;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// block tree + last-block finish; out[i] receives accumulator i (fixed order: bitwise repeatable)
-template <int NACC>
-__device__ __forceinline__ void reduce_to(double (&acc)[NACC], double *(&out)[NACC], double *partials,
-                                          unsigned int *ticket) {
-    __shared__ double sh[NACC][kThreads / 32];
-    __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NACC; i++) {
-        const double v = warp_sum(acc[i]);
-        if (lane == 0) sh[i][warp] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < NACC) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
-        partials[(size_t)blockIdx.x * NACC + threadIdx.x] = s;
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    if (warp < NACC) {
-        double s = 0.0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * NACC + warp]);
-        s = warp_sum(s);
-        if (lane == 0) *out[warp] = s;
-    }
-    if (threadIdx.x == 0) *ticket = 0u;
-}
+namespace red = flgpu::red;
+constexpr int kThreads = red::kThreads;
 
 struct Args {
     const double *x;      // the point, or x0 when FUSED
     const double *p;      // FUSED
     double a;             // FUSED
-    double *x_out, *g_out, *f_out, *gp_out;
-    int64_t n, offset;
-    double *partials;
-    unsigned int *ticket;
+    double *x_out, *g_out;
+    int64_t n, offset, ch;   // local rows, global index of row 0, chunk elements (flgpu_chunk_elems(n_global))
+    double *partials;        // chunk sums: f -> row 0 (or the only row), f'.p -> the next row
+    int64_t stride;
 };
 
-// this thread's share of the units, in grid-stride order (shared by objective_kernel and search_kernel: same bits)
+// One CHUNK of an evaluation (flgpu_reduce.cuh): this thread's 16-byte units of chunk c in order (shared by
+// objective_kernel and search_kernel: same chunk sums, same bits)
 template <class Obj, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
-__device__ __forceinline__ void accumulate(const Obj &obj, const Args &a, double &fsum, double &gpsum) {
-    const int64_t nu = a.n >> 1;
-    const int64_t stride = (int64_t)gridDim.x * kThreads;
-    for (int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x; u < nu; u += stride) {
+__device__ __forceinline__ void chunk(const Obj &obj, const Args &a, int64_t c, int64_t nchunks, double &fsum, double &gpsum) {
+    const int64_t nu = a.n >> 1, cu = a.ch >> 1;
+    const int64_t lo = c * cu, hi = (lo + cu < nu) ? lo + cu : nu;
+    for (int64_t u = lo + threadIdx.x; u < hi; u += kThreads) {
         double2 x = __ldg(reinterpret_cast<const double2 *>(a.x) + u), pv = make_double2(0.0, 0.0);
         if (FUSED) {
             pv = __ldg(reinterpret_cast<const double2 *>(a.p) + u);
@@ -114,7 +77,7 @@ __device__ __forceinline__ void accumulate(const Obj &obj, const Args &a, double
         if (WRITE_G) reinterpret_cast<double2 *>(a.g_out)[u] = g;
         if (WANT_GP) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
     }
-    if ((a.n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // last element of an odd-length shard
+    if ((a.n & 1) && c == nchunks - 1 && threadIdx.x == 0) {   // last element of an odd-length shard
         const int64_t k = a.n - 1;
         double x = a.x[k], pv = 0.0, f = 0.0, g = 0.0;
         if (FUSED) {
@@ -132,33 +95,33 @@ __device__ __forceinline__ void accumulate(const Obj &obj, const Args &a, double
 
 template <class Obj, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
 __global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a) {
-    double fsum = 0.0, gpsum = 0.0;
-    accumulate<Obj, FUSED, WANT_F, WANT_GP, WRITE_X, WRITE_G>(obj, a, fsum, gpsum);
-    if (WANT_F && WANT_GP) {
-        double acc[2] = {fsum, gpsum};
-        double *out[2] = {a.f_out, a.gp_out};
-        reduce_to<2>(acc, out, a.partials, a.ticket);
-    } else if (WANT_F) {
-        double acc[1] = {fsum};
-        double *out[1] = {a.f_out};
-        reduce_to<1>(acc, out, a.partials, a.ticket);
-    } else if (WANT_GP) {
-        double acc[1] = {gpsum};
-        double *out[1] = {a.gp_out};
-        reduce_to<1>(acc, out, a.partials, a.ticket);
+    const int64_t nchunks = red::num_chunks(a.n, a.ch);
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        double fsum = 0.0, gpsum = 0.0;
+        chunk<Obj, FUSED, WANT_F, WANT_GP, WRITE_X, WRITE_G>(obj, a, c, nchunks, fsum, gpsum);
+        if (WANT_F && WANT_GP) {
+            const double acc[2] = {fsum, gpsum};
+            red::chunk_flush<2>(acc, parity, a.partials, a.stride, c);
+        } else if (WANT_F) {
+            const double acc[1] = {fsum};
+            red::chunk_flush<1>(acc, parity, a.partials, a.stride, c);
+        } else if (WANT_GP) {
+            const double acc[1] = {gpsum};
+            red::chunk_flush<1>(acc, parity, a.partials, a.stride, c);
+        }
     }
 }
 
 // ---- device-resident line search (flgpu_search_fn) for functor objectives: the whole Wolfe / Strong-Wolfe search in
 // one cooperative kernel.  Every thread runs the same SearchCore state machine (flgpu_search_core.hpp, the source the
-// host driver compiles) on the same values; an evaluation = accumulate() + block tree + one grid barrier + the
-// fixed-order sum over blocks, repeated by every block.  Same grid as objective_kernel => same bits as the host-driven
-// fused search => same decisions.  Single GPU (row-sharded runs fall back to the host-driven search).
+// host driver compiles) on the same values; an evaluation = this block's chunks + one grid barrier + the tree over the
+// chunk sums, repeated by every block.  Same chunk sums and tree as objective_kernel + flgpu_reduce_tree => same bits
+// as the host-driven fused search => same decisions.  Single GPU (row-sharded runs fall back to the host-driven search).
 struct SearchArgs {
-    Args o;                                  // x = x0; x_out / g_out = accepted point / gradient
+    Args o;                                  // x = x0; x_out / g_out = accepted point / gradient; partials rows [2*parity + i]
     double c1, c2abs, fx0, phid0, incr, a0;
-    int strong, fdwithf;
-    double *partials;                        // [2][gridDim.x][2]
+    int strong, fdwithf, store;
     double *result;
 };
 
@@ -168,48 +131,40 @@ template <class Obj>
 struct DevSearch : flgpu::SearchCore<DevSearch<Obj>> {
     const Obj &obj;
     const SearchArgs &K;
-    double (*sh)[kThreads / 32];
-    double *bc;
+    double *rsh;                             // red::kWarps + red::kTopMax doubles of block scratch
     double f_cur = 0.0, gp_cur = 0.0, a_x = 0.0, a_g = 0.0;
     bool have_x = false, have_g = false;
-    int parity = 0;
+    int parity = 0, fpar = 0;
     double trials = 0.0, n_f = 0.0, n_fd = 0.0, n_ffd = 0.0, n_fonly = 0.0;
-    __device__ DevSearch(const Obj &o, const SearchArgs &k, double (*s)[kThreads / 32], double *b)
-        : obj(o), K(k), sh(s), bc(b) {}
+    __device__ DevSearch(const Obj &o, const SearchArgs &k, double *s) : obj(o), K(k), rsh(s) {}
     template <bool F, bool GP>
     __device__ void eval() {
         constexpr int NACC = (F && GP) ? 2 : 1;
         Args o = K.o;
         o.a = a_x;
-        double fsum = 0.0, gpsum = 0.0;
-        accumulate<Obj, true, F, GP, false, false>(obj, o, fsum, gpsum);
-        double acc[2] = {F ? fsum : gpsum, gpsum};
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int i = 0; i < NACC; i++) {
-            const double v = warp_sum(acc[i]);
-            if (lane == 0) sh[i][warp] = v;
-        }
-        __syncthreads();
-        double *part = K.partials + (size_t)parity * gridDim.x * 2;
-        if (threadIdx.x < NACC) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < kThreads / 32; q++) s += sh[threadIdx.x][q];
-            part[(size_t)blockIdx.x * 2 + threadIdx.x] = s;
+        const int64_t nchunks = red::num_chunks(o.n, o.ch);
+        double *rows = o.partials + (int64_t)(2 * parity) * o.stride;
+        for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            double fsum = 0.0, gpsum = 0.0;
+            chunk<Obj, true, F, GP, false, false>(obj, o, c, nchunks, fsum, gpsum);
+            if (NACC == 2) {
+                const double acc[2] = {fsum, gpsum};
+                red::chunk_flush<2>(acc, fpar, rows, o.stride, c);
+            } else {
+                const double acc[1] = {F ? fsum : gpsum};
+                red::chunk_flush<1>(acc, fpar, rows, o.stride, c);
+            }
         }
         __threadfence();
         cooperative_groups::this_grid().sync();
-        if (warp < NACC) {
-            double s = 0.0;
-            for (unsigned b = lane; b < gridDim.x; b += 32) s += __ldcg(&part[(size_t)b * 2 + warp]);
-            s = warp_sum(s);
-            if (lane == 0) bc[warp] = s;
+        double v[2] = {0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < NACC; i++) {
+            v[i] = red::cta_root(rows + (int64_t)i * o.stride, nchunks, rsh);
+            __syncthreads();
         }
-        __syncthreads();
-        if (F) f_cur = bc[0];
-        if (GP) gp_cur = bc[NACC - 1];
-        __syncthreads();
+        if (F) f_cur = v[0];
+        if (GP) gp_cur = v[NACC - 1];
         parity ^= 1;
     }
     __device__ void form(double step) { a_x = step; have_x = true; trials += 1.0; }
@@ -228,22 +183,26 @@ struct DevSearch : flgpu::SearchCore<DevSearch<Obj>> {
 
 // FAST = the FLGPU_LS_FAST searcher (SearchCore::fast), a template parameter: the reference-exact kernel stays as it is
 template <class Obj, bool FAST>
-__global__ void __launch_bounds__(kThreads, 4) search_kernel(Obj obj, SearchArgs K) {
-    __shared__ double sh[2][kThreads / 32];
-    __shared__ double bc[2];
-    DevSearch<Obj> S(obj, K, sh, bc);
+__global__ void __launch_bounds__(kThreads, 3) search_kernel(Obj obj, SearchArgs K) {
+    __shared__ double rsh[red::kWarps + red::kTopMax];
+    DevSearch<Obj> S(obj, K, rsh);
     S.c1 = K.c1; S.c2abs = K.c2abs; S.fx0 = K.fx0; S.phid0 = K.phid0; S.incr = K.incr;
     S.fdwithf = K.fdwithf != 0; S.a = K.a0; S.f_cur = K.fx0; S.pre = 0;
     if (FAST) S.fast(K.strong != 0);
     else if (K.strong) S.strongwolfe(); else S.wolfe();
     Args o = K.o;
+    const int64_t nchunks = red::num_chunks(o.n, o.ch);
     double f0 = 0.0, g0 = 0.0;
-    if (S.have_x && S.have_g && S.a_x == S.a_g) {
-        o.a = S.a_x;
-        accumulate<Obj, true, false, false, true, true>(obj, o, f0, g0);
-    } else {                                  // never taken by the reference's searchers; kept for fidelity
-        if (S.have_x) { o.a = S.a_x; accumulate<Obj, true, false, false, true, false>(obj, o, f0, g0); }
-        if (S.have_g) { o.a = S.a_g; accumulate<Obj, true, false, false, false, true>(obj, o, f0, g0); }
+    if (K.store) {
+        for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+            if (S.have_x && S.have_g && S.a_x == S.a_g) {
+                o.a = S.a_x;
+                chunk<Obj, true, false, false, true, true>(obj, o, c, nchunks, f0, g0);
+            } else {                                  // never taken by the reference's searchers; kept for fidelity
+                if (S.have_x) { o.a = S.a_x; chunk<Obj, true, false, false, true, false>(obj, o, c, nchunks, f0, g0); }
+                if (S.have_g) { o.a = S.a_g; chunk<Obj, true, false, false, false, true>(obj, o, c, nchunks, f0, g0); }
+            }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
@@ -254,24 +213,33 @@ __global__ void __launch_bounds__(kThreads, 4) search_kernel(Obj obj, SearchArgs
 
 template <class Obj>
 struct Callbacks {
+    static void geometry(const flgpu_eval_ctx *ctx, int64_t n, Args &A, int64_t &nchunks) {
+        const int64_t n_global = ctx->n_global < n ? n : ctx->n_global;
+        A.ch = flgpu_chunk_elems(n_global);
+        nchunks = n > 0 ? (n + A.ch - 1) / A.ch : 1;
+        flgpu_reduction_workspace(ctx->stream, nchunks, &A.partials, &A.stride);   // per-stream, library-owned
+        A.n = n; A.offset = ctx->offset;
+    }
     template <bool FUSED, bool F, bool GP, bool WX, bool WG>
     static void launch(const flgpu_eval_ctx *ctx, double *f_dev, double *gp_dev, double *x_out, double *g_out,
                        const double *x, const double *p, double a, int64_t n) {
         cudaStream_t s = (cudaStream_t)ctx->stream;
         Args A;
-        int max_blocks = 0;
-        flgpu_reduction_workspace(ctx->stream, &A.partials, &A.ticket, &max_blocks);   // per-stream, library-owned
-        A.x = x; A.p = p; A.a = a; A.x_out = x_out; A.g_out = g_out; A.f_out = f_dev; A.gp_out = gp_dev;
-        A.n = n; A.offset = ctx->offset;
-        objective_kernel<Obj, FUSED, F, GP, WX, WG><<<grid_for(n, max_blocks), kThreads, 0, s>>>(*(const Obj *)ctx->user, A);
+        int64_t nchunks = 1;
+        geometry(ctx, n, A, nchunks);
+        A.x = x; A.p = p; A.a = a; A.x_out = x_out; A.g_out = g_out;
+        objective_kernel<Obj, FUSED, F, GP, WX, WG><<<grid_for(nchunks), kThreads, 0, s>>>(*(const Obj *)ctx->user, A);
+        if (F || GP) {                     // chunk sums -> this rank's roots (the library's tree kernel)
+            double *out[2] = {F ? f_dev : gp_dev, gp_dev};
+            flgpu_reduce_tree(ctx->stream, nchunks, (F && GP) ? 2 : 1, out);
+        }
     }
-    static int grid_for(int64_t n, int max_blocks) {
+    static int grid_for(int64_t nchunks) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int64_t need = (n / 2 + kThreads) / kThreads, grid = (int64_t)sms * 4;       // one full wave of resident CTAs
-        if (grid > max_blocks) grid = max_blocks;
-        if (need < grid) grid = need < 1 ? 1 : need;
+        int64_t grid = (int64_t)sms * 4;                                              // one full wave of resident CTAs
+        if (nchunks < grid) grid = nchunks < 1 ? 1 : nchunks;
         return (int)grid;
     }
     static void search(const flgpu_eval_ctx *ctx, const flgpu_search_args *A, int64_t n) {
@@ -281,18 +249,16 @@ struct Callbacks {
     static void search_policy(const flgpu_eval_ctx *ctx, const flgpu_search_args *A, int64_t n) {
         if (A->comm) { std::fprintf(stderr, "flgpu_obj: the header's device-resident search is single-GPU\n"); std::abort(); }
         SearchArgs K;
-        int max_blocks = 0;
-        flgpu_reduction_workspace(ctx->stream, &K.partials, &K.o.ticket, &max_blocks);
-        K.o.partials = K.partials;
+        int64_t nchunks = 1;
+        geometry(ctx, n, K.o, nchunks);
         K.o.x = A->x0_dev; K.o.p = A->p_dev; K.o.a = 0.0; K.o.x_out = A->x_out; K.o.g_out = A->g_out;
-        K.o.f_out = nullptr; K.o.gp_out = nullptr; K.o.n = n; K.o.offset = ctx->offset;
         K.c1 = A->c1; K.c2abs = A->c2abs; K.fx0 = A->fx0; K.phid0 = A->phid0; K.incr = A->incr; K.a0 = A->a;
-        K.strong = A->strong; K.fdwithf = A->fdwithf; K.result = A->result_dev;
+        K.strong = A->strong; K.fdwithf = A->fdwithf; K.store = A->no_store ? 0 : 1; K.result = A->result_dev;
         int resident = 0, sms = 148, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, search_kernel<Obj, FAST>, kThreads, 0);
-        int grid = grid_for(n, max_blocks);
+        int grid = grid_for(nchunks);
         if (grid > resident * sms) grid = resident * sms;
         Obj obj = *(const Obj *)ctx->user;
         void *params[] = {&obj, &K};

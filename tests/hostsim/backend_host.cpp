@@ -17,6 +17,7 @@
 #include "../../fortran_library_b200/csrc/backend.hpp"
 #include "../../fortran_library_b200/csrc/driver.hpp"
 #include "../../fortran_library_b200/csrc/lbfgs_gram.hpp"
+#include "../../include/flgpu_reduce_geom.h"
 #include "../../include/flgpu_search_core.hpp"
 #include "../../oracle/oracle.h"
 
@@ -208,16 +209,12 @@ public:
         slots[flgpu::SL_GP0] = blocked_sum(n, [&](long i) { return g1[i] * p[i]; });
     }
 
-    // sum over ranks in rank order (bitwise identical on every rank)
+    // the product's rank tree (flgpu_reduce_geom.h) over the gathered per-rank values: bitwise identical on every rank
     void combine(double *v, int count) {
         if (g_nranks <= 1 || !g_allgather) return;
         std::vector<double> all((size_t)count * g_nranks);
         g_allgather(g_allgather_user, v, all.data(), count);
-        for (int i = 0; i < count; i++) {
-            double s = 0.0;
-            for (int r = 0; r < g_nranks; r++) s += all[(size_t)r * count + i];
-            v[i] = s;
-        }
+        for (int i = 0; i < count; i++) v[i] = flgpu::red::rank_tree(all.data() + i, g_nranks, count);
     }
     void fetch(double *host) override {
         syncs++;

@@ -55,9 +55,12 @@ def test_sass_is_sm_100a_fp64():
     _build()
     out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN5flgpu1k10dot_kernelEPKdS2_lNS0_4WorkEPdi", LIB],
-                          capture_output=True, text=True).stdout
-    assert "DFMA" in sass and "LDG.E.128" in sass
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    dot = sass[sass.index("dot_kernel"):]
+    dot = dot[:dot.index("Function :", 10) if "Function :" in dot[10:] else len(dot)]
+    assert "DFMA" in dot and "LDG.E.128" in dot
+    # K3 streams its columns with 1-D bulk async copies (cp.async.bulk -> UBLKCP) signalled on mbarriers
+    assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass
 
 
 def test_struct_layout_matches_ctypes(tmp_path):

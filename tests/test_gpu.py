@@ -203,6 +203,60 @@ def test_no_out_of_bounds_writes(fl, n):
     L.flgpu_history_destroy(h)
 
 
+# ----------------------------------------------------------------------------- partition-independent reductions
+def _rank_tree(vals):
+    """red::rank_tree (include/flgpu_reduce_geom.h): aligned binary tree over the rank index."""
+    v = list(vals) + [0.0] * (16 - len(vals))
+    s = 1
+    while s < 16:
+        for j in range(0, 16 - s, 2 * s):
+            v[j] = v[j] + v[j + s]
+        s *= 2
+    return v[0]
+
+
+@pytest.mark.parametrize("log2n", [13, 20, 22, 26])
+def test_reductions_do_not_depend_on_the_partition(fl, log2n):
+    """The same vector reduced as 1, 2, 4 and 8 row shards (each shard's root from the kernels, the roots combined by
+    the rank tree) gives IDENTICAL bits -- dot products and the objective value of all three built-in objectives.
+    2^13: 8 chunks (one per shard at 8 shards); 2^22: 4096 chunks = one tree block; 2^26: 8192 chunks of 8192 elements,
+    two tree blocks on one GPU against one block per shard."""
+    n = 1 << log2n
+    L = fl.lib()
+    L.flgpu_vec_dot_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(log2n)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    ad, bd, out = fl.DeviceVector.from_numpy(a), fl.DeviceVector.from_numpy(b), fl.DeviceVector(2)
+    results = {}
+    for G in (1, 2, 4, 8):
+        m = n // G
+        roots = []
+        for r in range(G):
+            L.flgpu_vec_dot_sharded(ad.ptr + 8 * r * m, bd.ptr + 8 * r * m, m, n, out.ptr, None)
+            roots.append(out.numpy()[0])
+        results[G] = _rank_tree(roots)
+    assert results[1] == results[2] == results[4] == results[8], results
+    assert abs(results[1] - math.fsum(a * b)) <= 4e-16 * float(np.sum(np.abs(a * b)))
+    for name in ("quartic", "rosenR1", "diag"):
+        kind = _cases.OBJECTIVES[name][0]
+        prob = fl.builtin_problem(kind)
+        fused = C.cast(prob.fused, fl.capi.FUSED_FN)
+        x0 = _cases.start(name, n) + 0.01 * a
+        x0d = fl.DeviceVector.from_numpy(x0)
+        res = {}
+        for G in (1, 2, 4, 8):
+            m = n // G
+            fs, gps = [], []
+            for r in range(G):
+                ctx = fl.capi.EvalCtx(None, None, r * m, n, r, G, 0)
+                fused(C.byref(ctx), fl.capi.WANT_F | fl.capi.WANT_GP, out.ptr, out.ptr + 8, None, None, x0d.ptr + 8 * r * m,
+                      bd.ptr + 8 * r * m, 0.125, m)
+                o = out.numpy()
+                fs.append(o[0]); gps.append(o[1])
+            res[G] = (_rank_tree(fs), _rank_tree(gps))
+        assert res[1] == res[2] == res[4] == res[8], (name, res)
+
+
 # ----------------------------------------------------------------------------- parity: strict tier
 @pytest.mark.parametrize("name,mem", [("rosenR1", 10), ("rosenR1", 3), ("quartic", 10), ("diag", 30), ("rosenR0", 5),
                                       ("quartic", 1), ("rosenR1", 17)])
