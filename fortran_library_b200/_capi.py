@@ -33,7 +33,8 @@ FUSED_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_int, C.c_void_p, C.c_void_p
 
 class Problem(C.Structure):
     _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p),
-                ("fused", C.c_void_p), ("search", C.c_void_p), ("search_caps", C.c_int)]
+                ("fused", C.c_void_p), ("search", C.c_void_p), ("search_caps", C.c_int),
+                ("update", C.c_void_p)]
 
 
 class IterInfo(C.Structure):

@@ -270,7 +270,7 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
 
     flgpu_problem L;
     L.f = al_f; L.fd = al_fd; L.f_fd = al_ffd;       // the reference always passes f_fd = L_Ld / L_Ld_fdwithf
-    L.user = &S; L.fused = nullptr; L.search = nullptr; L.search_caps = 0;
+    L.user = &S; L.fused = nullptr; L.search = nullptr; L.search_caps = 0; L.update = nullptr;
     flgpu_eval_ctx ctx;
     ctx.user = prob->user; ctx.stream = (void *)s; ctx.offset = in.offset; ctx.n_global = in.n_global ? in.n_global : n;
     ctx.rank = S.comm ? S.comm->rank : 0; ctx.nranks = G; ctx.device = dev;
@@ -380,6 +380,7 @@ void __nonlinearoptimization_MOD_augmentedlagrangian(
     ref_adapter_init(U.obj, f, fd, f_fd, *N, &prob);
     prob.user = &U;                                   // RefAdapter is the first member: ad_f / ad_fd / ad_ffd still work
     prob.fused = nullptr;
+    prob.update = nullptr;
     U.con.c = c; U.con.cd = cd; U.con.cb_space = U.obj.cb_space; U.con.N = *N; U.con.M = *M;
     FLGPU_CUDA_CHECK(cudaMallocHost((void **)&U.con.ch, sizeof(double) * (size_t)(*M > 0 ? *M : 1)));
     if (U.con.cb_space == FLGPU_SPACE_HOST) {

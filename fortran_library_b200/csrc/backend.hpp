@@ -58,7 +58,7 @@ public:
     virtual void device_search(int /*policy: FLGPU_LS_* */, bool /*strong*/, bool /*fdwithf*/, double /*c1*/,
                                double /*c2abs*/, double /*fx0*/,
                                double /*phid0*/, double /*incr*/, double /*a*/, const double * /*x0*/,
-                               const double * /*p*/, double * /*xt*/, double * /*gt*/) {}
+                               const double * /*p*/, double * /*xt*/, double * /*gt*/, bool /*no_store*/ = false) {}
     virtual void search_result(double * /*out: FLGPU_SEARCH_RESULT_DOUBLES*/) {}
     // algorithmic bytes of the last device_search(), known only once its evaluation count is (kernel timing)
     virtual void credit_search_bytes(double /*bytes*/) {}
@@ -73,6 +73,11 @@ public:
     //     columns against g1 and y_new; g1.g1 -> SL_GG.
     virtual void lbfgs_update_dots(const double *x1, const double *x0, const double *g1,
                                    const double *g0, int new_slot, int k_after) = 0;
+    // K1 with the accepted point formed inside the kernel (flgpu_problem.update): x1 = x0 + a*p and g1 = f'(x1) are
+    // computed in registers and STORED to x1 / g1 together with the new column; same dots as lbfgs_update_dots.
+    virtual bool fused_update_available() const { return false; }
+    virtual void lbfgs_update_dots_fused(double /*a*/, const double * /*x0*/, const double * /*p*/, const double * /*g0*/,
+                                         double * /*x1*/, double * /*g1*/, int /*new_slot*/, int /*k_after*/) {}
     // K2: two-loop recursion carried out on the (2k+1)-dimensional Gram representation.
     virtual void lbfgs_solve(int k, int recent) = 0;
     // K3: p = -H g1 from the coefficients of K2, xt = x1 + p (skipped when xt is null), g1.p -> SL_GP0,

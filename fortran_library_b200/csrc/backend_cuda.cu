@@ -484,13 +484,14 @@ void CudaBackend::fused_eval(int flags, double a, const double *x0, const double
 }
 
 void CudaBackend::device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0,
-                                double incr, double a, const double *x0, const double *p, double *xt, double *gt) {
+                                double incr, double a, const double *x0, const double *p, double *xt, double *gt,
+                                bool no_store) {
     flgpu_search_args A;
     A.x0_dev = x0; A.p_dev = p; A.x_out = xt; A.g_out = gt;
     A.c1 = c1; A.c2abs = c2abs; A.fx0 = fx0; A.phid0 = phid0; A.incr = incr; A.a = a;
     A.strong = strong ? 1 : 0; A.fdwithf = fdwithf ? 1 : 0;
     A.policy = policy;
-    A.no_store = 0;
+    A.no_store = no_store ? 1 : 0;
     A.result_dev = Rsearch;
     A.comm = ctx.nranks > 1 ? comm : nullptr;
     const int t = time_begin("callback:device_search", 0.0);   // bytes depend on the trial count: see flgpu_stats
@@ -531,26 +532,12 @@ void CudaBackend::neg(double *p, const double *g) {
 int g_k1_shape[2] = {0, 0};
 namespace {
 // per-device launch facts (a process may drive several GPUs: never cache these per process)
-struct DeviceFacts { int k1_resident[8] = {0}; bool k2_attr = false; int k3_tma_attr[2] = {0, 0}; int k3_mode = -1; };
+struct DeviceFacts { bool k2_attr = false; int k3_tma_attr[16] = {0}; int k3_mode = -1; };
 DeviceFacts &facts(int device) {
     static std::mutex mu;
     static std::map<int, DeviceFacts> m;
     std::lock_guard<std::mutex> lock(mu);
     return m[device];
-}
-// grid = SMs x CTAs actually resident for this instantiation (one full wave), capped by the number of chunks
-template <int MT, int NG, class Src>
-void launch_k1(const k::K1Args &a, const Src &src, int device, int shape_id, int num_sms, int64_t nchunks, cudaStream_t s) {
-    int &resident = facts(device).k1_resident[shape_id];
-    if (!resident) {
-        FLGPU_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k::k1_update_dots_kernel<MT, NG, Src>,
-                                                                       k::kThreads, 0));
-        if (resident < 1) resident = 1;
-    }
-    int64_t grid = (int64_t)num_sms * resident;
-    if (grid > k::kMaxGrid) grid = k::kMaxGrid;
-    if (nchunks < grid) grid = nchunks < 1 ? 1 : nchunks;
-    k::k1_update_dots_kernel<MT, NG, Src><<<(int)grid, k::kThreads, 0, s>>>(a, src);
 }
 }  // namespace
 
@@ -567,6 +554,33 @@ void k1_shape_for(int rem, int &mt, int &ng) {
     // <5,2> (256-byte runs, 2 CTAs/SM) sustains 6.3-7.0 TB/s even counting the re-read of x, g per pass.
 }
 
+// The K1 passes over the k_after-1 older columns (NG*MT per pass; the first pass also builds the new column).  With a
+// fused source the first pass is launched by the objective (flgpu_problem.update); later passes read the x1, g1 it stored.
+void CudaBackend::k1_passes(k::K1Args &a, int nother, bool fused, int t) {
+    int age = 1;
+    bool first = true;
+    do {
+        k::K1Launch L;
+        a.age_base = age;
+        a.write_new = first ? 1 : 0;
+        k1_shape_for(nother - (age - 1), L.mt, L.ng);
+        L.a = a; L.num_sms = num_sms; L.nchunks = nchunks; L.stream = (void *)stream;
+        if (first && fused) {
+            flgpu_update_args ua;
+            ua.k1 = &L; ua.k1_bytes = sizeof L;
+            prob.update(&ctx, &ua, n);
+            callback_launches++;
+        } else {
+            k::launch_k1_pass(L, k::PlainSrc());
+            launches++;
+        }
+        age += L.mt * L.ng;
+        first = false;
+    } while (age - 1 < nother);
+    lbfgs_dots_tree();
+    time_end(t);
+}
+
 void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const double *g1,
                                     const double *g0, int new_slot, int k_after) {
     const int nother = k_after - 1;
@@ -575,24 +589,19 @@ void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const do
     k::K1Args a{};
     a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.S = S; a.Y = Y; a.ld = ld; a.n = n; a.ch = ch;
     a.m = mem; a.new_slot = new_slot; a.k_after = k_after; a.w = work;
-    int age = 1;
-    bool first = true;
-    // one pass covers NG*MT older columns
-    do {
-        a.age_base = age;
-        a.write_new = first ? 1 : 0;
-        int mt, ng;
-        k1_shape_for(nother - (age - 1), mt, ng);
-#define FLGPU_K1_CASE(MT, NG, ID) if (mt == MT && ng == NG) launch_k1<MT, NG, k::PlainSrc>(a, k::PlainSrc(), device, ID, num_sms, nchunks, stream); else
-        FLGPU_K1_CASE(2, 1, 0) FLGPU_K1_CASE(4, 1, 1) FLGPU_K1_CASE(5, 1, 2) FLGPU_K1_CASE(4, 2, 3) FLGPU_K1_CASE(5, 2, 4)
-        fatal("K1: unsupported (columns per group, groups) shape");
-#undef FLGPU_K1_CASE
-        launches++;
-        age += mt * ng;
-        first = false;
-    } while (age - 1 < nother);
-    lbfgs_dots_tree();
-    time_end(t);
+    k1_passes(a, nother, false, t);
+}
+
+void CudaBackend::lbfgs_update_dots_fused(double step, const double *x0, const double *p, const double *g0, double *x1,
+                                          double *g1, int new_slot, int k_after) {
+    const int nother = k_after - 1;
+    // reads x0, p, g0 and the older columns; writes x1, g1 and the new column pair
+    const int t = time_begin("k1_update_dots_fused", 8.0 * n * (2.0 * nother + 7.0));
+    k::K1Args a{};
+    a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.p = p; a.step = step; a.x1_out = x1; a.g1_out = g1;
+    a.S = S; a.Y = Y; a.ld = ld; a.n = n; a.ch = ch; a.offset = ctx.offset; a.n_global = ctx.n_global;
+    a.m = mem; a.new_slot = new_slot; a.k_after = k_after; a.w = work;
+    k1_passes(a, nother, true, t);
 }
 
 // chunk sums of all nd dots -> R[kResSlots + d]; g.g also to its result slot
@@ -634,22 +643,34 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
     a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n; a.ch = ch;
     a.m = mem; a.k = kk; a.recent = recent; a.w = work;
     DeviceFacts &f = facts(device);
-    if (f.k3_mode < 0) {                  // FLGPU_K3 = regs | tma (default) | tma4 (4 pieces x 6 stages)
+    if (f.k3_mode < 0) {
+        // FLGPU_K3 = regs (register double buffers) | tma (default: bulk-async ring, 8 pieces x 3 stages, 2 CTAs/SM) |
+        // "P,NST": another ring shape (tuning; the instantiated ones are listed below)
         const char *v = std::getenv("FLGPU_K3");
-        f.k3_mode = (v && !std::strcmp(v, "regs")) ? 0 : (v && !std::strcmp(v, "tma4")) ? 2 : 1;
+        f.k3_mode = 1;
+        if (v && !std::strcmp(v, "regs")) f.k3_mode = 0;
+        else if (v && std::strchr(v, ',')) f.k3_mode = 100 * std::atoi(v) + std::atoi(std::strchr(v, ',') + 1);
     }
     if (f.k3_mode == 0) {
         k::k3_direction_kernel<8><<<grid_for(2), k::kThreads, 0, stream>>>(a);
     } else {
-        constexpr size_t smem = 3 * 8 * k::kThreads * sizeof(double2);       // 96 KB ring: 2 CTAs per SM
-        int &attr = f.k3_tma_attr[f.k3_mode - 1];
-        if (f.k3_mode == 1) {
-            if (!attr) { FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = 1; }
-            k::k3_direction_tma_kernel<8, 3><<<grid_for(2), k::kThreads + 32, smem, stream>>>(a);
-        } else {
-            if (!attr) { FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = 1; }
-            k::k3_direction_tma_kernel<4, 6><<<grid_for(2), k::kThreads + 32, smem, stream>>>(a);
+        bool done = false;
+#define FLGPU_K3_CASE(P, NST, MINB, ID)                                                                                  \
+        if (!done && (f.k3_mode == 100 * P + NST || (ID == 0 && f.k3_mode == 1))) {                                        \
+            constexpr size_t smem = (size_t)NST * P * k::kThreads * sizeof(double2);                                       \
+            if (!f.k3_tma_attr[ID]) {                                                                                      \
+                FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<P, NST, MINB>,                            \
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+                f.k3_tma_attr[ID] = 1;                                                                                     \
+            }                                                                                                              \
+            k::k3_direction_tma_kernel<P, NST, MINB><<<grid_for(MINB), k::kThreads + 32, smem, stream>>>(a);               \
+            done = true;                                                                                                   \
         }
+        FLGPU_K3_CASE(8, 3, 2, 0) FLGPU_K3_CASE(7, 3, 2, 1) FLGPU_K3_CASE(4, 6, 2, 2) FLGPU_K3_CASE(11, 2, 2, 3)
+        FLGPU_K3_CASE(6, 4, 2, 4) FLGPU_K3_CASE(8, 6, 1, 5) FLGPU_K3_CASE(7, 7, 1, 6) FLGPU_K3_CASE(11, 4, 1, 7)
+        FLGPU_K3_CASE(5, 5, 2, 8) FLGPU_K3_CASE(9, 3, 2, 9) FLGPU_K3_CASE(4, 4, 3, 10) FLGPU_K3_CASE(7, 2, 3, 11)
+#undef FLGPU_K3_CASE
+        if (!done) fatal("FLGPU_K3: this ring shape is not instantiated");
     }
     launches++;
     double *out[2] = {R + SL_GP0, R + SL_PP};

@@ -80,7 +80,10 @@ public:
                (ctx.nranks == 1 || (comm && comm->p2p && (prob.search_caps & FLGPU_SEARCH_ROW_SHARDS)));
     }
     void device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
-                       double a, const double *x0, const double *p, double *xt, double *gt) override;
+                       double a, const double *x0, const double *p, double *xt, double *gt, bool no_store = false) override;
+    bool fused_update_available() const override { return prob.update != nullptr && prob.fused != nullptr; }
+    void lbfgs_update_dots_fused(double a, const double *x0, const double *p, const double *g0, double *x1, double *g1,
+                                 int new_slot, int k_after) override;
     void search_result(double *out) override;
     void credit_search_bytes(double bytes) override;
     void trial_x(double *x, const double *x0, const double *p, double a) override;
@@ -134,6 +137,7 @@ private:
     void alloc_work(int rows);
     void tree(int nrows, double *const *out);                    // chunk sums of rows [0, nrows) -> out[row]
     void lbfgs_dots_tree();
+    void k1_passes(k::K1Args &a, int nother, bool fused, int t);
     int work_rows = 0;
     int time_begin(const char *name, double bytes);
     void time_end(int token);

@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 
@@ -115,6 +116,8 @@ struct Search : SearchCore<Search> {
         a_x = a; have_x = true;
         if (pre == 3) { a_g = a; have_g = true; }
     }
+    // the accepted point is x0 + a_x*p and its gradient was evaluated there: the reference's searchers always end so
+    bool can_defer() const { return fused && have_x && have_g && a_x == a_g; }
     void finish() {
         if (!fused) return;
         if (have_x && have_g && a_x == a_g) {
@@ -142,12 +145,13 @@ bool use_device_search(const Params &P, Backend &B) {
 // has an f_fd callback; on the unfused path f_fd is used when present, else f then fd.
 bool fast_uses_ffd(const Params &P, Backend &B) { return P.has_f_fd || (P.fused && B.fused_available()); }
 
-// Runs one line search; on return xt/gt hold the accepted point and gradient.
-struct SearchResult { double a, fx; int64_t trials; };
+// Runs one line search; on return xt/gt hold the accepted point and gradient -- unless the caller asked to defer the
+// store (L-BFGS with flgpu_problem.update: K1 forms x0 + a*p and f' itself) and the result says `deferred`.
+struct SearchResult { double a, fx; int64_t trials; bool deferred; };
 
 SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool strong, bool fdwithf,
                          const double *x0, double *xt, double *gt, const double *p, double a,
-                         double fx0, double phid0, int pre, double pre_f, double pre_gp) {
+                         double fx0, double phid0, int pre, double pre_f, double pre_gp, bool defer_store = false) {
     Search S(B, st);
     S.x0 = x0; S.xt = xt; S.gt = gt; S.p = p;
     S.c1 = P.c1; S.c2abs = P.c2 * std::fabs(phid0); S.fx0 = fx0; S.phid0 = phid0; S.incr = P.incr;
@@ -162,7 +166,7 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     if (S.fused && pre == 0 && use_device_search(P, B)) {
         // the same SearchCore, run by every thread of one cooperative kernel; one host round trip per search
         double res[FLGPU_SEARCH_RESULT_DOUBLES], slots[NSLOTS];
-        B.device_search(P.line_search, strong, fdwithf, S.c1, S.c2abs, fx0, phid0, S.incr, a, x0, p, xt, gt);
+        B.device_search(P.line_search, strong, fdwithf, S.c1, S.c2abs, fx0, phid0, S.incr, a, x0, p, xt, gt, defer_store);
         B.fetch(slots); st.host_syncs++;
         B.search_result(res);
         st.n_trials += (int64_t)res[2]; st.n_f += (int64_t)res[3]; st.n_fd += (int64_t)res[4];
@@ -172,13 +176,14 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
             std::printf(" Line search warning: the device-resident search gave up after %.0f evaluations "
                         "(does the objective return NaN?)\n", res[3] + res[4] + res[5]);
         SearchResult r;
-        r.a = res[0]; r.fx = res[1]; r.trials = (int64_t)res[2];
+        r.a = res[0]; r.fx = res[1]; r.trials = (int64_t)res[2]; r.deferred = defer_store;
         return r;
     }
     if (fast) S.fast(strong);
     else if (strong) S.strongwolfe(); else S.wolfe();
-    S.finish();
     SearchResult r;
+    r.deferred = defer_store && S.can_defer() && S.a_x == S.a;
+    if (!r.deferred) S.finish();
     r.fx = S.fx();
     r.a = S.a;
     r.trials = S.trials;
@@ -213,6 +218,10 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
     const int mem = P.mem;
     const bool fused = P.fused && B.fused_available();
     const bool dsearch = fused && use_device_search(P, B);   // the search kernel does every trial
+    // K1 forms and stores the accepted point itself (FLGPU_FUSED_UPDATE=0: the search stores it, K1 reads it back --
+    // the same bits, 3n more doubles of traffic; kept for comparison)
+    const char *fu = std::getenv("FLGPU_FUSED_UPDATE");
+    const bool fuse_k1 = fused && B.fused_update_available() && !(fu && fu[0] == '0');
     B.lbfgs_alloc(mem);
     B.upload(xc, x_user, x_space);
 
@@ -238,26 +247,33 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             // which searcher this outer iteration uses: never _fdwithf before the main loop (f90:448-498)
             const bool in_main = it >= mem;
             const bool fdwithf = in_main && P.has_f_fd;
+            // the step after this search ends the run by count: no K1 follows, the search stores its point itself
+            const bool defer = fuse_k1 && (it + 1 < total);
             SearchResult r = line_search(B, st, P, P.strong, fdwithf && P.strong, xc, xo, go, p, a, fnew,
-                                         phid0, pre, pre_f, pre_gp);
+                                         phid0, pre, pre_f, pre_gp, defer);
             std::swap(xc, xo); std::swap(gc, go);       // accepted point becomes current; xo/go = xold/fdold
             a = r.a; fnew = r.fx;
             st.iterations = ++it;
             st.f = fnew;
-            const bool stop = observe(P, B, st, it - 1, a, fnew, phid0, r.trials, p, xc, gc);
-            // ---- After() f90:609-624 fused with the next Before() f90:586-608
-            const bool last = (it >= total) || stop;
             int new_slot, k_after;
             if (it <= mem) { new_slot = recent + 1; k_after = k + 1; }       // f90:470,508 (append)
             else { new_slot = (recent + 1) % mem; k_after = mem; }           // f90:622 (overwrite oldest)
+            // ---- After() f90:609-624 fused with the next Before() f90:586-608
+            bool k1_done = false;
+            if (r.deferred) {            // K1 with x1 = xo + a*p and f'(x1) formed in registers, stored to xc / gc
+                B.lbfgs_update_dots_fused(a, xo, p, go, xc, gc, new_slot, k_after);
+                k1_done = true;
+            }
+            const bool stop = observe(P, B, st, it - 1, a, fnew, phid0, r.trials, p, xc, gc);
+            const bool last = (it >= total) || stop;
             const bool fast = P.line_search == FLGPU_LS_FAST;
             // fast: f and f' at the first trial of every search; reference: f_fd only in the main loop (f90:448-498)
             const bool next_both = fast;
             const bool next_fdwithf = fast ? fast_uses_ffd(P, B) : (it >= mem) && P.has_f_fd && P.strong;
             if (last) {
-                B.dot(gc, gc, SL_GG);
+                if (!k1_done) B.dot(gc, gc, SL_GG);                          // (K1 delivers g.g as well)
             } else {
-                B.lbfgs_update_dots(xc, xo, gc, go, new_slot, k_after);      // K1
+                if (!k1_done) B.lbfgs_update_dots(xc, xo, gc, go, new_slot, k_after);   // K1
                 B.lbfgs_solve(k_after, new_slot);                            // K2
                 if (dsearch) {                                               // K3: new p only
                     B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);

@@ -232,6 +232,34 @@ __device__ __forceinline__ ObjIndex load_tables(int64_t offset, int64_t n_global
     return ix;
 }
 
+// K1 source for the built-in objectives (flgpu_problem.update, include/flgpu_k1.cuh): the accepted point
+// x1 = x0 + a*p (multiply, then add: f90:1482) and f'(x1) are formed in registers -- the same roundings as the fused
+// evaluation that would otherwise store them -- and stored by the column group that owns the new column.
+template <int KIND>
+struct BuiltinSrc {
+    const double *tables;
+    double scale;
+    ObjIndex ix;
+    __device__ void init(const K1Args &a) {
+        __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
+        ix = load_tables<KIND>(a.offset, a.n_global, scale, tables, tab, kThreads);
+    }
+    __device__ __forceinline__ void unit(const K1Args &a, int64_t u, bool own_new, double2 x0, double2 &x1, double2 &g1) const {
+        const double2 pv = ld2(a.p, u);
+        x1.x = add(x0.x, mul(a.step, pv.x));
+        x1.y = add(x0.y, mul(a.step, pv.y));
+        double f = 0.0;
+        objective_unit<KIND, false, true>(ix, u, x1, f, g1);
+        if (own_new) { st2(a.x1_out, u, x1); st2(a.g1_out, u, g1); }
+    }
+    __device__ __forceinline__ void tail(const K1Args &a, int64_t i, bool own_new, double x0, double &x1, double &g1) const {
+        x1 = add(x0, mul(a.step, a.p[i]));
+        double f = 0.0;
+        objective_tail<KIND, false>(ix, i, x1, f, g1);
+        if (own_new) { a.x1_out[i] = x1; a.g1_out[i] = g1; }
+    }
+};
+
 // One kernel serves the plain callbacks (f, fd, f_fd) and the fused line-search evaluation (flgpu_fused_fn).
 template <int KIND, bool FUSED, bool WANT_F, bool WANT_GP, bool WRITE_X, bool WRITE_G>
 __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
@@ -520,6 +548,19 @@ static void dev_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp,
                      (cudaStream_t)c->stream);
 }
 
+// flgpu_problem.update: the first K1 pass with the accepted point formed in the kernel
+template <int KIND>
+static void dev_update(const flgpu_eval_ctx *c, const flgpu_update_args *A, int64_t n) {
+    (void)n;
+    if (A->k1_bytes != sizeof(k::K1Launch)) fatal("flgpu_problem.update: K1Launch layout mismatch (header / library versions differ)");
+    const k::K1Launch &L = *(const k::K1Launch *)A->k1;
+    Scratch &sc = scratch_for((cudaStream_t)c->stream, 1);
+    k::BuiltinSrc<KIND> src;
+    src.tables = sc.tables;
+    src.scale = L.a.n_global > 1 ? 16777216.0 / (double)(L.a.n_global - 1) : 0.0;
+    k::launch_k1_pass(L, src);
+}
+
 // device-resident search: same chunk sums and tree as the probes (bit-identical f, f'.p); the grid is capped by what
 // can be co-resident (any grid gives the same bits: the chunk sums do not depend on which block forms them)
 template <int KIND, bool FAST>
@@ -588,9 +629,9 @@ using namespace flgpu;
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {
-    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; return 0;
-    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; return 0;
-    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; return 0;
+    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<0>; return 0;
+    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<1>; return 0;
+    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<2>; return 0;
     }
     return 1;
 }
@@ -601,6 +642,12 @@ flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f) {
     if (f == ref_f<0>) return dev_fused<0>;
     if (f == ref_f<1>) return dev_fused<1>;
     if (f == ref_f<2>) return dev_fused<2>;
+    return nullptr;
+}
+flgpu_update_fn builtin_update_for(flgpu_ref_f_fn f) {
+    if (f == ref_f<0>) return dev_update<0>;
+    if (f == ref_f<1>) return dev_update<1>;
+    if (f == ref_f<2>) return dev_update<2>;
     return nullptr;
 }
 }  // namespace flgpu

@@ -105,6 +105,20 @@ typedef struct flgpu_search_args {
 } flgpu_search_args;
 typedef void (*flgpu_search_fn)(const flgpu_eval_ctx *ctx, const flgpu_search_args *args, int64_t n_local);
 
+/* Optional FUSED ACCEPTED-POINT UPDATE (an extension; L-BFGS with a fused line search only).  After a line search the
+ * reference has x and f'(x) in memory and forms s = x - xold, y = f' - f'old and the dot products of the next
+ * two-loop recursion (f90:609-624, 590-606).  With this callback the accepted point is never stored by the search:
+ * the library's K1 kernel, instantiated by the objective with a source that forms x1 = x0 + a*p and f'(x1) in
+ * registers (include/flgpu_k1.cuh), writes x1, f'(x1), s and y and accumulates every dot in ONE pass -- 7n instead of
+ * 10n doubles per iteration, the same bits.  The callback launches exactly that pass on ctx->stream:
+ *     flgpu::k::launch_k1_pass(*(const flgpu::k::K1Launch *)args->k1, MySource{...});
+ * (libflgpu's built-in objectives and include/flgpu_objective.cuh provide it). */
+typedef struct flgpu_update_args {
+    const void *k1;     /* flgpu::k::K1Launch prepared by the library: vectors, step, ring buffers, shape, geometry */
+    size_t k1_bytes;    /* sizeof(flgpu::k::K1Launch) the library was built with (callbacks check it) */
+} flgpu_update_args;
+typedef void (*flgpu_update_fn)(const flgpu_eval_ctx *ctx, const flgpu_update_args *args, int64_t n_local);
+
 typedef struct flgpu_problem {
     flgpu_f_fn f;       /* required */
     flgpu_fd_fn fd;     /* required */
@@ -113,6 +127,7 @@ typedef struct flgpu_problem {
     flgpu_fused_fn fused; /* optional (NULL = trial points are materialised and f / fd / f_fd are called) */
     flgpu_search_fn search; /* optional (NULL = the host drives the search, one round trip per evaluation) */
     int search_caps;        /* FLGPU_SEARCH_ROW_SHARDS if `search` handles flgpu_search_args.comm != NULL; else 0 */
+    flgpu_update_fn update; /* optional, needs `fused` (NULL = the search stores the accepted point, K1 reads it back) */
 } flgpu_problem;
 
 /* ------------------------------------------------------------------ options / results */

@@ -1,4 +1,4 @@
-// lbfgs_gram.hpp -- layouts shared by K1/K2/K3 and the scalar statement of K2.
+// flgpu_lbfgs_gram.hpp -- layouts shared by K1/K2/K3 and the scalar statement of K2.
 //
 // The reference's two-loop recursion (f90:589-607) interleaves 2k+2 full-length dot products
 // with 2k full-length axpys, each dot depending on the previous axpy.  Here the recursion is

@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include "flgpu.h"
+#include "flgpu_k1.cuh"
 #include "flgpu_reduce.cuh"
 #include "flgpu_search_core.hpp"
 
@@ -211,6 +212,35 @@ __global__ void __launch_bounds__(kThreads, 3) search_kernel(Obj obj, SearchArgs
     }
 }
 
+// K1 source for functor objectives (flgpu_problem.update, flgpu_k1.cuh): x1 = x0 + a*p and f'(x1) formed in registers
+template <class Obj>
+struct FunctorSrc {
+    Obj obj;
+    __device__ void init(const flgpu::k::K1Args &) {}
+    __device__ __forceinline__ void unit(const flgpu::k::K1Args &a, int64_t u, bool own_new, double2 x0, double2 &x1,
+                                         double2 &g1) const {
+        const double2 pv = __ldg(reinterpret_cast<const double2 *>(a.p) + u);
+        x1.x = __dadd_rn(x0.x, __dmul_rn(a.step, pv.x));
+        x1.y = __dadd_rn(x0.y, __dmul_rn(a.step, pv.y));
+        const int64_t i = a.offset + 2 * u;
+        double f = 0.0;
+        if constexpr (Obj::WIDTH == 2) obj.eval2(i, x1.x, x1.y, f, g1.x, g1.y);
+        else { obj.eval(i, x1.x, f, g1.x); obj.eval(i + 1, x1.y, f, g1.y); }
+        if (own_new) {
+            reinterpret_cast<double2 *>(a.x1_out)[u] = x1;
+            reinterpret_cast<double2 *>(a.g1_out)[u] = g1;
+        }
+    }
+    __device__ __forceinline__ void tail(const flgpu::k::K1Args &a, int64_t i, bool own_new, double x0, double &x1,
+                                         double &g1) const {
+        x1 = __dadd_rn(x0, __dmul_rn(a.step, a.p[i]));
+        double f = 0.0;
+        if constexpr (Obj::WIDTH == 2) obj.eval_tail(a.offset + i, x1, f, g1);
+        else obj.eval(a.offset + i, x1, f, g1);
+        if (own_new) { a.x1_out[i] = x1; a.g1_out[i] = g1; }
+    }
+};
+
 template <class Obj>
 struct Callbacks {
     static void geometry(const flgpu_eval_ctx *ctx, int64_t n, Args &A, int64_t &nchunks) {
@@ -266,6 +296,14 @@ struct Callbacks {
                                                     (cudaStream_t)ctx->stream);
         if (e != cudaSuccess) { std::fprintf(stderr, "flgpu_obj: cooperative launch failed: %s\n", cudaGetErrorString(e)); std::abort(); }
     }
+    static void update(const flgpu_eval_ctx *ctx, const flgpu_update_args *A, int64_t) {
+        if (A->k1_bytes != sizeof(flgpu::k::K1Launch)) {
+            std::fprintf(stderr, "flgpu_obj: K1Launch layout mismatch (header and libflgpu.so versions differ)\n");
+            std::abort();
+        }
+        FunctorSrc<Obj> src{*(const Obj *)ctx->user};
+        flgpu::k::launch_k1_pass(*(const flgpu::k::K1Launch *)A->k1, src);
+    }
     static void f(const flgpu_eval_ctx *ctx, double *f_dev, const double *x, int64_t n) {
         launch<false, true, false, false, false>(ctx, f_dev, nullptr, nullptr, nullptr, x, nullptr, 0.0, n);
     }
@@ -310,6 +348,7 @@ inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool wi
     p.fused = with_fused ? Callbacks<Obj>::fused : nullptr;
     p.search = (with_fused && with_search) ? Callbacks<Obj>::search : nullptr;
     p.search_caps = 0;                        // single GPU: row-sharded runs use the host-driven search
+    p.update = with_fused ? Callbacks<Obj>::update : nullptr;
     return p;
 }
 

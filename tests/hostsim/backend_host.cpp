@@ -16,7 +16,7 @@
 
 #include "../../fortran_library_b200/csrc/backend.hpp"
 #include "../../fortran_library_b200/csrc/driver.hpp"
-#include "../../fortran_library_b200/csrc/lbfgs_gram.hpp"
+#include "../../include/flgpu_lbfgs_gram.hpp"
 #include "../../include/flgpu_reduce_geom.h"
 #include "../../include/flgpu_search_core.hpp"
 #include "../../oracle/oracle.h"
@@ -116,7 +116,7 @@ public:
     double search_res[FLGPU_SEARCH_RESULT_DOUBLES] = {0};
     bool device_search_available() const override { return prob.fused != nullptr && g_nranks <= 1; }
     void device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0, double incr,
-                       double a, const double *x0, const double *p, double *xt, double *gt) override {
+                       double a, const double *x0, const double *p, double *xt, double *gt, bool = false) override {
         callback_launches++;
         EagerSearch S(*this, x0, p);
         S.c1 = c1; S.c2abs = c2abs; S.fx0 = fx0; S.phid0 = phid0; S.incr = incr; S.fdwithf = fdwithf;
@@ -276,6 +276,7 @@ void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->fused = obj_fused;
     out->search = nullptr;
     out->search_caps = 0;
+    out->update = nullptr;
 }
 
 void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {

@@ -8,6 +8,7 @@ Tolerances (BASELINE.json north_star, and DESIGN.md "parity" for why they are ap
   * minimisers 1e-8 relative, iteration counts 2 % where the oracle itself is that stable.
 """
 import ctypes as C
+import json
 import math
 import os
 import subprocess
@@ -502,6 +503,41 @@ def test_device_resident_search_terminates_on_nan():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "returned" in r.stdout, r.stdout + r.stderr
     assert "gave up after" in r.stdout
+
+
+@pytest.mark.parametrize("name,kw", [("rosenR1", dict(Memory=10, MaxIteration=40)), ("quartic", dict(Memory=3)),
+                                     ("diag", dict(Memory=30, MaxIteration=45)), ("rosenR1", dict(Memory=12, use_ffd=False, MaxIteration=30))])
+@pytest.mark.parametrize("n", [10_001, 1 << 20])
+def test_fused_update_is_the_same_algorithm(name, kw, n):
+    """flgpu_problem.update: K1 forms x1 = x0 + a*p and f'(x1) in registers and stores them, instead of the line search
+    storing the accepted point and K1 reading it back.  Same roundings, same chunk sums: every iterate, step and counter
+    must be IDENTICAL with the callback switched off (FLGPU_FUSED_UPDATE=0), host-driven and device-resident search."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\nimport numpy as np, fortran_library_b200 as fl\n"
+            "kind, start, seed = %r\n"
+            "out = {}\n"
+            "for ds in (False, True):\n"
+            "    x = fl.DeviceVector.start(start, %d, seed=seed)\n"
+            "    p = fl.builtin_problem(kind)\n"
+            "    if not %r: p.f_fd = None\n"
+            "    ob = fl.Observer()\n"
+            "    st = fl.LBFGS(p, x, Warning=False, observer=ob, device_search=ds, **%r)\n"
+            "    out[str(ds)] = dict(rows=ob.rows, x=x.numpy().tobytes().hex()[:4096], xs=float(np.sum(x.numpy())), n_f_fd=st.n_f_fd, n_f=st.n_f,\n"
+            "                        n_fd=st.n_fd, trials=st.n_trials, it=st.iterations, status=st.status, launches=st.gpu_launches)\n"
+            "print(json.dumps(out))\n" % (ROOT, os.path.join(ROOT, "tests"), _cases.OBJECTIVES[name], n, use, kw))
+    res = []
+    for env in ({}, {"FLGPU_FUSED_UPDATE": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    on, off = res
+    for ds in ("False", "True"):
+        a, b = on[ds], off[ds]
+        assert a["rows"] == b["rows"] and a["x"] == b["x"] and a["xs"] == b["xs"]
+        for k in ("n_f_fd", "n_f", "n_fd", "trials", "it", "status"):
+            assert a[k] == b[k], k
+    assert on["False"]["rows"] == on["True"]["rows"] and on["False"]["x"] == on["True"]["x"]
 
 
 # ----------------------------------------------------------------------------- user objectives (flgpu_objective.cuh)

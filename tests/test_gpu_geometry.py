@@ -67,7 +67,7 @@ def oracle_jobs(tmp_path_factory):
 
 # ----------------------------------------------------------------------------- (a) K1 + K2 + K3, bit-exact
 def _gram_solve(m, k, recent, D, SY, YY):
-    """lbfgs_gram_solve() of csrc/lbfgs_gram.hpp (the scalar statement of K2) in Python floats: same operations in
+    """lbfgs_gram_solve() of include/flgpu_lbfgs_gram.hpp (the scalar statement of K2) in Python floats: same operations in
     the same order, every multiply and add rounded separately."""
     r = recent
     slot = lambda t: (recent - t + m) % m          # noqa: E731
