@@ -4,13 +4,18 @@ L-BFGS (m = 10) outer iterations per second on extended Rosenbrock at n = 2^28, 
 --gpus N B200s (strong scaling: the global n is fixed), plus the HBM roofline of the dominant kernel.
 
 A "step" is one main-loop L-BFGS iteration = Before + line search + After of the reference
-(NonlinearOptimization.f90:514-518), i.e. one accepted step: K1 (ring update + all dots) -> K2 -> K3
-(direction + first trial) -> Strong-Wolfe trials (x0 + a p, f_fd callback, f'.p).  Iteration 0 and the
+(NonlinearOptimization.f90:514-518), i.e. one accepted step: K1 (accepted point, ring update and all dots in one
+pass) -> K2 -> K3 (direction) -> Strong-Wolfe trials (fused probes of x0 + a p).  Iteration 0 and the
 m-1 pre-iterations (f90:442-510) always run first and are never timed.
 
   python bench.py [--gpus N --steps K --warmup W]         our arm (one JSON line on rank 0)
   python bench.py --impl reference [...]                   the reference's CPU algorithm (oracle port): one thread
                                                            (its own semantics) and, as the line's value, all host cores
+
+Beside the headline the line carries (same run, same box):
+  secondary   BASELINE.json configs[2] (CG Dai-Yuan / Polak-Ribiere+ on the separable quartic, n = 2^28) and configs[3]
+              (LBFGS m = 30 on the diagonal quadratic, 2^28 rows per GPU: n = 2^31 on 8 GPUs -- the weak-scaling series)
+  parity      (N > 1) a 2^20-row L-BFGS run on the shards against the same problem on rank 0 alone, before any timing
 
 Timing: CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks.
 Inputs are 2 GiB per vector (>> 126 MB L2), so no L2 flush is needed between iterations.
@@ -50,12 +55,21 @@ def workload(n, mem, objective="rosenbrock"):
             f"seed {SEED}, f_fd present, default tunables (Strong, c1=1e-4, c2=0.9, Increment=1.05)")
 
 
+def static_config(n, mem, objective):
+    """What is measured -- IDENTICAL in our arm and in the reference arm (everything about HOW a run went lives in
+    the line's `run` object instead)."""
+    return {"workload": workload(n, mem, objective), "n_global": n, "memory": mem, "objective": objective,
+            "l2": "inputs (2 GiB/vector) exceed L2; no flush needed"}
+
+
 POLICIES = {"reference": "reference (StrongWolfe_fdwithf f90:1582-1698, statement by statement)",
             "fast": "fast (FLGPU_LS_FAST: first trial satisfying the strong Wolfe conditions is accepted; not a "
                     "reference routine)"}
-LS_MODES = {True: "fused (flgpu_fused_fn: objective kernel forms x0+a*p; 2n doubles per trial + 4n per accepted step)",
+LS_MODES = {True: "fused (flgpu_fused_fn + flgpu_update_fn: the objective kernel forms x0+a*p; 2n doubles per trial, the "
+                  "accepted point is formed and stored by K1)",
             False: "plain (opaque f/fd/f_fd device callbacks; 7n doubles per f+g trial)"}
-NCU_NAMES = {"k1_update_dots": "k1_update_dots_kernel", "k3_direction": "k3_direction_kernel", "trial_x": "trial_kernel",
+NCU_NAMES = {"k1_update_dots": "k1_update_dots_kernel", "k1_update_dots_fused": "k1_update_dots_kernel",
+             "k3_direction": "k3_direction_tma_kernel", "trial_x": "trial_kernel",
              "dot": "dot_kernel", "cg_dots": "cg_dots_kernel", "cg_update": "cg_update_kernel"}
 
 
@@ -110,8 +124,10 @@ class ClockSampler:
 # --------------------------------------------------------------------------- CPU baseline (oracle = checker, timed)
 def cpu_lbfgs(n_sample, mem, warmup, steps, n_target, objective="rosenbrock"):
     """Times the oracle (C restatement of the reference, strict IEEE, sequential sums, ONE thread -- the
-    reference has no threading on this path) on a bounded sample of the same workload and
-    scales the iteration rate linearly in n (a streaming workload)."""
+    reference has no threading on this path) on a bounded sample of the same workload.  The workload is
+    streaming, so rates scale with 1/n: `value` is the sample's rate x n_sample/n_target and says so
+    (`extrapolated`); `ms_per_trial_at_n` is the size-normalised figure that does not depend on how many trials the
+    timed iterations happened to need."""
     import _oracle as O
     marks = {}
 
@@ -131,15 +147,19 @@ def cpu_lbfgs(n_sample, mem, warmup, steps, n_target, objective="rosenbrock"):
     its = last - first
     trials = sum(marks[i][1] for i in range(first + 1, last + 1))
     rate_sample = its / dt
+    scale = n_sample / n_target
     threads = int(O.lib().orc_threads())
     build = ("oracle/liboracle_omp.so (the same source with OpenMP-parallel loops and dots, gcc -O3 -march=native "
              f"-fopenmp, {threads} threads: a GENEROUS baseline, the reference itself is serial)" if O.OMP_VARIANT else
              "oracle/liboracle.so (gcc -O2 -ffp-contract=off, 1 thread = the reference's semantics)")
-    return {"value": rate_sample * n_sample / n_target, "unit": UNIT, "cores": threads, "kind": "port",
+    return {"value": rate_sample * scale, "unit": UNIT, "cores": threads, "kind": "port",
+            "extrapolated": n_sample != n_target, "n_sample": n_sample, "n_target": n_target,
             "sample": (f"{build} on n=2^{n_sample.bit_length() - 1}: "
                        f"{its} main-loop iterations, {trials} trials, {dt:.2f} s = {rate_sample:.3f} it/s; scaled by "
                        f"n_sample/n (streaming)"),
-            "sample_it_per_s": rate_sample, "sample_trials_per_iteration": trials / max(its, 1)}
+            "sample_it_per_s": rate_sample, "sample_trials_per_iteration": trials / max(its, 1),
+            "trials_per_sec": trials / dt * scale, "ms_per_trial_at_n": dt / max(trials, 1) / scale * 1e3,
+            "sample_seconds": dt}
 
 
 def cpu_lbfgs_all_cores(n_sample, mem, warmup, steps, n_target, objective="rosenbrock"):
@@ -174,14 +194,23 @@ def run_reference(args):
     t0 = time.time()
     # the reference's algorithm on ONE thread (its own semantics: it has no threading on this path) ...
     single = cpu_lbfgs(n_sample, args.mem, args.warmup, args.steps, n, args.objective)
-    # ... and on all host cores (OpenMP build of the same port).  The line's value is the faster, all-cores one, so the
-    # driver's ours/reference ratio is the conservative reading; the single-thread sample is reported beside it.
-    cb = cpu_lbfgs_all_cores(n_sample, args.mem, args.warmup, args.steps, n, args.objective) or single
+    # ... and on all host cores (OpenMP build of the same port, a larger sample).  The line's value is the faster,
+    # all-cores one, so the driver's ours/reference ratio is the conservative reading; the single-thread figure -- what
+    # the reference itself would do -- is `value_reference_semantics`.
+    n_omp = 1 << min(args.log2n, args.cpu_log2n + 2)
+    cb = cpu_lbfgs_all_cores(n_omp, args.mem, args.warmup, args.steps, n, args.objective) or single
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload(n, args.mem, args.objective),
-                       "timing": "host perf_counter around oracle iterations"},
+            "config": static_config(n, args.mem, args.objective),
+            "kind": "port", "extrapolated": cb["extrapolated"], "n_sample": cb["n_sample"],
+            "value_reference_semantics": single["value"],
+            "trials_per_sec": cb["trials_per_sec"], "ms_per_trial": cb["ms_per_trial_at_n"],
+            "run": {"timing": "host perf_counter around oracle iterations; rates measured on n_sample rows and scaled by "
+                              "n_sample/n (streaming workload): ms_per_step is DERIVED (1e3/value), not measured at n",
+                    "sample_seconds": cb["sample_seconds"], "trials_per_iteration": cb["sample_trials_per_iteration"],
+                    "note": "the reference cannot be compiled here (Fortran + MKL, SURVEY F1/F2): this is the C "
+                            "restatement oracle/oracle.c, parity-unpinned"},
             "cpu_baseline": cb, "single_thread": single,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
@@ -190,7 +219,62 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- our arm
+def shard_bounds(n, rank, world):
+    lo = (n * rank // world) // 2 * 2            # even boundaries: Rosenbrock pairs never straddle shards
+    hi = n if rank == world - 1 else (n * (rank + 1) // world) // 2 * 2
+    return lo, hi
+
+
+def load_peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return peak, ("MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)")
+
+
+def kernel_table(kt, peak):
+    kernels = {}
+    for name, v in kt.items():
+        if v["ms"] > 0 and v["bytes"] > 0:
+            kernels[name] = {"launches": v["launches"], "ms": round(v["ms"], 3), "avg_ms": v["ms"] / v["launches"],
+                             "GBps": v["bytes"] / v["ms"] / 1e6, "frac": v["bytes"] / v["ms"] / 1e6 / peak}
+    return kernels
+
+
+def roofline_of(kt, peak, peak_src, n_local, mem):
+    """Roofline object of the dominant LIBRARY kernel of the timed region (CUDA-event times of pass 2)."""
+    kernels = kernel_table(kt, peak)
+    own = {k: v for k, v in kernels.items() if not k.startswith("callback:")}
+    top = max(own, key=lambda k: own[k]["ms"])
+    # DRAM bytes per launch from the committed ncu --set full capture of the same kernel; the capture was taken at one
+    # size (recorded beside it), so it is scaled by rows per GPU and only used when the memory matches
+    traffic, traffic_note = None, None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        ent = prof.get(NCU_NAMES.get(top, top), {})
+        if ent.get("dram_bytes_per_launch") and ent.get("n") and ent.get("memory") == mem:
+            traffic = ent["dram_bytes_per_launch"] * n_local / ent["n"]
+            traffic_note = (f"ncu --set full capture {ent.get('tag')} at n=2^{int(ent['n']).bit_length() - 1}, "
+                            f"m={ent['memory']}" + ("" if n_local == ent["n"] else ", scaled by rows per GPU"))
+    except (OSError, ValueError):
+        pass
+    total_bytes = sum(v["bytes"] for v in kt.values())
+    total_kernel_ms = sum(v["ms"] for v in kt.values())
+    return {"bound": "hbm", "kernel": top, "achieved": own[top]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": own[top]["frac"], "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": kt[top]["bytes"] / kt[top]["launches"],
+            "share_of_step": kt[top]["ms"] / total_kernel_ms,
+            "whole_step": {"algorithmic_GB": total_bytes / 1e9, "kernel_ms": total_kernel_ms,
+                           "GBps": total_bytes / total_kernel_ms / 1e6, "frac": total_bytes / total_kernel_ms / 1e6 / peak,
+                           "note": "all kernels of the K timed iterations (per-kernel CUDA events)"},
+            "kernels": kernels}
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import fortran_library_b200 as fl
 
@@ -202,7 +286,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     fl.require_gpu()
     dist = None
-    comm = None
+    comm = comm_nccl = None
+    L = fl.lib()
+    L.flgpu_comm_uses_peer_memory.argtypes = [C.c_void_p]
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -214,29 +300,46 @@ def run_ours(args):
             dist.broadcast(t, 0)
             return bytes(t.cpu().numpy().tobytes())
         comm = fl.comm_create(rank, world, bcast)
-        fl.lib().flgpu_comm_uses_peer_memory.argtypes = [C.c_void_p]
+        os.environ["FLGPU_EXCHANGE"] = "nccl"            # a second communicator on the ncclAllGather fallback (parity)
+        comm_nccl = fl.comm_create(rank, world, bcast)
+        del os.environ["FLGPU_EXCHANGE"]
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allmin_flag(ok):
+        t = torch.tensor([int(bool(ok))], device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
     n = 1 << args.log2n
     mem, W, K = args.mem, args.warmup, args.steps
-    lo = (n * rank // world) // 2 * 2            # even boundaries: Rosenbrock pairs never straddle shards
-    hi = n if rank == world - 1 else (n * (rank + 1) // world) // 2 * 2
+    lo, hi = shard_bounds(n, rank, world)
     n_local = hi - lo
-    diag = args.objective == "diag"
-    OBJ, START = (fl.OBJ_DIAGQUAD, fl.START_ZERO) if diag else (fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT)
-    prob = fl.builtin_problem(OBJ)
-    first, last = mem + W - 1, mem + W + K - 1   # observer indices bracketing exactly K main-loop iterations
+    peak, peak_src = load_peak()
+    DS = {"auto": None, "on": True, "off": False}[args.device_search]
+    OBJS = {"rosenbrock": (fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, SEED), "diag": (fl.OBJ_DIAGQUAD, fl.START_ZERO, 0),
+            "quartic": (fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345)}
 
-    def timed_run(time_kernels, fused=True, policy=None):
-        policy = policy or args.line_search
-        x = fl.DeviceVector.start(START, n_local, seed=SEED, offset=lo, n_global=n)
+    def timed_run(algo, objective, n_glob, m, time_kernels, fused=True, policy="reference", method=None):
+        """K iterations of `algo` bracketed by CUDA events on the library's stream (observer callbacks mark the
+        window): LBFGS skips iteration 0 and the m-1 pre-iterations, CG its first W iterations."""
+        kind, start, seed = OBJS[objective]
+        a, b = shard_bounds(n_glob, rank, world)
+        first = max((m if algo == "lbfgs" else 0) + W - 1, 0)
+        last = first + K
+        x = fl.DeviceVector.start(start, b - a, seed=seed, offset=a, n_global=n_glob)
         ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         mark = {}
-
         per = mark["per"] = []          # one event per iteration boundary inside the window (SURVEY 8d: median)
 
         def stamp(i):
@@ -271,11 +374,16 @@ def run_ours(args):
                     return True
             return False
         ob = fl.Observer(on_iteration=on_iter)
-        st = fl.LBFGS(prob, x, Memory=mem, Warning=False, MaxIteration=W + K, observer=ob, comm=comm, offset=lo,
-                      n_global=n, time_kernels=time_kernels, fused=fused, device_search=DS, line_search=policy)
+        prob = fl.builtin_problem(kind)
+        common = dict(Warning=False, MaxIteration=W + K + 1, observer=ob, comm=comm, offset=a, n_global=n_glob,
+                      time_kernels=time_kernels, fused=fused, device_search=DS, line_search=policy)
+        if algo == "lbfgs":
+            st = fl.LBFGS(prob, x, Memory=m, **common)
+        else:
+            st = fl.ConjugateGradient(prob, x, Method=method, **common)
         if "t1" not in mark:
-            raise SystemExit(f"bench.py: optimizer stopped after {st.iterations} iterations (status {st.status}) "
-                             f"before {last + 1}; lower --steps")
+            raise SystemExit(f"bench.py: {algo} on {objective} stopped after {st.iterations} iterations (status "
+                             f"{st.status}) before {last + 1}; lower --steps")
         ms = ev[0].elapsed_time(ev[1])
         try:
             evs = mark.get("per") or []
@@ -285,20 +393,96 @@ def run_ours(args):
         x.free()
         return ms, mark, st, fl.kernel_times() if time_kernels else None
 
+    def record(algo, objective, n_glob, m, method=None):
+        """A secondary record: one pass with per-kernel events -> rate, trials and the roofline of its top kernel."""
+        ms, mark, st, kt = timed_run(algo, objective, n_glob, m, True, True, "reference", method)
+        ms = allmax(ms)
+        trials = mark["c1"][2] - mark["c0"][2]
+        a, b = shard_bounds(n_glob, rank, world)
+        rf = roofline_of(kt, peak, peak_src, b - a, m)
+        return {"workload": (f"{'LBFGS m=' + str(m) if algo == 'lbfgs' else 'ConjugateGradient ' + method} on {objective}, "
+                             f"n=2^{n_glob.bit_length() - 1} ({b - a} rows per GPU), fused line search, reference policy"),
+                "value": K / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / K, "trials_per_iteration": trials / K,
+                "trials_per_sec": trials / (ms * 1e-3),
+                "roofline": {k: rf[k] for k in ("kernel", "achieved", "peak", "frac", "share_of_step", "unit")},
+                "whole_step_GBps": rf["whole_step"]["GBps"], "whole_step_frac": rf["whole_step"]["frac"],
+                "kernels": {k: {"avg_ms": v["avg_ms"], "GBps": v["GBps"], "frac": v["frac"], "launches": v["launches"]}
+                            for k, v in rf["kernels"].items()}}
+
+    # ---- parity (N > 1), before any timing: a 2^20-row problem on the shards against rank 0 alone.  The reductions are
+    # partition-independent (include/flgpu_reduce.cuh) and these shards are aligned subtrees, so the comparison is
+    # BITWISE: every rank's scalars, the gathered iterate and the first directions must equal the single-GPU run's.
+    parity = None
+    if world > 1:
+        parity = {}
+        n_par = 1 << args.parity_log2n
+        pa, pb = shard_bounds(n_par, rank, world)
+
+        def gather(v):
+            t = torch.from_numpy(np.ascontiguousarray(v)).cuda()
+            outs = []
+            for r in range(world):
+                ra, rb = shard_bounds(n_par, r, world)
+                buf = t if r == rank else torch.empty(rb - ra, dtype=torch.float64, device="cuda")
+                dist.broadcast(buf, r)
+                outs.append(buf.clone())
+            return torch.cat(outs).cpu().numpy()
+
+        def sharded(policy, c, ds=None):
+            x = fl.DeviceVector.start(fl.START_ROSEN_PERT, pb - pa, seed=SEED, offset=pa, n_global=n_par)
+            ob = fl.Observer(keep_vectors=True, max_vec_iters=6)
+            st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=mem, Warning=False, MaxIteration=25 - mem,
+                          observer=ob, comm=c, offset=pa, n_global=n_par, line_search=policy, device_search=ds)
+            out = (x.numpy(), ob, st)
+            x.free()
+            return out
+
+        for policy in ("reference", "fast"):
+            xs, ob, st = sharded(policy, comm)
+            mine = torch.tensor([v for r in ob.rows for v in (r[1], r[2], r[3], float(r[4]))] + [float(st.iterations)],
+                                dtype=torch.float64, device="cuda")
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            same = allmin_flag(ref.numel() == mine.numel() and torch.equal(ref.view(torch.int64), mine.view(torch.int64)))
+            x2, _, st2 = sharded(policy, comm_nccl)
+            x3, _, st3 = sharded(policy, comm, ds=False)     # host-driven search over the same exchange
+            modes = allmin_flag(np.array_equal(xs, x2) and np.array_equal(xs, x3) and st2.iterations == st.iterations
+                                and st3.iterations == st.iterations)
+            xg = gather(xs)
+            pg = [gather(p) for p in ob.p[:6]]
+            rec = {"ranks_identical_scalars": same, "peer_exchange==nccl_fallback==host_driven_search": modes,
+                   "iterations": st.iterations}
+            if rank == 0:
+                x1 = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_par, seed=SEED)
+                ob1 = fl.Observer(keep_vectors=True, max_vec_iters=6)
+                st1 = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x1, Memory=mem, Warning=False,
+                               MaxIteration=25 - mem, observer=ob1, line_search=policy)
+                x1n = x1.numpy()
+                rec["bitwise_equal_to_single_gpu"] = bool(np.array_equal(xg, x1n) and ob1.rows == ob.rows and
+                                                          all(np.array_equal(a, b) for a, b in zip(pg, ob1.p[:6])))
+                rec["rel_dx"] = float(np.linalg.norm(xg - x1n) / np.linalg.norm(x1n))
+                rec["max_rel_dp_first6"] = float(max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(pg, ob1.p[:6])))
+                rec["iterations_single_gpu"] = st1.iterations
+                rec["ok"] = bool(same and modes and rec["rel_dx"] < 1e-8 and rec["max_rel_dp_first6"] < 1e-9
+                                 and st1.iterations == st.iterations)
+                x1.free()
+            parity[policy] = rec
+        parity["n_global"] = n_par
+        parity["what"] = (f"LBFGS m={mem}, Rosenbrock R1, n=2^{args.parity_log2n} over {world} row shards vs rank 0 alone, "
+                          "25 accepted steps; asserted before timing")
+        ok = allmin_flag(rank != 0 or all(parity[p]["ok"] for p in ("reference", "fast")))
+        parity["ok"] = ok
+
     # ---- pass 1: the metric (device-resident inputs, no per-kernel events)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     fused = not args.plain
-    DS = {"auto": None, "on": True, "off": False}[args.device_search]
     ds_active = fused and (DS is True or (DS is None and n_local <= (1 << 25))) and \
-        (comm is None or bool(fl.lib().flgpu_comm_uses_peer_memory(comm)))
-    ms, mark, st, _ = timed_run(False, fused)
+        (comm is None or bool(L.flgpu_comm_uses_peer_memory(comm)))
+    ms, mark, st, _ = timed_run("lbfgs", args.objective, n, mem, False, fused, args.line_search)
     clocks = sampler.stop(mark["t0"], mark["t1"]) if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = allmax(ms)
     launches = (mark["c1"][0] - mark["c0"][0]) + (mark["c1"][1] - mark["c0"][1])   # library kernels + objective kernels
     trials = mark["c1"][2] - mark["c0"][2]
     it_ms = mark.get("iter_ms") or []
@@ -307,65 +491,42 @@ def run_ours(args):
                               "(iterations differ by their trial counts)"} if it_ms else None)
 
     # ---- pass 2: per-kernel CUDA-event times over the same timed region -> roofline of the dominant kernel
-    ms2, mark2, st2, kt = timed_run(True, fused)
+    ms2, mark2, st2, kt = timed_run("lbfgs", args.objective, n, mem, True, fused, args.line_search)
+    roofline = roofline_of(kt, peak, peak_src, n_local, mem)
     # ---- pass 3: the other line-search mode, for the record (same iterates up to summation order)
-    ms3, mark3, _, _ = timed_run(False, not fused)
-    t3 = torch.tensor([ms3], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-    other = {"line_search": LS_MODES[not fused], "value": K / (float(t3.item()) * 1e-3), "unit": UNIT,
+    ms3, mark3, _, _ = timed_run("lbfgs", args.objective, n, mem, False, not fused, args.line_search)
+    other = {"line_search": LS_MODES[not fused], "value": K / (allmax(ms3) * 1e-3), "unit": UNIT,
              "trials_in_timed_region": mark3["c1"][2] - mark3["c0"][2]}
     # ---- pass 4: the optional FLGPU_LS_FAST policy (NOT the reference's searcher: iterates differ, so this is a
     # separate record and never the headline)
     fast = None
-    if args.line_search == "reference" and world == 1:   # 1 GPU only: the policy has not been run on row shards yet
-        ms4, mark4, _, _ = timed_run(False, fused, "fast")
-        t4 = torch.tensor([ms4], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+    if args.line_search == "reference":
+        ms4, mark4, _, _ = timed_run("lbfgs", args.objective, n, mem, False, fused, "fast")
+        t4 = allmax(ms4)
         tr4 = mark4["c1"][2] - mark4["c0"][2]
-        fast = {"line_search_policy": POLICIES["fast"], "value": K / (float(t4.item()) * 1e-3), "unit": UNIT,
-                "ms_per_step": float(t4.item()) / K, "trials_in_timed_region": tr4, "trials_per_iteration": tr4 / K,
+        fast = {"line_search_policy": POLICIES["fast"], "value": K / (t4 * 1e-3), "unit": UNIT,
+                "ms_per_step": t4 / K, "trials_in_timed_region": tr4, "trials_per_iteration": tr4 / K,
                 "note": "same K-iteration window of a run made with line_search=fast; iteration rate, not time to "
                         "solution (DESIGN.md 3.2: with WolfeConst2 = 0.9 this policy needs more iterations on Rosenbrock)"}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-    kernels = {}
-    for name, v in kt.items():
-        if v["ms"] > 0 and v["bytes"] > 0:
-            kernels[name] = {"launches": v["launches"], "ms": round(v["ms"], 3), "avg_ms": v["ms"] / v["launches"],
-                             "GBps": v["bytes"] / v["ms"] / 1e6, "frac": v["bytes"] / v["ms"] / 1e6 / peak}
-    own = {k: v for k, v in kernels.items() if not k.startswith("callback:")}
-    top = max(own, key=lambda k: own[k]["ms"])
-    traffic = None
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-        traffic = prof.get(NCU_NAMES.get(top, top), {}).get("dram_bytes_per_launch")
-    except (OSError, ValueError):
-        pass
-    total_bytes = sum(v["bytes"] for v in kt.values())
-    total_kernel_ms = sum(v["ms"] for v in kt.values())
-    roofline = {"bound": "hbm", "kernel": top, "achieved": own[top]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": own[top]["frac"], "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": kt[top]["bytes"] / kt[top]["launches"],
-                "share_of_step": kt[top]["ms"] / total_kernel_ms,
-                "whole_step": {"algorithmic_GB": total_bytes / 1e9, "kernel_ms": total_kernel_ms,
-                               "GBps": total_bytes / total_kernel_ms / 1e6, "frac": total_bytes / total_kernel_ms / 1e6 / peak,
-                               "note": "all kernels of the K timed iterations (pass 2)"},
-                "kernels": kernels}
+
+    # ---- secondary records: BASELINE.json configs[2] and [3], driver-run beside the headline
+    secondary = {}
+    if not args.no_secondary and args.objective == "rosenbrock" and args.line_search == "reference" and fused:
+        secondary["cg_dy_quartic"] = record("cg", "quartic", n, 0, "DY")
+        secondary["cg_pr_quartic"] = record("cg", "quartic", n, 0, "PR")
+        # configs[3]: 2^28 rows per GPU (130 GiB of work space) -- the weak-scaling series 2^28 x N, n = 2^31 on 8 GPUs
+        n30 = (1 << 28) * world
+        secondary[f"lbfgs_m30_diag_2p{n30.bit_length() - 1}"] = dict(
+            record("lbfgs", "diag", n30, 30), scaling="weak: 2^28 rows per GPU at every N (n = 2^31 on 8 GPUs)")
 
     # ---- e2e: the reference-facing call with HOST buffers (pinned): H2D of x, the whole optimisation (iteration 0,
     # the m-1 pre-iterations, Ke main iterations) and D2H of x inside the timed region.  Called twice: cold (work space
     # allocated and returned to the driver inside the call, as the reference does) and warm (flgpu_set_workspace_cache:
     # buffers parked by an untimed warm-up call are reused) -- `value` is the warm call, the cold one is reported beside it.
     Ke = args.e2e_steps
+    OBJ, START, _ = OBJS[args.objective]
+    prob = fl.builtin_problem(OBJ)
     xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
-    L = fl.lib()
     if world == 1 and not fused:
         os.environ["FLGPU_NO_FUSED"] = "1"
     L.flgpu_set_line_search(fl.LS_FAST if args.line_search == "fast" else fl.LS_REFERENCE)   # Fortran-ABI calls
@@ -391,11 +552,7 @@ def run_ours(args):
                            fused=fused, line_search=args.line_search)
         e1.record()
         barrier()
-        ms = max(e0.elapsed_time(e1), (time.time() - te) * 1e3)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), ste
+        return allmax(max(e0.elapsed_time(e1), (time.time() - te) * 1e3)), ste
 
     cold_ms, cold_st = e2e_call(Ke)
     L.flgpu_set_workspace_cache(1)
@@ -404,7 +561,8 @@ def run_ours(args):
     L.flgpu_set_workspace_cache(0)               # releases the parked buffers
     e2e = {"value": ste.iterations / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n / ste.iterations,
            "d2h_bytes_per_step": 8 * n / ste.iterations, "iterations": ste.iterations, "ms": e2e_ms,
-           "call": ("__nonlinearoptimization_MOD_lbfgs (host x, device-pointer callbacks)" if world == 1
+           "trials": ste.n_trials, "trials_per_sec": ste.n_trials / (e2e_ms * 1e-3),
+           "call": ("__nonlinearoptimization_MOD_lbfgs (host x, built-in CUDA objective in reference-ABI form)" if world == 1
                     else "flgpu_lbfgs (host x shard, row-shard communicator)"),
            "cold_call": {"value": cold_st.iterations / (cold_ms * 1e-3), "ms": cold_ms,
                          "note": "first call: work space cudaMalloc'ed and cudaFree'd inside the call"},
@@ -414,37 +572,43 @@ def run_ours(args):
                    "PCIe once per call)"}
 
     cpu = cpu_all = None
-    if rank == 0 and world == 1 and not args.no_cpu and not diag:
+    if rank == 0 and world == 1 and not args.no_cpu and args.objective == "rosenbrock":
         cpu = cpu_lbfgs(1 << min(args.log2n, args.cpu_log2n), mem, min(W, 3), min(K, 10), n)
-        cpu_all = cpu_lbfgs_all_cores(1 << min(args.log2n, args.cpu_log2n), mem, min(W, 3), min(K, 10), n)
+        cpu_all = cpu_lbfgs_all_cores(1 << min(args.log2n, args.cpu_log2n + 2), mem, min(W, 3), min(K, 10), n)
 
+    rc = 0
     if rank == 0:
         line = {"metric": METRIC, "value": K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload(n, mem, args.objective), "n_global": n, "rows_per_gpu": n_local,
-                           "parallelism": f"row-shard x{world}" if world > 1 else "1 GPU",
-                           "exchange": (None if comm is None else
-                                        ("one kernel over IPC-mapped peer memory (NVLink stores + flags), rank-ordered sum"
-                                         if fl.lib().flgpu_comm_uses_peer_memory(comm) else "ncclAllGather + combine kernel")),
-                           "l2": "inputs (2 GiB/vector) exceed L2; no flush needed",
-                           "line_search": LS_MODES[fused],
-                           "line_search_policy": POLICIES[args.line_search],
-                           "device_resident_search": (f"{args.device_search}: " + (
-                               "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
-                               "off at this size (host-driven, one round trip per trial)")),
-                           "trials_in_timed_region": trials, "trials_per_iteration": trials / K,
-                           "trials_per_sec": trials / (ms_max * 1e-3)},
+                "config": static_config(n, mem, args.objective),
+                "hbm_GBps_whole_step": roofline["whole_step"]["GBps"], "hbm_frac_whole_step": roofline["whole_step"]["frac"],
+                "trials_per_sec": trials / (ms_max * 1e-3), "ms_per_trial": ms_max / max(trials, 1),
+                "run": {"rows_per_gpu": n_local, "parallelism": f"row-shard x{world}" if world > 1 else "1 GPU",
+                        "exchange": (None if comm is None else
+                                     ("one kernel over IPC-mapped peer memory (NVLink stores + flags), rank tree"
+                                      if L.flgpu_comm_uses_peer_memory(comm) else "ncclAllGather + combine kernel")),
+                        "reductions": "partition-independent: fixed chunks on global indices + aligned binary tree over "
+                                      "chunks and ranks (include/flgpu_reduce.cuh)",
+                        "line_search": LS_MODES[fused], "line_search_policy": POLICIES[args.line_search],
+                        "device_resident_search": (f"{args.device_search}: " + (
+                            "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
+                            "off at this size (host-driven, one round trip per trial)")),
+                        "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
                 "per_iteration": per_iteration,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-                "cpu_baseline_all_cores": cpu_all,
+                "cpu_baseline_all_cores": cpu_all, "parity": parity, "secondary": secondary,
                 "other_line_search_mode": other, "fast_line_search_policy": fast}
         print(json.dumps(line), flush=True)
+        if parity is not None and not parity["ok"]:
+            print("bench.py: PARITY FAILED -- the sharded run does not reproduce the single-GPU run", file=sys.stderr)
+            rc = 3
     if comm is not None:
-        fl.lib().flgpu_comm_destroy(comm)
+        L.flgpu_comm_destroy(comm)
+        L.flgpu_comm_destroy(comm_nccl)
     if dist is not None:
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 def main():
@@ -456,7 +620,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="override the global dimension (debugging only)")
     ap.add_argument("--mem", type=int, default=MEM)
     ap.add_argument("--objective", default="rosenbrock", choices=["rosenbrock", "diag"],
-                    help="diag = BASELINE.json configs[3] (with --mem 30 --log2n 31 --gpus 8); not the headline")
+                    help="diag = BASELINE.json configs[3] as the headline (the default run already records it under `secondary`)")
     ap.add_argument("--e2e-steps", type=int, default=100,
                     help="main-loop iterations of the end-to-end optimizer call (its 487-trial prologue is amortised over them)")
     ap.add_argument("--device-search", default="auto", choices=["auto", "on", "off"],
@@ -465,8 +629,10 @@ def main():
                     help="flgpu_options.line_search for the whole run; the headline is `reference` (the default run "
                          "also records the `fast` rate beside it)")
     ap.add_argument("--plain", action="store_true", help="headline with opaque callbacks (no fused line-search evaluation)")
-    ap.add_argument("--cpu-log2n", type=int, default=None, help="size of the bounded CPU sample")
+    ap.add_argument("--cpu-log2n", type=int, default=None, help="size of the bounded single-thread CPU sample (all cores: x4)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs[2]/[3] records")
+    ap.add_argument("--parity-log2n", type=int, default=20, help="global rows of the N > 1 parity problem")
     args = ap.parse_args()
     if args.cpu_log2n is None:       # bounded CPU sample: ~40 s of one core for the reference arm, ~5 s inside our arm
         args.cpu_log2n = 23 if args.impl == "reference" else 22

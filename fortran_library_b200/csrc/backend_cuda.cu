@@ -644,7 +644,8 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
     a.m = mem; a.k = kk; a.recent = recent; a.w = work;
     DeviceFacts &f = facts(device);
     if (f.k3_mode < 0) {
-        // FLGPU_K3 = regs (register double buffers) | tma (default: bulk-async ring, 8 pieces x 3 stages, 2 CTAs/SM) |
+        // FLGPU_K3 = regs (register double buffers) | tma (default: bulk-async ring, 11 pieces x 2 stages, 2 CTAs/SM:
+        // profiles/r02_k3_ring_shapes.md) |
         // "P,NST": another ring shape (tuning; the instantiated ones are listed below)
         const char *v = std::getenv("FLGPU_K3");
         f.k3_mode = 1;
@@ -666,7 +667,7 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
             k::k3_direction_tma_kernel<P, NST, MINB><<<grid_for(MINB), k::kThreads + 32, smem, stream>>>(a);               \
             done = true;                                                                                                   \
         }
-        FLGPU_K3_CASE(8, 3, 2, 0) FLGPU_K3_CASE(7, 3, 2, 1) FLGPU_K3_CASE(4, 6, 2, 2) FLGPU_K3_CASE(11, 2, 2, 3)
+        FLGPU_K3_CASE(11, 2, 2, 0) FLGPU_K3_CASE(7, 3, 2, 1) FLGPU_K3_CASE(4, 6, 2, 2) FLGPU_K3_CASE(8, 3, 2, 3)
         FLGPU_K3_CASE(6, 4, 2, 4) FLGPU_K3_CASE(8, 6, 1, 5) FLGPU_K3_CASE(7, 7, 1, 6) FLGPU_K3_CASE(11, 4, 1, 7)
         FLGPU_K3_CASE(5, 5, 2, 8) FLGPU_K3_CASE(9, 3, 2, 9) FLGPU_K3_CASE(4, 4, 3, 10) FLGPU_K3_CASE(7, 2, 3, 11)
 #undef FLGPU_K3_CASE

@@ -23,7 +23,7 @@ st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=mem, Warning=Fals
               observer=fl.Observer(on_iteration=on_iter))
 kt = fl.kernel_times()
 out = [os.environ.get("FLGPU_K3", "default")]
-for name in ("k3_direction", "k1_update_dots", "callback:fused_probe", "callback:fused_store"):
+for name in ("k3_direction", "k1_update_dots", "k1_update_dots_fused", "callback:fused_probe", "callback:fused_store"):
     if name in kt and kt[name]["launches"]:
         v = kt[name]
         out.append(f"{name}: {v['ms'] / v['launches']:.3f} ms {v['bytes'] / v['ms'] / 1e6:.0f} GB/s x{v['launches']}")

@@ -1,14 +1,16 @@
 """Row-sharded run on N GPUs (one process per GPU, NCCL), checked against the single-GPU run.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 \
-        tests/gpu_multi.py [log2n]            (FLGPU_MULTI_EXTRA=fast adds the fast line-search policy cases)
+        tests/gpu_multi.py [log2n]
 
 Checks (exit status 0 iff all hold):
   * every rank sees bitwise identical scalars (step, f, phi'(0), trials) at every iteration -- the
     rank-ordered combination makes all ranks take identical branch decisions;
-  * the gathered shards of the first directions and of the minimiser agree with the 1-GPU run of the same
-    global problem within the summation-order noise (the split changes the order of the partial sums);
-  * iteration counts within 2 %.
+  * the gathered shards of the first directions and of the minimiser EQUAL the 1-GPU run of the same global
+    problem BIT FOR BIT, and so do all per-iteration scalars and the iteration count: the reductions are
+    partition-independent (include/flgpu_reduce.cuh) and these shards hold the same power-of-two number of chunks;
+    (the AugmentedLagrangian case at the end uses 512-row shards -- half a chunk each -- and is compared within
+    tolerance: ragged shards give a deterministic, rank-identical sum, only not the single-GPU bits).
 Not a pytest file; tests/test_gpu.py::test_row_sharded_nccl launches it when >= 2 GPUs are visible."""
 import os
 import sys
@@ -58,11 +60,9 @@ def main():
              ("lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=5, MaxIteration=40, fused=False)),
              ("cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY")),
              ("cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="PR"))]
-    if os.environ.get("FLGPU_MULTI_EXTRA", "") == "fast":
-        # the optional FLGPU_LS_FAST policy on row shards: opt-in here until it has been run on >= 2 GPUs once
-        # (DESIGN.md "still open" 7); on the CPU the same driver code is covered by the world_size-2 gloo test
-        cases += [("lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10, line_search="fast", MaxIteration=60)),
-                  ("cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY", line_search="fast"))]
+    # the optional FLGPU_LS_FAST policy on row shards (not a reference routine; same exchange, same bitwise bar)
+    cases += [("lbfgs", fl.OBJ_ROSENBROCK, fl.START_ROSEN_PERT, 7, dict(Memory=10, line_search="fast", MaxIteration=60)),
+              ("cg", fl.OBJ_QUARTIC, fl.START_QUARTIC_U, 12345, dict(Method="DY", line_search="fast"))]
     for algo, kind, start, seed, kw in cases:
         run = fl.LBFGS if algo == "lbfgs" else fl.ConjugateGradient
         prob = fl.builtin_problem(kind)
@@ -117,17 +117,14 @@ def main():
             st1 = run(prob, x1, observer=ob1, Warning=False, **kw)
             xs = x1.numpy()
             x0n = np.linalg.norm(fl.DeviceVector.start(start, n, seed=seed).numpy())
-            converged = st1.status in (fl.CONVERGED, fl.STEP_CONVERGED) and kind == fl.OBJ_ROSENBROCK
-            dx = np.linalg.norm(xg - xs) / (np.linalg.norm(xs) if converged else max(x0n, np.linalg.norm(xs)))
+            dx = np.linalg.norm(xg - xs) / max(x0n, np.linalg.norm(xs))
             dp = max(np.linalg.norm(a - b) / np.linalg.norm(b) for a, b in zip(pg, ob1.p[:6]))
-            # a converged Rosenbrock run ends in a long tail of 1e-15-sized steps whose length moves by +-50 % under
-            # one-ULP perturbations (tests/_cases.py oracle_iteration_range): only a loose sanity bound there
-            its_ok = (0.4 * st1.iterations <= st.iterations <= 2.5 * st1.iterations) if converged else \
-                abs(st.iterations - st1.iterations) <= max(2, 0.3 * st1.iterations)
-            good = (same and modes_equal and dx < (1e-8 if converged else 1e-4) and dp < 1e-9 and its_ok
-                    and st.status == st1.status)
+            bitwise = bool(np.array_equal(xg, xs) and all(np.array_equal(a, b) for a, b in zip(pg, ob1.p[:6]))
+                           and ob.rows == ob1.rows and st.iterations == st1.iterations and st.status == st1.status)
+            good = same and modes_equal and bitwise
             print(f"[{world} ranks] {algo} kind={kind} {kw}: iterations {st.iterations}/{st1.iterations} "
-                  f"ranks_identical={same} device-search==host-driven==nccl:{modes_equal} |dx|={dx:.2e} max|dp|(first 6)={dp:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
+                  f"ranks_identical={same} device-search==host-driven==nccl:{modes_equal} bitwise==1-GPU:{bitwise} "
+                  f"|dx|={dx:.2e} max|dp|(first 6)={dp:.2e} -> {'OK' if good else 'FAIL'}", flush=True)
             ok = ok and good
             x1.free()
         x.free()
@@ -172,7 +169,7 @@ def main():
     L.flgpu_history_destroy(hs)
     if rank == 0:
         L.flgpu_history_destroy(h1)
-        good = worst < 1e-12
+        good = worst == 0.0            # 2^14 rows over <= 8 ranks: whole chunks per rank -> the single-GPU bits
         print(f"[{world} ranks] two-loop operator on shards vs 1 GPU: worst relative difference {worst:.2e} -> "
               f"{'OK' if good else 'FAIL'}", flush=True)
         ok = ok and good

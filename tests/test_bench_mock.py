@@ -63,8 +63,8 @@ def _fake_fl(calls):
     capi = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(capi)
     fl.capi = capi
-    for k in ("OBJ_ROSENBROCK", "OBJ_DIAGQUAD", "START_ROSEN_PERT", "START_ZERO", "SPACE_HOST", "SPACE_DEVICE",
-              "LS_FAST", "LS_REFERENCE"):
+    for k in ("OBJ_ROSENBROCK", "OBJ_DIAGQUAD", "OBJ_QUARTIC", "START_ROSEN_PERT", "START_ZERO", "START_QUARTIC_U",
+              "SPACE_HOST", "SPACE_DEVICE", "LS_FAST", "LS_REFERENCE"):
         setattr(fl, k, getattr(capi, k))
     fl.require_gpu = lambda: None
     fl.builtin_problem = lambda kind: object()
@@ -96,6 +96,15 @@ def _fake_fl(calls):
                 break
         return _Stats(it + 1)
     fl.LBFGS = LBFGS
+
+    def ConjugateGradient(prob, x, Method=None, MaxIteration=0, observer=None, **kw):
+        calls.append(("CG", Method, kw.get("fused"), kw.get("time_kernels")))
+        for it in range(MaxIteration):
+            info = types.SimpleNamespace(iteration=it, stream=0, gpu_launches=3 * it, callbacks=15 * it, total_trials=15 * it)
+            if observer is not None and observer.on_iteration(info):
+                break
+        return _Stats(it + 1)
+    fl.ConjugateGradient = ConjugateGradient
     fl.kernel_times = lambda: {"k1_update_dots": {"ms": 7.0, "launches": 30, "bytes": 30 * 5.0e10},
                                "k3_direction": {"ms": 7.5, "launches": 30, "bytes": 30 * 4.7e10},
                                "callback:fused_probe": {"ms": 5.0, "launches": 240, "bytes": 240 * 4.3e9}}
@@ -133,9 +142,14 @@ def test_bench_control_flow_with_stand_ins(monkeypatch):
     d = json.loads(lines[0])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
                 "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline",
-                "cpu_baseline_all_cores", "other_line_search_mode", "fast_line_search_policy", "per_iteration"):
+                "cpu_baseline_all_cores", "other_line_search_mode", "fast_line_search_policy", "per_iteration", "run",
+                "secondary", "parity", "hbm_GBps_whole_step", "trials_per_sec"):
         assert key in d, key
-    assert d["steps"] == 6 and d["config"]["trials_in_timed_region"] == 6 * 8
+    assert d["steps"] == 6 and d["run"]["trials_in_timed_region"] == 6 * 8
+    assert d["parity"] is None                                  # single GPU: nothing to compare
+    assert set(d["secondary"]) == {"cg_dy_quartic", "cg_pr_quartic", "lbfgs_m30_diag_2p28"}
+    assert d["secondary"]["cg_dy_quartic"]["trials_per_iteration"] == 15.0
+    assert d["config"] == bench.static_config(1 << 16, 10, "rosenbrock")   # the reference arm prints the same object
     assert d["per_iteration"]["n"] == 6 and d["per_iteration"]["min_ms"] <= d["per_iteration"]["median_ms"]
     assert d["fast_line_search_policy"]["trials_per_iteration"] == 1.0
     assert d["roofline"]["kernel"] == "k3_direction" and d["roofline"]["bound"] == "hbm"
