@@ -5,8 +5,8 @@
 # 3. one --set full capture of the L-BFGS kernels K1/K3 and of the line-search kernels in steady state.
 # Outputs land in gpurun_out/; summaries are made here with profiles/summarise.py and committed under profiles/.
 set -u
-TAG=${1:-r01}
-CMD="python bench.py --steps 4 --warmup 3 --no-cpu --e2e-steps 2"
+TAG=${1:-r02}
+CMD="python bench.py --steps 4 --warmup 3 --no-cpu --no-secondary --e2e-steps 2"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 cat gpurun_out/${TAG}_plain.json | cut -c1-400

@@ -18,7 +18,7 @@ PROF = os.path.join(ROOT, "profiles")
 
 
 def short(name):
-    m = re.search(r"(k1_update_dots_kernel|k3_direction_kernel|k2_solve_kernel|trial_kernel|dot_kernel|neg_kernel|"
+    m = re.search(r"(k1_update_dots_kernel|k3_direction_tma_kernel|k3_direction_kernel|tree_kernel|search_kernel|k2_solve_kernel|trial_kernel|dot_kernel|neg_kernel|"
                   r"cg_dots_kernel|cg_update_kernel|objective_kernel|start_kernel|combine_kernel|set_scalar_kernel)(<[^(]*>)?", name)
     if m:
         return m.group(1) + (m.group(2) or "")
@@ -100,7 +100,10 @@ def kernels(tag, parts):
                 lines.append(f"| **DRAM GB/s under ncu** | {tot / dur_s / 1e9:.0f} | GB/s |")
                 key = re.sub(r"<.*", "", name)
                 traffic.setdefault(key, {})
-                traffic[key] = {"dram_bytes_per_launch": tot, "duration_s_under_ncu": dur_s, "tag": tag, "kernel": name}
+                # n and memory of the capture (run_ncu.sh profiles bench.py's default workload): bench.py scales the
+                # figure by rows per GPU and ignores it for another memory
+                traffic[key] = {"dram_bytes_per_launch": tot, "duration_s_under_ncu": dur_s, "tag": tag, "kernel": name,
+                                "n": 1 << 28, "memory": 10}
             except (KeyError, ValueError) as e:
                 lines.append(f"| (derived metrics unavailable: {e}) | | |")
             lines.append("")
