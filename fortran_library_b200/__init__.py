@@ -192,7 +192,11 @@ def _run(fn, for_cg, problem, x, n, x_space, observer, stream, comm, offset, n_g
     if observer is not None:
         o.observer = C.cast(observer.cb, C.c_void_p)
     st = capi.Stats()
-    fn(C.byref(problem), C.byref(o), x, n, x_space, C.byref(st))
+    rc = fn(C.byref(problem), C.byref(o), x, n, x_space, C.byref(st))
+    if rc == capi.ERR_MEMORY_LIMIT:
+        raise FlgpuError(f"LBFGS Memory = {o.memory} exceeds FLGPU_MAX_MEMORY = {capi.MAX_MEMORY}: nothing was done")
+    if rc != 0:
+        raise FlgpuError(f"libflgpu returned error {rc}")
     return st
 
 

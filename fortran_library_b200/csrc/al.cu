@@ -244,8 +244,7 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
     if (!s) { FLGPU_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); own_stream = true; in.stream = (void *)s; }
     // every outer iteration runs a full inner solve: keep the work space between them (f90:2150-2185 re-enters
     // LBFGS / ConjugateGradient, which re-allocate; here the buffers are parked and reused)
-    const bool cache_was_on = ws_is_enabled();
-    ws_set_enabled(true);
+    ws_arena_begin();                             // a per-call arena: the process-wide cache switch is not touched
     ALState S;
     S.user = *prob; S.con = *con; S.comm = in.comm; S.m = m;
     S.ld = (n + 31) / 32 * 32; if (S.ld == 0) S.ld = 32;
@@ -319,7 +318,7 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
     ws_free(S.gather, sizeof(double) * kMaxConstraints * (size_t)(G > 1 ? G : 1));
     ws_free(S.cd_dev, sizeof(double) * (size_t)S.ld * (size_t)m);
     if (own_stream) { scratch_release(s); cudaStreamDestroy(s); }
-    if (!cache_was_on) ws_set_enabled(false);       // returns the parked work space to the driver
+    ws_arena_end();                                 // returns the parked work space to the driver
     tls_al = A;
     if (stats) *stats = A;
     return 0;

@@ -54,9 +54,12 @@ int x_space_now() {
     int v = g_x_space.load();
     return v >= 0 ? v : space_from_env("FLGPU_X_SPACE", FLGPU_SPACE_HOST);
 }
+// -1 = not chosen (flgpu_set_callback_space / FLGPU_CALLBACK_SPACE): ref_adapter_init then picks HOST -- what code
+// compiled against the reference expects: x and fdx it can dereference -- unless the objective is one the library knows
+// to be a device callback (its built-ins, anything registered with flgpu_register_fused)
 int cb_space_now() {
     int v = g_cb_space.load();
-    return v >= 0 ? v : space_from_env("FLGPU_CALLBACK_SPACE", FLGPU_SPACE_DEVICE);
+    return v >= 0 ? v : space_from_env("FLGPU_CALLBACK_SPACE", -1);
 }
 
 double wall_ms() {
@@ -70,6 +73,13 @@ int run(int algo, const flgpu_problem *prob, const flgpu_options *opt, double *x
     require_device();
     if (!prob || !prob->f || !prob->fd) fatal("flgpu: f and fd callbacks are required (f90:40)");
     if (n < 0) fatal("flgpu: negative dimension");
+    if (algo == ALGO_LBFGS && opt->memory > FLGPU_MAX_MEMORY) {
+        // the reference accepts any Memory >= 1 (f90:419, 435); K2 / K3 hold their tables for at most 64 pairs
+        std::fprintf(stderr, "flgpu: LBFGS Memory = %d exceeds FLGPU_MAX_MEMORY = %d; nothing was done (x is unchanged)\n",
+                     opt->memory, FLGPU_MAX_MEMORY);
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->status = FLGPU_INVALID_ARGUMENT; }
+        return FLGPU_ERR_MEMORY_LIMIT;
+    }
     const char *tr = std::getenv("FLGPU_TRACE_PHASES");   // wall-clock phases of one call, to stderr
     const bool trace = tr && tr[0] && tr[0] != '0';
     const double t0 = wall_ms();
@@ -164,6 +174,14 @@ void ad_ffd(const flgpu_eval_ctx *c, double *f_dev, double *g, const double *x, 
 void ref_adapter_init(RefAdapter &A, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, int dim,
                       flgpu_problem *prob) {
     A.f = f; A.fd = fd; A.f_fd = f_fd; A.cb_space = cb_space_now();
+    if (A.cb_space < 0) {
+        bool known_device = builtin_fused_for(f) != nullptr;
+        if (!known_device) {
+            std::lock_guard<std::mutex> lock(g_fused_mu);
+            known_device = g_fused.find(f) != g_fused.end();
+        }
+        A.cb_space = known_device ? FLGPU_SPACE_DEVICE : FLGPU_SPACE_HOST;
+    }
     if (A.cb_space == FLGPU_SPACE_HOST) {
         FLGPU_CUDA_CHECK(cudaMallocHost((void **)&A.xh, sizeof(double) * (size_t)(dim > 0 ? dim : 1)));
         FLGPU_CUDA_CHECK(cudaMallocHost((void **)&A.gh, sizeof(double) * (size_t)(dim > 0 ? dim : 1)));
@@ -353,6 +371,14 @@ void __nonlinearoptimization_MOD_lbfgs(flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, dou
     flgpu_options_default(&o, 0);
     if (Memory) o.memory = *Memory;
     fill_optional(o, Strong, Warning, MaxIteration, Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment);
+    if (o.memory > FLGPU_MAX_MEMORY) {
+        // this signature has no error channel and the reference would simply run (f90:419): run with the largest memory
+        // the kernels hold and say so, rather than end the host program
+        if (o.warning)
+            std::printf(" L-BFGS warning: Memory = %d is above the %d pairs the GPU kernels hold; running with Memory = %d\n",
+                        o.memory, FLGPU_MAX_MEMORY, FLGPU_MAX_MEMORY);
+        o.memory = FLGPU_MAX_MEMORY;
+    }
     run_ref(ALGO_LBFGS, f, fd, f_fd, x, *dim, o);
 }
 

@@ -23,12 +23,19 @@ static double now_ms() {
 // ---- work-space cache (opt-in): device buffers of a finished call are kept for the next call on the same
 // device instead of going back to the driver (cudaFree of a 50 GiB work space costs 0.25-0.55 s on B200:
 // profiles/r01_e2e_phases.md).  Off by default: like the reference, nothing then persists between calls.
+// Two scopes: the process-wide cache (flgpu_set_workspace_cache / FLGPU_WORKSPACE_CACHE) and a per-thread ARENA that
+// a composite call (AugmentedLagrangian: one inner solve per outer iteration) opens for its own duration -- it never
+// touches the process-wide switch, so concurrent users of the library are unaffected.
 namespace {
+typedef std::multimap<std::pair<int, size_t>, void *> FreeList;
 struct WsCache {
     std::mutex mu;
-    std::multimap<std::pair<int, size_t>, void *> free_;
+    FreeList free_;
+    std::map<void *, int> device_of;     // owning device, recorded when the buffer was allocated
     bool enabled = false, env_read = false;
 } g_ws;
+struct WsArena { int depth = 0; FreeList free_; };
+thread_local WsArena t_arena;
 bool ws_enabled() {
     if (!g_ws.env_read) {
         const char *v = std::getenv("FLGPU_WORKSPACE_CACHE");
@@ -37,40 +44,62 @@ bool ws_enabled() {
     }
     return g_ws.enabled;
 }
+void release_list(FreeList &fl) {
+    for (auto &kv : fl) {
+        cudaFree(kv.second);
+        std::lock_guard<std::mutex> lock(g_ws.mu);
+        g_ws.device_of.erase(kv.second);
+    }
+    fl.clear();
+}
 }  // namespace
 void *ws_alloc(size_t bytes) {
     int dev = 0;
     cudaGetDevice(&dev);
+    const auto key = std::make_pair(dev, bytes);
+    if (t_arena.depth > 0) {
+        auto it = t_arena.free_.find(key);
+        if (it != t_arena.free_.end()) { void *p = it->second; t_arena.free_.erase(it); return p; }
+    }
     {
         std::lock_guard<std::mutex> lock(g_ws.mu);
-        auto it = g_ws.free_.find(std::make_pair(dev, bytes));
+        auto it = g_ws.free_.find(key);
         if (it != g_ws.free_.end()) { void *p = it->second; g_ws.free_.erase(it); return p; }
     }
     void *p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) {            // out of memory with buffers parked in the cache: release them and retry
+    if (e != cudaSuccess) {            // out of memory with buffers parked in a cache: release them and retry
         cudaGetLastError();
+        release_list(t_arena.free_);
         ws_release();
         e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) cuda_fail("cudaMalloc (work space)", e, __FILE__, __LINE__);
+    std::lock_guard<std::mutex> lock(g_ws.mu);
+    g_ws.device_of[p] = dev;
     return p;
 }
 void ws_free(void *p, size_t bytes) {
     if (!p) return;
+    int dev = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_ws.mu);
+        auto it = g_ws.device_of.find(p);
+        if (it != g_ws.device_of.end()) dev = it->second; else cudaGetDevice(&dev);
+    }
+    if (t_arena.depth > 0) { t_arena.free_.emplace(std::make_pair(dev, bytes), p); return; }
     std::lock_guard<std::mutex> lock(g_ws.mu);
     if (ws_enabled()) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         g_ws.free_.emplace(std::make_pair(dev, bytes), p);
     } else {
+        g_ws.device_of.erase(p);
         cudaFree(p);
     }
 }
 void ws_release() {
-    std::lock_guard<std::mutex> lock(g_ws.mu);
-    for (auto &kv : g_ws.free_) cudaFree(kv.second);
-    g_ws.free_.clear();
+    FreeList taken;
+    { std::lock_guard<std::mutex> lock(g_ws.mu); taken.swap(g_ws.free_); }
+    release_list(taken);
 }
 bool ws_is_enabled() {
     std::lock_guard<std::mutex> lock(g_ws.mu);
@@ -79,6 +108,10 @@ bool ws_is_enabled() {
 void ws_set_enabled(bool on) {
     { std::lock_guard<std::mutex> lock(g_ws.mu); g_ws.enabled = on; g_ws.env_read = true; }
     if (!on) ws_release();
+}
+void ws_arena_begin() { t_arena.depth++; }
+void ws_arena_end() {
+    if (t_arena.depth > 0 && --t_arena.depth == 0) release_list(t_arena.free_);
 }
 
 void cuda_fail(const char *what, cudaError_t e, const char *file, int line) {
@@ -355,10 +388,7 @@ double *CudaBackend::vec_alloc() {
 }
 
 void CudaBackend::lbfgs_alloc(int m) {
-    if (m > k::kMaxMem) {
-        std::fprintf(stderr, "flgpu: LBFGS Memory=%d exceeds the supported maximum %d\n", m, k::kMaxMem);
-        std::abort();
-    }
+    if (m > k::kMaxMem) fatal("LBFGS Memory above FLGPU_MAX_MEMORY reached the backend (internal error: the API checks it)");
     mem = m;
     alloc_work(nd_of(m));
     auto dalloc = [&](size_t bytes) {

@@ -42,6 +42,9 @@ void ws_free(void *p, size_t bytes);
 void ws_release();
 void ws_set_enabled(bool on);
 bool ws_is_enabled();
+// per-thread arena: buffers freed between begin/end are parked for this thread's next allocation, released at end
+void ws_arena_begin();
+void ws_arena_end();
 
 // ---- per-stream scratch of the built-in objectives / primitives (objectives.cu)
 void scratch_release(cudaStream_t s);

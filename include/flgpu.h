@@ -34,10 +34,9 @@ extern "C" {
 
 /* ------------------------------------------------------------------ callbacks */
 
-/* Reference callback ABI (f90:33-38, hpp:281-284).  Under the Fortran-ABI entry points
- * x and fdx are DEVICE pointers by default (flgpu_set_callback_space); fx is a host
- * scalar that must be valid when the callback returns.  Work must be enqueued on
- * flgpu_current_stream(). */
+/* Reference callback ABI (f90:33-38, hpp:281-284).  Under the Fortran-ABI entry points x and fdx are HOST pointers
+ * by default, DEVICE pointers for callbacks known or declared to be device code (flgpu_set_callback_space); fx is a
+ * host scalar that must be valid when the callback returns.  Device callbacks enqueue on flgpu_current_stream(). */
 typedef void (*flgpu_ref_f_fn)(double *fx, const double *x, const int *dim);
 typedef void (*flgpu_ref_fd_fn)(double *fdx, const double *x, const int *dim);
 typedef int (*flgpu_ref_f_fd_fn)(double *fx, double *fdx, const double *x, const int *dim);
@@ -149,8 +148,17 @@ enum {
     FLGPU_STEP_CONVERGED = 1,   /* |p|^2 a^2 < MinStepLength^2 (f90:615) */
     FLGPU_MAX_ITERATION = 2,    /* f90:580 */
     FLGPU_INITIAL_CONVERGED = 3,/* f90:443 */
-    FLGPU_STOPPED_BY_OBSERVER = 4
+    FLGPU_STOPPED_BY_OBSERVER = 4,
+    FLGPU_INVALID_ARGUMENT = 5  /* the call was refused (see the return code); x is unchanged */
 };
+/* Return codes of the flgpu_* entry points.  CUDA / NCCL failures still abort with a message: like the reference,
+ * the optimizers have no channel to report them and no way to continue. */
+enum { FLGPU_OK = 0, FLGPU_ERR_MEMORY_LIMIT = 2 };
+/* Largest LBFGS Memory the kernels hold (K2: two ring slots per lane of one warp; K3: coefficient tables in shared
+ * memory).  The reference allocates s(dim,0:mem) for any mem (f90:419-420, 435) and recommends [3, 30] (f90:397).
+ * flgpu_lbfgs refuses a larger Memory with FLGPU_ERR_MEMORY_LIMIT; the Fortran-ABI symbol, which cannot return an
+ * error, prints a warning and runs with Memory = FLGPU_MAX_MEMORY. */
+#define FLGPU_MAX_MEMORY 64
 
 
 /* Per outer iteration, called on the host after the line search accepted a step.
@@ -174,7 +182,7 @@ typedef int (*flgpu_observer_fn)(void *user, const flgpu_iter_info *info);
 /* Tunables: names, defaults and fail-safe clamps of f90:417-434 (LBFGS), f90:212-229
  * (CG) and f90:1478-1479 (Increment).  Fill with flgpu_options_default(). */
 typedef struct flgpu_options {
-    int memory;             /* LBFGS Memory, default 10, clamped max(1,.) */
+    int memory;             /* LBFGS Memory, default 10, clamped max(1,.); at most FLGPU_MAX_MEMORY */
     int method;             /* CG: FLGPU_CG_DY (default) / FLGPU_CG_PR */
     int strong;             /* default 1 */
     int warning;            /* default 1 */
@@ -213,8 +221,8 @@ typedef struct flgpu_stats {
 void flgpu_options_default(flgpu_options *o, int for_cg);
 
 /* x: n_local doubles, host (x_space = FLGPU_SPACE_HOST) or device memory; in: initial
- * guess, out: minimiser (f90:52).  Returns 0, or aborts on CUDA/NCCL failure (the
- * reference has no error channel either). */
+ * guess, out: minimiser (f90:52).  Returns FLGPU_OK, or FLGPU_ERR_MEMORY_LIMIT (nothing done); aborts on CUDA/NCCL
+ * failure (the reference has no error channel either). */
 int flgpu_lbfgs(const flgpu_problem *prob, const flgpu_options *opt, double *x, int64_t n_local,
                 int x_space, flgpu_stats *stats);
 int flgpu_conjugate_gradient(const flgpu_problem *prob, const flgpu_options *opt, double *x,
@@ -278,10 +286,13 @@ void flgpu_comm_destroy(flgpu_comm *c);
 int flgpu_comm_uses_peer_memory(const flgpu_comm *c);
 
 /* ------------------------------------------------------------------ Fortran ABI (drop-in symbols) */
-/* Where x and the callbacks' vectors live for the entry points below.  Defaults:
- * x in HOST memory (as in the reference), callbacks receive DEVICE pointers.  With
- * callback space HOST the library stages x/f' through pinned host buffers so that
- * unmodified host callbacks (e.g. the reference's test/test.cpp) keep working.
+/* Where x and the callbacks' vectors live for the entry points below.  Defaults: x in HOST memory and HOST
+ * callbacks, exactly what a program compiled against the reference passes: the library stages x / f' through pinned
+ * host buffers around every callback, so unmodified code (e.g. the reference's test/test.cpp) runs as it is -- correct,
+ * and PCIe-bound.  Objectives the library knows to be device callbacks -- its built-in ones
+ * (flgpu_builtin_ref_callbacks) and anything registered with flgpu_register_fused -- get DEVICE pointers without any
+ * setting.  A user callback that expects device pointers and is not registered opts in with
+ * flgpu_set_callback_space(FLGPU_SPACE_DEVICE) or FLGPU_CALLBACK_SPACE=device.  -1 restores the automatic choice.
  * Environment overrides: FLGPU_X_SPACE, FLGPU_CALLBACK_SPACE = host|device. */
 void flgpu_set_x_space(int space);
 void flgpu_set_callback_space(int space);

@@ -1,7 +1,7 @@
 // Drop-in check in the manner of the reference's test/test.cpp:84-101: host callbacks written the way
 // a user of libFL.so writes them (f = sum x^4, f' = 4 x^3, dim = 10, start in [0,1)^10), called
 // through the FL::NO wrappers, linked against libflgpu.so instead of libFL.so.
-// Run with FLGPU_CALLBACK_SPACE=host (the callbacks dereference host pointers).
+// Host callbacks are the default for the reference-named symbols: no setting is needed.
 // "Correct routines should print close to 0" (test.cpp:74): exit status 0 iff every norm < 1e-3.
 #include <cmath>
 #include <cstdio>

@@ -2,7 +2,7 @@
 // included by absolute path, never copied): the optimizer calls of the reference's test/test.cpp:84-124 that lie on
 // the hot path, with host callbacks exactly as a libFL user writes them.  __graft_entry__.build() compiles it here,
 // where the reference tree is mounted, against libflgpu.so; the binary travels to the GPU box and
-// tests/test_gpu.py::test_reference_header_program_runs executes it with FLGPU_CALLBACK_SPACE=host.
+// tests/test_gpu.py::test_reference_header_program_runs executes it as it is (host callbacks are the default of the reference-named symbols).
 // "Correct routines should print close to 0" (test.cpp:74): exit status = number of results that are not.
 #include <cmath>
 #include <cstdio>

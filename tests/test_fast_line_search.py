@@ -474,7 +474,7 @@ def test_gpu_fast_fortran_abi_torture_1d_bitwise(fl, case, method):
                 keep[0], keep[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), m, keep[2] if use else None,
                 None, C.byref(C.c_int32(0)), C.byref(C.c_int(30)), None, None, None, None, None, C.c_int(len(m)))
         finally:
-            L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+            L.flgpu_set_callback_space(-1)             # back to the automatic choice
             L.flgpu_set_line_search(-1)
         st = fl.capi.Stats()
         L.flgpu_last_stats(C.byref(st))

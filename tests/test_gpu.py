@@ -381,7 +381,7 @@ def _ref_call_cg(fl, cf, cfd, cffd, x, method, use, maxit):
             keep[0], keep[1], x.ctypes.data_as(C.c_void_p), C.byref(dim), m, keep[2] if use else None,
             None, C.byref(C.c_int32(0)), C.byref(C.c_int(maxit)), None, None, None, None, None, C.c_int(len(m)))
     finally:
-        L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+        L.flgpu_set_callback_space(-1)             # back to the automatic choice
     st = fl.capi.Stats()
     L.flgpu_last_stats(C.byref(st))
     return st
@@ -454,7 +454,7 @@ def test_fortran_abi_steepest_descent(fl):
                 keep2[0], keep2[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), keep2[2] if use else None,
                 None, C.byref(C.c_int32(0)), C.byref(C.c_int(25)), None, None, None, None, None)
         finally:
-            L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+            L.flgpu_set_callback_space(-1)             # back to the automatic choice
         st = fl.capi.Stats()
         L.flgpu_last_stats(C.byref(st))
         assert fa.xs == fb.xs, "different trial points"
@@ -726,7 +726,7 @@ def test_fortran_abi_augmented_lagrangian(fl):
             b"LBFGS", None, None, None, None, None, None, None, None, None, C.byref(C.c_int32(0)),
             C.byref(C.c_int(60)), C.byref(C.c_double(1e-10)), None, None, None, None, C.c_int(5), C.c_int(0))
     finally:
-        L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+        L.flgpu_set_callback_space(-1)             # back to the automatic choice
     assert abs(np.linalg.norm(x) - 1.0) < 1e-9
 
 
@@ -736,7 +736,7 @@ def test_cpp_dropin_program_runs(fl, tmp_path):
     libdir = os.path.join(ROOT, "fortran_library_b200")
     subprocess.run(["g++", "-std=c++11", os.path.join(ROOT, "tests", "link", "cpp_dropin.cpp"), "-o", str(exe),
                     "-L" + libdir, "-lflgpu", "-Wl,-rpath," + libdir], check=True)
-    env = dict(os.environ, FLGPU_CALLBACK_SPACE="host")
+    env = {k: v for k, v in os.environ.items() if k != "FLGPU_CALLBACK_SPACE"}   # host callbacks are the default
     r = subprocess.run([str(exe)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
 
@@ -795,7 +795,7 @@ def test_reference_header_program_runs(fl):
     exe = os.path.join(ROOT, "tests", "link", "ref_header_prog")
     if not os.path.exists(exe):
         pytest.skip("tests/link/ref_header_prog was not built (reference header not mounted at build time)")
-    env = dict(os.environ, FLGPU_CALLBACK_SPACE="host")
+    env = {k: v for k, v in os.environ.items() if k != "FLGPU_CALLBACK_SPACE"}   # host callbacks are the default
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
 
@@ -828,12 +828,26 @@ def test_edge_cases(fl):
     assert st.iterations == 4 and st.status == fl.MAX_ITERATION and st.n_f_fd == 1
 
 
-def test_memory_above_limit_aborts_with_message(fl):
-    code = ("import sys; sys.path.insert(0, %r)\nimport fortran_library_b200 as fl\n"
-            "x = fl.DeviceVector.start(fl.START_ROSEN_PERT, 100, seed=7)\n"
-            "fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=65, Warning=False)\n" % ROOT)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
-    assert r.returncode != 0 and "exceeds the supported maximum" in r.stderr
+def test_memory_above_limit_is_refused_not_fatal(fl):
+    """The reference allocates s(dim,0:mem) for any Memory (f90:419-420); the kernels hold FLGPU_MAX_MEMORY = 64 pairs.
+    flgpu_lbfgs refuses more with an error code (x untouched, the process lives); the Fortran-ABI symbol, which has no
+    error channel, warns and runs with 64."""
+    x0 = _cases.start("rosenR1", 100)
+    x = fl.DeviceVector.from_numpy(x0)
+    with pytest.raises(fl.FlgpuError, match="FLGPU_MAX_MEMORY"):
+        fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=65, Warning=False)
+    assert np.array_equal(x.numpy(), x0)
+    st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=64, Warning=False, MaxIteration=5)
+    assert st.iterations == 69
+    L = fl.lib()
+    f, fd, ffd = fl.capi.REF_F_FN(), fl.capi.REF_FD_FN(), fl.capi.REF_F_FD_FN()
+    L.flgpu_builtin_ref_callbacks(fl.OBJ_ROSENBROCK, C.byref(f), C.byref(fd), C.byref(ffd))
+    xa, xb = x0.copy(), x0.copy()
+    sym = L.__getattr__("__nonlinearoptimization_MOD_lbfgs")
+    for xv, mem in ((xa, 100), (xb, 64)):
+        sym(f, fd, xv.ctypes.data_as(C.c_void_p), C.byref(C.c_int(100)), C.byref(C.c_int(mem)), ffd, None,
+            C.byref(C.c_int32(0)), C.byref(C.c_int(5)), None, None, None, None, None)
+    assert np.array_equal(xa, xb)
 
 
 # ----------------------------------------------------------------------------- full size (BASELINE configs[1], [2])

@@ -146,7 +146,7 @@ def test_gpu_fortran_abi_trajectories_are_bitwise_the_oracles(algo, kind, p, q, 
             L.__getattr__("__nonlinearoptimization_MOD_steepestdescent")(
                 k2[0], k2[1], x.ctypes.data_as(C.c_void_p), C.byref(C.c_int(1)), k2[2] if use else None, *common)
     finally:
-        L.flgpu_set_callback_space(fl.SPACE_DEVICE)
+        L.flgpu_set_callback_space(-1)             # back to the automatic choice
     stt = fl.capi.Stats()
     L.flgpu_last_stats(C.byref(stt))
     assert fa.xs == fb.xs, "different trial points"
