@@ -12,6 +12,7 @@ import os
 
 from . import _capi as capi
 from ._capi import (CG_DY, CG_PR, LS_REFERENCE, LS_FAST, SPACE_HOST, SPACE_DEVICE, OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD,  # noqa: F401
+                    OBJ_QUARTIC_SHIFTED,
                     START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO, CONVERGED,
                     STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER, AL_LBFGS, AL_CG,
                     CON_SPHERE)

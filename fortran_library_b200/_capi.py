@@ -7,7 +7,7 @@ LS_REFERENCE, LS_FAST = 0, 1
 SPACE_HOST, SPACE_DEVICE = 0, 1
 CONVERGED, STEP_CONVERGED, MAX_ITERATION, INITIAL_CONVERGED, STOPPED_BY_OBSERVER, INVALID_ARGUMENT = 0, 1, 2, 3, 4, 5
 ERR_MEMORY_LIMIT, MAX_MEMORY = 2, 64
-OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD = 0, 1, 2
+OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD, OBJ_QUARTIC_SHIFTED = 0, 1, 2, 3
 START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO = 0, 1, 2, 3
 
 

@@ -571,17 +571,10 @@ DeviceFacts &facts(int device) {
 }
 }  // namespace
 
-// K1 shape for `rem` older columns still to be covered: (columns per group, groups per warp)
+// K1 shape for `rem` older columns still to be covered (k1_pass_shape, flgpu_lbfgs_gram.hpp), or the tuning override
 void k1_shape_for(int rem, int &mt, int &ng) {
-    if (g_k1_shape[0] > 0) { mt = g_k1_shape[0]; ng = g_k1_shape[1]; }   // tuning override (flgpu_debug_set_k1_shape)
-    else if (rem <= 2)  { mt = 2; ng = 1; }
-    else if (rem <= 4)  { mt = 4; ng = 1; }
-    else if (rem <= 5)  { mt = 5; ng = 1; }
-    else if (rem <= 8)  { mt = 4; ng = 2; }
-    else                { mt = 5; ng = 2; }   // 10 columns per pass; m = 30 takes 3 passes
-    // Measured on B200 (profiles/r01_k1_shapes.md): shapes with 4 or 8 groups per warp (128 / 64-byte
-    // column runs) or more than 5 columns per thread (> 128 registers, 1 CTA/SM) run at 2.6-5.6 TB/s;
-    // <5,2> (256-byte runs, 2 CTAs/SM) sustains 6.3-7.0 TB/s even counting the re-read of x, g per pass.
+    if (g_k1_shape[0] > 0) { mt = g_k1_shape[0]; ng = g_k1_shape[1]; }   // flgpu_debug_set_k1_shape
+    else k1_pass_shape(rem, mt, ng);
 }
 
 // The K1 passes over the k_after-1 older columns (NG*MT per pass; the first pass also builds the new column).  With a

@@ -5,6 +5,7 @@
 //                                                    x**4 = (x*x)*(x*x), x**3 = (x*x)*x as gfortran expands them)
 //   Rosenbrock  f = sum_j 100 (x_{2j+1} - x_{2j}^2)^2 + (1 - x_{2j})^2   (extended, pairwise)
 //   diag quad   f = 1/2 sum d_i (x_i - 1)^2, d_i log-uniform in [1, 1e6]
+//   quartic1    f = sum (x-1)^4 + (x-1)^2       (the quartic with a non-zero, well-conditioned minimiser x* = 1)
 //
 // Element-wise arithmetic uses separate multiply/add roundings in the same order as the CPU
 // oracle's objectives so that f' agrees bit for bit for the same x.
@@ -138,6 +139,11 @@ __device__ __forceinline__ void objective_unit(const ObjIndex &ix, int64_t u, co
             g.x = sub(mul(mul(-400.0, x.x), t1), mul(2.0, t2));
             g.y = mul(200.0, t1);
         }
+    } else if (KIND == FLGPU_OBJ_QUARTIC_SHIFTED) {
+        const double t0 = sub(x.x, 1.0), t1 = sub(x.y, 1.0);
+        const double a2 = mul(t0, t0), b2 = mul(t1, t1);
+        if (WANT_F) { fsum += add(mul(a2, a2), a2); fsum += add(mul(b2, b2), b2); }
+        if (NEED_G) { g.x = add(mul(4.0, mul(a2, t0)), mul(2.0, t0)); g.y = add(mul(4.0, mul(b2, t1)), mul(2.0, t1)); }
     } else {
         const double i = ix.offset_d + (double)(2 * u);   // exact: both terms and the sum are integers < 2^53
         const double d0 = ix.coeff(i), d1 = ix.coeff(i + 1.0);
@@ -157,6 +163,10 @@ __device__ __forceinline__ void objective_tail(const ObjIndex &ix, int64_t i, co
         const double t2 = sub(1.0, x);
         if (WANT_F) fsum += mul(t2, t2);
         g = mul(-2.0, t2);
+    } else if (KIND == FLGPU_OBJ_QUARTIC_SHIFTED) {
+        const double t = sub(x, 1.0), t2 = mul(t, t);
+        if (WANT_F) fsum += add(mul(t2, t2), t2);
+        g = add(mul(4.0, mul(t2, t)), mul(2.0, t));
     } else {
         const double d = ix.coeff(ix.offset_d + (double)i), t = sub(x, 1.0);
         if (WANT_F) fsum += mul(mul(mul(0.5, d), t), t);
@@ -513,6 +523,7 @@ void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp
     case FLGPU_OBJ_QUARTIC: FLGPU_OBJ_LAUNCH(FLGPU_OBJ_QUARTIC); break;
     case FLGPU_OBJ_ROSENBROCK: FLGPU_OBJ_LAUNCH(FLGPU_OBJ_ROSENBROCK); break;
     case FLGPU_OBJ_DIAGQUAD: FLGPU_OBJ_LAUNCH(FLGPU_OBJ_DIAGQUAD); break;
+    case FLGPU_OBJ_QUARTIC_SHIFTED: FLGPU_OBJ_LAUNCH(FLGPU_OBJ_QUARTIC_SHIFTED); break;
     default: fatal("unknown built-in objective");
     }
 #undef FLGPU_OBJ_LAUNCH
@@ -632,6 +643,7 @@ extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<0>; return 0;
     case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<1>; return 0;
     case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<2>; return 0;
+    case FLGPU_OBJ_QUARTIC_SHIFTED: out->f = dev_f<3>; out->fd = dev_fd<3>; out->f_fd = dev_ffd<3>; out->fused = dev_fused<3>; out->search = dev_search<3>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<3>; return 0;
     }
     return 1;
 }
@@ -642,12 +654,14 @@ flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f) {
     if (f == ref_f<0>) return dev_fused<0>;
     if (f == ref_f<1>) return dev_fused<1>;
     if (f == ref_f<2>) return dev_fused<2>;
+    if (f == ref_f<3>) return dev_fused<3>;
     return nullptr;
 }
 flgpu_update_fn builtin_update_for(flgpu_ref_f_fn f) {
     if (f == ref_f<0>) return dev_update<0>;
     if (f == ref_f<1>) return dev_update<1>;
     if (f == ref_f<2>) return dev_update<2>;
+    if (f == ref_f<3>) return dev_update<3>;
     return nullptr;
 }
 }  // namespace flgpu
@@ -657,6 +671,7 @@ extern "C" int flgpu_builtin_ref_callbacks(int kind, flgpu_ref_f_fn *f, flgpu_re
     case FLGPU_OBJ_QUARTIC: *f = ref_f<0>; *fd = ref_fd<0>; *f_fd = ref_ffd<0>; return 0;
     case FLGPU_OBJ_ROSENBROCK: *f = ref_f<1>; *fd = ref_fd<1>; *f_fd = ref_ffd<1>; return 0;
     case FLGPU_OBJ_DIAGQUAD: *f = ref_f<2>; *fd = ref_fd<2>; *f_fd = ref_ffd<2>; return 0;
+    case FLGPU_OBJ_QUARTIC_SHIFTED: *f = ref_f<3>; *fd = ref_fd<3>; *f_fd = ref_ffd<3>; return 0;
     }
     return 1;
 }

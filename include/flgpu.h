@@ -374,7 +374,8 @@ void nonlinearoptimization_mp_conjugategradient_basic_(
 
 /* ------------------------------------------------------------------ built-in objectives (CUDA) */
 /* The synthetic objectives of the benchmark configs (BASELINE.json), as CUDA kernels. */
-enum { FLGPU_OBJ_QUARTIC = 0, FLGPU_OBJ_ROSENBROCK = 1, FLGPU_OBJ_DIAGQUAD = 2 };
+/* QUARTIC_SHIFTED: f = sum (x-1)^4 + (x-1)^2, x* = 1 -- the quartic with a non-zero, well-conditioned minimiser */
+enum { FLGPU_OBJ_QUARTIC = 0, FLGPU_OBJ_ROSENBROCK = 1, FLGPU_OBJ_DIAGQUAD = 2, FLGPU_OBJ_QUARTIC_SHIFTED = 3 };
 enum { FLGPU_START_QUARTIC_U = 0, FLGPU_START_ROSEN_STD = 1, FLGPU_START_ROSEN_PERT = 2, FLGPU_START_ZERO = 3 };
 /* 64-bit device-callback form */
 int flgpu_builtin_problem(int kind, flgpu_problem *out);

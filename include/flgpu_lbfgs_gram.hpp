@@ -34,6 +34,19 @@ FLGPU_HD inline int nc_of(int m) { return 2 * m + 1; }
 // slot of the t-th newest pair (t = 0 is `recent`), valid for t < k (f90:590-597 visiting order)
 FLGPU_HD inline int slot_of_age(int recent, int t, int m) { return (recent - t + m) % m; }
 
+// K1 covers the k-1 older columns in passes; thread shape of the pass that still has `rem` columns to cover:
+// MT columns per thread group, NG groups per warp (include/flgpu_k1.cuh).  Shared with the test host simulator, which
+// models the kernels' summation order.  Measured on B200 (profiles/r01_k1_shapes.md): shapes with 4 or 8 groups per
+// warp (128 / 64-byte column runs) or more than 5 columns per thread (> 128 registers, 1 CTA/SM) run at 2.6-5.6 TB/s;
+// <5,2> (256-byte runs, 2 CTAs/SM) sustains 6.3-7.0 TB/s even counting the re-read of x, g per pass.
+inline void k1_pass_shape(int rem, int &mt, int &ng) {
+    if (rem <= 2)      { mt = 2; ng = 1; }
+    else if (rem <= 4) { mt = 4; ng = 1; }
+    else if (rem <= 5) { mt = 5; ng = 1; }
+    else if (rem <= 8) { mt = 4; ng = 2; }
+    else               { mt = 5; ng = 2; }   // 10 columns per pass; m = 30 takes 3 passes
+}
+
 // Scalar statement of K2.  D: global dots; SY, YY: persistent m x m row-major Gram blocks in
 // ring-slot indexing, updated in place with the newest pair (slot `recent`); C: coefficients.
 // sq, yq, al: work arrays of m doubles.  Multiplies and adds are separate roundings.

@@ -1,8 +1,11 @@
 /*
  * oracle/objectives.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * The three synthetic objectives of SURVEY.md 8(d) as reference-ABI callbacks
- * (f90:33-38).  Only the quartic exists in the reference (test/test.f90:630-663:
+ * The synthetic objectives of SURVEY.md 8(d) as reference-ABI callbacks
+ * (f90:33-38), plus the quartic shifted to a non-zero, well-conditioned minimiser
+ * (f = sum (x-1)^4 + (x-1)^2, x* = 1: "minimisers to relative 1e-8" needs a scale and
+ * linear convergence, which sum x^4 with x* = 0 does not offer).
+ * Only the quartic exists in the reference (test/test.f90:630-663:
  * f = sum x**4, f' = 4 x**3, evaluated as gfortran expands integer powers:
  * x**4 = (x*x)*(x*x), x**3 = (x*x)*x).  Extended Rosenbrock and the diagonal
  * quadratic are defined here; the CUDA objective kernels use the same operation
@@ -125,6 +128,13 @@ static double eval_range(int want_f, double *g, const double *x, long lo, long h
             if (want_f) facc_add(&f, t2 * t2);
             if (g) g[i] = -2.0 * t2;
         }
+    } else if (g_kind == ORC_OBJ_QUARTIC_SHIFTED) {
+        for (long i = lo; i < hi; i++) {
+            const double t = x[i] - 1.0;
+            const double t2 = t * t;
+            if (want_f) facc_add(&f, t2 * t2 + t2);
+            if (g) g[i] = 4.0 * (t2 * t) + 2.0 * t;
+        }
     } else {
         for (long i = lo; i < hi; i++) {
             const double d = orc_diag_coeff(g_offset + i, g_nglobal);
@@ -161,6 +171,33 @@ static int eval(double *fx, double *g, const double *x, int n) {
     if (fx) *fx = f;
 #endif
     return 0;
+}
+
+/* f-term of every element (Rosenbrock: the pair's term at the even index, +0.0 at the odd one; the unpaired last
+ * element of an odd-length problem carries its own term), in the arithmetic of eval_range().  For the host simulator's
+ * bit-level model of the CUDA reductions (tests/hostsim): sum of terms[] in any order = f. */
+void orc_obj_terms(double *terms, const double *x, const int *dim) {
+    const long n = *dim;
+    if (g_kind == ORC_OBJ_QUARTIC) {
+        for (long i = 0; i < n; i++) { const double x2 = x[i] * x[i]; terms[i] = x2 * x2; }
+    } else if (g_kind == ORC_OBJ_ROSENBROCK) {
+        long i = 0;
+        for (; i + 1 < n; i += 2) {
+            const double a = x[i], b = x[i + 1];
+            const double t1 = b - a * a, t2 = 1.0 - a;
+            terms[i] = (100.0 * t1) * t1 + t2 * t2;
+            terms[i + 1] = 0.0;
+        }
+        if (i < n) { const double t2 = 1.0 - x[i]; terms[i] = t2 * t2; }
+    } else if (g_kind == ORC_OBJ_QUARTIC_SHIFTED) {
+        for (long i = 0; i < n; i++) { const double t = x[i] - 1.0; const double t2 = t * t; terms[i] = t2 * t2 + t2; }
+    } else {
+        for (long i = 0; i < n; i++) {
+            const double d = orc_diag_coeff(g_offset + i, g_nglobal);
+            const double t = x[i] - 1.0;
+            terms[i] = ((0.5 * d) * t) * t;
+        }
+    }
 }
 
 void orc_obj_f(double *fx, const double *x, const int *dim) { eval(fx, 0, x, *dim); }

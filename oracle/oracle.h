@@ -130,7 +130,7 @@ void orc_strongwolfe_fdwithf(const double *c1, const double *c2, orc_f_t f, orc_
                              const double *Increment);
 
 /* ---- synthetic objectives (oracle/objectives.c), SURVEY.md 8(d) ---- */
-enum { ORC_OBJ_QUARTIC = 0, ORC_OBJ_ROSENBROCK = 1, ORC_OBJ_DIAGQUAD = 2 };
+enum { ORC_OBJ_QUARTIC = 0, ORC_OBJ_ROSENBROCK = 1, ORC_OBJ_DIAGQUAD = 2, ORC_OBJ_QUARTIC_SHIFTED = 3 };
 enum { ORC_START_QUARTIC_U = 0, ORC_START_ROSEN_STD = 1, ORC_START_ROSEN_PERT = 2, ORC_START_ZERO = 3 };
 /* Select the objective the three callbacks below evaluate.  offset/n_global let a
  * row shard be evaluated (index-dependent objectives). */
@@ -138,6 +138,7 @@ void orc_obj_select(int kind, long long offset, long long n_global);
 /* summation order of the objective VALUE (0 sequential = reference test callback, 1 long double,
  * 2 pairwise); orc_set_sum_mode() sets it too, so the noise envelope covers every reduction. */
 void orc_obj_set_sum_mode(int mode);
+void orc_obj_terms(double *terms, const double *x, const int *dim);
 void orc_obj_f(double *fx, const double *x, const int *dim);
 void orc_obj_fd(double *fdx, const double *x, const int *dim);
 int orc_obj_f_fd(double *fx, double *fdx, const double *x, const int *dim);

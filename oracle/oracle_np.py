@@ -588,6 +588,22 @@ def quartic():
     return f, fd, f_fd
 
 
+def quartic_shifted():
+    """f = sum (x-1)^4 + (x-1)^2 (objectives.c ORC_OBJ_QUARTIC_SHIFTED): x* = 1, Hessian 2 at the minimiser."""
+    def f(x):
+        t = x - 1.0
+        t2 = t * t
+        return float(np.cumsum(t2 * t2 + t2)[-1])
+
+    def fd(x):
+        t = x - 1.0
+        return 4.0 * ((t * t) * t) + 2.0 * t
+
+    def f_fd(x):
+        return f(x), fd(x)
+    return f, fd, f_fd
+
+
 def rosenbrock():
     def parts(x):
         a = x[0::2]; b = x[1::2]

@@ -11,6 +11,8 @@ OBJECTIVES = {
     "rosenR1": (O.OBJ_ROSENBROCK, O.START_ROSEN_PERT, 7),
     "quartic": (O.OBJ_QUARTIC, O.START_QUARTIC_U, 12345),
     "diag": (O.OBJ_DIAGQUAD, O.START_ZERO, 0),
+    # sum (x-1)^4 + (x-1)^2 from u in [0,1): x* = 1, Hessian 2 at the minimiser -- the CG case with a well-defined minimiser
+    "quartic1": (O.OBJ_QUARTIC_SHIFTED, O.START_QUARTIC_U, 12345),
 }
 
 
@@ -23,7 +25,8 @@ def rel(a, b):
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
 
 
-ENV_FACTOR = 64.0    # allowed multiple of the oracle's own summation-order noise (same order of magnitude)
+ENV_FACTOR = 4.0     # allowed multiple of the oracle's own summation-order noise (measured on B200 over every case of
+                     # the GPU suite, tests/gpu_calibrate.py: worst ratio 1.66, typical 0.0-0.5)
 FLOOR = 1e-12        # north_star tolerance, asserted wherever that noise is below it
 
 
@@ -57,11 +60,10 @@ def two_loop_extended(pairs, g):
     return np.asarray(-q, dtype=np.float64)
 
 
-def check_one_step(history_cls, name, mem, n=2000, steps=20):
+def check_one_step(history_cls, name, mem, n=2000, steps=20, strict=True):
     """One-step direction parity (strict tier): fed the ORACLE's own accepted points and gradients,
-    the compact two-loop (K1+K2+K3) must reproduce the direction to 1e-12 -- or, where the
-    reference's own sequential arithmetic is further than that from the exact (extended-precision)
-    two-loop on the same history, to within 4x that distance."""
+    the compact two-loop (K1+K2+K3) must reproduce the exact (extended-precision) two-loop direction on the
+    same history to 1e-12, the north_star tolerance, on every objective."""
     import ctypes as C
     kind = OBJECTIVES[name][0]
     x0 = start(name, n)
@@ -82,10 +84,13 @@ def check_one_step(history_cls, name, mem, n=2000, steps=20):
         noise = rel(tr.p[k + 1], exact)            # the reference's own rounding error on this step
         err = rel(p, exact)
         worst = max(worst, err)
-        # rosenR0 is degenerate (n/2 identical 2-D problems: the Gram matrix of the pairs has rank 2), which
-        # costs the Gram-space recurrences two digits (DESIGN.md "accuracy of the compact form")
-        floor = 1e-10 if name == "rosenR0" else 1e-12
-        assert err <= max(floor, 4.0 * noise), f"direction after step {k}: {err:.2e} (reference's own: {noise:.2e})"
+        # north_star: search directions to relative 1e-12.  Measured (tests/gpu_calibrate.py): <= 1.3e-15 on the
+        # benchmark objectives, 9.5e-14 on the degenerate standard-start Rosenbrock (n/2 identical 2-D problems: the
+        # Gram matrix of the pairs has rank 2), where the oracle's own sequential sums are 3.2e-12 from the exact value
+        # (strict=False: the CPU host simulator, whose blocked sequential sums are only as accurate as the oracle's:
+        # within 4x the oracle's own distance from the exact direction)
+        bound = 1e-12 if strict else max(1e-12, 4.0 * noise)
+        assert err <= bound, f"direction after step {k}: {err:.2e} (reference's own: {noise:.2e})"
         assert np.array_equal(xt, xs[k + 1] + p)
         assert abs(gp - float(np.dot(gs[k + 1], p))) <= 1e-10 * abs(gp)
         assert abs(pp - float(np.dot(p, p))) <= 1e-10 * abs(pp)

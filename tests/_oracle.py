@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB_PATH = os.path.join(ORACLE_DIR, "liboracle.so")
 
-OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD = 0, 1, 2
+OBJ_QUARTIC, OBJ_ROSENBROCK, OBJ_DIAGQUAD, OBJ_QUARTIC_SHIFTED = 0, 1, 2, 3
 START_QUARTIC_U, START_ROSEN_STD, START_ROSEN_PERT, START_ZERO = 0, 1, 2, 3
 
 F_T = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int))

@@ -6,9 +6,14 @@
 // over a caller-supplied all-gather (gloo in the tests).  Built into
 // tests/hostsim/libflgpu_hostsim.so; libflgpu.so never links or loads it and has no CPU path.
 //
-// Element-wise arithmetic matches the CUDA kernels (separate multiply and add roundings);
-// reductions are blocked sums, so results agree with the GPU up to summation order only.
+// Element-wise arithmetic matches the CUDA kernels (separate multiply and add roundings), and so do the
+// REDUCTIONS: namespace model below restates include/flgpu_reduce.cuh and each kernel's per-chunk thread order in
+// scalar C++ (which thread adds which 16-byte unit, FMA accumulation, lane butterfly, warps left to right, aligned
+// binary tree over chunks, rank tree) -- an independent statement of the same arithmetic, so a run of the host
+// simulator and a run of libflgpu.so on the GPU agree BIT FOR BIT (tests/test_gpu.py::test_gpu_equals_host_simulator).
+#include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,19 +33,74 @@ allgather_fn g_allgather = nullptr;
 void *g_allgather_user = nullptr;
 int g_rank = 0, g_nranks = 1;
 
-const long BLK = 1024;
+// ---- scalar model of the CUDA reductions (include/flgpu_reduce.cuh + the kernels' per-chunk thread order)
+namespace model {
 
-template <class F>
-double blocked_sum(long n, F term) {
-    double total = 0.0;
-    for (long b = 0; b < n; b += BLK) {
-        double s = 0.0;
-        const long e = b + BLK < n ? b + BLK : n;
-        for (long i = b; i < e; i++) s += term(i);
-        total += s;
-    }
-    return total;
+// aligned binary tree over v[0 .. count) with +0.0 for the missing leaves (cta_tree + top_tree: 2^18 leaves)
+double node(const std::vector<double> &v, int64_t lo, int64_t hi) {
+    if (lo >= (int64_t)v.size()) return 0.0;
+    if (hi - lo == 1) return v[(size_t)lo];
+    const int64_t mid = lo + (hi - lo) / 2;
+    return node(v, lo, mid) + node(v, mid, hi);
 }
+double tree(const std::vector<double> &chunk_sums) {
+    return node(chunk_sums, 0, (int64_t)flgpu::red::kTopMax * flgpu::red::kBlockChunks);
+}
+
+// A reducing kernel: NACC accumulators per thread.  Each chunk of ch elements is summed by a block of 8 warps; a warp
+// holds SEG lanes of the accumulator's column group (SEG = 32 except in K1 with two groups per warp), so TX = 8 * SEG
+// threads share the chunk's 16-byte units: thread tx takes units lo+tx, lo+tx+TX, ... in order (unit(u, acc)); the odd
+// last element of the shard is added by thread 0 of the last chunk after its units (tail(acc)); lanes are combined by an
+// xor butterfly (far first), the 8 warps left to right; the chunk sums by the aligned binary tree.
+template <int NACC, class Unit, class Tail>
+void reduce(int64_t n, int64_t ch, int SEG, Unit unit, Tail tail, double (&out)[NACC]) {
+    const int TX = 8 * SEG;
+    const int64_t nu = n >> 1, cu = ch >> 1, nchunks = flgpu::red::num_chunks(n, ch);
+    std::vector<double> sums[NACC];
+    for (int i = 0; i < NACC; i++) sums[i].assign((size_t)nchunks, 0.0);
+    std::vector<double> acc((size_t)TX * NACC);
+    for (int64_t c = 0; c < nchunks; c++) {
+        const int64_t lo = c * cu, hi = (lo + cu < nu) ? lo + cu : nu;
+        std::fill(acc.begin(), acc.end(), 0.0);
+        for (int tx = 0; tx < TX; tx++)
+            for (int64_t u = lo + tx; u < hi; u += TX) unit(u, &acc[(size_t)tx * NACC]);
+        if ((n & 1) && c == nchunks - 1) tail(&acc[0]);
+        for (int i = 0; i < NACC; i++) {
+            double s = 0.0;
+            for (int q = 0; q < 8; q++) {
+                double v[32], t[32];
+                for (int l = 0; l < SEG; l++) v[l] = acc[(size_t)(q * SEG + l) * NACC + i];
+                for (int o = SEG / 2; o > 0; o >>= 1) {
+                    for (int l = 0; l < SEG; l++) t[l] = v[l] + v[l ^ o];
+                    for (int l = 0; l < SEG; l++) v[l] = t[l];
+                }
+                s += v[0];
+            }
+            sums[i][(size_t)c] = s;
+        }
+    }
+    for (int i = 0; i < NACC; i++) out[i] = tree(sums[i]);
+}
+
+// dot_kernel: a.b
+double dot(const double *a, const double *b, int64_t n, int64_t ch) {
+    double out[1];
+    reduce<1>(n, ch, 32,
+              [&](int64_t u, double *acc) { acc[0] = std::fma(a[2 * u + 1], b[2 * u + 1], std::fma(a[2 * u], b[2 * u], acc[0])); },
+              [&](double *acc) { acc[0] = std::fma(a[n - 1], b[n - 1], acc[0]); }, out);
+    return out[0];
+}
+// objective kernels: f = sum of per-element terms (a unit adds its first element's term, then its second's;
+// Rosenbrock has one term per unit), f'.p as a dot
+double fsum(const double *terms, int64_t n, int64_t ch, bool one_term_per_unit) {
+    double out[1];
+    reduce<1>(n, ch, 32,
+              [&](int64_t u, double *acc) { acc[0] += terms[2 * u]; if (!one_term_per_unit) acc[0] += terms[2 * u + 1]; },
+              [&](double *acc) { acc[0] += terms[n - 1]; }, out);
+    return out[0];
+}
+
+}  // namespace model
 
 class HostBackend : public flgpu::Backend {
 public:
@@ -51,12 +111,14 @@ public:
     int mem = 0;
     double *S = nullptr, *Y = nullptr;
     std::vector<double> SY, YY, D, C, w1, w2, w3;
+    int64_t ch = 1024;     // chunk elements, from the GLOBAL dimension (flgpu_reduce_geom.h)
 
     HostBackend(const flgpu_problem &p, int64_t n_, int64_t offset, int64_t n_global) : prob(p) {
         n = n_;
         std::memset(slots, 0, sizeof slots);
         ctx.user = p.user; ctx.stream = nullptr; ctx.offset = offset;
         ctx.n_global = n_global ? n_global : n_; ctx.rank = g_rank; ctx.nranks = g_nranks; ctx.device = -1;
+        ch = flgpu::red::chunk_elems(ctx.n_global);
     }
     ~HostBackend() override { for (double *v : owned) std::free(v); }
 
@@ -141,28 +203,72 @@ public:
     }
     void dot(const double *a, const double *b, int slot) override {
         launches++;
-        slots[slot] = blocked_sum(n, [&](long i) { return a[i] * b[i]; });
+        slots[slot] = model::dot(a, b, n, ch);
     }
     void neg(double *p, const double *g) override {
         launches++;
         for (long i = 0; i < n; i++) p[i] = -g[i];
     }
 
+    // K1 (include/flgpu_k1.cuh): the new column pair, then every dot in the thread order of the pass that owns it --
+    // pass shapes from k1_pass_shape(); the dots of the new column and g.g belong to group 0 of the first pass
     void lbfgs_update_dots(const double *x1, const double *x0, const double *g1, const double *g0,
                            int new_slot, int k_after) override {
         launches++;
         const int m = mem;
         double *sn = S + (long)new_slot * n, *yn = Y + (long)new_slot * n;
         for (long i = 0; i < n; i++) { sn[i] = x1[i] - x0[i]; yn[i] = g1[i] - g0[i]; }
-        for (int t = 0; t < k_after; t++) {
-            const int j = flgpu::slot_of_age(new_slot, t, m);
-            const double *sj = S + (long)j * n, *yj = Y + (long)j * n;
-            D[flgpu::d_A(m, j)] = blocked_sum(n, [&](long i) { return sj[i] * g1[i]; });
-            D[flgpu::d_B(m, j)] = blocked_sum(n, [&](long i) { return yj[i] * g1[i]; });
-            D[flgpu::d_SYN(m, j)] = blocked_sum(n, [&](long i) { return sj[i] * yn[i]; });
-            D[flgpu::d_YYN(m, j)] = blocked_sum(n, [&](long i) { return yj[i] * yn[i]; });
-        }
-        D[flgpu::d_GG(m)] = blocked_sum(n, [&](long i) { return g1[i] * g1[i]; });
+        const int nother = k_after - 1;
+        int age = 1;
+        bool first = true;
+        do {
+            int mt, ng;
+            flgpu::k1_pass_shape(nother - (age - 1), mt, ng);
+            const int SEG = 32 / ng;
+            auto four = [&](int j) {          // s_j.g1, y_j.g1, s_j.y_new, y_j.y_new
+                const double *sj = S + (long)j * n, *yj = Y + (long)j * n;
+                double out[4];
+                model::reduce<4>(n, ch, SEG,
+                    [&](int64_t u, double *acc) {
+                        const long a = 2 * u, b = 2 * u + 1;
+                        acc[0] = std::fma(sj[b], g1[b], std::fma(sj[a], g1[a], acc[0]));
+                        acc[1] = std::fma(yj[b], g1[b], std::fma(yj[a], g1[a], acc[1]));
+                        acc[2] = std::fma(sj[b], yn[b], std::fma(sj[a], yn[a], acc[2]));
+                        acc[3] = std::fma(yj[b], yn[b], std::fma(yj[a], yn[a], acc[3]));
+                    },
+                    [&](double *acc) {
+                        const long i = n - 1;
+                        acc[0] = std::fma(sj[i], g1[i], acc[0]); acc[1] = std::fma(yj[i], g1[i], acc[1]);
+                        acc[2] = std::fma(sj[i], yn[i], acc[2]); acc[3] = std::fma(yj[i], yn[i], acc[3]);
+                    }, out);
+                D[flgpu::d_A(m, j)] = out[0]; D[flgpu::d_B(m, j)] = out[1];
+                D[flgpu::d_SYN(m, j)] = out[2]; D[flgpu::d_YYN(m, j)] = out[3];
+            };
+            if (first) {                      // g.g, sn.g, yn.g, sn.yn, yn.yn
+                double out[5];
+                model::reduce<5>(n, ch, SEG,
+                    [&](int64_t u, double *acc) {
+                        const long a = 2 * u, b = 2 * u + 1;
+                        acc[0] = std::fma(g1[b], g1[b], std::fma(g1[a], g1[a], acc[0]));
+                        acc[1] = std::fma(sn[b], g1[b], std::fma(sn[a], g1[a], acc[1]));
+                        acc[2] = std::fma(yn[b], g1[b], std::fma(yn[a], g1[a], acc[2]));
+                        acc[3] = std::fma(sn[b], yn[b], std::fma(sn[a], yn[a], acc[3]));
+                        acc[4] = std::fma(yn[b], yn[b], std::fma(yn[a], yn[a], acc[4]));
+                    },
+                    [&](double *acc) {
+                        const long i = n - 1;
+                        acc[0] = std::fma(g1[i], g1[i], acc[0]); acc[1] = std::fma(sn[i], g1[i], acc[1]);
+                        acc[2] = std::fma(yn[i], g1[i], acc[2]); acc[3] = std::fma(sn[i], yn[i], acc[3]);
+                        acc[4] = std::fma(yn[i], yn[i], acc[4]);
+                    }, out);
+                D[flgpu::d_GG(m)] = out[0];
+                D[flgpu::d_A(m, new_slot)] = out[1]; D[flgpu::d_B(m, new_slot)] = out[2];
+                D[flgpu::d_SYN(m, new_slot)] = out[3]; D[flgpu::d_YYN(m, new_slot)] = out[4];
+            }
+            for (int t = age; t < age + mt * ng && t < k_after; t++) four(flgpu::slot_of_age(new_slot, t, m));
+            age += mt * ng;
+            first = false;
+        } while (age - 1 < nother);
         slots[flgpu::SL_GG] = D[flgpu::d_GG(m)];
     }
     void lbfgs_solve(int k, int recent) override {
@@ -191,22 +297,36 @@ public:
             p[i] = -r;
             if (xt) xt[i] = x1[i] + p[i];
         }
-        slots[flgpu::SL_GP0] = blocked_sum(n, [&](long i) { return g1[i] * p[i]; });
-        slots[flgpu::SL_PP] = blocked_sum(n, [&](long i) { return p[i] * p[i]; });
+        double out[2];                      // K3: g.p and p.p in one kernel (256 threads per chunk)
+        model::reduce<2>(n, ch, 32,
+            [&](int64_t u, double *acc) {
+                const long a = 2 * u, b = 2 * u + 1;
+                acc[0] = std::fma(g1[b], p[b], std::fma(g1[a], p[a], acc[0]));
+                acc[1] = std::fma(p[b], p[b], std::fma(p[a], p[a], acc[1]));
+            },
+            [&](double *acc) { const long i = n - 1; acc[0] = std::fma(g1[i], p[i], acc[0]); acc[1] = std::fma(p[i], p[i], acc[1]); },
+            out);
+        slots[flgpu::SL_GP0] = out[0];
+        slots[flgpu::SL_PP] = out[1];
     }
 
     void cg_dots(const double *g1, const double *g0, const double *p) override {
         launches++;
-        slots[flgpu::SL_GG] = blocked_sum(n, [&](long i) { return g1[i] * g1[i]; });
-        slots[flgpu::SL_PP] = blocked_sum(n, [&](long i) { return p[i] * p[i]; });
-        slots[flgpu::SL_DGP] = blocked_sum(n, [&](long i) { return (g1[i] - g0[i]) * p[i]; });
-        slots[flgpu::SL_GDG] = blocked_sum(n, [&](long i) { return g1[i] * (g1[i] - g0[i]); });
-        slots[flgpu::SL_G0G0] = blocked_sum(n, [&](long i) { return g0[i] * g0[i]; });
+        auto term = [&](long i, double *acc) {        // cg_dots_kernel's `term`
+            const double a = g1[i], b = g0[i], q = p[i], d = a - b;
+            acc[0] = std::fma(a, a, acc[0]); acc[1] = std::fma(q, q, acc[1]); acc[2] = std::fma(d, q, acc[2]);
+            acc[3] = std::fma(a, d, acc[3]); acc[4] = std::fma(b, b, acc[4]);
+        };
+        double out[5];
+        model::reduce<5>(n, ch, 32, [&](int64_t u, double *acc) { term(2 * u, acc); term(2 * u + 1, acc); },
+                         [&](double *acc) { term(n - 1, acc); }, out);
+        slots[flgpu::SL_GG] = out[0]; slots[flgpu::SL_PP] = out[1]; slots[flgpu::SL_DGP] = out[2];
+        slots[flgpu::SL_GDG] = out[3]; slots[flgpu::SL_G0G0] = out[4];
     }
     void cg_update(double *p, const double *g1, double beta) override {
         launches++;
         for (long i = 0; i < n; i++) p[i] = -g1[i] + beta * p[i];
-        slots[flgpu::SL_GP0] = blocked_sum(n, [&](long i) { return g1[i] * p[i]; });
+        slots[flgpu::SL_GP0] = model::dot(g1, p, n, ch);
     }
 
     // the product's rank tree (flgpu_reduce_geom.h) over the gathered per-rank values: bitwise identical on every rank
@@ -223,26 +343,26 @@ public:
     }
 };
 
-// ---- objective adapters over oracle/objectives.c (host pointers)
-// The simulator sums f pairwise (a GPU callback cannot sum sequentially either), so CPU tests see the
-// same kind of objective-value noise the CUDA objective kernels produce.
-int g_obj_sum_mode = 2;
-void obj_f(const flgpu_eval_ctx *c, double *f, const double *x, int64_t n) {
+// ---- objective adapters over oracle/objectives.c (host pointers): element-wise values from the oracle's formulas,
+// f and f'.p reduced in the CUDA objective kernels' order (model::fsum / model::dot)
+int g_obj_sum_mode = 2;    // (kept for ABI compatibility of the test helper; the model has one summation order)
+double model_f(const flgpu_eval_ctx *c, const double *x, int64_t n) {
     int d = (int)n;
-    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
-    orc_obj_set_sum_mode(g_obj_sum_mode);
-    orc_obj_f(f, x, &d);
+    const int kind = (int)(intptr_t)c->user;
+    orc_obj_select(kind, c->offset, c->n_global);
+    std::vector<double> terms((size_t)(n > 0 ? n : 1));
+    orc_obj_terms(terms.data(), x, &d);
+    return model::fsum(terms.data(), n, flgpu::red::chunk_elems(c->n_global ? c->n_global : n), kind == ORC_OBJ_ROSENBROCK);
 }
+void obj_f(const flgpu_eval_ctx *c, double *f, const double *x, int64_t n) { *f = model_f(c, x, n); }
 void obj_fd(const flgpu_eval_ctx *c, double *g, const double *x, int64_t n) {
     int d = (int)n;
     orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
     orc_obj_fd(g, x, &d);
 }
 void obj_ffd(const flgpu_eval_ctx *c, double *f, double *g, const double *x, int64_t n) {
-    int d = (int)n;
-    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
-    orc_obj_set_sum_mode(g_obj_sum_mode);
-    orc_obj_f_fd(f, g, x, &d);
+    obj_fd(c, g, x, n);
+    *f = model_f(c, x, n);
 }
 
 // fused evaluation (flgpu_fused_fn) on host memory: the point is formed element-wise, multiply then add
@@ -250,13 +370,9 @@ void obj_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp, double
                const double *x0, const double *p, double a, int64_t n) {
     std::vector<double> x((size_t)(n > 0 ? n : 1)), g((size_t)(n > 0 ? n : 1));
     for (int64_t i = 0; i < n; i++) x[i] = x0[i] + a * p[i];
-    int d = (int)n;
-    double fv = 0.0;
-    orc_obj_select((int)(intptr_t)c->user, c->offset, c->n_global);
-    orc_obj_set_sum_mode(g_obj_sum_mode);
-    orc_obj_f_fd(&fv, g.data(), x.data(), &d);
-    if (flags & FLGPU_WANT_F) *f = fv;
-    if (flags & FLGPU_WANT_GP) *gp = blocked_sum(n, [&](long i) { return g[i] * p[i]; });
+    obj_fd(c, g.data(), x.data(), n);
+    if (flags & FLGPU_WANT_F) *f = model_f(c, x.data(), n);
+    if (flags & FLGPU_WANT_GP) *gp = model::dot(g.data(), p, n, flgpu::red::chunk_elems(c->n_global ? c->n_global : n));
     if (flags & FLGPU_WRITE_X) std::memcpy(x_out, x.data(), sizeof(double) * n);
     if (flags & FLGPU_WRITE_G) std::memcpy(g_out, g.data(), sizeof(double) * n);
 }

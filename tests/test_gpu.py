@@ -260,7 +260,7 @@ def test_reductions_do_not_depend_on_the_partition(fl, log2n):
 
 # ----------------------------------------------------------------------------- parity: strict tier
 @pytest.mark.parametrize("name,mem", [("rosenR1", 10), ("rosenR1", 3), ("quartic", 10), ("diag", 30), ("rosenR0", 5),
-                                      ("quartic", 1), ("rosenR1", 17)])
+                                      ("quartic", 1), ("rosenR1", 17), ("rosenR0", 10), ("quartic1", 10)])
 def test_one_step_direction_parity_1e12(fl, name, mem):
     """K1+K2+K3 on the oracle's own history reproduce its next direction to 1e-12 (20 iterations)."""
     _cases.check_one_step(fl.History, name, mem, n=10_000)
@@ -294,7 +294,7 @@ def test_two_loop_operator_all_kernel_shapes(fl, mem):
     ("rosenR0", dict(Memory=10)), ("rosenR1", dict(Memory=10)), ("rosenR1", dict(Memory=5)),
     ("quartic", dict(Memory=10)), ("diag", dict(Memory=30, MaxIteration=40)),
     ("rosenR1", dict(Memory=1, MaxIteration=30)), ("rosenR1", dict(Memory=10, Strong=False, MaxIteration=30)),
-    ("rosenR1", dict(Memory=10, use_ffd=False)),
+    ("rosenR1", dict(Memory=10, use_ffd=False)), ("quartic1", dict(Memory=10)),
 ])
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
 def test_lbfgs_trajectory_within_oracle_envelope(fl, name, kw, fused):
@@ -314,7 +314,7 @@ def test_lbfgs_trajectory_within_oracle_envelope(fl, name, kw, fused):
 @pytest.mark.parametrize("method", ["DY", "PR"])
 @pytest.mark.parametrize("name,kw", [("quartic", dict()), ("rosenR1", dict(MaxIteration=60)),
                                      ("diag", dict(MaxIteration=60)), ("quartic", dict(Strong=False, MaxIteration=60)),
-                                     ("quartic", dict(use_ffd=False))])
+                                     ("quartic", dict(use_ffd=False)), ("quartic1", dict())])
 @pytest.mark.parametrize("fused", [True, False], ids=["fused", "plain"])
 def test_cg_trajectory_within_oracle_envelope(fl, method, name, kw, fused):
     n = 10_000
@@ -359,14 +359,37 @@ def test_minimisers_and_iteration_counts(fl):
             assert _cases.rel(x.numpy(), x_ref) < 1e-8              # minimiser, relative 1e-8
             _cases.check_iteration_count(st.iterations, counts, f"lbfgs {name} fused={fused}")
             assert st.status in statuses
-    # CG on the quartic (config 3): x* = 0, scale by |x0| (SURVEY.md 7 "x*=0 objectives")
+    # CG where the minimiser is well defined: sum (x-1)^4 + (x-1)^2, x* = 1, linear convergence.  north_star as
+    # written: minimiser to relative 1e-8, iteration count within 2 % (17 and 7 iterations: equal), same exit.
+    # L-BFGS on it likewise.
+    x0 = _cases.start("quartic1", n)
+    cbs = lambda: O.builtin_callbacks(O.OBJ_QUARTIC_SHIFTED, 0, n)     # noqa: E731
+    for M in ("DY", "PR"):
+        xr, sr = O.cg(cbs(), x0.copy(), Method=M, use_ffd=True, Warning=False)
+        assert sr.status == 0 and np.abs(xr - 1.0).max() < 1e-12
+        for fused in (True, False):
+            x = _dev_start(fl, "quartic1", n)
+            st = fl.ConjugateGradient(_problem(fl, "quartic1"), x, Method=M, Warning=False, fused=fused)
+            assert _cases.rel(x.numpy(), xr) < 1e-8, (M, fused, _cases.rel(x.numpy(), xr))
+            assert abs(st.iterations - sr.n_iter) <= 0.02 * sr.n_iter, (M, fused, st.iterations, sr.n_iter)
+            assert st.status == sr.status
+    xr, sr = O.lbfgs(cbs(), x0.copy(), use_ffd=True, Warning=False)
+    x = _dev_start(fl, "quartic1", n)
+    st = fl.LBFGS(_problem(fl, "quartic1"), x, Warning=False)
+    assert _cases.rel(x.numpy(), xr) < 1e-8 and abs(st.iterations - sr.n_iter) <= 0.02 * sr.n_iter and st.status == sr.status
+    # CG on the reference's own test objective sum x^4 (config 3; test.f90:350-373 expects "norm2(x) close to 0"): the
+    # minimiser is 0 and convergence is sub-linear, so a RELATIVE distance between two runs has no scale (the oracle's
+    # own summation orders differ by 15 % of |x| there).  Asserted: the reference's criterion -- both runs end as
+    # close to 0 -- the distance in units of |x0|, and the iteration count within 2 % (+-1).
     x0 = _cases.start("quartic", n)
     for M in ("DY", "PR"):
         xr, sr = O.cg(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Method=M, use_ffd=True, Warning=False)
         x = _dev_start(fl, "quartic", n)
         st = fl.ConjugateGradient(_problem(fl, "quartic"), x, Method=M, Warning=False)
-        assert np.linalg.norm(x.numpy() - xr) / np.linalg.norm(x0) < 1e-5
-        assert abs(st.iterations - sr.n_iter) <= max(2, 0.05 * sr.n_iter)
+        nx, nr, n0 = np.linalg.norm(x.numpy()), np.linalg.norm(xr), np.linalg.norm(x0)
+        assert nx / n0 < 1e-5 and 0.5 < nx / nr < 2.0
+        assert np.linalg.norm(x.numpy() - xr) / n0 < 1e-6
+        assert abs(st.iterations - sr.n_iter) <= max(1, 0.02 * sr.n_iter) and st.status == sr.status
 
 
 # ----------------------------------------------------------------------------- Fortran ABI (drop-in)
@@ -540,6 +563,41 @@ def test_fused_update_is_the_same_algorithm(name, kw, n):
     assert on["False"]["rows"] == on["True"]["rows"] and on["False"]["x"] == on["True"]["x"]
 
 
+# ----------------------------------------------------------------------------- GPU == scalar C++ statement, bit for bit
+@pytest.mark.parametrize("algo,name,kw", [
+    ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=40)), ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=25, fused=False)),
+    ("lbfgs", "diag", dict(Memory=30, MaxIteration=20)), ("lbfgs", "quartic", dict(Memory=7, use_ffd=False)),
+    ("lbfgs", "quartic1", dict(Memory=10)), ("lbfgs", "rosenR1", dict(Memory=4, Strong=False, MaxIteration=30)),
+    ("cg", "quartic", dict(Method="DY")), ("cg", "quartic", dict(Method="PR", fused=False)), ("cg", "quartic1", dict(Method="PR")),
+    ("cg", "rosenR1", dict(Method="DY", MaxIteration=60)), ("sd", "rosenR1", dict(MaxIteration=30)),
+    ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=30, line_search="fast")),
+])
+@pytest.mark.parametrize("n", [10_001, (1 << 17) + 2])
+def test_gpu_equals_host_simulator_bit_for_bit(fl, algo, name, kw, n):
+    """tests/hostsim is the product's driver.cpp over a scalar C++ backend whose element-wise arithmetic AND reductions
+    restate the CUDA kernels (which thread adds which unit, FMA accumulation, lane butterfly, aligned binary tree:
+    namespace model in backend_host.cpp) -- written independently of the kernels and checked against the oracle on the
+    CPU.  A whole optimisation on the GPU must therefore reproduce it BIT FOR BIT: every step length, objective value,
+    trial count and the final iterate; 10 001 rows = 10 chunks with an odd tail, 2^17 + 2 rows = 129 chunks (a ragged
+    tree), K1 in every thread shape, fused and plain line searches."""
+    import _hostsim as H
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    kind = _cases.OBJECTIVES[name][0]
+    x0 = _cases.start(name, n)
+    obh = H.Observer(keep_vectors=False)
+    hrun = {"lbfgs": H.lbfgs, "cg": H.cg, "sd": H.sd}[algo]
+    xh, sth = hrun(kind, x0, observer=obh, use_ffd=use, Warning=False, n_global=n, **kw)
+    grun = {"lbfgs": fl.LBFGS, "cg": fl.ConjugateGradient, "sd": fl.SteepestDescent}[algo]
+    x = _dev_start(fl, name, n)
+    ob = fl.Observer()
+    st = grun(_problem(fl, name, use), x, observer=ob, Warning=False, **kw)
+    assert ob.rows == obh.rows, next((k, a, b) for k, (a, b) in enumerate(zip(ob.rows, obh.rows)) if a != b)
+    assert np.array_equal(x.numpy(), xh)
+    for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
+        assert getattr(st, k) == getattr(sth, k), k
+
+
 # ----------------------------------------------------------------------------- user objectives (flgpu_objective.cuh)
 def _np_user_objective(which, n):
     """NumPy statement of tests/link/user_objective.cu (same operation order, no FMA)."""
@@ -633,7 +691,7 @@ def test_user_objective_header(fl, user_objective_lib, which, n):
     xr, sr = O.cg(cbs, x0.copy(), Method="PR", use_ffd=True, Warning=False, MaxIteration=300)
     x = x0.copy()
     st = fl.ConjugateGradient(prob, x, Method="PR", Warning=False, MaxIteration=300)
-    assert _cases.rel(x, xr) < 1e-7
+    assert _cases.rel(x, xr) < 1e-8
     # the header's device-resident search (one cooperative kernel per line search) == the host-driven fused search
     res = []
     for dev in (False, True):
@@ -811,10 +869,16 @@ def test_edge_cases(fl):
         assert st.status == fl.INITIAL_CONVERGED and st.iterations == 0
     for n in (1, 2, 3, 7, 33, 1001):                            # tiny, odd, not a multiple of the vector width
         x0 = _cases.start("quartic", n)
-        xr, sr = O.lbfgs(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Memory=4, Warning=False, MaxIteration=5)
+        xs = [O.lbfgs(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), x0.copy(), Memory=4, Warning=False, MaxIteration=5,
+                      sum_mode=mode) for mode in (0, 1, 2)]
+        xr, sr = xs[0]
+        # Memory = 4 > n makes the pairs linearly dependent: at n = 2 the oracle itself moves by 8e-9 when its dots are
+        # summed in long double.  Bound: 1e-10, or 4x the oracle's own spread over its summation orders.
+        spread = max(_cases.rel(xs[0][0], xs[1][0]), _cases.rel(xs[2][0], xs[1][0]))
         x = fl.DeviceVector.from_numpy(x0)
         st = fl.LBFGS(_problem(fl, "quartic", False), x, Memory=4, Warning=False, MaxIteration=5)
-        assert st.iterations == sr.n_iter and _cases.rel(x.numpy(), xr) < 1e-6, n
+        err = _cases.rel(x.numpy(), xs[1][0])
+        assert st.iterations == sr.n_iter and err <= max(1e-10, _cases.ENV_FACTOR * spread), (n, err, spread)
     # host x (numpy, updated in place) equals device x
     n = 4097
     xh = _cases.start("rosenR1", n)

@@ -15,6 +15,8 @@ def _np_objective(name, n):
         return N.rosenbrock()
     if name == "quartic":
         return N.quartic()
+    if name == "quartic1":
+        return N.quartic_shifted()
     d = np.array([O.lib().orc_diag_coeff(i, n) for i in range(n)])
     return N.diagquad(d)
 
@@ -38,6 +40,7 @@ LBFGS_CASES = [
     ("quartic", 10, dict(Strong=True)),                        # test.f90:380-383
     ("quartic", 10, dict(use_ffd=True, Memory=5)),             # test.f90:385-388
     ("diag", 300, dict(Memory=30, use_ffd=True, MaxIteration=80)),
+    ("quartic1", 200, dict(use_ffd=True)),
 ]
 
 
@@ -66,6 +69,8 @@ CG_CASES = [(m, name, n, kw) for m in ("DY", "PR") for name, n, kw in [
     ("quartic", 300, dict(use_ffd=True)),
     ("rosenR1", 100, dict(MaxIteration=150)),
     ("diag", 200, dict(use_ffd=True, MaxIteration=100)),
+    ("quartic1", 300, dict(use_ffd=True)),
+    ("quartic1", 100, dict()),
 ]]
 
 
