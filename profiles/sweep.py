@@ -8,10 +8,12 @@ warm-up iterations, per-kernel CUDA-event totals of rank 0 -> achieved GB/s per 
     python profiles/sweep.py [--out gpurun_out/sweep.md] [--max-log2n 28] [--line-search fast]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 profiles/sweep.py ...
 
-The single-GPU path is the one the round-1 tables were made with; the torchrun path (row shards through the same
-communicator set-up as bench.py) was written without a GPU at hand and has not been run yet.
+Every rate is timed on the device (CUDA events on the library's stream around the K timed iterations) and is the
+MAX over ranks; cells whose work space does not fit 180 GB per GPU are listed as skipped.  --json writes the rows for
+profiles/make_sweep_table.py, which combines the 1/2/4/8-GPU files into the efficiency table.
 """
 import argparse
+import json
 import os
 import sys
 import time
@@ -61,11 +63,16 @@ def one(algo, kind, start, seed, n, K, W, **kw):
     last = first + K
     mark = {}
 
+    import torch
+    ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+
     def on_iter(i):
         if i.iteration == first:
             fl.lib().flgpu_reset_kernel_times()
+            ev[0].record(torch.cuda.ExternalStream(i.stream))
             mark["t0"], mark["tr0"] = time.perf_counter(), i.total_trials
         elif i.iteration == last:
+            ev[1].record(torch.cuda.ExternalStream(i.stream))
             fl.lib().flgpu_memcpy(None, None, 0, 1, 1, i.stream)       # drain the stream
             mark["t1"], mark["tr1"] = time.perf_counter(), i.total_trials
             return True
@@ -79,9 +86,15 @@ def one(algo, kind, start, seed, n, K, W, **kw):
     kt = fl.kernel_times()
     ms = sum(v["ms"] for v in kt.values())
     gb = sum(v["bytes"] for v in kt.values()) / 1e9
-    wall = mark["t1"] - mark["t0"]
-    return {"it_per_s": K / wall, "trials_per_it": (mark["tr1"] - mark["tr0"]) / K, "kernel_ms_per_it": ms / K,
-            "GBps": gb / (ms * 1e-3), "frac": gb / (ms * 1e-3) / PEAK, "GB_per_it": gb / K}
+    dev_ms = ev[0].elapsed_time(ev[1])
+    if WORLD > 1:                                    # the slowest rank counts
+        import torch.distributed as dist
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    return {"it_per_s": K / (dev_ms * 1e-3), "trials_per_it": (mark["tr1"] - mark["tr0"]) / K, "kernel_ms_per_it": ms / K,
+            "GBps": gb / (ms * 1e-3), "frac": gb / (ms * 1e-3) / PEAK, "GB_per_it": gb / K, "ms_per_it": dev_ms / K,
+            "step_GBps": gb / (dev_ms * 1e-3)}
 
 
 def main():
@@ -94,6 +107,7 @@ def main():
     ap.add_argument("--line-search", default="reference", choices=["reference", "fast"],
                     help="flgpu_options.line_search for every case (fast = FLGPU_LS_FAST, not a reference routine)")
     ap.add_argument("--skip", default="", help="comma-separated substrings of case labels to leave out")
+    ap.add_argument("--json", default=None, help="also write the rows as JSON (for profiles/make_sweep_table.py)")
     a = ap.parse_args()
     fl.require_gpu()
     dist = setup_comm()
@@ -118,6 +132,9 @@ def main():
                 label += f", line_search={a.line_search}"
             mem = kw.get("Memory", 0)
             if (2 * mem + 6) * 8 * n / WORLD > 170e9:
+                if RANK == 0:
+                    rows.append((log2n, label, None))
+                    print(f"2^{log2n} {label}: skipped, {(2 * mem + 6) * 8 * n / WORLD / 2**30:.0f} GiB per GPU do not fit", flush=True)
                 continue
             r = one(algo, kind, start, seed, n, a.steps, a.warmup, **kw)
             if RANK != 0:
@@ -125,6 +142,7 @@ def main():
             if r is None:
                 print(f"2^{log2n} {label}: converged before the timed window", flush=True)
                 continue
+            r["memory"], r["algo"] = mem, algo
             rows.append((log2n, label, r))
             print(f"2^{log2n} {label:48.48s} {r['it_per_s']:8.2f} it/s  {r['trials_per_it']:5.1f} trials/it  "
                   f"{r['GB_per_it']:7.1f} GB/it  {r['GBps']:7.0f} GB/s ({r['frac']:.0%} of measured)", flush=True)
@@ -134,11 +152,18 @@ def main():
     if RANK != 0:
         return
     with open(a.out, "w") as fh:
-        fh.write("| n | workload | it/s (wall) | trials/it | algorithmic GB/it | kernel ms/it | achieved GB/s | of measured 6467.7 |\n")
+        fh.write("| n | workload | it/s (device time, max over ranks) | trials/it | algorithmic GB/it | kernel ms/it | achieved GB/s | of measured 6467.7 |\n")
         fh.write("|---|---|---:|---:|---:|---:|---:|---:|\n")
         for log2n, label, r in rows:
+            if r is None:
+                fh.write(f"| 2^{log2n} | {label} | skipped: work space exceeds 180 GB per GPU | | | | | |\n")
+                continue
             fh.write(f"| 2^{log2n} | {label} | {r['it_per_s']:.2f} | {r['trials_per_it']:.1f} | {r['GB_per_it']:.1f} | "
                      f"{r['kernel_ms_per_it']:.2f} | {r['GBps']:.0f} | {r['frac']:.1%} |\n")
+    if a.json:
+        json.dump({"gpus": WORLD, "line_search": a.line_search, "steps": a.steps, "warmup": a.warmup,
+                   "rows": [{"log2n": l, "workload": w, **(r or {"skipped": True})} for l, w, r in rows]},
+                  open(a.json, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -65,6 +65,24 @@ def oracle_jobs(tmp_path_factory):
     shutil.rmtree(root, ignore_errors=True)
 
 
+# ----------------------------------------------------------------------------- GPU == scalar C++ statement at full grid
+def test_gpu_equals_host_simulator_at_full_grid(fl):
+    """The host simulator (tests/hostsim: the product's driver over a scalar C++ statement of the kernels' arithmetic,
+    reductions included) against the GPU at n = 2^22 + 3 -- 4097 chunks, so every kernel's chunk loop wraps its grid
+    several times and the tree has two blocks: L-BFGS m = 3 through the 181-trial first line search and four main-loop
+    iterations, bit for bit.  (Runs while the oracle workers of this module compute.)"""
+    import _hostsim as H
+    n = N_ODD
+    x0 = _cases.start("rosenR1", n)
+    obh = H.Observer(keep_vectors=False)
+    xh, sth = H.lbfgs(O.OBJ_ROSENBROCK, x0, observer=obh, use_ffd=True, Warning=False, n_global=n, Memory=3, MaxIteration=4)
+    x = fl.DeviceVector.start(fl.START_ROSEN_PERT, n, seed=7)
+    ob = fl.Observer()
+    st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, observer=ob, Warning=False, Memory=3, MaxIteration=4)
+    assert ob.rows == obh.rows, next((k, a, b) for k, (a, b) in enumerate(zip(ob.rows, obh.rows)) if a != b)
+    assert np.array_equal(x.numpy(), xh) and st.n_trials == sth.n_trials and st.iterations == sth.iterations == 7
+
+
 # ----------------------------------------------------------------------------- (a) K1 + K2 + K3, bit-exact
 def _gram_solve(m, k, recent, D, SY, YY):
     """lbfgs_gram_solve() of include/flgpu_lbfgs_gram.hpp (the scalar statement of K2) in Python floats: same operations in
@@ -170,8 +188,7 @@ def test_two_loop_operator_bit_exact_on_integer_data(fl, mem, n):
 
 def test_one_step_direction_on_oracle_history_at_full_grid(fl, oracle_jobs):
     """K1+K2+K3 fed the oracle's own accepted points and gradients at n = 2^22 + 3 (LBFGS m = 10, Rosenbrock R1):
-    the next direction to 1e-12 of the extended-precision two-loop recursion -- or within 4x the distance the
-    oracle's own (sequential double) direction has from it, where that is larger."""
+    the next direction to 1e-12 of the extended-precision two-loop recursion (north_star's tolerance)."""
     n, mem = N_ODD, 10
     tr = oracle_jobs["lbfgs", 0].result()
     x0 = _cases.start("rosenR1", n)
@@ -191,7 +208,7 @@ def test_one_step_direction_on_oracle_history_at_full_grid(fl, oracle_jobs):
         noise = _cases.rel(tr["p"][k + 1], exact)
         err = _cases.rel(p, exact)
         worst = max(worst, err)
-        assert err <= max(1e-12, 4.0 * noise), f"direction after step {k}: {err:.2e} (oracle's own: {noise:.2e})"
+        assert err <= 1e-12, f"direction after step {k}: {err:.2e} (oracle's own: {noise:.2e})"
         assert np.array_equal(xt, xs[k + 1] + p)
     h.close()
     print(f"worst one-step error at n=2^22+3: {worst:.2e}")
