@@ -478,7 +478,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     fused = not args.plain
-    ds_active = fused and (DS is True or (DS is None and n_local <= (1 << 25))) and \
+    ds_active = fused and (DS is True or (DS is None and n_local <= (1 << 18))) and \
         (comm is None or bool(L.flgpu_comm_uses_peer_memory(comm)))
     ms, mark, st, _ = timed_run("lbfgs", args.objective, n, mem, False, fused, args.line_search)
     clocks = sampler.stop(mark["t0"], mark["t1"]) if rank == 0 else None
@@ -624,7 +624,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100,
                     help="main-loop iterations of the end-to-end optimizer call (its 487-trial prologue is amortised over them)")
     ap.add_argument("--device-search", default="auto", choices=["auto", "on", "off"],
-                    help="flgpu_options.device_search; auto = up to 2^25 rows per GPU (same bits either way)")
+                    help="flgpu_options.device_search; auto = up to 2^18 rows per GPU (same bits either way)")
     ap.add_argument("--line-search", default="reference", choices=["reference", "fast"],
                     help="flgpu_options.line_search for the whole run; the headline is `reference` (the default run "
                          "also records the `fast` rate beside it)")

@@ -130,15 +130,18 @@ struct Search : SearchCore<Search> {
 };
 
 // Device-resident search (flgpu_search_fn) gives the same bits as the host-driven fused search; it pays when the
-// host round trip per trial (~15 us) is visible next to a probe kernel, i.e. below ~2^25 rows (2.3x at 2^14, 1.07x
-// at 2^24, -0.4 % at 2^28: profiles/r01_device_search.md).  Auto mode switches by size.
+// host round trip per trial (~15 us) is large next to a probe kernel.  Measured with the chunked reductions of round 2
+// (profiles/r02_device_search.md): 1.34x at 2^18 rows, 0.87x at 2^20, 0.73x at 2^22, 0.93x at 2^26 on one GPU, and
+// 0.88-0.95x at 2^20..2^25 rows per GPU on two -- every block re-forms the tree over all chunk sums after the grid
+// barrier, which the separate tree kernel of the host-driven path does once.  Auto mode therefore uses it up to 2^18
+// rows per GPU.
 bool use_device_search(const Params &P, Backend &B) {
     if (!P.fused || P.device_search == 0 || !B.device_search_available()) return false;
     if (P.device_search == 1) return true;
     // FLGPU_LS_FAST accepts the first trial most of the time, and LBFGS evaluates that trial inside the speculative
     // K1->K2->K3 chain: the host-driven search already costs one round trip per iteration, a search kernel would add one
     if (P.line_search == FLGPU_LS_FAST) return false;
-    return B.n <= ((int64_t)1 << 25);
+    return B.n <= ((int64_t)1 << 18);
 }
 
 // FLGPU_LS_FAST asks for f and f' at every trial.  A fused probe delivers both in one pass whether or not the problem

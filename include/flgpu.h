@@ -203,7 +203,7 @@ typedef struct flgpu_options {
     int time_kernels;       /* 1 = bracket every library kernel with CUDA events (flgpu_kernel_times) */
     int no_fused;           /* 1 = ignore flgpu_problem.fused (always materialise trial points) */
     int device_search;      /* flgpu_problem.search (single GPU, fused mode): 0 never, 1 always, 2 = auto (default):
-                               used up to 2^25 rows, where the per-trial host round trip shows; same bits either way */
+                               used up to 2^18 rows per GPU, where the per-trial host round trip dominates; same bits either way */
     int line_search;        /* FLGPU_LS_REFERENCE (default) / FLGPU_LS_FAST */
 } flgpu_options;
 
