@@ -438,7 +438,7 @@ def run_ours(args):
             return out
 
         for policy in ("reference", "fast"):
-            xs, ob, st = sharded(policy, comm)
+            xs, ob, st = sharded(policy, comm, ds=True)      # device-resident search, in-kernel exchange
             mine = torch.tensor([v for r in ob.rows for v in (r[1], r[2], r[3], float(r[4]))] + [float(st.iterations)],
                                 dtype=torch.float64, device="cuda")
             ref = mine.clone()
@@ -450,7 +450,7 @@ def run_ours(args):
                                 and st3.iterations == st.iterations)
             xg = gather(xs)
             pg = [gather(p) for p in ob.p[:6]]
-            rec = {"ranks_identical_scalars": same, "peer_exchange==nccl_fallback==host_driven_search": modes,
+            rec = {"ranks_identical_scalars": same, "device_search==nccl_fallback==host_driven_search": modes,
                    "iterations": st.iterations}
             if rank == 0:
                 x1 = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_par, seed=SEED)
