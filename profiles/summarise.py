@@ -70,9 +70,13 @@ def kernels(tag, parts):
     lines = [f"# ncu --set full summaries `{tag}` (per launch; --clock-control none)", ""]
     for part in parts:
         rep = os.path.join(OUT, f"{tag}_{part}.ncu-rep")
-        if not os.path.exists(rep):
+        raw = os.path.join(OUT, f"{tag}_{part}.raw.csv")          # exported on the GPU box by run_ncu.sh
+        if os.path.exists(raw):
+            txt = open(raw).read()
+        elif os.path.exists(rep):
+            txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        else:
             continue
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rd = list(csv.reader(io.StringIO(txt)))
         hdr, units, data = rd[0], rd[1], rd[2:]
         idx = {h: i for i, h in enumerate(hdr)}
@@ -116,4 +120,4 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     if os.path.exists(os.path.join(OUT, f"{tag}_launches.csv")):
         launches(tag)
-    kernels(tag, sys.argv[2:] or ["k1k3", "ls"])
+    kernels(tag, sys.argv[2:] or ["k1k3", "ls", "tree"])
