@@ -8,12 +8,36 @@
 !
 !NOT COMPILED IN THIS REPOSITORY'S IMAGE: no Fortran compiler exists there (SURVEY.md F1).  Build with
 !    gfortran -c NonlinearOptimization_flgpu.f90 && gfortran prog.f90 NonlinearOptimization_flgpu.o -lflgpu
-!The callbacks keep the reference's interface (f90:33-38).  By default they receive DEVICE pointers
-!(x, fdx) on flgpu_current_stream(); call flgpu_set_callback_space(0) to have the library stage host
-!copies instead, which lets unmodified host callbacks run (slow: every evaluation crosses PCIe).
+!The callbacks keep the reference's interface (f90:33-38).  By default they are HOST callbacks, as in the
+!reference: the library stages x / fdx through pinned host buffers around every call, so unmodified code
+!runs as it is (slow: every evaluation crosses PCIe).  A callback that launches CUDA kernels itself calls
+!flgpu_set_callback_space(1) first and then receives DEVICE pointers on flgpu_current_stream().
+!Written to the letter of Fortran 2008 where this image could not check it with a compiler: explicit
+!interfaces for the callback dummies (c_funloc of a dummy procedure), character(*) Method copied into a
+!character(kind=c_char) array (c_loc of a len /= 1 character is not interoperable in F2003).
 module NonlinearOptimization_flgpu
     use iso_c_binding
     implicit none
+
+    abstract interface
+        !the reference's callback contract (f90:33-38)
+        subroutine flgpu_f_iface(fx, x, dim)
+            integer, intent(in) :: dim
+            real*8, intent(out) :: fx
+            real*8, dimension(dim), intent(in) :: x
+        end subroutine flgpu_f_iface
+        subroutine flgpu_fd_iface(fdx, x, dim)
+            integer, intent(in) :: dim
+            real*8, dimension(dim), intent(out) :: fdx
+            real*8, dimension(dim), intent(in) :: x
+        end subroutine flgpu_fd_iface
+        integer function flgpu_f_fd_iface(fx, fdx, x, dim)
+            integer, intent(in) :: dim
+            real*8, intent(out) :: fx
+            real*8, dimension(dim), intent(out) :: fdx
+            real*8, dimension(dim), intent(in) :: x
+        end function flgpu_f_fd_iface
+    end interface
 
     interface
         !gfortran-mangled entry points exported by libflgpu.so; all arguments by reference
@@ -70,8 +94,9 @@ contains
     !Same dummy-argument list as the reference's LBFGS (f90:398-400)
     subroutine LBFGS(f, fd, x, dim, Memory, f_fd, Strong, Warning, MaxIteration, Precision, MinStepLength, &
             WolfeConst1, WolfeConst2, Increment)
-        external :: f, fd
-        integer, external, optional :: f_fd
+        procedure(flgpu_f_iface) :: f
+        procedure(flgpu_fd_iface) :: fd
+        procedure(flgpu_f_fd_iface), optional :: f_fd
         integer, intent(in) :: dim
         real*8, dimension(dim), intent(inout), target :: x
         integer, intent(in), optional, target :: Memory, MaxIteration
@@ -90,8 +115,9 @@ contains
     !Same dummy-argument list as the reference's SteepestDescent (f90:55-56)
     subroutine SteepestDescent(f, fd, x, dim, f_fd, Strong, Warning, MaxIteration, Precision, MinStepLength, &
             WolfeConst1, WolfeConst2, Increment)
-        external :: f, fd
-        integer, external, optional :: f_fd
+        procedure(flgpu_f_iface) :: f
+        procedure(flgpu_fd_iface) :: fd
+        procedure(flgpu_f_fd_iface), optional :: f_fd
         integer, intent(in) :: dim
         real*8, dimension(dim), intent(inout), target :: x
         integer, intent(in), optional, target :: MaxIteration
@@ -109,11 +135,13 @@ contains
     !Same dummy-argument list as the reference's ConjugateGradient (f90:193-195)
     subroutine ConjugateGradient(f, fd, x, dim, Method, f_fd, Strong, Warning, MaxIteration, Precision, &
             MinStepLength, WolfeConst1, WolfeConst2, Increment)
-        external :: f, fd
-        integer, external, optional :: f_fd
+        procedure(flgpu_f_iface) :: f
+        procedure(flgpu_fd_iface) :: fd
+        procedure(flgpu_f_fd_iface), optional :: f_fd
         integer, intent(in) :: dim
         real*8, dimension(dim), intent(inout), target :: x
-        character*2, intent(in), optional, target :: Method
+        character(*), intent(in), optional :: Method          !as the reference (f90:201); 'DY' or 'PR'
+        character(kind=c_char), dimension(32), target :: mbuf
         integer, intent(in), optional, target :: MaxIteration
         logical, intent(in), optional :: Strong, Warning
         real*8, intent(in), optional, target :: Precision, MinStepLength, WolfeConst1, WolfeConst2, Increment
@@ -121,10 +149,15 @@ contains
         type(c_funptr) :: cffd
         type(c_ptr) :: pstrong, pwarning, pmethod
         integer(c_int) :: lmethod
+        integer :: ich
         cffd = c_null_funptr; if (present(f_fd)) cffd = c_funloc(f_fd)
         pmethod = c_null_ptr; lmethod = 0
         if (present(Method)) then
-            pmethod = c_loc(Method); lmethod = 2
+            lmethod = min(len(Method), 32)
+            do ich = 1, lmethod
+                mbuf(ich) = Method(ich:ich)
+            end do
+            pmethod = c_loc(mbuf)
         end if
         call logical_arg(Strong, istrong, pstrong); call logical_arg(Warning, iwarning, pwarning)
         call flgpu_cg_ref(c_funloc(f), c_funloc(fd), x, dim, pmethod, cffd, pstrong, pwarning, &
