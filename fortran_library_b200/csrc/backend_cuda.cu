@@ -545,10 +545,10 @@ void CudaBackend::trial_x(double *x, const double *x0, const double *p, double a
 }
 void CudaBackend::dot(const double *a, const double *b, int slot) {
     const int t = time_begin("dot", (a == b ? 8.0 : 16.0) * n);
-    k::dot_kernel<<<grid_for(8), k::kThreads, 0, stream>>>(a, b, n, ch, work, 0);
+    const bool in_kernel = nchunks <= red::kBlockChunks;     // small reductions finish inside the producing kernel
+    k::dot_kernel<<<grid_for(8), k::kThreads, 0, stream>>>(a, b, n, ch, work, 0, in_kernel ? R + slot : nullptr);
     launches++;
-    double *out[1] = {R + slot};
-    tree(1, out);
+    if (!in_kernel) { double *out[1] = {R + slot}; tree(1, out); }
     time_end(t);
 }
 void CudaBackend::neg(double *p, const double *g) {
@@ -705,18 +705,21 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
 // ---- CG
 void CudaBackend::cg_dots(const double *g1, const double *g0, const double *p) {
     const int t = time_begin("cg_dots", 24.0 * n);
-    k::cg_dots_kernel<<<grid_for(6), k::kThreads, 0, stream>>>(g1, g0, p, n, ch, work);
-    launches++;
     double *out[5] = {R + SL_GG, R + SL_PP, R + SL_DGP, R + SL_GDG, R + SL_G0G0};
-    tree(5, out);
+    const bool in_kernel = nchunks <= red::kBlockChunks;
+    k::Outs5 o{};
+    if (in_kernel) for (int i = 0; i < 5; i++) o.p[i] = out[i];
+    k::cg_dots_kernel<<<grid_for(6), k::kThreads, 0, stream>>>(g1, g0, p, n, ch, work, o);
+    launches++;
+    if (!in_kernel) tree(5, out);
     time_end(t);
 }
 void CudaBackend::cg_update(double *p, const double *g1, double beta) {
     const int t = time_begin("cg_update", 24.0 * n);
-    k::cg_update_kernel<<<grid_for(6), k::kThreads, 0, stream>>>(p, g1, beta, n, ch, work);
+    const bool in_kernel = nchunks <= red::kBlockChunks;
+    k::cg_update_kernel<<<grid_for(6), k::kThreads, 0, stream>>>(p, g1, beta, n, ch, work, in_kernel ? R + SL_GP0 : nullptr);
     launches++;
-    double *out[1] = {R + SL_GP0};
-    tree(1, out);
+    if (!in_kernel) { double *out[1] = {R + SL_GP0}; tree(1, out); }
     time_end(t);
 }
 

@@ -97,8 +97,9 @@ static __global__ void __launch_bounds__(kThreads) neg_kernel(double *__restrict
 
 // ------------------------------------------------------------------ K4b: dot_product(a,b) (f90:1485)
 // chunk sums of a.b go to row `row` of the partials
+// out != null (and at most 4096 chunks): the last block also forms the tree and stores the root (no tree_kernel launch)
 static __global__ void __launch_bounds__(kThreads) dot_kernel(const double *__restrict__ a, const double *__restrict__ b,
-                                                       int64_t n, int64_t ch, Work w, int row) {
+                                                       int64_t n, int64_t ch, Work w, int row, double *out) {
     const Chunks C(n, ch);
     double *part = w.partials + (int64_t)row * w.stride;
     int parity = 0;
@@ -122,12 +123,18 @@ static __global__ void __launch_bounds__(kThreads) dot_kernel(const double *__re
         const double acc[1] = {s};
         red::chunk_flush<1>(acc, parity, part, w.stride, c);
     }
+    if (out) {
+        double *const o[1] = {out};
+        red::finish_in_kernel<1>(part, w.stride, C.nchunks, w.tickets, o);
+    }
 }
 
 // ------------------------------------------------------------------ K5a: CG dots (f90:354-366, 375-387)
 // one pass over f'new, f'old, p:  g.g, p.p, (g-gold).p, g.(g-gold), gold.gold  -> rows 0..4
+struct Outs5 { double *p[5]; };   // destinations of an in-kernel finish (null p[0]: tree_kernel follows instead)
 static __global__ void __launch_bounds__(kThreads) cg_dots_kernel(const double *__restrict__ g1, const double *__restrict__ g0,
-                                                           const double *__restrict__ p, int64_t n, int64_t ch, Work w) {
+                                                           const double *__restrict__ p, int64_t n, int64_t ch, Work w,
+                                                           Outs5 outs) {
     const Chunks C(n, ch);
     int parity = 0;
     for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
@@ -156,11 +163,15 @@ static __global__ void __launch_bounds__(kThreads) cg_dots_kernel(const double *
         if (C.tail_here(c) && threadIdx.x == 0) term(g1[n - 1], g0[n - 1], p[n - 1]);
         red::chunk_flush<5>(acc, parity, w.partials, w.stride, c);
     }
+    if (outs.p[0]) {
+        double *const o[5] = {outs.p[0], outs.p[1], outs.p[2], outs.p[3], outs.p[4]};
+        red::finish_in_kernel<5>(w.partials, w.stride, C.nchunks, w.tickets, o);
+    }
 }
 
 // ------------------------------------------------------------------ K5b: p = -g + beta*p; g.p (f90:366-367) -> row 0
 static __global__ void __launch_bounds__(kThreads) cg_update_kernel(double *__restrict__ p, const double *__restrict__ g1,
-                                                             double beta, int64_t n, int64_t ch, Work w) {
+                                                             double beta, int64_t n, int64_t ch, Work w, double *out) {
     const Chunks C(n, ch);
     int parity = 0;
     for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
@@ -189,6 +200,10 @@ static __global__ void __launch_bounds__(kThreads) cg_update_kernel(double *__re
             acc[0] = fma(g1[n - 1], v, acc[0]);
         }
         red::chunk_flush<1>(acc, parity, w.partials, w.stride, c);
+    }
+    if (out) {
+        double *const o[1] = {out};
+        red::finish_in_kernel<1>(w.partials, w.stride, C.nchunks, w.tickets, o);
     }
 }
 

@@ -108,6 +108,7 @@ struct ObjArgs {
     double scale;       // diag quad: 2^24/(n_global-1)
     const double *tables;
     Work w;             // chunk sums: f -> row 0 (or the only row), f'.p -> the next row
+    double *out[2];     // in-kernel finish (at most 4096 chunks): where the roots of those rows go; null: tree_kernel follows
 };
 
 // What an objective needs to know about where a unit sits in the global vector.
@@ -289,6 +290,15 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
         } else if (WANT_GP) {
             const double acc[1] = {gpsum};
             red::chunk_flush<1>(acc, parity, a.w.partials, a.w.stride, c);
+        }
+    }
+    if (a.out[0]) {                      // small reduction: the last block forms the tree(s) itself
+        if (WANT_F && WANT_GP) {
+            double *const o[2] = {a.out[0], a.out[1]};
+            red::finish_in_kernel<2>(a.w.partials, a.w.stride, C.nchunks, a.w.tickets, o);
+        } else if (WANT_F || WANT_GP) {
+            double *const o[1] = {a.out[0]};
+            red::finish_in_kernel<1>(a.w.partials, a.w.stride, C.nchunks, a.w.tickets, o);
         }
     }
 }
@@ -497,6 +507,12 @@ void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp
     a.n = n; a.offset = offset; a.n_global = n_global; a.ch = ch;
     a.scale = n_global > 1 ? 16777216.0 / (double)(n_global - 1) : 0.0;
     a.tables = sc.tables; a.w = sc.work;
+    // chunk sums -> this rank's roots: f in row 0 (or f'.p when only that was asked for), f'.p in the next row; up to 4096
+    // chunks the producing kernel's last block forms the trees itself, above that tree_kernel follows
+    const bool wf = (flags & FLGPU_WANT_F) != 0, wgp = (flags & FLGPU_WANT_GP) != 0;
+    double *out[2] = {wf ? f_dev : gp_dev, gp_dev};
+    const bool in_kernel = (wf || wgp) && nchunks <= red::kBlockChunks;
+    a.out[0] = in_kernel ? out[0] : nullptr; a.out[1] = in_kernel ? out[1] : nullptr;
     const int grid = chunk_grid(nchunks, 4);     // = resident CTAs per SM (__launch_bounds__(256, 4)): one full wave
 #define FLGPU_OBJ_CASE(KIND, FU, F, GP, WX, WG)                                                                 \
     k::objective_kernel<KIND, FU, F, GP, WX, WG><<<grid, k::kThreads, 0, s>>>(a)
@@ -528,12 +544,7 @@ void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp
     }
 #undef FLGPU_OBJ_LAUNCH
 #undef FLGPU_OBJ_CASE
-    // chunk sums -> this rank's roots: f in row 0 (or f'.p when only that was asked for), f'.p in the next row
-    const bool wf = (flags & FLGPU_WANT_F) != 0, wgp = (flags & FLGPU_WANT_GP) != 0;
-    if (wf || wgp) {
-        double *out[2] = {wf ? f_dev : gp_dev, gp_dev};
-        launch_tree(sc.work, nchunks, wf && wgp ? 2 : 1, out, s);
-    }
+    if ((wf || wgp) && !in_kernel) launch_tree(sc.work, nchunks, wf && wgp ? 2 : 1, out, s);
 }
 
 // 64-bit device-callback flavour
@@ -592,6 +603,7 @@ static void dev_search_policy(const flgpu_eval_ctx *c, const flgpu_search_args *
     K.o.n = n; K.o.offset = c->offset; K.o.n_global = n_global; K.o.ch = ch;
     K.o.scale = n_global > 1 ? 16777216.0 / (double)(n_global - 1) : 0.0;
     K.o.tables = sc.tables; K.o.w = sc.work;       // rows 0..3: [evaluation parity][f, f'.p]
+    K.o.out[0] = K.o.out[1] = nullptr;
     K.c1 = A->c1; K.c2abs = A->c2abs; K.fx0 = A->fx0; K.phid0 = A->phid0; K.incr = A->incr; K.a0 = A->a;
     K.strong = A->strong; K.fdwithf = A->fdwithf; K.store = A->no_store ? 0 : 1;
     K.glob = sc.work.blockvals + (size_t)(kScratchRows - 1) * red::kTopMax;   // 4 doubles nobody else uses during a search
@@ -716,9 +728,9 @@ extern "C" int flgpu_vec_dot_sharded(const double *a_dev, const double *b_dev, i
     if (n_global < n) n_global = n;
     const int64_t ch = red::chunk_elems(n_global), nchunks = red::num_chunks(n, ch);
     Scratch &sc = scratch_for(s, nchunks);
-    k::dot_kernel<<<chunk_grid(nchunks, 8), k::kThreads, 0, s>>>(a_dev, b_dev, n, ch, sc.work, 0);
-    double *out[1] = {out_dev};
-    launch_tree(sc.work, nchunks, 1, out, s);
+    const bool in_kernel = nchunks <= red::kBlockChunks;
+    k::dot_kernel<<<chunk_grid(nchunks, 8), k::kThreads, 0, s>>>(a_dev, b_dev, n, ch, sc.work, 0, in_kernel ? out_dev : nullptr);
+    if (!in_kernel) { double *out[1] = {out_dev}; launch_tree(sc.work, nchunks, 1, out, s); }
     FLGPU_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
