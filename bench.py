@@ -431,7 +431,7 @@ def run_ours(args):
         def sharded(policy, c, ds=None):
             x = fl.DeviceVector.start(fl.START_ROSEN_PERT, pb - pa, seed=SEED, offset=pa, n_global=n_par)
             ob = fl.Observer(keep_vectors=True, max_vec_iters=6)
-            st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=mem, Warning=False, MaxIteration=25 - mem,
+            st = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x, Memory=mem, Warning=False, MaxIteration=max(25 - mem, 2),
                           observer=ob, comm=c, offset=pa, n_global=n_par, line_search=policy, device_search=ds)
             out = (x.numpy(), ob, st)
             x.free()
@@ -456,7 +456,7 @@ def run_ours(args):
                 x1 = fl.DeviceVector.start(fl.START_ROSEN_PERT, n_par, seed=SEED)
                 ob1 = fl.Observer(keep_vectors=True, max_vec_iters=6)
                 st1 = fl.LBFGS(fl.builtin_problem(fl.OBJ_ROSENBROCK), x1, Memory=mem, Warning=False,
-                               MaxIteration=25 - mem, observer=ob1, line_search=policy)
+                               MaxIteration=max(25 - mem, 2), observer=ob1, line_search=policy)
                 x1n = x1.numpy()
                 rec["bitwise_equal_to_single_gpu"] = bool(np.array_equal(xg, x1n) and ob1.rows == ob.rows and
                                                           all(np.array_equal(a, b) for a, b in zip(pg, ob1.p[:6])))
