@@ -252,13 +252,17 @@ dist.destroy_process_group()
                                            (False, "quartic", dict(Method="PR")),
                                            (True, "rosenR1", dict(Memory=6, line_search="fast")),
                                            (False, "quartic", dict(Method="DY", line_search="fast"))])
-def test_row_sharded_two_ranks_gloo(tmp_path, lbfgs, name, kw):
-    """N>1 path on CPU: two processes, each owning a row shard, exchanging only the partial dots
-    (all-gather over gloo) and summing them in rank order.  Both ranks must take identical decisions
-    (bitwise equal scalars) and the assembled result must match a single-process run."""
-    n, split, maxit = 1000, 400, 25
+@pytest.mark.parametrize("n,split", [(1000, 400), (4096, 2048)], ids=["ragged", "aligned"])
+def test_row_sharded_two_ranks_gloo(tmp_path, lbfgs, name, kw, n, split):
+    """N>1 path on CPU: two processes, each owning a row shard, exchanging only the per-rank roots
+    (all-gather over gloo) and combining them by the rank tree.  Both ranks must take identical decisions
+    (bitwise equal scalars) and the assembled result must match a single-process run -- within tolerance for the
+    ragged split (400 + 600 rows: partial chunks), BIT FOR BIT for the aligned one (2 + 2 whole chunks of 1024: each
+    rank's root is a node of the single-process tree, include/flgpu_reduce.cuh)."""
+    maxit = 25
     kind, start, seed = _cases.OBJECTIVES[name]
     out = str(tmp_path / "r")
+    H.lib()                     # build once here: the two workers must not race on `make`
     import socket
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -279,6 +283,9 @@ def test_row_sharded_two_ranks_gloo(tmp_path, lbfgs, name, kw):
     x2 = np.concatenate([r0["x"], r1["x"]])
     p2 = np.concatenate([r0["p"], r1["p"]], axis=1)
     assert st.iterations == int(r0["iters"])
+    if split * 2 == n and split % 1024 == 0:
+        assert np.array_equal(x2, xs) and np.array_equal(np.array(ob.rows), r0["rows"])
+        assert all(np.array_equal(p2[k], ob.p[k]) for k in range(min(len(ob.p), len(p2))))
     # relative 1e-7, scaled by |x0| where the minimiser is 0 (quartic: |x| ~ 1e-3 |x0| after 25 iterations)
     assert np.linalg.norm(x2 - xs) / max(np.linalg.norm(xs), np.linalg.norm(x0)) < 1e-7
     for k in range(min(len(ob.p), len(p2), 8)):
