@@ -618,8 +618,9 @@ void CudaBackend::lbfgs_update_dots(const double *x1, const double *x0, const do
 void CudaBackend::lbfgs_update_dots_fused(double step, const double *x0, const double *p, const double *g0, double *x1,
                                           double *g1, int new_slot, int k_after) {
     const int nother = k_after - 1;
-    // reads x0, p, g0 and the older columns; writes x1, g1 and the new column pair
-    const int t = time_begin("k1_update_dots_fused", 8.0 * n * (2.0 * nother + 7.0));
+    // reads x0, p (and g0, unless the source re-evaluates it: the built-in objectives do) and the older columns; writes
+    // x1, g1 and the new column pair.  Credited as the leaner of the two: 2 + 2(k-1) in, 4 out.
+    const int t = time_begin("k1_update_dots_fused", 8.0 * n * (2.0 * nother + 6.0));
     k::K1Args a{};
     a.x1 = x1; a.x0 = x0; a.g1 = g1; a.g0 = g0; a.p = p; a.step = step; a.x1_out = x1; a.g1_out = g1;
     a.S = S; a.Y = Y; a.ld = ld; a.n = n; a.ch = ch; a.offset = ctx.offset; a.n_global = ctx.n_global;

@@ -3,8 +3,8 @@
 //
 // libflgpu instantiates it with PlainSrc (x1 and f'(x1) are read from memory).  An objective that can evaluate its
 // gradient inside a kernel instantiates it with a source that forms x1 = x0 + a*p and f'(x1) in registers and stores
-// them (flgpu_problem.update): the line search then never stores its accepted point in a pass of its own, 10n -> 7n
-// doubles of traffic per iteration.  libflgpu's built-in objectives do this in csrc/objectives.cu,
+// them, and RE-EVALUATES f'(x0) from the x0 it reads anyway instead of loading it (flgpu_problem.update): the line search
+// then never stores its accepted point in a pass of its own, 10n -> 6n doubles of traffic per iteration.  libflgpu's built-in objectives do this in csrc/objectives.cu,
 // include/flgpu_objective.cuh does it for user functors.
 #pragma once
 #include <cstdint>
@@ -75,15 +75,17 @@ struct K1Args {
 struct PlainSrc {
     static constexpr bool kFused = false;
     __device__ void init(const K1Args &) {}
-    // unit u: the accepted point and its gradient
-    __device__ __forceinline__ void unit(const K1Args &a, int64_t u, bool, double2 x0, double2 &x1, double2 &g1) const {
+    // unit u: the accepted point, its gradient and the gradient at the previous point
+    __device__ __forceinline__ void unit(const K1Args &a, int64_t u, bool, double2 x0, double2 &x1, double2 &g1,
+                                         double2 &g0) const {
         (void)x0;
+        g0 = ld2(a.g0, u);
         g1 = ld2(a.g1, u);
         if (a.write_new) x1 = ld2(a.x1, u);
     }
-    __device__ __forceinline__ void tail(const K1Args &a, int64_t i, bool, double x0, double &x1, double &g1) const {
+    __device__ __forceinline__ void tail(const K1Args &a, int64_t i, bool, double x0, double &x1, double &g1, double &g0) const {
         (void)x0;
-        x1 = a.x1[i]; g1 = a.g1[i];
+        x1 = a.x1[i]; g1 = a.g1[i]; g0 = a.g0[i];
     }
 };
 
@@ -93,7 +95,7 @@ struct PlainSrc {
 // instruction and coalesce into a single request (no re-read of those four vectors per group), while
 // each group's column loads stay contiguous runs of SEG*16 bytes.
 template <int MT, int NG, class Src>
-static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args a, Src src) {
+static __global__ void __launch_bounds__(kThreads, 2) k1_update_dots_kernel(K1Args a, Src src) {
     constexpr int SEG = 32 / NG;                     // lanes per column group inside a warp
     constexpr int TX = kThreads / NG;                // double2 elements per block and loop trip
     constexpr int NW = kThreads / 32;                // every warp contributes to every group
@@ -127,15 +129,14 @@ static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args 
         for (int c = 0; c < MT; c++) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
         double ex[5] = {0.0, 0.0, 0.0, 0.0, 0.0};        // g.g, sn.g, yn.g, sn.yn, yn.yn
         for (int64_t u = C.lo(chunk) + tx; u < hi; u += TX) {
-            const double2 g0 = ld2(a.g0, u);
             double2 x0 = make_double2(0.0, 0.0);
             if (a.write_new) x0 = ld2(a.x0, u);          // later passes need only y_new = g1 - g0
             double2 s[MT], y[MT];
 #pragma unroll
             for (int c = 0; c < MT; c++)
                 if (valid[c]) { s[c] = ld2(cs[c], u); y[c] = ld2(cy[c], u); }
-            double2 x1 = make_double2(0.0, 0.0), g1;
-            src.unit(a, u, own_new, x0, x1, g1);
+            double2 x1 = make_double2(0.0, 0.0), g1, g0;
+            src.unit(a, u, own_new, x0, x1, g1, g0);
             const double2 sn = make_double2(x1.x - x0.x, x1.y - x0.y);   // s=x-xold  f90:623
             const double2 yn = make_double2(g1.x - g0.x, g1.y - g0.y);   // y=fdnew-fdold
             if (own_new) {
@@ -157,9 +158,9 @@ static __global__ void __launch_bounds__(kThreads) k1_update_dots_kernel(K1Args 
         }
         if (C.tail_here(chunk) && tx == 0) {             // odd tail element (one thread per column group)
             const int64_t i = a.n - 1;
-            const double g0 = a.g0[i], x0 = a.write_new ? a.x0[i] : 0.0;
-            double x1 = 0.0, g1;
-            src.tail(a, i, own_new, x0, x1, g1);
+            const double x0 = a.write_new ? a.x0[i] : 0.0;
+            double x1 = 0.0, g1, g0;
+            src.tail(a, i, own_new, x0, x1, g1, g0);
             if (!a.write_new) x1 = 0.0;
             const double sn = x1 - x0, yn = g1 - g0;
             if (own_new) {

@@ -217,9 +217,12 @@ template <class Obj>
 struct FunctorSrc {
     Obj obj;
     __device__ void init(const flgpu::k::K1Args &) {}
+    // f'(x0) is read back from memory here: a user objective may be expensive to evaluate twice (libflgpu's built-in
+    // objectives re-evaluate it from x0 instead, which saves the load)
     __device__ __forceinline__ void unit(const flgpu::k::K1Args &a, int64_t u, bool own_new, double2 x0, double2 &x1,
-                                         double2 &g1) const {
+                                         double2 &g1, double2 &g0) const {
         const double2 pv = __ldg(reinterpret_cast<const double2 *>(a.p) + u);
+        g0 = __ldg(reinterpret_cast<const double2 *>(a.g0) + u);
         x1.x = __dadd_rn(x0.x, __dmul_rn(a.step, pv.x));
         x1.y = __dadd_rn(x0.y, __dmul_rn(a.step, pv.y));
         const int64_t i = a.offset + 2 * u;
@@ -232,7 +235,8 @@ struct FunctorSrc {
         }
     }
     __device__ __forceinline__ void tail(const flgpu::k::K1Args &a, int64_t i, bool own_new, double x0, double &x1,
-                                         double &g1) const {
+                                         double &g1, double &g0) const {
+        g0 = a.g0[i];
         x1 = __dadd_rn(x0, __dmul_rn(a.step, a.p[i]));
         double f = 0.0;
         if constexpr (Obj::WIDTH == 2) obj.eval_tail(a.offset + i, x1, f, g1);
