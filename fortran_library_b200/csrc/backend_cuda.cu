@@ -691,9 +691,9 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
             k::k3_direction_tma_kernel<P, NST, MINB><<<grid_for(MINB), k::kThreads + 32, smem, stream>>>(a);               \
             done = true;                                                                                                   \
         }
-        FLGPU_K3_CASE(11, 2, 2, 0) FLGPU_K3_CASE(7, 3, 2, 1) FLGPU_K3_CASE(4, 6, 2, 2) FLGPU_K3_CASE(8, 3, 2, 3)
-        FLGPU_K3_CASE(6, 4, 2, 4) FLGPU_K3_CASE(8, 6, 1, 5) FLGPU_K3_CASE(7, 7, 1, 6) FLGPU_K3_CASE(11, 4, 1, 7)
-        FLGPU_K3_CASE(5, 5, 2, 8) FLGPU_K3_CASE(9, 3, 2, 9) FLGPU_K3_CASE(4, 4, 3, 10) FLGPU_K3_CASE(7, 2, 3, 11)
+        // the shapes of profiles/r02_k3_ring_shapes.md worth keeping selectable (the one-CTA-per-SM and 3-CTA ones lost)
+        FLGPU_K3_CASE(11, 2, 2, 0) FLGPU_K3_CASE(9, 3, 2, 1) FLGPU_K3_CASE(8, 3, 2, 2) FLGPU_K3_CASE(7, 3, 2, 3)
+        FLGPU_K3_CASE(4, 6, 2, 4)
 #undef FLGPU_K3_CASE
         if (!done) fatal("FLGPU_K3: this ring shape is not instantiated");
     }
