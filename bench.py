@@ -65,11 +65,13 @@ def static_config(n, mem, objective):
 POLICIES = {"reference": "reference (StrongWolfe_fdwithf f90:1582-1698, statement by statement)",
             "fast": "fast (FLGPU_LS_FAST: first trial satisfying the strong Wolfe conditions is accepted; not a "
                     "reference routine)"}
-LS_MODES = {True: "fused (flgpu_fused_fn + flgpu_update_fn: the objective kernel forms x0+a*p; 2n doubles per trial, the "
-                  "accepted point is formed and stored by K1)",
+LS_MODES = {True: "fused (flgpu_fused_fn + flgpu_update_fn + flgpu_direction_fn: the objective kernel forms x0+a*p; 2n doubles "
+                  "per trial, the first trial of a search is evaluated by K3 while it writes p, the accepted point is formed "
+                  "and stored by K1)",
             False: "plain (opaque f/fd/f_fd device callbacks; 7n doubles per f+g trial)"}
 NCU_NAMES = {"k1_update_dots": "k1_update_dots_kernel", "k1_update_dots_fused": "k1_update_dots_kernel",
-             "k3_direction": "k3_direction_tma_kernel", "trial_x": "trial_kernel",
+             "k3_direction": "k3_direction_tma_kernel", "k3_direction_probe": "k3_direction_tma_kernel_probe",
+             "trial_x": "trial_kernel",
              "dot": "dot_kernel", "cg_dots": "cg_dots_kernel", "cg_update": "cg_update_kernel"}
 
 

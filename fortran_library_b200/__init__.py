@@ -277,10 +277,11 @@ def builtin_constraints(kind=CON_SPHERE):
 def AugmentedLagrangian(problem, constraints, x, UnconstrainedSolver="LBFGS", lambda0=None, miu0=None, Memory=None,
                         Method=None, Strong=None, Warning=None, MaxIteration=None, Precision=None, MinStepLength=None,
                         WolfeConst1=None, WolfeConst2=None, Increment=None, stream=None, comm=None, offset=0, n_global=0,
-                        line_search=None):
+                        line_search=None, fused=True):
     """Equality-constrained minimisation (reference: AugmentedLagrangian, f90:2005-2241) with the hot path as inner
     solver: UnconstrainedSolver 'LBFGS' or 'ConjugateGradient' (the dense-Hessian solvers are outside the GPU path).
-    line_search="fast" runs every inner solve with FLGPU_LS_FAST (not a reference routine)."""
+    line_search="fast" runs every inner solve with FLGPU_LS_FAST (not a reference routine).  fused=False ignores
+    `problem.fused` / `constraints.fused` (every trial point of the inner solves is then materialised)."""
     import numpy as np
     if UnconstrainedSolver not in ("LBFGS", "ConjugateGradient"):
         raise SystemExit("Program abort: unsupported unconstrained solver " + str(UnconstrainedSolver))
@@ -295,6 +296,7 @@ def AugmentedLagrangian(problem, constraints, x, UnconstrainedSolver="LBFGS", la
                        Precision=Precision, MinStepLength=MinStepLength, WolfeConst1=WolfeConst1,
                        WolfeConst2=WolfeConst2, Increment=Increment, line_search=line_search)
     o.inner.stream, o.inner.comm, o.inner.offset, o.inner.n_global = stream, comm, offset, n_global
+    o.inner.no_fused = int(not fused)
     lam = None
     if lambda0 is not None:
         lam = np.ascontiguousarray(lambda0, dtype=np.float64)

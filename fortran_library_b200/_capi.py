@@ -35,7 +35,7 @@ FUSED_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_int, C.c_void_p, C.c_void_p
 class Problem(C.Structure):
     _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p),
                 ("fused", C.c_void_p), ("search", C.c_void_p), ("search_caps", C.c_int),
-                ("update", C.c_void_p)]
+                ("update", C.c_void_p), ("direction", C.c_void_p)]
 
 
 class IterInfo(C.Structure):
@@ -79,7 +79,7 @@ REF_CD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POIN
 
 
 class Constraints(C.Structure):
-    _fields_ = [("c", C.c_void_p), ("cd", C.c_void_p), ("m", C.c_int)]
+    _fields_ = [("c", C.c_void_p), ("cd", C.c_void_p), ("m", C.c_int), ("fused", C.c_void_p)]
 
 
 class ALOptions(C.Structure):

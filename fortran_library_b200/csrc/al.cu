@@ -46,6 +46,25 @@ __global__ void __launch_bounds__(k::kThreads) al_grad_kernel(double *g, const d
     }
 }
 
+// Fused probe (flgpu_c_fused_fn): L and L'.p from the scalars f, f'.p, c_j, cd_j.p at the trial point.
+//   L    = f - lambda.c + miu/2 c.c            on ONE rank's partial (apply != 0 on rank 0 only), as al_terms_kernel
+//   L'.p = f'.p + sum_j (miu c_j - lambda_j) (cd_j.p)    on every rank's partial (c is already summed over the ranks)
+__global__ void al_probe_terms_kernel(double *f_dev, double *gp_dev, const double *c, const double *cdp, const double *lambda,
+                                      double miu, int m, int apply_f, int want_gp) {
+    if (threadIdx.x != 0) return;
+    if (apply_f) {
+        double d1 = 0.0, d2 = 0.0;
+        for (int j = 0; j < m; j++) d1 = __dadd_rn(d1, __dmul_rn(lambda[j], c[j]));
+        for (int j = 0; j < m; j++) d2 = __dadd_rn(d2, __dmul_rn(c[j], c[j]));
+        *f_dev = __dadd_rn(__dadd_rn(*f_dev, -d1), __dmul_rn(miu / 2.0, d2));
+    }
+    if (want_gp) {
+        double r = 0.0;
+        for (int j = 0; j < m; j++) r = __dadd_rn(r, __dmul_rn(cdp[j], __dadd_rn(__dmul_rn(miu, c[j]), -lambda[j])));
+        *gp_dev = __dadd_rn(*gp_dev, r);
+    }
+}
+
 struct ALState {
     flgpu_problem user;
     flgpu_constraints con;
@@ -54,7 +73,11 @@ struct ALState {
     int64_t ld = 0;
     double miu = 1.0;
     double *lambda_dev = nullptr, *cpart = nullptr, *cglob = nullptr, *cd_dev = nullptr, *gather = nullptr;
+    double *cdp = nullptr;      // fused probe: this rank's partials of cd_j . p
+    double *xtmp = nullptr;     // fused store of f' alone (never requested by the reference's searchers): the point
+    int64_t n = 0;
     int grid = 1;
+    int64_t fused_probes = 0;
 };
 
 flgpu_eval_ctx user_ctx(const flgpu_eval_ctx *c, const ALState *S) {
@@ -104,6 +127,39 @@ void al_ffd(const flgpu_eval_ctx *c, double *f_dev, double *g, const double *x, 
     add_grad(&u, S, g, x, n);
 }
 
+// L / L'.p at x0 + a*p without storing the point (flgpu_fused_fn of the composed problem); the accepted point is
+// stored by the user's fused evaluation and L' is completed in place exactly as al_ffd does.
+void al_fused(const flgpu_eval_ctx *c, int flags, double *f_dev, double *gp_dev, double *x_out, double *g_out,
+              const double *x0, const double *p, double a, int64_t n) {
+    ALState *S = (ALState *)c->user;
+    flgpu_eval_ctx u = user_ctx(c, S);
+    cudaStream_t s = (cudaStream_t)u.stream;
+    const int want = flags & (FLGPU_WANT_F | FLGPU_WANT_GP), write = flags & (FLGPU_WRITE_X | FLGPU_WRITE_G);
+    if (want) {
+        S->user.fused(&u, want, f_dev, gp_dev, nullptr, nullptr, x0, p, a, n);
+        // c is needed for L and for the weights miu c - lambda of L'.p alike
+        S->con.fused(&u, FLGPU_WANT_F | (want & FLGPU_WANT_GP), S->cpart, S->cdp, x0, p, a, S->m, n);
+        if (S->comm && S->comm->nranks > 1) rank_sum(S->comm, s, S->cpart, S->m, S->cglob, S->gather, nullptr, 0);
+        else FLGPU_CUDA_CHECK(cudaMemcpyAsync(S->cglob, S->cpart, sizeof(double) * S->m, cudaMemcpyDeviceToDevice, s));
+        al_probe_terms_kernel<<<1, 32, 0, s>>>(f_dev, gp_dev, S->cglob, S->cdp, S->lambda_dev, S->miu, S->m,
+                                               (want & FLGPU_WANT_F) && u.rank == 0, (want & FLGPU_WANT_GP) != 0);
+        S->fused_probes++;
+    }
+    if (write) {
+        S->user.fused(&u, write, nullptr, nullptr, x_out, g_out, x0, p, a, n);
+        if (write & FLGPU_WRITE_G) {
+            const double *xp = x_out;
+            if (!(write & FLGPU_WRITE_X)) {          // f' at a point that is not stored: form it in a scratch vector
+                if (!S->xtmp) S->xtmp = (double *)ws_alloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+                flgpu_vec_trial(S->xtmp, x0, p, a, n, u.stream);
+                xp = S->xtmp;
+            }
+            eval_c(&u, S, xp, n);
+            add_grad(&u, S, g_out, xp, n);
+        }
+    }
+}
+
 thread_local flgpu_al_stats tls_al{};
 
 // ---- built-in constraint: unit sphere (test.f90:692-705)
@@ -121,6 +177,51 @@ void sphere_cd(const flgpu_eval_ctx *ctx, double *cd_dev, const double *x, int m
     int64_t need = (n + k::kThreads - 1) / k::kThreads;
     const int grid = (int)(need < 1 ? 1 : (need > 148 * 8 ? 148 * 8 : need));
     scale2_kernel<<<grid, k::kThreads, 0, (cudaStream_t)ctx->stream>>>(cd_dev, x, n);
+}
+// fused form (flgpu_c_fused_fn): x.x - 1 and 2x.p at x = x0 + a*p; x.x in dot_kernel's order, hence the bits of sphere_c
+// at the same point
+__global__ void __launch_bounds__(k::kThreads, 4) sphere_fused_kernel(const double *__restrict__ x0, const double *__restrict__ p,
+                                                                      double a, int64_t n, int64_t ch, k::Work w,
+                                                                      double *out_c, double *out_cdp) {
+    const k::Chunks C(n, ch);
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+        const int64_t hi = C.hi(c);
+        double acc[2] = {0.0, 0.0};
+        for (int64_t u = C.lo(c) + threadIdx.x; u < hi; u += k::kThreads) {
+            const double2 xv = k::ld2(x0, u), pv = k::ld2(p, u);
+            const double x = __dadd_rn(xv.x, __dmul_rn(a, pv.x)), y = __dadd_rn(xv.y, __dmul_rn(a, pv.y));
+            acc[0] = fma(y, y, fma(x, x, acc[0]));
+            acc[1] = fma(__dmul_rn(2.0, y), pv.y, fma(__dmul_rn(2.0, x), pv.x, acc[1]));
+        }
+        if (C.tail_here(c) && threadIdx.x == 0) {
+            const double pv = p[n - 1], x = __dadd_rn(x0[n - 1], __dmul_rn(a, pv));
+            acc[0] = fma(x, x, acc[0]);
+            acc[1] = fma(__dmul_rn(2.0, x), pv, acc[1]);
+        }
+        red::chunk_flush<2>(acc, parity, w.partials, w.stride, c);
+    }
+    if (out_c) {
+        double *const o[2] = {out_c, out_cdp};
+        red::finish_in_kernel<2>(w.partials, w.stride, C.nchunks, w.tickets, o);
+    }
+}
+void sphere_fused(const flgpu_eval_ctx *ctx, int flags, double *c_dev, double *cdp_dev, const double *x0, const double *p,
+                  double a, int m, int64_t n) {
+    (void)m; (void)flags;                          // both sums come out of the one pass
+    cudaStream_t s = (cudaStream_t)ctx->stream;
+    const int64_t n_global = ctx->n_global < n ? n : ctx->n_global;
+    const int64_t ch = red::chunk_elems(n_global), nchunks = red::num_chunks(n, ch);
+    const k::Work w = scratch_work(s, nchunks);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (int64_t)sms * 4;
+    if (nchunks < grid) grid = nchunks < 1 ? 1 : nchunks;
+    const bool in_kernel = nchunks <= red::kBlockChunks;
+    sphere_fused_kernel<<<(int)grid, k::kThreads, 0, s>>>(x0, p, a, n, ch, w, in_kernel ? c_dev : nullptr, cdp_dev);
+    if (!in_kernel) { double *out[2] = {c_dev, cdp_dev}; flgpu_reduce_tree(ctx->stream, nchunks, 2, out); }
+    if (ctx->rank == 0) k::add_scalar_kernel<<<1, 1, 0, s>>>(c_dev, -1.0);
 }
 // reference-ABI form of the same constraint: device x / cdx, host cx
 void ref_sphere_c(double *cx, const double *x, const int *M, const int *N) {
@@ -209,7 +310,7 @@ void flgpu_last_al_stats(flgpu_al_stats *out) { *out = tls_al; }
 
 int flgpu_builtin_constraints(int kind, flgpu_constraints *out) {
     if (kind != FLGPU_CON_SPHERE) return 1;
-    out->c = sphere_c; out->cd = sphere_cd; out->m = 1;
+    out->c = sphere_c; out->cd = sphere_cd; out->m = 1; out->fused = sphere_fused;
     return 0;
 }
 int flgpu_builtin_ref_constraints(int kind, flgpu_ref_c_fn *c, flgpu_ref_cd_fn *cd) {
@@ -259,6 +360,8 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
     S.cglob = (double *)ws_alloc(sizeof(double) * kMaxConstraints);
     S.gather = (double *)ws_alloc(sizeof(double) * kMaxConstraints * (size_t)(G > 1 ? G : 1));
     S.cd_dev = (double *)ws_alloc(sizeof(double) * (size_t)S.ld * (size_t)m);
+    S.cdp = (double *)ws_alloc(sizeof(double) * kMaxConstraints);
+    S.n = n;
     double *xdev = x;
     if (x_space == FLGPU_SPACE_HOST) {          // x stays in HBM across the outer iterations
         xdev = (double *)ws_alloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
@@ -269,7 +372,10 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
 
     flgpu_problem L;
     L.f = al_f; L.fd = al_fd; L.f_fd = al_ffd;       // the reference always passes f_fd = L_Ld / L_Ld_fdwithf
-    L.user = &S; L.fused = nullptr; L.search = nullptr; L.search_caps = 0; L.update = nullptr;
+    // line-search trials without materialised points when both the objective and the constraints can be probed
+    // (flgpu_options.no_fused switches it off like every other fused evaluation)
+    const bool al_fuse = prob->fused && con->fused;
+    L.user = &S; L.fused = al_fuse ? al_fused : nullptr; L.search = nullptr; L.search_caps = 0; L.update = nullptr; L.direction = nullptr;
     flgpu_eval_ctx ctx;
     ctx.user = prob->user; ctx.stream = (void *)s; ctx.offset = in.offset; ctx.n_global = in.n_global ? in.n_global : n;
     ctx.rank = S.comm ? S.comm->rank : 0; ctx.nranks = G; ctx.device = dev;
@@ -317,6 +423,8 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
     ws_free(S.cglob, sizeof(double) * kMaxConstraints);
     ws_free(S.gather, sizeof(double) * kMaxConstraints * (size_t)(G > 1 ? G : 1));
     ws_free(S.cd_dev, sizeof(double) * (size_t)S.ld * (size_t)m);
+    ws_free(S.cdp, sizeof(double) * kMaxConstraints);
+    if (S.xtmp) ws_free(S.xtmp, sizeof(double) * (size_t)(n > 0 ? n : 1));
     if (own_stream) { scratch_release(s); cudaStreamDestroy(s); }
     ws_arena_end();                                 // returns the parked work space to the driver
     tls_al = A;
@@ -380,6 +488,7 @@ void __nonlinearoptimization_MOD_augmentedlagrangian(
     prob.user = &U;                                   // RefAdapter is the first member: ad_f / ad_fd / ad_ffd still work
     prob.fused = nullptr;
     prob.update = nullptr;
+    prob.direction = nullptr;
     U.con.c = c; U.con.cd = cd; U.con.cb_space = U.obj.cb_space; U.con.N = *N; U.con.M = *M;
     FLGPU_CUDA_CHECK(cudaMallocHost((void **)&U.con.ch, sizeof(double) * (size_t)(*M > 0 ? *M : 1)));
     if (U.con.cb_space == FLGPU_SPACE_HOST) {
@@ -387,7 +496,7 @@ void __nonlinearoptimization_MOD_augmentedlagrangian(
         FLGPU_CUDA_CHECK(cudaMallocHost((void **)&U.con.cdh, sizeof(double) * (size_t)(*N > 0 ? *N : 1) * (size_t)(*M > 0 ? *M : 1)));
     }
     flgpu_constraints con;
-    con.c = ad_c; con.cd = ad_cd; con.m = *M;
+    con.c = ad_c; con.cd = ad_cd; con.m = *M; con.fused = nullptr;
     flgpu_augmented_lagrangian(&prob, &con, &o, x, *N, x_space_now(), nullptr);
     ref_adapter_free(U.obj);
     if (U.con.ch) cudaFreeHost(U.con.ch);

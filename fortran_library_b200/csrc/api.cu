@@ -19,6 +19,7 @@ using namespace flgpu;
 namespace flgpu {
 flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f);   // objectives.cu
 flgpu_update_fn builtin_update_for(flgpu_ref_f_fn f);
+flgpu_direction_fn builtin_direction_for(flgpu_ref_f_fn f);
 extern int g_k1_shape[2];                             // backend_cuda.cu
 }
 
@@ -131,6 +132,12 @@ void ad_update(const flgpu_eval_ctx *c, const flgpu_update_args *args, int64_t n
     inner.user = A->fused_user;
     A->update(&inner, args, n);
 }
+void ad_direction(const flgpu_eval_ctx *c, const flgpu_direction_args *args, int64_t n) {
+    const RefAdapter *A = (const RefAdapter *)c->user;
+    flgpu_eval_ctx inner = *c;
+    inner.user = A->fused_user;
+    A->direction(&inner, args, n);
+}
 void to_host(const RefAdapter *A, const double *x_dev, int64_t n, cudaStream_t s) {
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(A->xh, x_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -191,15 +198,17 @@ void ref_adapter_init(RefAdapter &A, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu
     prob->search = nullptr;
     prob->search_caps = 0;
     prob->update = nullptr;
+    prob->direction = nullptr;
     if (A.cb_space == FLGPU_SPACE_DEVICE) {
         {
             std::lock_guard<std::mutex> lock(g_fused_mu);
             auto it = g_fused.find(f);
             if (it != g_fused.end()) { A.fused = it->second.fn; A.fused_user = it->second.user; }
         }
-        if (!A.fused) { A.fused = builtin_fused_for(f); A.update = builtin_update_for(f); }
+        if (!A.fused) { A.fused = builtin_fused_for(f); A.update = builtin_update_for(f); A.direction = builtin_direction_for(f); }
         if (A.fused) prob->fused = ad_fused;
         if (A.fused && A.update) prob->update = ad_update;
+        if (A.fused && A.direction) prob->direction = ad_direction;
     }
 }
 void ref_adapter_free(RefAdapter &A) {

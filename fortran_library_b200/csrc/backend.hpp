@@ -85,6 +85,13 @@ public:
     virtual void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
                                  int recent) = 0;
 
+    // K3 with the first trial of the next search (a = 1) evaluated inside the kernel (flgpu_problem.direction): p is
+    // written, x1 + p is formed in registers only; f -> SL_F and (flags & FLGPU_WANT_GP) f'.p -> SL_GP with the bits a
+    // fused_eval(flags, 1.0, x1, p) would deliver.
+    virtual bool fused_direction_available() const { return false; }
+    virtual void lbfgs_direction_probe(double * /*p*/, const double * /*g1*/, const double * /*x1*/, int /*k*/,
+                                       int /*recent*/, int /*flags*/) {}
+
     // ---- CG (f90:352-393)
     virtual void cg_dots(const double *g1, const double *g0, const double *p) = 0;
     virtual void cg_update(double *p, const double *g1, double beta) = 0;  // p = -g1 + beta*p; g1.p -> SL_GP0

@@ -665,7 +665,7 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
     const int t = time_begin("k3_direction", 8.0 * n * (2.0 * kk + (xt ? 4.0 : 2.0)));
     k::K3Args a;
     a.p = p; a.xt = xt; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n; a.ch = ch;
-    a.m = mem; a.k = kk; a.recent = recent; a.w = work;
+    a.m = mem; a.k = kk; a.recent = recent; a.offset = ctx.offset; a.n_global = ctx.n_global; a.w = work;
     DeviceFacts &f = facts(device);
     if (f.k3_mode < 0) {
         // FLGPU_K3 = regs (register double buffers) | tma (default: bulk-async ring, 11 pieces x 2 stages, 2 CTAs/SM:
@@ -684,11 +684,11 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
         if (!done && (f.k3_mode == 100 * P + NST || (ID == 0 && f.k3_mode == 1))) {                                        \
             constexpr size_t smem = (size_t)NST * P * k::kThreads * sizeof(double2);                                       \
             if (!f.k3_tma_attr[ID]) {                                                                                      \
-                FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<P, NST, MINB>,                            \
+                FLGPU_CUDA_CHECK(cudaFuncSetAttribute(k::k3_direction_tma_kernel<P, NST, MINB, k::NoProbe>,                           \
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
                 f.k3_tma_attr[ID] = 1;                                                                                     \
             }                                                                                                              \
-            k::k3_direction_tma_kernel<P, NST, MINB><<<grid_for(MINB), k::kThreads + 32, smem, stream>>>(a);               \
+            k::k3_direction_tma_kernel<P, NST, MINB, k::NoProbe><<<grid_for(MINB), k::kThreads + 32, smem, stream>>>(a, k::NoProbe()); \
             done = true;                                                                                                   \
         }
         // the shapes of profiles/r02_k3_ring_shapes.md worth keeping selectable (the one-CTA-per-SM and 3-CTA ones lost)
@@ -700,6 +700,25 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
     launches++;
     double *out[2] = {R + SL_GP0, R + SL_PP};
     tree(2, out);
+    time_end(t);
+}
+
+// K3 launched by the objective with its probe (flgpu_problem.direction): reads g1, x1 and the 2k columns, writes p; the
+// chunk sums of g1.p, p.p, f(x1+p), f'(x1+p).p go to rows 0..3.
+void CudaBackend::lbfgs_direction_probe(double *p, const double *g1, const double *x1, int kk, int recent, int flags) {
+    const int t = time_begin("k3_direction_probe", 8.0 * n * (2.0 * kk + 3.0));
+    k::K3Launch L;
+    k::K3Args &a = L.a;
+    a.p = p; a.xt = nullptr; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n; a.ch = ch;
+    a.m = mem; a.k = kk; a.recent = recent; a.offset = ctx.offset; a.n_global = ctx.n_global; a.w = work;
+    L.grid = grid_for(2); L.stream = (void *)stream;
+    flgpu_direction_args da;
+    da.k3 = &L; da.k3_bytes = sizeof L; da.flags = flags;
+    prob.direction(&ctx, &da, n);
+    callback_launches++;
+    const bool wgp = (flags & FLGPU_WANT_GP) != 0;
+    double *out[4] = {R + SL_GP0, R + SL_PP, R + SL_F, R + SL_GP};
+    tree(wgp ? 4 : 3, out);
     time_end(t);
 }
 

@@ -49,6 +49,7 @@ void ws_arena_end();
 // ---- per-stream scratch of the built-in objectives / primitives (objectives.cu)
 void scratch_release(cudaStream_t s);
 double *scratch_scalar(cudaStream_t s);   // device double[4] private to the stream
+k::Work scratch_work(cudaStream_t s, int64_t nchunks);   // the stream's reduction rows (8), tickets zero between kernels
 
 // ---- NCCL (resolved with dlopen so single-GPU use has no NCCL dependency)
 void nccl_allgather_f64(flgpu_comm *c, const double *send, double *recv, size_t count, cudaStream_t s);
@@ -95,6 +96,8 @@ public:
     void lbfgs_update_dots(const double *x1, const double *x0, const double *g1, const double *g0,
                            int new_slot, int k_after) override;
     void lbfgs_solve(int k, int recent) override;
+    bool fused_direction_available() const override { return prob.direction != nullptr && prob.fused != nullptr; }
+    void lbfgs_direction_probe(double *p, const double *g1, const double *x1, int k, int recent, int flags) override;
     void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
                          int recent) override;
     void cg_dots(const double *g1, const double *g0, const double *p) override;

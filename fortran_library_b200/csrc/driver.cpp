@@ -225,6 +225,10 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
     // the same bits, 3n more doubles of traffic; kept for comparison)
     const char *fu = std::getenv("FLGPU_FUSED_UPDATE");
     const bool fuse_k1 = fused && B.fused_update_available() && !(fu && fu[0] == '0');
+    // K3 evaluates the first trial (a = 1) of the next search while it writes p (FLGPU_FUSED_DIRECTION=0: a separate
+    // probe launch follows K3 -- the same bits, n more doubles of traffic; kept for comparison)
+    const char *fd_env = std::getenv("FLGPU_FUSED_DIRECTION");
+    const bool fuse_k3 = fused && B.fused_direction_available() && !(fd_env && fd_env[0] == '0');
     B.lbfgs_alloc(mem);
     B.upload(xc, x_user, x_space);
 
@@ -280,6 +284,11 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
                 B.lbfgs_solve(k_after, new_slot);                            // K2
                 if (dsearch) {                                               // K3: new p only
                     B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);
+                } else if (fuse_k3) {                                        // K3: new p and the first trial (a=1) in one pass
+                    B.lbfgs_direction_probe(p, gc, xc, k_after, new_slot,
+                                            next_fdwithf ? (FLGPU_WANT_F | FLGPU_WANT_GP) : FLGPU_WANT_F);
+                    st.n_trials++;
+                    if (next_fdwithf) st.n_f_fd++; else st.n_f++;
                 } else if (fused) {                                          // K3: new p; first trial (a=1) probed
                     B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);
                     st.n_trials++;

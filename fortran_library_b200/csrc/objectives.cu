@@ -82,6 +82,7 @@ void scratch_release(cudaStream_t s) {
     g_scratch.erase(it);
 }
 double *scratch_scalar(cudaStream_t s) { return scratch_for(s, 1).scalar; }
+k::Work scratch_work(cudaStream_t s, int64_t nchunks) { return scratch_for(s, nchunks < 1 ? 1 : nchunks).work; }
 
 // chunk sums of rows [0, nrows) of `w` -> out[row] (device pointers; null = skip)
 void launch_tree(const k::Work &w, int64_t nchunks, int nrows, double *const *out, cudaStream_t s) {
@@ -274,6 +275,32 @@ struct BuiltinSrc {
         objective_tail<KIND, false>(ix, i, x1, f, g1);
         objective_tail<KIND, false>(ix, i, x0, f, g0);
         if (own_new) { a.x1_out[i] = x1; a.g1_out[i] = g1; }
+    }
+};
+
+// K3 probe for the built-in objectives (flgpu_problem.direction, include/flgpu_k3.cuh): f and f'.p at the a = 1 trial
+// point K3 forms in registers -- objective_unit on the same point in the same per-thread unit order as
+// objective_chunk, hence the chunk sums (and everything above them) of the separate fused evaluation.
+template <int KIND>
+struct BuiltinProbe {
+    static constexpr bool kOn = true;
+    const double *tables;
+    double scale;
+    int want_gp;
+    ObjIndex ix;
+    __device__ void init(const K3Args &a, int nthreads) {
+        __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
+        ix = load_tables<KIND>(a.offset, a.n_global, scale, tables, tab, nthreads);
+    }
+    __device__ __forceinline__ void unit(int64_t u, const double2 xt, const double2 pv, double &fsum, double &gpsum) const {
+        double2 g = make_double2(0.0, 0.0);
+        objective_unit<KIND, true, true>(ix, u, xt, fsum, g);
+        if (want_gp) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
+    }
+    __device__ __forceinline__ void tail(int64_t i, const double xt, const double pv, double &fsum, double &gpsum) const {
+        double g = 0.0;
+        objective_tail<KIND, true>(ix, i, xt, fsum, g);
+        if (want_gp) gpsum = fma(g, pv, gpsum);
     }
 };
 
@@ -589,6 +616,20 @@ static void dev_update(const flgpu_eval_ctx *c, const flgpu_update_args *A, int6
     k::launch_k1_pass(L, src);
 }
 
+// flgpu_problem.direction: K3 with the first trial of the next search evaluated inside the kernel
+template <int KIND>
+static void dev_direction(const flgpu_eval_ctx *c, const flgpu_direction_args *A, int64_t n) {
+    (void)n;
+    if (A->k3_bytes != sizeof(k::K3Launch)) fatal("flgpu_problem.direction: K3Launch layout mismatch (header / library versions differ)");
+    const k::K3Launch &L = *(const k::K3Launch *)A->k3;
+    Scratch &sc = scratch_for((cudaStream_t)c->stream, 1);
+    k::BuiltinProbe<KIND> probe;
+    probe.tables = sc.tables;
+    probe.scale = L.a.n_global > 1 ? 16777216.0 / (double)(L.a.n_global - 1) : 0.0;
+    probe.want_gp = (A->flags & FLGPU_WANT_GP) ? 1 : 0;
+    k::launch_k3_probe(L, probe);
+}
+
 // device-resident search: same chunk sums and tree as the probes (bit-identical f, f'.p); the grid is capped by what
 // can be co-resident (any grid gives the same bits: the chunk sums do not depend on which block forms them)
 template <int KIND, bool FAST>
@@ -658,10 +699,10 @@ using namespace flgpu;
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {
-    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<0>; return 0;
-    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<1>; return 0;
-    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<2>; return 0;
-    case FLGPU_OBJ_QUARTIC_SHIFTED: out->f = dev_f<3>; out->fd = dev_fd<3>; out->f_fd = dev_ffd<3>; out->fused = dev_fused<3>; out->search = dev_search<3>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<3>; return 0;
+    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<0>; out->direction = dev_direction<0>; return 0;
+    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<1>; out->direction = dev_direction<1>; return 0;
+    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<2>; out->direction = dev_direction<2>; return 0;
+    case FLGPU_OBJ_QUARTIC_SHIFTED: out->f = dev_f<3>; out->fd = dev_fd<3>; out->f_fd = dev_ffd<3>; out->fused = dev_fused<3>; out->search = dev_search<3>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<3>; out->direction = dev_direction<3>; return 0;
     }
     return 1;
 }
@@ -673,6 +714,13 @@ flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f) {
     if (f == ref_f<1>) return dev_fused<1>;
     if (f == ref_f<2>) return dev_fused<2>;
     if (f == ref_f<3>) return dev_fused<3>;
+    return nullptr;
+}
+flgpu_direction_fn builtin_direction_for(flgpu_ref_f_fn f) {
+    if (f == ref_f<0>) return dev_direction<0>;
+    if (f == ref_f<1>) return dev_direction<1>;
+    if (f == ref_f<2>) return dev_direction<2>;
+    if (f == ref_f<3>) return dev_direction<3>;
     return nullptr;
 }
 flgpu_update_fn builtin_update_for(flgpu_ref_f_fn f) {

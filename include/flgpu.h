@@ -118,6 +118,22 @@ typedef struct flgpu_update_args {
 } flgpu_update_args;
 typedef void (*flgpu_update_fn)(const flgpu_eval_ctx *ctx, const flgpu_update_args *args, int64_t n_local);
 
+/* Optional FUSED FIRST TRIAL (an extension; L-BFGS with a fused line search only).  Every line search of the L-BFGS main
+ * loop starts at a = 1 (f90:607), i.e. at x + p with the direction p that Before() has just formed (f90:589-607).  With
+ * this callback the library's K3 kernel, instantiated by the objective with a probe (include/flgpu_k3.cuh), evaluates
+ * that trial while it writes p: it reads x as well, forms x + 1*p in registers and reduces f and f'.p with the chunk
+ * order of the fused evaluation -- the same bits as a separate flgpu_fused_fn call with a = 1, for n instead of 2n doubles
+ * and one launch less per iteration.  flags = FLGPU_WANT_F or FLGPU_WANT_F | FLGPU_WANT_GP (the reference's f / f_fd call
+ * at the first trial).  The callback launches exactly that pass on ctx->stream:
+ *     flgpu::k::launch_k3_probe(*(const flgpu::k::K3Launch *)args->k3, MyProbe{...});
+ * (libflgpu's built-in objectives and include/flgpu_objective.cuh provide it). */
+typedef struct flgpu_direction_args {
+    const void *k3;     /* flgpu::k::K3Launch prepared by the library: vectors, coefficients, ring buffers, geometry */
+    size_t k3_bytes;    /* sizeof(flgpu::k::K3Launch) the library was built with (callbacks check it) */
+    int flags;          /* FLGPU_WANT_F [| FLGPU_WANT_GP] */
+} flgpu_direction_args;
+typedef void (*flgpu_direction_fn)(const flgpu_eval_ctx *ctx, const flgpu_direction_args *args, int64_t n_local);
+
 typedef struct flgpu_problem {
     flgpu_f_fn f;       /* required */
     flgpu_fd_fn fd;     /* required */
@@ -127,6 +143,7 @@ typedef struct flgpu_problem {
     flgpu_search_fn search; /* optional (NULL = the host drives the search, one round trip per evaluation) */
     int search_caps;        /* FLGPU_SEARCH_ROW_SHARDS if `search` handles flgpu_search_args.comm != NULL; else 0 */
     flgpu_update_fn update; /* optional, needs `fused` (NULL = the search stores the accepted point, K1 reads it back) */
+    flgpu_direction_fn direction; /* optional, needs `fused` (NULL = the first trial of a search is a flgpu_fused_fn call) */
 } flgpu_problem;
 
 /* ------------------------------------------------------------------ options / results */
@@ -242,10 +259,25 @@ int flgpu_steepest_descent(const flgpu_problem *prob, const flgpu_options *opt, 
 typedef void (*flgpu_c_fn)(const flgpu_eval_ctx *ctx, double *c_dev, const double *x_dev, int m, int64_t n_local);
 typedef void (*flgpu_cd_fn)(const flgpu_eval_ctx *ctx, double *cd_dev, const double *x_dev, int m, int64_t n_local,
                             int64_t ld);
+/* Optional FUSED constraint evaluation (an extension; used when flgpu_problem.fused exists too).  The reference composes
+ * L = f - lambda.c + miu/2 c.c and L' = f' + cd (miu c - lambda) (f90:2193-2228) and its line search evaluates them at
+ * every trial point x = x0 + a*p: x stored, c and the N x M Jacobian stored, L' stored, then dot_product(L', p) --
+ * 13n doubles per trial with one constraint.  A line search only needs the scalars L(x) and L'(x).p =
+ * f'.p + sum_j (miu c_j - lambda_j) (cd_j . p); with this callback the library asks for them without storing anything:
+ *     x = x0 + a*p                         element-wise, multiply THEN add, never stored
+ *     FLGPU_WANT_F  : c_dev[j]   = this rank's partial of c_j(x)
+ *     FLGPU_WANT_GP : cdp_dev[j] = this rank's partial of (d c_j / d x)(x) . p
+ * 2n per trial for the objective plus what the constraints read (2n for an element-local constraint).  The accepted
+ * point, c, the Jacobian and L' are formed and stored once per search, as before.  The slope L'.p is then summed in a
+ * different association than dot_product(L', p): iterates agree with the unfused composition to rounding, not bit for bit
+ * (unlike flgpu_fused_fn for a plain objective). */
+typedef void (*flgpu_c_fused_fn)(const flgpu_eval_ctx *ctx, int flags, double *c_dev, double *cdp_dev,
+                                 const double *x0_dev, const double *p_dev, double a, int m, int64_t n_local);
 typedef struct flgpu_constraints {
     flgpu_c_fn c;
     flgpu_cd_fn cd;
     int m;
+    flgpu_c_fused_fn fused; /* optional (NULL = trial points of the inner solves are materialised) */
 } flgpu_constraints;
 enum { FLGPU_AL_LBFGS = 0, FLGPU_AL_CG = 1 };
 typedef struct flgpu_al_options {

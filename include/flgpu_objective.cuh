@@ -31,6 +31,7 @@
 
 #include "flgpu.h"
 #include "flgpu_k1.cuh"
+#include "flgpu_k3.cuh"
 #include "flgpu_reduce.cuh"
 #include "flgpu_search_core.hpp"
 
@@ -245,6 +246,39 @@ struct FunctorSrc {
     }
 };
 
+// K3 probe for functor objectives (flgpu_problem.direction, flgpu_k3.cuh): f and f'.p at the a = 1 trial point that K3
+// forms in registers, accumulated exactly as chunk<Obj, true, true, WANT_GP, ...> does for the same units
+template <class Obj>
+struct FunctorProbe {
+    static constexpr bool kOn = true;
+    Obj obj;
+    int64_t offset;
+    int want_gp;
+    __device__ void init(const flgpu::k::K3Args &, int) {}
+    __device__ __forceinline__ void unit(int64_t u, const double2 xt, const double2 pv, double &fsum, double &gpsum) const {
+        const int64_t i = offset + 2 * u;
+        double2 g;
+        if constexpr (Obj::WIDTH == 2) {
+            double f = 0.0;
+            obj.eval2(i, xt.x, xt.y, f, g.x, g.y);
+            fsum += f;
+        } else {
+            double f0 = 0.0, f1 = 0.0;
+            obj.eval(i, xt.x, f0, g.x);
+            obj.eval(i + 1, xt.y, f1, g.y);
+            fsum += f0; fsum += f1;
+        }
+        if (want_gp) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
+    }
+    __device__ __forceinline__ void tail(int64_t k, const double xt, const double pv, double &fsum, double &gpsum) const {
+        double f = 0.0, g = 0.0;
+        if constexpr (Obj::WIDTH == 2) obj.eval_tail(offset + k, xt, f, g);
+        else obj.eval(offset + k, xt, f, g);
+        fsum += f;
+        if (want_gp) gpsum = fma(g, pv, gpsum);
+    }
+};
+
 template <class Obj>
 struct Callbacks {
     static void geometry(const flgpu_eval_ctx *ctx, int64_t n, Args &A, int64_t &nchunks) {
@@ -308,6 +342,14 @@ struct Callbacks {
         FunctorSrc<Obj> src{*(const Obj *)ctx->user};
         flgpu::k::launch_k1_pass(*(const flgpu::k::K1Launch *)A->k1, src);
     }
+    static void direction(const flgpu_eval_ctx *ctx, const flgpu_direction_args *A, int64_t) {
+        if (A->k3_bytes != sizeof(flgpu::k::K3Launch)) {
+            std::fprintf(stderr, "flgpu_obj: K3Launch layout mismatch (header and libflgpu.so versions differ)\n");
+            std::abort();
+        }
+        FunctorProbe<Obj> probe{*(const Obj *)ctx->user, ctx->offset, (A->flags & FLGPU_WANT_GP) ? 1 : 0};
+        flgpu::k::launch_k3_probe(*(const flgpu::k::K3Launch *)A->k3, probe);
+    }
     static void f(const flgpu_eval_ctx *ctx, double *f_dev, const double *x, int64_t n) {
         launch<false, true, false, false, false>(ctx, f_dev, nullptr, nullptr, nullptr, x, nullptr, 0.0, n);
     }
@@ -353,6 +395,7 @@ inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool wi
     p.search = (with_fused && with_search) ? Callbacks<Obj>::search : nullptr;
     p.search_caps = 0;                        // single GPU: row-sharded runs use the host-driven search
     p.update = with_fused ? Callbacks<Obj>::update : nullptr;
+    p.direction = with_fused ? Callbacks<Obj>::direction : nullptr;
     return p;
 }
 

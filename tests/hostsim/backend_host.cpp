@@ -393,6 +393,7 @@ void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->search = nullptr;
     out->search_caps = 0;
     out->update = nullptr;
+    out->direction = nullptr;
 }
 
 void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {

@@ -563,6 +563,42 @@ def test_fused_update_is_the_same_algorithm(name, kw, n):
     assert on["False"]["rows"] == on["True"]["rows"] and on["False"]["x"] == on["True"]["x"]
 
 
+@pytest.mark.parametrize("name,kw", [("rosenR1", dict(Memory=10, MaxIteration=40)), ("quartic", dict(Memory=3)),
+                                     ("diag", dict(Memory=30, MaxIteration=45)), ("rosenR1", dict(Memory=12, use_ffd=False, MaxIteration=30)),
+                                     ("rosenR1", dict(Memory=10, MaxIteration=30, line_search="fast")),
+                                     ("quartic1", dict(Memory=5, Strong=False))])
+@pytest.mark.parametrize("n", [10_001, 1 << 20, (1 << 22) + 3])
+def test_fused_direction_is_the_same_algorithm(name, kw, n):
+    """flgpu_problem.direction: K3 evaluates the a = 1 trial of the next line search while it writes p (x1 + p formed in
+    registers; f and f'.p reduced in the chunk order of the fused evaluation).  Every iterate, step and counter must be
+    IDENTICAL with the callback switched off (FLGPU_FUSED_DIRECTION=0: a separate probe launch after K3);
+    n = 2^22+3 runs the full 296-block grid with an odd tail."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    code = ("import sys, json; sys.path.insert(0, %r); sys.path.insert(0, %r)\nimport numpy as np, fortran_library_b200 as fl\n"
+            "kind, start, seed = %r\n"
+            "x = fl.DeviceVector.start(start, %d, seed=seed)\n"
+            "p = fl.builtin_problem(kind)\n"
+            "if not %r: p.f_fd = None\n"
+            "ob = fl.Observer()\n"
+            "st = fl.LBFGS(p, x, Warning=False, observer=ob, device_search=False, **%r)\n"
+            "xn = x.numpy()\n"
+            "import hashlib\n"
+            "print(json.dumps(dict(rows=ob.rows, x=hashlib.sha256(xn.tobytes()).hexdigest(), xs=float(np.sum(xn)), n_f_fd=st.n_f_fd, n_f=st.n_f,\n"
+            "                 n_fd=st.n_fd, trials=st.n_trials, it=st.iterations, status=st.status, f=st.f, g2=st.gnorm2)))\n"
+            % (ROOT, os.path.join(ROOT, "tests"), _cases.OBJECTIVES[name], n, use, kw))
+    res = []
+    for env in ({}, {"FLGPU_FUSED_DIRECTION": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    on, off = res
+    assert on["rows"] == off["rows"] and on["x"] == off["x"] and on["xs"] == off["xs"]
+    for k in ("n_f_fd", "n_f", "n_fd", "trials", "it", "status", "f", "g2"):
+        assert on[k] == off[k], k
+    assert on["it"] > 3
+
+
 # ----------------------------------------------------------------------------- GPU == scalar C++ statement, bit for bit
 @pytest.mark.parametrize("algo,name,kw", [
     ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=40)), ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=25, fused=False)),
@@ -735,6 +771,41 @@ def test_augmented_lagrangian_vs_oracle(fl, solver, kw, n):
                                 **kw)
     assert st.status == 0 and abs(np.linalg.norm(x) - 1.0) < 1e-9      # "norm2(x)-1 should print close to 0"
     assert _cases.rel(x, xr) < max(1e-7, 1e-10 * n)
+
+
+@pytest.mark.parametrize("solver,kw", [("LBFGS", dict()), ("LBFGS", dict(Memory=5, miu0=4.0, lambda0=[0.3], Increment=1.3)),
+                                       ("ConjugateGradient", dict()), ("ConjugateGradient", dict(Method="PR")),
+                                       ("LBFGS", dict(line_search="fast"))])
+@pytest.mark.parametrize("n", [10, 4097, (1 << 20) + 1])
+def test_augmented_lagrangian_fused_probe(fl, solver, kw, n):
+    """flgpu_constraints.fused: the inner solves' line searches ask for L(x0+a p) and L'(x0+a p).p as scalars (objective
+    probe + constraint probe, nothing stored) instead of materialising the point, c, the Jacobian and L'.  L is the
+    same sum; L'.p = f'.p + sum_j (miu c_j - lambda_j)(cd_j.p) is associated differently from dot_product(L', p), so the
+    two compositions agree to rounding, not bit for bit: same outer iterations (+-1 where the unfused run itself is
+    on an edge: PR), same multiplier schedule, same point on the sphere to the inner tolerance; far fewer bytes."""
+    x0 = _cases.start("quartic", n)
+    prob, con = fl.builtin_problem(fl.OBJ_QUARTIC), fl.builtin_constraints()
+    assert con.fused
+    res = []
+    for fused in (True, False):
+        x = fl.DeviceVector.from_numpy(x0)
+        st = fl.AugmentedLagrangian(prob, con, x, UnconstrainedSolver=solver, Warning=False, MaxIteration=60, Precision=1e-6,
+                                    fused=fused, **kw)
+        res.append((x.numpy(), st))
+    (xf, sf), (xp, sp) = res
+    assert sf.status == 0 and sp.status == 0
+    slack = 1 if kw.get("Method") == "PR" or kw.get("line_search") == "fast" else 0
+    assert abs(sf.outer_iterations - sp.outer_iterations) <= slack, (sf.outer_iterations, sp.outer_iterations)
+    if sf.outer_iterations == sp.outer_iterations:
+        assert sf.miu == sp.miu
+    assert abs(np.linalg.norm(xf) - 1.0) < 1e-6
+    assert _cases.rel(xf, xp) < max(1e-6, 1e-6 * n), _cases.rel(xf, xp)
+    assert abs(sf.f - sp.f) <= 1e-6 * abs(sp.f)
+    if n <= 4097 and "line_search" not in kw:                 # and against the oracle, like the unfused composition
+        xr, sr = O.al(O.builtin_callbacks(O.OBJ_QUARTIC, 0, n), O.sphere_constraint(), x0.copy(), UnconstrainedSolver=solver,
+                      use_ffd=True, Warning=False, MaxIteration=60, Precision=1e-6, **kw)
+        assert abs(sf.outer_iterations - sr.outer_iterations) <= slack
+        assert _cases.rel(xf, xr) < max(1e-6, 1e-6 * n)
 
 
 def test_fortran_abi_augmented_lagrangian(fl):
