@@ -65,12 +65,12 @@ def static_config(n, mem, objective):
 POLICIES = {"reference": "reference (StrongWolfe_fdwithf f90:1582-1698, statement by statement)",
             "fast": "fast (FLGPU_LS_FAST: first trial satisfying the strong Wolfe conditions is accepted; not a "
                     "reference routine)"}
-LS_MODES = {True: "fused (flgpu_fused_fn + flgpu_update_fn + flgpu_direction_fn: the objective kernel forms x0+a*p; 2n doubles "
-                  "per trial, the first trial of a search is evaluated by K3 while it writes p, the accepted point is formed "
-                  "and stored by K1)",
+LS_MODES = {True: "fused (flgpu_fused_fn / flgpu_fused_multi_fn + flgpu_update_fn + flgpu_direction_fn: the objective kernel "
+                  "forms x0+a*p; 2n doubles per PASS, a pass evaluating up to four trials of a bracketing walk; the first four "
+                  "trials of a search are evaluated by K3 while it writes p; the accepted point is formed and stored by K1)",
             False: "plain (opaque f/fd/f_fd device callbacks; 7n doubles per f+g trial)"}
 NCU_NAMES = {"k1_update_dots": "k1_update_dots_kernel", "k1_update_dots_fused": "k1_update_dots_kernel",
-             "k3_direction": "k3_direction_tma_kernel", "k3_direction_probe": "k3_direction_tma_kernel_probe",
+             "k3_direction": "k3_direction_tma_kernel", "k3_direction_probe": "k3_direction_tma_kernel",
              "trial_x": "trial_kernel",
              "dot": "dot_kernel", "cg_dots": "cg_dots_kernel", "cg_update": "cg_update_kernel"}
 
@@ -596,7 +596,12 @@ def run_ours(args):
                         "device_resident_search": (f"{args.device_search}: " + (
                             "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
                             "off at this size (host-driven, one round trip per trial)")),
-                        "trials_in_timed_region": trials, "trials_per_iteration": trials / K},
+                        "trials_in_timed_region": trials, "trials_per_iteration": trials / K,
+                        "objective_kernel_launches_per_iteration": (mark["c1"][1] - mark["c0"][1]) / K,
+                        "batching": "the trials of a bracketing walk (a, a*Increment, ...) share one pass over x0 and p, four "
+                                    "at a time; K3 evaluates the first four of every search (flgpu_fused_multi_fn, "
+                                    "flgpu_direction_fn): same trial points, decisions, counts and bits, fewer passes"
+                                    if fused else None},
                 "per_iteration": per_iteration,
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "cpu_baseline_all_cores": cpu_all, "parity": parity, "secondary": secondary,

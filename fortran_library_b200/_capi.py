@@ -35,7 +35,7 @@ FUSED_FN = C.CFUNCTYPE(None, C.POINTER(EvalCtx), C.c_int, C.c_void_p, C.c_void_p
 class Problem(C.Structure):
     _fields_ = [("f", C.c_void_p), ("fd", C.c_void_p), ("f_fd", C.c_void_p), ("user", C.c_void_p),
                 ("fused", C.c_void_p), ("search", C.c_void_p), ("search_caps", C.c_int),
-                ("update", C.c_void_p), ("direction", C.c_void_p)]
+                ("update", C.c_void_p), ("direction", C.c_void_p), ("fused_multi", C.c_void_p)]
 
 
 class IterInfo(C.Structure):
@@ -63,7 +63,7 @@ class Stats(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("status", C.c_int), ("n_f", C.c_int64), ("n_fd", C.c_int64),
                 ("n_f_fd", C.c_int64), ("n_trials", C.c_int64), ("n_f_only_trials", C.c_int64),
                 ("n_linesearch", C.c_int64), ("gpu_launches", C.c_int64), ("host_syncs", C.c_int64),
-                ("f", C.c_double), ("gnorm2", C.c_double)]
+                ("f", C.c_double), ("gnorm2", C.c_double), ("n_batched_passes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

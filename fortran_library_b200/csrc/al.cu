@@ -375,7 +375,7 @@ int flgpu_augmented_lagrangian(const flgpu_problem *prob, const flgpu_constraint
     // line-search trials without materialised points when both the objective and the constraints can be probed
     // (flgpu_options.no_fused switches it off like every other fused evaluation)
     const bool al_fuse = prob->fused && con->fused;
-    L.user = &S; L.fused = al_fuse ? al_fused : nullptr; L.search = nullptr; L.search_caps = 0; L.update = nullptr; L.direction = nullptr;
+    L.user = &S; L.fused = al_fuse ? al_fused : nullptr; L.search = nullptr; L.search_caps = 0; L.update = nullptr; L.direction = nullptr; L.fused_multi = nullptr;
     flgpu_eval_ctx ctx;
     ctx.user = prob->user; ctx.stream = (void *)s; ctx.offset = in.offset; ctx.n_global = in.n_global ? in.n_global : n;
     ctx.rank = S.comm ? S.comm->rank : 0; ctx.nranks = G; ctx.device = dev;
@@ -489,6 +489,7 @@ void __nonlinearoptimization_MOD_augmentedlagrangian(
     prob.fused = nullptr;
     prob.update = nullptr;
     prob.direction = nullptr;
+    prob.fused_multi = nullptr;
     U.con.c = c; U.con.cd = cd; U.con.cb_space = U.obj.cb_space; U.con.N = *N; U.con.M = *M;
     FLGPU_CUDA_CHECK(cudaMallocHost((void **)&U.con.ch, sizeof(double) * (size_t)(*M > 0 ? *M : 1)));
     if (U.con.cb_space == FLGPU_SPACE_HOST) {

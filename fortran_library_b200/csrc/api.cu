@@ -20,6 +20,7 @@ namespace flgpu {
 flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f);   // objectives.cu
 flgpu_update_fn builtin_update_for(flgpu_ref_f_fn f);
 flgpu_direction_fn builtin_direction_for(flgpu_ref_f_fn f);
+flgpu_fused_multi_fn builtin_fused_multi_for(flgpu_ref_f_fn f);
 extern int g_k1_shape[2];                             // backend_cuda.cu
 }
 
@@ -138,6 +139,13 @@ void ad_direction(const flgpu_eval_ctx *c, const flgpu_direction_args *args, int
     inner.user = A->fused_user;
     A->direction(&inner, args, n);
 }
+void ad_fused_multi(const flgpu_eval_ctx *c, int count, const double *steps, double *out_dev, const double *x0,
+                    const double *p, int64_t n) {
+    const RefAdapter *A = (const RefAdapter *)c->user;
+    flgpu_eval_ctx inner = *c;
+    inner.user = A->fused_user;
+    A->fused_multi(&inner, count, steps, out_dev, x0, p, n);
+}
 void to_host(const RefAdapter *A, const double *x_dev, int64_t n, cudaStream_t s) {
     FLGPU_CUDA_CHECK(cudaMemcpyAsync(A->xh, x_dev, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
     FLGPU_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -199,16 +207,19 @@ void ref_adapter_init(RefAdapter &A, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu
     prob->search_caps = 0;
     prob->update = nullptr;
     prob->direction = nullptr;
+    prob->fused_multi = nullptr;
     if (A.cb_space == FLGPU_SPACE_DEVICE) {
         {
             std::lock_guard<std::mutex> lock(g_fused_mu);
             auto it = g_fused.find(f);
             if (it != g_fused.end()) { A.fused = it->second.fn; A.fused_user = it->second.user; }
         }
-        if (!A.fused) { A.fused = builtin_fused_for(f); A.update = builtin_update_for(f); A.direction = builtin_direction_for(f); }
+        if (!A.fused) { A.fused = builtin_fused_for(f); A.update = builtin_update_for(f); A.direction = builtin_direction_for(f);
+                        A.fused_multi = builtin_fused_multi_for(f); }
         if (A.fused) prob->fused = ad_fused;
         if (A.fused && A.update) prob->update = ad_update;
         if (A.fused && A.direction) prob->direction = ad_direction;
+        if (A.fused && A.fused_multi) prob->fused_multi = ad_fused_multi;
     }
 }
 void ref_adapter_free(RefAdapter &A) {

@@ -24,6 +24,7 @@ struct RefAdapter {
     void *fused_user = nullptr;
     flgpu_update_fn update = nullptr;     // fused accepted-point update of the built-in objectives
     flgpu_direction_fn direction = nullptr;   // K3 with the first trial evaluated inside (built-in objectives)
+    flgpu_fused_multi_fn fused_multi = nullptr;   // batched fused evaluation (built-in objectives)
 };
 void ref_adapter_init(RefAdapter &A, flgpu_ref_f_fn f, flgpu_ref_fd_fn fd, flgpu_ref_f_fd_fn f_fd, int dim,
                       flgpu_problem *prob);

@@ -52,6 +52,12 @@ public:
     virtual void fused_eval(int /*flags*/, double /*a*/, const double * /*x0*/, const double * /*p*/,
                             double * /*x_out*/, double * /*g_out*/) {}
 
+    // ---- batched fused evaluation (flgpu_fused_multi_fn): f and f'.p at x0 + steps[j]*p for j < count <= FLGPU_MULTI_MAX
+    // in ONE pass over x0 and p; f_j -> SL_AUX + 2j, (f'.p)_j -> SL_AUX + 2j + 1, each with the bits of fused_eval
+    virtual bool fused_multi_available() const { return false; }
+    virtual void fused_eval_multi(int /*count*/, const double * /*steps (host)*/, const double * /*x0*/,
+                                  const double * /*p*/) {}
+
     // ---- device-resident line search (flgpu_search_fn): the whole search in one cooperative kernel; the accepted
     // point / gradient land in xt / gt, the scalars in search_result() after the next fetch()
     virtual bool device_search_available() const { return false; }
@@ -85,12 +91,12 @@ public:
     virtual void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
                                  int recent) = 0;
 
-    // K3 with the first trial of the next search (a = 1) evaluated inside the kernel (flgpu_problem.direction): p is
-    // written, x1 + p is formed in registers only; f -> SL_F and (flags & FLGPU_WANT_GP) f'.p -> SL_GP with the bits a
-    // fused_eval(flags, 1.0, x1, p) would deliver.
+    // K3 with the first trials of the next search evaluated inside the kernel (flgpu_problem.direction): p is written,
+    // x1 + steps[j]*p (steps[0] = 1; FLGPU_MULTI_MAX steps) is formed in registers only; f, f'.p at step 0 -> SL_F, SL_GP
+    // and at step j >= 1 -> SL_AUX + 2j, SL_AUX + 2j + 1, each with the bits fused_eval(.., steps[j], x1, p) would deliver.
     virtual bool fused_direction_available() const { return false; }
     virtual void lbfgs_direction_probe(double * /*p*/, const double * /*g1*/, const double * /*x1*/, int /*k*/,
-                                       int /*recent*/, int /*flags*/) {}
+                                       int /*recent*/, int /*flags*/, const double * /*steps*/) {}
 
     // ---- CG (f90:352-393)
     virtual void cg_dots(const double *g1, const double *g0, const double *p) = 0;

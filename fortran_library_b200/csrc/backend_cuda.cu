@@ -335,7 +335,7 @@ CudaBackend::CudaBackend(const flgpu_problem &prob_, int64_t n_local, const flgp
     // reduction geometry: chunk size from the GLOBAL dimension (flgpu_reduce.cuh), one partial per chunk and accumulator
     ch = red::chunk_elems(ctx.n_global);
     nchunks = red::num_chunks(n, ch);
-    alloc_work(8);
+    alloc_work(12);
     FLGPU_CUDA_CHECK(cudaMallocHost((void **)&host_pinned, (NSLOTS + 16) * sizeof(double)));
     std::memset(host_pinned, 0, (NSLOTS + 16) * sizeof(double));
     const char *sync_mode = std::getenv("FLGPU_SYNC");
@@ -367,11 +367,11 @@ void CudaBackend::alloc_work(int rows) {
     work_rows = rows;
 }
 
-// chunk sums of rows [0, nrows) -> this rank's roots at out[row] (nrows <= 8)
+// chunk sums of rows [0, nrows) -> this rank's roots at out[row] (nrows <= 12)
 void CudaBackend::tree(int nrows, double *const *out) {
     k::TreeArgs a;
     a.w = work; a.nchunks = nchunks; a.lin_out = nullptr; a.dup_row = -1; a.dup_out = nullptr;
-    for (int i = 0; i < 8; i++) a.out[i] = i < nrows ? out[i] : nullptr;
+    for (int i = 0; i < 12; i++) a.out[i] = i < nrows ? out[i] : nullptr;
     const int nblk = (int)((nchunks + red::kBlockChunks - 1) / red::kBlockChunks);
     k::tree_kernel<<<dim3(nblk, nrows), k::kThreads, 0, stream>>>(a);
     launches++;
@@ -513,6 +513,13 @@ void CudaBackend::fused_eval(int flags, double a, const double *x0, const double
     callback_launches++;
 }
 
+void CudaBackend::fused_eval_multi(int count, const double *steps, const double *x0, const double *p) {
+    const int t = time_begin("callback:fused_probe_multi", 16.0 * n);   // one pass over x0 and p, whatever the count
+    prob.fused_multi(&ctx, count, steps, R + SL_AUX, x0, p, n);
+    time_end(t);
+    callback_launches++;
+}
+
 void CudaBackend::device_search(int policy, bool strong, bool fdwithf, double c1, double c2abs, double fx0, double phid0,
                                 double incr, double a, const double *x0, const double *p, double *xt, double *gt,
                                 bool no_store) {
@@ -632,7 +639,7 @@ void CudaBackend::lbfgs_update_dots_fused(double step, const double *x0, const d
 void CudaBackend::lbfgs_dots_tree() {
     k::TreeArgs a;
     a.w = work; a.nchunks = nchunks; a.lin_out = R + k::kResSlots; a.dup_row = d_GG(mem); a.dup_out = R + SL_GG;
-    for (int i = 0; i < 8; i++) a.out[i] = nullptr;
+    for (int i = 0; i < 12; i++) a.out[i] = nullptr;
     const int nblk = (int)((nchunks + red::kBlockChunks - 1) / red::kBlockChunks);
     k::tree_kernel<<<dim3(nblk, nd_of(mem)), k::kThreads, 0, stream>>>(a);
     launches++;
@@ -703,22 +710,26 @@ void CudaBackend::lbfgs_direction(double *p, double *xt, const double *g1, const
     time_end(t);
 }
 
+static_assert(k::kProbeSteps == FLGPU_MULTI_MAX, "the K3 probe fills one batch of the line search");
 // K3 launched by the objective with its probe (flgpu_problem.direction): reads g1, x1 and the 2k columns, writes p; the
-// chunk sums of g1.p, p.p, f(x1+p), f'(x1+p).p go to rows 0..3.
-void CudaBackend::lbfgs_direction_probe(double *p, const double *g1, const double *x1, int kk, int recent, int flags) {
+// chunk sums of g1.p, p.p go to rows 0, 1 and those of f, f'.p at x1 + steps[j]*p to rows 2+2j, 3+2j.  Step 0 (= 1, the
+// first trial) is delivered to SL_F / SL_GP like a probe; steps 1.. to the batch slots SL_AUX+2j, SL_AUX+2j+1.
+void CudaBackend::lbfgs_direction_probe(double *p, const double *g1, const double *x1, int kk, int recent, int flags,
+                                        const double *steps) {
     const int t = time_begin("k3_direction_probe", 8.0 * n * (2.0 * kk + 3.0));
     k::K3Launch L;
     k::K3Args &a = L.a;
     a.p = p; a.xt = nullptr; a.g1 = g1; a.x1 = x1; a.S = S; a.Y = Y; a.C = C; a.ld = ld; a.n = n; a.ch = ch;
     a.m = mem; a.k = kk; a.recent = recent; a.offset = ctx.offset; a.n_global = ctx.n_global; a.w = work;
+    for (int j = 0; j < k::kProbeSteps; j++) a.steps[j] = steps[j];
     L.grid = grid_for(2); L.stream = (void *)stream;
     flgpu_direction_args da;
     da.k3 = &L; da.k3_bytes = sizeof L; da.flags = flags;
     prob.direction(&ctx, &da, n);
     callback_launches++;
-    const bool wgp = (flags & FLGPU_WANT_GP) != 0;
-    double *out[4] = {R + SL_GP0, R + SL_PP, R + SL_F, R + SL_GP};
-    tree(wgp ? 4 : 3, out);
+    double *out[2 + 2 * k::kProbeSteps] = {R + SL_GP0, R + SL_PP, R + SL_F, R + SL_GP};
+    for (int j = 1; j < k::kProbeSteps; j++) { out[2 + 2 * j] = R + SL_AUX + 2 * j; out[3 + 2 * j] = R + SL_AUX + 2 * j + 1; }
+    tree(2 + 2 * k::kProbeSteps, out);
     time_end(t);
 }
 

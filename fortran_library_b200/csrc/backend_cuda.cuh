@@ -96,8 +96,11 @@ public:
     void lbfgs_update_dots(const double *x1, const double *x0, const double *g1, const double *g0,
                            int new_slot, int k_after) override;
     void lbfgs_solve(int k, int recent) override;
+    bool fused_multi_available() const override { return prob.fused_multi != nullptr && prob.fused != nullptr; }
+    void fused_eval_multi(int count, const double *steps, const double *x0, const double *p) override;
     bool fused_direction_available() const override { return prob.direction != nullptr && prob.fused != nullptr; }
-    void lbfgs_direction_probe(double *p, const double *g1, const double *x1, int k, int recent, int flags) override;
+    void lbfgs_direction_probe(double *p, const double *g1, const double *x1, int k, int recent, int flags,
+                               const double *steps) override;
     void lbfgs_direction(double *p, double *xt, const double *g1, const double *x1, int k,
                          int recent) override;
     void cg_dots(const double *g1, const double *g0, const double *p) override;

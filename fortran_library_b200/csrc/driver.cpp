@@ -69,10 +69,28 @@ struct Search : SearchCore<Search> {
     double fx_ = 0.0;
     bool f_pending = false;
     double slots[NSLOTS];
+
+    // ---- batched evaluation (flgpu_fused_multi_fn).  While the reference's searchers bracket, every next step is the
+    // previous one times or divided by `incr` (f90:1499-1501, 1488-1490, 1518, 1308-1310, 1325): when a trial continues
+    // such a walk -- or is the first of a search -- the next FLGPU_MULTI_MAX steps of the walk are evaluated in the same
+    // pass over x0 and p.  The state machine then finds the following trials already evaluated (same bits as separate
+    // probes) and takes its decisions without a launch or a host round trip; what it never asks for is dropped.
+    bool multi = false;
+    int nb = 0;                                   // steps of the current batch
+    double b_a[FLGPU_MULTI_MAX], b_f[FLGPU_MULTI_MAX], b_gp[FLGPU_MULTI_MAX];
+    bool b_inflight = false;                      // launched; values not on the host yet
+    int f_idx = -1, gp_idx = -1;                  // source of the pending f / of the current f'.p: batch entry, or -1 = slots
+    double prev_a = 0.0;                          // the step formed before the current one
+    bool have_prev = false;
+
     void sync() {
         B.fetch(slots);
         st.host_syncs++;
-        if (f_pending) { fx_ = slots[SL_F]; f_pending = false; }
+        if (b_inflight) {
+            for (int j = 0; j < nb; j++) { b_f[j] = slots[SL_AUX + 2 * j]; b_gp[j] = slots[SL_AUX + 2 * j + 1]; }
+            b_inflight = false;
+        }
+        if (f_pending) { fx_ = f_idx >= 0 ? b_f[f_idx] : slots[SL_F]; f_pending = false; }
     }
     double fx() { if (f_pending) sync(); return fx_; }
     void set_fx(double v) { f_pending = false; fx_ = v; }
@@ -87,26 +105,68 @@ struct Search : SearchCore<Search> {
     bool have_x = false, have_g = false;
 
     void form(double step) {                                                         // x=x0+a*p
-        if (fused) { a_x = step; have_x = true; }
+        if (fused) {
+            if (have_x) { prev_a = a_x; have_prev = true; }
+            a_x = step; have_x = true;
+        }
         else B.trial_x(xt, x0, p, step);
         trials++; st.n_trials++;
     }
+    // The batch entry that holds f and f'.p at a_x (launching a batch if a_x starts or continues a walk); -1: none
+    int batch_entry() {
+        if (!multi) return -1;
+        for (int j = 0; j < nb; j++) if (b_a[j] == a_x) return j;
+        int dir = 0;
+        if (!have_prev) dir = 1;                          // first trial: growth follows whenever it is acceptable
+        else if (a_x == prev_a * incr) dir = 1;
+        else if (a_x == prev_a / incr) dir = -1;
+        if (dir == 0) return -1;                          // a zoom step: nothing to predict
+        if (b_inflight || (f_pending && f_idx >= 0)) sync();   // the old batch is about to be overwritten
+        nb = FLGPU_MULTI_MAX;
+        b_a[0] = a_x;
+        for (int j = 1; j < nb; j++) b_a[j] = dir > 0 ? b_a[j - 1] * incr : b_a[j - 1] / incr;
+        B.fused_eval_multi(nb, b_a, x0, p);
+        b_inflight = true;
+        st.n_batched_passes++;
+        return 0;
+    }
+    void take_f(int j) {
+        f_idx = j;
+        if (j >= 0 && !b_inflight) { fx_ = b_f[j]; f_pending = false; }
+        else f_pending = true;
+    }
     void call_f() {
-        if (fused) B.fused_eval(FLGPU_WANT_F, a_x, x0, p, nullptr, nullptr); else B.eval_f(xt);
-        st.n_f++; f_pending = true;
+        if (fused) {
+            const int j = batch_entry();
+            if (j < 0) B.fused_eval(FLGPU_WANT_F, a_x, x0, p, nullptr, nullptr);
+            take_f(j);
+        } else { B.eval_f(xt); f_pending = true; }
+        st.n_f++;
     }
     void call_fd() {
-        if (fused) { B.fused_eval(FLGPU_WANT_GP, a_x, x0, p, nullptr, nullptr); a_g = a_x; have_g = true; }
+        if (fused) {
+            const int j = batch_entry();
+            if (j < 0) B.fused_eval(FLGPU_WANT_GP, a_x, x0, p, nullptr, nullptr);
+            gp_idx = j; a_g = a_x; have_g = true;
+        }
         else B.eval_g(xt, gt);
         st.n_fd++;
     }
     void call_ffd() {
-        if (fused) { B.fused_eval(FLGPU_WANT_F | FLGPU_WANT_GP, a_x, x0, p, nullptr, nullptr); a_g = a_x; have_g = true; }
-        else B.eval_fg(xt, gt);
-        st.n_f_fd++; f_pending = true;
+        if (fused) {
+            const int j = batch_entry();
+            if (j < 0) B.fused_eval(FLGPU_WANT_F | FLGPU_WANT_GP, a_x, x0, p, nullptr, nullptr);
+            take_f(j);
+            gp_idx = j; a_g = a_x; have_g = true;
+        } else { B.eval_fg(xt, gt); f_pending = true; }
+        st.n_f_fd++;
     }
     double slope() {                                                                 // dot_product(fdx,p)
         if (!fused) B.dot(gt, p, SL_GP);       // fused: f'.p was reduced by the probe that evaluated f'
+        if (fused && gp_idx >= 0) {            // ... or by the batch that did
+            if (b_inflight || f_pending) sync();
+            return b_gp[gp_idx];
+        }
         sync();
         return slots[SL_GP];
     }
@@ -114,7 +174,7 @@ struct Search : SearchCore<Search> {
     void adopt_pre() {
         trials++; set_fx(pre_f);
         a_x = a; have_x = true;
-        if (pre == 3) { a_g = a; have_g = true; }
+        if (pre == 3) { a_g = a; have_g = true; gp_idx = -1; }
     }
     // the accepted point is x0 + a_x*p and its gradient was evaluated there: the reference's searchers always end so
     bool can_defer() const { return fused && have_x && have_g && a_x == a_g; }
@@ -152,9 +212,12 @@ bool fast_uses_ffd(const Params &P, Backend &B) { return P.has_f_fd || (P.fused 
 // store (L-BFGS with flgpu_problem.update: K1 forms x0 + a*p and f' itself) and the result says `deferred`.
 struct SearchResult { double a, fx; int64_t trials; bool deferred; };
 
+// pre_steps / pre_vals (optional): the caller's chain evaluated the first FLGPU_MULTI_MAX steps of the bracketing walk
+// already (K3 with a probe): steps, and f, f'.p at each.
 SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool strong, bool fdwithf,
                          const double *x0, double *xt, double *gt, const double *p, double a,
-                         double fx0, double phid0, int pre, double pre_f, double pre_gp, bool defer_store = false) {
+                         double fx0, double phid0, int pre, double pre_f, double pre_gp, bool defer_store = false,
+                         const double *pre_steps = nullptr, const double *pre_vals = nullptr) {
     Search S(B, st);
     S.x0 = x0; S.xt = xt; S.gt = gt; S.p = p;
     S.c1 = P.c1; S.c2abs = P.c2 * std::fabs(phid0); S.fx0 = fx0; S.phid0 = phid0; S.incr = P.incr;
@@ -162,6 +225,14 @@ SearchResult line_search(Backend &B, flgpu_stats &st, const Params &P, bool stro
     S.pre = pre; S.pre_f = pre_f; S.pre_gp = pre_gp;
     S.fused = P.fused && B.fused_available();
     const bool fast = P.line_search == FLGPU_LS_FAST;
+    // the fast policy's steps come from interpolation, not from a walk: nothing to batch (FLGPU_FUSED_MULTI=0: one probe
+    // per trial -- the same bits, more passes; kept for comparison)
+    const char *fm = std::getenv("FLGPU_FUSED_MULTI");
+    S.multi = S.fused && !fast && B.fused_multi_available() && !(fm && fm[0] == '0');
+    if (S.multi && pre != 0 && pre_steps) {       // the walk's first steps are on the host already
+        S.nb = FLGPU_MULTI_MAX;
+        for (int j = 0; j < S.nb; j++) { S.b_a[j] = pre_steps[j]; S.b_f[j] = pre_vals[2 * j]; S.b_gp[j] = pre_vals[2 * j + 1]; }
+    }
     // FLGPU_LS_FAST evaluates f and f' together at every trial: one fused probe, else f_fd when the problem has one
     if (fast) fdwithf = fast_uses_ffd(P, B);
     S.fdwithf = fdwithf;
@@ -250,6 +321,12 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
         int64_t it = 0;                                                      // accepted steps so far
         const int64_t total = 1 + (int64_t)(mem - 1) + (int64_t)P.maxit;     // f90:448,472,511
         int pre = 0; double pre_f = 0, pre_gp = 0;
+        // the bracketing walk every main-loop search starts with (a = 1, then a = a*Increment: f90:607, 1499-1501), formed
+        // as the search will form it; K3 with a probe evaluates these steps while it writes p
+        double walk[FLGPU_MULTI_MAX], walk_vals[2 * FLGPU_MULTI_MAX];
+        walk[0] = 1.0;
+        for (int j = 1; j < FLGPU_MULTI_MAX; j++) walk[j] = walk[j - 1] * P.incr;
+        bool have_walk = false;
         for (;;) {
             // which searcher this outer iteration uses: never _fdwithf before the main loop (f90:448-498)
             const bool in_main = it >= mem;
@@ -257,7 +334,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             // the step after this search ends the run by count: no K1 follows, the search stores its point itself
             const bool defer = fuse_k1 && (it + 1 < total);
             SearchResult r = line_search(B, st, P, P.strong, fdwithf && P.strong, xc, xo, go, p, a, fnew,
-                                         phid0, pre, pre_f, pre_gp, defer);
+                                         phid0, pre, pre_f, pre_gp, defer, have_walk ? walk : nullptr, walk_vals);
             std::swap(xc, xo); std::swap(gc, go);       // accepted point becomes current; xo/go = xold/fdold
             a = r.a; fnew = r.fx;
             st.iterations = ++it;
@@ -286,7 +363,7 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
                     B.lbfgs_direction(p, nullptr, gc, xc, k_after, new_slot);
                 } else if (fuse_k3) {                                        // K3: new p and the first trial (a=1) in one pass
                     B.lbfgs_direction_probe(p, gc, xc, k_after, new_slot,
-                                            next_fdwithf ? (FLGPU_WANT_F | FLGPU_WANT_GP) : FLGPU_WANT_F);
+                                            next_fdwithf ? (FLGPU_WANT_F | FLGPU_WANT_GP) : FLGPU_WANT_F, walk);
                     st.n_trials++;
                     if (next_fdwithf) st.n_f_fd++; else st.n_f++;
                 } else if (fused) {                                          // K3: new p; first trial (a=1) probed
@@ -335,6 +412,13 @@ void run_lbfgs(Backend &B, const Params &P, double *x_user, int x_space, flgpu_s
             pre = dsearch ? 0 : ((next_fdwithf || next_both) ? 3 : 2);
             pre_f = slots[SL_F];
             pre_gp = slots[SL_GP];
+            have_walk = fuse_k3 && !dsearch;
+            if (have_walk) {
+                walk_vals[0] = slots[SL_F]; walk_vals[1] = slots[SL_GP];
+                for (int j = 1; j < FLGPU_MULTI_MAX; j++) {
+                    walk_vals[2 * j] = slots[SL_AUX + 2 * j]; walk_vals[2 * j + 1] = slots[SL_AUX + 2 * j + 1];
+                }
+            }
         }
     }
 finish:

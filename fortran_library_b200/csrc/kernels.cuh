@@ -27,12 +27,12 @@ namespace k {
 constexpr int kResSlots = NSLOTS;     // R[0..16) = slots, R[16..) = K1 dots
 
 // ------------------------------------------------------------------ tree: chunk sums -> this rank's root
-// grid (blocks of 4096 chunks, rows).  Row r of the partials is reduced to one value which goes to out[r] (rows <= 8),
+// grid (blocks of 4096 chunks, rows).  Row r of the partials is reduced to one value which goes to out[r] (rows <= 12),
 // or to lin_out[r] (K1's dots); one row may be delivered to a second place (K1: g.g is also a result slot).
 struct TreeArgs {
     Work w;
     int64_t nchunks;
-    double *out[8];
+    double *out[12];
     double *lin_out;
     int dup_row;
     double *dup_out;

@@ -88,7 +88,7 @@ k::Work scratch_work(cudaStream_t s, int64_t nchunks) { return scratch_for(s, nc
 void launch_tree(const k::Work &w, int64_t nchunks, int nrows, double *const *out, cudaStream_t s) {
     k::TreeArgs a;
     a.w = w; a.nchunks = nchunks; a.lin_out = nullptr; a.dup_row = -1; a.dup_out = nullptr;
-    for (int i = 0; i < 8; i++) a.out[i] = i < nrows ? out[i] : nullptr;
+    for (int i = 0; i < 12; i++) a.out[i] = i < nrows ? out[i] : nullptr;
     const int nblk = (int)((nchunks + red::kBlockChunks - 1) / red::kBlockChunks);
     k::tree_kernel<<<dim3(nblk, nrows), k::kThreads, 0, s>>>(a);
 }
@@ -154,6 +154,29 @@ __device__ __forceinline__ void objective_unit(const ObjIndex &ix, int64_t u, co
         if (NEED_G) { g.x = mul(d0, t0); g.y = mul(d1, t1); }
     }
 }
+// Several evaluations of the same unit (the batched probe, K3's probe): what does not depend on the point -- the diagonal
+// quadratic's factors d_i and the products 0.5 d_i -- is formed once per unit; every point then sees the operations of
+// objective_unit in the same order on the same values.
+template <int KIND>
+struct UnitInvariants {
+    double d0 = 0.0, d1 = 0.0, h0 = 0.0, h1 = 0.0;
+    __device__ __forceinline__ void prepare(const ObjIndex &ix, int64_t u) {
+        if (KIND == FLGPU_OBJ_DIAGQUAD) {
+            const double i = ix.offset_d + (double)(2 * u);
+            d0 = ix.coeff(i); d1 = ix.coeff(i + 1.0);
+            h0 = mul(0.5, d0); h1 = mul(0.5, d1);
+        }
+    }
+    __device__ __forceinline__ void eval(const ObjIndex &ix, int64_t u, const double2 x, double &fsum, double2 &g) const {
+        if (KIND == FLGPU_OBJ_DIAGQUAD) {
+            const double t0 = sub(x.x, 1.0), t1 = sub(x.y, 1.0);
+            fsum += mul(mul(h0, t0), t0); fsum += mul(mul(h1, t1), t1);
+            g.x = mul(d0, t0); g.y = mul(d1, t1);
+        } else {
+            objective_unit<KIND, true, true>(ix, u, x, fsum, g);
+        }
+    }
+};
 // the unpaired last element of an odd-length shard (local element index i)
 template <int KIND, bool WANT_F>
 __device__ __forceinline__ void objective_tail(const ObjIndex &ix, int64_t i, const double x, double &fsum, double &g) {
@@ -278,29 +301,40 @@ struct BuiltinSrc {
     }
 };
 
-// K3 probe for the built-in objectives (flgpu_problem.direction, include/flgpu_k3.cuh): f and f'.p at the a = 1 trial
-// point K3 forms in registers -- objective_unit on the same point in the same per-thread unit order as
-// objective_chunk, hence the chunk sums (and everything above them) of the separate fused evaluation.
+// K3 probe for the built-in objectives (flgpu_problem.direction, include/flgpu_k3.cuh): f and f'.p at the first trial
+// points of the next search, formed in registers from the x1 and p K3 holds -- objective_unit on the same points in the
+// same per-thread unit order as objective_chunk, hence the chunk sums (and everything above them) of separate fused
+// evaluations.
 template <int KIND>
 struct BuiltinProbe {
     static constexpr bool kOn = true;
+    static constexpr int kSteps = kProbeSteps;
     const double *tables;
     double scale;
-    int want_gp;
     ObjIndex ix;
     __device__ void init(const K3Args &a, int nthreads) {
         __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
         ix = load_tables<KIND>(a.offset, a.n_global, scale, tables, tab, nthreads);
     }
-    __device__ __forceinline__ void unit(int64_t u, const double2 xt, const double2 pv, double &fsum, double &gpsum) const {
-        double2 g = make_double2(0.0, 0.0);
-        objective_unit<KIND, true, true>(ix, u, xt, fsum, g);
-        if (want_gp) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
+    __device__ __forceinline__ void unit(const K3Args &a, int64_t u, const double2 x1, const double2 pv, double *acc) const {
+        UnitInvariants<KIND> inv;
+        inv.prepare(ix, u);
+#pragma unroll
+        for (int j = 0; j < kSteps; j++) {
+            double2 x, g = make_double2(0.0, 0.0);
+            x.x = add(x1.x, mul(a.steps[j], pv.x));
+            x.y = add(x1.y, mul(a.steps[j], pv.y));
+            inv.eval(ix, u, x, acc[2 * j], g);
+            acc[2 * j + 1] = fma(g.y, pv.y, fma(g.x, pv.x, acc[2 * j + 1]));
+        }
     }
-    __device__ __forceinline__ void tail(int64_t i, const double xt, const double pv, double &fsum, double &gpsum) const {
-        double g = 0.0;
-        objective_tail<KIND, true>(ix, i, xt, fsum, g);
-        if (want_gp) gpsum = fma(g, pv, gpsum);
+    __device__ __forceinline__ void tail(const K3Args &a, int64_t i, const double x1, const double pv, double *acc) const {
+#pragma unroll
+        for (int j = 0; j < kSteps; j++) {
+            double g = 0.0;
+            objective_tail<KIND, true>(ix, i, add(x1, mul(a.steps[j], pv)), acc[2 * j], g);
+            acc[2 * j + 1] = fma(g, pv, acc[2 * j + 1]);
+        }
     }
 };
 
@@ -333,6 +367,74 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(ObjArgs a) {
             double *const o[1] = {a.out[0]};
             red::finish_in_kernel<1>(a.w.partials, a.w.stride, C.nchunks, a.w.tickets, o);
         }
+    }
+}
+
+// ------------------------------------------------------------------ batched fused evaluation (flgpu_fused_multi_fn)
+// f and f'.p at x0 + steps[j]*p for J steps in ONE pass over x0 and p: the traffic of one probe, J times its (few)
+// flops.  Per step the arithmetic and the accumulation order are objective_chunk's (thread t takes the chunk's units
+// t, t+256, ... in order; f terms added in element order, f'.p by FMA), so every pair of sums carries the bits of a
+// separate objective_kernel<KIND, FUSED, F, GP> launch with a = steps[j].  Chunk sums: f_j -> row 2j, (f'.p)_j -> row 2j+1.
+struct MultiArgs {
+    const double *x, *p;
+    double steps[FLGPU_MULTI_MAX];
+    int64_t n, offset, n_global, ch;
+    double scale;
+    const double *tables;
+    Work w;
+    double *out;        // in-kernel finish (at most 4096 chunks): out[0 .. 2J); null: tree_kernel follows
+};
+
+template <int KIND, int J>
+__global__ void __launch_bounds__(kThreads, 3) objective_multi_kernel(MultiArgs a) {
+    __shared__ double tab[KIND == FLGPU_OBJ_DIAGQUAD ? 768 : 1];
+    const ObjIndex ix = load_tables<KIND>(a.offset, a.n_global, a.scale, a.tables, tab, kThreads);
+    const Chunks C(a.n, a.ch);
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < C.nchunks; c += gridDim.x) {
+        double acc[2 * J];
+#pragma unroll
+        for (int i = 0; i < 2 * J; i++) acc[i] = 0.0;
+        auto unit = [&](int64_t u, const double2 x0v, const double2 pv) {
+            UnitInvariants<KIND> inv;
+            inv.prepare(ix, u);
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                double2 x, g = make_double2(0.0, 0.0);
+                x.x = add(x0v.x, mul(a.steps[j], pv.x));
+                x.y = add(x0v.y, mul(a.steps[j], pv.y));
+                inv.eval(ix, u, x, acc[2 * j], g);
+                acc[2 * j + 1] = fma(g.y, pv.y, fma(g.x, pv.x, acc[2 * j + 1]));
+            }
+        };
+        const int64_t hi = C.hi(c);
+        int64_t u = C.lo(c) + threadIdx.x;
+        for (; u + 3 * kThreads < hi; u += 4 * kThreads) {       // four units per trip, all eight loads issued first
+            const double2 x0v = ld2(a.x, u), x1v = ld2(a.x, u + kThreads), x2v = ld2(a.x, u + 2 * kThreads),
+                          x3v = ld2(a.x, u + 3 * kThreads);
+            const double2 p0v = ld2(a.p, u), p1v = ld2(a.p, u + kThreads), p2v = ld2(a.p, u + 2 * kThreads),
+                          p3v = ld2(a.p, u + 3 * kThreads);
+            unit(u, x0v, p0v); unit(u + kThreads, x1v, p1v); unit(u + 2 * kThreads, x2v, p2v); unit(u + 3 * kThreads, x3v, p3v);
+        }
+        for (; u < hi; u += kThreads) unit(u, ld2(a.x, u), ld2(a.p, u));
+        if (C.tail_here(c) && threadIdx.x == 0) {
+            const int64_t i = a.n - 1;
+            const double x0 = a.x[i], pv = a.p[i];
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                double g = 0.0;
+                objective_tail<KIND, true>(ix, i, add(x0, mul(a.steps[j], pv)), acc[2 * j], g);
+                acc[2 * j + 1] = fma(g, pv, acc[2 * j + 1]);
+            }
+        }
+        red::chunk_flush<2 * J>(acc, parity, a.w.partials, a.w.stride, c);
+    }
+    if (a.out) {
+        double *o[2 * J];
+#pragma unroll
+        for (int i = 0; i < 2 * J; i++) o[i] = a.out + i;
+        double *const(&oc)[2 * J] = o;
+        red::finish_in_kernel<2 * J>(a.w.partials, a.w.stride, C.nchunks, a.w.tickets, oc);
     }
 }
 
@@ -580,6 +682,38 @@ void launch_objective(int kind, bool fused, int flags, double *f_dev, double *gp
     if ((wf || wgp) && !in_kernel) launch_tree(sc.work, nchunks, wf && wgp ? 2 : 1, out, s);
 }
 
+// batched fused evaluation: out_dev[2j], out_dev[2j+1] = this rank's roots of f and f'.p at x0 + steps[j]*p
+void launch_objective_multi(int kind, int count, const double *steps, double *out_dev, const double *x_dev,
+                            const double *p_dev, int64_t n, int64_t offset, int64_t n_global, cudaStream_t s) {
+    constexpr int J = FLGPU_MULTI_MAX;
+    if (count < 1 || count > J) fatal("built-in objective: batched evaluation of 1 to 4 steps");
+    require_aligned16(x_dev, "objective: x"); require_aligned16(p_dev, "objective: p");
+    if (n_global < n) n_global = n;
+    const int64_t ch = red::chunk_elems(n_global), nchunks = red::num_chunks(n, ch);
+    Scratch &sc = scratch_for(s, nchunks);
+    k::MultiArgs a;
+    a.x = x_dev; a.p = p_dev;
+    for (int j = 0; j < J; j++) a.steps[j] = steps[j < count ? j : count - 1];   // unused lanes repeat the last step
+    a.n = n; a.offset = offset; a.n_global = n_global; a.ch = ch;
+    a.scale = n_global > 1 ? 16777216.0 / (double)(n_global - 1) : 0.0;
+    a.tables = sc.tables; a.w = sc.work;
+    const bool in_kernel = nchunks <= red::kBlockChunks;
+    a.out = in_kernel ? out_dev : nullptr;
+    const int grid = chunk_grid(nchunks, 3);     // = resident CTAs per SM (__launch_bounds__(256, 3)): one full wave
+    switch (kind) {
+    case FLGPU_OBJ_QUARTIC: k::objective_multi_kernel<FLGPU_OBJ_QUARTIC, J><<<grid, k::kThreads, 0, s>>>(a); break;
+    case FLGPU_OBJ_ROSENBROCK: k::objective_multi_kernel<FLGPU_OBJ_ROSENBROCK, J><<<grid, k::kThreads, 0, s>>>(a); break;
+    case FLGPU_OBJ_DIAGQUAD: k::objective_multi_kernel<FLGPU_OBJ_DIAGQUAD, J><<<grid, k::kThreads, 0, s>>>(a); break;
+    case FLGPU_OBJ_QUARTIC_SHIFTED: k::objective_multi_kernel<FLGPU_OBJ_QUARTIC_SHIFTED, J><<<grid, k::kThreads, 0, s>>>(a); break;
+    default: fatal("unknown built-in objective");
+    }
+    if (!in_kernel) {
+        double *out[2 * J];
+        for (int i = 0; i < 2 * J; i++) out[i] = i < 2 * count ? out_dev + i : nullptr;
+        launch_tree(sc.work, nchunks, 2 * count, out, s);
+    }
+}
+
 // 64-bit device-callback flavour
 template <int KIND>
 static void dev_f(const flgpu_eval_ctx *c, double *f, const double *x, int64_t n) {
@@ -601,6 +735,12 @@ static void dev_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp,
                       const double *x0, const double *p, double a, int64_t n) {
     launch_objective(KIND, true, flags, f, gp, x_out, g_out, x0, p, a, n, c->offset, c->n_global,
                      (cudaStream_t)c->stream);
+}
+
+template <int KIND>
+static void dev_fused_multi(const flgpu_eval_ctx *c, int count, const double *steps, double *out_dev, const double *x0,
+                            const double *p, int64_t n) {
+    launch_objective_multi(KIND, count, steps, out_dev, x0, p, n, c->offset, c->n_global, (cudaStream_t)c->stream);
 }
 
 // flgpu_problem.update: the first K1 pass with the accepted point formed in the kernel
@@ -626,7 +766,6 @@ static void dev_direction(const flgpu_eval_ctx *c, const flgpu_direction_args *A
     k::BuiltinProbe<KIND> probe;
     probe.tables = sc.tables;
     probe.scale = L.a.n_global > 1 ? 16777216.0 / (double)(L.a.n_global - 1) : 0.0;
-    probe.want_gp = (A->flags & FLGPU_WANT_GP) ? 1 : 0;
     k::launch_k3_probe(L, probe);
 }
 
@@ -699,10 +838,10 @@ using namespace flgpu;
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {
-    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<0>; out->direction = dev_direction<0>; return 0;
-    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<1>; out->direction = dev_direction<1>; return 0;
-    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<2>; out->direction = dev_direction<2>; return 0;
-    case FLGPU_OBJ_QUARTIC_SHIFTED: out->f = dev_f<3>; out->fd = dev_fd<3>; out->f_fd = dev_ffd<3>; out->fused = dev_fused<3>; out->search = dev_search<3>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<3>; out->direction = dev_direction<3>; return 0;
+    case FLGPU_OBJ_QUARTIC: out->f = dev_f<0>; out->fd = dev_fd<0>; out->f_fd = dev_ffd<0>; out->fused = dev_fused<0>; out->search = dev_search<0>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<0>; out->direction = dev_direction<0>; out->fused_multi = dev_fused_multi<0>; return 0;
+    case FLGPU_OBJ_ROSENBROCK: out->f = dev_f<1>; out->fd = dev_fd<1>; out->f_fd = dev_ffd<1>; out->fused = dev_fused<1>; out->search = dev_search<1>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<1>; out->direction = dev_direction<1>; out->fused_multi = dev_fused_multi<1>; return 0;
+    case FLGPU_OBJ_DIAGQUAD: out->f = dev_f<2>; out->fd = dev_fd<2>; out->f_fd = dev_ffd<2>; out->fused = dev_fused<2>; out->search = dev_search<2>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<2>; out->direction = dev_direction<2>; out->fused_multi = dev_fused_multi<2>; return 0;
+    case FLGPU_OBJ_QUARTIC_SHIFTED: out->f = dev_f<3>; out->fd = dev_fd<3>; out->f_fd = dev_ffd<3>; out->fused = dev_fused<3>; out->search = dev_search<3>; out->search_caps = FLGPU_SEARCH_ROW_SHARDS; out->update = dev_update<3>; out->direction = dev_direction<3>; out->fused_multi = dev_fused_multi<3>; return 0;
     }
     return 1;
 }
@@ -714,6 +853,13 @@ flgpu_fused_fn builtin_fused_for(flgpu_ref_f_fn f) {
     if (f == ref_f<1>) return dev_fused<1>;
     if (f == ref_f<2>) return dev_fused<2>;
     if (f == ref_f<3>) return dev_fused<3>;
+    return nullptr;
+}
+flgpu_fused_multi_fn builtin_fused_multi_for(flgpu_ref_f_fn f) {
+    if (f == ref_f<0>) return dev_fused_multi<0>;
+    if (f == ref_f<1>) return dev_fused_multi<1>;
+    if (f == ref_f<2>) return dev_fused_multi<2>;
+    if (f == ref_f<3>) return dev_fused_multi<3>;
     return nullptr;
 }
 flgpu_direction_fn builtin_direction_for(flgpu_ref_f_fn f) {

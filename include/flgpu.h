@@ -118,21 +118,36 @@ typedef struct flgpu_update_args {
 } flgpu_update_args;
 typedef void (*flgpu_update_fn)(const flgpu_eval_ctx *ctx, const flgpu_update_args *args, int64_t n_local);
 
-/* Optional FUSED FIRST TRIAL (an extension; L-BFGS with a fused line search only).  Every line search of the L-BFGS main
- * loop starts at a = 1 (f90:607), i.e. at x + p with the direction p that Before() has just formed (f90:589-607).  With
- * this callback the library's K3 kernel, instantiated by the objective with a probe (include/flgpu_k3.cuh), evaluates
- * that trial while it writes p: it reads x as well, forms x + 1*p in registers and reduces f and f'.p with the chunk
- * order of the fused evaluation -- the same bits as a separate flgpu_fused_fn call with a = 1, for n instead of 2n doubles
- * and one launch less per iteration.  flags = FLGPU_WANT_F or FLGPU_WANT_F | FLGPU_WANT_GP (the reference's f / f_fd call
- * at the first trial).  The callback launches exactly that pass on ctx->stream:
+/* Optional FUSED FIRST TRIALS (an extension; L-BFGS with a fused line search only).  Every line search of the L-BFGS main
+ * loop starts at a = 1 (f90:607), i.e. at x + p with the direction p that Before() has just formed (f90:589-607), and while
+ * the slope stays negative it walks on to Increment, Increment^2, ... (f90:1499-1501).  With this callback the library's K3
+ * kernel, instantiated by the objective with a probe (include/flgpu_k3.cuh), evaluates the first FOUR steps of that walk
+ * while it writes p: it reads x as well, forms x + a*p in registers and reduces f and f'.p at each step with the chunk order
+ * of the fused evaluation -- the same bits as separate flgpu_fused_fn calls, for n doubles of extra traffic in all and no
+ * launch.  The search consumes the values in the reference's order with the reference's counts; what it does not reach is
+ * dropped.  The callback launches exactly that pass on ctx->stream:
  *     flgpu::k::launch_k3_probe(*(const flgpu::k::K3Launch *)args->k3, MyProbe{...});
  * (libflgpu's built-in objectives and include/flgpu_objective.cuh provide it). */
 typedef struct flgpu_direction_args {
     const void *k3;     /* flgpu::k::K3Launch prepared by the library: vectors, coefficients, ring buffers, geometry */
     size_t k3_bytes;    /* sizeof(flgpu::k::K3Launch) the library was built with (callbacks check it) */
-    int flags;          /* FLGPU_WANT_F [| FLGPU_WANT_GP] */
+    int flags;          /* what the reference evaluates at the first trial (FLGPU_WANT_F [| FLGPU_WANT_GP]); informational:
+                           the probe always reduces both sums at every step */
 } flgpu_direction_args;
 typedef void (*flgpu_direction_fn)(const flgpu_eval_ctx *ctx, const flgpu_direction_args *args, int64_t n_local);
+
+/* Optional BATCHED fused evaluation (an extension; needs `fused`).  While the reference's searchers bracket, the next
+ * trial steps are known in advance: a, a*Increment, a*Increment^2, ... (f90:1499-1501, 1308-1310) or a/Increment, ...
+ * (f90:1488-1490, 1518, 1325).  One pass over x0 and p can evaluate several of them -- the traffic of ONE trial, a few more
+ * flops per element -- and the host then takes its decisions from values it already holds, in the reference's order, with
+ * the reference's counts; evaluations the search never reaches are dropped.  For j < count <= FLGPU_MULTI_MAX:
+ *     out_dev[2j]   = this rank's partial sum of f (x0 + steps[j]*p)
+ *     out_dev[2j+1] = this rank's partial sum of f'(x0 + steps[j]*p) . p
+ * each with exactly the bits a flgpu_fused_fn call with a = steps[j] delivers (same per-element roundings, same
+ * summation order).  `steps` is a HOST array (pass it to the kernel by value).  Enqueue on ctx->stream, do not synchronise. */
+#define FLGPU_MULTI_MAX 4
+typedef void (*flgpu_fused_multi_fn)(const flgpu_eval_ctx *ctx, int count, const double *steps, double *out_dev,
+                                     const double *x0_dev, const double *p_dev, int64_t n_local);
 
 typedef struct flgpu_problem {
     flgpu_f_fn f;       /* required */
@@ -144,6 +159,7 @@ typedef struct flgpu_problem {
     int search_caps;        /* FLGPU_SEARCH_ROW_SHARDS if `search` handles flgpu_search_args.comm != NULL; else 0 */
     flgpu_update_fn update; /* optional, needs `fused` (NULL = the search stores the accepted point, K1 reads it back) */
     flgpu_direction_fn direction; /* optional, needs `fused` (NULL = the first trial of a search is a flgpu_fused_fn call) */
+    flgpu_fused_multi_fn fused_multi; /* optional, needs `fused` (NULL = one flgpu_fused_fn call per trial) */
 } flgpu_problem;
 
 /* ------------------------------------------------------------------ options / results */
@@ -233,6 +249,7 @@ typedef struct flgpu_stats {
     int64_t host_syncs;
     double f;             /* final objective */
     double gnorm2;        /* final |f'|^2 */
+    int64_t n_batched_passes; /* flgpu_fused_multi_fn launches: passes that evaluated up to FLGPU_MULTI_MAX trials at once */
 } flgpu_stats;
 
 void flgpu_options_default(flgpu_options *o, int for_cg);

@@ -3,9 +3,10 @@
 //
 // libflgpu instantiates it with NoProbe (p only; with plain callbacks also the trial point x1 + p).  An objective that
 // can evaluate f and f' inside a kernel instantiates it with a probe (flgpu_problem.direction): K3 then also loads x1,
-// forms x1 + p in registers (1*p is exact, so this IS x0 + a*p with a = 1: the bits of the fused evaluation), and
-// reduces f(x1+p) and f'(x1+p).p in the chunk order every other kernel uses -- the same bits the separate probe launch
-// would deliver, for 1n instead of 2n doubles and one launch less per iteration.  libflgpu's built-in objectives do this
+// forms x1 + a*p in registers for the first steps of the search's bracketing walk -- a = 1 (1*p is exact: this IS the
+// fused evaluation's x0 + a*p), Increment, Increment^2, Increment^3 (f90:1499-1501) -- and reduces f and f'.p at each in
+// the chunk order every other kernel uses: the bits separate probe launches would deliver, for 1n instead of 2n doubles
+// per evaluated trial and no launch at all.  libflgpu's built-in objectives do this
 // in csrc/objectives.cu, include/flgpu_objective.cuh does it for user functors.
 #pragma once
 #include <cstdint>
@@ -23,22 +24,27 @@ namespace k {
 // ------------------------------------------------------------------ K3: direction + first trial point
 // p = -( gamma (g - sum_newest..oldest alpha_i y_i) + sum_oldest..newest e_i s_i )   (f90:589-607)
 // xt = x1 + p (the a=1 trial of the next line search, f90:607+1482); chunk sums of g.p -> row 0, p.p -> row 1.
-// With a probe: x1 is read, rows 2 and 3 of the chunk sums carry f(x1+p) and f'(x1+p).p.
+// With a probe of S steps: x1 is read, rows 2+2j and 3+2j of the chunk sums carry f and f'.p at x1 + steps[j]*p.
+constexpr int kProbeSteps = 4;
 struct K3Args {
     double *p, *xt;
     const double *g1, *x1, *S, *Y, *C;
     int64_t ld, n, ch;
     int m, k, recent;
     int64_t offset, n_global;   // probe only (index-dependent objectives)
+    double steps[kProbeSteps];  // probe only: 1, Increment, Increment^2, ... as the host will form them
     Work w;
 };
 
 // No first-trial evaluation: what libflgpu launches on its own.
+// A probe accumulates, for j < kSteps, f(x + steps[j]*p) into acc[2j] and f'(x + steps[j]*p).p into acc[2j+1] (x + a*p:
+// multiply, then add) -- per unit, in the order the fused evaluation uses.
 struct NoProbe {
     static constexpr bool kOn = false;
+    static constexpr int kSteps = 0;
     __device__ void init(const K3Args &, int) {}
-    __device__ __forceinline__ void unit(int64_t, double2, double2, double &, double &) const {}
-    __device__ __forceinline__ void tail(int64_t, double, double, double &, double &) const {}
+    __device__ __forceinline__ void unit(const K3Args &, int64_t, double2, double2, double *) const {}
+    __device__ __forceinline__ void tail(const K3Args &, int64_t, double, double, double *) const {}
 };
 
 // The 2k column operations are one list in the reference's order -- y_newest..y_oldest (q -= alpha y),
@@ -75,7 +81,7 @@ __device__ __forceinline__ void k3_tail(const K3Args &a, const K3Tables &T, cons
     if (a.xt) a.xt[i] = a.x1[i] + pv;
     acc[0] = fma(g, pv, acc[0]);
     acc[1] = fma(pv, pv, acc[1]);
-    if (Probe::kOn) probe.tail(i, __dadd_rn(a.x1[i], pv), pv, acc[NACC - 2], acc[NACC - 1]);
+    if (Probe::kOn) probe.tail(a, i, a.x1[i], pv, &acc[2]);
 }
 
 // ---- K3, register version (FLGPU_K3=regs; the r01 kernel on the chunked reduction): the column list is walked in
@@ -180,7 +186,7 @@ static __global__ void __launch_bounds__(kThreads + 32, MINB) k3_direction_tma_k
     double2 *ring = reinterpret_cast<double2 *>(dyn);            // [NST][P][kThreads]
     __shared__ K3Tables T;
     __shared__ __align__(8) uint64_t full[NST], empty[NST];
-    constexpr int NACC = Probe::kOn ? 4 : 2;                     // g.p, p.p (, f, f'.p at the first trial point)
+    constexpr int NACC = 2 + 2 * Probe::kSteps;                  // g.p, p.p (, f and f'.p at each probed step)
     probe.init(a, kThreads + 32);
     k3_build_tables(a, T, kThreads + 32);
     if (threadIdx.x == 0) {
@@ -265,9 +271,8 @@ static __global__ void __launch_bounds__(kThreads + 32, MINB) k3_direction_tma_k
                 if (a.xt) st2(a.xt, u, make_double2(x.x + pv.x, x.y + pv.y));
                 acc[0] = fma(g.y, pv.y, fma(g.x, pv.x, acc[0]));
                 acc[1] = fma(pv.y, pv.y, fma(pv.x, pv.x, acc[1]));
-                // the a = 1 trial point of the next search: x1 + 1*p, the roundings of the fused evaluation
-                if (Probe::kOn)
-                    probe.unit(u, make_double2(__dadd_rn(x.x, pv.x), __dadd_rn(x.y, pv.y)), pv, acc[NACC - 2], acc[NACC - 1]);
+                // the first trial points of the next search, x1 + a*p with the roundings of the fused evaluation
+                if (Probe::kOn) probe.unit(a, u, x, pv, &acc[2]);
             }
         }
         if (C.tail_here(chunk) && threadIdx.x == 0) k3_tail(a, T, probe, acc);

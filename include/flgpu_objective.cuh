@@ -115,6 +115,64 @@ __global__ void __launch_bounds__(kThreads, 4) objective_kernel(Obj obj, Args a)
     }
 }
 
+// ---- batched fused evaluation (flgpu_fused_multi_fn): f and f'.p at x0 + steps[j]*p for FLGPU_MULTI_MAX steps in one pass
+// over x0 and p.  Per step: chunk<Obj, true, true, true, false, false>'s arithmetic and accumulation order, hence its bits.
+struct MultiArgs {
+    const double *x, *p;
+    double steps[FLGPU_MULTI_MAX];
+    int64_t n, offset, ch;
+    double *partials;        // chunk sums: f_j -> row 2j, (f'.p)_j -> row 2j+1
+    int64_t stride;
+};
+template <class Obj>
+__global__ void __launch_bounds__(kThreads, 3) objective_multi_kernel(Obj obj, MultiArgs a) {
+    constexpr int J = FLGPU_MULTI_MAX;
+    const int64_t nchunks = red::num_chunks(a.n, a.ch);
+    const int64_t nu = a.n >> 1, cu = a.ch >> 1;
+    int parity = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        double acc[2 * J];
+#pragma unroll
+        for (int i = 0; i < 2 * J; i++) acc[i] = 0.0;
+        const int64_t lo = c * cu, hi = (lo + cu < nu) ? lo + cu : nu;
+        for (int64_t u = lo + threadIdx.x; u < hi; u += kThreads) {
+            const double2 x0 = __ldg(reinterpret_cast<const double2 *>(a.x) + u);
+            const double2 pv = __ldg(reinterpret_cast<const double2 *>(a.p) + u);
+            const int64_t i = a.offset + 2 * u;
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                const double xa = __dadd_rn(x0.x, __dmul_rn(a.steps[j], pv.x)), xb = __dadd_rn(x0.y, __dmul_rn(a.steps[j], pv.y));
+                double2 g;
+                if constexpr (Obj::WIDTH == 2) {
+                    double f = 0.0;
+                    obj.eval2(i, xa, xb, f, g.x, g.y);
+                    acc[2 * j] += f;
+                } else {
+                    double f0 = 0.0, f1 = 0.0;
+                    obj.eval(i, xa, f0, g.x);
+                    obj.eval(i + 1, xb, f1, g.y);
+                    acc[2 * j] += f0; acc[2 * j] += f1;
+                }
+                acc[2 * j + 1] = fma(g.y, pv.y, fma(g.x, pv.x, acc[2 * j + 1]));
+            }
+        }
+        if ((a.n & 1) && c == nchunks - 1 && threadIdx.x == 0) {
+            const int64_t k = a.n - 1;
+            const double x0 = a.x[k], pv = a.p[k];
+#pragma unroll
+            for (int j = 0; j < J; j++) {
+                double f = 0.0, g = 0.0;
+                const double x = __dadd_rn(x0, __dmul_rn(a.steps[j], pv));
+                if constexpr (Obj::WIDTH == 2) obj.eval_tail(a.offset + k, x, f, g);
+                else obj.eval(a.offset + k, x, f, g);
+                acc[2 * j] += f;
+                acc[2 * j + 1] = fma(g, pv, acc[2 * j + 1]);
+            }
+        }
+        red::chunk_flush<2 * J>(acc, parity, a.partials, a.stride, c);
+    }
+}
+
 // ---- device-resident line search (flgpu_search_fn) for functor objectives: the whole Wolfe / Strong-Wolfe search in
 // one cooperative kernel.  Every thread runs the same SearchCore state machine (flgpu_search_core.hpp, the source the
 // host driver compiles) on the same values; an evaluation = this block's chunks + one grid barrier + the tree over the
@@ -251,31 +309,40 @@ struct FunctorSrc {
 template <class Obj>
 struct FunctorProbe {
     static constexpr bool kOn = true;
+    static constexpr int kSteps = flgpu::k::kProbeSteps;
     Obj obj;
     int64_t offset;
-    int want_gp;
     __device__ void init(const flgpu::k::K3Args &, int) {}
-    __device__ __forceinline__ void unit(int64_t u, const double2 xt, const double2 pv, double &fsum, double &gpsum) const {
+    __device__ __forceinline__ void unit(const flgpu::k::K3Args &a, int64_t u, const double2 x1, const double2 pv,
+                                         double *acc) const {
         const int64_t i = offset + 2 * u;
-        double2 g;
-        if constexpr (Obj::WIDTH == 2) {
-            double f = 0.0;
-            obj.eval2(i, xt.x, xt.y, f, g.x, g.y);
-            fsum += f;
-        } else {
-            double f0 = 0.0, f1 = 0.0;
-            obj.eval(i, xt.x, f0, g.x);
-            obj.eval(i + 1, xt.y, f1, g.y);
-            fsum += f0; fsum += f1;
+#pragma unroll
+        for (int j = 0; j < kSteps; j++) {
+            const double xa = __dadd_rn(x1.x, __dmul_rn(a.steps[j], pv.x)), xb = __dadd_rn(x1.y, __dmul_rn(a.steps[j], pv.y));
+            double2 g;
+            if constexpr (Obj::WIDTH == 2) {
+                double f = 0.0;
+                obj.eval2(i, xa, xb, f, g.x, g.y);
+                acc[2 * j] += f;
+            } else {
+                double f0 = 0.0, f1 = 0.0;
+                obj.eval(i, xa, f0, g.x);
+                obj.eval(i + 1, xb, f1, g.y);
+                acc[2 * j] += f0; acc[2 * j] += f1;
+            }
+            acc[2 * j + 1] = fma(g.y, pv.y, fma(g.x, pv.x, acc[2 * j + 1]));
         }
-        if (want_gp) gpsum = fma(g.y, pv.y, fma(g.x, pv.x, gpsum));
     }
-    __device__ __forceinline__ void tail(int64_t k, const double xt, const double pv, double &fsum, double &gpsum) const {
-        double f = 0.0, g = 0.0;
-        if constexpr (Obj::WIDTH == 2) obj.eval_tail(offset + k, xt, f, g);
-        else obj.eval(offset + k, xt, f, g);
-        fsum += f;
-        if (want_gp) gpsum = fma(g, pv, gpsum);
+    __device__ __forceinline__ void tail(const flgpu::k::K3Args &a, int64_t k, const double x1, const double pv, double *acc) const {
+#pragma unroll
+        for (int j = 0; j < kSteps; j++) {
+            double f = 0.0, g = 0.0;
+            const double x = __dadd_rn(x1, __dmul_rn(a.steps[j], pv));
+            if constexpr (Obj::WIDTH == 2) obj.eval_tail(offset + k, x, f, g);
+            else obj.eval(offset + k, x, f, g);
+            acc[2 * j] += f;
+            acc[2 * j + 1] = fma(g, pv, acc[2 * j + 1]);
+        }
     }
 };
 
@@ -302,11 +369,11 @@ struct Callbacks {
             flgpu_reduce_tree(ctx->stream, nchunks, (F && GP) ? 2 : 1, out);
         }
     }
-    static int grid_for(int64_t nchunks) {
+    static int grid_for(int64_t nchunks, int per_sm = 4) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        int64_t grid = (int64_t)sms * 4;                                              // one full wave of resident CTAs
+        int64_t grid = (int64_t)sms * per_sm;                                         // one full wave of resident CTAs
         if (nchunks < grid) grid = nchunks < 1 ? 1 : nchunks;
         return (int)grid;
     }
@@ -342,12 +409,26 @@ struct Callbacks {
         FunctorSrc<Obj> src{*(const Obj *)ctx->user};
         flgpu::k::launch_k1_pass(*(const flgpu::k::K1Launch *)A->k1, src);
     }
+    static void fused_multi(const flgpu_eval_ctx *ctx, int count, const double *steps, double *out_dev, const double *x0,
+                            const double *p, int64_t n) {
+        if (count < 1 || count > FLGPU_MULTI_MAX) { std::fprintf(stderr, "flgpu_obj: batched evaluation of 1 to 4 steps\n"); std::abort(); }
+        Args G;
+        int64_t nchunks = 1;
+        geometry(ctx, n, G, nchunks);
+        MultiArgs A;
+        A.x = x0; A.p = p; A.n = n; A.offset = G.offset; A.ch = G.ch; A.partials = G.partials; A.stride = G.stride;
+        for (int j = 0; j < FLGPU_MULTI_MAX; j++) A.steps[j] = steps[j < count ? j : count - 1];
+        objective_multi_kernel<Obj><<<grid_for(nchunks, 3), kThreads, 0, (cudaStream_t)ctx->stream>>>(*(const Obj *)ctx->user, A);
+        double *out[2 * FLGPU_MULTI_MAX];
+        for (int i = 0; i < 2 * FLGPU_MULTI_MAX; i++) out[i] = out_dev + i;
+        flgpu_reduce_tree(ctx->stream, nchunks, 2 * count, out);
+    }
     static void direction(const flgpu_eval_ctx *ctx, const flgpu_direction_args *A, int64_t) {
         if (A->k3_bytes != sizeof(flgpu::k::K3Launch)) {
             std::fprintf(stderr, "flgpu_obj: K3Launch layout mismatch (header and libflgpu.so versions differ)\n");
             std::abort();
         }
-        FunctorProbe<Obj> probe{*(const Obj *)ctx->user, ctx->offset, (A->flags & FLGPU_WANT_GP) ? 1 : 0};
+        FunctorProbe<Obj> probe{*(const Obj *)ctx->user, ctx->offset};
         flgpu::k::launch_k3_probe(*(const flgpu::k::K3Launch *)A->k3, probe);
     }
     static void f(const flgpu_eval_ctx *ctx, double *f_dev, const double *x, int64_t n) {
@@ -396,6 +477,7 @@ inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool wi
     p.search_caps = 0;                        // single GPU: row-sharded runs use the host-driven search
     p.update = with_fused ? Callbacks<Obj>::update : nullptr;
     p.direction = with_fused ? Callbacks<Obj>::direction : nullptr;
+    p.fused_multi = with_fused ? Callbacks<Obj>::fused_multi : nullptr;
     return p;
 }
 

@@ -22,6 +22,7 @@ capture() {   # name, kernel regex, skip, count
     rm -f gpurun_out/${TAG}_$1.ncu-rep
 }
 capture k1k3 'k1_update_dots|k3_direction' 24 2
-capture ls 'objective_kernel' 300 4
+capture multi 'objective_multi_kernel' 150 2     # batched probes (steady state: past the prologue's walks)
+capture ls 'objective_kernel' 12 2
 capture tree 'tree_kernel' 60 2
 ls -la gpurun_out/ | grep ${TAG}

@@ -19,7 +19,7 @@ PROF = os.path.join(ROOT, "profiles")
 
 def short(name):
     m = re.search(r"(k1_update_dots_kernel|k3_direction_tma_kernel|k3_direction_kernel|tree_kernel|search_kernel|k2_solve_kernel|trial_kernel|dot_kernel|neg_kernel|"
-                  r"cg_dots_kernel|cg_update_kernel|objective_kernel|start_kernel|combine_kernel|set_scalar_kernel)(<[^(]*>)?", name)
+                  r"cg_dots_kernel|cg_update_kernel|objective_multi_kernel|objective_kernel|start_kernel|combine_kernel|set_scalar_kernel)(<[^(]*>)?", name)
     if m:
         return m.group(1) + (m.group(2) or "")
     return name[:60]
@@ -120,4 +120,4 @@ if __name__ == "__main__":
     tag = sys.argv[1]
     if os.path.exists(os.path.join(OUT, f"{tag}_launches.csv")):
         launches(tag)
-    kernels(tag, sys.argv[2:] or ["k1k3", "ls", "tree"])
+    kernels(tag, sys.argv[2:] or ["k1k3", "multi", "ls", "tree"])

@@ -148,6 +148,11 @@ public:
         prob.fused(&ctx, flags, &slots[flgpu::SL_F], &slots[flgpu::SL_GP], x_out, g_out, x0, p, a, n);
         callback_launches++;
     }
+    bool fused_multi_available() const override { return prob.fused_multi != nullptr; }
+    void fused_eval_multi(int count, const double *steps, const double *x0, const double *p) override {
+        prob.fused_multi(&ctx, count, steps, &slots[flgpu::SL_AUX], x0, p, n);
+        callback_launches++;
+    }
     // "device-resident" search on the host: the same SearchCore the CUDA search kernels instantiate, with EAGER
     // evaluations (every call computes f / f'.p at once, as a cooperative kernel does) instead of the driver's lazy
     // ones -- so the driver's device-search branch and the eager evaluator semantics are testable without a GPU.
@@ -377,6 +382,13 @@ void obj_fused(const flgpu_eval_ctx *c, int flags, double *f, double *gp, double
     if (flags & FLGPU_WRITE_G) std::memcpy(g_out, g.data(), sizeof(double) * n);
 }
 
+// batched fused evaluation (flgpu_fused_multi_fn): by definition the values of `count` separate fused evaluations
+void obj_fused_multi(const flgpu_eval_ctx *c, int count, const double *steps, double *out, const double *x0,
+                     const double *p, int64_t n) {
+    for (int j = 0; j < count; j++)
+        obj_fused(c, FLGPU_WANT_F | FLGPU_WANT_GP, &out[2 * j], &out[2 * j + 1], nullptr, nullptr, x0, p, steps[j], n);
+}
+
 }  // namespace
 
 extern "C" {
@@ -394,6 +406,7 @@ void flgpu_hostsim_builtin_problem(int kind, flgpu_problem *out) {
     out->search_caps = 0;
     out->update = nullptr;
     out->direction = nullptr;
+    out->fused_multi = obj_fused_multi;
 }
 
 void flgpu_hostsim_options_default(flgpu_options *o, int for_cg) {

@@ -599,6 +599,75 @@ def test_fused_direction_is_the_same_algorithm(name, kw, n):
     assert on["it"] > 3
 
 
+@pytest.mark.parametrize("kind", ["quartic", "rosenR1", "diag", "quartic1"])
+@pytest.mark.parametrize("n", [1, 2, 777, 10_001, (1 << 22) + 3])
+def test_fused_multi_kernel_bitwise(fl, kind, n):
+    """flgpu_fused_multi_fn: f and f'.p at four steps from ONE pass over x0 and p carry exactly the bits of four separate
+    flgpu_fused_fn evaluations (same per-element roundings, same chunk sums, same tree); n = 2^22+3: full grid, grid-
+    stride wrap, odd tail; also with fewer than four steps."""
+    k, start, seed = _cases.OBJECTIVES[kind]
+    prob = fl.builtin_problem(k)
+    assert prob.fused_multi
+    MULTI_FN = C.CFUNCTYPE(None, C.POINTER(fl.capi.EvalCtx), C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
+                           C.c_void_p, C.c_int64)
+    x = fl.DeviceVector.start(start, n, seed=seed)
+    rng = np.random.default_rng(n)
+    p = fl.DeviceVector.from_numpy(rng.standard_normal(n) * 0.1)
+    ctx = fl.capi.EvalCtx(C.c_void_p(prob.user), None, 0, n, 0, 1, 0)
+    W = fl.capi
+    for steps in ([1.05, 1.05 * 1.05, 1.05 * 1.05 * 1.05, 1.2155062500000001], [0.3, -0.7], [1e-3, 0.0, 2.5]):
+        out = fl.DeviceVector(8)
+        arr = (C.c_double * len(steps))(*steps)
+        C.cast(prob.fused_multi, MULTI_FN)(C.byref(ctx), len(steps), arr, out.ptr, x.ptr, p.ptr, n)
+        got = out.numpy()
+        for j, a in enumerate(steps):
+            sc = fl.DeviceVector(2)
+            C.cast(prob.fused, W.FUSED_FN)(C.byref(ctx), W.WANT_F | W.WANT_GP, sc.ptr, sc.ptr + 8, None, None, x.ptr, p.ptr,
+                                           a, n)
+            one = sc.numpy()
+            assert got[2 * j] == one[0] and got[2 * j + 1] == one[1], (kind, n, j, got[2 * j:2 * j + 2], one)
+
+
+@pytest.mark.parametrize("algo,name,kw", [
+    ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=40)), ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=30, use_ffd=False)),
+    ("lbfgs", "rosenR1", dict(Memory=5, MaxIteration=30, Strong=False)), ("lbfgs", "diag", dict(Memory=30, MaxIteration=45)),
+    ("lbfgs", "quartic", dict(Memory=3)), ("cg", "quartic", dict(Method="DY")), ("cg", "quartic1", dict(Method="PR")),
+    ("cg", "rosenR1", dict(Method="DY", MaxIteration=40, Strong=False)), ("sd", "rosenR1", dict(MaxIteration=25)),
+    ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=30, Increment=2.0)),
+])
+@pytest.mark.parametrize("n", [10_001, 1 << 20, (1 << 22) + 3])
+def test_fused_multi_is_the_same_algorithm(algo, name, kw, n):
+    """Batched evaluation of a bracketing walk (flgpu_problem.fused_multi): the next four steps a, a*Increment, ... (or
+    a/Increment, ...) are evaluated in the pass that evaluates the first.  Every iterate, step, trial count and
+    evaluation count must be IDENTICAL with batching off (FLGPU_FUSED_MULTI=0: one probe launch per trial) -- only the
+    number of passes and of host round trips drops."""
+    kw = dict(kw)
+    use = kw.pop("use_ffd", True)
+    fn = {"lbfgs": "LBFGS", "cg": "ConjugateGradient", "sd": "SteepestDescent"}[algo]
+    code = ("import sys, json, hashlib; sys.path.insert(0, %r); sys.path.insert(0, %r)\nimport numpy as np, fortran_library_b200 as fl\n"
+            "kind, start, seed = %r\n"
+            "x = fl.DeviceVector.start(start, %d, seed=seed)\n"
+            "p = fl.builtin_problem(kind)\n"
+            "if not %r: p.f_fd = None\n"
+            "ob = fl.Observer()\n"
+            "st = fl.%s(p, x, Warning=False, observer=ob, device_search=False, **%r)\n"
+            "xn = x.numpy()\n"
+            "print(json.dumps(dict(rows=ob.rows, x=hashlib.sha256(xn.tobytes()).hexdigest(), n_f_fd=st.n_f_fd, n_f=st.n_f,\n"
+            "                 n_fd=st.n_fd, trials=st.n_trials, fonly=st.n_f_only_trials, it=st.iterations, status=st.status, f=st.f,\n"
+            "                 g2=st.gnorm2, syncs=st.host_syncs, batched=st.n_batched_passes)))\n"
+            % (ROOT, os.path.join(ROOT, "tests"), _cases.OBJECTIVES[name], n, use, fn, kw))
+    res = []
+    for env in ({}, {"FLGPU_FUSED_MULTI": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    on, off = res
+    assert on["rows"] == off["rows"] and on["x"] == off["x"]
+    for k in ("n_f_fd", "n_f", "n_fd", "trials", "fonly", "it", "status", "f", "g2"):
+        assert on[k] == off[k], k
+    assert off["batched"] == 0 and on["batched"] > 0 and on["syncs"] < off["syncs"], (on["batched"], on["syncs"], off["syncs"])
+
+
 # ----------------------------------------------------------------------------- GPU == scalar C++ statement, bit for bit
 @pytest.mark.parametrize("algo,name,kw", [
     ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=40)), ("lbfgs", "rosenR1", dict(Memory=10, MaxIteration=25, fused=False)),
