@@ -12,7 +12,7 @@ CMD="python bench.py --steps 4 --warmup 3 --no-cpu --no-secondary --e2e-steps 2"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }
 cut -c1-300 gpurun_out/${TAG}_plain.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_LAUNCHES:-3000} --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
 capture() {   # name, kernel regex, skip, count
     ncu --set full --clock-control none --import-source on -k regex:"$2" -s $3 -c $4 -f -o gpurun_out/${TAG}_$1 $CMD > gpurun_out/${TAG}_ncu_$1.log 2>&1
@@ -24,5 +24,5 @@ capture() {   # name, kernel regex, skip, count
 capture k1k3 'k1_update_dots|k3_direction' 24 2
 capture multi 'objective_multi_kernel' 150 2     # batched probes (steady state: past the prologue's walks)
 capture ls 'objective_kernel' 12 2
-capture tree 'tree_kernel' 60 2
+[ -z "${NCU_LIGHT:-}" ] && capture tree 'tree_kernel' 60 2
 ls -la gpurun_out/ | grep ${TAG}
