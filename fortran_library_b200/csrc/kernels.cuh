@@ -18,6 +18,7 @@
 
 #include "../../include/flgpu_k1.cuh"
 #include "../../include/flgpu_k3.cuh"
+#include "../../include/flgpu_exchange.cuh"
 #include "../../include/flgpu_reduce.cuh"
 #include "backend.hpp"
 
@@ -305,74 +306,7 @@ static __global__ void __launch_bounds__(32) k2_solve_kernel(int m, int k, int r
 // on all ranks, and the bits of the single-GPU tree when the shards are aligned subtrees (flgpu_reduce.cuh).
 // Mailboxes are double-buffered on the sequence parity: a peer can be at most one exchange ahead (it
 // needs this rank's flag of exchange seq+1 before it can start seq+2), so two buffers suffice.
-constexpr int kMailWidth = 320;       // doubles per rank slot: >= NSLOTS + nd_of(kMaxMem)
-constexpr int kMaxRanks = red::kMaxRanks;
-
-struct Mailbox {
-    double data[2][kMaxRanks][kMailWidth];
-    unsigned long long flag[2][kMaxRanks];
-    unsigned long long error;         // set to the offending sequence number on a wait timeout
-};
-
-struct PeerTable { Mailbox *box[kMaxRanks]; };
-
-// One IPC-shared allocation per rank: the mailbox of the host-driven exchanges (exchange_kernel), a second one for
-// the exchanges a device-resident line search performs on its own, and that search's sequence counter (the host
-// cannot know how many evaluations a search will make, so the counter lives on the device; every rank makes the
-// same evaluations, so the counters agree without communication).
-struct MailboxPair {
-    Mailbox host_driven;
-    Mailbox device_search;
-    unsigned long long dseq;
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-// Executed by ONE block: store vals[0..count) (count <= blockDim.x) into slot [me] of every rank's mailbox, publish
-// `seq`, wait for every rank's slot of this rank's mailbox, return the rank-tree sums in out[0..count).
-// timeout_ns: how long a peer may stay silent before this rank records the failure in its mailbox and traps.
-__device__ __forceinline__ void mailbox_exchange_block(const PeerTable &peers, int me, int G, unsigned long long seq,
-                                                       const double *vals, int count, double *out,
-                                                       unsigned long long timeout_ns) {
-    const int par = (int)(seq & 1ull), t = threadIdx.x;
-    if (t < count) {
-        const double v = vals[t];
-        for (int r = 0; r < G; r++) peers.box[r]->data[par][me][t] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (t < G) st_release_sys(&peers.box[t]->flag[par][me], seq);
-    Mailbox *mine = peers.box[me];
-    if (t < G) {
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(&mine->flag[par][t]) < seq) {
-            if (global_timer_ns() - t0 > timeout_ns) {
-                mine->error = seq;
-                __threadfence_system();
-                __trap();
-            }
-        }
-    }
-    __syncthreads();
-    if (t < count) {
-        double v[kMaxRanks];
-        for (int r = 0; r < G; r++) v[r] = __ldcv(&mine->data[par][r][t]);
-        out[t] = red::rank_tree(v, G);
-    }
-}
-
+// (Mailbox, PeerTable, mailbox_exchange_block: include/flgpu_exchange.cuh -- shared with include/flgpu_objective.cuh)
 
 // src: this rank's `count` values; out: their rank-tree sum (count <= kMailWidth); host_out (optional):
 // the same sums stored straight into pinned host memory followed by the flag word host_out[NSLOTS] = seq_host.

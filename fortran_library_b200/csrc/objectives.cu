@@ -842,6 +842,17 @@ static int ref_ffd(double *fx, double *fdx, const double *x, const int *dim) {
 
 using namespace flgpu;
 
+extern "C" int flgpu_comm_search_exchange(const flgpu_comm *c, void *stream, void *out, size_t out_bytes) {
+    if (out_bytes != sizeof(k::SearchExchange)) return 2;
+    if (!c || !c->p2p) return 1;
+    Scratch &sc = scratch_for((cudaStream_t)stream, 1);
+    k::SearchExchange E;
+    E.peers = c->peers_search; E.me = c->rank; E.G = c->nranks; E.dseq = &c->local->dseq; E.timeout_ns = c->timeout_ns;
+    E.glob = sc.work.blockvals + (size_t)(kScratchRows - 1) * red::kTopMax;   // the four doubles the built-in search uses
+    std::memcpy(out, &E, sizeof E);
+    return 0;
+}
+
 extern "C" int flgpu_builtin_problem(int kind, flgpu_problem *out) {
     out->user = nullptr;
     switch (kind) {

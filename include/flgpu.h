@@ -328,6 +328,11 @@ int flgpu_builtin_ref_constraints(int kind, flgpu_ref_c_fn *c, flgpu_ref_cd_fn *
 /* One process per GPU.  Rank 0 obtains a 128-byte id, the caller distributes it
  * (MPI / torch.distributed / file), every rank creates the communicator. */
 int flgpu_comm_unique_id(void *id128);
+/* For a device-resident line search written outside the library (include/flgpu_objective.cuh generates one): fills
+ * `out` (a flgpu::k::SearchExchange, include/flgpu_exchange.cuh; out_bytes = its size, checked) with what a kernel needs to
+ * trade partial sums with the other ranks INSIDE the kernel over the communicator's search mailboxes.  Returns 0; 1 if
+ * the communicator has no peer-memory exchange (NCCL fallback: use the host-driven search); 2 on a size mismatch. */
+int flgpu_comm_search_exchange(const flgpu_comm *c, void *stream, void *out, size_t out_bytes);
 flgpu_comm *flgpu_comm_create(const void *id128, int rank, int nranks);
 void flgpu_comm_destroy(flgpu_comm *c);
 /* 1 when the per-reduction exchange runs as one kernel over IPC-mapped peer memory (NVLink/NVSwitch

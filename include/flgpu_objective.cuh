@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 
 #include "flgpu.h"
+#include "flgpu_exchange.cuh"
 #include "flgpu_k1.cuh"
 #include "flgpu_k3.cuh"
 #include "flgpu_reduce.cuh"
@@ -177,12 +178,15 @@ __global__ void __launch_bounds__(kThreads, 3) objective_multi_kernel(Obj obj, M
 // one cooperative kernel.  Every thread runs the same SearchCore state machine (flgpu_search_core.hpp, the source the
 // host driver compiles) on the same values; an evaluation = this block's chunks + one grid barrier + the tree over the
 // chunk sums, repeated by every block.  Same chunk sums and tree as objective_kernel + flgpu_reduce_tree => same bits
-// as the host-driven fused search => same decisions.  Single GPU (row-sharded runs fall back to the host-driven search).
+// as the host-driven fused search => same decisions.  On row shards block 0 trades the rank's roots with the other ranks
+// inside the kernel (flgpu_exchange.cuh: stores into the peers' search mailboxes, flags, rank tree) and a second grid
+// barrier hands the sums to the other blocks -- as libflgpu's own search kernel does.
 struct SearchArgs {
     Args o;                                  // x = x0; x_out / g_out = accepted point / gradient; partials rows [2*parity + i]
     double c1, c2abs, fx0, phid0, incr, a0;
     int strong, fdwithf, store;
     double *result;
+    flgpu::k::SearchExchange ex;             // ex.G <= 1: single GPU
 };
 
 constexpr double kEvalBudget = 100000.0;
@@ -196,7 +200,10 @@ struct DevSearch : flgpu::SearchCore<DevSearch<Obj>> {
     bool have_x = false, have_g = false;
     int parity = 0, fpar = 0;
     double trials = 0.0, n_f = 0.0, n_fd = 0.0, n_ffd = 0.0, n_fonly = 0.0;
-    __device__ DevSearch(const Obj &o, const SearchArgs &k, double *s) : obj(o), K(k), rsh(s) {}
+    unsigned long long seq_base = 0, nexch = 0;   // exchanges made so far (uniform over the grid)
+    __device__ DevSearch(const Obj &o, const SearchArgs &k, double *s) : obj(o), K(k), rsh(s) {
+        if (K.ex.G > 1) seq_base = *K.ex.dseq;
+    }
     template <bool F, bool GP>
     __device__ void eval() {
         constexpr int NACC = (F && GP) ? 2 : 1;
@@ -223,8 +230,25 @@ struct DevSearch : flgpu::SearchCore<DevSearch<Obj>> {
             v[i] = red::cta_root(rows + (int64_t)i * o.stride, nchunks, rsh);
             __syncthreads();
         }
-        if (F) f_cur = v[0];
-        if (GP) gp_cur = v[NACC - 1];
+        if (K.ex.G > 1) {
+            nexch++;
+            double *gl = K.ex.glob + parity * 2;
+            if (blockIdx.x == 0) {
+                __shared__ double mine[2], summed[2];
+                if (threadIdx.x < NACC) mine[threadIdx.x] = v[threadIdx.x];
+                __syncthreads();
+                flgpu::k::mailbox_exchange_block(K.ex.peers, K.ex.me, K.ex.G, seq_base + nexch, mine, NACC, summed,
+                                                 K.ex.timeout_ns);
+                if (threadIdx.x < NACC) gl[threadIdx.x] = summed[threadIdx.x];
+                __threadfence();
+            }
+            cooperative_groups::this_grid().sync();
+            if (F) f_cur = __ldcg(&gl[0]);
+            if (GP) gp_cur = __ldcg(&gl[NACC - 1]);
+        } else {
+            if (F) f_cur = v[0];
+            if (GP) gp_cur = v[NACC - 1];
+        }
         parity ^= 1;
     }
     __device__ void form(double step) { a_x = step; have_x = true; trials += 1.0; }
@@ -267,7 +291,8 @@ __global__ void __launch_bounds__(kThreads, 3) search_kernel(Obj obj, SearchArgs
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         K.result[0] = S.a; K.result[1] = S.f_cur; K.result[2] = S.trials; K.result[3] = S.n_f;
         K.result[4] = S.n_fd; K.result[5] = S.n_ffd; K.result[6] = S.n_fonly;
-        K.result[7] = S.aborted() ? -1.0 : 0.0;
+        K.result[7] = S.aborted() ? -1.0 : (double)S.nexch;
+        if (K.ex.G > 1) *K.ex.dseq = S.seq_base + S.nexch;
     }
 }
 
@@ -382,8 +407,12 @@ struct Callbacks {
     }
     template <bool FAST>
     static void search_policy(const flgpu_eval_ctx *ctx, const flgpu_search_args *A, int64_t n) {
-        if (A->comm) { std::fprintf(stderr, "flgpu_obj: the header's device-resident search is single-GPU\n"); std::abort(); }
         SearchArgs K;
+        K.ex.G = 1; K.ex.me = 0; K.ex.dseq = nullptr; K.ex.glob = nullptr; K.ex.timeout_ns = 0;
+        if (A->comm && flgpu_comm_search_exchange(A->comm, ctx->stream, &K.ex, sizeof K.ex) != 0) {
+            std::fprintf(stderr, "flgpu_obj: the device-resident search on row shards needs the peer-memory exchange\n");
+            std::abort();
+        }
         int64_t nchunks = 1;
         geometry(ctx, n, K.o, nchunks);
         K.o.x = A->x0_dev; K.o.p = A->p_dev; K.o.a = 0.0; K.o.x_out = A->x_out; K.o.g_out = A->g_out;
@@ -474,7 +503,7 @@ inline flgpu_problem make_problem(const Obj *obj, bool with_f_fd = true, bool wi
     p.user = (void *)obj;
     p.fused = with_fused ? Callbacks<Obj>::fused : nullptr;
     p.search = (with_fused && with_search) ? Callbacks<Obj>::search : nullptr;
-    p.search_caps = 0;                        // single GPU: row-sharded runs use the host-driven search
+    p.search_caps = FLGPU_SEARCH_ROW_SHARDS;  // the search kernel trades its sums with the other ranks itself
     p.update = with_fused ? Callbacks<Obj>::update : nullptr;
     p.direction = with_fused ? Callbacks<Obj>::direction : nullptr;
     p.fused_multi = with_fused ? Callbacks<Obj>::fused_multi : nullptr;

@@ -130,6 +130,46 @@ def main():
             ok = ok and good
             x1.free()
         x.free()
+    # a USER objective written with include/flgpu_objective.cuh (tests/link/user_objective.cu, compiled by the caller):
+    # its device-resident search trades the partial sums inside the kernel (flgpu_comm_search_exchange) and must give
+    # the bits of the host-driven search on the same shards and of the single-GPU run
+    if len(sys.argv) > 2 and p2p:
+        ulib = C.CDLL(sys.argv[2])
+        nu = 1 << 16
+        lo_u, hi_u = nu * rank // world, nu * (rank + 1) // world
+        x0u = np.random.default_rng(99).uniform(-0.5, 1.5, nu)
+        for which in (0, 1):
+            uprob = fl.capi.Problem()
+            ulib.user_problem(which, C.byref(uprob))
+            res = []
+            for ds in (True, False):
+                xu = fl.DeviceVector.from_numpy(x0u[lo_u:hi_u])
+                obu = fl.Observer()
+                stu = fl.LBFGS(uprob, xu, Memory=6, Warning=False, MaxIteration=60, observer=obu, comm=comm, offset=lo_u,
+                               n_global=nu, device_search=ds)
+                res.append((xu.numpy(), obu.rows, stu.iterations, stu.n_trials, stu.host_syncs))
+                xu.free()
+            same_modes = bool(np.array_equal(res[0][0], res[1][0])) and res[0][1:4] == res[1][1:4] and res[0][4] < res[1][4]
+            t = torch.from_numpy(res[0][0]).cuda()
+            parts = []
+            for r in range(world):
+                buf = t if r == rank else torch.empty(nu * (r + 1) // world - nu * r // world, dtype=torch.float64, device="cuda")
+                dist.broadcast(buf, r)
+                parts.append(buf.clone())
+            xg = torch.cat(parts).cpu().numpy()
+            flag = torch.tensor([int(same_modes)], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            same_modes = bool(flag.item())
+            if rank == 0:
+                x1 = fl.DeviceVector.from_numpy(x0u)
+                ob1 = fl.Observer()
+                st1 = fl.LBFGS(uprob, x1, Memory=6, Warning=False, MaxIteration=60, observer=ob1, device_search=False)
+                bitwise = bool(np.array_equal(xg, x1.numpy())) and ob1.rows == res[0][1] and st1.iterations == res[0][2]
+                good = same_modes and bitwise
+                print(f"[{world} ranks] user functor {which}: in-kernel exchange == host-driven: {same_modes}, "
+                      f"bitwise == 1 GPU: {bitwise}, round trips {res[0][4]} vs {res[1][4]} -> {'OK' if good else 'FAIL'}", flush=True)
+                ok = ok and good
+                x1.free()
     # the two-loop operator (flgpu_history_*) on row shards: K1's dots are rank-summed before K2
     nh = 1 << 14
     lo_h, hi_h = nh * rank // world, nh * (rank + 1) // world

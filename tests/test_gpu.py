@@ -954,7 +954,7 @@ def test_cpp_dropin_program_runs(fl, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-def test_row_sharded_nccl(fl):
+def test_row_sharded_nccl(fl, user_objective_lib):
     """Row-sharded over every visible GPU (one process per GPU, NCCL exchange) against the 1-GPU run.
     Needs >= 2 GPUs; the round-end single-GPU run skips it (the CPU suite covers the same host logic with
     gloo at world_size 2: tests/test_hostsim.py::test_row_sharded_two_ranks_gloo)."""
@@ -963,8 +963,11 @@ def test_row_sharded_nccl(fl):
         pytest.skip("needs >= 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(ngpu, 8)}",
                         "--master-addr", "127.0.0.1", "--master-port", "29512",
-                        os.path.join(ROOT, "tests", "gpu_multi.py"), "20"], capture_output=True, text=True, timeout=900)
+                        os.path.join(ROOT, "tests", "gpu_multi.py"), "20", user_objective_lib._name],
+                       capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    if "peer-memory exchange: yes" in r.stdout:
+        assert "user functor 1" in r.stdout, r.stdout[-3000:]
 
 
 def test_fortran_abi_device_x_and_stream_sync_mode(fl):

@@ -132,6 +132,21 @@ def test_fused_line_search_is_the_same_algorithm(lbfgs, name, kw):
     assert all(np.array_equal(u, v) for u, v in zip(oa.g, ob_.g))
     for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
         assert getattr(sa, k) == getattr(sb, k), k
+    # the fused run above batched the trials of every bracketing walk four to a pass (flgpu_fused_multi_fn; here a batch
+    # is by definition four separate evaluations).  With batching off: the same everything, more passes and round trips.
+    import os
+    os.environ["FLGPU_FUSED_MULTI"] = "0"
+    try:
+        od = H.Observer(max_vec_iters=10**9)
+        xd, sd_ = run(kind, _cases.start(name, n), observer=od, Warning=False, n_global=n, fused=True, device_search=False, **kw)
+    finally:
+        del os.environ["FLGPU_FUSED_MULTI"]
+    assert np.array_equal(xa, xd) and oa.rows == od.rows
+    assert all(np.array_equal(u, v) for u, v in zip(oa.p, od.p))
+    for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
+        assert getattr(sa, k) == getattr(sd_, k), ("unbatched", k)
+    assert sd_.n_batched_passes == 0 and sa.n_batched_passes > 0
+    assert sa.host_syncs < sd_.host_syncs and 2 * sa.n_batched_passes < sa.n_trials
 
 
 def _py_problem(fuse):
