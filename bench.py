@@ -597,6 +597,12 @@ def run_ours(args):
                             "ON (one cooperative kernel per line search, flgpu_search_fn)" if ds_active else
                             "off at this size (host-driven, one round trip per trial)")),
                         "trials_in_timed_region": trials, "trials_per_iteration": trials / K,
+                        "bytes_note": ("fused mode: every trial of the reference is evaluated (same points, same values), but up "
+                                       "to four share one 2n-double pass over x0 and p and the first four of a search ride on "
+                                       "K3, so the step moves (4m+7+2P)n doubles with P = probe passes per iteration -- NOT "
+                                       "(4m+6)n + 2n per trial; charging 2n per trial would put this line above the HBM peak. "
+                                       "`roofline.whole_step` and `hbm_GBps_whole_step` count the bytes of the passes actually "
+                                       "made; `roofline.traffic` / profiles/r02m_kernels.md hold ncu's DRAM counters") if fused else None,
                         "objective_kernel_launches_per_iteration": (mark["c1"][1] - mark["c0"][1]) / K,
                         "batching": "the trials of a bracketing walk (a, a*Increment, ...) share one pass over x0 and p, four "
                                     "at a time; K3 evaluates the first four of every search (flgpu_fused_multi_fn, "
