@@ -314,6 +314,19 @@ public:
         slots[flgpu::SL_GP0] = out[0];
         slots[flgpu::SL_PP] = out[1];
     }
+    // K3 with the first trials of the next search (flgpu_problem.direction on the GPU): by definition the direction
+    // followed by separate fused evaluations at x1 + steps[j]*p -- what the CUDA kernel must reproduce bit for bit
+    bool fused_direction_available() const override { return prob.fused != nullptr; }
+    void lbfgs_direction_probe(double *p, const double *g1, const double *x1, int k, int recent, int /*flags*/,
+                               const double *steps) override {
+        lbfgs_direction(p, nullptr, g1, x1, k, recent);
+        for (int j = 0; j < FLGPU_MULTI_MAX; j++) {
+            double *f = j == 0 ? &slots[flgpu::SL_F] : &slots[flgpu::SL_AUX + 2 * j];
+            double *gp = j == 0 ? &slots[flgpu::SL_GP] : &slots[flgpu::SL_AUX + 2 * j + 1];
+            prob.fused(&ctx, FLGPU_WANT_F | FLGPU_WANT_GP, f, gp, nullptr, nullptr, x1, p, steps[j], n);
+        }
+        callback_launches++;
+    }
 
     void cg_dots(const double *g1, const double *g0, const double *p) override {
         launches++;
