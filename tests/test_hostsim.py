@@ -147,6 +147,19 @@ def test_fused_line_search_is_the_same_algorithm(lbfgs, name, kw):
         assert getattr(sa, k) == getattr(sd_, k), ("unbatched", k)
     assert sd_.n_batched_passes == 0 and sa.n_batched_passes > 0
     assert sa.host_syncs < sd_.host_syncs and 2 * sa.n_batched_passes < sa.n_trials
+    # L-BFGS: the first four trials of every search after the first ride on K3 (flgpu_problem.direction; here: the direction
+    # followed by four separate evaluations) and seed the search's first batch.  Without it: the same, more batches.
+    if lbfgs is True:
+        os.environ["FLGPU_FUSED_DIRECTION"] = "0"
+        try:
+            oe = H.Observer(max_vec_iters=10**9)
+            xe, se = run(kind, _cases.start(name, n), observer=oe, Warning=False, n_global=n, fused=True, device_search=False, **kw)
+        finally:
+            del os.environ["FLGPU_FUSED_DIRECTION"]
+        assert np.array_equal(xa, xe) and oa.rows == oe.rows
+        for k in ("iterations", "status", "n_f", "n_fd", "n_f_fd", "n_trials", "n_f_only_trials", "n_linesearch"):
+            assert getattr(sa, k) == getattr(se, k), ("no K3 probe", k)
+        assert sa.n_batched_passes <= se.n_batched_passes
 
 
 def _py_problem(fuse):
